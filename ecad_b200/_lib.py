@@ -1,0 +1,222 @@
+"""ctypes binding of libecad_b200.so (C ABI: include/ecad_b200.h).
+
+The product path has NO fallback: if the shared library is missing or the device is not sm_100 the calls raise.
+PyTorch is used only for device memory and the stream handle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import torch
+
+_LIB_PATH = Path(__file__).resolve().parent / "libecad_b200.so"
+MAX_REUSE = 6
+HEAD_DIM = 72
+HEAD_PAD = 80
+
+EXPORTED_SYMBOLS = [
+    "ecadk_abi_version",
+    "ecadk_last_error",
+    "ecadk_device_check",
+    "ecadk_residual_ln",
+    "ecadk_patch_embed",
+    "ecadk_timestep_sinusoid",
+    "ecadk_small_linear",
+    "ecadk_cast_f32_bf16",
+    "ecadk_mask_bias",
+    "ecadk_final_layer",
+    "ecadk_cfg_dpm_step",
+    "ecadk_gemm_bias",
+    "ecadk_gemm_bias_gated_residual_cache",
+    "ecadk_gemm_bias_headmajor",
+    "ecadk_attention",
+    "ecadk_create",
+    "ecadk_destroy",
+    "ecadk_pixart_blocks",
+    "ecadk_pixart_text_kv",
+]
+
+
+class EcadkReuse(C.Structure):
+    _fields_ = [("cache", C.c_void_p), ("gate_table", C.c_void_p), ("gate_temb", C.c_void_p)]
+
+
+class EcadkResidualLnArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p),
+        ("xb", C.c_void_p),
+        ("h", C.c_void_p),
+        ("rows", C.c_int),
+        ("tokens", C.c_int),
+        ("dim", C.c_int),
+        ("n_reuse", C.c_int),
+        ("reuse", EcadkReuse * MAX_REUSE),
+        ("shift_table", C.c_void_p),
+        ("scale_table", C.c_void_p),
+        ("shift_temb", C.c_void_p),
+        ("scale_temb", C.c_void_p),
+        ("temb_stride", C.c_int),
+        ("eps", C.c_float),
+    ]
+
+
+class EcadkModelDesc(C.Structure):
+    _fields_ = [
+        ("num_layers", C.c_int),
+        ("dim", C.c_int),
+        ("heads", C.c_int),
+        ("ff_dim", C.c_int),
+        ("norm_eps", C.c_float),
+    ]
+
+
+class EcadkBlockWeights(C.Structure):
+    _fields_ = [
+        (n, C.c_void_p)
+        for n in (
+            "w_qkv1", "b_qkv1", "w_out1", "b_out1", "w_q2", "b_q2", "w_kv2", "b_kv2", "w_out2", "b_out2",
+            "w_ff1", "b_ff1", "w_ff2", "b_ff2", "scale_shift_table",
+        )
+    ]
+
+
+class EcadkBlocksArgs(C.Structure):
+    _fields_ = [
+        ("samples", C.c_int),
+        ("tokens", C.c_int),
+        ("text_pad", C.c_int),
+        ("x", C.c_void_p),
+        ("xb", C.c_void_p),
+        ("h", C.c_void_p),
+        ("q", C.c_void_p),
+        ("k", C.c_void_p),
+        ("v", C.c_void_p),
+        ("attn_o", C.c_void_p),
+        ("ffh", C.c_void_p),
+        ("temb6", C.c_void_p),
+        ("text_bias", C.c_void_p),
+        ("k2", C.POINTER(C.c_void_p)),
+        ("v2", C.POINTER(C.c_void_p)),
+        ("cache", C.POINTER(C.c_void_p)),
+    ]
+
+
+_lib = None
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree library; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise RuntimeError(
+            f"{_LIB_PATH} is missing - build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU or PyTorch fallback for the ECAD B200 hot path)"
+        )
+    lib = C.CDLL(os.fspath(_LIB_PATH))
+    lib.ecadk_abi_version.restype = C.c_int
+    lib.ecadk_last_error.restype = C.c_char_p
+    i, f, p, sz = C.c_int, C.c_float, C.c_void_p, C.c_size_t
+    sigs = {
+        "ecadk_device_check": [i],
+        "ecadk_residual_ln": [C.POINTER(EcadkResidualLnArgs), p],
+        "ecadk_patch_embed": [p, p, p, p, p, i, i, i, i, i, p],
+        "ecadk_timestep_sinusoid": [p, p, i, i, p],
+        "ecadk_small_linear": [p, p, p, p, i, i, i, i, i, i, i, p],
+        "ecadk_cast_f32_bf16": [p, p, sz, p],
+        "ecadk_mask_bias": [p, p, i, i, i, p],
+        "ecadk_final_layer": [p, p, p, p, p, p, i, i, i, i, i, f, p],
+        "ecadk_cfg_dpm_step": [p, p, p, i, i, i, i, f, f, f, f, f, f, p],
+        "ecadk_gemm_bias": [p, p, p, p, i, i, i, i, i, p],
+        "ecadk_gemm_bias_gated_residual_cache": [p, p, p, p, p, p, p, p, i, i, i, i, i, p],
+        "ecadk_gemm_bias_headmajor": [p, p, p, p, p, p, i, i, i, i, i, i, p],
+        "ecadk_attention": [p, p, p, p, p, i, i, i, i, p],
+        "ecadk_create": [i, C.POINTER(EcadkModelDesc), C.POINTER(EcadkBlockWeights), C.POINTER(p)],
+        "ecadk_destroy": [p],
+        "ecadk_pixart_blocks": [p, C.POINTER(EcadkBlocksArgs), C.POINTER(C.c_uint8), C.POINTER(i), p],
+        "ecadk_pixart_text_kv": [p, p, i, i, i, C.POINTER(p), C.POINTER(p), C.POINTER(i), p],
+    }
+    for name, argtypes in sigs.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    if lib.ecadk_abi_version() != 1:
+        raise RuntimeError(f"libecad_b200.so ABI version {lib.ecadk_abi_version()} != 1")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().ecadk_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"libecad_b200 {what} failed (code {rc}): {msg}")
+
+
+def ptr(t: torch.Tensor | None) -> int | None:
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+# ---------------------------------------------------------------------------------------------------
+# thin tensor-level wrappers (shape checking happens in C; these only pass pointers)
+# ---------------------------------------------------------------------------------------------------
+def gemm_bias(a, w, bias, out, gelu=False):
+    m, k = a.shape
+    n = w.shape[0]
+    check(load().ecadk_gemm_bias(ptr(a), ptr(w), ptr(bias), ptr(out), m, n, k, out.stride(0), int(gelu), stream_ptr()),
+          "gemm_bias")
+    return out
+
+
+def gemm_gated_residual(a, w, bias, x, cache, tokens, xb=None, gate_table=None, gate_temb=None, temb_stride=0):
+    m, k = a.shape
+    n = w.shape[0]
+    check(
+        load().ecadk_gemm_bias_gated_residual_cache(
+            ptr(a), ptr(w), ptr(bias), ptr(x), ptr(xb), ptr(cache), ptr(gate_table), ptr(gate_temb), temb_stride,
+            tokens, m, n, k, stream_ptr()),
+        "gemm_bias_gated_residual_cache")
+
+
+def gemm_headmajor(a, w, bias, outs, heads, tokens, tokens_pad):
+    m, k = a.shape
+    o = list(outs) + [None] * (3 - len(outs))
+    check(
+        load().ecadk_gemm_bias_headmajor(ptr(a), ptr(w), ptr(bias), ptr(o[0]), ptr(o[1]), ptr(o[2]), len(outs), heads,
+                                         tokens, tokens_pad, m, k, stream_ptr()),
+        "gemm_bias_headmajor")
+
+
+def attention(q, k, v, bias, out, samples, heads, q_tokens, n_keys):
+    check(load().ecadk_attention(ptr(q), ptr(k), ptr(v), ptr(bias), ptr(out), samples, heads, q_tokens, n_keys,
+                                 stream_ptr()), "attention")
+    return out
+
+
+def residual_ln(x, tokens, reuse=(), xb=None, h=None, shift_table=None, scale_table=None, shift_temb=None,
+                scale_temb=None, temb_stride=0, eps=1e-6):
+    """reuse: iterable of (cache, gate_table|None, gate_temb|None) tensors."""
+    a = EcadkResidualLnArgs()
+    a.x, a.xb, a.h = ptr(x), ptr(xb), ptr(h)
+    a.rows, a.dim = x.shape[0], x.shape[1]
+    a.tokens = tokens
+    reuse = list(reuse)
+    a.n_reuse = len(reuse)
+    for j, (c, gt, ge) in enumerate(reuse):
+        a.reuse[j].cache, a.reuse[j].gate_table, a.reuse[j].gate_temb = ptr(c), ptr(gt), ptr(ge)
+    a.shift_table, a.scale_table = ptr(shift_table), ptr(scale_table)
+    a.shift_temb, a.scale_temb = ptr(shift_temb), ptr(scale_temb)
+    a.temb_stride, a.eps = temb_stride, eps
+    check(load().ecadk_residual_ln(C.byref(a), stream_ptr()), "residual_ln")

@@ -1,0 +1,241 @@
+// Single-pass tcgen05 attention tile for short key sequences (NK <= 256 keys: PixArt 256x256 self-attention,
+// N = 256, and cross-attention against T5 tokens padded to 128).  One CTA = 128 queries x NK keys of one
+// (sample, head); the whole score row lives in TMEM, so there is no online-softmax rescaling:
+//
+//   TMA   : Q[128 x 80], K[NK x 80], V[NK x 80] tiles (head_dim 72 zero-padded to 80 = one 64-wide
+//           128B-swizzled chunk + one 16-wide 32B-swizzled chunk)
+//   MMA 1 : S[128 x NK]  = Q K^T            (tcgen05, fp32 in TMEM, 5 K-steps of 16)
+//   warps : softmax over the TMEM row (scale, additive key bias, exp2), P -> bf16 -> smem (K-major, SW128)
+//   MMA 2 : O[128 x 80]  = P V              (V consumed MN-major straight from its [key, d] TMA tile)
+//   warps : O / rowsum -> bf16 -> [sample, token, head*72 + e]
+//
+// Two CTAs fit per SM (104 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the other's TMA/MMA.
+#pragma once
+#include <cuda.h>
+
+#include "ptx.cuh"
+
+namespace ecadk {
+
+constexpr int kHeadDim = 72;
+constexpr int kHeadPad = 80;
+constexpr int kAttnBM = 128;
+constexpr int kAttnThreads = 160;
+
+struct AttnParams {
+  int heads;
+  int q_tokens;       // queries per (sample, head) in the Q layout (multiple of 128)
+  int out_ld;         // row pitch of the output in elements (= heads * 72)
+  float scale_log2e;  // (1/sqrt(d)) * log2(e)
+  const float* bias;  // [samples, NK] additive key bias in natural-log units (0 / -10000 / -inf), or null
+  __nv_bfloat16* out;  // [samples, q_tokens, out_ld]
+};
+
+template <int NK>
+struct AttnCfg {
+  // shared-memory map (bytes); every chunk base is a multiple of 1024
+  static constexpr int kQ64 = 0;                         // 128 rows x 128 B  (SW128)
+  static constexpr int kQ16 = kQ64 + kAttnBM * 128;      // 128 rows x  32 B  (SW32)
+  static constexpr int kK64 = kQ16 + kAttnBM * 32;       // NK rows x 128 B
+  static constexpr int kK16 = kK64 + NK * 128;           // NK rows x 32 B
+  static constexpr int kQKEnd = kK16 + NK * 32;
+  static constexpr int kPBytes = kAttnBM * NK * 2;       // P aliases Q/K once S is complete
+  static constexpr int kV64 = (kQKEnd > kPBytes ? kQKEnd : kPBytes);
+  static constexpr int kV16 = kV64 + NK * 128;
+  static constexpr int kBars = kV16 + NK * 32;
+  static constexpr int kSmemBytes = kBars + 64 + 1024;
+  static constexpr int kTmemCols = NK < 128 ? 128 : NK;  // S needs NK fp32 columns; O reuses columns [0,80)
+  static constexpr uint32_t kBytesQK = (kAttnBM + NK) * kHeadPad * 2;
+  static constexpr uint32_t kBytesV = NK * kHeadPad * 2;
+};
+
+template <int NK, bool HAS_BIAS>
+__global__ void __launch_bounds__(kAttnThreads, 2)
+attn_tile_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_constant__ CUtensorMap tm_q16,
+                 const __grid_constant__ CUtensorMap tm_k64, const __grid_constant__ CUtensorMap tm_k16,
+                 const __grid_constant__ CUtensorMap tm_v64, const __grid_constant__ CUtensorMap tm_v16,
+                 const AttnParams p) {
+  using Cfg = AttnCfg<NK>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar_qk = reinterpret_cast<uint64_t*>(smem + Cfg::kBars);
+  uint64_t* bar_v = bar_qk + 1;
+  uint64_t* bar_s = bar_qk + 2;
+  uint64_t* bar_p = bar_qk + 3;
+  uint64_t* bar_o = bar_qk + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_qk + 5);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q_tile = blockIdx.x;
+  const int sh = blockIdx.y;  // sample * heads + head
+  const int sample = sh / p.heads;
+  const int head = sh - sample * p.heads;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_qk, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 4);
+    mbar_init(bar_o, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ---- TMA: Q + K on one barrier, V on another so S = QK^T can start before V lands
+      const int q_row = sh * p.q_tokens + q_tile * kAttnBM;
+      const int k_row = sh * NK;
+      mbar_arrive_expect_tx(bar_qk, Cfg::kBytesQK);
+      tma_load_2d(smem + Cfg::kQ64, &tm_q64, bar_qk, 0, q_row);
+      tma_load_2d(smem + Cfg::kQ16, &tm_q16, bar_qk, 64, q_row);
+      tma_load_2d(smem + Cfg::kK64, &tm_k64, bar_qk, 0, k_row);
+      tma_load_2d(smem + Cfg::kK16, &tm_k16, bar_qk, 64, k_row);
+      mbar_arrive_expect_tx(bar_v, Cfg::kBytesV);
+      tma_load_2d(smem + Cfg::kV64, &tm_v64, bar_v, 0, k_row);
+      tma_load_2d(smem + Cfg::kV16, &tm_v16, bar_v, 64, k_row);
+
+      // ---- MMA 1: S = Q K^T  (both operands K-major; K extent 80 = 4 x 16 (SW128) + 1 x 16 (SW32))
+      mbar_wait(bar_qk, 0);
+      tc_fence_after();
+      {
+        constexpr uint32_t idesc = make_idesc_bf16(kAttnBM, NK);
+        const uint32_t sbase = smem_u32(smem);
+        const uint64_t dq = make_smem_desc(sbase + Cfg::kQ64, 0, 1024, kLayoutSW128);
+        const uint64_t dk = make_smem_desc(sbase + Cfg::kK64, 0, 1024, kLayoutSW128);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem, dq + 2 * k, dk + 2 * k, idesc, k != 0);
+        const uint64_t dq2 = make_smem_desc(sbase + Cfg::kQ16, 16, 256, kLayoutSW32);
+        const uint64_t dk2 = make_smem_desc(sbase + Cfg::kK16, 16, 256, kLayoutSW32);
+        umma_bf16_ss(tmem, dq2, dk2, idesc, 1);
+        umma_commit(bar_s);
+      }
+
+      // ---- MMA 2: O = P V  (A = P K-major SW128 in 64-key chunks; B = V MN-major, N = 64 + 16)
+      mbar_wait(bar_v, 0);
+      mbar_wait(bar_p, 0);
+      tc_fence_after();
+      {
+        constexpr uint32_t idesc64 = make_idesc_bf16(kAttnBM, 64, 0, 1);
+        constexpr uint32_t idesc16 = make_idesc_bf16(kAttnBM, 16, 0, 1);
+        const uint32_t sbase = smem_u32(smem);
+#pragma unroll
+        for (int ks = 0; ks < NK / 16; ++ks) {
+          const int chunk = ks >> 2, kin = ks & 3;
+          const uint64_t dp =
+              make_smem_desc(sbase + chunk * (kAttnBM * 128) + kin * 32, 0, 1024, kLayoutSW128);
+          // V tile rows are keys: 16 keys per K-step = 16 rows of 128 B (SW128 part) / 32 B (SW32 part)
+          const uint64_t dv64 = make_smem_desc(sbase + Cfg::kV64 + ks * 16 * 128, NK * 128, 1024, kLayoutSW128);
+          const uint64_t dv16 = make_smem_desc(sbase + Cfg::kV16 + ks * 16 * 32, NK * 32, 256, kLayoutSW32);
+          umma_bf16_ss(tmem, dp, dv64, idesc64, ks != 0);
+          umma_bf16_ss(tmem + 64, dp, dv16, idesc16, ks != 0);
+        }
+        umma_commit(bar_o);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---- softmax + epilogue warps: thread = one query row = one TMEM lane
+    const int row = warp * 32 + lane;
+    const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    const float* bias = HAS_BIAS ? p.bias + static_cast<size_t>(sample) * NK : nullptr;
+    constexpr float kLog2e = 1.4426950408889634f;
+
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < NK / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(t_row + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float t = __uint_as_float(v[j]) * p.scale_log2e;
+        if constexpr (HAS_BIAS) t += __ldg(bias + c * 32 + j) * kLog2e;
+        mx = fmaxf(mx, t);
+      }
+    }
+    float sum = 0.f;
+    uint8_t* prow = smem + row * 128;
+#pragma unroll 1
+    for (int c = 0; c < NK / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(t_row + c * 32, v);
+      tmem_ld_wait();
+      float e[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float t = __uint_as_float(v[j]) * p.scale_log2e;
+        if constexpr (HAS_BIAS) t += __ldg(bias + c * 32 + j) * kLog2e;
+        e[j] = exp2f(t - mx);
+        sum += e[j];
+      }
+      // keys [c*32, c*32+32) live in 64-key chunk (c>>1), 16-byte groups g0..g0+3 of the 128-byte row
+      uint8_t* pchunk = prow + (c >> 1) * (kAttnBM * 128);
+      const int g0 = (c & 1) * 4;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 o;
+        o.x = pack_bf16x2(e[g * 8 + 0], e[g * 8 + 1]);
+        o.y = pack_bf16x2(e[g * 8 + 2], e[g * 8 + 3]);
+        o.z = pack_bf16x2(e[g * 8 + 4], e[g * 8 + 5]);
+        o.w = pack_bf16x2(e[g * 8 + 6], e[g * 8 + 7]);
+        *reinterpret_cast<uint4*>(pchunk + (((g0 + g) ^ (row & 7)) << 4)) = o;
+      }
+    }
+    fence_proxy_async_smem();  // generic-proxy P writes -> visible to the tensor core (async proxy)
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_p);
+
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    const float inv = 1.0f / sum;
+    const int q = q_tile * kAttnBM + row;
+    __nv_bfloat16* dst = p.out + (static_cast<size_t>(sample) * p.q_tokens + q) * p.out_ld + head * kHeadDim;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(t_row + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]) * inv, __uint_as_float(v[g * 8 + 1]) * inv);
+        o.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]) * inv, __uint_as_float(v[g * 8 + 3]) * inv);
+        o.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]) * inv, __uint_as_float(v[g * 8 + 5]) * inv);
+        o.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]) * inv, __uint_as_float(v[g * 8 + 7]) * inv);
+        *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = o;
+      }
+    }
+    {
+      uint32_t v[16];
+      tmem_ld_32x16(t_row + 64, v);  // columns 64..79; 72..79 are padding
+      tmem_ld_wait();
+      uint4 o;
+      o.x = pack_bf16x2(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
+      o.y = pack_bf16x2(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
+      o.z = pack_bf16x2(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
+      o.w = pack_bf16x2(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
+      *reinterpret_cast<uint4*>(dst + 64) = o;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem, Cfg::kTmemCols);
+  }
+}
+
+}  // namespace ecadk

@@ -1,0 +1,591 @@
+// C ABI of libecad_b200.so (see include/ecad_b200.h).  Host-side launch logic only; kernels live in the .cuh files.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/ecad_b200.h"
+#include "attn.cuh"
+#include "gemm.cuh"
+#include "glue.cuh"
+
+namespace {
+
+using namespace ecadk;
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define ECADK_CHECK_CUDA(expr)                                                                   \
+  do {                                                                                           \
+    cudaError_t err__ = (expr);                                                                  \
+    if (err__ != cudaSuccess) return fail(ECADK_ECUDA, "%s: %s", #expr, cudaGetErrorString(err__)); \
+  } while (0)
+
+#define ECADK_REQUIRE(cond, ...)                        \
+  do {                                                  \
+    if (!(cond)) return fail(ECADK_EINVAL, __VA_ARGS__); \
+  } while (0)
+
+int check_launch(const char* what) {
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(ECADK_ECUDA, "%s launch failed: %s", what, cudaGetErrorString(err));
+  return ECADK_OK;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ---------------------------------------------------------------------------------------------------
+// TMA descriptors.  cuTensorMapEncodeTiled is fetched through the runtime so the library has no link-time
+// dependency on libcuda (it must load - and export its symbols - on a CPU-only box).
+// ---------------------------------------------------------------------------------------------------
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode_fn() {
+  static EncodeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeFn>(ptr);
+    }
+  });
+  return fn;
+}
+
+struct TmapKey {
+  const void* ptr;
+  uint64_t rows, cols, pitch;
+  uint32_t box_rows, box_cols, swizzle;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && pitch == o.pitch && box_rows == o.box_rows &&
+           box_cols == o.box_cols && swizzle == o.swizzle;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    auto mix = [&h](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    mix(k.rows); mix(k.cols); mix(k.pitch); mix(k.box_rows); mix(k.box_cols); mix(k.swizzle);
+    return h;
+  }
+};
+
+// Process-wide descriptor cache: a descriptor depends only on (pointer, shape, box), never on contents.
+std::mutex g_tmap_mu;
+std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+
+// 2-D bf16 tensor [rows, cols] with row pitch `pitch` elements; box = [box_rows, box_cols]; swizzle in bytes.
+int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch,
+                   uint32_t box_rows, uint32_t box_cols, uint32_t swizzle_bytes) {
+  TmapKey key{ptr, rows, cols, pitch, box_rows, box_cols, swizzle_bytes};
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) {
+      *out = it->second;
+      return ECADK_OK;
+    }
+  }
+  EncodeFn encode = get_encode_fn();
+  if (encode == nullptr) return fail(ECADK_EDRIVER, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {pitch * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    return fail(ECADK_EINVAL, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu pitch=%llu box=%ux%u sw=%u",
+                static_cast<int>(r), (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)pitch,
+                box_rows, box_cols, swizzle_bytes);
+  }
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  if (g_tmap_cache.size() > 65536) g_tmap_cache.clear();
+  g_tmap_cache.emplace(key, *out);
+  return ECADK_OK;
+}
+
+int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// GEMM launcher
+// ---------------------------------------------------------------------------------------------------
+template <int BN, int EPI>
+int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool configured = false;
+  auto kern = gemm_bf16_kernel<BN, EPI>;
+  if (!configured) {
+    ECADK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int tiles = ((p.M + kGemmBM - 1) / kGemmBM) * (p.N / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  return check_launch("gemm_bf16_kernel");
+}
+
+// Tile-N choice: the widest tile that divides N and still gives every SM work; ties go to fewer partial waves.
+int pick_bn(int M, int N) {
+  const int m_tiles = (M + kGemmBM - 1) / kGemmBM;
+  const int cands[3] = {256, 192, 128};
+  int best = 0;
+  double best_cost = 1e30;
+  for (int bn : cands) {
+    if (N % bn) continue;
+    const int tiles = m_tiles * (N / bn);
+    const int waves = (tiles + num_sms() - 1) / num_sms();
+    // cost ~ waves * per-tile time (proportional to bn, plus a fixed per-tile overhead)
+    const double cost = static_cast<double>(waves) * (bn + 24.0);
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+template <int EPI>
+int launch_gemm(const void* a, const void* w, GemmParams& p, cudaStream_t stream) {
+  ECADK_REQUIRE(a && w, "gemm: null operand");
+  ECADK_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: bad shape M=%d N=%d K=%d", p.M, p.N, p.K);
+  ECADK_REQUIRE(p.K % kGemmBK == 0, "gemm: K=%d must be a multiple of %d", p.K, kGemmBK);
+  ECADK_REQUIRE(p.N % 128 == 0, "gemm: N=%d must be a multiple of 128", p.N);
+  ECADK_REQUIRE(aligned16(a) && aligned16(w), "gemm: operands must be 16-byte aligned");
+  const int bn = pick_bn(p.M, p.N);
+  ECADK_REQUIRE(bn != 0, "gemm: no tile width divides N=%d", p.N);
+  CUtensorMap ta, tb;
+  int rc = make_tmap_bf16(&ta, a, p.M, p.K, p.K, kGemmBM, kGemmBK, 128);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tb, w, p.N, p.K, p.K, bn, kGemmBK, 128);
+  if (rc) return rc;
+  switch (bn) {
+    case 256: return launch_gemm_inst<256, EPI>(ta, tb, p, stream);
+    case 192: return launch_gemm_inst<192, EPI>(ta, tb, p, stream);
+    default: return launch_gemm_inst<128, EPI>(ta, tb, p, stream);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// attention launcher
+// ---------------------------------------------------------------------------------------------------
+template <int NK, bool HAS_BIAS>
+int launch_attn_inst(const CUtensorMap* tm, const AttnParams& p, int samples, cudaStream_t stream) {
+  using Cfg = AttnCfg<NK>;
+  static bool configured = false;
+  auto kern = attn_tile_kernel<NK, HAS_BIAS>;
+  if (!configured) {
+    ECADK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  dim3 grid(p.q_tokens / kAttnBM, samples * p.heads);
+  kern<<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
+  return check_launch("attn_tile_kernel");
+}
+
+int launch_attention(const void* q, const void* k, const void* v, const float* bias, void* out, int samples,
+                     int heads, int q_tokens, int n_keys, cudaStream_t stream) {
+  ECADK_REQUIRE(q && k && v && out, "attention: null pointer");
+  ECADK_REQUIRE(n_keys == 128 || n_keys == 256, "attention: n_keys=%d (supported: 128, 256)", n_keys);
+  ECADK_REQUIRE(q_tokens > 0 && q_tokens % kAttnBM == 0, "attention: q_tokens=%d must be a multiple of 128", q_tokens);
+  ECADK_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(out), "attention: 16-byte alignment");
+  const uint64_t q_rows = static_cast<uint64_t>(samples) * heads * q_tokens;
+  const uint64_t k_rows = static_cast<uint64_t>(samples) * heads * n_keys;
+  CUtensorMap tm[6];
+  int rc;
+  if ((rc = make_tmap_bf16(&tm[0], q, q_rows, kHeadPad, kHeadPad, kAttnBM, 64, 128))) return rc;
+  if ((rc = make_tmap_bf16(&tm[1], q, q_rows, kHeadPad, kHeadPad, kAttnBM, 16, 32))) return rc;
+  if ((rc = make_tmap_bf16(&tm[2], k, k_rows, kHeadPad, kHeadPad, n_keys, 64, 128))) return rc;
+  if ((rc = make_tmap_bf16(&tm[3], k, k_rows, kHeadPad, kHeadPad, n_keys, 16, 32))) return rc;
+  if ((rc = make_tmap_bf16(&tm[4], v, k_rows, kHeadPad, kHeadPad, n_keys, 64, 128))) return rc;
+  if ((rc = make_tmap_bf16(&tm[5], v, k_rows, kHeadPad, kHeadPad, n_keys, 16, 32))) return rc;
+  AttnParams p;
+  p.heads = heads;
+  p.q_tokens = q_tokens;
+  p.out_ld = heads * kHeadDim;
+  p.scale_log2e = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(kHeadDim)));
+  p.bias = bias;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  if (n_keys == 256) {
+    return bias ? launch_attn_inst<256, true>(tm, p, samples, stream) : launch_attn_inst<256, false>(tm, p, samples, stream);
+  }
+  return bias ? launch_attn_inst<128, true>(tm, p, samples, stream) : launch_attn_inst<128, false>(tm, p, samples, stream);
+}
+
+int launch_residual_ln(const EcadkResidualLnArgs& a, cudaStream_t stream) {
+  ECADK_REQUIRE(a.x != nullptr && a.rows > 0 && a.tokens > 0, "residual_ln: bad x/rows/tokens");
+  ECADK_REQUIRE(a.dim == 1152 || a.dim == 3072, "residual_ln: dim=%d (supported: 1152, 3072)", a.dim);
+  ECADK_REQUIRE(a.n_reuse >= 0 && a.n_reuse <= ECADK_MAX_REUSE, "residual_ln: n_reuse=%d", a.n_reuse);
+  ECADK_REQUIRE(a.h == nullptr || (a.shift_table && a.scale_table && a.shift_temb && a.scale_temb),
+                "residual_ln: LayerNorm path needs shift/scale tables");
+  ECADK_REQUIRE(a.n_reuse > 0 || a.h != nullptr || a.xb != nullptr, "residual_ln: nothing to do");
+  ResidualLnParams p;
+  p.x = a.x;
+  p.xb = static_cast<__nv_bfloat16*>(a.xb);
+  p.h = static_cast<__nv_bfloat16*>(a.h);
+  p.M = a.rows;
+  p.tokens = a.tokens;
+  p.n_reuse = a.n_reuse;
+  for (int i = 0; i < ECADK_MAX_REUSE; ++i) {
+    p.reuse[i].cache = static_cast<const __nv_bfloat16*>(a.reuse[i].cache);
+    p.reuse[i].gate_table = a.reuse[i].gate_table;
+    p.reuse[i].gate_temb = a.reuse[i].gate_temb;
+    if (i < a.n_reuse) {
+      ECADK_REQUIRE(p.reuse[i].cache != nullptr, "residual_ln: reuse[%d].cache is null", i);
+      ECADK_REQUIRE((p.reuse[i].gate_table == nullptr) == (p.reuse[i].gate_temb == nullptr),
+                    "residual_ln: reuse[%d] gate_table/gate_temb must both be set or both null", i);
+    }
+  }
+  p.shift_table = a.shift_table;
+  p.scale_table = a.scale_table;
+  p.shift_temb = a.shift_temb;
+  p.scale_temb = a.scale_temb;
+  p.temb_stride = a.temb_stride;
+  p.eps = a.eps;
+  const int grid = (a.rows + 7) / 8;
+  if (a.dim == 1152) {
+    residual_ln_kernel<9><<<grid, 256, 0, stream>>>(p);
+  } else {
+    residual_ln_kernel<24><<<grid, 256, 0, stream>>>(p);
+  }
+  return check_launch("residual_ln_kernel");
+}
+
+}  // namespace
+
+// =====================================================================================================
+// exported C ABI
+// =====================================================================================================
+struct EcadkHandle_ {
+  int device;
+  EcadkModelDesc desc;
+  std::vector<EcadkBlockWeights> blocks;
+};
+
+extern "C" {
+
+int ecadk_abi_version(void) { return ECADK_ABI_VERSION; }
+
+const char* ecadk_last_error(void) { return g_last_error.c_str(); }
+
+int ecadk_device_check(int device) {
+  cudaDeviceProp prop;
+  ECADK_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    return fail(ECADK_EARCH, "device %d is sm_%d%d; libecad_b200 is built for sm_100a only", device, prop.major,
+                prop.minor);
+  }
+  return ECADK_OK;
+}
+
+int ecadk_residual_ln(const EcadkResidualLnArgs* args, ecadk_stream_t stream) {
+  ECADK_REQUIRE(args != nullptr, "residual_ln: null args");
+  return launch_residual_ln(*args, static_cast<cudaStream_t>(stream));
+}
+
+int ecadk_patch_embed(const float* latents, const float* wt, const float* bias, const float* pos, float* x,
+                      int samples, int channels, int hl, int wl, int dim, ecadk_stream_t stream) {
+  ECADK_REQUIRE(latents && wt && bias && pos && x, "patch_embed: null pointer");
+  ECADK_REQUIRE(channels * 4 <= 64 && hl % 2 == 0 && wl % 2 == 0 && dim % 4 == 0, "patch_embed: bad shape");
+  PatchEmbedParams p{latents, wt, bias, pos, x, samples, channels, hl, wl, dim};
+  const int tokens = samples * (hl / 2) * (wl / 2);
+  patch_embed_kernel<<<tokens, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return check_launch("patch_embed_kernel");
+}
+
+int ecadk_timestep_sinusoid(const float* t, float* out, int samples, int dim, ecadk_stream_t stream) {
+  ECADK_REQUIRE(t && out && samples > 0 && dim > 0 && dim % 2 == 0, "timestep_sinusoid: bad args");
+  const int n = samples * (dim / 2);
+  timestep_sinusoid_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(t, out, samples, dim);
+  return check_launch("timestep_sinusoid_kernel");
+}
+
+int ecadk_small_linear(const float* x, const float* w, const float* b, float* y, int samples, int k, int o, int ldy,
+                       int y_off, int act_in, int accumulate, ecadk_stream_t stream) {
+  ECADK_REQUIRE(x && w && b && y && samples > 0 && k > 0 && o > 0, "small_linear: bad args");
+  SmallLinearParams p{x, w, b, y, samples, k, o, ldy, y_off, act_in, accumulate};
+  small_linear_kernel<<<(o + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return check_launch("small_linear_kernel");
+}
+
+int ecadk_cast_f32_bf16(const float* in, void* out, size_t n, ecadk_stream_t stream) {
+  ECADK_REQUIRE(in && out && n % 4 == 0 && aligned16(in), "cast_f32_bf16: n must be a multiple of 4, 16B aligned");
+  const size_t n4 = n / 4;
+  size_t blocks = (n4 + 255) / 256;
+  if (blocks > static_cast<size_t>(num_sms()) * 16) blocks = static_cast<size_t>(num_sms()) * 16;
+  if (blocks == 0) return ECADK_OK;
+  cast_to_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, static_cast<__nv_bfloat16*>(out), n4);
+  return check_launch("cast_to_bf16_kernel");
+}
+
+int ecadk_mask_bias(const float* mask, float* bias, int samples, int t, int t_pad, ecadk_stream_t stream) {
+  ECADK_REQUIRE(mask && bias && samples > 0 && t > 0 && t_pad >= t, "mask_bias: bad args");
+  const int n = samples * t_pad;
+  mask_bias_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, bias, samples, t, t_pad);
+  return check_launch("mask_bias_kernel");
+}
+
+int ecadk_final_layer(const float* x, const float* table, const float* emb, const float* w, const float* bias,
+                      float* out, int samples, int hp, int wp, int dim, int out_channels, float eps,
+                      ecadk_stream_t stream) {
+  ECADK_REQUIRE(x && table && emb && w && bias && out, "final_layer: null pointer");
+  ECADK_REQUIRE(dim == 1152, "final_layer: dim=%d (supported: 1152)", dim);
+  FinalLayerParams p{x, table, emb, w, bias, out, samples * hp * wp, hp * wp, wp, hp, out_channels, 4 * out_channels, eps};
+  final_layer_kernel<9><<<(p.M + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return check_launch("final_layer_kernel");
+}
+
+int ecadk_cfg_dpm_step(const float* noise, float* latents, float* x0_prev, int batch, int channels, int hw,
+                       int has_cfg, float guidance, float sigma_s, float alpha_s, float c_x, float c_d0, float c_d1,
+                       ecadk_stream_t stream) {
+  ECADK_REQUIRE(noise && latents && x0_prev && batch > 0 && channels > 0 && hw > 0, "cfg_dpm_step: bad args");
+  CfgDpmParams p{noise, latents, x0_prev, batch, channels, hw, has_cfg, guidance, sigma_s, alpha_s, c_x, c_d0, c_d1};
+  const int n = batch * channels * hw;
+  cfg_dpm_step_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return check_launch("cfg_dpm_step_kernel");
+}
+
+int ecadk_gemm_bias(const void* a, const void* w, const float* bias, void* out, int m, int n, int k, int ldo,
+                    int gelu, ecadk_stream_t stream) {
+  ECADK_REQUIRE(out != nullptr && aligned16(out) && ldo % 8 == 0 && ldo >= n, "gemm_bias: bad output");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = m; p.N = n; p.K = k;
+  p.bias = bias;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.ldo = ldo;
+  p.tokens = 1;
+  return gelu ? launch_gemm<EPI_BIAS_GELU>(a, w, p, static_cast<cudaStream_t>(stream))
+              : launch_gemm<EPI_BIAS>(a, w, p, static_cast<cudaStream_t>(stream));
+}
+
+int ecadk_gemm_bias_gated_residual_cache(const void* a, const void* w, const float* bias, float* x, void* xb,
+                                         void* cache, const float* gate_table, const float* gate_temb,
+                                         int temb_stride, int tokens, int m, int n, int k, ecadk_stream_t stream) {
+  ECADK_REQUIRE(x && cache && aligned16(x) && aligned16(cache) && (xb == nullptr || aligned16(xb)),
+                "gemm_gated_residual: bad x/cache");
+  ECADK_REQUIRE(tokens > 0 && tokens % 32 == 0, "gemm_gated_residual: tokens=%d must be a multiple of 32", tokens);
+  ECADK_REQUIRE((gate_table == nullptr) == (gate_temb == nullptr), "gemm_gated_residual: gate table/temb mismatch");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = m; p.N = n; p.K = k;
+  p.bias = bias;
+  p.x = x;
+  p.xb = static_cast<__nv_bfloat16*>(xb);
+  p.cache = static_cast<__nv_bfloat16*>(cache);
+  p.gate_table = gate_table;
+  p.gate_temb = gate_temb;
+  p.temb_stride = temb_stride;
+  p.tokens = tokens;
+  return launch_gemm<EPI_GATED_RESIDUAL>(a, w, p, static_cast<cudaStream_t>(stream));
+}
+
+int ecadk_gemm_bias_headmajor(const void* a, const void* w, const float* bias, void* out0, void* out1, void* out2,
+                              int n_parts, int heads, int tokens, int tokens_pad, int m, int k,
+                              ecadk_stream_t stream) {
+  ECADK_REQUIRE(n_parts >= 1 && n_parts <= 3 && out0, "gemm_headmajor: n_parts=%d", n_parts);
+  ECADK_REQUIRE(tokens > 0 && tokens_pad >= tokens && heads > 0, "gemm_headmajor: bad token/head counts");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = m; p.N = n_parts * heads * kHeadDim; p.K = k;
+  p.bias = bias;
+  p.hm_out[0] = static_cast<__nv_bfloat16*>(out0);
+  p.hm_out[1] = static_cast<__nv_bfloat16*>(out1);
+  p.hm_out[2] = static_cast<__nv_bfloat16*>(out2);
+  for (int i = 0; i < n_parts; ++i) ECADK_REQUIRE(p.hm_out[i] && aligned16(p.hm_out[i]), "gemm_headmajor: out%d", i);
+  p.heads = heads;
+  p.head_dim = kHeadDim;
+  p.head_pad = kHeadPad;
+  p.tokens = tokens;
+  p.tokens_pad = tokens_pad;
+  return launch_gemm<EPI_HEADMAJOR>(a, w, p, static_cast<cudaStream_t>(stream));
+}
+
+int ecadk_attention(const void* q, const void* k, const void* v, const float* bias, void* out, int samples,
+                    int heads, int q_tokens, int n_keys, ecadk_stream_t stream) {
+  return launch_attention(q, k, v, bias, out, samples, heads, q_tokens, n_keys, static_cast<cudaStream_t>(stream));
+}
+
+int ecadk_create(int device, const EcadkModelDesc* desc, const EcadkBlockWeights* blocks, ecadk_handle_t* out) {
+  ECADK_REQUIRE(desc && blocks && out, "create: null argument");
+  ECADK_REQUIRE(desc->num_layers > 0 && desc->dim == desc->heads * kHeadDim, "create: dim must be heads*72");
+  int rc = ecadk_device_check(device);
+  if (rc) return rc;
+  auto* h = new EcadkHandle_();
+  h->device = device;
+  h->desc = *desc;
+  h->blocks.assign(blocks, blocks + desc->num_layers);
+  *out = h;
+  return ECADK_OK;
+}
+
+int ecadk_destroy(ecadk_handle_t h) {
+  delete h;
+  return ECADK_OK;
+}
+
+int ecadk_pixart_text_kv(ecadk_handle_t h, const void* enc, int samples, int text_tokens, int text_pad,
+                         void* const* k2, void* const* v2, int* n_launches, ecadk_stream_t stream) {
+  ECADK_REQUIRE(h && enc && k2 && v2, "text_kv: null argument");
+  const EcadkModelDesc& d = h->desc;
+  int launches = 0;
+  for (int b = 0; b < d.num_layers; ++b) {
+    const EcadkBlockWeights& w = h->blocks[b];
+    int rc = ecadk_gemm_bias_headmajor(enc, w.w_kv2, w.b_kv2, k2[b], v2[b], nullptr, 2, d.heads, text_tokens,
+                                       text_pad, samples * text_tokens, d.dim, stream);
+    if (rc) return rc;
+    ++launches;
+  }
+  if (n_launches) *n_launches = launches;
+  return ECADK_OK;
+}
+
+int ecadk_pixart_blocks(ecadk_handle_t h, const EcadkBlocksArgs* a, const uint8_t* executed, int* n_launches,
+                        ecadk_stream_t stream_) {
+  ECADK_REQUIRE(h && a && executed, "pixart_blocks: null argument");
+  const EcadkModelDesc& d = h->desc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int D = d.dim, M = a->samples * a->tokens, S6 = 6 * D;
+  ECADK_REQUIRE(a->tokens == 256, "pixart_blocks: tokens=%d (this build covers N=256 self-attention)", a->tokens);
+  int launches = 0;
+  int rc;
+
+  EcadkResidualLnArgs pend;  // pending cached-residual reuse, flushed lazily into the next kernel that reads x
+  memset(&pend, 0, sizeof(pend));
+  auto reset_pend = [&]() {
+    memset(&pend, 0, sizeof(pend));
+    pend.x = a->x;
+    pend.rows = M;
+    pend.tokens = a->tokens;
+    pend.dim = D;
+    pend.temb_stride = S6;
+    pend.eps = d.norm_eps;
+  };
+  reset_pend();
+  auto flush = [&]() -> int {
+    if (pend.n_reuse == 0 && pend.h == nullptr && pend.xb == nullptr) return ECADK_OK;
+    int r = launch_residual_ln(pend, stream);
+    ++launches;
+    reset_pend();
+    return r;
+  };
+  auto push_reuse = [&](const void* cache, const float* gate_table, const float* gate_temb) -> int {
+    if (pend.n_reuse == ECADK_MAX_REUSE) {
+      int r = flush();
+      if (r) return r;
+    }
+    pend.reuse[pend.n_reuse++] = EcadkReuse{cache, gate_table, gate_temb};
+    return ECADK_OK;
+  };
+
+  for (int b = 0; b < d.num_layers; ++b) {
+    const EcadkBlockWeights& w = h->blocks[b];
+    const float* tab = w.scale_shift_table;
+    const bool ex1 = executed[b * 3 + 0], ex2 = executed[b * 3 + 1], ex3 = executed[b * 3 + 2];
+    void* c1 = a->cache[b * 3 + 0];
+    void* c2 = a->cache[b * 3 + 1];
+    void* c3 = a->cache[b * 3 + 2];
+    bool xb_valid = false;
+
+    // ---- attn1 (cached_transformer_block.py:208-246)
+    if (ex1) {
+      pend.h = a->h;
+      pend.shift_table = tab + 0 * D;
+      pend.scale_table = tab + 1 * D;
+      pend.shift_temb = a->temb6 + 0 * D;
+      pend.scale_temb = a->temb6 + 1 * D;
+      if ((rc = flush())) return rc;
+      if ((rc = ecadk_gemm_bias_headmajor(a->h, w.w_qkv1, w.b_qkv1, a->q, a->k, a->v, 3, d.heads, a->tokens,
+                                          a->tokens, M, D, stream_)))
+        return rc;
+      if ((rc = launch_attention(a->q, a->k, a->v, nullptr, a->attn_o, a->samples, d.heads, a->tokens, a->tokens,
+                                 stream)))
+        return rc;
+      if ((rc = ecadk_gemm_bias_gated_residual_cache(a->attn_o, w.w_out1, w.b_out1, a->x, ex2 ? a->xb : nullptr, c1,
+                                                     tab + 2 * D, a->temb6 + 2 * D, S6, a->tokens, M, D, D, stream_)))
+        return rc;
+      launches += 3;
+      xb_valid = ex2;
+    } else {
+      if ((rc = push_reuse(c1, tab + 2 * D, a->temb6 + 2 * D))) return rc;
+    }
+
+    // ---- attn2 on the un-normalised stream (:264-289)
+    if (ex2) {
+      if (!xb_valid) {
+        pend.xb = a->xb;
+        if ((rc = flush())) return rc;
+      }
+      if ((rc = ecadk_gemm_bias_headmajor(a->xb, w.w_q2, w.b_q2, a->q, nullptr, nullptr, 1, d.heads, a->tokens,
+                                          a->tokens, M, D, stream_)))
+        return rc;
+      if ((rc = launch_attention(a->q, a->k2[b], a->v2[b], a->text_bias, a->attn_o, a->samples, d.heads, a->tokens,
+                                 a->text_pad, stream)))
+        return rc;
+      if ((rc = ecadk_gemm_bias_gated_residual_cache(a->attn_o, w.w_out2, w.b_out2, a->x, nullptr, c2, nullptr,
+                                                     nullptr, S6, a->tokens, M, D, D, stream_)))
+        return rc;
+      launches += 3;
+    } else {
+      if ((rc = push_reuse(c2, nullptr, nullptr))) return rc;
+    }
+
+    // ---- feed-forward (:306-320)
+    if (ex3) {
+      pend.h = a->h;
+      pend.shift_table = tab + 3 * D;
+      pend.scale_table = tab + 4 * D;
+      pend.shift_temb = a->temb6 + 3 * D;
+      pend.scale_temb = a->temb6 + 4 * D;
+      if ((rc = flush())) return rc;
+      if ((rc = ecadk_gemm_bias(a->h, w.w_ff1, w.b_ff1, a->ffh, M, d.ff_dim, D, d.ff_dim, 1, stream_))) return rc;
+      if ((rc = ecadk_gemm_bias_gated_residual_cache(a->ffh, w.w_ff2, w.b_ff2, a->x, nullptr, c3, tab + 5 * D,
+                                                     a->temb6 + 5 * D, S6, a->tokens, M, D, d.ff_dim, stream_)))
+        return rc;
+      launches += 2;
+    } else {
+      if ((rc = push_reuse(c3, tab + 5 * D, a->temb6 + 5 * D))) return rc;
+    }
+  }
+  if ((rc = flush())) return rc;
+  if (n_launches) *n_launches = launches;
+  return ECADK_OK;
+}
+
+}  // extern "C"

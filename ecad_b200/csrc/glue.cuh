@@ -1,0 +1,341 @@
+// Memory-bound glue of the PixArt hot path: vectorised, coalesced, warp-shuffle reductions (no tensor cores).
+//
+//   residual_ln_kernel   K2/K9/K12 of SURVEY.md section 2b in one kernel: optional cached-residual reuse
+//                        (x += sum_j gate_j * cache_j), optional bf16 shadow of x, optional LayerNorm + adaLN
+//                        modulate -> bf16.  One warp per token row, the row stays in registers.
+//   patch_embed_kernel   K13: 2x2/s2 patch conv + bias + 2-D sincos position table -> fp32 residual stream.
+//   final_layer_kernel   K16: LayerNorm + modulate + Linear(D->32) + unpatchify.
+//   small_linear_kernel  K14: fp32 GEMV-ish linears of the timestep / adaLN-single embedder.
+//   timestep_sinusoid_kernel, cast_to_bf16_kernel, mask_bias_kernel, cfg_dpm_step_kernel (K17).
+#pragma once
+#include "ptx.cuh"
+
+namespace ecadk {
+
+constexpr int kMaxReuse = 6;
+
+struct ReuseEntry {
+  const __nv_bfloat16* cache;  // [M, D] cached un-gated sub-block output
+  const float* gate_table;     // [D] gate row of the block's scale_shift_table, or null (attn2: no gate)
+  const float* gate_temb;      // [samples, temb_stride] offset to the gate chunk
+};
+
+struct ResidualLnParams {
+  float* x;            // [M, D] fp32 residual stream (read; written when n_reuse > 0)
+  __nv_bfloat16* xb;   // optional bf16 copy of the (updated) stream
+  __nv_bfloat16* h;    // optional LN+modulate output
+  int M, tokens;       // rows; rows per sample
+  int n_reuse;
+  ReuseEntry reuse[kMaxReuse];
+  const float* shift_table;  // [D]   (LN path)
+  const float* scale_table;  // [D]
+  const float* shift_temb;   // [samples, temb_stride] offset to the shift chunk
+  const float* scale_temb;   // [samples, temb_stride] offset to the scale chunk
+  int temb_stride;
+  float eps;
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// VPL = float4 vectors per lane: D = 128 * VPL  (1152 -> 9, 3072 -> 24)
+template <int VPL>
+__global__ void __launch_bounds__(256) residual_ln_kernel(const ResidualLnParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= p.M) return;
+  constexpr int D = 128 * VPL;
+  const int sample = row / p.tokens;
+  const size_t roff = static_cast<size_t>(row) * D;
+  float4 v[VPL];
+  const float4* xr = reinterpret_cast<const float4*>(p.x + roff);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) v[i] = xr[lane + 32 * i];
+
+  if (p.n_reuse > 0) {
+    for (int r = 0; r < p.n_reuse; ++r) {
+      const ReuseEntry e = p.reuse[r];
+      const uint2* cr = reinterpret_cast<const uint2*>(e.cache + roff);
+      const float4* gt = reinterpret_cast<const float4*>(e.gate_table);
+      const float4* ge =
+          reinterpret_cast<const float4*>(e.gate_temb ? e.gate_temb + static_cast<size_t>(sample) * p.temb_stride : nullptr);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const uint2 c = __ldg(cr + lane + 32 * i);
+        const float2 c01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&c.x));
+        const float2 c23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&c.y));
+        float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (gt != nullptr) {
+          const float4 a = __ldg(gt + lane + 32 * i), b = __ldg(ge + lane + 32 * i);
+          g = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+        }
+        v[i].x = fmaf(g.x, c01.x, v[i].x);
+        v[i].y = fmaf(g.y, c01.y, v[i].y);
+        v[i].z = fmaf(g.z, c23.x, v[i].z);
+        v[i].w = fmaf(g.w, c23.y, v[i].w);
+      }
+    }
+    float4* xw = reinterpret_cast<float4*>(p.x + roff);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) xw[lane + 32 * i] = v[i];
+  }
+  if (p.xb != nullptr) {
+    uint2* bw = reinterpret_cast<uint2*>(p.xb + roff);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      uint2 o;
+      o.x = pack_bf16x2(v[i].x, v[i].y);
+      o.y = pack_bf16x2(v[i].z, v[i].w);
+      bw[lane + 32 * i] = o;
+    }
+  }
+  if (p.h != nullptr) {
+    // two-pass LayerNorm statistics in fp32 (no affine, eps inside the sqrt), like torch.nn.LayerNorm
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + p.eps);
+    const float4* st = reinterpret_cast<const float4*>(p.shift_table);
+    const float4* ct = reinterpret_cast<const float4*>(p.scale_table);
+    const float4* se = reinterpret_cast<const float4*>(p.shift_temb + static_cast<size_t>(sample) * p.temb_stride);
+    const float4* ce = reinterpret_cast<const float4*>(p.scale_temb + static_cast<size_t>(sample) * p.temb_stride);
+    uint2* hw = reinterpret_cast<uint2*>(p.h + roff);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int k = lane + 32 * i;
+      const float4 sa = __ldg(st + k), sb = __ldg(se + k), ca = __ldg(ct + k), cb = __ldg(ce + k);
+      const float y0 = (v[i].x - mean) * rstd * (1.f + (ca.x + cb.x)) + (sa.x + sb.x);
+      const float y1 = (v[i].y - mean) * rstd * (1.f + (ca.y + cb.y)) + (sa.y + sb.y);
+      const float y2 = (v[i].z - mean) * rstd * (1.f + (ca.z + cb.z)) + (sa.z + sb.z);
+      const float y3 = (v[i].w - mean) * rstd * (1.f + (ca.w + cb.w)) + (sa.w + sb.w);
+      uint2 o;
+      o.x = pack_bf16x2(y0, y1);
+      o.y = pack_bf16x2(y2, y3);
+      hw[k] = o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K13 patch embed: latents [S, C, Hl, Wl] fp32 -> x [S, N, D] fp32, N = (Hl/2)*(Wl/2).
+// wt = conv weight transposed to [C*4, D] (k = c*4 + p*2 + q), pos = [N, D] sincos table.
+struct PatchEmbedParams {
+  const float* latents;
+  const float* wt;
+  const float* bias;
+  const float* pos;
+  float* x;
+  int S, C, Hl, Wl, D;
+};
+__global__ void __launch_bounds__(128) patch_embed_kernel(const PatchEmbedParams p) {
+  const int Wp = p.Wl >> 1, Hp = p.Hl >> 1;
+  const int N = Wp * Hp;
+  const int token = blockIdx.x;  // s*N + n
+  const int s = token / N, n = token - s * N;
+  const int i = n / Wp, j = n - i * Wp;
+  __shared__ float in[64];
+  const int K = p.C * 4;
+  if (threadIdx.x < K) {
+    const int c = threadIdx.x >> 2, pq = threadIdx.x & 3;
+    in[threadIdx.x] =
+        p.latents[((static_cast<size_t>(s) * p.C + c) * p.Hl + (2 * i + (pq >> 1))) * p.Wl + 2 * j + (pq & 1)];
+  }
+  __syncthreads();
+  for (int d4 = threadIdx.x; d4 < p.D / 4; d4 += blockDim.x) {
+    float4 acc = __ldg(reinterpret_cast<const float4*>(p.bias) + d4);
+    for (int k = 0; k < K; ++k) {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(p.wt + static_cast<size_t>(k) * p.D) + d4);
+      const float a = in[k];
+      acc.x = fmaf(a, w.x, acc.x);
+      acc.y = fmaf(a, w.y, acc.y);
+      acc.z = fmaf(a, w.z, acc.z);
+      acc.w = fmaf(a, w.w, acc.w);
+    }
+    const float4 pe = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(n) * p.D) + d4);
+    acc.x += pe.x; acc.y += pe.y; acc.z += pe.z; acc.w += pe.w;
+    reinterpret_cast<float4*>(p.x + static_cast<size_t>(token) * p.D)[d4] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K16 final layer: out[s, c, 2i+p, 2j+q] = Linear_{D->P*P*C}( LN(x) * (1 + scale) + shift )[(p*2+q)*C + c]
+struct FinalLayerParams {
+  const float* x;            // [S*N, D]
+  const float* table;        // [2, D]: shift, scale
+  const float* emb;          // [S, D] embedded_timestep
+  const float* w;            // [OUT, D] fp32
+  const float* bias;         // [OUT]
+  float* out;                // [S, C, 2Hp, 2Wp]
+  int M, tokens, Wp, Hp, C, OUT;
+  float eps;
+};
+template <int VPL>
+__global__ void __launch_bounds__(256) final_layer_kernel(const FinalLayerParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= p.M) return;
+  constexpr int D = 128 * VPL;
+  const int s = row / p.tokens, n = row - s * p.tokens;
+  float4 v[VPL];
+  const float4* xr = reinterpret_cast<const float4*>(p.x + static_cast<size_t>(row) * D);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    v[i] = xr[lane + 32 * i];
+    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(sum) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + p.eps);
+  const float4* sh = reinterpret_cast<const float4*>(p.table);
+  const float4* sc = reinterpret_cast<const float4*>(p.table + D);
+  const float4* em = reinterpret_cast<const float4*>(p.emb + static_cast<size_t>(s) * D);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int k = lane + 32 * i;
+    const float4 a = __ldg(sh + k), b = __ldg(sc + k), e = __ldg(em + k);
+    v[i].x = (v[i].x - mean) * rstd * (1.f + (b.x + e.x)) + (a.x + e.x);
+    v[i].y = (v[i].y - mean) * rstd * (1.f + (b.y + e.y)) + (a.y + e.y);
+    v[i].z = (v[i].z - mean) * rstd * (1.f + (b.z + e.z)) + (a.z + e.z);
+    v[i].w = (v[i].w - mean) * rstd * (1.f + (b.w + e.w)) + (a.w + e.w);
+  }
+  const int i_h = n / p.Wp, j_w = n - i_h * p.Wp;
+  const int Hout = 2 * p.Hp, Wout = 2 * p.Wp;
+  for (int o = 0; o < p.OUT; ++o) {
+    const float4* wr = reinterpret_cast<const float4*>(p.w + static_cast<size_t>(o) * D);
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const float4 w = __ldg(wr + lane + 32 * i);
+      acc += (v[i].x * w.x + v[i].y * w.y) + (v[i].z * w.z + v[i].w * w.w);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const int pq = o / p.C, c = o - pq * p.C;
+      const int pp = pq >> 1, qq = pq & 1;
+      p.out[((static_cast<size_t>(s) * p.C + c) * Hout + (2 * i_h + pp)) * Wout + 2 * j_w + qq] = acc + p.bias[o];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K14 helpers.  y[s, o] = b[o] + sum_i W[o, i] * act_in(x[s, i]);  act_in: 0 none, 1 SiLU.  fp32 throughout.
+// One warp per output feature; the weight row is read once and reused across all samples.
+struct SmallLinearParams {
+  const float* x;  // [S, K]
+  const float* w;  // [O, K]
+  const float* b;  // [O]
+  float* y;        // [S, ldy] written at column offset y_off
+  int S, K, O, ldy, y_off, act_in, accumulate;
+};
+__global__ void __launch_bounds__(256) small_linear_kernel(const SmallLinearParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o = blockIdx.x * 8 + warp;
+  if (o >= p.O) return;
+  const float* wr = p.w + static_cast<size_t>(o) * p.K;
+  for (int s0 = 0; s0 < p.S; s0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int k = lane; k < p.K; k += 32) {
+      const float w = __ldg(wr + k);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (s0 + j < p.S) {
+          float a = __ldg(p.x + static_cast<size_t>(s0 + j) * p.K + k);
+          if (p.act_in == 1) a = a / (1.f + __expf(-a));
+          acc[j] = fmaf(w, a, acc[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float r = warp_sum(acc[j]);
+      if (lane == 0 && s0 + j < p.S) {
+        float* dst = p.y + static_cast<size_t>(s0 + j) * p.ldy + p.y_off + o;
+        const float val = r + p.b[o];
+        *dst = p.accumulate ? (*dst + val) : val;
+      }
+    }
+  }
+}
+
+// diffusers Timesteps(256, flip_sin_to_cos=True, shift 0): out[s] = [cos(t f_i) | sin(t f_i)], f_i = 1e4^(-i/128)
+__global__ void timestep_sinusoid_kernel(const float* t, float* out, int S, int dim) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = dim >> 1;
+  if (idx >= S * half) return;
+  const int s = idx / half, i = idx - s * half;
+  const float f = expf(-9.210340371976184f * static_cast<float>(i) / static_cast<float>(half));
+  const float a = t[s] * f;
+  out[static_cast<size_t>(s) * dim + i] = cosf(a);
+  out[static_cast<size_t>(s) * dim + half + i] = sinf(a);
+}
+
+__global__ void cast_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n4) {
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (; i < n4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(in) + i);
+    uint2 o;
+    o.x = pack_bf16x2(v.x, v.y);
+    o.y = pack_bf16x2(v.z, v.w);
+    reinterpret_cast<uint2*>(out)[i] = o;
+  }
+}
+
+// (1 - mask) * -10000 for real text tokens (pixart_transformer_2d_edited.py:282-289), -inf for padding keys
+__global__ void mask_bias_kernel(const float* mask, float* bias, int S, int T, int T_pad) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= S * T_pad) return;
+  const int s = idx / T_pad, t = idx - s * T_pad;
+  bias[idx] = t < T ? (1.0f - mask[s * T + t]) * -10000.0f : -INFINITY;
+}
+
+// K17: classifier-free guidance + learned-sigma drop + one DPM-Solver++(2M) update, fused.
+//   eps = uncond + g * (text - uncond) on channels [0, C);  x0 = (x - sigma_s * eps) / alpha_s
+//   x_next = c_x * x + c_d0 * x0 + c_d1 * x0_prev      (host folds the 1st/2nd-order coefficients)
+struct CfgDpmParams {
+  const float* noise;  // [2B or B, 2C, H, W] transformer output
+  float* latents;      // [B, C, H, W] in/out
+  float* x0_prev;      // [B, C, H, W] in/out (previous x0 prediction)
+  int B, C, HW, has_cfg;
+  float guidance, sigma_s, alpha_s, c_x, c_d0, c_d1;
+};
+__global__ void cfg_dpm_step_kernel(const CfgDpmParams p) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = p.C * p.HW;
+  if (idx >= p.B * per) return;
+  const int b = idx / per, r = idx - b * per;  // r = c*HW + hw, c < C
+  const size_t nper = static_cast<size_t>(2 * p.C) * p.HW;
+  float eps;
+  if (p.has_cfg) {
+    const float u = p.noise[static_cast<size_t>(b) * nper + r];
+    const float t = p.noise[static_cast<size_t>(b + p.B) * nper + r];
+    eps = u + p.guidance * (t - u);
+  } else {
+    eps = p.noise[static_cast<size_t>(b) * nper + r];
+  }
+  const float x = p.latents[idx];
+  const float x0 = (x - p.sigma_s * eps) / p.alpha_s;
+  const float prev = p.x0_prev[idx];
+  p.latents[idx] = p.c_x * x + p.c_d0 * x0 + p.c_d1 * prev;
+  p.x0_prev[idx] = x0;
+}
+
+}  // namespace ecadk

@@ -1,0 +1,98 @@
+"""Analytic work model of the PixArt hot path.
+
+Two conventions, both per *sample* (one CFG image = 2 samples per step):
+
+* ``calflops`` convention - Linear/Conv MACs only, no SDPA, no norms - the one the reference's
+  ecad/benchmark/compute_macs.py:255-303 records into ``metrics.by_inference_step`` of the shipped schedule
+  JSONs.  Reproducing those numbers from a decision trace is the known-answer test for the compute/reuse
+  decisions.
+* algorithmic FLOPs - 2 x MACs *including* the SDPA matmuls - the numerator of the tensor roofline that
+  bench.py reports.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+
+@dataclass(frozen=True)
+class PixArtShape:
+    tokens: int = 256  # N image tokens = (H/16)*(W/16)
+    text_tokens: int = 120  # T (120 alpha, 300 sigma)
+    dim: int = 1152  # D
+    heads: int = 16
+    head_dim: int = 72
+    ff_mult: int = 4
+    caption_channels: int = 4096
+    patch_in: int = 16  # in_channels * patch^2 = 4*2*2
+    patch_out: int = 32  # patch^2 * out_channels = 2*2*8
+    additional_conditions: bool = False  # 1024-MS alpha only (resolution + aspect-ratio embedders)
+
+    # ---- calflops convention (MACs of nn.Linear / nn.Conv2d only) --------------------------------
+    def macs_attn1(self) -> int:
+        return 4 * self.tokens * self.dim**2
+
+    def macs_attn2(self) -> int:
+        return 2 * self.tokens * self.dim**2 + 2 * self.text_tokens * self.dim**2
+
+    def macs_ff(self) -> int:
+        return 2 * self.ff_mult * self.tokens * self.dim**2
+
+    def macs_fixed(self) -> int:
+        N, D, T = self.tokens, self.dim, self.text_tokens
+        fixed = (
+            self.patch_in * N * D  # patch-embed conv
+            + 256 * D + D * D  # timestep MLP
+            + 6 * D * D  # adaLN-single linear
+            + T * (self.caption_channels * D + D * D)  # caption projection
+            + self.patch_out * N * D  # proj_out
+        )
+        if self.additional_conditions:
+            fixed += 3 * (256 * 384 + 384 * 384)
+        return fixed
+
+    def macs_components(self) -> np.ndarray:
+        return np.array([self.macs_attn1(), self.macs_attn2(), self.macs_ff()], dtype=np.int64)
+
+    # ---- algorithmic FLOPs (2*MACs incl. SDPA) ----------------------------------------------------
+    def flops_attn1(self) -> int:
+        return 2 * (4 * self.tokens * self.dim**2 + 2 * self.tokens**2 * self.dim)
+
+    def flops_attn2(self) -> int:
+        N, D, T = self.tokens, self.dim, self.text_tokens
+        return 2 * (2 * N * D * D + 2 * T * D * D + 2 * N * T * D)
+
+    def flops_ff(self) -> int:
+        return 2 * self.macs_ff()
+
+    def flops_fixed(self) -> int:
+        return 2 * self.macs_fixed()
+
+    def flops_components(self) -> np.ndarray:
+        return np.array([self.flops_attn1(), self.flops_attn2(), self.flops_ff()], dtype=np.int64)
+
+
+def macs_per_step(
+    executed: np.ndarray, shape: PixArtShape, batch: int = 2, tgate_gate_step: int | None = None
+) -> np.ndarray:
+    """``macs[step] = batch_s * (fixed + sum_{b,c} executed[s][b][c] * comp_c)``.
+
+    ``batch`` is the calflops input batch (2 = one CFG pair, compute_macs.py:40); under the TGATE pipeline the
+    batch drops to 1 from ``gate_step`` on (ecad/pipelines/tgate.py:329-341).
+    """
+    executed = np.asarray(executed)
+    comp = shape.macs_components()
+    per = shape.macs_fixed() + (executed.astype(np.int64) * comp[None, None, :]).sum(axis=(1, 2))
+    b = np.full(executed.shape[0], batch, dtype=np.int64)
+    if tgate_gate_step is not None:
+        b[tgate_gate_step:] = batch // 2
+    return per * b
+
+
+def flops_per_image(executed: np.ndarray, shape: PixArtShape, samples_per_image: int = 2) -> int:
+    """Algorithmic FLOPs of one generated image (all steps, both CFG samples) under a decision trace."""
+    executed = np.asarray(executed)
+    comp = shape.flops_components()
+    per_step = shape.flops_fixed() + (executed.astype(np.int64) * comp[None, None, :]).sum(axis=(1, 2))
+    return int(per_step.sum()) * samples_per_image

@@ -1,0 +1,236 @@
+"""Cache schedules: which sub-block of which transformer block is recomputed at which denoising step.
+
+Host-side mirror of the reference's schedule objects for the hot path (same names, argument meaning, JSON
+format and error behaviour), re-laid-out for the B200 step executor: the flags live in one dense
+``bool[S][NB][3]`` array so that a whole step's decision row is a single 84-byte slice handed to the C-ABI
+(`ecadk_pixart_step`), instead of three dict look-ups per sub-block.
+
+Reference interfaces mirrored (all under /root/reference/):
+  * ``CacheSchedule``            ecad/schedulers/cache_scheduler/cache_schedule.py:18-112
+  * ``PixArtCacheSchedule``      ecad/schedulers/cache_scheduler/pixart_cache_schedule.py:9-37
+  * schedule JSON TypedDicts     ecad/types.py:43-64
+  * genome <-> schedule dict     ecad/genetic/pixart_population_io_manager.py:213-240
+"""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+from typing import Any, Iterable
+
+import numpy as np
+
+PIXART_COMPONENTS = ("attn1", "attn2", "ff")
+
+# Names registered by the reference's compute registries (ecad/transformer_blocks/custom_attn_ff.py:52-59,
+# ecad/transformer_blocks/cached_transformer_block.py:326,362,393).
+ATTN_CACHED = "compute_attn_cached"
+ATTN_TGATE = "compute_attn_tgate"
+FF_CACHED = "compute_ff_cached"
+
+
+class CacheSchedule:
+    """``schedule[step][block][component] -> bool`` plus the step counter the pipeline callback advances.
+
+    Mirrors ecad/schedulers/cache_scheduler/cache_schedule.py:18-112.  ``schedule`` accepts the same
+    dict-of-dict-of-dict the reference JSON holds (step keys may be ``"000"`` strings or ints).
+    """
+
+    components: tuple[str, ...] = ()
+
+    def __init__(
+        self,
+        num_blocks: int,
+        num_inference_steps: int,
+        name: str,
+        schedule: dict[int | str, dict[str, dict[str, Any]]],
+        top_level_config: dict[str, Any] | None = None,
+        attributes: dict[str, Any] | None = None,
+        metrics: dict[str, Any] | None = None,
+        **kwargs: Any,
+    ) -> None:
+        self.num_blocks = int(num_blocks)
+        self.num_inference_steps = int(num_inference_steps)
+        self.name = name
+        self.metrics = metrics if metrics is not None else {}
+        self.attributes = attributes if attributes is not None else {}
+        self.top_level_config = top_level_config if top_level_config is not None else {}
+        # step keys are cast to int on load (cache_schedule.py:38-41)
+        self.schedule: dict[int, dict[str, dict[str, Any]]] = {int(s): blocks for s, blocks in schedule.items()}
+        self._last_step = -1
+        self._flags: np.ndarray | None = None
+
+    # ---- step counter (cache_schedule.py:58-66) -------------------------------------------------
+    def reset_step(self) -> None:
+        self._last_step = -1
+
+    @property
+    def curr_step(self) -> int:
+        return self._last_step + 1
+
+    def per_step_callback(self, step: int, timestep: Any = None, **kwargs: Any) -> None:
+        self._last_step = int(step)
+
+    # ---- lookups ---------------------------------------------------------------------------------
+    def block_keys(self) -> list[str]:
+        raise NotImplementedError
+
+    def get_recompute(self, block_num: str, component: str) -> bool:
+        """cache_schedule.py:68-73 - ValueError on an unknown component, KeyError on an unknown step/block."""
+        if component not in self.components:
+            raise ValueError(f"Invalid component {component}. Must be one of {list(self.components)}.")
+        return bool(self.schedule[self.curr_step][block_num][component])
+
+    # ---- dense view ------------------------------------------------------------------------------
+    def to_numpy(self, flatten: bool = False) -> np.ndarray:
+        raise NotImplementedError
+
+    @property
+    def flags(self) -> np.ndarray:
+        """Dense read-only ``bool[S][NB][C]`` view, built once (the executor slices one row per step)."""
+        if self._flags is None:
+            arr = self.to_numpy()
+            arr.setflags(write=False)
+            self._flags = arr
+        return self._flags
+
+    # ---- JSON (cache_schedule.py:75-112) ----------------------------------------------------------
+    def to_dict(self) -> dict[str, Any]:
+        return {
+            "cache_schedule": {
+                "num_blocks": self.num_blocks,
+                "num_inference_steps": self.num_inference_steps,
+                "name": self.name,
+                "attributes": self.attributes,
+                "schedule": {f"{step:03}": blocks for step, blocks in self.schedule.items()},
+            },
+            "config": self.top_level_config,
+            "metrics": self.metrics,
+        }
+
+    def to_json(self, file_path: Path) -> None:
+        with Path(file_path).open("w") as f:
+            json.dump(self.to_dict(), f, indent=4)
+
+    @classmethod
+    def from_dict(cls, data: dict[str, Any]) -> "CacheSchedule":
+        data = dict(data)
+        top_level_config = data.pop("config", None)
+        metrics = data.pop("metrics", None)
+        # a file without a "cache_schedule" key raises KeyError, which the image generator catches to fall
+        # back to the default schedule (ecad/image_generators/image_generator.py:119-125)
+        return cls(**data["cache_schedule"], top_level_config=top_level_config, metrics=metrics)
+
+    @classmethod
+    def from_json(cls, file_path: Path) -> "CacheSchedule":
+        with Path(file_path).open("r") as f:
+            return cls.from_dict(json.load(f))
+
+
+class PixArtCacheSchedule(CacheSchedule):
+    """PixArt-alpha/sigma schedule: 28 blocks x (attn1, attn2, ff).  pixart_cache_schedule.py:9-37."""
+
+    components = PIXART_COMPONENTS
+
+    def block_keys(self) -> list[str]:
+        return [str(b) for b in range(self.num_blocks)]
+
+    def to_numpy(self, flatten: bool = False) -> np.ndarray:
+        arr = np.zeros((self.num_inference_steps, self.num_blocks, 3), dtype=np.bool_)
+        for step, blocks in self.schedule.items():
+            for block_num, comp in blocks.items():
+                b = int(block_num)
+                arr[step, b, 0] = comp["attn1"]
+                arr[step, b, 1] = comp["attn2"]
+                arr[step, b, 2] = comp["ff"]
+        return arr.reshape(-1) if flatten else arr
+
+    def get_custom_compute_attn(self, block_num: str) -> dict[str, Any]:
+        return self.schedule[self.curr_step][block_num].get("custom_compute_attn", {})
+
+    def get_custom_compute_ff(self, block_num: str) -> dict[str, Any]:
+        return self.schedule[self.curr_step][block_num].get("custom_compute_ff", {})
+
+    # ---- constructors the GA side uses ------------------------------------------------------------
+    @classmethod
+    def from_numpy(
+        cls,
+        flags: np.ndarray | Iterable[bool],
+        num_inference_steps: int = 20,
+        num_blocks: int = 28,
+        name: str = "from_numpy",
+        custom_compute_attn: dict[str, Any] | None = None,
+        top_level_config: dict[str, Any] | None = None,
+        attributes: dict[str, Any] | None = None,
+        metrics: dict[str, Any] | None = None,
+    ) -> "PixArtCacheSchedule":
+        """Genome -> schedule; inverse of ``to_numpy`` (pixart_population_io_manager.py:213-240)."""
+        arr = np.asarray(flags).astype(np.bool_).reshape(num_inference_steps, num_blocks, 3)
+        sched: dict[int, dict[str, dict[str, Any]]] = {}
+        for s in range(num_inference_steps):
+            blocks: dict[str, dict[str, Any]] = {}
+            for b in range(num_blocks):
+                entry: dict[str, Any] = {
+                    "attn1": bool(arr[s, b, 0]),
+                    "attn2": bool(arr[s, b, 1]),
+                    "ff": bool(arr[s, b, 2]),
+                }
+                if custom_compute_attn:
+                    entry["custom_compute_attn"] = json.loads(json.dumps(custom_compute_attn))
+                blocks[str(b)] = entry
+            sched[s] = blocks
+        return cls(num_blocks, num_inference_steps, name, sched, top_level_config, attributes, metrics)
+
+    @classmethod
+    def default(cls, num_inference_steps: int = 20, num_blocks: int = 28) -> "PixArtCacheSchedule":
+        """All-true schedule == the uncached model (schedules/alpha_cache_schedules/gen_default/default.json)."""
+        return cls.from_numpy(
+            np.ones((num_inference_steps, num_blocks, 3), np.bool_), num_inference_steps, num_blocks, "default"
+        )
+
+    # ---- per-step rows for the executor -----------------------------------------------------------
+    def attn_kinds(self, step: int) -> list[tuple[str, dict[str, Any]]]:
+        """Per block: (registry name lower-cased or default, kwargs) for `custom_compute_attn` at `step`."""
+        out = []
+        for b in self.block_keys():
+            cfg = self.schedule[step][b].get("custom_compute_attn", {}) or {}
+            name = cfg.get("name")
+            out.append(((name or ATTN_CACHED).lower(), dict(cfg.get("kwargs", {}) or {})))
+        return out
+
+    def gate_step(self) -> int | None:
+        """TGATE gate step, from the pipeline config (ecad/pipelines/tgate.py:329-341) or the block kwargs."""
+        pipe = (self.top_level_config or {}).get("pipeline") or {}
+        if pipe.get("name") == "tgate":
+            g = (pipe.get("kwargs") or {}).get("gate_step")
+            if g is not None:
+                return int(g)
+        return None
+
+
+def trace_decisions(
+    flags: np.ndarray,
+    attn2_tgate_gate_step: int | None = None,
+) -> np.ndarray:
+    """Executed/reused decision of every (step, block, component) over one generation.
+
+    Rule (ecad/transformer_blocks/cached_transformer_block.py:340-347,367-373): a sub-block is executed iff
+    ``flag or cache_is_None``; caches start empty (reset at the end of the previous generation,
+    ecad/image_generators/image_generator.py:197-202) and are filled by the first pass through a sub-block.
+    TGATE attn2 (``compute_attn_tgate``, :393-454): the flag rule applies while ``curr_step <= gate_step-1``;
+    from ``gate_step`` on attn2 is never executed (the reference asserts the cache exists).
+
+    Returns ``uint8[S][NB][3]``: 1 = execute, 0 = reuse the cached tensor.
+    """
+    flags = np.asarray(flags, dtype=np.bool_)
+    S, NB, C = flags.shape
+    executed = np.zeros((S, NB, C), dtype=np.uint8)
+    have_cache = np.zeros((NB, C), dtype=np.bool_)
+    for s in range(S):
+        run = flags[s] | ~have_cache
+        if attn2_tgate_gate_step is not None and s >= attn2_tgate_gate_step:
+            if not have_cache[:, 1].all():
+                raise AssertionError("Cross-Attention must be cached at gate step for TGATE.")
+            run[:, 1] = False
+        executed[s] = run
+        have_cache |= run
+    return executed

@@ -1,0 +1,108 @@
+"""Random-init weights of the named architecture (BASELINE.json: "random-init weights of the named architecture").
+
+There is no network for checkpoints, so the protocol is the one the reference itself uses for MAC counting on
+FLUX (``skip_transformer_block_init=True``, /root/reference/ecad/transformer_2d_models/flux_transformer_2d_edited.py:75-83):
+construct the architecture and keep its constructor initialisation.  Keys follow
+``diffusers.PixArtTransformer2DModel.state_dict()`` so a real PixArt-alpha/sigma checkpoint loads through the
+same path; init scales are the constructor's (nn.Linear / nn.Conv2d Kaiming-uniform(a=sqrt 5) => U(+-1/sqrt(fan_in))
+for weight and bias, ``scale_shift_table = randn/sqrt(D)``), SURVEY.md section 8d.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import torch
+
+
+@dataclass(frozen=True)
+class PixArtConfig:
+    """Mirror of the reference's constructor defaults (pixart_transformer_2d_edited.py:25-45)."""
+
+    num_attention_heads: int = 16
+    attention_head_dim: int = 72
+    in_channels: int = 4
+    out_channels: int = 8
+    num_layers: int = 28
+    cross_attention_dim: int = 1152
+    sample_size: int = 32
+    patch_size: int = 2
+    norm_eps: float = 1e-6
+    caption_channels: int = 4096
+    interpolation_scale: int | None = None
+    use_additional_conditions: bool | None = None
+
+    @property
+    def inner_dim(self) -> int:
+        return self.num_attention_heads * self.attention_head_dim
+
+    @property
+    def resolved_interpolation_scale(self) -> int:
+        return self.interpolation_scale if self.interpolation_scale is not None else max(self.sample_size // 64, 1)
+
+    @property
+    def resolved_additional_conditions(self) -> bool:
+        if self.use_additional_conditions is None:
+            return self.sample_size == 128
+        return self.use_additional_conditions
+
+
+def _linear(sd, name, out_f, in_f, gen, fan_in=None):
+    bound = 1.0 / math.sqrt(fan_in or in_f)
+    sd[name + ".weight"] = (torch.rand(out_f, in_f, generator=gen) * 2 - 1) * bound
+    sd[name + ".bias"] = (torch.rand(out_f, generator=gen) * 2 - 1) * bound
+
+
+def random_init_state_dict(cfg: PixArtConfig = PixArtConfig(), seed: int = 0) -> dict[str, torch.Tensor]:
+    """fp32 CPU state dict, deterministic in ``seed``."""
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    D = cfg.inner_dim
+    sd: dict[str, torch.Tensor] = {}
+    p = cfg.patch_size
+    fan = cfg.in_channels * p * p
+    b = 1.0 / math.sqrt(fan)
+    sd["pos_embed.proj.weight"] = (torch.rand(D, cfg.in_channels, p, p, generator=gen) * 2 - 1) * b
+    sd["pos_embed.proj.bias"] = (torch.rand(D, generator=gen) * 2 - 1) * b
+    _linear(sd, "adaln_single.emb.timestep_embedder.linear_1", D, 256, gen)
+    _linear(sd, "adaln_single.emb.timestep_embedder.linear_2", D, D, gen)
+    if cfg.resolved_additional_conditions:
+        s = D // 3
+        for nm in ("resolution_embedder", "aspect_ratio_embedder"):
+            _linear(sd, f"adaln_single.emb.{nm}.linear_1", s, 256, gen)
+            _linear(sd, f"adaln_single.emb.{nm}.linear_2", s, s, gen)
+    _linear(sd, "adaln_single.linear", 6 * D, D, gen)
+    _linear(sd, "caption_projection.linear_1", D, cfg.caption_channels, gen)
+    _linear(sd, "caption_projection.linear_2", D, D, gen)
+    for i in range(cfg.num_layers):
+        pre = f"transformer_blocks.{i}"
+        sd[pre + ".scale_shift_table"] = torch.randn(6, D, generator=gen) / D**0.5
+        for attn, kv_in in (("attn1", D), ("attn2", cfg.cross_attention_dim)):
+            _linear(sd, f"{pre}.{attn}.to_q", D, D, gen)
+            _linear(sd, f"{pre}.{attn}.to_k", D, kv_in, gen)
+            _linear(sd, f"{pre}.{attn}.to_v", D, kv_in, gen)
+            _linear(sd, f"{pre}.{attn}.to_out.0", D, D, gen)
+        _linear(sd, f"{pre}.ff.net.0.proj", 4 * D, D, gen)
+        _linear(sd, f"{pre}.ff.net.2", D, 4 * D, gen)
+    sd["scale_shift_table"] = torch.randn(2, D, generator=gen) / D**0.5
+    _linear(sd, "proj_out", p * p * cfg.out_channels, D, gen)
+    return sd
+
+
+def synthetic_prompt_embeddings(batch: int, text_tokens: int = 120, channels: int = 4096, seed: int = 1,
+                                dtype: torch.dtype = torch.float32) -> dict[str, torch.Tensor]:
+    """Synthetic T5-like caption embeddings in the reference's ``PixArtPromptEmbedding`` layout
+    (/root/reference/ecad/types.py:14-18): randn*0.2, per-prompt valid length U{8..T}, and ONE null embedding
+    (valid length 2) repeated over the batch like the reference's "" embedding
+    (/root/reference/ecad/image_generators/pixart_image_generator.py:237-242)."""
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    emb = torch.randn(batch, text_tokens, channels, generator=gen) * 0.2
+    lens = torch.randint(8, text_tokens + 1, (batch,), generator=gen)
+    mask = (torch.arange(text_tokens)[None, :] < lens[:, None]).to(torch.int64)
+    neg = (torch.randn(1, text_tokens, channels, generator=gen) * 0.2).repeat(batch, 1, 1)
+    neg_mask = (torch.arange(text_tokens)[None, :] < 2).to(torch.int64).repeat(batch, 1)
+    return {
+        "prompt_embeds": emb.to(dtype),
+        "prompt_attention_mask": mask,
+        "negative_prompt_embeds": neg.to(dtype),
+        "negative_prompt_attention_mask": neg_mask,
+    }

@@ -1,0 +1,217 @@
+/*
+ * ecad_b200.h - C ABI of libecad_b200.so: the B200 (sm_100a) kernels behind ECAD's cached diffusion-transformer
+ * forward pass.
+ *
+ * The reference (AniAggarwal/ecad) is 100% Python and has NO FFI; every entry point below replaces work the
+ * reference reaches through torch/diffusers modules.  Each declaration cites the reference code it stands in for
+ * (paths relative to the reference repo root).  INTEGRATION.md shows the ctypes binding and the reference-side
+ * plug-in (ImageGeneratorRegistry / ComputeAttnRegistry) a maintainer would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only; no torch/C++ types cross the boundary.
+ *   - All pointers are DEVICE pointers unless a comment says "host".  The caller (PyTorch) owns every buffer; the
+ *     library never allocates persistent device memory.  No tensor lifetime crosses a call.
+ *   - Every entry point is an asynchronous enqueue on `stream` (a cudaStream_t passed as void*).
+ *   - Return 0 on success, a negative ECADK_E* code on failure; ecadk_last_error() gives the thread-local message.
+ *     No C++ exception crosses the boundary.  There is no CPU fallback: on a non-sm_100 device the calls fail.
+ *   - bf16 tensors are passed as void* (uint16 storage); fp32 as float*.
+ */
+#ifndef ECAD_B200_H_
+#define ECAD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ECADK_ABI_VERSION 1
+
+#define ECADK_OK 0
+#define ECADK_EINVAL (-1)  /* bad shape / alignment / null pointer */
+#define ECADK_ECUDA (-2)   /* CUDA runtime or launch error */
+#define ECADK_EARCH (-3)   /* device is not sm_100 */
+#define ECADK_EDRIVER (-4) /* driver entry point (cuTensorMapEncodeTiled) unavailable */
+
+#define ECADK_MAX_REUSE 6
+#define ECADK_HEAD_DIM 72 /* PixArt attention_head_dim (pixart_transformer_2d_edited.py:27) */
+#define ECADK_HEAD_PAD 80 /* head_dim zero-padded to a multiple of the UMMA K step (16) */
+
+typedef void* ecadk_stream_t;
+typedef struct EcadkHandle_* ecadk_handle_t;
+
+int ecadk_abi_version(void);
+const char* ecadk_last_error(void);
+/* 0 if `device` is an sm_100 GPU, ECADK_EARCH otherwise. */
+int ecadk_device_check(int device);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Glue kernels (HBM-bound)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+typedef struct {
+  const void* cache;       /* bf16 [rows, dim] cached un-gated sub-block output */
+  const float* gate_table; /* fp32 [dim] gate row of the block's scale_shift_table; NULL = no gate (attn2) */
+  const float* gate_temb;  /* fp32 [samples, temb_stride], already offset to the gate chunk */
+} EcadkReuse;
+
+typedef struct {
+  float* x;      /* fp32 [rows, dim] residual stream; rewritten when n_reuse > 0 */
+  void* xb;      /* optional bf16 [rows, dim] copy of the (updated) stream, or NULL */
+  void* h;       /* optional bf16 [rows, dim] LayerNorm+modulate output, or NULL */
+  int rows;      /* samples * tokens */
+  int tokens;    /* rows per sample */
+  int dim;       /* 1152 (PixArt) or 3072 */
+  int n_reuse;   /* 0..ECADK_MAX_REUSE */
+  EcadkReuse reuse[ECADK_MAX_REUSE];
+  const float* shift_table; /* fp32 [dim]  (needed when h != NULL) */
+  const float* scale_table; /* fp32 [dim] */
+  const float* shift_temb;  /* fp32 [samples, temb_stride], offset to the shift chunk */
+  const float* scale_temb;  /* fp32 [samples, temb_stride], offset to the scale chunk */
+  int temb_stride;          /* 6*dim for adaLN-single */
+  float eps;                /* 1e-6 */
+} EcadkResidualLnArgs;
+
+/* Fused cached-residual reuse + LayerNorm + adaLN-single modulate.
+ * Replaces: norm1/norm2 + `norm*(1+scale)+shift` (ecad/transformer_blocks/cached_transformer_block.py:208-215,
+ * 306-310) and the reuse branch `gate * cached + hidden_states` (:244-246, :289, :318-320 fed by :355, :386). */
+int ecadk_residual_ln(const EcadkResidualLnArgs* args, ecadk_stream_t stream);
+
+/* Patch embedding: Conv2d(C, dim, k=2, s=2) + bias + 2-D sincos position table -> fp32 stream.
+ * Replaces self.pos_embed(hidden_states) (ecad/transformer_2d_models/pixart_transformer_2d_edited.py:306).
+ * latents fp32 [S,C,Hl,Wl]; wt fp32 [C*4, dim] (conv weight transposed); pos fp32 [(Hl/2)*(Wl/2), dim]. */
+int ecadk_patch_embed(const float* latents, const float* wt, const float* bias, const float* pos, float* x,
+                      int samples, int channels, int hl, int wl, int dim, ecadk_stream_t stream);
+
+/* Timestep sinusoid (diffusers Timesteps(256, flip_sin_to_cos=True)): out fp32 [S, dim] = [cos | sin].
+ * Replaces the first stage of self.adaln_single (pixart_transformer_2d_edited.py:308-313). */
+int ecadk_timestep_sinusoid(const float* t, float* out, int samples, int dim, ecadk_stream_t stream);
+
+/* y[s, y_off + o] (+)= b[o] + sum_i W[o,i] * act(x[s,i]); act_in: 0 none, 1 SiLU.  fp32.
+ * Replaces the TimestepEmbedding MLPs and AdaLayerNormSingle.linear (pixart_transformer_2d_edited.py:308-313). */
+int ecadk_small_linear(const float* x, const float* w, const float* b, float* y, int samples, int k, int o, int ldy,
+                       int y_off, int act_in, int accumulate, ecadk_stream_t stream);
+
+int ecadk_cast_f32_bf16(const float* in, void* out, size_t n, ecadk_stream_t stream);
+
+/* bias[s,t] = (1-mask[s,t]) * -10000 for t < T, -inf for padding keys t in [T, T_pad).
+ * Replaces _create_attention_mask (pixart_transformer_2d_edited.py:255-291). */
+int ecadk_mask_bias(const float* mask, float* bias, int samples, int t, int t_pad, ecadk_stream_t stream);
+
+/* Final layer: LayerNorm + (scale_shift_table[2,dim] + embedded_timestep) modulate + Linear(dim -> p*p*C) +
+ * unpatchify "nhwpqc->nchpwq".  Replaces _create_output (pixart_transformer_2d_edited.py:332-376).
+ * out fp32 [S, C, 2*hp, 2*wp]. */
+int ecadk_final_layer(const float* x, const float* table, const float* emb, const float* w, const float* bias,
+                      float* out, int samples, int hp, int wp, int dim, int out_channels, float eps,
+                      ecadk_stream_t stream);
+
+/* Fused classifier-free guidance + learned-sigma drop + one DPM-Solver++(2M) update on fp32 latents.
+ * Replaces the tail of the denoising loop (ecad/pipelines/pass_through.py:341-370).
+ * x_next = c_x*x + c_d0*x0 + c_d1*x0_prev with x0 = (x - sigma_s*eps)/alpha_s; x0_prev is updated to x0. */
+int ecadk_cfg_dpm_step(const float* noise, float* latents, float* x0_prev, int batch, int channels, int hw,
+                       int has_cfg, float guidance, float sigma_s, float alpha_s, float c_x, float c_d0, float c_d1,
+                       ecadk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Dense contractions (tcgen05 / TMEM / TMA)
+ * All GEMMs: C[M,N] = A[M,K] * W[N,K]^T + bias;  A, W bf16 row-major (K contiguous, pitch = K), bias fp32 [N].
+ * Requirements: K % 64 == 0, N % 128 == 0, pointers 16-byte aligned.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* out bf16 [M, ldo].  gelu != 0 applies GELU(tanh) (diffusers GELU(approximate="tanh")).
+ * Replaces FeedForward.net[0] (cached_transformer_block.py:382) and PixArtAlphaTextProjection
+ * (pixart_transformer_2d_edited.py:315-321). */
+int ecadk_gemm_bias(const void* a, const void* w, const float* bias, void* out, int m, int n, int k, int ldo,
+                    int gelu, ecadk_stream_t stream);
+
+/* o = A W^T + bias;  cache = bf16(o);  x += gate * o  (gate = gate_table + gate_temb[sample], or 1 if NULL);
+ * optional xb = bf16(x).  x fp32 [M,N] in place.
+ * Replaces attn.to_out[0] / ff.net[2] + "update the cache" + gated residual
+ * (cached_transformer_block.py:357-358,388-389 and :244-246, :289, :318-320). */
+int ecadk_gemm_bias_gated_residual_cache(const void* a, const void* w, const float* bias, float* x, void* xb,
+                                         void* cache, const float* gate_table, const float* gate_temb,
+                                         int temb_stride, int tokens, int m, int n, int k, ecadk_stream_t stream);
+
+/* Q/K/V projection with head-major scatter: column c of the GEMM output belongs to part c/(heads*72)
+ * (0..n_parts-1), head (c%(heads*72))/72; row r to sample r/tokens, token r%tokens.  Written to
+ * out[part][sample][head][token (pitch tokens_pad)][ECADK_HEAD_PAD] bf16; padding is left untouched (keep it zero).
+ * Replaces attn.to_q/to_k/to_v + the (B,L,H,d)->(B,H,L,d) reshape of AttnProcessor2_0
+ * (cached_transformer_block.py:348-353). */
+int ecadk_gemm_bias_headmajor(const void* a, const void* w, const float* bias, void* out0, void* out1, void* out2,
+                              int n_parts, int heads, int tokens, int tokens_pad, int m, int k,
+                              ecadk_stream_t stream);
+
+/* softmax(Q K^T / sqrt(72) + bias) V for one-tile key sequences.
+ * q bf16 [samples, heads, q_tokens, 80]; k, v bf16 [samples, heads, n_keys, 80] (n_keys in {128, 256});
+ * bias fp32 [samples, n_keys] or NULL; out bf16 [samples, q_tokens, heads*72].
+ * Replaces F.scaled_dot_product_attention inside AttnProcessor2_0 (cached_transformer_block.py:348-353). */
+int ecadk_attention(const void* q, const void* k, const void* v, const float* bias, void* out, int samples,
+                    int heads, int q_tokens, int n_keys, ecadk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Step-level executor: all transformer blocks of one forward pass under one decision row.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+typedef struct {
+  int num_layers;  /* 28 */
+  int dim;         /* 1152 */
+  int heads;       /* 16 */
+  int ff_dim;      /* 4608 */
+  float norm_eps;  /* 1e-6 */
+} EcadkModelDesc;
+
+typedef struct {
+  const void* w_qkv1; const float* b_qkv1; /* attn1 to_q|to_k|to_v stacked: bf16 [3*dim, dim] */
+  const void* w_out1; const float* b_out1; /* attn1.to_out[0]: [dim, dim] */
+  const void* w_q2;   const float* b_q2;   /* attn2.to_q */
+  const void* w_kv2;  const float* b_kv2;  /* attn2 to_k|to_v stacked: [2*dim, dim] */
+  const void* w_out2; const float* b_out2;
+  const void* w_ff1;  const float* b_ff1;  /* ff.net[0].proj: [ff_dim, dim] */
+  const void* w_ff2;  const float* b_ff2;  /* ff.net[2]: [dim, ff_dim] */
+  const float* scale_shift_table;          /* fp32 [6, dim]: shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp */
+} EcadkBlockWeights;
+
+/* Creates a host-side handle (weight pointer table + TMA descriptor cache); allocates no device memory.
+ * `blocks` is a host array of num_layers entries (copied). */
+int ecadk_create(int device, const EcadkModelDesc* desc, const EcadkBlockWeights* blocks, ecadk_handle_t* out);
+int ecadk_destroy(ecadk_handle_t h);
+
+typedef struct {
+  int samples;      /* 2B with CFG */
+  int tokens;       /* N image tokens per sample */
+  int text_pad;     /* padded key count of the cross-attention (128) */
+  float* x;         /* fp32 [samples*tokens, dim] residual stream (in/out) */
+  void* xb;         /* bf16 scratch [samples*tokens, dim] */
+  void* h;          /* bf16 scratch [samples*tokens, dim] */
+  void* q;          /* bf16 scratch [samples, heads, tokens, 80]; padding must be zero */
+  void* k;
+  void* v;
+  void* attn_o;     /* bf16 scratch [samples*tokens, dim] */
+  void* ffh;        /* bf16 scratch [samples*tokens, ff_dim] */
+  const float* temb6;    /* fp32 [samples, 6*dim] adaLN-single output for this timestep */
+  const float* text_bias;/* fp32 [samples, text_pad] */
+  void* const* k2;       /* host array [num_layers]: bf16 [samples, heads, text_pad, 80] projected caption keys */
+  void* const* v2;       /* host array [num_layers] */
+  void* const* cache;    /* host array [num_layers*3]: bf16 [samples*tokens, dim] cached attn1/attn2/ff outputs */
+} EcadkBlocksArgs;
+
+/* Runs blocks 0..num_layers-1.  executed[b*3 + c] != 0 -> compute sub-block c in {attn1, attn2, ff} of block b and
+ * refresh its cache; 0 -> reuse the cached tensor (the caller has already applied the reference's
+ * "flag or cache is None" rule, cached_transformer_block.py:340-347,367-373).  `executed` is a HOST array.
+ * Replaces DiTScheduler.forward over the default sequential graph + CachedTransformerBlock.forward
+ * (ecad/schedulers/dit_scheduler/dit_scheduler.py:50-59, cached_transformer_block.py:167-324).
+ * n_launches (host, optional) receives the number of kernels enqueued. */
+int ecadk_pixart_blocks(ecadk_handle_t h, const EcadkBlocksArgs* args, const uint8_t* executed, int* n_launches,
+                        ecadk_stream_t stream);
+
+/* Projects caption embeddings once per generation: enc bf16 [samples*text_tokens, dim] -> k2[b], v2[b] for every
+ * block (head-major, zero padding preserved).  Hoists attn2.to_k/to_v, which the reference recomputes every step
+ * (cached_transformer_block.py:348-353 with encoder_hidden_states). */
+int ecadk_pixart_text_kv(ecadk_handle_t h, const void* enc, int samples, int text_tokens, int text_pad,
+                         void* const* k2, void* const* v2, int* n_launches, ecadk_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ECAD_B200_H_ */
