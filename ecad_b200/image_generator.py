@@ -1,0 +1,152 @@
+"""User-facing generator API, mirroring the reference's ImageGenerator classes for the hot path.
+
+Reference: /root/reference/ecad/image_generators/image_generator.py:29-495 (schedule loading :99-170, callback wiring
+:153-159, reset callback :193-202, timing :442-487) and pixart_image_generator.py:30-441 (pipeline construction
+:128-150, generate_images :314-393, generate_images_timed :395-441).  What is kept: the schedule-JSON contract, the
+callback ORDER (step counters first, reset LAST), seeds, and the call surface.  What is different: one resident model
+serves any number of schedules (``set_schedule``) instead of reloading weights per schedule
+(ecad/benchmark/generate_images.py:48-51), and the result is latents (the VAE / PIL stage is out of scope).
+"""
+from __future__ import annotations
+
+from pathlib import Path
+from typing import Any, Callable
+
+import torch
+
+from .pipeline import B200PixArtPipeline
+from .registry import ImageGeneratorRegistry
+from .schedule import PixArtCacheSchedule
+from .transformer import B200PixArtTransformer2D, SequentialDiTScheduler
+from .weights import PixArtConfig, random_init_state_dict
+
+
+class B200PixArtImageGenerator:
+    default_pipeline_name = "pixart_alpha"
+    text_tokens = 120
+
+    def __init__(
+        self,
+        schedule_path: Path | str | None = None,
+        start_seed: int = 0,
+        seed_step: int = 1,
+        additional_callbacks: list[Callable[..., None]] | None = None,
+        state_dict: dict[str, torch.Tensor] | None = None,
+        model_config: PixArtConfig = PixArtConfig(),
+        weight_seed: int = 0,
+        device: str = "cuda:0",
+        cache_schedule: PixArtCacheSchedule | None = None,
+    ):
+        if not torch.cuda.is_available():
+            # pixart_image_generator.py:55-56
+            raise ValueError("CUDA is not available.")
+        self.device = device
+        self.start_seed = start_seed
+        self.seed_step = seed_step
+        self.additional_callbacks = list(additional_callbacks or [])
+        self.model_config = model_config
+        self.height = self.width = model_config.sample_size * 8
+        self._state_dict = state_dict if state_dict is not None else random_init_state_dict(model_config, weight_seed)
+        self.diffusion_pipeline: B200PixArtPipeline | None = None
+        self._initialize_random_generator()
+        self._load_schedule(schedule_path, cache_schedule)
+
+    # image_generator.py:89-97 - always a CPU generator for reproducibility
+    def _initialize_random_generator(self) -> None:
+        self.random_generator = torch.Generator(device="cpu")
+        self.random_generator.manual_seed(self.start_seed)
+
+    # image_generator.py:99-170
+    def _load_schedule(self, schedule_path, cache_schedule: PixArtCacheSchedule | None) -> None:
+        if cache_schedule is None and schedule_path is not None:
+            import json
+
+            data = json.loads(Path(schedule_path).read_text())
+            if "dit_schedule" in data:
+                raise NotImplementedError("non-default DiT block graphs are out of scope (no shipped schedule uses one)")
+            try:
+                cache_schedule = PixArtCacheSchedule.from_dict(data)
+            except KeyError:
+                cache_schedule = None
+        if cache_schedule is None:
+            cache_schedule = PixArtCacheSchedule.default(20, self.model_config.num_layers)
+        self.cache_schedule = cache_schedule
+        self.num_inference_steps = cache_schedule.num_inference_steps
+        self.dit_scheduler = SequentialDiTScheduler(self.num_inference_steps)
+        self.config = cache_schedule.top_level_config or {}
+        pipe = (self.config.get("pipeline") or {})
+        self.gate_step = (pipe.get("kwargs") or {}).get("gate_step") if pipe.get("name") == "tgate" else None
+        self.callbacks = [self.dit_scheduler.per_step_callback, self.cache_schedule.per_step_callback]
+        self.callbacks.extend(self.additional_callbacks)
+        # IMPORTANT: reset MUST be LAST in the list (image_generator.py:156-159)
+        self.callbacks.append(self._reset_schedules_callback)
+        if self.diffusion_pipeline is not None:
+            tr = self.diffusion_pipeline.transformer
+            tr.cache_schedule = self.cache_schedule
+            tr.dit_scheduler = self.dit_scheduler
+            tr.reset_cache()
+            self.diffusion_pipeline.gate_step = self.gate_step
+
+    def set_schedule(self, cache_schedule: PixArtCacheSchedule) -> None:
+        """Swap the candidate schedule on the resident model (no weight reload)."""
+        self._load_schedule(None, cache_schedule)
+
+    # image_generator.py:193-202
+    def _reset_schedules_callback(self, step: int, timestep: Any, **kwargs: Any) -> None:
+        if step >= self.num_inference_steps - 1:
+            self.dit_scheduler.reset_step()
+            self.cache_schedule.reset_step()
+            if self.diffusion_pipeline is not None:
+                self.diffusion_pipeline.transformer.reset_cache()
+
+    def _call_callbacks(self, step: int, timestep: Any, **kwargs: Any) -> None:
+        for cb in self.callbacks:
+            cb(step, timestep, **kwargs)
+
+    def _call_callbacks_wrapper(self, step: int, timestep: Any, latents: torch.Tensor) -> None:
+        self._call_callbacks(step, timestep, latents=latents)
+
+    # pixart_image_generator.py:128-150
+    def create_diffusion_pipeline(self) -> B200PixArtPipeline:
+        if self.diffusion_pipeline is None:
+            tr = B200PixArtTransformer2D(self._state_dict, self.model_config, self.dit_scheduler, self.cache_schedule,
+                                         self.device)
+            self.diffusion_pipeline = B200PixArtPipeline(tr, gate_step=self.gate_step)
+        return self.diffusion_pipeline
+
+    # pixart_image_generator.py:314-393 (returns latents [images_per_prompt][B,4,h,w] instead of PIL images)
+    @torch.inference_mode()
+    def generate_images(self, prompt_embeds: dict[str, torch.Tensor], images_per_prompt: int = 1,
+                        height: int | None = None, width: int | None = None, **kwargs) -> list[torch.Tensor]:
+        pipe = self.create_diffusion_pipeline()
+        out = []
+        for i in range(images_per_prompt):
+            self.random_generator.manual_seed(self.start_seed + i * self.seed_step)
+            lat = pipe(
+                prompt=None, negative_prompt=None,
+                prompt_embeds=prompt_embeds["prompt_embeds"],
+                prompt_attention_mask=prompt_embeds["prompt_attention_mask"],
+                negative_prompt_embeds=prompt_embeds["negative_prompt_embeds"],
+                negative_prompt_attention_mask=prompt_embeds["negative_prompt_attention_mask"],
+                num_images_per_prompt=1, num_inference_steps=self.num_inference_steps,
+                generator=self.random_generator, return_dict=False, guidance_scale=4.5,
+                height=height or self.height, width=width or self.width,
+                callback=self._call_callbacks_wrapper, callback_steps=1,
+            )[0]
+            out.append(lat.clone())
+        return out
+
+    # pixart_image_generator.py:395-441: CUDA-event time of one pipeline call / batch size -> ms per image
+    @torch.inference_mode()
+    def generate_images_timed(self, prompt_embeds: dict[str, torch.Tensor], **kwargs) -> float:
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        self.generate_images(prompt_embeds, images_per_prompt=1)
+        end.record()
+        torch.cuda.synchronize()
+        return start.elapsed_time(end) / prompt_embeds["prompt_embeds"].shape[0]
+
+
+@ImageGeneratorRegistry.register("b200_pixart_alpha")
+class B200PixArtAlphaImageGenerator(B200PixArtImageGenerator):
+    """Selected by ``config.image_generator = "b200_pixart_alpha"`` in a schedule JSON (ecad/types.py:43-47)."""

@@ -1,0 +1,92 @@
+"""Population evaluation sharded over the GPUs of one box (BASELINE config 2).
+
+The NSGA-II driver of the reference evaluates a population of candidate schedules by shelling out to
+``ecad/benchmark/generate_images.py`` once per generation, which rebuilds the pipeline and reloads all weights for
+every candidate (/root/reference/ecad/genetic/train_nsga2_single_gpu.py:131-158,198-224;
+ecad/benchmark/generate_images.py:48-63).  Here one resident model per GPU serves every candidate assigned to it.
+
+A unit of work is (candidate schedule, prompt batch); units share nothing but read-only weights, so the path shards
+with NO data-path collective.  One process per GPU (torchrun); the only communication is the final gather of latents
+(16 KB / image) and per-candidate metrics to the search driver on rank 0 - NCCL over NVLink on GPUs, gloo in the
+CPU tests.
+"""
+from __future__ import annotations
+
+from typing import Callable, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def partition_lpt(costs: Sequence[float], world_size: int) -> list[list[int]]:
+    """Longest-processing-time-first assignment of units to ranks (deterministic; ties by index).
+
+    ``costs`` = analytic FLOPs of each candidate (ecad_b200.macs.flops_per_image) - cheap schedules and expensive
+    ones differ by >5x, so a round-robin split would leave GPUs idle."""
+    order = sorted(range(len(costs)), key=lambda i: (-float(costs[i]), i))
+    loads = [0.0] * world_size
+    parts: list[list[int]] = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda k: (loads[k], k))
+        parts[r].append(i)
+        loads[r] += float(costs[i])
+    return [sorted(p) for p in parts]
+
+
+def partition_round_robin(n_units: int, world_size: int) -> list[list[int]]:
+    return [list(range(r, n_units, world_size)) for r in range(world_size)]
+
+
+class PopulationEvaluator:
+    """Runs ``run_unit(i) -> Tensor`` for the units of this rank and gathers all results on every rank.
+
+    ``run_unit`` returns a tensor of a fixed shape (e.g. final latents ``[B, 4, h, w]``) on ``device``.
+    """
+
+    def __init__(self, rank: int = 0, world_size: int = 1, device: torch.device | str = "cpu",
+                 group: dist.ProcessGroup | None = None):
+        self.rank, self.world_size = rank, world_size
+        self.device = torch.device(device)
+        self.group = group
+        if world_size > 1 and not dist.is_initialized():
+            raise RuntimeError("torch.distributed must be initialised for world_size > 1")
+
+    def evaluate(self, n_units: int, run_unit: Callable[[int], torch.Tensor], costs: Sequence[float] | None = None,
+                 gather: bool = True) -> dict:
+        parts = (partition_lpt(costs, self.world_size) if costs is not None
+                 else partition_round_robin(n_units, self.world_size))
+        mine = parts[self.rank]
+        local = [run_unit(i) for i in mine]
+        out = {"assignment": parts, "local_indices": mine, "local": local}
+        if gather:
+            out["results"] = self.gather(local, parts, n_units)
+        return out
+
+    def gather(self, local: list[torch.Tensor], parts: list[list[int]], n_units: int) -> list[torch.Tensor | None]:
+        """All ranks receive every unit's result, ordered by unit index."""
+        if self.world_size == 1:
+            res: list[torch.Tensor | None] = [None] * n_units
+            for i, t in zip(parts[0], local):
+                res[i] = t
+            return res
+        max_units = max(len(p) for p in parts)
+        shape_t = torch.zeros(8, dtype=torch.int64, device=self.device)
+        if local:
+            shp = list(local[0].shape)
+            shape_t[0] = len(shp)
+            shape_t[1:1 + len(shp)] = torch.tensor(shp, dtype=torch.int64)
+        # ranks with no unit learn the unit shape from the others
+        dist.all_reduce(shape_t, op=dist.ReduceOp.MAX, group=self.group)
+        shp = [int(v) for v in shape_t[1:1 + int(shape_t[0])]]
+        dtype = local[0].dtype if local else torch.float32
+        buf = torch.zeros(max_units, *shp, dtype=dtype, device=self.device)
+        for j, t in enumerate(local):
+            buf[j].copy_(t)
+        allbuf = torch.empty(self.world_size, max_units, *shp, dtype=dtype, device=self.device)
+        dist.all_gather_into_tensor(allbuf.view(-1, *shp), buf, group=self.group)
+        res = [None] * n_units
+        for r, p in enumerate(parts):
+            for j, i in enumerate(p):
+                res[i] = allbuf[r, j]
+        return res

@@ -234,3 +234,24 @@ def trace_decisions(
         executed[s] = run
         have_cache |= run
     return executed
+
+
+def load_packed_schedules(path: Path | str) -> list[dict[str, Any]]:
+    """Rows of a packed schedule collection (format: tests/golden/make_schedule_fixtures.py)."""
+    import gzip
+
+    with gzip.open(path, "rb") as f:
+        return json.loads(f.read())["rows"]
+
+
+def schedule_from_packed(row: dict[str, Any]) -> PixArtCacheSchedule:
+    """Rebuild a PixArtCacheSchedule (reference JSON semantics) from one packed row."""
+    S, NB = row["S"], row["NB"]
+    bits = np.unpackbits(np.frombuffer(bytes.fromhex(row["bits"]), np.uint8))[: S * NB * 3]
+    custom = None
+    if row.get("custom"):
+        custom = {"name": row["custom"]["attn"], "kwargs": {"gate_step": row["custom"]["gate_step"]}}
+    return PixArtCacheSchedule.from_numpy(
+        bits.reshape(S, NB, 3).astype(np.bool_), S, NB, row["name"], custom_compute_attn=custom,
+        top_level_config=row.get("config") or {}, attributes=row.get("attributes") or {},
+    )

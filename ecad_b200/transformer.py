@@ -1,0 +1,410 @@
+"""B200PixArtTransformer2D - drop-in for the reference's ``PixArtTransformer2DEdited`` on the hot path.
+
+Same call surface as /root/reference/ecad/transformer_2d_models/pixart_transformer_2d_edited.py:
+``forward(hidden_states, encoder_hidden_states, timestep, added_cond_kwargs, cross_attention_kwargs,
+attention_mask, encoder_attention_mask, return_dict)`` (:160-170), ``reset_cache()`` (:155-158), attributes
+``cache_schedule`` / ``dit_scheduler`` / ``config`` / ``dtype``; constructed with ``(dit_scheduler, cache_schedule)``
+like ``from_pretrained(..., dit_scheduler=, cache_schedule=)`` (:104-117).  It reads ``cache_schedule.curr_step`` and
+never advances it (the pipeline callback does, ecad/image_generators/image_generator.py:153-159).
+
+Everything numerical runs in libecad_b200.so (hand-written sm_100a kernels); PyTorch only owns the buffers.  There is
+no CPU path: constructing the module without a CUDA device or without the built library raises.
+
+HBM layout (S = samples = 2B with CFG, N image tokens, D = 1152, H = 16, T text tokens padded to 128):
+  x        fp32 [S*N, D]      residual stream (fp32: see DESIGN.md "precision policy")
+  xb, h    bf16 [S*N, D]      bf16 shadow of x for the attn2 query projection; LN+modulate output
+  q, k, v  bf16 [S,H,N,80]    head-major, head_dim 72 zero-padded to 80 (one TMA box per (sample, head))
+  attn_o   bf16 [S*N, D]      attention output, A operand of the out projection
+  ffh      bf16 [S*N, 4D]     GELU hidden
+  cache    bf16 [L*3, S*N, D] the reference's cached_attn1/attn2/ff_output of all 28 blocks
+  k2, v2   bf16 [L][S,H,128,80] caption keys/values, projected once per generation
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from types import SimpleNamespace
+from typing import Any, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .registry import ComputeAttnRegistry, ComputeFFRegistry, DecisionContext
+from .schedule import PixArtCacheSchedule
+from .weights import PixArtConfig, random_init_state_dict
+
+TEXT_PAD = 128
+
+
+@dataclass
+class Transformer2DModelOutput:
+    """Stand-in for diffusers.models.modeling_outputs.Transformer2DModelOutput."""
+
+    sample: torch.Tensor
+
+
+class SequentialDiTScheduler:
+    """The default DiT schedule: the blocks in order, every step.
+
+    Mirrors the step-counter surface of /root/reference/ecad/schedulers/dit_scheduler/dit_scheduler.py:11-59.  Every
+    shipped schedule uses the default sequential graph; non-default block graphs are out of
+    scope and rejected by the image generator.
+    """
+
+    def __init__(self, num_inference_steps: int = 20, name: str = "default"):
+        self.num_inference_steps = num_inference_steps
+        self.name = name
+        self._last_step = -1
+
+    @property
+    def curr_step(self) -> int:
+        return self._last_step + 1
+
+    def per_step_callback(self, step: int, timestep: Any = None, **kwargs: Any) -> None:
+        self._last_step = step
+
+    def reset_step(self) -> None:
+        self._last_step = -1
+
+
+def _sincos_pos_embed(dim: int, grid_hw: tuple[int, int], base_size: int, interpolation_scale: float) -> torch.Tensor:
+    """2-D sin-cos table of diffusers' PatchEmbed (w-meshgrid first; each axis = concat(sin, cos))."""
+    gh, gw = grid_hw
+    ys = np.arange(gh, dtype=np.float32) / (gh / base_size) / interpolation_scale
+    xs = np.arange(gw, dtype=np.float32) / (gw / base_size) / interpolation_scale
+    col = np.tile(xs[None, :], (gh, 1)).reshape(-1)  # varies along w
+    row = np.tile(ys[:, None], (1, gw)).reshape(-1)  # varies along h
+    quarter = dim // 4
+    omega = 1.0 / 10000 ** (np.arange(quarter, dtype=np.float64) / quarter)
+
+    def axis(pos):
+        ang = pos.astype(np.float64)[:, None] * omega[None, :]
+        return np.concatenate([np.sin(ang), np.cos(ang)], axis=1)
+
+    return torch.from_numpy(np.concatenate([axis(col), axis(row)], axis=1)).float()
+
+
+class B200PixArtTransformer2D:
+    """PixArt-alpha/sigma transformer with layer-wise feature caching, executed by libecad_b200.so."""
+
+    def __init__(
+        self,
+        state_dict: dict[str, torch.Tensor],
+        config: PixArtConfig = PixArtConfig(),
+        dit_scheduler: SequentialDiTScheduler | None = None,
+        cache_schedule: PixArtCacheSchedule | None = None,
+        device: str | torch.device = "cuda:0",
+    ):
+        if dit_scheduler is None:
+            # pixart_transformer_2d_edited.py:86-87
+            raise ValueError("A DiTScheduler object must be provided.")
+        if not torch.cuda.is_available():
+            raise RuntimeError("B200PixArtTransformer2D needs a CUDA device; there is no CPU path")
+        self.device = torch.device(device)
+        self._lib = _lib.load()
+        _lib.check(self._lib.ecadk_device_check(self.device.index or 0), "device_check")
+        self.cfg = config
+        self.config = SimpleNamespace(
+            sample_size=config.sample_size, in_channels=config.in_channels, out_channels=config.out_channels,
+            patch_size=config.patch_size, num_attention_heads=config.num_attention_heads,
+            attention_head_dim=config.attention_head_dim, num_layers=config.num_layers,
+            cross_attention_dim=config.cross_attention_dim, caption_channels=config.caption_channels,
+            norm_eps=config.norm_eps,
+        )
+        self.dtype = torch.bfloat16
+        self.dit_scheduler = dit_scheduler
+        self.cache_schedule = cache_schedule if cache_schedule is not None else PixArtCacheSchedule.default(
+            dit_scheduler.num_inference_steps, config.num_layers)
+        if config.attention_head_dim != _lib.HEAD_DIM:
+            raise ValueError("libecad_b200 is specialised for attention_head_dim = 72")
+        if config.resolved_additional_conditions:
+            raise NotImplementedError("1024-MS additional conditions (resolution/aspect-ratio embedders) not built yet")
+        self._pack_weights(state_dict)
+        self._ws: dict[str, Any] = {}
+        self._ws_key: tuple | None = None
+        self._has_cache = np.zeros((config.num_layers, 3), dtype=np.bool_)
+        self._text_key: tuple | None = None
+        self.last_executed: np.ndarray | None = None
+        self.launches = 0  # kernels of libecad_b200 enqueued so far (bench.py's gpu_launches)
+
+    # ------------------------------------------------------------------------------------------------
+    @classmethod
+    def from_random_init(cls, dit_scheduler, cache_schedule=None, config: PixArtConfig = PixArtConfig(),
+                         seed: int = 0, device="cuda:0") -> "B200PixArtTransformer2D":
+        return cls(random_init_state_dict(config, seed), config, dit_scheduler, cache_schedule, device)
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, dit_scheduler=None, cache_schedule=None, **kwargs):
+        """Same keyword surface as the reference's from_pretrained (:104-117); loads a diffusers-format state dict
+        (``diffusion_pytorch_model.safetensors`` / ``.bin``) from a local directory - there is no network here."""
+        from pathlib import Path
+
+        path = Path(pretrained_model_name_or_path)
+        cand = [path / "diffusion_pytorch_model.bin", path / "transformer" / "diffusion_pytorch_model.bin"]
+        for f in cand:
+            if f.exists():
+                sd = torch.load(f, map_location="cpu")
+                return cls(sd, kwargs.get("config", PixArtConfig()), dit_scheduler, cache_schedule,
+                           kwargs.get("device", "cuda:0"))
+        raise FileNotFoundError(f"no diffusers-format transformer weights under {path}")
+
+    def _pack_weights(self, sd: dict[str, torch.Tensor]) -> None:
+        dev, cfg = self.device, self.cfg
+        D = cfg.inner_dim
+
+        def f32(t):
+            return t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+        def bf16(t):
+            return t.detach().to(device=dev, dtype=torch.bfloat16).contiguous()
+
+        w = {}
+        p = cfg.patch_size
+        w["patch_wt"] = f32(sd["pos_embed.proj.weight"].reshape(D, cfg.in_channels * p * p).t())
+        w["patch_b"] = f32(sd["pos_embed.proj.bias"])
+        for i, nm in enumerate(("linear_1", "linear_2")):
+            w[f"t_w{i}"] = f32(sd[f"adaln_single.emb.timestep_embedder.{nm}.weight"])
+            w[f"t_b{i}"] = f32(sd[f"adaln_single.emb.timestep_embedder.{nm}.bias"])
+        w["ada_w"] = f32(sd["adaln_single.linear.weight"])
+        w["ada_b"] = f32(sd["adaln_single.linear.bias"])
+        w["cap_w1"] = bf16(sd["caption_projection.linear_1.weight"])
+        w["cap_b1"] = f32(sd["caption_projection.linear_1.bias"])
+        w["cap_w2"] = bf16(sd["caption_projection.linear_2.weight"])
+        w["cap_b2"] = f32(sd["caption_projection.linear_2.bias"])
+        w["final_table"] = f32(sd["scale_shift_table"])
+        w["final_w"] = f32(sd["proj_out.weight"])
+        w["final_b"] = f32(sd["proj_out.bias"])
+        self.w = w
+        self.blocks_w: list[dict[str, torch.Tensor]] = []
+        arr = (_lib.EcadkBlockWeights * cfg.num_layers)()
+        for b in range(cfg.num_layers):
+            pre = f"transformer_blocks.{b}"
+            bw = {
+                "w_qkv1": bf16(torch.cat([sd[f"{pre}.attn1.to_{n}.weight"] for n in "qkv"], 0)),
+                "b_qkv1": f32(torch.cat([sd[f"{pre}.attn1.to_{n}.bias"] for n in "qkv"], 0)),
+                "w_out1": bf16(sd[f"{pre}.attn1.to_out.0.weight"]),
+                "b_out1": f32(sd[f"{pre}.attn1.to_out.0.bias"]),
+                "w_q2": bf16(sd[f"{pre}.attn2.to_q.weight"]),
+                "b_q2": f32(sd[f"{pre}.attn2.to_q.bias"]),
+                "w_kv2": bf16(torch.cat([sd[f"{pre}.attn2.to_{n}.weight"] for n in "kv"], 0)),
+                "b_kv2": f32(torch.cat([sd[f"{pre}.attn2.to_{n}.bias"] for n in "kv"], 0)),
+                "w_out2": bf16(sd[f"{pre}.attn2.to_out.0.weight"]),
+                "b_out2": f32(sd[f"{pre}.attn2.to_out.0.bias"]),
+                "w_ff1": bf16(sd[f"{pre}.ff.net.0.proj.weight"]),
+                "b_ff1": f32(sd[f"{pre}.ff.net.0.proj.bias"]),
+                "w_ff2": bf16(sd[f"{pre}.ff.net.2.weight"]),
+                "b_ff2": f32(sd[f"{pre}.ff.net.2.bias"]),
+                "scale_shift_table": f32(sd[f"{pre}.scale_shift_table"]),
+            }
+            self.blocks_w.append(bw)
+            for name, t in bw.items():
+                setattr(arr[b], name, t.data_ptr())
+        desc = _lib.EcadkModelDesc(cfg.num_layers, D, cfg.num_attention_heads, 4 * D, cfg.norm_eps)
+        handle = C.c_void_p()
+        _lib.check(self._lib.ecadk_create(self.device.index or 0, C.byref(desc), arr, C.byref(handle)), "create")
+        self._handle = handle
+        self._pos_cache: dict[tuple[int, int], torch.Tensor] = {}
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h:
+            try:
+                self._lib.ecadk_destroy(h)
+            except Exception:
+                pass
+
+    # ------------------------------------------------------------------------------------------------
+    def _pos_table(self, hp: int, wp: int) -> torch.Tensor:
+        key = (hp, wp)
+        if key not in self._pos_cache:
+            base = self.cfg.sample_size // self.cfg.patch_size
+            self._pos_cache[key] = _sincos_pos_embed(
+                self.cfg.inner_dim, (hp, wp), base, self.cfg.resolved_interpolation_scale).to(self.device)
+        return self._pos_cache[key]
+
+    def _workspace(self, S: int, N: int, T: int, hl: int, wl: int) -> dict[str, Any]:
+        key = (S, N, T, hl, wl)
+        if self._ws_key == key:
+            return self._ws
+        cfg, dev = self.cfg, self.device
+        D, H, L = cfg.inner_dim, cfg.num_attention_heads, cfg.num_layers
+        bf, f32 = torch.bfloat16, torch.float32
+        self._ws = {}  # drop the old workspace before allocating the new one
+        ws: dict[str, Any] = {}
+        M = S * N
+        ws["x"] = torch.empty(M, D, device=dev, dtype=f32)
+        for n in ("xb", "h", "attn_o"):
+            ws[n] = torch.empty(M, D, device=dev, dtype=bf)
+        for n in ("q", "k", "v"):
+            ws[n] = torch.zeros(S, H, N, _lib.HEAD_PAD, device=dev, dtype=bf)  # padding columns stay zero
+        ws["ffh"] = torch.empty(M, 4 * D, device=dev, dtype=bf)
+        ws["cache"] = torch.empty(L * 3, M, D, device=dev, dtype=bf)
+        ws["k2"] = torch.zeros(L, S, H, TEXT_PAD, _lib.HEAD_PAD, device=dev, dtype=bf)
+        ws["v2"] = torch.zeros(L, S, H, TEXT_PAD, _lib.HEAD_PAD, device=dev, dtype=bf)
+        ws["text_bias"] = torch.empty(S, TEXT_PAD, device=dev, dtype=f32)
+        ws["enc_bf"] = torch.empty(S * T, cfg.caption_channels, device=dev, dtype=bf)
+        ws["enc_h"] = torch.empty(S * T, D, device=dev, dtype=bf)
+        ws["enc_p"] = torch.empty(S * T, D, device=dev, dtype=bf)
+        ws["t_proj"] = torch.empty(S, 256, device=dev, dtype=f32)
+        ws["t_e1"] = torch.empty(S, D, device=dev, dtype=f32)
+        ws["t_emb"] = torch.empty(S, D, device=dev, dtype=f32)
+        ws["temb6"] = torch.empty(S, 6 * D, device=dev, dtype=f32)
+        ws["out"] = torch.empty(S, cfg.out_channels, hl, wl, device=dev, dtype=f32)
+        ptrs = C.c_void_p * L
+        ws["k2_ptrs"] = ptrs(*[ws["k2"][b].data_ptr() for b in range(L)])
+        ws["v2_ptrs"] = ptrs(*[ws["v2"][b].data_ptr() for b in range(L)])
+        ws["cache_ptrs"] = (C.c_void_p * (L * 3))(*[ws["cache"][i].data_ptr() for i in range(L * 3)])
+        args = _lib.EcadkBlocksArgs()
+        args.samples, args.tokens, args.text_pad = S, N, TEXT_PAD
+        for n in ("x", "xb", "h", "q", "k", "v", "attn_o", "ffh", "temb6", "text_bias"):
+            setattr(args, n, ws[n].data_ptr())
+        args.k2 = C.cast(ws["k2_ptrs"], C.POINTER(C.c_void_p))
+        args.v2 = C.cast(ws["v2_ptrs"], C.POINTER(C.c_void_p))
+        args.cache = C.cast(ws["cache_ptrs"], C.POINTER(C.c_void_p))
+        ws["args"] = args
+        self._ws, self._ws_key = ws, key
+        # a new workspace means new (empty) cache tensors
+        self._has_cache[:] = False
+        self._text_key = None
+        return ws
+
+    # ------------------------------------------------------------------------------------------------
+    def reset_cache(self) -> None:
+        """pixart_transformer_2d_edited.py:155-158 + cached_transformer_block.py:120-123: drop every cached tensor.
+        The HBM slots are kept (no allocator churn); only their validity is cleared."""
+        self._has_cache[:] = False
+        self._text_key = None
+
+    def _decide(self) -> np.ndarray:
+        """Decision row of the current step: the reference's per-sub-block rule, evaluated through the same
+        registries (cached_transformer_block.py:125-165 dispatch, :340-347 / :367-373 rule)."""
+        sched = self.cache_schedule
+        step = sched.curr_step
+        L = self.cfg.num_layers
+        executed = np.zeros((L, 3), dtype=np.uint8)
+        row = sched.schedule[step]
+        for b in range(L):
+            entry = row[str(b)]
+            attn_cfg = entry.get("custom_compute_attn", {}) or {}
+            ff_cfg = entry.get("custom_compute_ff", {}) or {}
+            attn_fn = ComputeAttnRegistry.get(attn_cfg.get("name"), False)
+            ff_fn = ComputeFFRegistry.get(ff_cfg.get("name"), False)
+            for c, comp in enumerate(("attn1", "attn2")):
+                ctx = DecisionContext(b, comp, bool(sched.get_recompute(str(b), comp)), not self._has_cache[b, c],
+                                      step, dict(attn_cfg.get("kwargs", {}) or {}))
+                executed[b, c] = attn_fn(ctx)
+            ctx = DecisionContext(b, "ff", bool(sched.get_recompute(str(b), "ff")), not self._has_cache[b, 2], step,
+                                  dict(ff_cfg.get("kwargs", {}) or {}))
+            executed[b, 2] = ff_fn(ctx)
+        return executed
+
+    # ------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(
+        self,
+        hidden_states: torch.Tensor,
+        encoder_hidden_states: Optional[torch.Tensor] = None,
+        timestep: Optional[torch.Tensor] = None,
+        added_cond_kwargs: dict[str, torch.Tensor] | None = None,
+        cross_attention_kwargs: dict[str, Any] | None = None,
+        attention_mask: Optional[torch.Tensor] = None,
+        encoder_attention_mask: Optional[torch.Tensor] = None,
+        return_dict: bool = True,
+    ):
+        cfg, lib, w = self.cfg, self._lib, self.w
+        if attention_mask is not None:
+            raise NotImplementedError("self-attention masks are never passed on the PixArt path")
+        if encoder_hidden_states is None or timestep is None:
+            raise ValueError("encoder_hidden_states and timestep are required")
+        dev = self.device
+        S, Cin, hl, wl = hidden_states.shape
+        p = cfg.patch_size
+        hp, wp = hl // p, wl // p
+        N = hp * wp
+        T = encoder_hidden_states.shape[1]
+        D = cfg.inner_dim
+        if N != 256:
+            raise NotImplementedError(f"{N} image tokens: this build covers 256x256 (N=256) self-attention only")
+        if T > TEXT_PAD:
+            raise NotImplementedError(f"{T} text tokens > {TEXT_PAD}: PixArt-sigma (T=300) not built yet")
+        ws = self._workspace(S, N, T, hl, wl)
+        st = _lib.stream_ptr()
+        launches = 0
+
+        # 1. input: patch embed + position table (pixart_transformer_2d_edited.py:306)
+        lat = hidden_states.to(device=dev, dtype=torch.float32).contiguous()
+        pos = self._pos_table(hp, wp)
+        _lib.check(lib.ecadk_patch_embed(lat.data_ptr(), w["patch_wt"].data_ptr(), w["patch_b"].data_ptr(),
+                                         pos.data_ptr(), ws["x"].data_ptr(), S, Cin, hl, wl, D, st), "patch_embed")
+        # adaLN-single: sinusoid -> MLP -> SiLU -> Linear(D, 6D)  (:308-313)
+        t32 = timestep.to(device=dev, dtype=torch.float32).expand(S).contiguous()
+        _lib.check(lib.ecadk_timestep_sinusoid(t32.data_ptr(), ws["t_proj"].data_ptr(), S, 256, st), "sinusoid")
+        _lib.check(lib.ecadk_small_linear(ws["t_proj"].data_ptr(), w["t_w0"].data_ptr(), w["t_b0"].data_ptr(),
+                                          ws["t_e1"].data_ptr(), S, 256, D, D, 0, 0, 0, st), "t_mlp1")
+        _lib.check(lib.ecadk_small_linear(ws["t_e1"].data_ptr(), w["t_w1"].data_ptr(), w["t_b1"].data_ptr(),
+                                          ws["t_emb"].data_ptr(), S, D, D, D, 0, 1, 0, st), "t_mlp2")
+        _lib.check(lib.ecadk_small_linear(ws["t_emb"].data_ptr(), w["ada_w"].data_ptr(), w["ada_b"].data_ptr(),
+                                          ws["temb6"].data_ptr(), S, D, 6 * D, 6 * D, 0, 1, 0, st), "adaln_linear")
+        launches += 5
+
+        # caption projection + per-block K/V: step-invariant, done once per generation (:315-321; hoisted)
+        mask = encoder_attention_mask
+        # identity = (pointer, shape); the projections are also redone at step 0 and after reset_cache(), so a new
+        # generation never sees stale keys even if the allocator hands back the same address
+        text_key = (encoder_hidden_states.data_ptr(), tuple(encoder_hidden_states.shape),
+                    None if mask is None else (mask.data_ptr(), tuple(mask.shape)))
+        if self._text_key != text_key or self.cache_schedule.curr_step == 0:
+            enc = encoder_hidden_states.to(device=dev)
+            if enc.dtype == torch.float32:
+                enc = enc.contiguous()
+                _lib.check(lib.ecadk_cast_f32_bf16(enc.data_ptr(), ws["enc_bf"].data_ptr(), enc.numel(), st), "cast")
+                launches += 1
+            else:
+                ws["enc_bf"].copy_(enc.reshape(S * T, -1))
+            _lib.gemm_bias(ws["enc_bf"], w["cap_w1"], w["cap_b1"], ws["enc_h"], gelu=True)
+            _lib.gemm_bias(ws["enc_h"], w["cap_w2"], w["cap_b2"], ws["enc_p"], gelu=False)
+            n_l = C.c_int(0)
+            _lib.check(lib.ecadk_pixart_text_kv(self._handle, ws["enc_p"].data_ptr(), S, T, TEXT_PAD,
+                                                C.cast(ws["k2_ptrs"], C.POINTER(C.c_void_p)),
+                                                C.cast(ws["v2_ptrs"], C.POINTER(C.c_void_p)), C.byref(n_l), st),
+                       "text_kv")
+            launches += 2 + n_l.value
+            # mask -> additive bias (:255-291); padding keys get -inf
+            if mask is None:
+                ws["text_bias"].zero_()
+                ws["text_bias"][:, T:] = float("-inf")
+            elif mask.ndim == 2:
+                m32 = mask.to(device=dev, dtype=torch.float32).contiguous()
+                _lib.check(lib.ecadk_mask_bias(m32.data_ptr(), ws["text_bias"].data_ptr(), S, T, TEXT_PAD, st),
+                           "mask_bias")
+                launches += 1
+            else:  # already a (S,1,T) bias
+                ws["text_bias"][:, :T] = mask.to(device=dev, dtype=torch.float32).reshape(S, T)
+                ws["text_bias"][:, T:] = float("-inf")
+            self._text_key = text_key
+
+        # 2. blocks under the decision row of the current step
+        executed = self._decide()
+        self.last_executed = executed
+        ex = np.ascontiguousarray(executed.reshape(-1))
+        n_l = C.c_int(0)
+        _lib.check(lib.ecadk_pixart_blocks(self._handle, C.byref(ws["args"]),
+                                           ex.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(n_l), st), "pixart_blocks")
+        launches += n_l.value
+        self._has_cache |= executed.astype(np.bool_)
+
+        # 3. output (:332-376)
+        _lib.check(lib.ecadk_final_layer(ws["x"].data_ptr(), w["final_table"].data_ptr(), ws["t_emb"].data_ptr(),
+                                         w["final_w"].data_ptr(), w["final_b"].data_ptr(), ws["out"].data_ptr(), S,
+                                         hp, wp, D, cfg.out_channels, cfg.norm_eps, st), "final_layer")
+        launches += 1
+        self.launches += launches
+        out = ws["out"]
+        if hidden_states.dtype != torch.float32:
+            out = out.to(hidden_states.dtype)
+        if not return_dict:
+            return (out,)
+        return Transformer2DModelOutput(sample=out)
+
+    __call__ = forward

@@ -403,7 +403,7 @@ class OracleDPMSolver:
                  beta_start: float = 1e-4, beta_end: float = 0.02):
         betas = torch.linspace(beta_start, beta_end, num_train_timesteps, dtype=torch.float32)
         alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
-        sig = np.array(((1 - alphas_cumprod) / alphas_cumprod) ** 0.5)
+        sig = (((1 - alphas_cumprod) / alphas_cumprod) ** 0.5).numpy()
         ts = np.linspace(0, num_train_timesteps - 1, num_inference_steps + 1).round()[::-1][:-1].copy().astype(np.int64)
         sig = np.interp(ts, np.arange(0, len(sig)), sig)
         self.sigmas = torch.from_numpy(np.concatenate([sig, [0.0]]).astype(np.float32))
