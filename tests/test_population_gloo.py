@@ -1,0 +1,70 @@
+"""N>1 host logic on CPU: world_size-2 gloo run of the population evaluator (partitioning + final gather)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from ecad_b200.population import PopulationEvaluator, partition_lpt, partition_round_robin
+
+
+def test_partition_lpt_balances_and_is_deterministic():
+    costs = [10, 1, 1, 1, 9, 2, 2, 8]
+    parts = partition_lpt(costs, 3)
+    assert sorted(i for p in parts for i in p) == list(range(8))
+    loads = [sum(costs[i] for i in p) for p in parts]
+    assert max(loads) - min(loads) <= 2
+    assert parts == partition_lpt(costs, 3)
+    assert partition_round_robin(5, 2) == [[0, 2, 4], [1, 3]]
+    assert partition_lpt([3, 2, 1], 1) == [[0, 1, 2]]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ev = PopulationEvaluator(rank, world, "cpu")
+        costs = [5.0, 1.0, 4.0, 2.0, 3.0]
+
+        def run_unit(i):
+            return torch.full((2, 4, 3, 3), float(i)) + rank * 0.0
+
+        out = ev.evaluate(len(costs), run_unit, costs)
+        ok = all(torch.equal(t, torch.full((2, 4, 3, 3), float(i))) for i, t in enumerate(out["results"]))
+        mine = out["local_indices"]
+        q.put((rank, ok, mine, out["assignment"]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gather():
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _, _ in res)
+    assert res[0][3] == res[1][3]  # both ranks computed the same assignment
+    assert sorted(res[0][2] + res[1][2]) == [0, 1, 2, 3, 4]  # every unit ran exactly once
+    assert res[0][2] and res[1][2]
+
+
+def test_single_rank_gather_is_identity():
+    ev = PopulationEvaluator(0, 1, "cpu")
+    out = ev.evaluate(3, lambda i: torch.tensor([i]))
+    assert [int(t) for t in out["results"]] == [0, 1, 2]
