@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -160,17 +161,31 @@ int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
   return check_launch("gemm_bf16_kernel");
 }
 
-// Tile-N choice: the widest tile that divides N and still gives every SM work; ties go to fewer partial waves.
-int pick_bn(int M, int N) {
-  const int m_tiles = (M + kGemmBM - 1) / kGemmBM;
+template <int BN, int EPI>
+int launch_gemm2_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BN>;
+  static bool configured = false;
+  auto kern = gemm2_bf16_kernel<BN, EPI>;
+  if (!configured) {
+    ECADK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int tiles = ((p.M + 2 * kGemmBM - 1) / (2 * kGemmBM)) * (p.N / BN);
+  const int pairs = num_sms() / 2;
+  const int grid = 2 * (tiles < pairs ? tiles : pairs);
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  return check_launch("gemm2_bf16_kernel");
+}
+
+// Tile-N choice: among the widths that divide N, minimise waves x per-tile time (~ BN + fixed overhead).
+int pick_bn(int m_tiles, int N, int workers) {
   const int cands[3] = {256, 192, 128};
   int best = 0;
   double best_cost = 1e30;
   for (int bn : cands) {
     if (N % bn) continue;
     const int tiles = m_tiles * (N / bn);
-    const int waves = (tiles + num_sms() - 1) / num_sms();
-    // cost ~ waves * per-tile time (proportional to bn, plus a fixed per-tile overhead)
+    const int waves = (tiles + workers - 1) / workers;
     const double cost = static_cast<double>(waves) * (bn + 24.0);
     if (cost < best_cost) {
       best_cost = cost;
@@ -180,6 +195,18 @@ int pick_bn(int M, int N) {
   return best;
 }
 
+// ECADK_GEMM_CTA_GROUP=1|2 forces the 1-CTA / 2-CTA kernel (A/B measurements); default: 2-CTA when the problem has
+// enough 256-row tiles to fill every CTA pair, else the 1-CTA kernel (small-batch latency configuration).
+int gemm_cta_group(int M, int N) {
+  static int forced = [] {
+    const char* e = getenv("ECADK_GEMM_CTA_GROUP");
+    return e ? atoi(e) : 0;
+  }();
+  if (forced == 1 || forced == 2) return forced;
+  const int m2 = (M + 2 * kGemmBM - 1) / (2 * kGemmBM);
+  return (m2 * (N / 128) >= num_sms() / 2) ? 2 : 1;
+}
+
 template <int EPI>
 int launch_gemm(const void* a, const void* w, GemmParams& p, cudaStream_t stream) {
   ECADK_REQUIRE(a && w, "gemm: null operand");
@@ -187,13 +214,23 @@ int launch_gemm(const void* a, const void* w, GemmParams& p, cudaStream_t stream
   ECADK_REQUIRE(p.K % kGemmBK == 0, "gemm: K=%d must be a multiple of %d", p.K, kGemmBK);
   ECADK_REQUIRE(p.N % 128 == 0, "gemm: N=%d must be a multiple of 128", p.N);
   ECADK_REQUIRE(aligned16(a) && aligned16(w), "gemm: operands must be 16-byte aligned");
-  const int bn = pick_bn(p.M, p.N);
-  ECADK_REQUIRE(bn != 0, "gemm: no tile width divides N=%d", p.N);
+  const int group = gemm_cta_group(p.M, p.N);
   CUtensorMap ta, tb;
   int rc = make_tmap_bf16(&ta, a, p.M, p.K, p.K, kGemmBM, kGemmBK, 128);
   if (rc) return rc;
-  rc = make_tmap_bf16(&tb, w, p.N, p.K, p.K, bn, kGemmBK, 128);
-  if (rc) return rc;
+  if (group == 2) {
+    const int bn = pick_bn((p.M + 2 * kGemmBM - 1) / (2 * kGemmBM), p.N, num_sms() / 2);
+    ECADK_REQUIRE(bn != 0, "gemm: no tile width divides N=%d", p.N);
+    if ((rc = make_tmap_bf16(&tb, w, p.N, p.K, p.K, bn / 2, kGemmBK, 128))) return rc;
+    switch (bn) {
+      case 256: return launch_gemm2_inst<256, EPI>(ta, tb, p, stream);
+      case 192: return launch_gemm2_inst<192, EPI>(ta, tb, p, stream);
+      default: return launch_gemm2_inst<128, EPI>(ta, tb, p, stream);
+    }
+  }
+  const int bn = pick_bn((p.M + kGemmBM - 1) / kGemmBM, p.N, num_sms());
+  ECADK_REQUIRE(bn != 0, "gemm: no tile width divides N=%d", p.N);
+  if ((rc = make_tmap_bf16(&tb, w, p.N, p.K, p.K, bn, kGemmBK, 128))) return rc;
   switch (bn) {
     case 256: return launch_gemm_inst<256, EPI>(ta, tb, p, stream);
     case 192: return launch_gemm_inst<192, EPI>(ta, tb, p, stream);
@@ -277,11 +314,20 @@ int launch_residual_ln(const EcadkResidualLnArgs& a, cudaStream_t stream) {
   p.scale_temb = a.scale_temb;
   p.temb_stride = a.temb_stride;
   p.eps = a.eps;
-  const int grid = (a.rows + 7) / 8;
+  ECADK_REQUIRE(a.tokens % kRlnRowsPerBlock == 0, "residual_ln: tokens=%d must be a multiple of %d", a.tokens,
+                kRlnRowsPerBlock);
+  const int grid = (a.rows + kRlnRowsPerBlock - 1) / kRlnRowsPerBlock;
+  const int smem = (2 + a.n_reuse) * a.dim * 4;
   if (a.dim == 1152) {
-    residual_ln_kernel<9><<<grid, 256, 0, stream>>>(p);
+    residual_ln_kernel<9><<<grid, 256, smem, stream>>>(p);
   } else {
-    residual_ln_kernel<24><<<grid, 256, 0, stream>>>(p);
+    static bool configured = false;
+    if (!configured) {
+      ECADK_CHECK_CUDA(cudaFuncSetAttribute(residual_ln_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (2 + ECADK_MAX_REUSE) * 3072 * 4));
+      configured = true;
+    }
+    residual_ln_kernel<24><<<grid, 256, smem, stream>>>(p);
   }
   return check_launch("residual_ln_kernel");
 }
@@ -339,7 +385,7 @@ int ecadk_small_linear(const float* x, const float* w, const float* b, float* y,
                        int y_off, int act_in, int accumulate, ecadk_stream_t stream) {
   ECADK_REQUIRE(x && w && b && y && samples > 0 && k > 0 && o > 0, "small_linear: bad args");
   SmallLinearParams p{x, w, b, y, samples, k, o, ldy, y_off, act_in, accumulate};
-  small_linear_kernel<<<(o + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  small_linear_kernel<<<dim3((o + 7) / 8, (samples + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   return check_launch("small_linear_kernel");
 }
 
@@ -361,13 +407,13 @@ int ecadk_mask_bias(const float* mask, float* bias, int samples, int t, int t_pa
   return check_launch("mask_bias_kernel");
 }
 
-int ecadk_final_layer(const float* x, const float* table, const float* emb, const float* w, const float* bias,
-                      float* out, int samples, int hp, int wp, int dim, int out_channels, float eps,
+int ecadk_final_layer(const float* x, const float* table, const float* emb, int emb_stride, const float* w,
+                      const float* bias, float* out, int samples, int hp, int wp, int dim, int out_channels, float eps,
                       ecadk_stream_t stream) {
   ECADK_REQUIRE(x && table && emb && w && bias && out, "final_layer: null pointer");
   ECADK_REQUIRE(dim == 1152, "final_layer: dim=%d (supported: 1152)", dim);
-  FinalLayerParams p{x, table, emb, w, bias, out, samples * hp * wp, hp * wp, wp, hp, out_channels, 4 * out_channels, eps};
-  final_layer_kernel<9><<<(p.M + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  FinalLayerParams p{x, table, emb, emb_stride, w, bias, out, samples * hp * wp, hp * wp, wp, hp, out_channels, 4 * out_channels, eps};
+  final_layer_kernel<9><<<(p.M + 15) / 16, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   return check_launch("final_layer_kernel");
 }
 
@@ -481,7 +527,8 @@ int ecadk_pixart_blocks(ecadk_handle_t h, const EcadkBlocksArgs* a, const uint8_
   ECADK_REQUIRE(h && a && executed, "pixart_blocks: null argument");
   const EcadkModelDesc& d = h->desc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const int D = d.dim, M = a->samples * a->tokens, S6 = 6 * D;
+  const int D = d.dim, M = a->samples * a->tokens, S6 = a->temb_stride;
+  ECADK_REQUIRE(S6 == 0 || S6 == 6 * D, "pixart_blocks: temb_stride must be 0 or 6*dim");
   ECADK_REQUIRE(a->tokens == 256, "pixart_blocks: tokens=%d (this build covers N=256 self-attention)", a->tokens);
   int launches = 0;
   int rc;

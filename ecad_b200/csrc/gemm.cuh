@@ -2,7 +2,7 @@
 //
 //   warp 0 (1 thread)  : TMA producer   - cp.async.bulk.tensor A/W tiles into a STAGES-deep smem ring
 //   warp 1 (1 thread)  : MMA issuer     - tcgen05.mma (M=128, N=BN, K=16) into one of two TMEM accumulators
-//   warps 2..5         : epilogue       - tcgen05.ld the finished accumulator, fused epilogue, global stores,
+//   warps 2..9         : epilogue       - tcgen05.ld the finished accumulator, fused epilogue, global stores,
 //                                         overlapped with the next tile's main loop (TMEM double buffering)
 //
 // Both operands are K-major (PyTorch nn.Linear weight is [out,in] = [N,K]), staged with the 128-byte TMA/UMMA swizzle.
@@ -42,18 +42,129 @@ struct GemmParams {
 
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kEpiWarps = 8;
+constexpr int kEpiPitch = 36;                           // floats; see epilogue_chunk
+constexpr int kEpiStageBytes = kEpiWarps * 32 * kEpiPitch * 4;  // one 32x32 fp32 transpose tile per epilogue warp
 
 template <int BN>
 struct GemmCfg {
   static constexpr int kStageA = kGemmBM * kGemmBK * 2;  // 16 KB
   static constexpr int kStageB = BN * kGemmBK * 2;
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = (BN <= 128) ? 6 : (BN <= 192 ? 5 : 4);
+  static constexpr int kStages = (BN <= 128) ? 5 : (BN <= 192 ? 4 : 3);
   static constexpr int kAccStride = 256;  // TMEM column offset between the two accumulators
   static constexpr int kTmemCols = 512;
-  static constexpr int kSmemBytes = kStages * kStage + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStage + kEpiStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
+
+
+// Epilogue of one 128 x BN accumulator tile, executed by 8 warps: warp e covers TMEM lane quarter (e & 3) - the
+// rows 32*(e&3) .. +31 of the tile - and every second 32-column chunk (parity e >> 2).
+//
+// tcgen05.ld hands each thread one ROW (32 consecutive columns); storing that way makes every global access touch 32
+// different rows.  Each chunk is therefore transposed through a padded smem tile (pitch 36 floats: conflict-free for
+// 128-bit accesses in both directions) so that one warp instruction covers 4 rows x 32 columns = 4 full 128-byte
+// lines of the fp32 stream; bias / gate vectors are loaded once per chunk, row -> (sample, token) maps once per tile,
+// and the residual-stream loads of a chunk are issued before its transpose so their latency overlaps it.
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_t t_row, float* stage, const int lane,
+                                              const int parity, const int row_base, const int n0) {
+  const int cg = lane & 7, rs = lane >> 3;
+  // per-tile row bookkeeping for the 8 rows this lane stores (r = 4*i + rs)
+  int row_off[8];  // EPI_HEADMAJOR: element offset of (sample, token) inside one head-major tensor, head 0
+  int sample0 = 0;
+  if constexpr (EPI == EPI_GATED_RESIDUAL) sample0 = row_base / p.tokens;  // tokens % 32 == 0: one sample per chunk
+  if constexpr (EPI == EPI_HEADMAJOR) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = row_base + i * 4 + rs;
+      const int sample = row / p.tokens;
+      const int tok = row - sample * p.tokens;
+      row_off[i] = (sample * p.heads * p.tokens_pad + tok) * p.head_pad;
+    }
+  }
+#pragma unroll 1
+  for (int c = parity; c < BN / 32; c += 2) {
+    const int col = n0 + c * 32 + cg * 4;
+    uint32_t v[32];
+    tmem_ld_32x32(t_row + c * 32, v);
+    // issue the independent global loads of this chunk before waiting on TMEM / the transpose
+    float4 xin[8];
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+    if constexpr (EPI == EPI_GATED_RESIDUAL) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = row_base + i * 4 + rs;
+        xin[i] = row < p.M ? *reinterpret_cast<const float4*>(p.x + static_cast<size_t>(row) * p.N + col)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (p.gate_table != nullptr) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p.gate_table + col));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.gate_temb + static_cast<size_t>(sample0) * p.temb_stride + col));
+        g4 = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+      }
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      *reinterpret_cast<uint4*>(stage + lane * kEpiPitch + 4 * j) =
+          make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+    __syncwarp();
+    int hm_off = 0;
+    __nv_bfloat16* hm_base = nullptr;
+    if constexpr (EPI == EPI_HEADMAJOR) {
+      const int part_cols = p.heads * p.head_dim;
+      const int part = col / part_cols;
+      const int rem = col - part * part_cols;
+      const int head = rem / p.head_dim;
+      hm_off = head * p.tokens_pad * p.head_pad + (rem - head * p.head_dim);
+      hm_base = part == 0 ? p.hm_out[0] : (part == 1 ? p.hm_out[1] : p.hm_out[2]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 4 + rs;
+      const int row = row_base + r;
+      float4 o = *reinterpret_cast<const float4*>(stage + r * kEpiPitch + cg * 4);
+      o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+      if (row < p.M) {
+        if constexpr (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU) {
+          if constexpr (EPI == EPI_BIAS_GELU) {
+            o.x = gelu_tanh(o.x); o.y = gelu_tanh(o.y); o.z = gelu_tanh(o.z); o.w = gelu_tanh(o.w);
+          }
+          uint2 w;
+          w.x = pack_bf16x2(o.x, o.y);
+          w.y = pack_bf16x2(o.z, o.w);
+          *reinterpret_cast<uint2*>(p.out + static_cast<size_t>(row) * p.ldo + col) = w;
+        } else if constexpr (EPI == EPI_GATED_RESIDUAL) {
+          const size_t off = static_cast<size_t>(row) * p.N + col;
+          uint2 cv;
+          cv.x = pack_bf16x2(o.x, o.y);
+          cv.y = pack_bf16x2(o.z, o.w);
+          *reinterpret_cast<uint2*>(p.cache + off) = cv;
+          float4 x = xin[i];
+          x.x = fmaf(g4.x, o.x, x.x); x.y = fmaf(g4.y, o.y, x.y);
+          x.z = fmaf(g4.z, o.z, x.z); x.w = fmaf(g4.w, o.w, x.w);
+          *reinterpret_cast<float4*>(p.x + off) = x;
+          if (p.xb != nullptr) {
+            uint2 xv;
+            xv.x = pack_bf16x2(x.x, x.y);
+            xv.y = pack_bf16x2(x.z, x.w);
+            *reinterpret_cast<uint2*>(p.xb + off) = xv;
+          }
+        } else {  // EPI_HEADMAJOR
+          uint2 w;
+          w.x = pack_bf16x2(o.x, o.y);
+          w.y = pack_bf16x2(o.z, o.w);
+          *reinterpret_cast<uint2*>(hm_base + row_off[i] + hm_off) = w;
+        }
+      }
+    }
+    __syncwarp();  // the stage tile is overwritten by the next chunk
+  }
+}
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -63,7 +174,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStage);
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::kStage);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStage + kEpiStageBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -85,7 +197,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], kEpiWarps);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -158,7 +270,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =====================
+    // ===================== epilogue (warps 2..9 -> TMEM lane quarters 2,3,0,1,2,3,0,1) =====================
     const int quarter = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -167,115 +279,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int n0 = (tile % num_n) * BN;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int row = m0 + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
+      const int row_base = m0 + quarter * 32;
       const uint32_t t_row = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(quarter * 32) << 16);
-      int sample = 0, tok = 0;
-      if constexpr (EPI == EPI_GATED_RESIDUAL || EPI == EPI_HEADMAJOR) {
-        sample = row / p.tokens;
-        tok = row - sample * p.tokens;
-      }
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_row + c * 32, v);
-        tmem_ld_wait();
-        const int col0 = n0 + c * 32;
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-            v[j + 0] = __float_as_uint(__uint_as_float(v[j + 0]) + b.x);
-            v[j + 1] = __float_as_uint(__uint_as_float(v[j + 1]) + b.y);
-            v[j + 2] = __float_as_uint(__uint_as_float(v[j + 2]) + b.z);
-            v[j + 3] = __float_as_uint(__uint_as_float(v[j + 3]) + b.w);
-          }
-        }
-        if (row_ok) {
-          if constexpr (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU) {
-            __nv_bfloat16* dst = p.out + static_cast<size_t>(row) * p.ldo + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              float f[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                f[e] = __uint_as_float(v[j + e]);
-                if constexpr (EPI == EPI_BIAS_GELU) f[e] = gelu_tanh(f[e]);
-              }
-              uint4 o;
-              o.x = pack_bf16x2(f[0], f[1]);
-              o.y = pack_bf16x2(f[2], f[3]);
-              o.z = pack_bf16x2(f[4], f[5]);
-              o.w = pack_bf16x2(f[6], f[7]);
-              *reinterpret_cast<uint4*>(dst + j) = o;
-            }
-          } else if constexpr (EPI == EPI_GATED_RESIDUAL) {
-            const size_t off = static_cast<size_t>(row) * p.N + col0;
-            float* xrow = p.x + off;
-            __nv_bfloat16* crow = p.cache + off;
-            const float* gt = p.gate_table ? p.gate_table + col0 : nullptr;
-            const float* ge = p.gate_table ? p.gate_temb + static_cast<size_t>(sample) * p.temb_stride + col0 : nullptr;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              float o[8], xn[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[j + e]);
-              uint4 cv;
-              cv.x = pack_bf16x2(o[0], o[1]);
-              cv.y = pack_bf16x2(o[2], o[3]);
-              cv.z = pack_bf16x2(o[4], o[5]);
-              cv.w = pack_bf16x2(o[6], o[7]);
-              *reinterpret_cast<uint4*>(crow + j) = cv;
-              const float4 x0 = *reinterpret_cast<const float4*>(xrow + j);
-              const float4 x1 = *reinterpret_cast<const float4*>(xrow + j + 4);
-              float g[8];
-              if (gt != nullptr) {
-                const float4 a0 = __ldg(reinterpret_cast<const float4*>(gt + j));
-                const float4 a1 = __ldg(reinterpret_cast<const float4*>(gt + j + 4));
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(ge + j));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(ge + j + 4));
-                g[0] = a0.x + b0.x; g[1] = a0.y + b0.y; g[2] = a0.z + b0.z; g[3] = a0.w + b0.w;
-                g[4] = a1.x + b1.x; g[5] = a1.y + b1.y; g[6] = a1.z + b1.z; g[7] = a1.w + b1.w;
-              } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) g[e] = 1.0f;
-              }
-              xn[0] = fmaf(g[0], o[0], x0.x); xn[1] = fmaf(g[1], o[1], x0.y);
-              xn[2] = fmaf(g[2], o[2], x0.z); xn[3] = fmaf(g[3], o[3], x0.w);
-              xn[4] = fmaf(g[4], o[4], x1.x); xn[5] = fmaf(g[5], o[5], x1.y);
-              xn[6] = fmaf(g[6], o[6], x1.z); xn[7] = fmaf(g[7], o[7], x1.w);
-              *reinterpret_cast<float4*>(xrow + j) = make_float4(xn[0], xn[1], xn[2], xn[3]);
-              *reinterpret_cast<float4*>(xrow + j + 4) = make_float4(xn[4], xn[5], xn[6], xn[7]);
-              if (p.xb != nullptr) {
-                uint4 xv;
-                xv.x = pack_bf16x2(xn[0], xn[1]);
-                xv.y = pack_bf16x2(xn[2], xn[3]);
-                xv.z = pack_bf16x2(xn[4], xn[5]);
-                xv.w = pack_bf16x2(xn[6], xn[7]);
-                *reinterpret_cast<uint4*>(p.xb + off + j) = xv;
-              }
-            }
-          } else {  // EPI_HEADMAJOR
-            const int part_cols = p.heads * p.head_dim;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const int col = col0 + j;
-              const int part = col / part_cols;
-              const int rem = col - part * part_cols;
-              const int h = rem / p.head_dim;
-              const int e0 = rem - h * p.head_dim;
-              __nv_bfloat16* dst = p.hm_out[part] +
-                                   ((static_cast<size_t>(sample) * p.heads + h) * p.tokens_pad + tok) * p.head_pad + e0;
-              uint4 o;
-              o.x = pack_bf16x2(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
-              o.y = pack_bf16x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-              o.z = pack_bf16x2(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
-              o.w = pack_bf16x2(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
-              *reinterpret_cast<uint4*>(dst) = o;
-            }
-          }
-        }
-      }
+      float* stage = epi_stage + (warp - 2) * 32 * kEpiPitch;
+      epilogue_tile<BN, EPI>(p, t_row, stage, lane, (warp - 2) >> 2, row_base, n0);
       // accumulator drained: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -292,6 +299,163 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// =====================================================================================================
+// 2-CTA variant (cta_group::2): a CTA pair on one TPC computes a 256 x BN tile.  Each CTA stages ITS 128 rows of A
+// and ITS half (BN/2 rows) of W, so the L2->SM traffic per FLOP drops by 1/3 (BN = 256) versus the 1-CTA kernel,
+// which is L2-bandwidth-bound on B200.  The leader CTA's single MMA thread issues tcgen05.mma.cta_group::2 for the
+// pair; tcgen05.commit multicasts the "slot free" / "accumulator ready" arrivals to both CTAs; every CTA's epilogue
+// warps drain their own 128 TMEM lanes.
+// =====================================================================================================
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int kStageA = kGemmBM * kGemmBK * 2;        // this CTA's 128 rows of A: 16 KB
+  static constexpr int kStageB = (BN / 2) * kGemmBK * 2;       // this CTA's half of W
+  static constexpr int kStage = kStageA + kStageB;
+  static constexpr int kStages = (BN <= 128) ? 7 : (BN <= 192 ? 6 : 5);
+  static constexpr int kAccStride = 256;
+  static constexpr int kTmemCols = 512;
+  static constexpr int kSmemBytes = kStages * kStage + kEpiStageBytes + 1024 + 256;
+};
+
+template <int BN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const GemmParams p) {
+  using Cfg = Gemm2Cfg<BN>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::kStage);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStage + kEpiStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();  // 0 = leader
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int num_m = (p.M + 2 * kGemmBM - 1) / (2 * kGemmBM);
+  const int num_n = p.N / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = p.K / kGemmBK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);   // used in the leader: its producer's arrive.expect_tx (bytes of both CTAs)
+      mbar_init(&empty_bar[i], 1);  // per CTA: multicast tcgen05.commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);   // per CTA: multicast tcgen05.commit
+      mbar_init(&tmem_empty[i], 2 * kEpiWarps);  // used in the leader: 8 epilogue warps x 2 CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync();  // barriers of both CTAs initialised before any remote arrive / TMA credit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer (both CTAs) =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m0 = (tile / num_n) * (2 * kGemmBM) + cta * kGemmBM;
+        const int n0 = (tile % num_n) * BN + cta * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStage;
+          uint8_t* sb = sa + Cfg::kStageA;
+          if (cta == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStage);
+          tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], kb * kGemmBK, m0);
+          tma_load_2d_2sm(sb, &tmap_b, &full_bar[stage], kb * kGemmBK, n0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && cta == 0) {
+      // ===================== MMA issuer (leader CTA only) =====================
+      constexpr uint32_t idesc = make_idesc_bf16(2 * kGemmBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * Cfg::kAccStride;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStage);
+          const uint32_t sb = sa + Cfg::kStageA;
+          const uint64_t da = make_smem_desc(sa, 16, 1024, kLayoutSW128);
+          const uint64_t db = make_smem_desc(sb, 16, 1024, kLayoutSW128);
+#pragma unroll
+          for (int k = 0; k < kGemmBK / 16; ++k) {
+            umma_bf16_ss_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit_2sm(&empty_bar[stage], 0b11);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2sm(&tmem_full[acc], 0b11);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (both CTAs; this CTA's 128 rows) =====================
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int m0 = (tile / num_n) * (2 * kGemmBM) + cta * kGemmBM;
+      const int n0 = (tile % num_n) * BN;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row_base = m0 + quarter * 32;
+      const uint32_t t_row = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(quarter * 32) << 16);
+      float* stage = epi_stage + (warp - 2) * 32 * kEpiPitch;
+      epilogue_tile<BN, EPI>(p, t_row, stage, lane, (warp - 2) >> 2, row_base, n0);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);  // the leader's barrier collects both CTAs
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync();  // the peer may still be reading our smem / signalling our barriers until here
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
   }
 }
 

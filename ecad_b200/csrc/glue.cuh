@@ -42,40 +42,35 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // VPL = float4 vectors per lane: D = 128 * VPL  (1152 -> 9, 3072 -> 24)
-template <int VPL>
-__global__ void __launch_bounds__(256) residual_ln_kernel(const ResidualLnParams p) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + warp;
-  if (row >= p.M) return;
-  constexpr int D = 128 * VPL;
-  const int sample = row / p.tokens;
-  const size_t roff = static_cast<size_t>(row) * D;
-  float4 v[VPL];
-  const float4* xr = reinterpret_cast<const float4*>(p.x + roff);
-#pragma unroll
-  for (int i = 0; i < VPL; ++i) v[i] = xr[lane + 32 * i];
+//
+// A block owns 32 consecutive rows of ONE sample (tokens % 32 == 0): the per-sample modulation vectors
+// (1 + scale, shift, and every reuse gate = table + temb[sample]) are combined once into shared memory instead of
+// being re-read from L2 by every row; each warp then streams 4 rows, two at a time so that two rows of x (and of each
+// cache) are in flight per warp.
+constexpr int kRlnRowsPerBlock = 32;
 
+template <int VPL>
+__device__ __forceinline__ void rln_row(const ResidualLnParams& p, const float4* __restrict__ sm, const int row,
+                                        const int lane, float4 (&v)[VPL]) {
+  constexpr int D = 128 * VPL;
+  constexpr int DV = D / 4;
+  const size_t roff = static_cast<size_t>(row) * D;
   if (p.n_reuse > 0) {
     for (int r = 0; r < p.n_reuse; ++r) {
-      const ReuseEntry e = p.reuse[r];
-      const uint2* cr = reinterpret_cast<const uint2*>(e.cache + roff);
-      const float4* gt = reinterpret_cast<const float4*>(e.gate_table);
-      const float4* ge =
-          reinterpret_cast<const float4*>(e.gate_temb ? e.gate_temb + static_cast<size_t>(sample) * p.temb_stride : nullptr);
+      const uint2* cr = reinterpret_cast<const uint2*>(p.reuse[r].cache + roff);
+      const float4* g = sm + (2 + r) * DV;
+      uint2 c[VPL];
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) c[i] = __ldg(cr + lane + 32 * i);
 #pragma unroll
       for (int i = 0; i < VPL; ++i) {
-        const uint2 c = __ldg(cr + lane + 32 * i);
-        const float2 c01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&c.x));
-        const float2 c23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&c.y));
-        float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (gt != nullptr) {
-          const float4 a = __ldg(gt + lane + 32 * i), b = __ldg(ge + lane + 32 * i);
-          g = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
-        }
-        v[i].x = fmaf(g.x, c01.x, v[i].x);
-        v[i].y = fmaf(g.y, c01.y, v[i].y);
-        v[i].z = fmaf(g.z, c23.x, v[i].z);
-        v[i].w = fmaf(g.w, c23.y, v[i].w);
+        const float2 c01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&c[i].x));
+        const float2 c23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&c[i].y));
+        const float4 gg = g[lane + 32 * i];
+        v[i].x = fmaf(gg.x, c01.x, v[i].x);
+        v[i].y = fmaf(gg.y, c01.y, v[i].y);
+        v[i].z = fmaf(gg.z, c23.x, v[i].z);
+        v[i].w = fmaf(gg.w, c23.y, v[i].w);
       }
     }
     float4* xw = reinterpret_cast<float4*>(p.x + roff);
@@ -105,24 +100,78 @@ __global__ void __launch_bounds__(256) residual_ln_kernel(const ResidualLnParams
       q += (a * a + b * b) + (c * c + d * d);
     }
     const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + p.eps);
-    const float4* st = reinterpret_cast<const float4*>(p.shift_table);
-    const float4* ct = reinterpret_cast<const float4*>(p.scale_table);
-    const float4* se = reinterpret_cast<const float4*>(p.shift_temb + static_cast<size_t>(sample) * p.temb_stride);
-    const float4* ce = reinterpret_cast<const float4*>(p.scale_temb + static_cast<size_t>(sample) * p.temb_stride);
     uint2* hw = reinterpret_cast<uint2*>(p.h + roff);
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int k = lane + 32 * i;
-      const float4 sa = __ldg(st + k), sb = __ldg(se + k), ca = __ldg(ct + k), cb = __ldg(ce + k);
-      const float y0 = (v[i].x - mean) * rstd * (1.f + (ca.x + cb.x)) + (sa.x + sb.x);
-      const float y1 = (v[i].y - mean) * rstd * (1.f + (ca.y + cb.y)) + (sa.y + sb.y);
-      const float y2 = (v[i].z - mean) * rstd * (1.f + (ca.z + cb.z)) + (sa.z + sb.z);
-      const float y3 = (v[i].w - mean) * rstd * (1.f + (ca.w + cb.w)) + (sa.w + sb.w);
+      const float4 sc = sm[k], sh = sm[DV + k];  // (1 + scale), shift
       uint2 o;
-      o.x = pack_bf16x2(y0, y1);
-      o.y = pack_bf16x2(y2, y3);
+      o.x = pack_bf16x2((v[i].x - mean) * rstd * sc.x + sh.x, (v[i].y - mean) * rstd * sc.y + sh.y);
+      o.y = pack_bf16x2((v[i].z - mean) * rstd * sc.z + sh.z, (v[i].w - mean) * rstd * sc.w + sh.w);
       hw[k] = o;
     }
+  }
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(256, (VPL <= 12) ? 2 : 1) residual_ln_kernel(const ResidualLnParams p) {
+  extern __shared__ float4 rln_sm[];  // [(2 + n_reuse)][D/4]
+  constexpr int D = 128 * VPL;
+  constexpr int DV = D / 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * kRlnRowsPerBlock;
+  const int sample = row0 / p.tokens;
+  for (int k = threadIdx.x; k < DV; k += blockDim.x) {
+    if (p.h != nullptr) {
+      const float4 ca = __ldg(reinterpret_cast<const float4*>(p.scale_table) + k);
+      const float4 cb = __ldg(reinterpret_cast<const float4*>(p.scale_temb + static_cast<size_t>(sample) * p.temb_stride) + k);
+      const float4 sa = __ldg(reinterpret_cast<const float4*>(p.shift_table) + k);
+      const float4 sb = __ldg(reinterpret_cast<const float4*>(p.shift_temb + static_cast<size_t>(sample) * p.temb_stride) + k);
+      rln_sm[k] = make_float4(1.f + (ca.x + cb.x), 1.f + (ca.y + cb.y), 1.f + (ca.z + cb.z), 1.f + (ca.w + cb.w));
+      rln_sm[DV + k] = make_float4(sa.x + sb.x, sa.y + sb.y, sa.z + sb.z, sa.w + sb.w);
+    }
+    for (int r = 0; r < p.n_reuse; ++r) {
+      float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (p.reuse[r].gate_table != nullptr) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p.reuse[r].gate_table) + k);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.reuse[r].gate_temb + static_cast<size_t>(sample) * p.temb_stride) + k);
+        g = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+      }
+      rln_sm[(2 + r) * DV + k] = g;
+    }
+  }
+  __syncthreads();
+  // rows row0 + warp + 8*j, j = 0..3: two rows in flight per warp
+  if constexpr (VPL > 12) {  // wide rows (D = 3072): one row per warp at a time keeps the row in registers
+#pragma unroll 1
+    for (int j = 0; j < kRlnRowsPerBlock / 8; ++j) {
+      const int ra = row0 + warp + 8 * j;
+      if (ra >= p.M) break;
+      float4 va[VPL];
+      const float4* xr = reinterpret_cast<const float4*>(p.x + static_cast<size_t>(ra) * D);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) va[i] = xr[lane + 32 * i];
+      rln_row<VPL>(p, rln_sm, ra, lane, va);
+    }
+  } else {
+#pragma unroll 1
+  for (int j = 0; j < kRlnRowsPerBlock / 8; j += 2) {
+    const int ra = row0 + warp + 8 * j, rb = ra + 8;
+    float4 va[VPL], vb[VPL];
+    const bool oka = ra < p.M, okb = rb < p.M;
+    if (oka) {
+      const float4* xr = reinterpret_cast<const float4*>(p.x + static_cast<size_t>(ra) * D);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) va[i] = xr[lane + 32 * i];
+    }
+    if (okb) {
+      const float4* xr = reinterpret_cast<const float4*>(p.x + static_cast<size_t>(rb) * D);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) vb[i] = xr[lane + 32 * i];
+    }
+    if (oka) rln_row<VPL>(p, rln_sm, ra, lane, va);
+    if (okb) rln_row<VPL>(p, rln_sm, rb, lane, vb);
+  }
   }
 }
 
@@ -172,7 +221,8 @@ __global__ void __launch_bounds__(128) patch_embed_kernel(const PatchEmbedParams
 struct FinalLayerParams {
   const float* x;            // [S*N, D]
   const float* table;        // [2, D]: shift, scale
-  const float* emb;          // [S, D] embedded_timestep
+  const float* emb;          // [S, D] embedded_timestep (row pitch emb_stride; 0 = shared)
+  int emb_stride;
   const float* w;            // [OUT, D] fp32
   const float* bias;         // [OUT]
   float* out;                // [S, C, 2Hp, 2Wp]
@@ -180,13 +230,9 @@ struct FinalLayerParams {
   float eps;
 };
 template <int VPL>
-__global__ void __launch_bounds__(256) final_layer_kernel(const FinalLayerParams p) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + warp;
-  if (row >= p.M) return;
+__device__ __forceinline__ void final_norm_row(const FinalLayerParams& p, const int row, const int lane, float4 (&v)[VPL]) {
   constexpr int D = 128 * VPL;
-  const int s = row / p.tokens, n = row - s * p.tokens;
-  float4 v[VPL];
+  const int s = row / p.tokens;
   const float4* xr = reinterpret_cast<const float4*>(p.x + static_cast<size_t>(row) * D);
   float sum = 0.f;
 #pragma unroll
@@ -204,7 +250,7 @@ __global__ void __launch_bounds__(256) final_layer_kernel(const FinalLayerParams
   const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + p.eps);
   const float4* sh = reinterpret_cast<const float4*>(p.table);
   const float4* sc = reinterpret_cast<const float4*>(p.table + D);
-  const float4* em = reinterpret_cast<const float4*>(p.emb + static_cast<size_t>(s) * D);
+  const float4* em = reinterpret_cast<const float4*>(p.emb + static_cast<size_t>(s) * p.emb_stride);
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int k = lane + 32 * i;
@@ -214,21 +260,41 @@ __global__ void __launch_bounds__(256) final_layer_kernel(const FinalLayerParams
     v[i].z = (v[i].z - mean) * rstd * (1.f + (b.z + e.z)) + (a.z + e.z);
     v[i].w = (v[i].w - mean) * rstd * (1.f + (b.w + e.w)) + (a.w + e.w);
   }
+}
+
+__device__ __forceinline__ void final_store(const FinalLayerParams& p, const int row, const int o, const float val) {
+  const int s = row / p.tokens, n = row - s * p.tokens;
   const int i_h = n / p.Wp, j_w = n - i_h * p.Wp;
-  const int Hout = 2 * p.Hp, Wout = 2 * p.Wp;
+  const int pq = o / p.C, c = o - pq * p.C;
+  p.out[((static_cast<size_t>(s) * p.C + c) * (2 * p.Hp) + (2 * i_h + (pq >> 1))) * (2 * p.Wp) + 2 * j_w + (pq & 1)] =
+      val + p.bias[o];
+}
+
+// one warp = two token rows (each Linear weight row is loaded once for both)
+template <int VPL>
+__global__ void __launch_bounds__(256) final_layer_kernel(const FinalLayerParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row_a = (blockIdx.x * 8 + warp) * 2, row_b = row_a + 1;
+  if (row_a >= p.M) return;
+  constexpr int D = 128 * VPL;
+  const bool has_b = row_b < p.M;
+  float4 va[VPL], vb[VPL];
+  final_norm_row<VPL>(p, row_a, lane, va);
+  final_norm_row<VPL>(p, has_b ? row_b : row_a, lane, vb);
   for (int o = 0; o < p.OUT; ++o) {
     const float4* wr = reinterpret_cast<const float4*>(p.w + static_cast<size_t>(o) * D);
-    float acc = 0.f;
+    float acc_a = 0.f, acc_b = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const float4 w = __ldg(wr + lane + 32 * i);
-      acc += (v[i].x * w.x + v[i].y * w.y) + (v[i].z * w.z + v[i].w * w.w);
+      acc_a += (va[i].x * w.x + va[i].y * w.y) + (va[i].z * w.z + va[i].w * w.w);
+      acc_b += (vb[i].x * w.x + vb[i].y * w.y) + (vb[i].z * w.z + vb[i].w * w.w);
     }
-    acc = warp_sum(acc);
+    acc_a = warp_sum(acc_a);
+    acc_b = warp_sum(acc_b);
     if (lane == 0) {
-      const int pq = o / p.C, c = o - pq * p.C;
-      const int pp = pq >> 1, qq = pq & 1;
-      p.out[((static_cast<size_t>(s) * p.C + c) * Hout + (2 * i_h + pp)) * Wout + 2 * j_w + qq] = acc + p.bias[o];
+      final_store(p, row_a, o, acc_a);
+      if (has_b) final_store(p, row_b, o, acc_b);
     }
   }
 }
@@ -248,7 +314,8 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const SmallLinearPara
   const int o = blockIdx.x * 8 + warp;
   if (o >= p.O) return;
   const float* wr = p.w + static_cast<size_t>(o) * p.K;
-  for (int s0 = 0; s0 < p.S; s0 += 8) {
+  {
+    const int s0 = blockIdx.y * 8;
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;

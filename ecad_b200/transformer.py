@@ -338,14 +338,24 @@ class B200PixArtTransformer2D:
         _lib.check(lib.ecadk_patch_embed(lat.data_ptr(), w["patch_wt"].data_ptr(), w["patch_b"].data_ptr(),
                                          pos.data_ptr(), ws["x"].data_ptr(), S, Cin, hl, wl, D, st), "patch_embed")
         # adaLN-single: sinusoid -> MLP -> SiLU -> Linear(D, 6D)  (:308-313)
-        t32 = timestep.to(device=dev, dtype=torch.float32).expand(S).contiguous()
-        _lib.check(lib.ecadk_timestep_sinusoid(t32.data_ptr(), ws["t_proj"].data_ptr(), S, 256, st), "sinusoid")
+        # The pipeline broadcasts ONE timestep over the batch (`t[None].expand(batch)`, pass_through.py:326-329):
+        # a stride-0 / single-element timestep is embedded once and every kernel reads it with row pitch 0.
+        shared_t = timestep.numel() == 1 or (timestep.ndim == 1 and timestep.stride(0) == 0)
+        St = 1 if shared_t else S
+        t32 = timestep.reshape(-1)[:1] if shared_t else timestep.reshape(-1)
+        if not shared_t and t32.numel() != S:
+            raise ValueError(f"timestep has {t32.numel()} entries for a batch of {S}")
+        t32 = t32.to(device=dev, dtype=torch.float32).contiguous()
+        temb_stride = 0 if shared_t else 6 * D
+        emb_stride = 0 if shared_t else D
+        ws["args"].temb_stride = temb_stride
+        _lib.check(lib.ecadk_timestep_sinusoid(t32.data_ptr(), ws["t_proj"].data_ptr(), St, 256, st), "sinusoid")
         _lib.check(lib.ecadk_small_linear(ws["t_proj"].data_ptr(), w["t_w0"].data_ptr(), w["t_b0"].data_ptr(),
-                                          ws["t_e1"].data_ptr(), S, 256, D, D, 0, 0, 0, st), "t_mlp1")
+                                          ws["t_e1"].data_ptr(), St, 256, D, D, 0, 0, 0, st), "t_mlp1")
         _lib.check(lib.ecadk_small_linear(ws["t_e1"].data_ptr(), w["t_w1"].data_ptr(), w["t_b1"].data_ptr(),
-                                          ws["t_emb"].data_ptr(), S, D, D, D, 0, 1, 0, st), "t_mlp2")
+                                          ws["t_emb"].data_ptr(), St, D, D, D, 0, 1, 0, st), "t_mlp2")
         _lib.check(lib.ecadk_small_linear(ws["t_emb"].data_ptr(), w["ada_w"].data_ptr(), w["ada_b"].data_ptr(),
-                                          ws["temb6"].data_ptr(), S, D, 6 * D, 6 * D, 0, 1, 0, st), "adaln_linear")
+                                          ws["temb6"].data_ptr(), St, D, 6 * D, 6 * D, 0, 1, 0, st), "adaln_linear")
         launches += 5
 
         # caption projection + per-block K/V: step-invariant, done once per generation (:315-321; hoisted)
@@ -396,7 +406,8 @@ class B200PixArtTransformer2D:
 
         # 3. output (:332-376)
         _lib.check(lib.ecadk_final_layer(ws["x"].data_ptr(), w["final_table"].data_ptr(), ws["t_emb"].data_ptr(),
-                                         w["final_w"].data_ptr(), w["final_b"].data_ptr(), ws["out"].data_ptr(), S,
+                                         emb_stride, w["final_w"].data_ptr(), w["final_b"].data_ptr(),
+                                         ws["out"].data_ptr(), S,
                                          hp, wp, D, cfg.out_channels, cfg.norm_eps, st), "final_layer")
         launches += 1
         self.launches += launches

@@ -101,9 +101,10 @@ int ecadk_mask_bias(const float* mask, float* bias, int samples, int t, int t_pa
 
 /* Final layer: LayerNorm + (scale_shift_table[2,dim] + embedded_timestep) modulate + Linear(dim -> p*p*C) +
  * unpatchify "nhwpqc->nchpwq".  Replaces _create_output (pixart_transformer_2d_edited.py:332-376).
+ * emb fp32 [S, dim] with row pitch emb_stride (0 = one embedded timestep shared by every sample);
  * out fp32 [S, C, 2*hp, 2*wp]. */
-int ecadk_final_layer(const float* x, const float* table, const float* emb, const float* w, const float* bias,
-                      float* out, int samples, int hp, int wp, int dim, int out_channels, float eps,
+int ecadk_final_layer(const float* x, const float* table, const float* emb, int emb_stride, const float* w,
+                      const float* bias, float* out, int samples, int hp, int wp, int dim, int out_channels, float eps,
                       ecadk_stream_t stream);
 
 /* Fused classifier-free guidance + learned-sigma drop + one DPM-Solver++(2M) update on fp32 latents.
@@ -190,6 +191,7 @@ typedef struct {
   void* attn_o;     /* bf16 scratch [samples*tokens, dim] */
   void* ffh;        /* bf16 scratch [samples*tokens, ff_dim] */
   const float* temb6;    /* fp32 [samples, 6*dim] adaLN-single output for this timestep */
+  int temb_stride;       /* row pitch of temb6 in floats: 6*dim, or 0 when every sample shares one timestep */
   const float* text_bias;/* fp32 [samples, text_pad] */
   void* const* k2;       /* host array [num_layers]: bf16 [samples, heads, text_pad, 80] projected caption keys */
   void* const* v2;       /* host array [num_layers] */

@@ -214,7 +214,7 @@ def test_patch_embed_and_final_layer(cuda_device):
     wo = torch.randn(32, D, device="cuda", generator=g) / math.sqrt(D)
     bo = torch.randn(32, device="cuda", generator=g)
     out = torch.empty(S, 8, Hl, Wl, device="cuda")
-    _lib.check(lib.ecadk_final_layer(x.data_ptr(), table.data_ptr(), emb.data_ptr(), wo.data_ptr(), bo.data_ptr(),
+    _lib.check(lib.ecadk_final_layer(x.data_ptr(), table.data_ptr(), emb.data_ptr(), D, wo.data_ptr(), bo.data_ptr(),
                                      out.data_ptr(), S, Hl // 2, Wl // 2, D, 8, 1e-6, _lib.stream_ptr()))
     torch.cuda.synchronize()
     shift, scale = (table[None] + emb[:, None]).chunk(2, dim=1)
