@@ -239,3 +239,279 @@ attn_tile_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_consta
 }
 
 }  // namespace ecadk
+
+namespace ecadk {
+// =====================================================================================================
+// Persistent pipelined variant: one work item = all 256 queries of one (sample, head) against NK keys.
+//
+//   warp 0      TMA producer: Q (2 tiles) + K of item i+1 are prefetched as soon as item i's QK^T has retired;
+//               V is double-buffered.  K/V are read ONCE per (sample, head).
+//   warp 1      MMA issuer:  S_t = Q_t K^T (SS), then O_t = P_t V with P_t read straight from TMEM (TS form).
+//   warps 2..5  softmax + epilogue of query tile 0;  warps 6..9 of query tile 1 (thread = one query row).
+//
+// TMEM map (512 columns): tile t owns columns [256t, 256t+256): S_t fp32 in [0,NK); P_t (bf16 pairs) is written IN
+// PLACE over the already-consumed low half of S_t; O_t accumulates in [128,208).  No shared memory is spent on P.
+// =====================================================================================================
+constexpr int kAttnPairThreads = 320;
+
+template <int NK>
+struct AttnPairCfg {
+  static constexpr int kQ64 = 0;                    // 256 rows x 128 B (tile 1 at +16 KB)
+  static constexpr int kQ16 = kQ64 + 256 * 128;     // 256 rows x 32 B  (tile 1 at +4 KB)
+  static constexpr int kK64 = kQ16 + 256 * 32;
+  static constexpr int kK16 = kK64 + NK * 128;
+  static constexpr int kV = kK16 + NK * 32;         // 2 buffers of (NK*128 + NK*32)
+  static constexpr int kVBuf = NK * 160;
+  static constexpr int kBias = kV + 2 * kVBuf;      // 8 warps x NK floats
+  static constexpr int kBars = kBias + 8 * NK * 4;
+  // the kernel allocates all 512 TMEM columns, so it must be alone on its SM: ask for more than half the smem
+  static constexpr int kSmemBytes = (kBars + 256 + 1024) > 120 * 1024 ? (kBars + 256 + 1024) : 120 * 1024;
+  static constexpr uint32_t kBytesQK = (256 + NK) * kHeadPad * 2;
+  static constexpr uint32_t kBytesV = NK * kHeadPad * 2;
+};
+
+template <int NK, bool HAS_BIAS>
+__global__ void __launch_bounds__(kAttnPairThreads, 1)
+attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_constant__ CUtensorMap tm_q16,
+                 const __grid_constant__ CUtensorMap tm_k64, const __grid_constant__ CUtensorMap tm_k16,
+                 const __grid_constant__ CUtensorMap tm_v64, const __grid_constant__ CUtensorMap tm_v16,
+                 const AttnParams p, const int num_items) {
+  using Cfg = AttnPairCfg<NK>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBars);
+  uint64_t* qk_full = bars + 0;
+  uint64_t* qk_empty = bars + 1;
+  uint64_t* v_full = bars + 2;    // [2]
+  uint64_t* v_empty = bars + 4;   // [2]
+  uint64_t* s_full = bars + 6;    // [2] per query tile
+  uint64_t* p_full = bars + 8;    // [2]
+  uint64_t* o_full = bars + 10;   // [2]
+  uint64_t* s_empty = bars + 12;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    mbar_init(qk_full, 1);
+    mbar_init(qk_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&s_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int n = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++n) {
+        const int q_row = item * 256;
+        const int k_row = item * NK;
+        mbar_wait(qk_empty, (n & 1) ^ 1);
+        mbar_arrive_expect_tx(qk_full, Cfg::kBytesQK);
+        tma_load_2d(smem + Cfg::kQ64, &tm_q64, qk_full, 0, q_row);
+        tma_load_2d(smem + Cfg::kQ16, &tm_q16, qk_full, 64, q_row);
+        tma_load_2d(smem + Cfg::kK64, &tm_k64, qk_full, 0, k_row);
+        tma_load_2d(smem + Cfg::kK16, &tm_k16, qk_full, 64, k_row);
+        const int vb = n & 1;
+        mbar_wait(&v_empty[vb], ((n >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&v_full[vb], Cfg::kBytesV);
+        uint8_t* vdst = smem + Cfg::kV + vb * Cfg::kVBuf;
+        tma_load_2d(vdst, &tm_v64, &v_full[vb], 0, k_row);
+        tma_load_2d(vdst + NK * 128, &tm_v16, &v_full[vb], 64, k_row);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc_s = make_idesc_bf16(kAttnBM, NK);
+      constexpr uint32_t idesc_o64 = make_idesc_bf16(kAttnBM, 64, 0, 1);
+      constexpr uint32_t idesc_o16 = make_idesc_bf16(kAttnBM, 16, 0, 1);
+      const uint32_t sbase = smem_u32(smem);
+      // Issue order is software-pipelined so that the two query tiles run in anti-phase: while tile 0's warps are in
+      // softmax(i), the tensor core serves tile 1's PV(i-1) and QK^T(i), and vice versa.  Each tile's chain
+      // (softmax -> PV -> read-out -> next QK^T) is serial, so overlapping the two chains is what hides it.
+      auto issue_qk = [&](int t) {
+        const uint32_t d = tmem + 256 * t;
+        const uint64_t dk = make_smem_desc(sbase + Cfg::kK64, 16, 1024, kLayoutSW128);
+        const uint64_t dk2 = make_smem_desc(sbase + Cfg::kK16, 16, 256, kLayoutSW32);
+        const uint64_t dq = make_smem_desc(sbase + Cfg::kQ64 + t * (kAttnBM * 128), 16, 1024, kLayoutSW128);
+        const uint64_t dq2 = make_smem_desc(sbase + Cfg::kQ16 + t * (kAttnBM * 32), 16, 256, kLayoutSW32);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(d, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+        umma_bf16_ss(d, dq2, dk2, idesc_s, 1);
+        umma_commit(&s_full[t]);
+      };
+      auto issue_pv = [&](int t, int vb) {
+        const uint32_t vbase = sbase + Cfg::kV + vb * Cfg::kVBuf;
+        const uint32_t p_tmem = tmem + 256 * t;  // bf16 pairs: 8 columns per 16-key step
+        const uint32_t o_tmem = tmem + 256 * t + 128;
+#pragma unroll
+        for (int ks = 0; ks < NK / 16; ++ks) {
+          const uint64_t dv64 = make_smem_desc(vbase + ks * 16 * 128, NK * 128, 1024, kLayoutSW128);
+          const uint64_t dv16 = make_smem_desc(vbase + NK * 128 + ks * 16 * 32, NK * 32, 256, kLayoutSW32);
+          umma_bf16_ts(o_tmem, p_tmem + ks * 8, dv64, idesc_o64, ks != 0);
+          umma_bf16_ts(o_tmem + 64, p_tmem + ks * 8, dv16, idesc_o16, ks != 0);
+        }
+        umma_commit(&o_full[t]);
+      };
+      int n = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++n) {
+        const uint32_t par = n & 1;
+        mbar_wait(qk_full, par);
+        // tile 0: S(i)
+        mbar_wait(&s_empty[0], par ^ 1);  // previous item's O_0 has been read out of TMEM
+        tc_fence_after();
+        issue_qk(0);
+        // tile 1: PV(i-1)  (V(i-1) sits in buffer (n-1)&1 and was waited for in the previous iteration)
+        if (n > 0) {
+          mbar_wait(&p_full[1], par ^ 1);
+          tc_fence_after();
+          issue_pv(1, (n - 1) & 1);
+          umma_commit(&v_empty[(n - 1) & 1]);
+        }
+        // tile 1: S(i)
+        mbar_wait(&s_empty[1], par ^ 1);
+        tc_fence_after();
+        issue_qk(1);
+        umma_commit(qk_empty);  // Q/K smem may be refilled with the next item
+        // tile 0: PV(i)
+        mbar_wait(&v_full[n & 1], (n >> 1) & 1);
+        mbar_wait(&p_full[0], par);
+        tc_fence_after();
+        issue_pv(0, n & 1);
+      }
+      if (n > 0) {  // drain: tile 1's PV of the last item
+        mbar_wait(&p_full[1], (n - 1) & 1);
+        tc_fence_after();
+        issue_pv(1, (n - 1) & 1);
+        umma_commit(&v_empty[(n - 1) & 1]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== softmax + epilogue: warps 2..5 -> tile 0, warps 6..9 -> tile 1 =====================
+    const int t = (warp - 2) >> 2;
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;
+    const uint32_t t_row = tmem + 256 * t + (static_cast<uint32_t>(quarter * 32) << 16);
+    float* bias_s = reinterpret_cast<float*>(smem + Cfg::kBias) + (warp - 2) * NK;
+    constexpr float kLog2e = 1.4426950408889634f;
+    int n = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++n) {
+      const uint32_t par = n & 1;
+      const int sample = item / p.heads;
+      const int head = item - sample * p.heads;
+      if constexpr (HAS_BIAS) {
+        // per-warp copy of this sample's key bias, pre-multiplied by log2(e)
+        const float* b = p.bias + static_cast<size_t>(sample) * NK;
+        for (int j = lane; j < NK; j += 32) bias_s[j] = __ldg(b + j) * kLog2e;
+        __syncwarp();
+      }
+      mbar_wait(&s_full[t], par);
+      tc_fence_after();
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < NK / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if constexpr (HAS_BIAS) b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + j);
+          mx = fmaxf(mx, fmaf(__uint_as_float(v[j + 0]), p.scale_log2e, b4.x));
+          mx = fmaxf(mx, fmaf(__uint_as_float(v[j + 1]), p.scale_log2e, b4.y));
+          mx = fmaxf(mx, fmaf(__uint_as_float(v[j + 2]), p.scale_log2e, b4.z));
+          mx = fmaxf(mx, fmaf(__uint_as_float(v[j + 3]), p.scale_log2e, b4.w));
+        }
+      }
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < NK / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + c * 32, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if constexpr (HAS_BIAS) b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + j);
+          const float e0 = fast_exp2(fmaf(__uint_as_float(v[j + 0]), p.scale_log2e, b4.x) - mx);
+          const float e1 = fast_exp2(fmaf(__uint_as_float(v[j + 1]), p.scale_log2e, b4.y) - mx);
+          const float e2 = fast_exp2(fmaf(__uint_as_float(v[j + 2]), p.scale_log2e, b4.z) - mx);
+          const float e3 = fast_exp2(fmaf(__uint_as_float(v[j + 3]), p.scale_log2e, b4.w) - mx);
+          sum += (e0 + e1) + (e2 + e3);
+          pk[j / 2] = pack_bf16x2(e0, e1);
+          pk[j / 2 + 1] = pack_bf16x2(e2, e3);
+        }
+        // P chunk c (keys 32c..32c+31) -> packed columns [16c, 16c+16): inside the already-read part of S
+        tmem_st_32x16(t_row + c * 16, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t]);
+
+      mbar_wait(&o_full[t], par);
+      tc_fence_after();
+      const float inv = 1.0f / sum;
+      const int q = t * kAttnBM + row;
+      __nv_bfloat16* dst = p.out + (static_cast<size_t>(sample) * p.q_tokens + q) * p.out_ld + head * kHeadDim;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + 128 + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]) * inv, __uint_as_float(v[g * 8 + 1]) * inv);
+          o.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]) * inv, __uint_as_float(v[g * 8 + 3]) * inv);
+          o.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]) * inv, __uint_as_float(v[g * 8 + 5]) * inv);
+          o.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]) * inv, __uint_as_float(v[g * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = o;
+        }
+      }
+      {
+        uint32_t v[16];
+        tmem_ld_32x16(t_row + 128 + 64, v);  // columns 64..79 of O; 72..79 are padding
+        tmem_ld_wait();
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
+        o.y = pack_bf16x2(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
+        o.z = pack_bf16x2(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
+        o.w = pack_bf16x2(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
+        *reinterpret_cast<uint4*>(dst + 64) = o;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[t]);  // TMEM columns of tile t are free for the next item
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace ecadk

@@ -255,6 +255,21 @@ int launch_attn_inst(const CUtensorMap* tm, const AttnParams& p, int samples, cu
   return check_launch("attn_tile_kernel");
 }
 
+template <int NK, bool HAS_BIAS>
+int launch_attn_pair_inst(const CUtensorMap* tq, const CUtensorMap* tm, const AttnParams& p, int items,
+                          cudaStream_t stream) {
+  using Cfg = AttnPairCfg<NK>;
+  static bool configured = false;
+  auto kern = attn_pair_kernel<NK, HAS_BIAS>;
+  if (!configured) {
+    ECADK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int grid = items < num_sms() ? items : num_sms();
+  kern<<<grid, kAttnPairThreads, Cfg::kSmemBytes, stream>>>(tq[0], tq[1], tm[2], tm[3], tm[4], tm[5], p, items);
+  return check_launch("attn_pair_kernel");
+}
+
 int launch_attention(const void* q, const void* k, const void* v, const float* bias, void* out, int samples,
                      int heads, int q_tokens, int n_keys, cudaStream_t stream) {
   ECADK_REQUIRE(q && k && v && out, "attention: null pointer");
@@ -278,6 +293,24 @@ int launch_attention(const void* q, const void* k, const void* v, const float* b
   p.scale_log2e = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(kHeadDim)));
   p.bias = bias;
   p.out = static_cast<__nv_bfloat16*>(out);
+  // ECADK_ATTN_MODE=tile forces the one-tile-per-CTA kernel (A/B measurements); default: the persistent pair
+  // kernel whenever a (sample, head) has exactly two 128-query tiles (PixArt 256x256).
+  static const bool force_tile = [] {
+    const char* e = getenv("ECADK_ATTN_MODE");
+    return e != nullptr && strcmp(e, "tile") == 0;
+  }();
+  if (q_tokens == 256 && !force_tile) {
+    CUtensorMap tq[2];
+    if ((rc = make_tmap_bf16(&tq[0], q, q_rows, kHeadPad, kHeadPad, 256, 64, 128))) return rc;
+    if ((rc = make_tmap_bf16(&tq[1], q, q_rows, kHeadPad, kHeadPad, 256, 16, 32))) return rc;
+    const int items = samples * heads;
+    if (n_keys == 256) {
+      return bias ? launch_attn_pair_inst<256, true>(tq, tm, p, items, stream)
+                  : launch_attn_pair_inst<256, false>(tq, tm, p, items, stream);
+    }
+    return bias ? launch_attn_pair_inst<128, true>(tq, tm, p, items, stream)
+                : launch_attn_pair_inst<128, false>(tq, tm, p, items, stream);
+  }
   if (n_keys == 256) {
     return bias ? launch_attn_inst<256, true>(tm, p, samples, stream) : launch_attn_inst<256, false>(tm, p, samples, stream);
   }

@@ -84,22 +84,28 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
       row_off[i] = (sample * p.heads * p.tokens_pad + tok) * p.head_pad;
     }
   }
+  // residual-stream prefetch: the x values of chunk c+2 are requested while chunk c is being processed
+  float4 xin[8];
+  auto load_x = [&](int c, float4 (&dst)[8]) {
+    const int col = n0 + c * 32 + cg * 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = row_base + i * 4 + rs;
+      dst[i] = row < p.M ? *reinterpret_cast<const float4*>(p.x + static_cast<size_t>(row) * p.N + col)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  if constexpr (EPI == EPI_GATED_RESIDUAL) load_x(parity, xin);
 #pragma unroll 1
   for (int c = parity; c < BN / 32; c += 2) {
     const int col = n0 + c * 32 + cg * 4;
     uint32_t v[32];
     tmem_ld_32x32(t_row + c * 32, v);
-    // issue the independent global loads of this chunk before waiting on TMEM / the transpose
-    float4 xin[8];
+    float4 xnext[8];
     float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
     if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
     if constexpr (EPI == EPI_GATED_RESIDUAL) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = row_base + i * 4 + rs;
-        xin[i] = row < p.M ? *reinterpret_cast<const float4*>(p.x + static_cast<size_t>(row) * p.N + col)
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      if (c + 2 < BN / 32) load_x(c + 2, xnext);
       if (p.gate_table != nullptr) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(p.gate_table + col));
         const float4 b = __ldg(reinterpret_cast<const float4*>(p.gate_temb + static_cast<size_t>(sample0) * p.temb_stride + col));
@@ -161,6 +167,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
           *reinterpret_cast<uint2*>(hm_base + row_off[i] + hm_off) = w;
         }
       }
+    }
+    if constexpr (EPI == EPI_GATED_RESIDUAL) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xin[i] = xnext[i];
     }
     __syncwarp();  // the stage tile is overwritten by the next chunk
   }

@@ -114,13 +114,8 @@ __device__ __forceinline__ void rln_row(const ResidualLnParams& p, const float4*
 }
 
 template <int VPL>
-__global__ void __launch_bounds__(256, (VPL <= 12) ? 2 : 1) residual_ln_kernel(const ResidualLnParams p) {
-  extern __shared__ float4 rln_sm[];  // [(2 + n_reuse)][D/4]
-  constexpr int D = 128 * VPL;
-  constexpr int DV = D / 4;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = blockIdx.x * kRlnRowsPerBlock;
-  const int sample = row0 / p.tokens;
+__device__ __forceinline__ void rln_stage_vectors(const ResidualLnParams& p, float4* rln_sm, const int sample) {
+  constexpr int DV = 32 * VPL;
   for (int k = threadIdx.x; k < DV; k += blockDim.x) {
     if (p.h != nullptr) {
       const float4 ca = __ldg(reinterpret_cast<const float4*>(p.scale_table) + k);
@@ -140,38 +135,52 @@ __global__ void __launch_bounds__(256, (VPL <= 12) ? 2 : 1) residual_ln_kernel(c
       rln_sm[(2 + r) * DV + k] = g;
     }
   }
-  __syncthreads();
-  // rows row0 + warp + 8*j, j = 0..3: two rows in flight per warp
+}
+
+template <int VPL>
+__device__ __forceinline__ void rln_load_row(const ResidualLnParams& p, const int row, const int lane, float4 (&v)[VPL]) {
+  const float4* xr = reinterpret_cast<const float4*>(p.x + static_cast<size_t>(row) * (128 * VPL));
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) v[i] = xr[lane + 32 * i];
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(256, (VPL <= 12) ? 2 : 1) residual_ln_kernel(const ResidualLnParams p) {
+  extern __shared__ float4 rln_sm[];  // [(2 + n_reuse)][D/4]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * kRlnRowsPerBlock;
+  const int sample = row0 / p.tokens;
   if constexpr (VPL > 12) {  // wide rows (D = 3072): one row per warp at a time keeps the row in registers
+    rln_stage_vectors<VPL>(p, rln_sm, sample);
+    __syncthreads();
 #pragma unroll 1
     for (int j = 0; j < kRlnRowsPerBlock / 8; ++j) {
       const int ra = row0 + warp + 8 * j;
       if (ra >= p.M) break;
       float4 va[VPL];
-      const float4* xr = reinterpret_cast<const float4*>(p.x + static_cast<size_t>(ra) * D);
-#pragma unroll
-      for (int i = 0; i < VPL; ++i) va[i] = xr[lane + 32 * i];
+      rln_load_row<VPL>(p, ra, lane, va);
       rln_row<VPL>(p, rln_sm, ra, lane, va);
     }
   } else {
-#pragma unroll 1
-  for (int j = 0; j < kRlnRowsPerBlock / 8; j += 2) {
-    const int ra = row0 + warp + 8 * j, rb = ra + 8;
+    // rows row0 + warp + 8*j, two in flight per warp; the first pair is requested BEFORE the modulation vectors are
+    // staged so the block's start-up latency overlaps with its first HBM reads
     float4 va[VPL], vb[VPL];
-    const bool oka = ra < p.M, okb = rb < p.M;
-    if (oka) {
-      const float4* xr = reinterpret_cast<const float4*>(p.x + static_cast<size_t>(ra) * D);
-#pragma unroll
-      for (int i = 0; i < VPL; ++i) va[i] = xr[lane + 32 * i];
+    int ra = row0 + warp, rb = ra + 8;
+    if (ra < p.M) rln_load_row<VPL>(p, ra, lane, va);
+    if (rb < p.M) rln_load_row<VPL>(p, rb, lane, vb);
+    rln_stage_vectors<VPL>(p, rln_sm, sample);
+    __syncthreads();
+#pragma unroll 1
+    for (int j = 0; j < kRlnRowsPerBlock / 8; j += 2) {
+      if (j > 0) {
+        ra = row0 + warp + 8 * j;
+        rb = ra + 8;
+        if (ra < p.M) rln_load_row<VPL>(p, ra, lane, va);
+        if (rb < p.M) rln_load_row<VPL>(p, rb, lane, vb);
+      }
+      if (ra < p.M) rln_row<VPL>(p, rln_sm, ra, lane, va);
+      if (rb < p.M) rln_row<VPL>(p, rln_sm, rb, lane, vb);
     }
-    if (okb) {
-      const float4* xr = reinterpret_cast<const float4*>(p.x + static_cast<size_t>(rb) * D);
-#pragma unroll
-      for (int i = 0; i < VPL; ++i) vb[i] = xr[lane + 32 * i];
-    }
-    if (oka) rln_row<VPL>(p, rln_sm, ra, lane, va);
-    if (okb) rln_row<VPL>(p, rln_sm, rb, lane, vb);
-  }
   }
 }
 
