@@ -36,6 +36,8 @@ EXPORTED_SYMBOLS = [
     "ecadk_destroy",
     "ecadk_pixart_blocks",
     "ecadk_pixart_text_kv",
+    "ecadk_profile_start",
+    "ecadk_profile_stop",
 ]
 
 
@@ -104,6 +106,12 @@ class EcadkBlocksArgs(C.Structure):
     ]
 
 
+class EcadkProfileRecord(C.Structure):
+    _fields_ = [("launches", C.c_longlong), ("total_ms", C.c_double), ("flops", C.c_double), ("bytes", C.c_double)]
+
+
+PROF_CLASSES = ("gemm", "attention", "glue", "other")
+
 _lib = None
 
 
@@ -143,6 +151,8 @@ def load() -> C.CDLL:
         "ecadk_destroy": [p],
         "ecadk_pixart_blocks": [p, C.POINTER(EcadkBlocksArgs), C.POINTER(C.c_uint8), C.POINTER(i), p],
         "ecadk_pixart_text_kv": [p, p, i, i, i, C.POINTER(p), C.POINTER(p), C.POINTER(i), p],
+        "ecadk_profile_start": [],
+        "ecadk_profile_stop": [C.POINTER(EcadkProfileRecord)],
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)
@@ -221,3 +231,15 @@ def residual_ln(x, tokens, reuse=(), xb=None, h=None, shift_table=None, scale_ta
     a.shift_temb, a.scale_temb = ptr(shift_temb), ptr(scale_temb)
     a.temb_stride, a.eps = temb_stride, eps
     check(load().ecadk_residual_ln(C.byref(a), stream_ptr()), "residual_ln")
+
+
+def profile_start() -> None:
+    check(load().ecadk_profile_start(), "profile_start")
+
+
+def profile_stop() -> dict[str, dict[str, float]]:
+    """Per kernel class: launches, summed CUDA-event ms, algorithmic flops / bytes of those launches."""
+    recs = (EcadkProfileRecord * len(PROF_CLASSES))()
+    check(load().ecadk_profile_stop(recs), "profile_stop")
+    return {n: {"launches": int(r.launches), "total_ms": r.total_ms, "flops": r.flops, "bytes": r.bytes}
+            for n, r in zip(PROF_CLASSES, recs)}

@@ -413,16 +413,26 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_consta
     const uint32_t t_row = tmem + 256 * t + (static_cast<uint32_t>(quarter * 32) << 16);
     float* bias_s = reinterpret_cast<float*>(smem + Cfg::kBias) + (warp - 2) * NK;
     constexpr float kLog2e = 1.4426950408889634f;
+    // key bias of the NEXT item is fetched one item ahead (registers), so its global latency is off the chain
+    float breg[NK / 32];
+    auto fetch_bias = [&](int it) {
+      const float* b = p.bias + static_cast<size_t>(it / p.heads) * NK;
+#pragma unroll
+      for (int j = 0; j < NK / 32; ++j) breg[j] = __ldg(b + lane + 32 * j) * kLog2e;
+    };
+    if constexpr (HAS_BIAS) {
+      if (static_cast<int>(blockIdx.x) < num_items) fetch_bias(blockIdx.x);
+    }
     int n = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++n) {
       const uint32_t par = n & 1;
       const int sample = item / p.heads;
       const int head = item - sample * p.heads;
       if constexpr (HAS_BIAS) {
-        // per-warp copy of this sample's key bias, pre-multiplied by log2(e)
-        const float* b = p.bias + static_cast<size_t>(sample) * NK;
-        for (int j = lane; j < NK; j += 32) bias_s[j] = __ldg(b + j) * kLog2e;
+#pragma unroll
+        for (int j = 0; j < NK / 32; ++j) bias_s[lane + 32 * j] = breg[j];
         __syncwarp();
+        if (item + static_cast<int>(gridDim.x) < num_items) fetch_bias(item + gridDim.x);
       }
       mbar_wait(&s_full[t], par);
       tc_fence_after();

@@ -132,6 +132,44 @@ int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t co
   return ECADK_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// in-situ profiler: CUDA event pairs around every launch while enabled
+// ---------------------------------------------------------------------------------------------------
+struct ProfRec {
+  int cls;
+  size_t ev;  // index of the start event; stop = ev + 1
+  double flops, bytes;
+};
+struct ProfState {
+  bool on = false;
+  std::vector<cudaEvent_t> events;
+  size_t used = 0;
+  std::vector<ProfRec> recs;
+};
+ProfState g_prof;
+
+struct ProfScope {
+  cudaStream_t stream;
+  bool active;
+  ProfScope(int cls, double flops, double bytes, cudaStream_t s) : stream(s), active(g_prof.on) {
+    if (!active) return;
+    while (g_prof.events.size() < g_prof.used + 2) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) {
+        active = false;
+        return;
+      }
+      g_prof.events.push_back(e);
+    }
+    g_prof.recs.push_back(ProfRec{cls, g_prof.used, flops, bytes});
+    cudaEventRecord(g_prof.events[g_prof.used], stream);
+    g_prof.used += 2;
+  }
+  ~ProfScope() {
+    if (active) cudaEventRecord(g_prof.events[g_prof.recs.back().ev + 1], stream);
+  }
+};
+
 int g_num_sms = 0;
 int num_sms() {
   if (g_num_sms == 0) {
@@ -215,6 +253,7 @@ int launch_gemm(const void* a, const void* w, GemmParams& p, cudaStream_t stream
   ECADK_REQUIRE(p.N % 128 == 0, "gemm: N=%d must be a multiple of 128", p.N);
   ECADK_REQUIRE(aligned16(a) && aligned16(w), "gemm: operands must be 16-byte aligned");
   const int group = gemm_cta_group(p.M, p.N);
+  ProfScope prof(ECADK_PROF_GEMM, 2.0 * p.M * p.N * p.K, 0.0, stream);
   CUtensorMap ta, tb;
   int rc = make_tmap_bf16(&ta, a, p.M, p.K, p.K, kGemmBM, kGemmBK, 128);
   if (rc) return rc;
@@ -278,6 +317,7 @@ int launch_attention(const void* q, const void* k, const void* v, const float* b
   ECADK_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(out), "attention: 16-byte alignment");
   const uint64_t q_rows = static_cast<uint64_t>(samples) * heads * q_tokens;
   const uint64_t k_rows = static_cast<uint64_t>(samples) * heads * n_keys;
+  ProfScope prof(ECADK_PROF_ATTENTION, 4.0 * samples * heads * q_tokens * n_keys * kHeadDim, 0.0, stream);
   CUtensorMap tm[6];
   int rc;
   if ((rc = make_tmap_bf16(&tm[0], q, q_rows, kHeadPad, kHeadPad, kAttnBM, 64, 128))) return rc;
@@ -351,6 +391,10 @@ int launch_residual_ln(const EcadkResidualLnArgs& a, cudaStream_t stream) {
                 kRlnRowsPerBlock);
   const int grid = (a.rows + kRlnRowsPerBlock - 1) / kRlnRowsPerBlock;
   const int smem = (2 + a.n_reuse) * a.dim * 4;
+  const double elems = static_cast<double>(a.rows) * a.dim;
+  ProfScope prof(ECADK_PROF_GLUE, 0.0,
+                 elems * (4.0 + (a.n_reuse > 0 ? 4.0 : 0.0) + 2.0 * a.n_reuse + (a.xb ? 2.0 : 0.0) + (a.h ? 2.0 : 0.0)),
+                 stream);
   if (a.dim == 1152) {
     residual_ln_kernel<9><<<grid, 256, smem, stream>>>(p);
   } else {
@@ -401,6 +445,7 @@ int ecadk_patch_embed(const float* latents, const float* wt, const float* bias, 
                       int samples, int channels, int hl, int wl, int dim, ecadk_stream_t stream) {
   ECADK_REQUIRE(latents && wt && bias && pos && x, "patch_embed: null pointer");
   ECADK_REQUIRE(channels * 4 <= 64 && hl % 2 == 0 && wl % 2 == 0 && dim % 4 == 0, "patch_embed: bad shape");
+  ProfScope prof(ECADK_PROF_OTHER, 0.0, 0.0, static_cast<cudaStream_t>(stream));
   PatchEmbedParams p{latents, wt, bias, pos, x, samples, channels, hl, wl, dim};
   const int tokens = samples * (hl / 2) * (wl / 2);
   patch_embed_kernel<<<tokens, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
@@ -409,6 +454,7 @@ int ecadk_patch_embed(const float* latents, const float* wt, const float* bias, 
 
 int ecadk_timestep_sinusoid(const float* t, float* out, int samples, int dim, ecadk_stream_t stream) {
   ECADK_REQUIRE(t && out && samples > 0 && dim > 0 && dim % 2 == 0, "timestep_sinusoid: bad args");
+  ProfScope prof(ECADK_PROF_OTHER, 0.0, 0.0, static_cast<cudaStream_t>(stream));
   const int n = samples * (dim / 2);
   timestep_sinusoid_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(t, out, samples, dim);
   return check_launch("timestep_sinusoid_kernel");
@@ -417,6 +463,7 @@ int ecadk_timestep_sinusoid(const float* t, float* out, int samples, int dim, ec
 int ecadk_small_linear(const float* x, const float* w, const float* b, float* y, int samples, int k, int o, int ldy,
                        int y_off, int act_in, int accumulate, ecadk_stream_t stream) {
   ECADK_REQUIRE(x && w && b && y && samples > 0 && k > 0 && o > 0, "small_linear: bad args");
+  ProfScope prof(ECADK_PROF_OTHER, 0.0, 0.0, static_cast<cudaStream_t>(stream));
   SmallLinearParams p{x, w, b, y, samples, k, o, ldy, y_off, act_in, accumulate};
   small_linear_kernel<<<dim3((o + 7) / 8, (samples + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   return check_launch("small_linear_kernel");
@@ -424,6 +471,7 @@ int ecadk_small_linear(const float* x, const float* w, const float* b, float* y,
 
 int ecadk_cast_f32_bf16(const float* in, void* out, size_t n, ecadk_stream_t stream) {
   ECADK_REQUIRE(in && out && n % 4 == 0 && aligned16(in), "cast_f32_bf16: n must be a multiple of 4, 16B aligned");
+  ProfScope prof(ECADK_PROF_OTHER, 0.0, 0.0, static_cast<cudaStream_t>(stream));
   const size_t n4 = n / 4;
   size_t blocks = (n4 + 255) / 256;
   if (blocks > static_cast<size_t>(num_sms()) * 16) blocks = static_cast<size_t>(num_sms()) * 16;
@@ -435,6 +483,7 @@ int ecadk_cast_f32_bf16(const float* in, void* out, size_t n, ecadk_stream_t str
 
 int ecadk_mask_bias(const float* mask, float* bias, int samples, int t, int t_pad, ecadk_stream_t stream) {
   ECADK_REQUIRE(mask && bias && samples > 0 && t > 0 && t_pad >= t, "mask_bias: bad args");
+  ProfScope prof(ECADK_PROF_OTHER, 0.0, 0.0, static_cast<cudaStream_t>(stream));
   const int n = samples * t_pad;
   mask_bias_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, bias, samples, t, t_pad);
   return check_launch("mask_bias_kernel");
@@ -445,6 +494,7 @@ int ecadk_final_layer(const float* x, const float* table, const float* emb, int 
                       ecadk_stream_t stream) {
   ECADK_REQUIRE(x && table && emb && w && bias && out, "final_layer: null pointer");
   ECADK_REQUIRE(dim == 1152, "final_layer: dim=%d (supported: 1152)", dim);
+  ProfScope prof(ECADK_PROF_OTHER, 0.0, 0.0, static_cast<cudaStream_t>(stream));
   FinalLayerParams p{x, table, emb, emb_stride, w, bias, out, samples * hp * wp, hp * wp, wp, hp, out_channels, 4 * out_channels, eps};
   final_layer_kernel<9><<<(p.M + 15) / 16, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   return check_launch("final_layer_kernel");
@@ -454,6 +504,7 @@ int ecadk_cfg_dpm_step(const float* noise, float* latents, float* x0_prev, int b
                        int has_cfg, float guidance, float sigma_s, float alpha_s, float c_x, float c_d0, float c_d1,
                        ecadk_stream_t stream) {
   ECADK_REQUIRE(noise && latents && x0_prev && batch > 0 && channels > 0 && hw > 0, "cfg_dpm_step: bad args");
+  ProfScope prof(ECADK_PROF_OTHER, 0.0, 0.0, static_cast<cudaStream_t>(stream));
   CfgDpmParams p{noise, latents, x0_prev, batch, channels, hw, has_cfg, guidance, sigma_s, alpha_s, c_x, c_d0, c_d1};
   const int n = batch * channels * hw;
   cfg_dpm_step_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
@@ -519,6 +570,32 @@ int ecadk_gemm_bias_headmajor(const void* a, const void* w, const float* bias, v
 int ecadk_attention(const void* q, const void* k, const void* v, const float* bias, void* out, int samples,
                     int heads, int q_tokens, int n_keys, ecadk_stream_t stream) {
   return launch_attention(q, k, v, bias, out, samples, heads, q_tokens, n_keys, static_cast<cudaStream_t>(stream));
+}
+
+int ecadk_profile_start(void) {
+  g_prof.used = 0;
+  g_prof.recs.clear();
+  g_prof.on = true;
+  return ECADK_OK;
+}
+
+int ecadk_profile_stop(EcadkProfileRecord* out) {
+  ECADK_REQUIRE(out != nullptr, "profile_stop: null output");
+  g_prof.on = false;
+  ECADK_CHECK_CUDA(cudaDeviceSynchronize());
+  for (int c = 0; c < ECADK_PROF_CLASSES; ++c) out[c] = EcadkProfileRecord{0, 0.0, 0.0, 0.0};
+  for (const ProfRec& r : g_prof.recs) {
+    float ms = 0.f;
+    ECADK_CHECK_CUDA(cudaEventElapsedTime(&ms, g_prof.events[r.ev], g_prof.events[r.ev + 1]));
+    EcadkProfileRecord& o = out[r.cls];
+    o.launches += 1;
+    o.total_ms += ms;
+    o.flops += r.flops;
+    o.bytes += r.bytes;
+  }
+  g_prof.recs.clear();
+  g_prof.used = 0;
+  return ECADK_OK;
 }
 
 int ecadk_create(int device, const EcadkModelDesc* desc, const EcadkBlockWeights* blocks, ecadk_handle_t* out) {

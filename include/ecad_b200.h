@@ -213,6 +213,28 @@ int ecadk_pixart_blocks(ecadk_handle_t h, const EcadkBlocksArgs* args, const uin
 int ecadk_pixart_text_kv(ecadk_handle_t h, const void* enc, int samples, int text_tokens, int text_pad,
                          void* const* k2, void* const* v2, int* n_launches, ecadk_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * In-situ kernel timing (measurement support for bench.py; no reference counterpart - the reference only times
+ * whole pipeline calls, ecad/image_generators/pixart_image_generator.py:405-439).
+ * Between ecadk_profile_start() and ecadk_profile_stop() every kernel the library enqueues is bracketed by a CUDA
+ * event pair on its launch stream.  stop() synchronises the device and fills one record per kernel class.
+ * ---------------------------------------------------------------------------------------------------------- */
+#define ECADK_PROF_GEMM 0      /* tcgen05 GEMMs, all epilogues */
+#define ECADK_PROF_ATTENTION 1 /* attention kernels */
+#define ECADK_PROF_GLUE 2      /* residual_ln (LayerNorm/modulate/cached-residual reuse) */
+#define ECADK_PROF_OTHER 3     /* embedders, final layer, casts, solver step */
+#define ECADK_PROF_CLASSES 4
+
+typedef struct {
+  long long launches;
+  double total_ms;   /* sum of per-launch CUDA-event durations */
+  double flops;      /* algorithmic FLOPs of those launches (GEMM: 2*M*N*K; attention: 4*Nq*Nk*72 per head) */
+  double bytes;      /* algorithmic HBM bytes (glue kernels), 0 where not tracked */
+} EcadkProfileRecord;
+
+int ecadk_profile_start(void);
+int ecadk_profile_stop(EcadkProfileRecord* out /* [ECADK_PROF_CLASSES] */);
+
 #ifdef __cplusplus
 }
 #endif
