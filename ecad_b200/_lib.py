@@ -141,7 +141,7 @@ def load() -> C.CDLL:
         "ecadk_small_linear": [p, p, p, p, i, i, i, i, i, i, i, p],
         "ecadk_cast_f32_bf16": [p, p, sz, p],
         "ecadk_mask_bias": [p, p, i, i, i, p],
-        "ecadk_final_layer": [p, p, p, i, p, p, p, i, i, i, i, i, f, p],
+        "ecadk_final_layer": [p, p, p, i, p, p, p, p, i, i, i, i, i, f, p],
         "ecadk_cfg_dpm_step": [p, p, p, i, i, i, i, f, f, f, f, f, f, p],
         "ecadk_gemm_bias": [p, p, p, p, i, i, i, i, i, p],
         "ecadk_gemm_bias_gated_residual_cache": [p, p, p, p, p, p, p, p, i, i, i, i, i, p],

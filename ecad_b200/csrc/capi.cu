@@ -448,7 +448,7 @@ int ecadk_patch_embed(const float* latents, const float* wt, const float* bias, 
   ProfScope prof(ECADK_PROF_OTHER, 0.0, 0.0, static_cast<cudaStream_t>(stream));
   PatchEmbedParams p{latents, wt, bias, pos, x, samples, channels, hl, wl, dim};
   const int tokens = samples * (hl / 2) * (wl / 2);
-  patch_embed_kernel<<<tokens, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  patch_embed_kernel<<<(tokens + kPatchTokensPerBlock - 1) / kPatchTokensPerBlock, 288, 0, static_cast<cudaStream_t>(stream)>>>(p);
   return check_launch("patch_embed_kernel");
 }
 
@@ -489,15 +489,40 @@ int ecadk_mask_bias(const float* mask, float* bias, int samples, int t, int t_pa
   return check_launch("mask_bias_kernel");
 }
 
-int ecadk_final_layer(const float* x, const float* table, const float* emb, int emb_stride, const float* w,
-                      const float* bias, float* out, int samples, int hp, int wp, int dim, int out_channels, float eps,
-                      ecadk_stream_t stream) {
-  ECADK_REQUIRE(x && table && emb && w && bias && out, "final_layer: null pointer");
-  ECADK_REQUIRE(dim == 1152, "final_layer: dim=%d (supported: 1152)", dim);
-  ProfScope prof(ECADK_PROF_OTHER, 0.0, 0.0, static_cast<cudaStream_t>(stream));
-  FinalLayerParams p{x, table, emb, emb_stride, w, bias, out, samples * hp * wp, hp * wp, wp, hp, out_channels, 4 * out_channels, eps};
-  final_layer_kernel<9><<<(p.M + 15) / 16, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
-  return check_launch("final_layer_kernel");
+int ecadk_final_layer(const float* x, const float* table, const float* emb, int emb_stride, const void* w_pad,
+                      const float* bias, void* h_scratch, float* out, int samples, int hp, int wp, int dim,
+                      int out_channels, float eps, ecadk_stream_t stream) {
+  ECADK_REQUIRE(x && table && emb && w_pad && bias && h_scratch && out, "final_layer: null pointer");
+  ECADK_REQUIRE(4 * out_channels <= 128 && out_channels % 4 == 0, "final_layer: out_channels=%d", out_channels);
+  const int tokens = hp * wp, M = samples * tokens;
+  // 1. h = LN(x) * (1 + scale) + shift with shift = table[0] + emb[s], scale = table[1] + emb[s]
+  EcadkResidualLnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = const_cast<float*>(x);
+  a.h = h_scratch;
+  a.rows = M;
+  a.tokens = tokens;
+  a.dim = dim;
+  a.shift_table = table;
+  a.scale_table = table + dim;
+  a.shift_temb = emb;
+  a.scale_temb = emb;
+  a.temb_stride = emb_stride;
+  a.eps = eps;
+  int rc = launch_residual_ln(a, static_cast<cudaStream_t>(stream));
+  if (rc) return rc;
+  // 2. [M, dim] x [128, dim]^T on the tensor cores; the epilogue keeps the first p*p*C columns and unpatchifies
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = 128; p.K = dim;
+  p.bias = bias;
+  p.tokens = tokens;
+  p.unp_out = out;
+  p.unp_wp = wp;
+  p.unp_hp = hp;
+  p.unp_c = out_channels;
+  p.unp_cols = 4 * out_channels;
+  return launch_gemm<EPI_UNPATCHIFY>(h_scratch, w_pad, p, static_cast<cudaStream_t>(stream));
 }
 
 int ecadk_cfg_dpm_step(const float* noise, float* latents, float* x0_prev, int batch, int channels, int hw,

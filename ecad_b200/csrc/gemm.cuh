@@ -19,6 +19,7 @@ enum GemmEpilogue : int {
   EPI_BIAS_GELU = 1,       // out = bf16(gelu_tanh(acc + bias))                        row-major [M, ldo]
   EPI_GATED_RESIDUAL = 2,  // o = acc + bias; cache = bf16(o); x += gate * o; (xb = bf16(x))
   EPI_HEADMAJOR = 3,       // out[part][sample][head][token][head_pad] = bf16(acc + bias)   (Q/K/V scatter)
+  EPI_UNPATCHIFY = 4,      // fp32 out[s][c][2i+p][2j+q] = acc + bias for the first unp_cols columns (final layer)
 };
 
 struct GemmParams {
@@ -38,6 +39,9 @@ struct GemmParams {
   // EPI_HEADMAJOR
   __nv_bfloat16* hm_out[3];
   int heads, head_dim, head_pad, tokens_pad;
+  // EPI_UNPATCHIFY (column o = (p*2+q)*C + c of token n = i*Wp + j of sample s)
+  float* unp_out;
+  int unp_wp, unp_hp, unp_c, unp_cols;
 };
 
 constexpr int kGemmBM = 128;
@@ -99,6 +103,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
 #pragma unroll 1
   for (int c = parity; c < BN / 32; c += 2) {
     const int col = n0 + c * 32 + cg * 4;
+    if constexpr (EPI == EPI_UNPATCHIFY) {
+      if (n0 + c * 32 >= p.unp_cols) break;  // zero-padded weight rows: nothing to store
+    }
     uint32_t v[32];
     tmem_ld_32x32(t_row + c * 32, v);
     float4 xnext[8];
@@ -160,11 +167,25 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
             xv.y = pack_bf16x2(x.z, x.w);
             *reinterpret_cast<uint2*>(p.xb + off) = xv;
           }
-        } else {  // EPI_HEADMAJOR
+        } else if constexpr (EPI == EPI_HEADMAJOR) {
           uint2 w;
           w.x = pack_bf16x2(o.x, o.y);
           w.y = pack_bf16x2(o.z, o.w);
           *reinterpret_cast<uint2*>(hm_base + row_off[i] + hm_off) = w;
+        } else {  // EPI_UNPATCHIFY: 4 consecutive columns = 4 channels of one (p, q) sub-pixel
+          if (col < p.unp_cols) {
+            const int s_ = row / p.tokens, n_ = row - s_ * p.tokens;
+            const int i_h = n_ / p.unp_wp, j_w = n_ - i_h * p.unp_wp;
+            const int pq = col / p.unp_c, ch = col - pq * p.unp_c;
+            const int hout = 2 * p.unp_hp, wout = 2 * p.unp_wp;
+            float* dst = p.unp_out + ((static_cast<size_t>(s_) * p.unp_c + ch) * hout + (2 * i_h + (pq >> 1))) * wout +
+                         2 * j_w + (pq & 1);
+            const size_t plane = static_cast<size_t>(hout) * wout;
+            dst[0] = o.x;
+            dst[plane] = o.y;
+            dst[2 * plane] = o.z;
+            dst[3 * plane] = o.w;
+          }
         }
       }
     }

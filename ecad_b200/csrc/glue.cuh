@@ -4,7 +4,7 @@
 //                        (x += sum_j gate_j * cache_j), optional bf16 shadow of x, optional LayerNorm + adaLN
 //                        modulate -> bf16.  One warp per token row, the row stays in registers.
 //   patch_embed_kernel   K13: 2x2/s2 patch conv + bias + 2-D sincos position table -> fp32 residual stream.
-//   final_layer_kernel   K16: LayerNorm + modulate + Linear(D->32) + unpatchify.
+//   (K16, the final layer, = residual_ln_kernel + the GEMM's EPI_UNPATCHIFY epilogue; see capi.cu)
 //   small_linear_kernel  K14: fp32 GEMV-ish linears of the timestep / adaLN-single embedder.
 //   timestep_sinusoid_kernel, cast_to_bf16_kernel, mask_bias_kernel, cfg_dpm_step_kernel (K17).
 #pragma once
@@ -195,115 +195,53 @@ struct PatchEmbedParams {
   float* x;
   int S, C, Hl, Wl, D;
 };
-__global__ void __launch_bounds__(128) patch_embed_kernel(const PatchEmbedParams p) {
+constexpr int kPatchTokensPerBlock = 8;
+__global__ void __launch_bounds__(288) patch_embed_kernel(const PatchEmbedParams p) {
   const int Wp = p.Wl >> 1, Hp = p.Hl >> 1;
   const int N = Wp * Hp;
-  const int token = blockIdx.x;  // s*N + n
-  const int s = token / N, n = token - s * N;
-  const int i = n / Wp, j = n - i * Wp;
-  __shared__ float in[64];
   const int K = p.C * 4;
-  if (threadIdx.x < K) {
-    const int c = threadIdx.x >> 2, pq = threadIdx.x & 3;
-    in[threadIdx.x] =
-        p.latents[((static_cast<size_t>(s) * p.C + c) * p.Hl + (2 * i + (pq >> 1))) * p.Wl + 2 * j + (pq & 1)];
+  const int token0 = blockIdx.x * kPatchTokensPerBlock;  // s*N + n
+  const int total = p.S * N;
+  __shared__ float in[kPatchTokensPerBlock][64];
+  for (int idx = threadIdx.x; idx < kPatchTokensPerBlock * K; idx += blockDim.x) {
+    const int tkn = idx / K, kk = idx - tkn * K;
+    const int token = token0 + tkn;
+    float val = 0.f;
+    if (token < total) {
+      const int s = token / N, n = token - s * N;
+      const int i = n / Wp, j = n - i * Wp;
+      const int c = kk >> 2, pq = kk & 3;
+      val = p.latents[((static_cast<size_t>(s) * p.C + c) * p.Hl + (2 * i + (pq >> 1))) * p.Wl + 2 * j + (pq & 1)];
+    }
+    in[tkn][kk] = val;
   }
   __syncthreads();
   for (int d4 = threadIdx.x; d4 < p.D / 4; d4 += blockDim.x) {
-    float4 acc = __ldg(reinterpret_cast<const float4*>(p.bias) + d4);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias) + d4);
+    float4 acc[kPatchTokensPerBlock];
+#pragma unroll
+    for (int t = 0; t < kPatchTokensPerBlock; ++t) acc[t] = b;
     for (int k = 0; k < K; ++k) {
       const float4 w = __ldg(reinterpret_cast<const float4*>(p.wt + static_cast<size_t>(k) * p.D) + d4);
-      const float a = in[k];
-      acc.x = fmaf(a, w.x, acc.x);
-      acc.y = fmaf(a, w.y, acc.y);
-      acc.z = fmaf(a, w.z, acc.z);
-      acc.w = fmaf(a, w.w, acc.w);
+#pragma unroll
+      for (int t = 0; t < kPatchTokensPerBlock; ++t) {
+        const float a = in[t][k];
+        acc[t].x = fmaf(a, w.x, acc[t].x);
+        acc[t].y = fmaf(a, w.y, acc[t].y);
+        acc[t].z = fmaf(a, w.z, acc[t].z);
+        acc[t].w = fmaf(a, w.w, acc[t].w);
+      }
     }
-    const float4 pe = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(n) * p.D) + d4);
-    acc.x += pe.x; acc.y += pe.y; acc.z += pe.z; acc.w += pe.w;
-    reinterpret_cast<float4*>(p.x + static_cast<size_t>(token) * p.D)[d4] = acc;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// K16 final layer: out[s, c, 2i+p, 2j+q] = Linear_{D->P*P*C}( LN(x) * (1 + scale) + shift )[(p*2+q)*C + c]
-struct FinalLayerParams {
-  const float* x;            // [S*N, D]
-  const float* table;        // [2, D]: shift, scale
-  const float* emb;          // [S, D] embedded_timestep (row pitch emb_stride; 0 = shared)
-  int emb_stride;
-  const float* w;            // [OUT, D] fp32
-  const float* bias;         // [OUT]
-  float* out;                // [S, C, 2Hp, 2Wp]
-  int M, tokens, Wp, Hp, C, OUT;
-  float eps;
-};
-template <int VPL>
-__device__ __forceinline__ void final_norm_row(const FinalLayerParams& p, const int row, const int lane, float4 (&v)[VPL]) {
-  constexpr int D = 128 * VPL;
-  const int s = row / p.tokens;
-  const float4* xr = reinterpret_cast<const float4*>(p.x + static_cast<size_t>(row) * D);
-  float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    v[i] = xr[lane + 32 * i];
-    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  }
-  const float mean = warp_sum(sum) * (1.0f / D);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-    q += (a * a + b * b) + (c * c + d * d);
-  }
-  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + p.eps);
-  const float4* sh = reinterpret_cast<const float4*>(p.table);
-  const float4* sc = reinterpret_cast<const float4*>(p.table + D);
-  const float4* em = reinterpret_cast<const float4*>(p.emb + static_cast<size_t>(s) * p.emb_stride);
-#pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int k = lane + 32 * i;
-    const float4 a = __ldg(sh + k), b = __ldg(sc + k), e = __ldg(em + k);
-    v[i].x = (v[i].x - mean) * rstd * (1.f + (b.x + e.x)) + (a.x + e.x);
-    v[i].y = (v[i].y - mean) * rstd * (1.f + (b.y + e.y)) + (a.y + e.y);
-    v[i].z = (v[i].z - mean) * rstd * (1.f + (b.z + e.z)) + (a.z + e.z);
-    v[i].w = (v[i].w - mean) * rstd * (1.f + (b.w + e.w)) + (a.w + e.w);
-  }
-}
-
-__device__ __forceinline__ void final_store(const FinalLayerParams& p, const int row, const int o, const float val) {
-  const int s = row / p.tokens, n = row - s * p.tokens;
-  const int i_h = n / p.Wp, j_w = n - i_h * p.Wp;
-  const int pq = o / p.C, c = o - pq * p.C;
-  p.out[((static_cast<size_t>(s) * p.C + c) * (2 * p.Hp) + (2 * i_h + (pq >> 1))) * (2 * p.Wp) + 2 * j_w + (pq & 1)] =
-      val + p.bias[o];
-}
-
-// one warp = two token rows (each Linear weight row is loaded once for both)
-template <int VPL>
-__global__ void __launch_bounds__(256) final_layer_kernel(const FinalLayerParams p) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row_a = (blockIdx.x * 8 + warp) * 2, row_b = row_a + 1;
-  if (row_a >= p.M) return;
-  constexpr int D = 128 * VPL;
-  const bool has_b = row_b < p.M;
-  float4 va[VPL], vb[VPL];
-  final_norm_row<VPL>(p, row_a, lane, va);
-  final_norm_row<VPL>(p, has_b ? row_b : row_a, lane, vb);
-  for (int o = 0; o < p.OUT; ++o) {
-    const float4* wr = reinterpret_cast<const float4*>(p.w + static_cast<size_t>(o) * D);
-    float acc_a = 0.f, acc_b = 0.f;
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const float4 w = __ldg(wr + lane + 32 * i);
-      acc_a += (va[i].x * w.x + va[i].y * w.y) + (va[i].z * w.z + va[i].w * w.w);
-      acc_b += (vb[i].x * w.x + vb[i].y * w.y) + (vb[i].z * w.z + vb[i].w * w.w);
-    }
-    acc_a = warp_sum(acc_a);
-    acc_b = warp_sum(acc_b);
-    if (lane == 0) {
-      final_store(p, row_a, o, acc_a);
-      if (has_b) final_store(p, row_b, o, acc_b);
+    for (int t = 0; t < kPatchTokensPerBlock; ++t) {
+      const int token = token0 + t;
+      if (token < total) {
+        const int n = token % N;
+        const float4 pe = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(n) * p.D) + d4);
+        float4 o = acc[t];
+        o.x += pe.x; o.y += pe.y; o.z += pe.z; o.w += pe.w;
+        reinterpret_cast<float4*>(p.x + static_cast<size_t>(token) * p.D)[d4] = o;
+      }
     }
   }
 }

@@ -173,8 +173,14 @@ class B200PixArtTransformer2D:
         w["cap_w2"] = bf16(sd["caption_projection.linear_2.weight"])
         w["cap_b2"] = f32(sd["caption_projection.linear_2.bias"])
         w["final_table"] = f32(sd["scale_shift_table"])
-        w["final_w"] = f32(sd["proj_out.weight"])
-        w["final_b"] = f32(sd["proj_out.bias"])
+        # proj_out zero-padded to 128 output rows: the final layer runs on the tensor cores (ecadk_final_layer)
+        n_out = sd["proj_out.weight"].shape[0]
+        fw = torch.zeros(128, D, dtype=torch.float32)
+        fw[:n_out] = sd["proj_out.weight"].detach().float()
+        fb = torch.zeros(128, dtype=torch.float32)
+        fb[:n_out] = sd["proj_out.bias"].detach().float()
+        w["final_w"] = bf16(fw)
+        w["final_b"] = f32(fb)
         self.w = w
         self.blocks_w: list[dict[str, torch.Tensor]] = []
         arr = (_lib.EcadkBlockWeights * cfg.num_layers)()
@@ -407,9 +413,9 @@ class B200PixArtTransformer2D:
         # 3. output (:332-376)
         _lib.check(lib.ecadk_final_layer(ws["x"].data_ptr(), w["final_table"].data_ptr(), ws["t_emb"].data_ptr(),
                                          emb_stride, w["final_w"].data_ptr(), w["final_b"].data_ptr(),
-                                         ws["out"].data_ptr(), S,
+                                         ws["h"].data_ptr(), ws["out"].data_ptr(), S,
                                          hp, wp, D, cfg.out_channels, cfg.norm_eps, st), "final_layer")
-        launches += 1
+        launches += 2
         self.launches += launches
         out = ws["out"]
         if hidden_states.dtype != torch.float32:

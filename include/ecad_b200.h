@@ -101,11 +101,14 @@ int ecadk_mask_bias(const float* mask, float* bias, int samples, int t, int t_pa
 
 /* Final layer: LayerNorm + (scale_shift_table[2,dim] + embedded_timestep) modulate + Linear(dim -> p*p*C) +
  * unpatchify "nhwpqc->nchpwq".  Replaces _create_output (pixart_transformer_2d_edited.py:332-376).
+ * Two kernels: the fused LayerNorm+modulate (bf16 into h_scratch) and a tcgen05 GEMM whose epilogue scatters the
+ * p*p*C real columns straight into the NCHW output.
  * emb fp32 [S, dim] with row pitch emb_stride (0 = one embedded timestep shared by every sample);
- * out fp32 [S, C, 2*hp, 2*wp]. */
-int ecadk_final_layer(const float* x, const float* table, const float* emb, int emb_stride, const float* w,
-                      const float* bias, float* out, int samples, int hp, int wp, int dim, int out_channels, float eps,
-                      ecadk_stream_t stream);
+ * w_pad bf16 [128, dim] = proj_out.weight zero-padded from p*p*C to 128 rows; bias fp32 [128] (zero-padded);
+ * h_scratch bf16 [S*hp*wp, dim]; out fp32 [S, C, 2*hp, 2*wp]. */
+int ecadk_final_layer(const float* x, const float* table, const float* emb, int emb_stride, const void* w_pad,
+                      const float* bias, void* h_scratch, float* out, int samples, int hp, int wp, int dim,
+                      int out_channels, float eps, ecadk_stream_t stream);
 
 /* Fused classifier-free guidance + learned-sigma drop + one DPM-Solver++(2M) update on fp32 latents.
  * Replaces the tail of the denoising loop (ecad/pipelines/pass_through.py:341-370).

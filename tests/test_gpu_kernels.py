@@ -213,16 +213,24 @@ def test_patch_embed_and_final_layer(cuda_device):
     emb = torch.randn(S, D, device="cuda", generator=g) * 0.1
     wo = torch.randn(32, D, device="cuda", generator=g) / math.sqrt(D)
     bo = torch.randn(32, device="cuda", generator=g)
-    out = torch.empty(S, 8, Hl, Wl, device="cuda")
-    _lib.check(lib.ecadk_final_layer(x.data_ptr(), table.data_ptr(), emb.data_ptr(), D, wo.data_ptr(), bo.data_ptr(),
-                                     out.data_ptr(), S, Hl // 2, Wl // 2, D, 8, 1e-6, _lib.stream_ptr()))
+    out = torch.full((S, 8, Hl, Wl), float("nan"), device="cuda")
+    w_pad = torch.zeros(128, D, device="cuda", dtype=torch.bfloat16)
+    w_pad[:32] = wo.to(torch.bfloat16)
+    b_pad = torch.zeros(128, device="cuda")
+    b_pad[:32] = bo
+    h_scr = torch.empty(S * N, D, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.ecadk_final_layer(x.data_ptr(), table.data_ptr(), emb.data_ptr(), D, w_pad.data_ptr(),
+                                     b_pad.data_ptr(), h_scr.data_ptr(), out.data_ptr(), S, Hl // 2, Wl // 2, D, 8,
+                                     1e-6, _lib.stream_ptr()))
     torch.cuda.synchronize()
     shift, scale = (table[None] + emb[:, None]).chunk(2, dim=1)
     hsd = torch.nn.functional.layer_norm(x.view(S, N, D), (D,), eps=1e-6) * (1 + scale) + shift
     hsd = hsd @ wo.T + bo
     hsd = hsd.reshape(-1, Hl // 2, Wl // 2, 2, 2, 8)
     ref_out = torch.einsum("nhwpqc->nchpwq", hsd).reshape(-1, 8, Hl, Wl)
-    assert _rel_err(out, ref_out) < 2e-5
+    assert torch.isfinite(out).all()  # every output element written
+    # bf16 operands (h and W rounded to 8 mantissa bits), fp32 accumulation over 1152 terms
+    assert _rel_err(out, ref_out) < 6e-3
 
 
 def test_timestep_path_and_small_ops(cuda_device):

@@ -21,7 +21,8 @@ g = torch.Generator(device=dev).manual_seed(0)
 bf = torch.bfloat16
 
 
-def timed(fn, iters=10):
+def timed(fn, iters=6, reps=4):
+    """mean per-launch ms; `reps` back-to-back launches per event pair so host launch gaps do not count"""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -29,10 +30,11 @@ def timed(fn, iters=10):
     for _ in range(iters):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        fn()
+        for _ in range(reps):
+            fn()
         b.record()
         torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b))
+        ts.append(a.elapsed_time(b) / reps)
     return statistics.mean(ts)
 
 
@@ -101,6 +103,23 @@ report("gemm FF1 bias+gelu [M,1152]x[4608,1152]", timed(lambda: _lib.gemm_bias(h
 report("gemm FF2 gated-residual+cache [M,4608]x[1152,4608]", timed(lambda: _lib.gemm_gated_residual(
     ffh, w_f2, b_d, x, cache[2], N, gate_table=table[5], gate_temb=temb[:, 5 * D:], temb_stride=6 * D)),
     flops=2.0 * M * 4 * D * D)
+lib = _lib.load()
+lat = torch.randn(S, 4, 32, 32, device=dev, generator=g)
+wt = torch.randn(16, D, device=dev, generator=g)
+pos = torch.randn(N, D, device=dev, generator=g)
+wo = torch.randn(32, D, device=dev, generator=g) / math.sqrt(D)
+bo = torch.randn(32, device=dev, generator=g)
+out = torch.empty(S, 8, 32, 32, device=dev)
+x2 = torch.empty(M, D, device=dev)
+report("patch_embed", timed(lambda: _lib.check(lib.ecadk_patch_embed(
+    lat.data_ptr(), wt.data_ptr(), b_d.data_ptr(), pos.data_ptr(), x2.data_ptr(), S, 4, 32, 32, D, _lib.stream_ptr()))),
+    bytes_=M * D * 4)
+w_pad = torch.zeros(128, D, device=dev, dtype=bf)
+w_pad[:32] = wo.to(bf)
+b_pad = torch.zeros(128, device=dev)
+report("final_layer (LN + tcgen05 GEMM + unpatchify)", timed(lambda: _lib.check(lib.ecadk_final_layer(
+    x2.data_ptr(), table.data_ptr(), temb.data_ptr(), 0, w_pad.data_ptr(), b_pad.data_ptr(), h.data_ptr(),
+    out.data_ptr(), S, 16, 16, D, 8, 1e-6, _lib.stream_ptr()))), bytes_=M * D * 4)
 for n_, k_ in [(1152, 1152), (3456, 1152), (4608, 1152), (1152, 4608)]:
     a_ = h if k_ == D else ffh
     w_ = rnd(n_, k_, scale=1 / math.sqrt(k_))
