@@ -11,9 +11,11 @@ own candidates (weak scaling, no data-path collective) and the final latents are
     python bench.py --impl reference                  # the CPU oracle (the reference cannot run without CUDA +
                                                       # diffusers) timed on the host cores, same metric/config
 
-Keys beyond the base contract: `roofline` (dominant kernel = the tcgen05 GEMM, timed alone with CUDA events, plus the
-whole-step tensor fraction), `cpu_baseline` (oracle on the host cores, bounded sample), `e2e` (through the
-ImageGenerator API with pinned host inputs and a device->host read of the latents), `gpu_launches`, `clocks`.
+Keys beyond the base contract: `roofline` (dominant kernel = the tcgen05 GEMM: algorithmic FLOPs of every GEMM launch
+of the timed region / their CUDA-event durations, recorded on the launch stream inside libecad_b200; plus the same
+kernel timed alone and the whole-step tensor fraction), `cpu_baseline` (oracle on the host cores, bounded sample),
+`e2e` (through the ImageGenerator API with pinned host inputs and a device->host read of the latents),
+`gpu_launches`, `clocks`.
 """
 from __future__ import annotations
 
@@ -214,12 +216,12 @@ def main():
     head_row, cand_rows, from_packed = load_candidates()
     W, K, B = args.warmup, args.steps, args.prompts
     total_steps = W + K
-    # rank r evaluates candidates r*total_steps + i of the 72-candidate population (wrapping), so every rank
-    # does different, fixed-size work: weak scaling
+    # Weak scaling with EQUAL work per rank: step i evaluates candidate i of the population on every rank, each rank on
+    # its own chunk of prompts (units = (candidate schedule, prompt chunk)).
     def row_for(step_idx):
         if args.fixed_schedule:
             return head_row
-        return cand_rows[(rank * total_steps + step_idx) % len(cand_rows)]
+        return cand_rows[step_idx % len(cand_rows)]
 
     sd = random_init_state_dict(PixArtConfig(), 0)
     gen = B200PixArtAlphaImageGenerator(cache_schedule=from_packed(head_row), start_seed=1234 + rank, state_dict=sd,

@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = [
     "ecadk_small_linear",
     "ecadk_cast_f32_bf16",
     "ecadk_mask_bias",
+    "ecadk_average_halves",
     "ecadk_final_layer",
     "ecadk_cfg_dpm_step",
     "ecadk_gemm_bias",
@@ -141,6 +142,7 @@ def load() -> C.CDLL:
         "ecadk_small_linear": [p, p, p, p, i, i, i, i, i, i, i, p],
         "ecadk_cast_f32_bf16": [p, p, sz, p],
         "ecadk_mask_bias": [p, p, i, i, i, p],
+        "ecadk_average_halves": [p, sz, p],
         "ecadk_final_layer": [p, p, p, i, p, p, p, p, i, i, i, i, i, f, p],
         "ecadk_cfg_dpm_step": [p, p, p, i, i, i, i, f, f, f, f, f, f, p],
         "ecadk_gemm_bias": [p, p, p, p, i, i, i, i, i, p],

@@ -481,6 +481,18 @@ int ecadk_cast_f32_bf16(const float* in, void* out, size_t n, ecadk_stream_t str
   return check_launch("cast_to_bf16_kernel");
 }
 
+int ecadk_average_halves(void* buf, size_t half_elems, ecadk_stream_t stream) {
+  ECADK_REQUIRE(buf && half_elems % 8 == 0 && aligned16(buf), "average_halves: need 16B alignment, multiple of 8");
+  ProfScope prof(ECADK_PROF_OTHER, 0.0, 0.0, static_cast<cudaStream_t>(stream));
+  const size_t n8 = half_elems / 8;
+  size_t blocks = (n8 + 255) / 256;
+  if (blocks > static_cast<size_t>(num_sms()) * 16) blocks = static_cast<size_t>(num_sms()) * 16;
+  if (blocks == 0) return ECADK_OK;
+  average_halves_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(buf), n8);
+  return check_launch("average_halves_kernel");
+}
+
 int ecadk_mask_bias(const float* mask, float* bias, int samples, int t, int t_pad, ecadk_stream_t stream) {
   ECADK_REQUIRE(mask && bias && samples > 0 && t > 0 && t_pad >= t, "mask_bias: bad args");
   ProfScope prof(ECADK_PROF_OTHER, 0.0, 0.0, static_cast<cudaStream_t>(stream));

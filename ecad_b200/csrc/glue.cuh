@@ -313,6 +313,27 @@ __global__ void cast_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16*
   }
 }
 
+// TGATE: cache[0:n] = (cache[0:n] + cache[n:2n]) / 2 (bf16, in place) - the averaged cross-attention output that
+// replaces the CFG pair from the gate step on (cached_transformer_block.py:443-449)
+__global__ void average_halves_kernel(__nv_bfloat16* buf, size_t n8) {
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  uint4* lo = reinterpret_cast<uint4*>(buf);
+  const uint4* hi = reinterpret_cast<const uint4*>(buf) + n8;
+  for (; i < n8; i += stride) {
+    const uint4 a = lo[i], b = hi[i];
+    const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&av[k]));
+      const float2 fb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bv[k]));
+      o[k] = pack_bf16x2((fa.x + fb.x) * 0.5f, (fa.y + fb.y) * 0.5f);
+    }
+    lo[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // (1 - mask) * -10000 for real text tokens (pixart_transformer_2d_edited.py:282-289), -inf for padding keys
 __global__ void mask_bias_kernel(const float* mask, float* bias, int S, int T, int T_pad) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;

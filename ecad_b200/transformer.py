@@ -230,9 +230,14 @@ class B200PixArtTransformer2D:
         return self._pos_cache[key]
 
     def _workspace(self, S: int, N: int, T: int, hl: int, wl: int) -> dict[str, Any]:
+        # Buffers are sample-major, so a forward with FEWER samples (TGATE drops the CFG pair from the gate step on,
+        # ecad/pipelines/tgate.py:329-341) runs in the prefix of the same workspace and keeps every cache slot.
+        if self._ws_key is not None:
+            S0, N0, T0, hl0, wl0 = self._ws_key
+            if (N0, T0, hl0, wl0) == (N, T, hl, wl) and S <= S0:
+                self._ws["args"].samples = S
+                return self._ws
         key = (S, N, T, hl, wl)
-        if self._ws_key == key:
-            return self._ws
         cfg, dev = self.cfg, self.device
         D, H, L = cfg.inner_dim, cfg.num_attention_heads, cfg.num_layers
         bf, f32 = torch.bfloat16, torch.float32
@@ -290,12 +295,17 @@ class B200PixArtTransformer2D:
         L = self.cfg.num_layers
         executed = np.zeros((L, 3), dtype=np.uint8)
         row = sched.schedule[step]
+        self._tgate_average = []  # blocks whose attn2 cache is averaged after this forward (TGATE, gate_step - 1)
         for b in range(L):
             entry = row[str(b)]
             attn_cfg = entry.get("custom_compute_attn", {}) or {}
             ff_cfg = entry.get("custom_compute_ff", {}) or {}
             attn_fn = ComputeAttnRegistry.get(attn_cfg.get("name"), False)
             ff_fn = ComputeFFRegistry.get(ff_cfg.get("name"), False)
+            if attn_fn.__name__ == "compute_attn_tgate":
+                g = (attn_cfg.get("kwargs") or {}).get("gate_step")
+                if g is not None and step == g - 1:
+                    self._tgate_average.append(b)
             for c, comp in enumerate(("attn1", "attn2")):
                 ctx = DecisionContext(b, comp, bool(sched.get_recompute(str(b), comp)), not self._has_cache[b, c],
                                       step, dict(attn_cfg.get("kwargs", {}) or {}))
@@ -372,14 +382,15 @@ class B200PixArtTransformer2D:
                     None if mask is None else (mask.data_ptr(), tuple(mask.shape)))
         if self._text_key != text_key or self.cache_schedule.curr_step == 0:
             enc = encoder_hidden_states.to(device=dev)
+            enc_bf, enc_h, enc_p = (ws[n][: S * T] for n in ("enc_bf", "enc_h", "enc_p"))
             if enc.dtype == torch.float32:
                 enc = enc.contiguous()
-                _lib.check(lib.ecadk_cast_f32_bf16(enc.data_ptr(), ws["enc_bf"].data_ptr(), enc.numel(), st), "cast")
+                _lib.check(lib.ecadk_cast_f32_bf16(enc.data_ptr(), enc_bf.data_ptr(), enc.numel(), st), "cast")
                 launches += 1
             else:
-                ws["enc_bf"].copy_(enc.reshape(S * T, -1))
-            _lib.gemm_bias(ws["enc_bf"], w["cap_w1"], w["cap_b1"], ws["enc_h"], gelu=True)
-            _lib.gemm_bias(ws["enc_h"], w["cap_w2"], w["cap_b2"], ws["enc_p"], gelu=False)
+                enc_bf.copy_(enc.reshape(S * T, -1))
+            _lib.gemm_bias(enc_bf, w["cap_w1"], w["cap_b1"], enc_h, gelu=True)
+            _lib.gemm_bias(enc_h, w["cap_w2"], w["cap_b2"], enc_p, gelu=False)
             n_l = C.c_int(0)
             _lib.check(lib.ecadk_pixart_text_kv(self._handle, ws["enc_p"].data_ptr(), S, T, TEXT_PAD,
                                                 C.cast(ws["k2_ptrs"], C.POINTER(C.c_void_p)),
@@ -388,16 +399,16 @@ class B200PixArtTransformer2D:
             launches += 2 + n_l.value
             # mask -> additive bias (:255-291); padding keys get -inf
             if mask is None:
-                ws["text_bias"].zero_()
-                ws["text_bias"][:, T:] = float("-inf")
+                ws["text_bias"][:S].zero_()
+                ws["text_bias"][:S, T:] = float("-inf")
             elif mask.ndim == 2:
                 m32 = mask.to(device=dev, dtype=torch.float32).contiguous()
                 _lib.check(lib.ecadk_mask_bias(m32.data_ptr(), ws["text_bias"].data_ptr(), S, T, TEXT_PAD, st),
                            "mask_bias")
                 launches += 1
             else:  # already a (S,1,T) bias
-                ws["text_bias"][:, :T] = mask.to(device=dev, dtype=torch.float32).reshape(S, T)
-                ws["text_bias"][:, T:] = float("-inf")
+                ws["text_bias"][:S, :T] = mask.to(device=dev, dtype=torch.float32).reshape(S, T)
+                ws["text_bias"][:S, T:] = float("-inf")
             self._text_key = text_key
 
         # 2. blocks under the decision row of the current step
@@ -409,6 +420,14 @@ class B200PixArtTransformer2D:
                                            ex.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(n_l), st), "pixart_blocks")
         launches += n_l.value
         self._has_cache |= executed.astype(np.bool_)
+        if self._tgate_average:
+            # cached_transformer_block.py:443-449: at gate_step - 1 the cache keeps (uncond + text) / 2
+            if S % 2:
+                raise ValueError("TGATE averaging needs the CFG pair (an even number of samples)")
+            half = (S // 2) * N * D
+            for b in self._tgate_average:
+                _lib.check(lib.ecadk_average_halves(ws["cache"][b * 3 + 1].data_ptr(), half, st), "average_halves")
+            launches += len(self._tgate_average)
 
         # 3. output (:332-376)
         _lib.check(lib.ecadk_final_layer(ws["x"].data_ptr(), w["final_table"].data_ptr(), ws["t_emb"].data_ptr(),
@@ -417,7 +436,7 @@ class B200PixArtTransformer2D:
                                          hp, wp, D, cfg.out_channels, cfg.norm_eps, st), "final_layer")
         launches += 2
         self.launches += launches
-        out = ws["out"]
+        out = ws["out"][:S]
         if hidden_states.dtype != torch.float32:
             out = out.to(hidden_states.dtype)
         if not return_dict:

@@ -110,6 +110,10 @@ int ecadk_final_layer(const float* x, const float* table, const float* emb, int 
                       const float* bias, void* h_scratch, float* out, int samples, int hp, int wp, int dim,
                       int out_channels, float eps, ecadk_stream_t stream);
 
+/* TGATE cache averaging: buf[0:half] = (buf[0:half] + buf[half:2*half]) / 2 over bf16 elements, in place.
+ * Replaces `to_cache = (hidden_uncond + hidden_pred_text) / 2` (cached_transformer_block.py:443-449). */
+int ecadk_average_halves(void* buf, size_t half_elems, ecadk_stream_t stream);
+
 /* Fused classifier-free guidance + learned-sigma drop + one DPM-Solver++(2M) update on fp32 latents.
  * Replaces the tail of the denoising loop (ecad/pipelines/pass_through.py:341-370).
  * x_next = c_x*x + c_d0*x0 + c_d1*x0_prev with x0 = (x - sigma_s*eps)/alpha_s; x0_prev is updated to x0. */

@@ -105,6 +105,40 @@ def test_generation_matches_oracle(cuda_device, weights, schedule_file, batch):
     assert not gen.diffusion_pipeline.transformer._has_cache.any()
 
 
+def test_tgate_generation_matches_oracle(cuda_device, weights):
+    """TGATE (ecad/pipelines/tgate.py + compute_attn_tgate): CFG pair until the gate step, the cross-attention cache
+    averaged at gate_step - 1, then the null embedding alone with attn2 always served from the averaged cache."""
+    from ecad_b200.image_generator import B200PixArtAlphaImageGenerator
+    from ecad_b200.weights import synthetic_prompt_embeddings
+
+    row = row_by_path("alpha_cache_schedules/gen_tgate/tgate_m_010_sp_003_fi_001_warmup_002.json")
+    flags = flags_of(row)
+    gate = row["config"]["pipeline"]["kwargs"]["gate_step"]
+    custom = {"name": row["custom"]["attn"], "kwargs": {"gate_step": row["custom"]["gate_step"]}}
+    emb = synthetic_prompt_embeddings(2, seed=7)
+    traces, per_step = [], []
+
+    def spy(step, timestep, latents=None, **kw):
+        traces.append(gen.diffusion_pipeline.transformer.last_executed.copy())
+        per_step.append(latents.detach().cpu().clone())
+
+    gen = B200PixArtAlphaImageGenerator(cache_schedule=schedule_of(row), start_seed=0, state_dict=weights,
+                                        additional_callbacks=[spy])
+    assert gen.gate_step == gate == 10
+    got = gen.generate_images(emb, images_per_prompt=1)[0].cpu()
+    noise = torch.randn(2, 4, 32, 32, generator=torch.Generator().manual_seed(0))
+    ref, ref_trace = _oracle_run(weights, flags, emb, noise, custom=custom, gate_step=gate)
+    assert np.array_equal(np.stack(traces), ref_trace)
+    assert not np.stack(traces)[gate:, :, 1].any()
+    for s, (a, b) in enumerate(zip(per_step, ref["per_step"])):
+        rel = float((a - b).abs().max() / b.abs().max())
+        assert rel <= PER_STEP_REL_MAXABS, (s, rel)
+    assert _cos(got, ref["latents"]) >= FINAL_COS
+    # a second generation on the same generator starts from the full CFG batch again
+    got2 = gen.generate_images(emb, images_per_prompt=1)[0].cpu()
+    assert torch.equal(got, got2)
+
+
 def test_second_generation_reuses_resident_model(cuda_device, weights):
     """Two seeds per prompt + a schedule swap on the resident model give the same result as fresh generators."""
     from ecad_b200.image_generator import B200PixArtAlphaImageGenerator
