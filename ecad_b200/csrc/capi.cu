@@ -200,7 +200,8 @@ int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
 }
 
 template <int BN, int EPI>
-int launch_gemm2_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+int launch_gemm2_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tb_tail, const GemmParams& p,
+                      int tail, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<BN>;
   static bool configured = false;
   auto kern = gemm2_bf16_kernel<BN, EPI>;
@@ -208,10 +209,10 @@ int launch_gemm2_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPa
     ECADK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
-  const int tiles = ((p.M + 2 * kGemmBM - 1) / (2 * kGemmBM)) * (p.N / BN);
+  const int tiles = ((p.M + 2 * kGemmBM - 1) / (2 * kGemmBM)) * ((p.N - tail) / BN + (tail ? 1 : 0));
   const int pairs = num_sms() / 2;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tb_tail, p, tail);
   return check_launch("gemm2_bf16_kernel");
 }
 
@@ -258,13 +259,25 @@ int launch_gemm(const void* a, const void* w, GemmParams& p, cudaStream_t stream
   int rc = make_tmap_bf16(&ta, a, p.M, p.K, p.K, kGemmBM, kGemmBK, 128);
   if (rc) return rc;
   if (group == 2) {
+    // ECADK_GEMM_TAIL=0 disables the 256-wide + 128-wide-tail tiling (A/B measurements)
+    static const bool use_tail = [] {
+      const char* e = getenv("ECADK_GEMM_TAIL");
+      return !(e != nullptr && atoi(e) == 0);
+    }();
+    if (use_tail && p.N > 256 && p.N % 256 == 128) {
+      // N = k*256 + 128 (1152, 3456): k full-width tiles + one 128-wide tail tile per row block
+      CUtensorMap tb_tail;
+      if ((rc = make_tmap_bf16(&tb, w, p.N, p.K, p.K, 128, kGemmBK, 128))) return rc;
+      if ((rc = make_tmap_bf16(&tb_tail, w, p.N, p.K, p.K, 64, kGemmBK, 128))) return rc;
+      return launch_gemm2_inst<256, EPI>(ta, tb, tb_tail, p, 128, stream);
+    }
     const int bn = pick_bn((p.M + 2 * kGemmBM - 1) / (2 * kGemmBM), p.N, num_sms() / 2);
     ECADK_REQUIRE(bn != 0, "gemm: no tile width divides N=%d", p.N);
     if ((rc = make_tmap_bf16(&tb, w, p.N, p.K, p.K, bn / 2, kGemmBK, 128))) return rc;
     switch (bn) {
-      case 256: return launch_gemm2_inst<256, EPI>(ta, tb, p, stream);
-      case 192: return launch_gemm2_inst<192, EPI>(ta, tb, p, stream);
-      default: return launch_gemm2_inst<128, EPI>(ta, tb, p, stream);
+      case 256: return launch_gemm2_inst<256, EPI>(ta, tb, tb, p, 0, stream);
+      case 192: return launch_gemm2_inst<192, EPI>(ta, tb, tb, p, 0, stream);
+      default: return launch_gemm2_inst<128, EPI>(ta, tb, tb, p, 0, stream);
     }
   }
   const int bn = pick_bn((p.M + kGemmBM - 1) / kGemmBM, p.N, num_sms());

@@ -71,9 +71,9 @@ struct GemmCfg {
 // 128-bit accesses in both directions) so that one warp instruction covers 4 rows x 32 columns = 4 full 128-byte
 // lines of the fp32 stream; bias / gate vectors are loaded once per chunk, row -> (sample, token) maps once per tile,
 // and the residual-stream loads of a chunk are issued before its transpose so their latency overlaps it.
-template <int BN, int EPI>
+template <int EPI>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_t t_row, float* stage, const int lane,
-                                              const int parity, const int row_base, const int n0) {
+                                              const int parity, const int row_base, const int n0, const int n_chunks) {
   const int cg = lane & 7, rs = lane >> 3;
   // per-tile row bookkeeping for the 8 rows this lane stores (r = 4*i + rs)
   int row_off[8];  // EPI_HEADMAJOR: element offset of (sample, token) inside one head-major tensor, head 0
@@ -101,7 +101,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
   };
   if constexpr (EPI == EPI_GATED_RESIDUAL) load_x(parity, xin);
 #pragma unroll 1
-  for (int c = parity; c < BN / 32; c += 2) {
+  for (int c = parity; c < n_chunks; c += 2) {
     const int col = n0 + c * 32 + cg * 4;
     if constexpr (EPI == EPI_UNPATCHIFY) {
       if (n0 + c * 32 >= p.unp_cols) break;  // zero-padded weight rows: nothing to store
@@ -112,7 +112,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
     float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
     if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
     if constexpr (EPI == EPI_GATED_RESIDUAL) {
-      if (c + 2 < BN / 32) load_x(c + 2, xnext);
+      if (c + 2 < n_chunks) load_x(c + 2, xnext);
       if (p.gate_table != nullptr) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(p.gate_table + col));
         const float4 b = __ldg(reinterpret_cast<const float4*>(p.gate_temb + static_cast<size_t>(sample0) * p.temb_stride + col));
@@ -313,7 +313,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int row_base = m0 + quarter * 32;
       const uint32_t t_row = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(quarter * 32) << 16);
       float* stage = epi_stage + (warp - 2) * 32 * kEpiPitch;
-      epilogue_tile<BN, EPI>(p, t_row, stage, lane, (warp - 2) >> 2, row_base, n0);
+      epilogue_tile<EPI>(p, t_row, stage, lane, (warp - 2) >> 2, row_base, n0, BN / 32);
       // accumulator drained: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -354,7 +354,9 @@ struct Gemm2Cfg {
 template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                  const GemmParams p) {
+                  const __grid_constant__ CUtensorMap tmap_b_tail, const GemmParams p, const int tail) {
+  // `tail` (0 or 128, only with BN = 256): N = k*256 + 128 is covered by k full-width tiles plus one 128-wide tile per
+  // row block, so N = 1152 / 3456 run at the L2->SM traffic per FLOP of 256-wide tiles instead of 192-wide ones.
   using Cfg = Gemm2Cfg<BN>;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -372,13 +374,15 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int pair = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
   const int num_m = (p.M + 2 * kGemmBM - 1) / (2 * kGemmBM);
-  const int num_n = p.N / BN;
+  const int num_n_full = (p.N - tail) / BN;
+  const int num_n = num_n_full + (tail ? 1 : 0);
   const int num_tiles = num_m * num_n;
   const int num_kb = p.K / kGemmBK;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (tail) tma_prefetch_desc(&tmap_b_tail);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);   // used in the leader: its producer's arrive.expect_tx (bytes of both CTAs)
       mbar_init(&empty_bar[i], 1);  // per CTA: multicast tcgen05.commit
@@ -405,14 +409,19 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int m0 = (tile / num_n) * (2 * kGemmBM) + cta * kGemmBM;
-        const int n0 = (tile % num_n) * BN + cta * (BN / 2);
+        const int n_idx = tile % num_n;
+        const bool is_tail = n_idx >= num_n_full;
+        const int bn_cur = is_tail ? tail : BN;
+        const int n0 = n_idx * BN + cta * (bn_cur / 2);
+        const CUtensorMap* tb = is_tail ? &tmap_b_tail : &tmap_b;
+        const uint32_t stage_bytes = 2 * (Cfg::kStageA + (bn_cur / 2) * kGemmBK * 2);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStage;
           uint8_t* sb = sa + Cfg::kStageA;
-          if (cta == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStage);
+          if (cta == 0) mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
           tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], kb * kGemmBK, m0);
-          tma_load_2d_2sm(sb, &tmap_b, &full_bar[stage], kb * kGemmBK, n0);
+          tma_load_2d_2sm(sb, tb, &full_bar[stage], kb * kGemmBK, n0);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -424,12 +433,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   } else if (warp == 1) {
     if (lane == 0 && cta == 0) {
       // ===================== MMA issuer (leader CTA only) =====================
-      constexpr uint32_t idesc = make_idesc_bf16(2 * kGemmBM, BN);
+      constexpr uint32_t idesc_full = make_idesc_bf16(2 * kGemmBM, BN);
+      constexpr uint32_t idesc_tail = make_idesc_bf16(2 * kGemmBM, 128);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const uint32_t idesc = (tile % num_n) >= num_n_full ? idesc_tail : idesc_full;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * Cfg::kAccStride;
@@ -465,13 +476,15 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int m0 = (tile / num_n) * (2 * kGemmBM) + cta * kGemmBM;
-      const int n0 = (tile % num_n) * BN;
+      const int n_idx = tile % num_n;
+      const int n0 = n_idx * BN;
+      const int n_chunks = (n_idx >= num_n_full ? tail : BN) / 32;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int row_base = m0 + quarter * 32;
       const uint32_t t_row = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(quarter * 32) << 16);
       float* stage = epi_stage + (warp - 2) * 32 * kEpiPitch;
-      epilogue_tile<BN, EPI>(p, t_row, stage, lane, (warp - 2) >> 2, row_base, n0);
+      epilogue_tile<EPI>(p, t_row, stage, lane, (warp - 2) >> 2, row_base, n0, n_chunks);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);  // the leader's barrier collects both CTAs
