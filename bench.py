@@ -100,20 +100,21 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_oracle_images_per_s(head_row, n_runs: int, warmup: int):
-    """The CPU oracle on BASELINE config 1 exactly: batch 1 (2 CFG samples), ours_fast, 20 steps."""
+def cpu_oracle_images_per_s(step_rows, warmup: int):
+    """The CPU oracle (fp32, all host threads) on a bounded sample of the SAME workload as the GPU arm: for each step
+    the same candidate schedule, 20 DPM steps, CFG on - but ONE prompt (2 samples per forward) instead of 100."""
     from ecad_b200.weights import PixArtConfig, random_init_state_dict, synthetic_prompt_embeddings
     from oracle.pixart_oracle import OracleConfig, OracleSchedule, PixArtOracle, generate_latents
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = random_init_state_dict(PixArtConfig(), 0)
-    S, NB = head_row["S"], head_row["NB"]
-    flags = np.unpackbits(np.frombuffer(bytes.fromhex(head_row["bits"]), np.uint8))[: S * NB * 3].reshape(S, NB, 3)
     emb = synthetic_prompt_embeddings(1, seed=1)
-    model = PixArtOracle(sd, OracleConfig(), OracleSchedule.from_flags(flags.astype(bool)))
     times = []
-    for it in range(warmup + n_runs):
+    for it, row in enumerate(step_rows):
+        S, NB = row["S"], row["NB"]
+        flags = np.unpackbits(np.frombuffer(bytes.fromhex(row["bits"]), np.uint8))[: S * NB * 3].reshape(S, NB, 3)
+        model = PixArtOracle(sd, OracleConfig(), OracleSchedule.from_flags(flags.astype(bool)))
         noise = torch.randn(1, 4, 32, 32, generator=torch.Generator().manual_seed(it))
         t0 = time.perf_counter()
         generate_latents(model, emb["prompt_embeds"], emb["prompt_attention_mask"], emb["negative_prompt_embeds"],
@@ -124,6 +125,13 @@ def cpu_oracle_images_per_s(head_row, n_runs: int, warmup: int):
     return times, cores
 
 
+def workload_text(fixed_schedule: bool, prompts: int) -> str:
+    return ("PixArt-alpha XL/2 256x256, 20 DPM-Solver++ steps, CFG 4.5, "
+            + ("ours_fast schedule" if fixed_schedule else
+               "candidates of the reference's gen_000 seed population (candidate i at step i)")
+            + f", {prompts} prompts per step (200 samples/forward), random-init weights, synthetic T5")
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path.  The reference itself refuses to start without CUDA
     (pixart_image_generator.py:55-56) and needs diffusers (absent, no network), so this arm times the fp32 CPU
@@ -131,19 +139,21 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    head_row, _, _ = load_candidates()
-    times, cores = cpu_oracle_images_per_s(head_row, args.steps, args.warmup)
+    head_row, cand_rows, _ = load_candidates()
+    n = args.warmup + args.steps
+    step_rows = [head_row if args.fixed_schedule else cand_rows[i % len(cand_rows)] for i in range(n)]
+    times, cores = cpu_oracle_images_per_s(step_rows, args.warmup)
     total = sum(times)
     value = len(times) / total
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "PixArt-alpha 256x256, 20 DPM-Solver++ steps, ours_fast schedule, CFG 4.5; bounded "
-                               "sample: 1 prompt (2 samples/forward) per step on the host CPU",
-                   "kind": "port (oracle/pixart_oracle.py); the reference needs CUDA+diffusers and cannot run here"},
+        "config": {"workload": workload_text(args.fixed_schedule, args.prompts),
+                   "bounded_sample": "1 prompt (2 samples/forward) per step instead of 100, same candidate schedules",
+                   "kind": "port (oracle/pixart_oracle.py): the reference needs CUDA + diffusers and cannot run here"},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": f"{len(times)} x (1 image, 20 steps, ours_fast)"},
+                         "sample": f"{len(times)} steps x (1 image, 20 denoising steps, the step's candidate schedule)"},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -332,18 +342,16 @@ def main():
         roof["step_frac_of_sustained"] = roof["step_tflops"] / peaks["tf_sustained"]
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            times, cores = cpu_oracle_images_per_s(head_row, n_runs=1, warmup=1)
+            times, cores = cpu_oracle_images_per_s([row_for(W), row_for(W)], warmup=1)
             cpu = {"value": len(times) / sum(times), "unit": "images/s", "cores": cores, "kind": "port",
-                   "sample": "1 image (batch 1, 2 CFG samples), 20 steps, ours_fast, after 1 warm-up"}
+                   "sample": "1 image (1 prompt, 2 CFG samples/forward), 20 steps, the first timed step's candidate "
+                             "schedule, after 1 warm-up image"}
         line = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": 1e3 * secs / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {
-                "workload": ("PixArt-alpha XL/2 256x256, 20 DPM-Solver++ steps, CFG 4.5, "
-                             + ("ours_fast schedule" if args.fixed_schedule else
-                                "candidates of the reference's gen_000 seed population (one per step)")
-                             + f", {B} prompts per step (200 samples/forward), random-init weights, synthetic T5"),
+                "workload": workload_text(args.fixed_schedule, B),
                 "images_per_step": B, "l2": "working set (9.9 GB of caches + activations) >> 126 MB L2",
                 "algorithmic_tflop_per_image": flops / images / 1e12,
             },
