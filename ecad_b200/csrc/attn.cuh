@@ -525,3 +525,326 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_consta
 }
 
 }  // namespace ecadk
+
+namespace ecadk {
+
+// =====================================================================================================
+// General flash-style variant for long key sequences (PixArt 512x512 / 1024x1024 self-attention, N = 1024 / 4096 keys,
+// and PixArt-sigma cross-attention, 300 text tokens padded to 384): keys are streamed in blocks of 128 with an online
+// softmax.  Same skeleton as attn_pair_kernel - one work item = 256 queries (two anti-phase tiles) of one
+// (sample, head); S_t (128 fp32 columns), P_t (bf16, in place over S_t) and O_t (80 columns) live in TMEM; K and V
+// blocks flow through 2-stage TMA rings.
+//
+// Rescaling of O is LAZY: the running reference maximum m_used only moves when the block maximum exceeds it by more
+// than 8 (log2 units), so P entries stay <= 2^8 and the TMEM round trip  O *= 2^(m_old - m_new)  is rare.
+// =====================================================================================================
+constexpr int kFlashKB = 128;  // keys per block
+
+struct AttnFlashCfg {
+  static constexpr int kQ64 = 0;                      // 256 rows x 128 B
+  static constexpr int kQ16 = kQ64 + 256 * 128;       // 256 rows x 32 B
+  static constexpr int kKStage = kFlashKB * 160;      // 128 B part then 32 B part
+  static constexpr int kK = kQ16 + 256 * 32;          // 2 stages
+  static constexpr int kV = kK + 2 * kKStage;         // 2 stages
+  static constexpr int kBias = kV + 2 * kKStage;      // 8 warps x 128 floats
+  static constexpr int kBars = kBias + 8 * kFlashKB * 4;
+  static constexpr int kSmemBytes = kBars + 256 + 1024;
+  static constexpr uint32_t kBytesQ = 256 * kHeadPad * 2;
+  static constexpr uint32_t kBytesKV = kFlashKB * kHeadPad * 2;
+};
+static_assert(AttnFlashCfg::kSmemBytes > 114 * 1024, "attn_flash_kernel must be alone on its SM (512 TMEM columns)");
+
+template <bool HAS_BIAS>
+__global__ void __launch_bounds__(kAttnPairThreads, 1)
+attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_constant__ CUtensorMap tm_q16,
+                  const __grid_constant__ CUtensorMap tm_k64, const __grid_constant__ CUtensorMap tm_k16,
+                  const __grid_constant__ CUtensorMap tm_v64, const __grid_constant__ CUtensorMap tm_v16,
+                  const AttnParams p, const int n_keys, const int num_items) {
+  using Cfg = AttnFlashCfg;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBars);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* k_full = bars + 2;    // [2]
+  uint64_t* k_empty = bars + 4;   // [2]
+  uint64_t* v_full = bars + 6;    // [2]
+  uint64_t* v_empty = bars + 8;   // [2]
+  uint64_t* s_full = bars + 10;   // [2] per query tile, one phase per key block
+  uint64_t* p_full = bars + 12;   // [2]
+  uint64_t* o_full = bars + 14;   // [2] one phase per item
+  uint64_t* s_empty = bars + 16;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nkb = n_keys / kFlashKB;            // key blocks per item
+  const int pairs = p.q_tokens / 256;           // 256-query pairs per (sample, head)
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&s_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int n = 0, nb = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++n) {
+        const int sh = item / pairs, pr = item - sh * pairs;
+        const int q_row = sh * p.q_tokens + pr * 256;
+        mbar_wait(q_empty, (n & 1) ^ 1);
+        mbar_arrive_expect_tx(q_full, Cfg::kBytesQ);
+        tma_load_2d(smem + Cfg::kQ64, &tm_q64, q_full, 0, q_row);
+        tma_load_2d(smem + Cfg::kQ16, &tm_q16, q_full, 64, q_row);
+        for (int j = 0; j < nkb; ++j, ++nb) {
+          const int st = nb & 1;
+          const uint32_t ph = ((nb >> 1) & 1) ^ 1;
+          const int k_row = sh * n_keys + j * kFlashKB;
+          uint8_t* kd = smem + Cfg::kK + st * Cfg::kKStage;
+          uint8_t* vd = smem + Cfg::kV + st * Cfg::kKStage;
+          mbar_wait(&k_empty[st], ph);
+          mbar_arrive_expect_tx(&k_full[st], Cfg::kBytesKV);
+          tma_load_2d(kd, &tm_k64, &k_full[st], 0, k_row);
+          tma_load_2d(kd + kFlashKB * 128, &tm_k16, &k_full[st], 64, k_row);
+          mbar_wait(&v_empty[st], ph);
+          mbar_arrive_expect_tx(&v_full[st], Cfg::kBytesKV);
+          tma_load_2d(vd, &tm_v64, &v_full[st], 0, k_row);
+          tma_load_2d(vd + kFlashKB * 128, &tm_v16, &v_full[st], 64, k_row);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc_s = make_idesc_bf16(kAttnBM, kFlashKB);
+      constexpr uint32_t idesc_o64 = make_idesc_bf16(kAttnBM, 64, 0, 1);
+      constexpr uint32_t idesc_o16 = make_idesc_bf16(kAttnBM, 16, 0, 1);
+      const uint32_t sbase = smem_u32(smem);
+      auto issue_qk = [&](int t, int st) {
+        const uint32_t d = tmem + 256 * t;
+        const uint32_t kb = sbase + Cfg::kK + st * Cfg::kKStage;
+        const uint64_t dk = make_smem_desc(kb, 16, 1024, kLayoutSW128);
+        const uint64_t dk2 = make_smem_desc(kb + kFlashKB * 128, 16, 256, kLayoutSW32);
+        const uint64_t dq = make_smem_desc(sbase + Cfg::kQ64 + t * (kAttnBM * 128), 16, 1024, kLayoutSW128);
+        const uint64_t dq2 = make_smem_desc(sbase + Cfg::kQ16 + t * (kAttnBM * 32), 16, 256, kLayoutSW32);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(d, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+        umma_bf16_ss(d, dq2, dk2, idesc_s, 1);
+        umma_commit(&s_full[t]);
+      };
+      auto issue_pv = [&](int t, int st, bool accumulate) {
+        const uint32_t vb = sbase + Cfg::kV + st * Cfg::kKStage;
+        const uint32_t p_tmem = tmem + 256 * t;
+        const uint32_t o_tmem = tmem + 256 * t + 128;
+#pragma unroll
+        for (int ks = 0; ks < kFlashKB / 16; ++ks) {
+          const uint64_t dv64 = make_smem_desc(vb + ks * 16 * 128, kFlashKB * 128, 1024, kLayoutSW128);
+          const uint64_t dv16 = make_smem_desc(vb + kFlashKB * 128 + ks * 16 * 32, kFlashKB * 32, 256, kLayoutSW32);
+          const uint32_t acc = (accumulate || ks != 0) ? 1u : 0u;
+          umma_bf16_ts(o_tmem, p_tmem + ks * 8, dv64, idesc_o64, acc);
+          umma_bf16_ts(o_tmem + 64, p_tmem + ks * 8, dv16, idesc_o16, acc);
+        }
+      };
+      // tile 1's PV of block nb-1 is deferred by one block so the two tiles run in anti-phase
+      bool pend = false, pend_last = false, pend_acc = false;
+      int pend_st = 0;
+      uint32_t pend_par = 0;
+      auto flush_pending = [&]() {
+        if (!pend) return;
+        mbar_wait(&p_full[1], pend_par);
+        tc_fence_after();
+        issue_pv(1, pend_st, pend_acc);
+        umma_commit(&v_empty[pend_st]);
+        if (pend_last) umma_commit(&o_full[1]);
+        pend = false;
+      };
+      int n = 0, nb = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++n) {
+        mbar_wait(q_full, n & 1);
+        for (int j = 0; j < nkb; ++j, ++nb) {
+          const int st = nb & 1;
+          const uint32_t ring_ph = (nb >> 1) & 1;
+          const uint32_t blk_par = nb & 1;
+          mbar_wait(&k_full[st], ring_ph);
+          if (j == 0) mbar_wait(&s_empty[0], (n & 1) ^ 1);  // previous item's O_0 read out
+          tc_fence_after();
+          issue_qk(0, st);
+          flush_pending();  // tile 1: PV of the previous block (its QK^T for this block comes next)
+          if (j == 0) mbar_wait(&s_empty[1], (n & 1) ^ 1);
+          tc_fence_after();
+          issue_qk(1, st);
+          umma_commit(&k_empty[st]);
+          if (j == nkb - 1) umma_commit(q_empty);
+          mbar_wait(&v_full[st], ring_ph);
+          mbar_wait(&p_full[0], blk_par);
+          tc_fence_after();
+          issue_pv(0, st, j != 0);
+          if (j == nkb - 1) umma_commit(&o_full[0]);
+          pend = true;
+          pend_st = st;
+          pend_par = blk_par;
+          pend_acc = j != 0;
+          pend_last = j == nkb - 1;
+        }
+      }
+      flush_pending();
+    }
+    __syncwarp();
+  } else {
+    // ===================== softmax + correction + epilogue =====================
+    const int t = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t t_row = tmem + 256 * t + (static_cast<uint32_t>(quarter * 32) << 16);
+    float* bias_s = reinterpret_cast<float*>(smem + Cfg::kBias) + (warp - 2) * kFlashKB;
+    constexpr float kLog2e = 1.4426950408889634f;
+    float breg[kFlashKB / 32];
+    auto fetch_bias = [&](int sample, int j) {
+      const float* b = p.bias + static_cast<size_t>(sample) * n_keys + j * kFlashKB;
+#pragma unroll
+      for (int i = 0; i < kFlashKB / 32; ++i) breg[i] = __ldg(b + lane + 32 * i) * kLog2e;
+    };
+    int n = 0, nb = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++n) {
+      const int sh = item / pairs, pr = item - sh * pairs;
+      const int sample = sh / p.heads, head = sh - sample * p.heads;
+      float m_used = -INFINITY, l_sum = 0.f;
+      if constexpr (HAS_BIAS) fetch_bias(sample, 0);
+      for (int j = 0; j < nkb; ++j, ++nb) {
+        if constexpr (HAS_BIAS) {
+#pragma unroll
+          for (int i = 0; i < kFlashKB / 32; ++i) bias_s[lane + 32 * i] = breg[i];
+          __syncwarp();
+          if (j + 1 < nkb) fetch_bias(sample, j + 1);
+        }
+        mbar_wait(&s_full[t], nb & 1);
+        tc_fence_after();
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < kFlashKB / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_row + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if constexpr (HAS_BIAS) b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + i);
+            mx = fmaxf(mx, fmaf(__uint_as_float(v[i + 0]), p.scale_log2e, b4.x));
+            mx = fmaxf(mx, fmaf(__uint_as_float(v[i + 1]), p.scale_log2e, b4.y));
+            mx = fmaxf(mx, fmaf(__uint_as_float(v[i + 2]), p.scale_log2e, b4.z));
+            mx = fmaxf(mx, fmaf(__uint_as_float(v[i + 3]), p.scale_log2e, b4.w));
+          }
+        }
+        // lazy rescale: move the reference maximum only when the block maximum exceeds it by > 8 (log2 units).
+        // tcgen05.ld/st are warp-collective (.sync.aligned): the TMEM round trip runs for the whole warp as soon as
+        // ANY row needs it; rows that do not need it use alpha = 1.
+        const bool need = mx > m_used + 8.0f;
+        const bool rescale = need && j > 0 && m_used != -INFINITY;
+        const float alpha = rescale ? fast_exp2(m_used - mx) : 1.0f;
+        if (__any_sync(0xffffffffu, rescale)) {
+#pragma unroll
+          for (int c = 0; c < 5; ++c) {  // O_t: 80 fp32 columns
+            uint32_t o[16];
+            tmem_ld_32x16(t_row + 128 + c * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x16(t_row + 128 + c * 16, o);
+          }
+        }
+        l_sum *= alpha;
+        if (need) m_used = mx;
+        const float m_eff = m_used == -INFINITY ? 0.f : m_used;  // a fully masked prefix must not produce NaN
+#pragma unroll 1
+        for (int c = 0; c < kFlashKB / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_row + c * 32, v);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if constexpr (HAS_BIAS) b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + i);
+            const float e0 = fast_exp2(fmaf(__uint_as_float(v[i + 0]), p.scale_log2e, b4.x) - m_eff);
+            const float e1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2e, b4.y) - m_eff);
+            const float e2 = fast_exp2(fmaf(__uint_as_float(v[i + 2]), p.scale_log2e, b4.z) - m_eff);
+            const float e3 = fast_exp2(fmaf(__uint_as_float(v[i + 3]), p.scale_log2e, b4.w) - m_eff);
+            l_sum += (e0 + e1) + (e2 + e3);
+            pk[i / 2] = pack_bf16x2(e0, e1);
+            pk[i / 2 + 1] = pack_bf16x2(e2, e3);
+          }
+          tmem_st_32x16(t_row + c * 16, pk);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
+      }
+      // ---- item done: O_t / l -> bf16 -> global
+      mbar_wait(&o_full[t], n & 1);
+      tc_fence_after();
+      const float inv = 1.0f / l_sum;
+      const int q = pr * 256 + t * kAttnBM + row;
+      __nv_bfloat16* dst = p.out + (static_cast<size_t>(sample) * p.q_tokens + q) * p.out_ld + head * kHeadDim;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + 128 + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]) * inv, __uint_as_float(v[g * 8 + 1]) * inv);
+          o.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]) * inv, __uint_as_float(v[g * 8 + 3]) * inv);
+          o.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]) * inv, __uint_as_float(v[g * 8 + 5]) * inv);
+          o.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]) * inv, __uint_as_float(v[g * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = o;
+        }
+      }
+      {
+        uint32_t v[16];
+        tmem_ld_32x16(t_row + 128 + 64, v);
+        tmem_ld_wait();
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
+        o.y = pack_bf16x2(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
+        o.z = pack_bf16x2(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
+        o.w = pack_bf16x2(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
+        *reinterpret_cast<uint4*>(dst + 64) = o;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[t]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace ecadk

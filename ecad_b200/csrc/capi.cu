@@ -322,23 +322,39 @@ int launch_attn_pair_inst(const CUtensorMap* tq, const CUtensorMap* tm, const At
   return check_launch("attn_pair_kernel");
 }
 
+template <bool HAS_BIAS>
+int launch_attn_flash_inst(const CUtensorMap* tq, const CUtensorMap* tkv, const AttnParams& p, int n_keys, int items,
+                           cudaStream_t stream) {
+  static bool configured = false;
+  auto kern = attn_flash_kernel<HAS_BIAS>;
+  if (!configured) {
+    ECADK_CHECK_CUDA(
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnFlashCfg::kSmemBytes));
+    configured = true;
+  }
+  const int grid = items < num_sms() ? items : num_sms();
+  kern<<<grid, kAttnPairThreads, AttnFlashCfg::kSmemBytes, stream>>>(tq[0], tq[1], tkv[0], tkv[1], tkv[2], tkv[3], p,
+                                                                      n_keys, items);
+  return check_launch("attn_flash_kernel");
+}
+
 int launch_attention(const void* q, const void* k, const void* v, const float* bias, void* out, int samples,
                      int heads, int q_tokens, int n_keys, cudaStream_t stream) {
   ECADK_REQUIRE(q && k && v && out, "attention: null pointer");
-  ECADK_REQUIRE(n_keys == 128 || n_keys == 256, "attention: n_keys=%d (supported: 128, 256)", n_keys);
+  ECADK_REQUIRE(n_keys > 0 && n_keys % 128 == 0, "attention: n_keys=%d must be a multiple of 128", n_keys);
   ECADK_REQUIRE(q_tokens > 0 && q_tokens % kAttnBM == 0, "attention: q_tokens=%d must be a multiple of 128", q_tokens);
+  ECADK_REQUIRE(n_keys <= 256 || q_tokens % 256 == 0,
+                "attention: q_tokens=%d must be a multiple of 256 when n_keys > 256", q_tokens);
   ECADK_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(out), "attention: 16-byte alignment");
   const uint64_t q_rows = static_cast<uint64_t>(samples) * heads * q_tokens;
   const uint64_t k_rows = static_cast<uint64_t>(samples) * heads * n_keys;
   ProfScope prof(ECADK_PROF_ATTENTION, 4.0 * samples * heads * q_tokens * n_keys * kHeadDim, 0.0, stream);
-  CUtensorMap tm[6];
-  int rc;
-  if ((rc = make_tmap_bf16(&tm[0], q, q_rows, kHeadPad, kHeadPad, kAttnBM, 64, 128))) return rc;
-  if ((rc = make_tmap_bf16(&tm[1], q, q_rows, kHeadPad, kHeadPad, kAttnBM, 16, 32))) return rc;
-  if ((rc = make_tmap_bf16(&tm[2], k, k_rows, kHeadPad, kHeadPad, n_keys, 64, 128))) return rc;
-  if ((rc = make_tmap_bf16(&tm[3], k, k_rows, kHeadPad, kHeadPad, n_keys, 16, 32))) return rc;
-  if ((rc = make_tmap_bf16(&tm[4], v, k_rows, kHeadPad, kHeadPad, n_keys, 64, 128))) return rc;
-  if ((rc = make_tmap_bf16(&tm[5], v, k_rows, kHeadPad, kHeadPad, n_keys, 16, 32))) return rc;
+  // ECADK_ATTN_MODE=tile / flash force the one-tile-per-CTA / the streaming kernel (A/B measurements)
+  static const int forced = [] {
+    const char* e = getenv("ECADK_ATTN_MODE");
+    if (e == nullptr) return 0;
+    return strcmp(e, "tile") == 0 ? 1 : (strcmp(e, "flash") == 0 ? 2 : 0);
+  }();
   AttnParams p;
   p.heads = heads;
   p.q_tokens = q_tokens;
@@ -346,13 +362,29 @@ int launch_attention(const void* q, const void* k, const void* v, const float* b
   p.scale_log2e = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(kHeadDim)));
   p.bias = bias;
   p.out = static_cast<__nv_bfloat16*>(out);
-  // ECADK_ATTN_MODE=tile forces the one-tile-per-CTA kernel (A/B measurements); default: the persistent pair
-  // kernel whenever a (sample, head) has exactly two 128-query tiles (PixArt 256x256).
-  static const bool force_tile = [] {
-    const char* e = getenv("ECADK_ATTN_MODE");
-    return e != nullptr && strcmp(e, "tile") == 0;
-  }();
-  if (q_tokens == 256 && !force_tile) {
+  int rc;
+  const bool use_flash = (n_keys > 256 || q_tokens > 256 || forced == 2) && q_tokens % 256 == 0;
+  if (use_flash) {
+    // long key sequences: stream 128-key blocks with an online softmax
+    CUtensorMap tq[2], tkv[4];
+    if ((rc = make_tmap_bf16(&tq[0], q, q_rows, kHeadPad, kHeadPad, 256, 64, 128))) return rc;
+    if ((rc = make_tmap_bf16(&tq[1], q, q_rows, kHeadPad, kHeadPad, 256, 16, 32))) return rc;
+    if ((rc = make_tmap_bf16(&tkv[0], k, k_rows, kHeadPad, kHeadPad, kFlashKB, 64, 128))) return rc;
+    if ((rc = make_tmap_bf16(&tkv[1], k, k_rows, kHeadPad, kHeadPad, kFlashKB, 16, 32))) return rc;
+    if ((rc = make_tmap_bf16(&tkv[2], v, k_rows, kHeadPad, kHeadPad, kFlashKB, 64, 128))) return rc;
+    if ((rc = make_tmap_bf16(&tkv[3], v, k_rows, kHeadPad, kHeadPad, kFlashKB, 16, 32))) return rc;
+    const int items = samples * heads * (q_tokens / 256);
+    return bias ? launch_attn_flash_inst<true>(tq, tkv, p, n_keys, items, stream)
+                : launch_attn_flash_inst<false>(tq, tkv, p, n_keys, items, stream);
+  }
+  CUtensorMap tm[6];
+  if ((rc = make_tmap_bf16(&tm[0], q, q_rows, kHeadPad, kHeadPad, kAttnBM, 64, 128))) return rc;
+  if ((rc = make_tmap_bf16(&tm[1], q, q_rows, kHeadPad, kHeadPad, kAttnBM, 16, 32))) return rc;
+  if ((rc = make_tmap_bf16(&tm[2], k, k_rows, kHeadPad, kHeadPad, n_keys, 64, 128))) return rc;
+  if ((rc = make_tmap_bf16(&tm[3], k, k_rows, kHeadPad, kHeadPad, n_keys, 16, 32))) return rc;
+  if ((rc = make_tmap_bf16(&tm[4], v, k_rows, kHeadPad, kHeadPad, n_keys, 64, 128))) return rc;
+  if ((rc = make_tmap_bf16(&tm[5], v, k_rows, kHeadPad, kHeadPad, n_keys, 16, 32))) return rc;
+  if (q_tokens == 256 && forced != 1) {
     CUtensorMap tq[2];
     if ((rc = make_tmap_bf16(&tq[0], q, q_rows, kHeadPad, kHeadPad, 256, 64, 128))) return rc;
     if ((rc = make_tmap_bf16(&tq[1], q, q_rows, kHeadPad, kHeadPad, 256, 16, 32))) return rc;
@@ -689,7 +721,9 @@ int ecadk_pixart_blocks(ecadk_handle_t h, const EcadkBlocksArgs* a, const uint8_
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int D = d.dim, M = a->samples * a->tokens, S6 = a->temb_stride;
   ECADK_REQUIRE(S6 == 0 || S6 == 6 * D, "pixart_blocks: temb_stride must be 0 or 6*dim");
-  ECADK_REQUIRE(a->tokens == 256, "pixart_blocks: tokens=%d (this build covers N=256 self-attention)", a->tokens);
+  ECADK_REQUIRE(a->tokens > 0 && a->tokens % 256 == 0, "pixart_blocks: tokens=%d must be a multiple of 256", a->tokens);
+  ECADK_REQUIRE(a->text_pad > 0 && a->text_pad % 128 == 0, "pixart_blocks: text_pad=%d must be a multiple of 128",
+                a->text_pad);
   int launches = 0;
   int rc;
 

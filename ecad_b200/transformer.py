@@ -17,7 +17,7 @@ HBM layout (S = samples = 2B with CFG, N image tokens, D = 1152, H = 16, T text 
   attn_o   bf16 [S*N, D]      attention output, A operand of the out projection
   ffh      bf16 [S*N, 4D]     GELU hidden
   cache    bf16 [L*3, S*N, D] the reference's cached_attn1/attn2/ff_output of all 28 blocks
-  k2, v2   bf16 [L][S,H,128,80] caption keys/values, projected once per generation
+  k2, v2   bf16 [L][S,H,Tp,80] caption keys/values (Tp = text tokens padded to 128 / 384), once per generation
 """
 from __future__ import annotations
 
@@ -34,7 +34,6 @@ from .registry import ComputeAttnRegistry, ComputeFFRegistry, DecisionContext
 from .schedule import PixArtCacheSchedule
 from .weights import PixArtConfig, random_init_state_dict
 
-TEXT_PAD = 128
 
 
 @dataclass
@@ -244,6 +243,8 @@ class B200PixArtTransformer2D:
         self._ws = {}  # drop the old workspace before allocating the new one
         ws: dict[str, Any] = {}
         M = S * N
+        TEXT_PAD = ((T + 127) // 128) * 128  # 120 -> 128 (alpha), 300 -> 384 (sigma)
+        ws["text_pad"] = TEXT_PAD
         ws["x"] = torch.empty(M, D, device=dev, dtype=f32)
         for n in ("xb", "h", "attn_o"):
             ws[n] = torch.empty(M, D, device=dev, dtype=bf)
@@ -340,11 +341,10 @@ class B200PixArtTransformer2D:
         N = hp * wp
         T = encoder_hidden_states.shape[1]
         D = cfg.inner_dim
-        if N != 256:
-            raise NotImplementedError(f"{N} image tokens: this build covers 256x256 (N=256) self-attention only")
-        if T > TEXT_PAD:
-            raise NotImplementedError(f"{T} text tokens > {TEXT_PAD}: PixArt-sigma (T=300) not built yet")
+        if N % 256:
+            raise NotImplementedError(f"{N} image tokens: the attention kernels need a multiple of 256 queries")
         ws = self._workspace(S, N, T, hl, wl)
+        TEXT_PAD = ws["text_pad"]
         st = _lib.stream_ptr()
         launches = 0
 

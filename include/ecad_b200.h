@@ -150,8 +150,9 @@ int ecadk_gemm_bias_headmajor(const void* a, const void* w, const float* bias, v
                               int n_parts, int heads, int tokens, int tokens_pad, int m, int k,
                               ecadk_stream_t stream);
 
-/* softmax(Q K^T / sqrt(72) + bias) V for one-tile key sequences.
- * q bf16 [samples, heads, q_tokens, 80]; k, v bf16 [samples, heads, n_keys, 80] (n_keys in {128, 256});
+/* softmax(Q K^T / sqrt(72) + bias) V.  n_keys <= 256 with q_tokens == 256: single-pass kernel (whole score row in
+ * TMEM); otherwise keys are streamed in blocks of 128 with an online softmax (q_tokens % 256 == 0 required).
+ * q bf16 [samples, heads, q_tokens, 80]; k, v bf16 [samples, heads, n_keys, 80] (n_keys % 128 == 0);
  * bias fp32 [samples, n_keys] or NULL; out bf16 [samples, q_tokens, heads*72].
  * Replaces F.scaled_dot_product_attention inside AttnProcessor2_0 (cached_transformer_block.py:348-353). */
 int ecadk_attention(const void* q, const void* k, const void* v, const float* bias, void* out, int samples,
@@ -188,7 +189,7 @@ int ecadk_destroy(ecadk_handle_t h);
 typedef struct {
   int samples;      /* 2B with CFG */
   int tokens;       /* N image tokens per sample */
-  int text_pad;     /* padded key count of the cross-attention (128) */
+  int text_pad;     /* padded key count of the cross-attention: text tokens rounded up to a multiple of 128 */
   float* x;         /* fp32 [samples*tokens, dim] residual stream (in/out) */
   void* xb;         /* bf16 scratch [samples*tokens, dim] */
   void* h;          /* bf16 scratch [samples*tokens, dim] */

@@ -134,6 +134,39 @@ def test_attention(cuda_device, samples, nk, use_bias):
     assert float((out.float() - ref).abs().mean() / ref.abs().mean()) < 6e-3
 
 
+@pytest.mark.parametrize("samples,q_tokens,nk,real_keys", [
+    (1, 512, 512, None),     # self-attention, 4 key blocks, two query pairs
+    (2, 1024, 1024, None),   # PixArt 512x512 self-attention shape
+    (2, 256, 384, 300),      # PixArt-sigma cross-attention: 300 text tokens padded to 384
+    (1, 1024, 128, 120),     # cross-attention at 512x512: many queries, one key block
+])
+def test_attention_streaming(cuda_device, samples, q_tokens, nk, real_keys):
+    """Keys streamed in 128-key blocks with an online softmax (lazy rescale) == one-shot softmax."""
+    from ecad_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(q_tokens + nk)
+
+    def mk(tokens, scale):
+        t = torch.zeros(samples, H, tokens, HP, device="cuda", dtype=torch.bfloat16)
+        t[..., :HD] = _bf(torch.randn(samples, H, tokens, HD, device="cuda", generator=g) * scale)
+        return t
+
+    # large score spread (scale 3) so the running maximum really moves between blocks and the rescale path runs
+    q, k, v = mk(q_tokens, 3.0), mk(nk, 3.0), mk(nk, 1.0)
+    bias = None
+    if real_keys is not None:
+        bias = torch.zeros(samples, nk, device="cuda")
+        for s in range(samples):
+            bias[s, real_keys - 17 * (s + 1):real_keys] = -10000.0
+        bias[:, real_keys:] = float("-inf")
+    out = torch.full((samples, q_tokens, H * HD), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.attention(q, k, v, bias, out, samples, H, q_tokens, nk)
+    torch.cuda.synchronize()
+    ref = _attn_ref(q[..., :HD], k[..., :HD], v[..., :HD], bias)
+    assert torch.isfinite(out.float()).all()
+    assert _rel_err(out, ref) < 2e-2, _rel_err(out, ref)
+    assert float((out.float() - ref).abs().mean() / ref.abs().mean()) < 8e-3
+
+
 def test_attention_all_masked_row_is_uniform(cuda_device):
     """mask of all zeros -> every real key gets -10000 -> softmax is uniform over the REAL keys (reference
     semantics of the additive -10000 bias, pixart_transformer_2d_edited.py:282-289), padding keys excluded."""

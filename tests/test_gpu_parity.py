@@ -105,6 +105,65 @@ def test_generation_matches_oracle(cuda_device, weights, schedule_file, batch):
     assert not gen.diffusion_pipeline.transformer._has_cache.any()
 
 
+@pytest.mark.parametrize("sample_size,text_tokens", [(64, 120), (32, 300)])
+def test_single_forward_other_shapes(cuda_device, sample_size, text_tokens):
+    """BASELINE configs 3 / 4 shapes on one forward: PixArt-alpha 512x512 (N = 1024 image tokens, streamed
+    self-attention) and PixArt-sigma's 300-token captions (cross-attention keys padded to 384)."""
+    from ecad_b200.schedule import PixArtCacheSchedule
+    from ecad_b200.transformer import B200PixArtTransformer2D, SequentialDiTScheduler
+    from ecad_b200.weights import PixArtConfig, random_init_state_dict, synthetic_prompt_embeddings
+    from oracle.pixart_oracle import OracleConfig, OracleSchedule, PixArtOracle
+
+    cfg = PixArtConfig(sample_size=sample_size, num_layers=4)
+    sd = random_init_state_dict(cfg, seed=2)
+    emb = synthetic_prompt_embeddings(1, text_tokens=text_tokens, seed=3)
+    lat = torch.randn(1, 4, sample_size, sample_size, generator=torch.Generator().manual_seed(4))
+    x_in = torch.cat([lat, lat])
+    e_in = torch.cat([emb["negative_prompt_embeds"], emb["prompt_embeds"]])
+    m_in = torch.cat([emb["negative_prompt_attention_mask"], emb["prompt_attention_mask"]])
+    ts = torch.full((2,), 749, dtype=torch.int64)
+    flags = np.ones((2, 4, 3), bool)
+    ocfg = OracleConfig(sample_size=sample_size, num_layers=4)
+    ref = PixArtOracle(sd, ocfg, OracleSchedule.from_flags(flags)).forward(x_in, e_in, ts, None, m_in)
+    tr = B200PixArtTransformer2D(sd, cfg, SequentialDiTScheduler(2), PixArtCacheSchedule.default(2, 4))
+    out = tr(x_in.cuda(), encoder_hidden_states=e_in.cuda(), encoder_attention_mask=m_in.cuda(), timestep=ts.cuda(),
+             added_cond_kwargs={"resolution": None, "aspect_ratio": None}, return_dict=False)[0].cpu()
+    assert out.shape == ref.shape == (2, 8, sample_size, sample_size)
+    rel = float((out - ref).abs().max() / ref.abs().max())
+    assert rel < 5e-3, rel
+    assert _cos(out, ref) > 0.99999
+
+
+def test_cached_generation_512px_small_model(cuda_device):
+    """A cached multi-step generation at 512x512 (N = 1024 tokens) on a 6-block model: exercises the streamed
+    self-attention together with the reuse / fused-residual paths at a second resolution."""
+    from ecad_b200.image_generator import B200PixArtAlphaImageGenerator
+    from ecad_b200.schedule import PixArtCacheSchedule
+    from ecad_b200.weights import PixArtConfig, random_init_state_dict, synthetic_prompt_embeddings
+    from oracle.pixart_oracle import OracleConfig, OracleSchedule, PixArtOracle, generate_latents
+
+    L, steps = 6, 5
+    cfg = PixArtConfig(sample_size=64, num_layers=L)
+    sd = random_init_state_dict(cfg, seed=5)
+    rng = np.random.default_rng(3)
+    flags = rng.random((steps, L, 3)) < 0.45
+    emb = synthetic_prompt_embeddings(1, seed=9)
+    traces = []
+    gen = B200PixArtAlphaImageGenerator(
+        cache_schedule=PixArtCacheSchedule.from_numpy(flags, steps, L, "rand512"), start_seed=0, state_dict=sd,
+        model_config=cfg,
+        additional_callbacks=[lambda s, t, **kw: traces.append(gen.diffusion_pipeline.transformer.last_executed.copy())])
+    got = gen.generate_images(emb, images_per_prompt=1)[0].cpu()
+    assert got.shape == (1, 4, 64, 64)
+    model = PixArtOracle(sd, OracleConfig(sample_size=64, num_layers=L), OracleSchedule.from_flags(flags))
+    noise = torch.randn(1, 4, 64, 64, generator=torch.Generator().manual_seed(0))
+    ref = generate_latents(model, emb["prompt_embeds"], emb["prompt_attention_mask"], emb["negative_prompt_embeds"],
+                           emb["negative_prompt_attention_mask"], noise, steps)["latents"]
+    assert np.array_equal(np.stack(traces), model.trace.to_numpy(steps, L))
+    assert float((got - ref).abs().max() / ref.abs().max()) <= PER_STEP_REL_MAXABS
+    assert _cos(got, ref) >= FINAL_COS
+
+
 def test_tgate_generation_matches_oracle(cuda_device, weights):
     """TGATE (ecad/pipelines/tgate.py + compute_attn_tgate): CFG pair until the gate step, the cross-attention cache
     averaged at gate_step - 1, then the null embedding alone with attn2 always served from the averaged cache."""
