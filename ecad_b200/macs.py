@@ -96,3 +96,36 @@ def flops_per_image(executed: np.ndarray, shape: PixArtShape, samples_per_image:
     comp = shape.flops_components()
     per_step = shape.flops_fixed() + (executed.astype(np.int64) * comp[None, None, :]).sum(axis=(1, 2))
     return int(per_step.sum()) * samples_per_image
+
+
+@dataclass(frozen=True)
+class FluxShape:
+    """FLUX.1-dev MAC model in the reference's calflops convention."""
+
+    tokens: int = 256  # image tokens N = (H/16)*(W/16)
+    text_tokens: int = 512
+    dim: int = 3072
+    num_blocks: int = 19
+    num_single_blocks: int = 38
+
+    def macs_components(self) -> np.ndarray:
+        """int64[NB + NS][3] per-sample MACs of each cacheable component, rows in FluxCacheSchedule.dense() order."""
+        N, T, D = self.tokens, self.text_tokens, self.dim
+        S = N + T
+        full = [4 * S * D * D, 8 * N * D * D, 8 * T * D * D]
+        single = [3 * S * D * D, 4 * S * D * D, 5 * S * D * D]
+        return np.array([full] * self.num_blocks + [single] * self.num_single_blocks, dtype=np.int64)
+
+    def macs_always(self) -> int:
+        """Modulation linears that run even when every component is reused + the embedders / output head."""
+        N, T, D = self.tokens, self.text_tokens, self.dim
+        per_block = 12 * D * D * self.num_blocks + 3 * D * D * self.num_single_blocks
+        fixed = 64 * N * D + T * 4096 * D + 2 * (256 * D + D * D) + (768 * D + D * D) + 2 * D * D + 64 * N * D
+        return per_block + fixed
+
+
+def flux_macs_per_step(executed: np.ndarray, shape: FluxShape, batch: int = 2) -> np.ndarray:
+    executed = np.asarray(executed)
+    comp = shape.macs_components()
+    per = shape.macs_always() + (executed.astype(np.int64) * comp[None]).sum(axis=(1, 2))
+    return per * batch

@@ -255,3 +255,66 @@ def schedule_from_packed(row: dict[str, Any]) -> PixArtCacheSchedule:
         bits.reshape(S, NB, 3).astype(np.bool_), S, NB, row["name"], custom_compute_attn=custom,
         top_level_config=row.get("config") or {}, attributes=row.get("attributes") or {},
     )
+
+
+FLUX_FULL_COMPONENTS = ("full_attn", "full_ff", "full_ff_context")
+FLUX_SINGLE_COMPONENTS = ("single_attn", "single_proj_mlp", "single_proj_out")
+
+
+class FluxCacheSchedule(CacheSchedule):
+    """FLUX.1 schedule: 19 double-stream blocks x (full_attn, full_ff, full_ff_context) and 38 single-stream blocks x
+    (single_attn, single_proj_mlp, single_proj_out); block keys "0".."18" and "single_0".."single_37".
+    Mirrors ecad/schedulers/cache_scheduler/flux_cache_schedule.py:13-90 (same constructor contract: a missing
+    ``num_single_blocks`` raises ValueError; ``to_numpy`` only supports ``flatten=True``)."""
+
+    components = FLUX_SINGLE_COMPONENTS + FLUX_FULL_COMPONENTS
+
+    def __init__(self, num_blocks, num_inference_steps, name, schedule, top_level_config=None, attributes=None,
+                 metrics=None, num_single_blocks: int | None = None, **kwargs: Any) -> None:
+        super().__init__(num_blocks, num_inference_steps, name, schedule, top_level_config, attributes, metrics)
+        if num_single_blocks is None:
+            raise ValueError("num_single_blocks must be provided for FluxCacheSchedule")
+        self.num_single_blocks = int(num_single_blocks)
+
+    def block_keys(self) -> list[str]:
+        return [str(b) for b in range(self.num_blocks)] + [f"single_{b}" for b in range(self.num_single_blocks)]
+
+    def to_dict(self) -> dict[str, Any]:
+        data = super().to_dict()
+        data["cache_schedule"]["num_single_blocks"] = self.num_single_blocks
+        return data
+
+    def dense(self) -> np.ndarray:
+        """``bool[S][NB + NS][3]``: double blocks first, then single blocks, reference component order per kind."""
+        arr = np.zeros((self.num_inference_steps, self.num_blocks + self.num_single_blocks, 3), dtype=np.bool_)
+        for step, blocks in self.schedule.items():
+            for key, comp in blocks.items():
+                if key.startswith("single_"):
+                    r, names = self.num_blocks + int(key[len("single_"):]), FLUX_SINGLE_COMPONENTS
+                else:
+                    r, names = int(key), FLUX_FULL_COMPONENTS
+                for i, c in enumerate(names):
+                    arr[step, r, i] = comp[c]
+        return arr
+
+    def to_numpy(self, flatten: bool = True) -> np.ndarray:
+        """Genome: per step all double-block flags then all single-block flags (flux_cache_schedule.py:62-90)."""
+        if not flatten:
+            raise NotImplementedError("FluxCacheSchedule only supports flatten=True")
+        return self.dense().reshape(-1)
+
+    @classmethod
+    def from_numpy(cls, flags, num_inference_steps: int = 20, num_blocks: int = 19, num_single_blocks: int = 38,
+                   name: str = "from_numpy", top_level_config=None, attributes=None, metrics=None):
+        arr = np.asarray(flags).astype(np.bool_).reshape(num_inference_steps, num_blocks + num_single_blocks, 3)
+        sched: dict[int, dict[str, dict[str, bool]]] = {}
+        for s in range(num_inference_steps):
+            blocks: dict[str, dict[str, bool]] = {}
+            for b in range(num_blocks):
+                blocks[str(b)] = {c: bool(arr[s, b, i]) for i, c in enumerate(FLUX_FULL_COMPONENTS)}
+            for b in range(num_single_blocks):
+                blocks[f"single_{b}"] = {c: bool(arr[s, num_blocks + b, i])
+                                         for i, c in enumerate(FLUX_SINGLE_COMPONENTS)}
+            sched[s] = blocks
+        return cls(num_blocks, num_inference_steps, name, sched, top_level_config, attributes, metrics,
+                   num_single_blocks=num_single_blocks)
