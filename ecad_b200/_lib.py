@@ -139,7 +139,7 @@ def load() -> C.CDLL:
         "ecadk_residual_ln": [C.POINTER(EcadkResidualLnArgs), p],
         "ecadk_patch_embed": [p, p, p, p, p, i, i, i, i, i, p],
         "ecadk_timestep_sinusoid": [p, p, i, i, p],
-        "ecadk_small_linear": [p, p, p, p, i, i, i, i, i, i, i, p],
+        "ecadk_small_linear": [p, i, p, p, p, i, i, i, i, i, i, i, p],
         "ecadk_cast_f32_bf16": [p, p, sz, p],
         "ecadk_mask_bias": [p, p, i, i, i, p],
         "ecadk_average_halves": [p, sz, p],

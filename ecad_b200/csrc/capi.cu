@@ -505,11 +505,12 @@ int ecadk_timestep_sinusoid(const float* t, float* out, int samples, int dim, ec
   return check_launch("timestep_sinusoid_kernel");
 }
 
-int ecadk_small_linear(const float* x, const float* w, const float* b, float* y, int samples, int k, int o, int ldy,
-                       int y_off, int act_in, int accumulate, ecadk_stream_t stream) {
+int ecadk_small_linear(const float* x, int ldx, const float* w, const float* b, float* y, int samples, int k, int o,
+                       int ldy, int y_off, int act_in, int accumulate, ecadk_stream_t stream) {
   ECADK_REQUIRE(x && w && b && y && samples > 0 && k > 0 && o > 0, "small_linear: bad args");
   ProfScope prof(ECADK_PROF_OTHER, 0.0, 0.0, static_cast<cudaStream_t>(stream));
-  SmallLinearParams p{x, w, b, y, samples, k, o, ldy, y_off, act_in, accumulate};
+  ECADK_REQUIRE(ldx >= k, "small_linear: ldx=%d < k=%d", ldx, k);
+  SmallLinearParams p{x, w, b, y, samples, k, o, ldy, y_off, act_in, accumulate, ldx};
   small_linear_kernel<<<dim3((o + 7) / 8, (samples + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   return check_launch("small_linear_kernel");
 }

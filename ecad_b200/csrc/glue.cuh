@@ -250,11 +250,11 @@ __global__ void __launch_bounds__(288) patch_embed_kernel(const PatchEmbedParams
 // K14 helpers.  y[s, o] = b[o] + sum_i W[o, i] * act_in(x[s, i]);  act_in: 0 none, 1 SiLU.  fp32 throughout.
 // One warp per output feature; the weight row is read once and reused across all samples.
 struct SmallLinearParams {
-  const float* x;  // [S, K]
+  const float* x;  // [S, K] with row pitch ldx
   const float* w;  // [O, K]
   const float* b;  // [O]
   float* y;        // [S, ldy] written at column offset y_off
-  int S, K, O, ldy, y_off, act_in, accumulate;
+  int S, K, O, ldy, y_off, act_in, accumulate, ldx;
 };
 __global__ void __launch_bounds__(256) small_linear_kernel(const SmallLinearParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const SmallLinearPara
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         if (s0 + j < p.S) {
-          float a = __ldg(p.x + static_cast<size_t>(s0 + j) * p.K + k);
+          float a = __ldg(p.x + static_cast<size_t>(s0 + j) * p.ldx + k);
           if (p.act_in == 1) a = a / (1.f + __expf(-a));
           acc[j] = fmaf(w, a, acc[j]);
         }

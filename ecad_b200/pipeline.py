@@ -163,6 +163,14 @@ class B200PixArtPipeline:
                                        latents).contiguous()
         x0_prev = torch.zeros_like(latents)
         added_cond_kwargs = {"resolution": None, "aspect_ratio": None}
+        if cfgm.sample_size == 128 and getattr(tr.cfg, "resolved_additional_conditions", False):
+            # 6.1 micro-conditions of the 1024-MS checkpoints (pass_through.py:268-290)
+            resolution = torch.tensor([float(height), float(width)]).repeat(batch_size, 1)
+            aspect_ratio = torch.tensor([float(height / width)]).repeat(batch_size, 1)
+            if do_cfg:
+                resolution = torch.cat([resolution, resolution], dim=0)
+                aspect_ratio = torch.cat([aspect_ratio, aspect_ratio], dim=0)
+            added_cond_kwargs = {"resolution": resolution.to(dev), "aspect_ratio": aspect_ratio.to(dev)}
         lib = _lib.load()
         hw = latents.shape[-2] * latents.shape[-1]
         learned_sigma = cfgm.out_channels // 2 == latent_channels
@@ -171,15 +179,17 @@ class B200PixArtPipeline:
 
         for i, t in enumerate(timesteps):
             gated = self.gate_step is not None and i >= self.gate_step
+            cond_in = added_cond_kwargs
             if gated:
                 model_in, e_in, m_in = latents, negative_prompt_embeds, negative_prompt_attention_mask
+                cond_in = {k: (v[:batch_size] if v is not None else None) for k, v in added_cond_kwargs.items()}
             else:
                 model_in = torch.cat([latents] * 2) if do_cfg else latents
                 e_in, m_in = embeds, mask
             model_in = sched.scale_model_input(model_in, t)
             current_timestep = t[None].to(dev).expand(model_in.shape[0])
             noise_pred = tr(model_in, encoder_hidden_states=e_in, encoder_attention_mask=m_in,
-                            timestep=current_timestep, added_cond_kwargs=added_cond_kwargs, return_dict=False)[0]
+                            timestep=current_timestep, added_cond_kwargs=cond_in, return_dict=False)[0]
             c = sched.coefficients()
             _lib.check(
                 lib.ecadk_cfg_dpm_step(noise_pred.data_ptr(), latents.data_ptr(), x0_prev.data_ptr(), batch_size,

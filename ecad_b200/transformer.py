@@ -117,8 +117,6 @@ class B200PixArtTransformer2D:
             dit_scheduler.num_inference_steps, config.num_layers)
         if config.attention_head_dim != _lib.HEAD_DIM:
             raise ValueError("libecad_b200 is specialised for attention_head_dim = 72")
-        if config.resolved_additional_conditions:
-            raise NotImplementedError("1024-MS additional conditions (resolution/aspect-ratio embedders) not built yet")
         self._pack_weights(state_dict)
         self._ws: dict[str, Any] = {}
         self._ws_key: tuple | None = None
@@ -165,6 +163,11 @@ class B200PixArtTransformer2D:
         for i, nm in enumerate(("linear_1", "linear_2")):
             w[f"t_w{i}"] = f32(sd[f"adaln_single.emb.timestep_embedder.{nm}.weight"])
             w[f"t_b{i}"] = f32(sd[f"adaln_single.emb.timestep_embedder.{nm}.bias"])
+        if cfg.resolved_additional_conditions:  # PixArt-alpha 1024-MS: resolution + aspect-ratio embedders
+            for nm in ("resolution_embedder", "aspect_ratio_embedder"):
+                for i, lin in enumerate(("linear_1", "linear_2")):
+                    w[f"{nm}_w{i}"] = f32(sd[f"adaln_single.emb.{nm}.{lin}.weight"])
+                    w[f"{nm}_b{i}"] = f32(sd[f"adaln_single.emb.{nm}.{lin}.bias"])
         w["ada_w"] = f32(sd["adaln_single.linear.weight"])
         w["ada_b"] = f32(sd["adaln_single.linear.bias"])
         w["cap_w1"] = bf16(sd["caption_projection.linear_1.weight"])
@@ -356,7 +359,12 @@ class B200PixArtTransformer2D:
         # adaLN-single: sinusoid -> MLP -> SiLU -> Linear(D, 6D)  (:308-313)
         # The pipeline broadcasts ONE timestep over the batch (`t[None].expand(batch)`, pass_through.py:326-329):
         # a stride-0 / single-element timestep is embedded once and every kernel reads it with row pitch 0.
-        shared_t = timestep.numel() == 1 or (timestep.ndim == 1 and timestep.stride(0) == 0)
+        addc = cfg.resolved_additional_conditions
+        if addc and (added_cond_kwargs is None or added_cond_kwargs.get("resolution") is None):
+            # pixart_transformer_2d_edited.py:206-209
+            raise ValueError("`added_cond_kwargs` cannot be None when using additional conditions for `adaln_single`.")
+        # (per-sample micro-conditions make the embedding per-sample, so the shared-timestep shortcut is off then)
+        shared_t = (not addc) and (timestep.numel() == 1 or (timestep.ndim == 1 and timestep.stride(0) == 0))
         St = 1 if shared_t else S
         t32 = timestep.reshape(-1)[:1] if shared_t else timestep.reshape(-1)
         if not shared_t and t32.numel() != S:
@@ -366,11 +374,38 @@ class B200PixArtTransformer2D:
         emb_stride = 0 if shared_t else D
         ws["args"].temb_stride = temb_stride
         _lib.check(lib.ecadk_timestep_sinusoid(t32.data_ptr(), ws["t_proj"].data_ptr(), St, 256, st), "sinusoid")
-        _lib.check(lib.ecadk_small_linear(ws["t_proj"].data_ptr(), w["t_w0"].data_ptr(), w["t_b0"].data_ptr(),
+        _lib.check(lib.ecadk_small_linear(ws["t_proj"].data_ptr(), 256, w["t_w0"].data_ptr(), w["t_b0"].data_ptr(),
                                           ws["t_e1"].data_ptr(), St, 256, D, D, 0, 0, 0, st), "t_mlp1")
-        _lib.check(lib.ecadk_small_linear(ws["t_e1"].data_ptr(), w["t_w1"].data_ptr(), w["t_b1"].data_ptr(),
+        _lib.check(lib.ecadk_small_linear(ws["t_e1"].data_ptr(), D, w["t_w1"].data_ptr(), w["t_b1"].data_ptr(),
                                           ws["t_emb"].data_ptr(), St, D, D, D, 0, 1, 0, st), "t_mlp2")
-        _lib.check(lib.ecadk_small_linear(ws["t_emb"].data_ptr(), w["ada_w"].data_ptr(), w["ada_b"].data_ptr(),
+        if addc:
+            # PixArtAlphaCombinedTimestepSizeEmbeddings: emb += cat([res_emb(h), res_emb(w), ar_emb]) with each
+            # micro-condition through its own sinusoid -> Linear(256,384) -> SiLU -> Linear(384,384)
+            E = D // 3
+            res = added_cond_kwargs["resolution"].to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+            ar = added_cond_kwargs["aspect_ratio"].to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+            if res.numel() != 2 * S or ar.numel() != S:
+                raise ValueError("resolution must be (batch, 2) and aspect_ratio (batch, 1)")
+            c_proj = torch.empty(3 * S, 256, device=dev, dtype=torch.float32)
+            c_e1 = torch.empty(3 * S, E, device=dev, dtype=torch.float32)
+            _lib.check(lib.ecadk_timestep_sinusoid(res.data_ptr(), c_proj.data_ptr(), 2 * S, 256, st), "res_sin")
+            _lib.check(lib.ecadk_timestep_sinusoid(ar.data_ptr(), c_proj[2 * S:].data_ptr(), S, 256, st), "ar_sin")
+            _lib.check(lib.ecadk_small_linear(c_proj.data_ptr(), 256, w["resolution_embedder_w0"].data_ptr(),
+                                              w["resolution_embedder_b0"].data_ptr(), c_e1.data_ptr(), 2 * S, 256, E,
+                                              E, 0, 0, 0, st), "res_mlp1")
+            _lib.check(lib.ecadk_small_linear(c_proj[2 * S:].data_ptr(), 256, w["aspect_ratio_embedder_w0"].data_ptr(),
+                                              w["aspect_ratio_embedder_b0"].data_ptr(), c_e1[2 * S:].data_ptr(), S,
+                                              256, E, E, 0, 0, 0, st), "ar_mlp1")
+            # second linears accumulate straight into the three thirds of the timestep embedding
+            for part in range(2):  # (height, width) rows of c_e1 are interleaved per sample: row pitch 2*E
+                _lib.check(lib.ecadk_small_linear(c_e1[part:].data_ptr(), 2 * E, w["resolution_embedder_w1"].data_ptr(),
+                                                  w["resolution_embedder_b1"].data_ptr(), ws["t_emb"].data_ptr(), S,
+                                                  E, E, D, part * E, 1, 1, st), "res_mlp2")
+            _lib.check(lib.ecadk_small_linear(c_e1[2 * S:].data_ptr(), E, w["aspect_ratio_embedder_w1"].data_ptr(),
+                                              w["aspect_ratio_embedder_b1"].data_ptr(), ws["t_emb"].data_ptr(), S, E,
+                                              E, D, 2 * E, 1, 1, st), "ar_mlp2")
+            launches += 7
+        _lib.check(lib.ecadk_small_linear(ws["t_emb"].data_ptr(), D, w["ada_w"].data_ptr(), w["ada_b"].data_ptr(),
                                           ws["temb6"].data_ptr(), St, D, 6 * D, 6 * D, 0, 1, 0, st), "adaln_linear")
         launches += 5
 

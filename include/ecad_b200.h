@@ -88,10 +88,11 @@ int ecadk_patch_embed(const float* latents, const float* wt, const float* bias, 
  * Replaces the first stage of self.adaln_single (pixart_transformer_2d_edited.py:308-313). */
 int ecadk_timestep_sinusoid(const float* t, float* out, int samples, int dim, ecadk_stream_t stream);
 
-/* y[s, y_off + o] (+)= b[o] + sum_i W[o,i] * act(x[s,i]); act_in: 0 none, 1 SiLU.  fp32.
- * Replaces the TimestepEmbedding MLPs and AdaLayerNormSingle.linear (pixart_transformer_2d_edited.py:308-313). */
-int ecadk_small_linear(const float* x, const float* w, const float* b, float* y, int samples, int k, int o, int ldy,
-                       int y_off, int act_in, int accumulate, ecadk_stream_t stream);
+/* y[s, y_off + o] (+)= b[o] + sum_i W[o,i] * act(x[s*ldx + i]); act_in: 0 none, 1 SiLU.  fp32.
+ * Replaces the TimestepEmbedding MLPs (timestep, and the 1024-MS resolution / aspect-ratio embedders) and
+ * AdaLayerNormSingle.linear (pixart_transformer_2d_edited.py:308-313). */
+int ecadk_small_linear(const float* x, int ldx, const float* w, const float* b, float* y, int samples, int k, int o,
+                       int ldy, int y_off, int act_in, int accumulate, ecadk_stream_t stream);
 
 int ecadk_cast_f32_bf16(const float* in, void* out, size_t n, ecadk_stream_t stream);
 

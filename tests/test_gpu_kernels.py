@@ -283,7 +283,7 @@ def test_timestep_path_and_small_ops(cuda_device):
     w = torch.randn(300, 256, device="cuda", generator=g) / 16
     b = torch.randn(300, device="cuda", generator=g)
     y = torch.zeros(S, 400, device="cuda")
-    _lib.check(lib.ecadk_small_linear(proj.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), S, 256, 300, 400, 100,
+    _lib.check(lib.ecadk_small_linear(proj.data_ptr(), 256, w.data_ptr(), b.data_ptr(), y.data_ptr(), S, 256, 300, 400, 100,
                                       1, 0, _lib.stream_ptr()))
     torch.cuda.synchronize()
     ref_y = torch.nn.functional.silu(proj) @ w.T + b

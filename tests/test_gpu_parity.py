@@ -134,6 +134,39 @@ def test_single_forward_other_shapes(cuda_device, sample_size, text_tokens):
     assert _cos(out, ref) > 0.99999
 
 
+def test_single_forward_1024ms_additional_conditions(cuda_device):
+    """PixArt-alpha 1024-MS (sample_size 128): resolution / aspect-ratio micro-conditions, interpolation_scale 2,
+    N = 4096 image tokens - one forward of a 2-block model against the oracle."""
+    from ecad_b200.schedule import PixArtCacheSchedule
+    from ecad_b200.transformer import B200PixArtTransformer2D, SequentialDiTScheduler
+    from ecad_b200.weights import PixArtConfig, random_init_state_dict, synthetic_prompt_embeddings
+    from oracle.pixart_oracle import OracleConfig, OracleSchedule, PixArtOracle
+
+    cfg = PixArtConfig(sample_size=128, num_layers=2)
+    assert cfg.resolved_additional_conditions and cfg.resolved_interpolation_scale == 2
+    sd = random_init_state_dict(cfg, seed=8)
+    emb = synthetic_prompt_embeddings(1, seed=3)
+    lat = torch.randn(1, 4, 128, 128, generator=torch.Generator().manual_seed(4))
+    x_in = torch.cat([lat, lat])
+    e_in = torch.cat([emb["negative_prompt_embeds"], emb["prompt_embeds"]])
+    m_in = torch.cat([emb["negative_prompt_attention_mask"], emb["prompt_attention_mask"]])
+    ts = torch.full((2,), 399, dtype=torch.int64)
+    added = {"resolution": torch.tensor([[1024.0, 768.0], [1024.0, 768.0]]),
+             "aspect_ratio": torch.tensor([[1024.0 / 768.0], [1024.0 / 768.0]])}
+    flags = np.ones((1, 2, 3), bool)
+    ref = PixArtOracle(sd, OracleConfig(sample_size=128, num_layers=2), OracleSchedule.from_flags(flags)) \
+        .forward(x_in, e_in, ts, added, m_in)
+    tr = B200PixArtTransformer2D(sd, cfg, SequentialDiTScheduler(1), PixArtCacheSchedule.default(1, 2))
+    out = tr(x_in.cuda(), encoder_hidden_states=e_in.cuda(), encoder_attention_mask=m_in.cuda(), timestep=ts.cuda(),
+             added_cond_kwargs={k: v.cuda() for k, v in added.items()}, return_dict=False)[0].cpu()
+    assert out.shape == ref.shape == (2, 8, 128, 128)
+    assert float((out - ref).abs().max() / ref.abs().max()) < 5e-3
+    assert _cos(out, ref) > 0.99999
+    with pytest.raises(ValueError, match="added_cond_kwargs"):
+        tr(x_in.cuda(), encoder_hidden_states=e_in.cuda(), encoder_attention_mask=m_in.cuda(), timestep=ts.cuda(),
+           added_cond_kwargs=None, return_dict=False)
+
+
 def test_cached_generation_512px_small_model(cuda_device):
     """A cached multi-step generation at 512x512 (N = 1024 tokens) on a 6-block model: exercises the streamed
     self-attention together with the reuse / fused-residual paths at a second resolution."""
