@@ -411,7 +411,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_consta
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
     const uint32_t t_row = tmem + 256 * t + (static_cast<uint32_t>(quarter * 32) << 16);
-    float* bias_s = reinterpret_cast<float*>(smem + Cfg::kBias) + (warp - 2) * NK;
+    const uint32_t bias_a = smem_u32(smem + Cfg::kBias) + (warp - 2) * NK * 4;  // per-warp bias slice (shared space)
     constexpr float kLog2e = 1.4426950408889634f;
     // key bias of the NEXT item is fetched one item ahead (registers), so its global latency is off the chain
     float breg[NK / 32];
@@ -430,7 +430,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_consta
       const int head = item - sample * p.heads;
       if constexpr (HAS_BIAS) {
 #pragma unroll
-        for (int j = 0; j < NK / 32; ++j) bias_s[lane + 32 * j] = breg[j];
+        for (int j = 0; j < NK / 32; ++j) sts_f1(bias_a + (lane + 32 * j) * 4, breg[j]);
         __syncwarp();
         if (item + static_cast<int>(gridDim.x) < num_items) fetch_bias(item + gridDim.x);
       }
@@ -445,7 +445,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_consta
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if constexpr (HAS_BIAS) b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + j);
+          if constexpr (HAS_BIAS) b4 = lds_f4(bias_a + (c * 32 + j) * 4);
           mx = fmaxf(mx, fmaf(__uint_as_float(v[j + 0]), p.scale_log2e, b4.x));
           mx = fmaxf(mx, fmaf(__uint_as_float(v[j + 1]), p.scale_log2e, b4.y));
           mx = fmaxf(mx, fmaf(__uint_as_float(v[j + 2]), p.scale_log2e, b4.z));
@@ -462,7 +462,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_consta
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if constexpr (HAS_BIAS) b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + j);
+          if constexpr (HAS_BIAS) b4 = lds_f4(bias_a + (c * 32 + j) * 4);
           const float e0 = fast_exp2(fmaf(__uint_as_float(v[j + 0]), p.scale_log2e, b4.x) - mx);
           const float e1 = fast_exp2(fmaf(__uint_as_float(v[j + 1]), p.scale_log2e, b4.y) - mx);
           const float e2 = fast_exp2(fmaf(__uint_as_float(v[j + 2]), p.scale_log2e, b4.z) - mx);
@@ -717,7 +717,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t t_row = tmem + 256 * t + (static_cast<uint32_t>(quarter * 32) << 16);
-    float* bias_s = reinterpret_cast<float*>(smem + Cfg::kBias) + (warp - 2) * kFlashKB;
+    const uint32_t bias_a = smem_u32(smem + Cfg::kBias) + (warp - 2) * kFlashKB * 4;
     constexpr float kLog2e = 1.4426950408889634f;
     float breg[kFlashKB / 32];
     auto fetch_bias = [&](int sample, int j) {
@@ -734,7 +734,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
       for (int j = 0; j < nkb; ++j, ++nb) {
         if constexpr (HAS_BIAS) {
 #pragma unroll
-          for (int i = 0; i < kFlashKB / 32; ++i) bias_s[lane + 32 * i] = breg[i];
+          for (int i = 0; i < kFlashKB / 32; ++i) sts_f1(bias_a + (lane + 32 * i) * 4, breg[i]);
           __syncwarp();
           if (j + 1 < nkb) fetch_bias(sample, j + 1);
         }
@@ -749,7 +749,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if constexpr (HAS_BIAS) b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + i);
+            if constexpr (HAS_BIAS) b4 = lds_f4(bias_a + (c * 32 + i) * 4);
             mx = fmaxf(mx, fmaf(__uint_as_float(v[i + 0]), p.scale_log2e, b4.x));
             mx = fmaxf(mx, fmaf(__uint_as_float(v[i + 1]), p.scale_log2e, b4.y));
             mx = fmaxf(mx, fmaf(__uint_as_float(v[i + 2]), p.scale_log2e, b4.z));
@@ -785,7 +785,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if constexpr (HAS_BIAS) b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + i);
+            if constexpr (HAS_BIAS) b4 = lds_f4(bias_a + (c * 32 + i) * 4);
             const float e0 = fast_exp2(fmaf(__uint_as_float(v[i + 0]), p.scale_log2e, b4.x) - m_eff);
             const float e1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2e, b4.y) - m_eff);
             const float e2 = fast_exp2(fmaf(__uint_as_float(v[i + 2]), p.scale_log2e, b4.z) - m_eff);

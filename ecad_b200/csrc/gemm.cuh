@@ -75,6 +75,7 @@ template <int EPI>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_t t_row, float* stage, const int lane,
                                               const int parity, const int row_base, const int n0, const int n_chunks) {
   const int cg = lane & 7, rs = lane >> 3;
+  const uint32_t stage_s = smem_u32(stage);  // explicit shared-space address of this warp's transpose tile
   // per-tile row bookkeeping for the 8 rows this lane stores (r = 4*i + rs)
   int row_off[8];  // EPI_HEADMAJOR: element offset of (sample, token) inside one head-major tensor, head 0
   int sample0 = 0;
@@ -122,8 +123,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
     tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      *reinterpret_cast<uint4*>(stage + lane * kEpiPitch + 4 * j) =
-          make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      sts_u4(stage_s + (lane * kEpiPitch + 4 * j) * 4, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
     __syncwarp();
     int hm_off = 0;
@@ -140,7 +140,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
     for (int i = 0; i < 8; ++i) {
       const int r = i * 4 + rs;
       const int row = row_base + r;
-      float4 o = *reinterpret_cast<const float4*>(stage + r * kEpiPitch + cg * 4);
+      float4 o = lds_f4(stage_s + (r * kEpiPitch + cg * 4) * 4);
       o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
       if (row < p.M) {
         if constexpr (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU) {
