@@ -12,7 +12,7 @@ from pathlib import Path
 import torch
 
 _LIB_PATH = Path(__file__).resolve().parent / "libecad_b200.so"
-MAX_REUSE = 6
+MAX_REUSE = 12
 HEAD_DIM = 72
 HEAD_PAD = 80
 

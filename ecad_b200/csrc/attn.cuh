@@ -241,6 +241,56 @@ attn_tile_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_consta
 }  // namespace ecadk
 
 namespace ecadk {
+
+// ---- softmax building blocks shared by attn_pair_kernel / attn_flash_kernel -------------------------------------
+// One 32-column chunk of a score row (thread = row).  `bias_a` = shared-space address of this warp's key-bias slice,
+// already multiplied by log2(e).  Packed fp32x2 math: one FFMA2 / FADD2 / FMNMX3 per two scores.
+template <bool HAS_BIAS>
+__device__ __forceinline__ float softmax_chunk_max(const uint32_t (&v)[32], float mx, float scale_log2e, uint32_t bias_a) {
+  if constexpr (!HAS_BIAS) {
+    // scale > 0: the maximum of the raw scores is taken here and scaled once by the caller
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) mx = fmax3(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+  } else {
+    const uint64_t sc2 = pack_f2(scale_log2e, scale_log2e);
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 b4 = lds_f4(bias_a + i * 4);
+      float t0, t1, t2, t3;
+      unpack_f2(ffma2(pack_f2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, pack_f2(b4.x, b4.y)), t0, t1);
+      unpack_f2(ffma2(pack_f2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])), sc2, pack_f2(b4.z, b4.w)), t2, t3);
+      mx = fmax3(mx, t0, t1);
+      mx = fmax3(mx, t2, t3);
+    }
+  }
+  return mx;
+}
+
+// p = exp2(score * scale + bias - m); accumulates the row sum as a packed pair; writes 16 packed bf16x2 words
+template <bool HAS_BIAS>
+__device__ __forceinline__ void softmax_chunk_exp(const uint32_t (&v)[32], uint32_t (&pk)[16], uint64_t& sum2, float m,
+                                                  float scale_log2e, uint32_t bias_a) {
+  const uint64_t sc2 = pack_f2(scale_log2e, scale_log2e);
+  const uint64_t nm2 = pack_f2(-m, -m);
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    uint64_t c01 = nm2, c23 = nm2;
+    if constexpr (HAS_BIAS) {
+      const float4 b4 = lds_f4(bias_a + i * 4);
+      c01 = fadd2(pack_f2(b4.x, b4.y), nm2);
+      c23 = fadd2(pack_f2(b4.z, b4.w), nm2);
+    }
+    float t0, t1, t2, t3;
+    unpack_f2(ffma2(pack_f2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, c01), t0, t1);
+    unpack_f2(ffma2(pack_f2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])), sc2, c23), t2, t3);
+    const float e0 = fast_exp2(t0), e1 = fast_exp2(t1), e2 = fast_exp2(t2), e3 = fast_exp2(t3);
+    sum2 = fadd2(sum2, pack_f2(e0, e1));
+    sum2 = fadd2(sum2, pack_f2(e2, e3));
+    pk[i / 2] = pack_bf16x2(e0, e1);
+    pk[i / 2 + 1] = pack_bf16x2(e2, e3);
+  }
+}
+
 // =====================================================================================================
 // Persistent pipelined variant: one work item = all 256 queries of one (sample, head) against NK keys.
 //
@@ -442,38 +492,23 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_consta
         uint32_t v[32];
         tmem_ld_32x32(t_row + c * 32, v);
         tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if constexpr (HAS_BIAS) b4 = lds_f4(bias_a + (c * 32 + j) * 4);
-          mx = fmaxf(mx, fmaf(__uint_as_float(v[j + 0]), p.scale_log2e, b4.x));
-          mx = fmaxf(mx, fmaf(__uint_as_float(v[j + 1]), p.scale_log2e, b4.y));
-          mx = fmaxf(mx, fmaf(__uint_as_float(v[j + 2]), p.scale_log2e, b4.z));
-          mx = fmaxf(mx, fmaf(__uint_as_float(v[j + 3]), p.scale_log2e, b4.w));
-        }
+        mx = softmax_chunk_max<HAS_BIAS>(v, mx, p.scale_log2e, bias_a + c * 128);
       }
-      float sum = 0.f;
+      if constexpr (!HAS_BIAS) mx *= p.scale_log2e;
+      uint64_t sum2 = pack_f2(0.f, 0.f);
 #pragma unroll 1
       for (int c = 0; c < NK / 32; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(t_row + c * 32, v);
         tmem_ld_wait();
         uint32_t pk[16];
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if constexpr (HAS_BIAS) b4 = lds_f4(bias_a + (c * 32 + j) * 4);
-          const float e0 = fast_exp2(fmaf(__uint_as_float(v[j + 0]), p.scale_log2e, b4.x) - mx);
-          const float e1 = fast_exp2(fmaf(__uint_as_float(v[j + 1]), p.scale_log2e, b4.y) - mx);
-          const float e2 = fast_exp2(fmaf(__uint_as_float(v[j + 2]), p.scale_log2e, b4.z) - mx);
-          const float e3 = fast_exp2(fmaf(__uint_as_float(v[j + 3]), p.scale_log2e, b4.w) - mx);
-          sum += (e0 + e1) + (e2 + e3);
-          pk[j / 2] = pack_bf16x2(e0, e1);
-          pk[j / 2 + 1] = pack_bf16x2(e2, e3);
-        }
+        softmax_chunk_exp<HAS_BIAS>(v, pk, sum2, mx, p.scale_log2e, bias_a + c * 128);
         // P chunk c (keys 32c..32c+31) -> packed columns [16c, 16c+16): inside the already-read part of S
         tmem_st_32x16(t_row + c * 16, pk);
       }
+      float sum_lo, sum_hi;
+      unpack_f2(sum2, sum_lo, sum_hi);
+      const float sum = sum_lo + sum_hi;
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -746,16 +781,9 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
           uint32_t v[32];
           tmem_ld_32x32(t_row + c * 32, v);
           tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if constexpr (HAS_BIAS) b4 = lds_f4(bias_a + (c * 32 + i) * 4);
-            mx = fmaxf(mx, fmaf(__uint_as_float(v[i + 0]), p.scale_log2e, b4.x));
-            mx = fmaxf(mx, fmaf(__uint_as_float(v[i + 1]), p.scale_log2e, b4.y));
-            mx = fmaxf(mx, fmaf(__uint_as_float(v[i + 2]), p.scale_log2e, b4.z));
-            mx = fmaxf(mx, fmaf(__uint_as_float(v[i + 3]), p.scale_log2e, b4.w));
-          }
+          mx = softmax_chunk_max<HAS_BIAS>(v, mx, p.scale_log2e, bias_a + c * 128);
         }
+        if constexpr (!HAS_BIAS) mx *= p.scale_log2e;
         // lazy rescale: move the reference maximum only when the block maximum exceeds it by > 8 (log2 units).
         // tcgen05.ld/st are warp-collective (.sync.aligned): the TMEM round trip runs for the whole warp as soon as
         // ANY row needs it; rows that do not need it use alpha = 1.
@@ -776,25 +804,20 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
         l_sum *= alpha;
         if (need) m_used = mx;
         const float m_eff = m_used == -INFINITY ? 0.f : m_used;  // a fully masked prefix must not produce NaN
+        uint64_t sum2 = pack_f2(0.f, 0.f);
 #pragma unroll 1
         for (int c = 0; c < kFlashKB / 32; ++c) {
           uint32_t v[32];
           tmem_ld_32x32(t_row + c * 32, v);
           tmem_ld_wait();
           uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if constexpr (HAS_BIAS) b4 = lds_f4(bias_a + (c * 32 + i) * 4);
-            const float e0 = fast_exp2(fmaf(__uint_as_float(v[i + 0]), p.scale_log2e, b4.x) - m_eff);
-            const float e1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2e, b4.y) - m_eff);
-            const float e2 = fast_exp2(fmaf(__uint_as_float(v[i + 2]), p.scale_log2e, b4.z) - m_eff);
-            const float e3 = fast_exp2(fmaf(__uint_as_float(v[i + 3]), p.scale_log2e, b4.w) - m_eff);
-            l_sum += (e0 + e1) + (e2 + e3);
-            pk[i / 2] = pack_bf16x2(e0, e1);
-            pk[i / 2 + 1] = pack_bf16x2(e2, e3);
-          }
+          softmax_chunk_exp<HAS_BIAS>(v, pk, sum2, m_eff, p.scale_log2e, bias_a + c * 128);
           tmem_st_32x16(t_row + c * 16, pk);
+        }
+        {
+          float s_lo, s_hi;
+          unpack_f2(sum2, s_lo, s_hi);
+          l_sum += s_lo + s_hi;
         }
         tmem_st_wait();
         tc_fence_before();

@@ -441,6 +441,12 @@ int launch_residual_ln(const EcadkResidualLnArgs& a, cudaStream_t stream) {
                  elems * (4.0 + (a.n_reuse > 0 ? 4.0 : 0.0) + 2.0 * a.n_reuse + (a.xb ? 2.0 : 0.0) + (a.h ? 2.0 : 0.0)),
                  stream);
   if (a.dim == 1152) {
+    static bool configured9 = false;
+    if (!configured9) {  // up to (2 + 12) staged vectors = 63 KB > the 48 KB default
+      ECADK_CHECK_CUDA(cudaFuncSetAttribute(residual_ln_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (2 + ECADK_MAX_REUSE) * 1152 * 4));
+      configured9 = true;
+    }
     residual_ln_kernel<9><<<grid, 256, smem, stream>>>(p);
   } else {
     static bool configured = false;

@@ -12,7 +12,7 @@
 
 namespace ecadk {
 
-constexpr int kMaxReuse = 6;
+constexpr int kMaxReuse = 12;
 
 struct ReuseEntry {
   const __nv_bfloat16* cache;  // [M, D] cached un-gated sub-block output

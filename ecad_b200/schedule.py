@@ -3,7 +3,7 @@
 Host-side mirror of the reference's schedule objects for the hot path (same names, argument meaning, JSON
 format and error behaviour), re-laid-out for the B200 step executor: the flags live in one dense
 ``bool[S][NB][3]`` array so that a whole step's decision row is a single 84-byte slice handed to the C-ABI
-(`ecadk_pixart_step`), instead of three dict look-ups per sub-block.
+(`ecadk_pixart_blocks`), instead of three dict look-ups per sub-block.
 
 Reference interfaces mirrored (all under /root/reference/):
   * ``CacheSchedule``            ecad/schedulers/cache_scheduler/cache_schedule.py:18-112

@@ -34,7 +34,7 @@ extern "C" {
 #define ECADK_EARCH (-3)   /* device is not sm_100 */
 #define ECADK_EDRIVER (-4) /* driver entry point (cuTensorMapEncodeTiled) unavailable */
 
-#define ECADK_MAX_REUSE 6
+#define ECADK_MAX_REUSE 12
 #define ECADK_HEAD_DIM 72 /* PixArt attention_head_dim (pixart_transformer_2d_edited.py:27) */
 #define ECADK_HEAD_PAD 80 /* head_dim zero-padded to a multiple of the UMMA K step (16) */
 

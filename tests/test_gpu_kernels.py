@@ -188,7 +188,8 @@ def test_attention_all_masked_row_is_uniform(cuda_device):
 
 
 @pytest.mark.parametrize("n_reuse,do_ln,do_xb", [(0, True, False), (3, True, False), (6, False, False),
-                                                  (2, False, True), (1, True, True)])
+                                                  (2, False, True), (1, True, True), (12, True, False),
+                                                  (9, False, True)])
 def test_residual_ln(cuda_device, n_reuse, do_ln, do_xb):
     from ecad_b200 import _lib
     g = torch.Generator(device="cuda").manual_seed(9)
