@@ -106,3 +106,62 @@ def synthetic_prompt_embeddings(batch: int, text_tokens: int = 120, channels: in
         "negative_prompt_embeds": neg.to(dtype),
         "negative_prompt_attention_mask": neg_mask,
     }
+
+
+@dataclass(frozen=True)
+class FluxConfig:
+    """FLUX.1-dev architecture (diffusers FluxTransformer2DModel defaults)."""
+
+    num_attention_heads: int = 24
+    attention_head_dim: int = 128
+    num_layers: int = 19
+    num_single_layers: int = 38
+    in_channels: int = 64
+    joint_attention_dim: int = 4096
+    pooled_projection_dim: int = 768
+    axes_dims_rope: tuple[int, int, int] = (16, 56, 56)
+    guidance_embeds: bool = True
+
+    @property
+    def inner_dim(self) -> int:
+        return self.num_attention_heads * self.attention_head_dim
+
+
+def flux_random_init_state_dict(cfg: FluxConfig = FluxConfig(), seed: int = 0) -> dict[str, torch.Tensor]:
+    """Constructor-initialised FLUX weights keyed like diffusers' FluxTransformer2DModel.state_dict()
+    (the reference's own random-init protocol: skip_transformer_block_init,
+    /root/reference/ecad/transformer_2d_models/flux_transformer_2d_edited.py:75-83)."""
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    D, hd = cfg.inner_dim, cfg.attention_head_dim
+    sd: dict[str, torch.Tensor] = {}
+    _linear(sd, "x_embedder", D, cfg.in_channels, gen)
+    _linear(sd, "context_embedder", D, cfg.joint_attention_dim, gen)
+    embs = ["timestep_embedder"] + (["guidance_embedder"] if cfg.guidance_embeds else [])
+    for nm in embs:
+        _linear(sd, f"time_text_embed.{nm}.linear_1", D, 256, gen)
+        _linear(sd, f"time_text_embed.{nm}.linear_2", D, D, gen)
+    _linear(sd, "time_text_embed.text_embedder.linear_1", D, cfg.pooled_projection_dim, gen)
+    _linear(sd, "time_text_embed.text_embedder.linear_2", D, D, gen)
+    for i in range(cfg.num_layers):
+        pre = f"transformer_blocks.{i}"
+        _linear(sd, f"{pre}.norm1.linear", 6 * D, D, gen)
+        _linear(sd, f"{pre}.norm1_context.linear", 6 * D, D, gen)
+        for nm in ("to_q", "to_k", "to_v", "add_q_proj", "add_k_proj", "add_v_proj", "to_out.0", "to_add_out"):
+            _linear(sd, f"{pre}.attn.{nm}", D, D, gen)
+        for nm in ("norm_q", "norm_k", "norm_added_q", "norm_added_k"):
+            sd[f"{pre}.attn.{nm}.weight"] = torch.ones(hd)
+        for ff in ("ff", "ff_context"):
+            _linear(sd, f"{pre}.{ff}.net.0.proj", 4 * D, D, gen)
+            _linear(sd, f"{pre}.{ff}.net.2", D, 4 * D, gen)
+    for i in range(cfg.num_single_layers):
+        pre = f"single_transformer_blocks.{i}"
+        _linear(sd, f"{pre}.norm.linear", 3 * D, D, gen)
+        _linear(sd, f"{pre}.proj_mlp", 4 * D, D, gen)
+        _linear(sd, f"{pre}.proj_out", D, 5 * D, gen)
+        for nm in ("to_q", "to_k", "to_v"):
+            _linear(sd, f"{pre}.attn.{nm}", D, D, gen)
+        for nm in ("norm_q", "norm_k"):
+            sd[f"{pre}.attn.{nm}.weight"] = torch.ones(hd)
+    _linear(sd, "norm_out.linear", 2 * D, D, gen)
+    _linear(sd, "proj_out", cfg.in_channels, D, gen)
+    return sd
