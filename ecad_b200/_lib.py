@@ -33,6 +33,12 @@ EXPORTED_SYMBOLS = [
     "ecadk_gemm_bias_gated_residual_cache",
     "ecadk_gemm_bias_headmajor",
     "ecadk_attention",
+    "ecadk_attention_d128",
+    "ecadk_qk_norm_rope",
+    "ecadk_strided_unary",
+    "ecadk_axpy_f32",
+    "ecadk_gemm_bias_f32",
+    "ecadk_gemm_bias_headmajor_ex",
     "ecadk_create",
     "ecadk_destroy",
     "ecadk_pixart_blocks",
@@ -149,6 +155,12 @@ def load() -> C.CDLL:
         "ecadk_gemm_bias_gated_residual_cache": [p, p, p, p, p, p, p, p, i, i, i, i, i, p],
         "ecadk_gemm_bias_headmajor": [p, p, p, p, p, p, i, i, i, i, i, i, p],
         "ecadk_attention": [p, p, p, p, p, i, i, i, i, p],
+        "ecadk_attention_d128": [p, p, p, p, i, p, i, i, i, i, i, p],
+        "ecadk_qk_norm_rope": [p, p, p, p, p, p, p, p, i, i, i, i, f, p],
+        "ecadk_strided_unary": [p, p, i, i, i, i, i, p],
+        "ecadk_axpy_f32": [p, p, f, sz, p],
+        "ecadk_gemm_bias_f32": [p, p, p, p, i, i, i, i, i, p],
+        "ecadk_gemm_bias_headmajor_ex": [p, p, p, p, p, p, i, i, i, i, i, i, i, i, i, p],
         "ecadk_create": [i, C.POINTER(EcadkModelDesc), C.POINTER(EcadkBlockWeights), C.POINTER(p)],
         "ecadk_destroy": [p],
         "ecadk_pixart_blocks": [p, C.POINTER(EcadkBlocksArgs), C.POINTER(C.c_uint8), C.POINTER(i), p],

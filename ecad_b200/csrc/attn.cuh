@@ -29,6 +29,10 @@ struct AttnParams {
   float scale_log2e;  // (1/sqrt(d)) * log2(e)
   const float* bias;  // [samples, NK] additive key bias in natural-log units (0 / -10000 / -inf), or null
   __nv_bfloat16* out;  // [samples, q_tokens, out_ld]
+  // optional split of the query sequence (FLUX double-stream blocks: text tokens first): rows q < split_tokens go to
+  // out_lo [samples, split_tokens, out_ld], the others to out [samples, q_tokens - split_tokens, out_ld]
+  __nv_bfloat16* out_lo;
+  int split_tokens;
 };
 
 template <int NK>
@@ -575,27 +579,37 @@ namespace ecadk {
 // =====================================================================================================
 constexpr int kFlashKB = 128;  // keys per block
 
+// HD = real head dim: 72 (PixArt; stored padded to 80 = 64 + 16 columns) or 128 (FLUX; 64 + 64 columns).  The head is
+// always staged as a 64-column 128B-swizzled chunk plus a second chunk of kC2 columns (32B- or 128B-swizzled).
+template <int HD>
 struct AttnFlashCfg {
+  static constexpr int kPad = HD == 72 ? 80 : HD;     // columns per head in the Q/K/V layout
+  static constexpr int kC2 = kPad - 64;               // columns of the second chunk (16 or 64)
+  static constexpr int kRow2 = kC2 * 2;               // bytes per row of the second chunk (32 or 128)
+  static constexpr uint32_t kSBO2 = 8 * kRow2;        // 8-row group stride of the second chunk
+  static constexpr uint64_t kLayout2 = kC2 == 16 ? kLayoutSW32 : kLayoutSW128;
   static constexpr int kQ64 = 0;                      // 256 rows x 128 B
-  static constexpr int kQ16 = kQ64 + 256 * 128;       // 256 rows x 32 B
-  static constexpr int kKStage = kFlashKB * 160;      // 128 B part then 32 B part
-  static constexpr int kK = kQ16 + 256 * 32;          // 2 stages
+  static constexpr int kQ2 = kQ64 + 256 * 128;        // 256 rows x kRow2
+  static constexpr int kKStage = kFlashKB * (128 + kRow2);
+  static constexpr int kK = kQ2 + 256 * kRow2;        // 2 stages
   static constexpr int kV = kK + 2 * kKStage;         // 2 stages
   static constexpr int kBias = kV + 2 * kKStage;      // 8 warps x 128 floats
   static constexpr int kBars = kBias + 8 * kFlashKB * 4;
   static constexpr int kSmemBytes = kBars + 256 + 1024;
-  static constexpr uint32_t kBytesQ = 256 * kHeadPad * 2;
-  static constexpr uint32_t kBytesKV = kFlashKB * kHeadPad * 2;
+  static constexpr uint32_t kBytesQ = 256 * kPad * 2;
+  static constexpr uint32_t kBytesKV = kFlashKB * kPad * 2;
+  static_assert(HD == 72 || HD == 128, "head dims built: 72 (PixArt), 128 (FLUX)");
+  static_assert(kSmemBytes > 114 * 1024 && kSmemBytes <= 227 * 1024,
+                "attn_flash_kernel must be alone on its SM (it owns all 512 TMEM columns) and fit in shared memory");
 };
-static_assert(AttnFlashCfg::kSmemBytes > 114 * 1024, "attn_flash_kernel must be alone on its SM (512 TMEM columns)");
 
-template <bool HAS_BIAS>
+template <int HD, bool HAS_BIAS>
 __global__ void __launch_bounds__(kAttnPairThreads, 1)
 attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_constant__ CUtensorMap tm_q16,
                   const __grid_constant__ CUtensorMap tm_k64, const __grid_constant__ CUtensorMap tm_k16,
                   const __grid_constant__ CUtensorMap tm_v64, const __grid_constant__ CUtensorMap tm_v16,
                   const AttnParams p, const int n_keys, const int num_items) {
-  using Cfg = AttnFlashCfg;
+  using Cfg = AttnFlashCfg<HD>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBars);
@@ -650,7 +664,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
         mbar_wait(q_empty, (n & 1) ^ 1);
         mbar_arrive_expect_tx(q_full, Cfg::kBytesQ);
         tma_load_2d(smem + Cfg::kQ64, &tm_q64, q_full, 0, q_row);
-        tma_load_2d(smem + Cfg::kQ16, &tm_q16, q_full, 64, q_row);
+        tma_load_2d(smem + Cfg::kQ2, &tm_q16, q_full, 64, q_row);
         for (int j = 0; j < nkb; ++j, ++nb) {
           const int st = nb & 1;
           const uint32_t ph = ((nb >> 1) & 1) ^ 1;
@@ -674,18 +688,19 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
       // ===================== MMA issuer =====================
       constexpr uint32_t idesc_s = make_idesc_bf16(kAttnBM, kFlashKB);
       constexpr uint32_t idesc_o64 = make_idesc_bf16(kAttnBM, 64, 0, 1);
-      constexpr uint32_t idesc_o16 = make_idesc_bf16(kAttnBM, 16, 0, 1);
+      constexpr uint32_t idesc_o2 = make_idesc_bf16(kAttnBM, Cfg::kC2, 0, 1);
       const uint32_t sbase = smem_u32(smem);
       auto issue_qk = [&](int t, int st) {
         const uint32_t d = tmem + 256 * t;
         const uint32_t kb = sbase + Cfg::kK + st * Cfg::kKStage;
         const uint64_t dk = make_smem_desc(kb, 16, 1024, kLayoutSW128);
-        const uint64_t dk2 = make_smem_desc(kb + kFlashKB * 128, 16, 256, kLayoutSW32);
+        const uint64_t dk2 = make_smem_desc(kb + kFlashKB * 128, 16, Cfg::kSBO2, Cfg::kLayout2);
         const uint64_t dq = make_smem_desc(sbase + Cfg::kQ64 + t * (kAttnBM * 128), 16, 1024, kLayoutSW128);
-        const uint64_t dq2 = make_smem_desc(sbase + Cfg::kQ16 + t * (kAttnBM * 32), 16, 256, kLayoutSW32);
+        const uint64_t dq2 = make_smem_desc(sbase + Cfg::kQ2 + t * (kAttnBM * Cfg::kRow2), 16, Cfg::kSBO2, Cfg::kLayout2);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16_ss(d, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-        umma_bf16_ss(d, dq2, dk2, idesc_s, 1);
+#pragma unroll
+        for (int k = 0; k < Cfg::kC2 / 16; ++k) umma_bf16_ss(d, dq2 + 2 * k, dk2 + 2 * k, idesc_s, 1);
         umma_commit(&s_full[t]);
       };
       auto issue_pv = [&](int t, int st, bool accumulate) {
@@ -695,10 +710,11 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
 #pragma unroll
         for (int ks = 0; ks < kFlashKB / 16; ++ks) {
           const uint64_t dv64 = make_smem_desc(vb + ks * 16 * 128, kFlashKB * 128, 1024, kLayoutSW128);
-          const uint64_t dv16 = make_smem_desc(vb + kFlashKB * 128 + ks * 16 * 32, kFlashKB * 32, 256, kLayoutSW32);
+          const uint64_t dv2 = make_smem_desc(vb + kFlashKB * 128 + ks * 16 * Cfg::kRow2, kFlashKB * Cfg::kRow2,
+                                              Cfg::kSBO2, Cfg::kLayout2);
           const uint32_t acc = (accumulate || ks != 0) ? 1u : 0u;
           umma_bf16_ts(o_tmem, p_tmem + ks * 8, dv64, idesc_o64, acc);
-          umma_bf16_ts(o_tmem + 64, p_tmem + ks * 8, dv16, idesc_o16, acc);
+          umma_bf16_ts(o_tmem + 64, p_tmem + ks * 8, dv2, idesc_o2, acc);
         }
       };
       // tile 1's PV of block nb-1 is deferred by one block so the two tiles run in anti-phase
@@ -792,7 +808,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
         const float alpha = rescale ? fast_exp2(m_used - mx) : 1.0f;
         if (__any_sync(0xffffffffu, rescale)) {
 #pragma unroll
-          for (int c = 0; c < 5; ++c) {  // O_t: 80 fp32 columns
+          for (int c = 0; c < Cfg::kPad / 16; ++c) {  // O_t: kPad fp32 columns
             uint32_t o[16];
             tmem_ld_32x16(t_row + 128 + c * 16, o);
             tmem_ld_wait();
@@ -829,9 +845,17 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
       tc_fence_after();
       const float inv = 1.0f / l_sum;
       const int q = pr * 256 + t * kAttnBM + row;
-      __nv_bfloat16* dst = p.out + (static_cast<size_t>(sample) * p.q_tokens + q) * p.out_ld + head * kHeadDim;
+      __nv_bfloat16* dst;
+      if (p.split_tokens > 0) {
+        dst = q < p.split_tokens
+                  ? p.out_lo + (static_cast<size_t>(sample) * p.split_tokens + q) * p.out_ld
+                  : p.out + (static_cast<size_t>(sample) * (p.q_tokens - p.split_tokens) + (q - p.split_tokens)) * p.out_ld;
+      } else {
+        dst = p.out + (static_cast<size_t>(sample) * p.q_tokens + q) * p.out_ld;
+      }
+      dst += head * HD;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < HD / 32; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(t_row + 128 + c * 32, v);
         tmem_ld_wait();
@@ -845,7 +869,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
           *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = o;
         }
       }
-      {
+      if constexpr (HD % 32 != 0) {  // HD = 72: columns 64..71 (72..79 are padding)
         uint32_t v[16];
         tmem_ld_32x16(t_row + 128 + 64, v);
         tmem_ld_wait();

@@ -322,20 +322,55 @@ int launch_attn_pair_inst(const CUtensorMap* tq, const CUtensorMap* tm, const At
   return check_launch("attn_pair_kernel");
 }
 
-template <bool HAS_BIAS>
+template <int HD, bool HAS_BIAS>
 int launch_attn_flash_inst(const CUtensorMap* tq, const CUtensorMap* tkv, const AttnParams& p, int n_keys, int items,
                            cudaStream_t stream) {
+  using Cfg = AttnFlashCfg<HD>;
   static bool configured = false;
-  auto kern = attn_flash_kernel<HAS_BIAS>;
+  auto kern = attn_flash_kernel<HD, HAS_BIAS>;
   if (!configured) {
-    ECADK_CHECK_CUDA(
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnFlashCfg::kSmemBytes));
+    ECADK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
   const int grid = items < num_sms() ? items : num_sms();
-  kern<<<grid, kAttnPairThreads, AttnFlashCfg::kSmemBytes, stream>>>(tq[0], tq[1], tkv[0], tkv[1], tkv[2], tkv[3], p,
-                                                                      n_keys, items);
+  kern<<<grid, kAttnPairThreads, Cfg::kSmemBytes, stream>>>(tq[0], tq[1], tkv[0], tkv[1], tkv[2], tkv[3], p, n_keys,
+                                                            items);
   return check_launch("attn_flash_kernel");
+}
+
+// FLUX joint attention: head_dim 128 (no padding), no key bias; out row pitch given (the single-stream blocks write
+// straight into the [attn | mlp] concat buffer).
+int launch_attention_d128(const void* q, const void* k, const void* v, void* out, int out_ld, void* out_lo,
+                          int split_tokens, int samples, int heads, int q_tokens, int n_keys, cudaStream_t stream) {
+  ECADK_REQUIRE(split_tokens == 0 || (out_lo != nullptr && split_tokens > 0 && split_tokens < q_tokens),
+                "attention_d128: split_tokens=%d needs out_lo and 0 < split < q_tokens", split_tokens);
+  ECADK_REQUIRE(q && k && v && out, "attention_d128: null pointer");
+  ECADK_REQUIRE(n_keys > 0 && n_keys % 128 == 0, "attention_d128: n_keys=%d must be a multiple of 128", n_keys);
+  ECADK_REQUIRE(q_tokens > 0 && q_tokens % 256 == 0, "attention_d128: q_tokens=%d must be a multiple of 256", q_tokens);
+  ECADK_REQUIRE(out_ld >= heads * 128 && out_ld % 8 == 0, "attention_d128: out_ld=%d", out_ld);
+  ECADK_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(out), "attention_d128: 16-byte alignment");
+  const uint64_t q_rows = static_cast<uint64_t>(samples) * heads * q_tokens;
+  const uint64_t k_rows = static_cast<uint64_t>(samples) * heads * n_keys;
+  ProfScope prof(ECADK_PROF_ATTENTION, 4.0 * samples * heads * q_tokens * n_keys * 128.0, 0.0, stream);
+  AttnParams p;
+  p.heads = heads;
+  p.q_tokens = q_tokens;
+  p.out_ld = out_ld;
+  p.scale_log2e = static_cast<float>(1.4426950408889634 / std::sqrt(128.0));
+  p.bias = nullptr;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.out_lo = static_cast<__nv_bfloat16*>(out_lo);
+  p.split_tokens = split_tokens;
+  CUtensorMap tq[2], tkv[4];
+  int rc;
+  if ((rc = make_tmap_bf16(&tq[0], q, q_rows, 128, 128, 256, 64, 128))) return rc;
+  tq[1] = tq[0];
+  if ((rc = make_tmap_bf16(&tkv[0], k, k_rows, 128, 128, kFlashKB, 64, 128))) return rc;
+  tkv[1] = tkv[0];
+  if ((rc = make_tmap_bf16(&tkv[2], v, k_rows, 128, 128, kFlashKB, 64, 128))) return rc;
+  tkv[3] = tkv[2];
+  const int items = samples * heads * (q_tokens / 256);
+  return launch_attn_flash_inst<128, false>(tq, tkv, p, n_keys, items, stream);
 }
 
 int launch_attention(const void* q, const void* k, const void* v, const float* bias, void* out, int samples,
@@ -362,6 +397,8 @@ int launch_attention(const void* q, const void* k, const void* v, const float* b
   p.scale_log2e = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(kHeadDim)));
   p.bias = bias;
   p.out = static_cast<__nv_bfloat16*>(out);
+  p.out_lo = nullptr;
+  p.split_tokens = 0;
   int rc;
   const bool use_flash = (n_keys > 256 || q_tokens > 256 || forced == 2) && q_tokens % 256 == 0;
   if (use_flash) {
@@ -374,8 +411,8 @@ int launch_attention(const void* q, const void* k, const void* v, const float* b
     if ((rc = make_tmap_bf16(&tkv[2], v, k_rows, kHeadPad, kHeadPad, kFlashKB, 64, 128))) return rc;
     if ((rc = make_tmap_bf16(&tkv[3], v, k_rows, kHeadPad, kHeadPad, kFlashKB, 16, 32))) return rc;
     const int items = samples * heads * (q_tokens / 256);
-    return bias ? launch_attn_flash_inst<true>(tq, tkv, p, n_keys, items, stream)
-                : launch_attn_flash_inst<false>(tq, tkv, p, n_keys, items, stream);
+    return bias ? launch_attn_flash_inst<72, true>(tq, tkv, p, n_keys, items, stream)
+                : launch_attn_flash_inst<72, false>(tq, tkv, p, n_keys, items, stream);
   }
   CUtensorMap tm[6];
   if ((rc = make_tmap_bf16(&tm[0], q, q_rows, kHeadPad, kHeadPad, kAttnBM, 64, 128))) return rc;
@@ -404,10 +441,11 @@ int launch_attention(const void* q, const void* k, const void* v, const float* b
 
 int launch_residual_ln(const EcadkResidualLnArgs& a, cudaStream_t stream) {
   ECADK_REQUIRE(a.x != nullptr && a.rows > 0 && a.tokens > 0, "residual_ln: bad x/rows/tokens");
-  ECADK_REQUIRE(a.dim == 1152 || a.dim == 3072, "residual_ln: dim=%d (supported: 1152, 3072)", a.dim);
+  ECADK_REQUIRE(a.dim == 512 || a.dim == 1152 || a.dim == 3072, "residual_ln: dim=%d (supported: 512, 1152, 3072)",
+                a.dim);
   ECADK_REQUIRE(a.n_reuse >= 0 && a.n_reuse <= ECADK_MAX_REUSE, "residual_ln: n_reuse=%d", a.n_reuse);
-  ECADK_REQUIRE(a.h == nullptr || (a.shift_table && a.scale_table && a.shift_temb && a.scale_temb),
-                "residual_ln: LayerNorm path needs shift/scale tables");
+  ECADK_REQUIRE(a.h == nullptr || (a.shift_temb && a.scale_temb),
+                "residual_ln: LayerNorm path needs the per-sample shift/scale vectors (tables are optional)");
   ECADK_REQUIRE(a.n_reuse > 0 || a.h != nullptr || a.xb != nullptr, "residual_ln: nothing to do");
   ResidualLnParams p;
   p.x = a.x;
@@ -422,8 +460,6 @@ int launch_residual_ln(const EcadkResidualLnArgs& a, cudaStream_t stream) {
     p.reuse[i].gate_temb = a.reuse[i].gate_temb;
     if (i < a.n_reuse) {
       ECADK_REQUIRE(p.reuse[i].cache != nullptr, "residual_ln: reuse[%d].cache is null", i);
-      ECADK_REQUIRE((p.reuse[i].gate_table == nullptr) == (p.reuse[i].gate_temb == nullptr),
-                    "residual_ln: reuse[%d] gate_table/gate_temb must both be set or both null", i);
     }
   }
   p.shift_table = a.shift_table;
@@ -440,7 +476,9 @@ int launch_residual_ln(const EcadkResidualLnArgs& a, cudaStream_t stream) {
   ProfScope prof(ECADK_PROF_GLUE, 0.0,
                  elems * (4.0 + (a.n_reuse > 0 ? 4.0 : 0.0) + 2.0 * a.n_reuse + (a.xb ? 2.0 : 0.0) + (a.h ? 2.0 : 0.0)),
                  stream);
-  if (a.dim == 1152) {
+  if (a.dim == 512) {
+    residual_ln_kernel<4><<<grid, 256, smem, stream>>>(p);
+  } else if (a.dim == 1152) {
     static bool configured9 = false;
     if (!configured9) {  // up to (2 + 12) staged vectors = 63 KB > the 48 KB default
       ECADK_CHECK_CUDA(cudaFuncSetAttribute(residual_ln_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -620,7 +658,8 @@ int ecadk_gemm_bias_gated_residual_cache(const void* a, const void* w, const flo
   ECADK_REQUIRE(x && cache && aligned16(x) && aligned16(cache) && (xb == nullptr || aligned16(xb)),
                 "gemm_gated_residual: bad x/cache");
   ECADK_REQUIRE(tokens > 0 && tokens % 32 == 0, "gemm_gated_residual: tokens=%d must be a multiple of 32", tokens);
-  ECADK_REQUIRE((gate_table == nullptr) == (gate_temb == nullptr), "gemm_gated_residual: gate table/temb mismatch");
+  ECADK_REQUIRE(gate_table == nullptr || gate_temb != nullptr || temb_stride == 0,
+                "gemm_gated_residual: a gate table without a per-sample vector needs temb_stride = 0");
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = m; p.N = n; p.K = k;
@@ -685,6 +724,88 @@ int ecadk_profile_stop(EcadkProfileRecord* out) {
   g_prof.recs.clear();
   g_prof.used = 0;
   return ECADK_OK;
+}
+
+int ecadk_attention_d128(const void* q, const void* k, const void* v, void* out, int out_ld, void* out_lo,
+                         int split_tokens, int samples, int heads, int q_tokens, int n_keys, ecadk_stream_t stream) {
+  return launch_attention_d128(q, k, v, out, out_ld, out_lo, split_tokens, samples, heads, q_tokens, n_keys,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int ecadk_qk_norm_rope(void* q, void* k, const float* wq, const float* wk, const float* wq_add, const float* wk_add,
+                       const float* rope_cos, const float* rope_sin, int samples, int heads, int seq, int split,
+                       float eps, ecadk_stream_t stream) {
+  ECADK_REQUIRE(q && k && wq && wk && rope_cos && rope_sin, "qk_norm_rope: null pointer");
+  ECADK_REQUIRE(split == 0 || (wq_add && wk_add), "qk_norm_rope: split > 0 needs the added-stream norm weights");
+  ProfScope prof(ECADK_PROF_OTHER, 0.0, 0.0, static_cast<cudaStream_t>(stream));
+  QkNormRopeParams p{static_cast<__nv_bfloat16*>(q), static_cast<__nv_bfloat16*>(k), wq, wk, wq_add, wk_add,
+                     rope_cos, rope_sin, samples * heads * seq, seq, split, eps};
+  qk_norm_rope_kernel<<<(p.rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return check_launch("qk_norm_rope_kernel");
+}
+
+int ecadk_strided_unary(const void* src, void* dst, int rows, int cols, int ld_src, int ld_dst, int op,
+                        ecadk_stream_t stream) {
+  ECADK_REQUIRE(src && dst && rows > 0 && cols > 0 && cols % 8 == 0 && ld_src % 8 == 0 && ld_dst % 8 == 0,
+                "strided_unary: cols / pitches must be multiples of 8");
+  ECADK_REQUIRE(aligned16(src) && aligned16(dst) && (op == 0 || op == 1), "strided_unary: alignment / op");
+  ProfScope prof(ECADK_PROF_OTHER, 0.0, 0.0, static_cast<cudaStream_t>(stream));
+  const size_t total = static_cast<size_t>(rows) * (cols / 8);
+  size_t blocks = (total + 255) / 256;
+  if (blocks > static_cast<size_t>(num_sms()) * 32) blocks = static_cast<size_t>(num_sms()) * 32;
+  strided_unary_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), rows, cols / 8, ld_src, ld_dst, op);
+  return check_launch("strided_unary_kernel");
+}
+
+int ecadk_axpy_f32(float* y, const float* x, float a, size_t n, ecadk_stream_t stream) {
+  ECADK_REQUIRE(y && x, "axpy: null pointer");
+  if (n == 0) return ECADK_OK;
+  ProfScope prof(ECADK_PROF_OTHER, 0.0, 0.0, static_cast<cudaStream_t>(stream));
+  size_t blocks = (n + 255) / 256;
+  if (blocks > static_cast<size_t>(num_sms()) * 16) blocks = static_cast<size_t>(num_sms()) * 16;
+  axpy_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(y, x, a, n);
+  return check_launch("axpy_kernel");
+}
+
+int ecadk_gemm_bias_f32(const void* a, const void* w, const float* bias, float* out, int m, int n, int k, int ldo,
+                        int out_cols, ecadk_stream_t stream) {
+  ECADK_REQUIRE(out != nullptr && aligned16(out) && ldo % 4 == 0 && out_cols > 0 && out_cols <= n && out_cols % 4 == 0 &&
+                    ldo >= out_cols,
+                "gemm_bias_f32: bad output");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = m; p.N = n; p.K = k;
+  p.bias = bias;
+  p.f32_out = out;
+  p.f32_cols = out_cols;
+  p.ldo = ldo;
+  p.tokens = 1;
+  return launch_gemm<EPI_BIAS_F32>(a, w, p, static_cast<cudaStream_t>(stream));
+}
+
+int ecadk_gemm_bias_headmajor_ex(const void* a, const void* w, const float* bias, void* out0, void* out1, void* out2,
+                                 int n_parts, int heads, int head_dim, int head_pad, int tokens, int tokens_pad,
+                                 int tok_offset, int m, int k, ecadk_stream_t stream) {
+  ECADK_REQUIRE(n_parts >= 1 && n_parts <= 3 && out0, "gemm_headmajor_ex: n_parts=%d", n_parts);
+  ECADK_REQUIRE(tokens > 0 && tok_offset >= 0 && tokens_pad >= tokens + tok_offset && heads > 0,
+                "gemm_headmajor_ex: bad token counts");
+  ECADK_REQUIRE(head_dim % 4 == 0 && head_pad >= head_dim && head_pad % 8 == 0, "gemm_headmajor_ex: bad head dims");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = m; p.N = n_parts * heads * head_dim; p.K = k;
+  p.bias = bias;
+  p.hm_out[0] = static_cast<__nv_bfloat16*>(out0);
+  p.hm_out[1] = static_cast<__nv_bfloat16*>(out1);
+  p.hm_out[2] = static_cast<__nv_bfloat16*>(out2);
+  for (int i = 0; i < n_parts; ++i) ECADK_REQUIRE(p.hm_out[i] && aligned16(p.hm_out[i]), "gemm_headmajor_ex: out%d", i);
+  p.heads = heads;
+  p.head_dim = head_dim;
+  p.head_pad = head_pad;
+  p.tokens = tokens;
+  p.tokens_pad = tokens_pad;
+  p.hm_tok_off = tok_offset;
+  return launch_gemm<EPI_HEADMAJOR>(a, w, p, static_cast<cudaStream_t>(stream));
 }
 
 int ecadk_create(int device, const EcadkModelDesc* desc, const EcadkBlockWeights* blocks, ecadk_handle_t* out) {

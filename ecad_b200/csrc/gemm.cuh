@@ -20,6 +20,7 @@ enum GemmEpilogue : int {
   EPI_GATED_RESIDUAL = 2,  // o = acc + bias; cache = bf16(o); x += gate * o; (xb = bf16(x))
   EPI_HEADMAJOR = 3,       // out[part][sample][head][token][head_pad] = bf16(acc + bias)   (Q/K/V scatter)
   EPI_UNPATCHIFY = 4,      // fp32 out[s][c][2i+p][2j+q] = acc + bias for the first unp_cols columns (final layer)
+  EPI_BIAS_F32 = 5,        // fp32 out[row, col] = acc + bias for col < f32_cols, row pitch ldo (embedders, FLUX head)
 };
 
 struct GemmParams {
@@ -39,6 +40,10 @@ struct GemmParams {
   // EPI_HEADMAJOR
   __nv_bfloat16* hm_out[3];
   int heads, head_dim, head_pad, tokens_pad;
+  int hm_tok_off;  // token offset inside the head-major sequence (FLUX: image tokens follow the text tokens)
+  // EPI_BIAS_F32
+  float* f32_out;
+  int f32_cols;
   // EPI_UNPATCHIFY (column o = (p*2+q)*C + c of token n = i*Wp + j of sample s)
   float* unp_out;
   int unp_wp, unp_hp, unp_c, unp_cols;
@@ -86,7 +91,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
       const int row = row_base + i * 4 + rs;
       const int sample = row / p.tokens;
       const int tok = row - sample * p.tokens;
-      row_off[i] = (sample * p.heads * p.tokens_pad + tok) * p.head_pad;
+      row_off[i] = (sample * p.heads * p.tokens_pad + tok + p.hm_tok_off) * p.head_pad;
     }
   }
   // residual-stream prefetch: the x values of chunk c+2 are requested while chunk c is being processed
@@ -107,6 +112,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
     if constexpr (EPI == EPI_UNPATCHIFY) {
       if (n0 + c * 32 >= p.unp_cols) break;  // zero-padded weight rows: nothing to store
     }
+    if constexpr (EPI == EPI_BIAS_F32) {
+      if (n0 + c * 32 >= p.f32_cols) break;
+    }
     uint32_t v[32];
     tmem_ld_32x32(t_row + c * 32, v);
     float4 xnext[8];
@@ -114,10 +122,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
     if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
     if constexpr (EPI == EPI_GATED_RESIDUAL) {
       if (c + 2 < n_chunks) load_x(c + 2, xnext);
-      if (p.gate_table != nullptr) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(p.gate_table + col));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p.gate_temb + static_cast<size_t>(sample0) * p.temb_stride + col));
-        g4 = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+      if (p.gate_table != nullptr || p.gate_temb != nullptr) {
+        g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.gate_table != nullptr) g4 = __ldg(reinterpret_cast<const float4*>(p.gate_table + col));
+        if (p.gate_temb != nullptr) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.gate_temb + static_cast<size_t>(sample0) * p.temb_stride + col));
+          g4 = make_float4(g4.x + b.x, g4.y + b.y, g4.z + b.z, g4.w + b.w);
+        }
       }
     }
     tmem_ld_wait();
@@ -172,6 +183,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
           w.x = pack_bf16x2(o.x, o.y);
           w.y = pack_bf16x2(o.z, o.w);
           *reinterpret_cast<uint2*>(hm_base + row_off[i] + hm_off) = w;
+        } else if constexpr (EPI == EPI_BIAS_F32) {
+          if (col < p.f32_cols) *reinterpret_cast<float4*>(p.f32_out + static_cast<size_t>(row) * p.ldo + col) = o;
         } else {  // EPI_UNPATCHIFY: 4 consecutive columns = 4 channels of one (p, q) sub-pixel
           if (col < p.unp_cols) {
             const int s_ = row / p.tokens, n_ = row - s_ * p.tokens;

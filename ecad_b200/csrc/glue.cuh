@@ -118,19 +118,24 @@ __device__ __forceinline__ void rln_stage_vectors(const ResidualLnParams& p, flo
   constexpr int DV = 32 * VPL;
   for (int k = threadIdx.x; k < DV; k += blockDim.x) {
     if (p.h != nullptr) {
-      const float4 ca = __ldg(reinterpret_cast<const float4*>(p.scale_table) + k);
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);  // a null table = modulation from the per-sample vector only
+      const float4 ca = p.scale_table ? __ldg(reinterpret_cast<const float4*>(p.scale_table) + k) : z4;
       const float4 cb = __ldg(reinterpret_cast<const float4*>(p.scale_temb + static_cast<size_t>(sample) * p.temb_stride) + k);
-      const float4 sa = __ldg(reinterpret_cast<const float4*>(p.shift_table) + k);
+      const float4 sa = p.shift_table ? __ldg(reinterpret_cast<const float4*>(p.shift_table) + k) : z4;
       const float4 sb = __ldg(reinterpret_cast<const float4*>(p.shift_temb + static_cast<size_t>(sample) * p.temb_stride) + k);
       rln_sm[k] = make_float4(1.f + (ca.x + cb.x), 1.f + (ca.y + cb.y), 1.f + (ca.z + cb.z), 1.f + (ca.w + cb.w));
       rln_sm[DV + k] = make_float4(sa.x + sb.x, sa.y + sb.y, sa.z + sb.z, sa.w + sb.w);
     }
     for (int r = 0; r < p.n_reuse; ++r) {
+      // gate = table + per-sample vector (PixArt adaLN-single), per-sample vector alone (FLUX), or 1 (no gate)
       float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
-      if (p.reuse[r].gate_table != nullptr) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(p.reuse[r].gate_table) + k);
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p.reuse[r].gate_temb + static_cast<size_t>(sample) * p.temb_stride) + k);
-        g = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+      if (p.reuse[r].gate_table != nullptr || p.reuse[r].gate_temb != nullptr) {
+        g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.reuse[r].gate_table != nullptr) g = __ldg(reinterpret_cast<const float4*>(p.reuse[r].gate_table) + k);
+        if (p.reuse[r].gate_temb != nullptr) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.reuse[r].gate_temb + static_cast<size_t>(sample) * p.temb_stride) + k);
+          g = make_float4(g.x + b.x, g.y + b.y, g.z + b.z, g.w + b.w);
+        }
       }
       rln_sm[(2 + r) * DV + k] = g;
     }
@@ -332,6 +337,78 @@ __global__ void average_halves_kernel(__nv_bfloat16* buf, size_t n8) {
     }
     lo[i] = make_uint4(o[0], o[1], o[2], o[3]);
   }
+}
+
+// FLUX: per-head RMSNorm (learned weight) + rotary embedding on head-major q and k, in place.
+// q, k: bf16 [B, H, S, 128]; tokens s < split use the "added" (text-stream) norm weights; rope: fp32 [S, 64] cos / sin.
+// One warp per (b, h, s) row of q and of k (lane = 4 consecutive elements = 2 rotation pairs).
+struct QkNormRopeParams {
+  __nv_bfloat16* q;
+  __nv_bfloat16* k;
+  const float* wq;       // [128] norm_q.weight
+  const float* wk;       // [128] norm_k.weight
+  const float* wq_add;   // [128] norm_added_q.weight (text tokens), or null
+  const float* wk_add;   // [128]
+  const float* cos_t;    // [S, 64]
+  const float* sin_t;    // [S, 64]
+  int rows;              // B * H * S
+  int S, split;
+  float eps;
+};
+__global__ void __launch_bounds__(256) qk_norm_rope_kernel(const QkNormRopeParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= p.rows) return;
+  const int s = row % p.S;
+  const bool added = s < p.split;
+  const float2 c2 = __ldg(reinterpret_cast<const float2*>(p.cos_t + static_cast<size_t>(s) * 64) + lane);
+  const float2 s2 = __ldg(reinterpret_cast<const float2*>(p.sin_t + static_cast<size_t>(s) * 64) + lane);
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+    __nv_bfloat16* base = (which == 0 ? p.q : p.k) + static_cast<size_t>(row) * 128;
+    const float* w = which == 0 ? (added ? p.wq_add : p.wq) : (added ? p.wk_add : p.wk);
+    const uint2 raw = *reinterpret_cast<const uint2*>(base + lane * 4);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+    const float ss = warp_sum(a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y);
+    const float r = rsqrtf(ss * (1.0f / 128.0f) + p.eps);
+    const float4 wv = __ldg(reinterpret_cast<const float4*>(w) + lane);
+    const float x0 = a.x * r * wv.x, x1 = a.y * r * wv.y, x2 = b.x * r * wv.z, x3 = b.y * r * wv.w;
+    uint2 o;
+    o.x = pack_bf16x2(c2.x * x0 - s2.x * x1, s2.x * x0 + c2.x * x1);
+    o.y = pack_bf16x2(c2.y * x2 - s2.y * x3, s2.y * x2 + c2.y * x3);
+    *reinterpret_cast<uint2*>(base + lane * 4) = o;
+  }
+}
+
+// dst[r, 0:cols] = op(src[r, 0:cols]) with independent row pitches; op: 0 copy, 1 GELU(tanh).  bf16, cols % 8 == 0.
+__global__ void strided_unary_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                     int rows, int cols8, int ld_src, int ld_dst, int op) {
+  const size_t total = static_cast<size_t>(rows) * cols8;
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (; i < total; i += stride) {
+    const size_t r = i / cols8;
+    const int c = static_cast<int>(i - r * cols8) * 8;
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(src + r * ld_src + c));
+    if (op == 1) {
+      uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+        w[k] = pack_bf16x2(gelu_tanh(f.x), gelu_tanh(f.y));
+      }
+      v = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    *reinterpret_cast<uint4*>(dst + r * ld_dst + c) = v;
+  }
+}
+
+// y += a * x (fp32): the flow-matching Euler update  latents += (sigma_next - sigma) * velocity
+__global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, float a, size_t n) {
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) y[i] = fmaf(a, x[i], y[i]);
 }
 
 // (1 - mask) * -10000 for real text tokens (pixart_transformer_2d_edited.py:282-289), -inf for padding keys

@@ -160,6 +160,49 @@ int ecadk_attention(const void* q, const void* k, const void* v, const float* bi
                     int heads, int q_tokens, int n_keys, ecadk_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * FLUX building blocks (kernel level; the FLUX step executor is built on them)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* FLUX joint attention: softmax(Q K^T / sqrt(128)) V with head_dim 128 (no padding, no key bias), keys streamed in
+ * blocks of 128.  q bf16 [samples, heads, q_tokens, 128] (q_tokens % 256 == 0); k, v bf16 [samples, heads, n_keys, 128]
+ * (n_keys % 128 == 0).  Head h is written at columns [h*128, h*128+128) of rows with pitch out_ld.  split_tokens == 0:
+ * out bf16 [samples, q_tokens, out_ld]; split_tokens > 0 (double-stream blocks, text tokens first): query rows
+ * q < split_tokens go to out_lo [samples, split_tokens, out_ld], the rest to out [samples, q_tokens-split_tokens, out_ld].
+ * Replaces F.scaled_dot_product_attention + the text/image split inside FluxAttnProcessor2_0
+ * (ecad/transformer_blocks/cached_flux_transformer_block.py:60-66,188-192). */
+int ecadk_attention_d128(const void* q, const void* k, const void* v, void* out, int out_ld, void* out_lo,
+                         int split_tokens, int samples, int heads, int q_tokens, int n_keys, ecadk_stream_t stream);
+
+/* Per-head RMSNorm (learned weight [128]) + rotary embedding, in place on head-major q and k
+ * (bf16 [samples, heads, seq, 128]).  Tokens s < split use the added-stream weights (norm_added_q / norm_added_k);
+ * rope_cos / rope_sin fp32 [seq, 64].  Replaces attn.norm_q/norm_k/norm_added_q/norm_added_k + apply_rope of
+ * FluxAttnProcessor2_0 (diffusers 0.30.3). */
+int ecadk_qk_norm_rope(void* q, void* k, const float* wq, const float* wk, const float* wq_add, const float* wk_add,
+                       const float* rope_cos, const float* rope_sin, int samples, int heads, int seq, int split,
+                       float eps, ecadk_stream_t stream);
+
+/* dst[r, 0:cols] = op(src[r, 0:cols]) on bf16 rows with independent pitches; op 0 = copy, 1 = GELU(tanh).
+ * Replaces act_mlp(...) on the (possibly cached, pre-activation) proj_mlp output and the torch.cat of the
+ * single-stream block (cached_flux_transformer_block.py:107-117). */
+int ecadk_strided_unary(const void* src, void* dst, int rows, int cols, int ld_src, int ld_dst, int op,
+                        ecadk_stream_t stream);
+
+/* y += a * x (fp32): FlowMatchEulerDiscreteScheduler.step, latents += (sigma_next - sigma) * model_output. */
+int ecadk_axpy_f32(float* y, const float* x, float a, size_t n, ecadk_stream_t stream);
+
+/* fp32 out[row, 0:out_cols] = A W^T + bias (row pitch ldo); W may be zero-padded to N % 128 == 0 rows.
+ * Replaces x_embedder / context_embedder / proj_out of FluxTransformer2DModel
+ * (ecad/transformer_2d_models/flux_transformer_2d_edited.py:275,288,317). */
+int ecadk_gemm_bias_f32(const void* a, const void* w, const float* bias, float* out, int m, int n, int k, int ldo,
+                        int out_cols, ecadk_stream_t stream);
+
+/* ecadk_gemm_bias_headmajor with explicit head geometry and a token offset inside the head-major sequence:
+ * row r -> sample r / tokens, token (r % tokens) + tok_offset of a sequence of pitch tokens_pad. */
+int ecadk_gemm_bias_headmajor_ex(const void* a, const void* w, const float* bias, void* out0, void* out1, void* out2,
+                                 int n_parts, int heads, int head_dim, int head_pad, int tokens, int tokens_pad,
+                                 int tok_offset, int m, int k, ecadk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Step-level executor: all transformer blocks of one forward pass under one decision row.
  * ---------------------------------------------------------------------------------------------------------- */
 
