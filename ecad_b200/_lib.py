@@ -43,6 +43,10 @@ EXPORTED_SYMBOLS = [
     "ecadk_destroy",
     "ecadk_pixart_blocks",
     "ecadk_pixart_text_kv",
+    "ecadk_silu_f32_bf16",
+    "ecadk_flux_create",
+    "ecadk_flux_destroy",
+    "ecadk_flux_blocks",
     "ecadk_profile_start",
     "ecadk_profile_stop",
 ]
@@ -113,6 +117,36 @@ class EcadkBlocksArgs(C.Structure):
     ]
 
 
+class EcadkFluxDesc(C.Structure):
+    _fields_ = [("num_layers", C.c_int), ("num_single_layers", C.c_int), ("dim", C.c_int), ("heads", C.c_int),
+                ("eps", C.c_float)]
+
+
+class EcadkFluxDoubleWeights(C.Structure):
+    _fields_ = [
+        (n, C.c_void_p)
+        for n in (
+            "w_qkv", "b_qkv", "w_qkv_ctx", "b_qkv_ctx", "w_out", "b_out", "w_out_ctx", "b_out_ctx", "w_ff1", "b_ff1",
+            "w_ff2", "b_ff2", "w_ff1_ctx", "b_ff1_ctx", "w_ff2_ctx", "b_ff2_ctx", "norm_q", "norm_k", "norm_added_q",
+            "norm_added_k",
+        )
+    ]
+
+
+class EcadkFluxSingleWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("w_qkv", "b_qkv", "w_mlp", "b_mlp", "w_out", "b_out", "norm_q", "norm_k")]
+
+
+class EcadkFluxArgs(C.Structure):
+    _fields_ = (
+        [("samples", C.c_int), ("img_tokens", C.c_int), ("txt_tokens", C.c_int)]
+        + [(n, C.c_void_p) for n in ("x_img", "x_txt", "x_cat", "h_img", "h_txt", "h_cat", "q", "k", "v", "attn_img",
+                                     "attn_txt", "ffh", "cat", "mod")]
+        + [("mod_stride", C.c_int), ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p),
+           ("cache_double", C.POINTER(C.c_void_p)), ("cache_single", C.POINTER(C.c_void_p))]
+    )
+
+
 class EcadkProfileRecord(C.Structure):
     _fields_ = [("launches", C.c_longlong), ("total_ms", C.c_double), ("flops", C.c_double), ("bytes", C.c_double)]
 
@@ -165,6 +199,11 @@ def load() -> C.CDLL:
         "ecadk_destroy": [p],
         "ecadk_pixart_blocks": [p, C.POINTER(EcadkBlocksArgs), C.POINTER(C.c_uint8), C.POINTER(i), p],
         "ecadk_pixart_text_kv": [p, p, i, i, i, C.POINTER(p), C.POINTER(p), C.POINTER(i), p],
+        "ecadk_silu_f32_bf16": [p, p, sz, p],
+        "ecadk_flux_create": [i, C.POINTER(EcadkFluxDesc), C.POINTER(EcadkFluxDoubleWeights),
+                              C.POINTER(EcadkFluxSingleWeights), C.POINTER(p)],
+        "ecadk_flux_destroy": [p],
+        "ecadk_flux_blocks": [p, C.POINTER(EcadkFluxArgs), C.POINTER(C.c_uint8), C.POINTER(i), p],
         "ecadk_profile_start": [],
         "ecadk_profile_stop": [C.POINTER(EcadkProfileRecord)],
     }

@@ -509,6 +509,60 @@ struct EcadkHandle_ {
   std::vector<EcadkBlockWeights> blocks;
 };
 
+struct EcadkFluxHandle_ {
+  int device;
+  EcadkFluxDesc desc;
+  std::vector<EcadkFluxDoubleWeights> dbl;
+  std::vector<EcadkFluxSingleWeights> sgl;
+};
+
+namespace {
+
+// One residual stream of the FLUX executor with its lazily applied cached-residual reuses (same idea as the PixArt
+// executor: a reused component only queues (cache, gate); the next kernel that reads the stream folds them in).
+struct FluxStream {
+  float* x;
+  int rows, tokens, dim, mod_stride;
+  float eps;
+  cudaStream_t stream;
+  int* launches;
+  EcadkResidualLnArgs pend;
+
+  void reset() {
+    memset(&pend, 0, sizeof(pend));
+    pend.x = x;
+    pend.rows = rows;
+    pend.tokens = tokens;
+    pend.dim = dim;
+    pend.temb_stride = mod_stride;
+    pend.eps = eps;
+  }
+  int flush() {
+    if (pend.n_reuse == 0 && pend.h == nullptr && pend.xb == nullptr) return ECADK_OK;
+    const int rc = launch_residual_ln(pend, stream);
+    ++*launches;
+    reset();
+    return rc;
+  }
+  int push(const void* cache, const float* gate_vec) {
+    if (pend.n_reuse == ECADK_MAX_REUSE) {
+      const int rc = flush();
+      if (rc) return rc;
+    }
+    pend.reuse[pend.n_reuse++] = EcadkReuse{cache, nullptr, gate_vec};
+    return ECADK_OK;
+  }
+  // h = LN(x + pending) * (1 + scale) + shift, modulation vectors per sample (no table)
+  int layer_norm(void* h, const float* shift_vec, const float* scale_vec) {
+    pend.h = h;
+    pend.shift_temb = shift_vec;
+    pend.scale_temb = scale_vec;
+    return flush();
+  }
+};
+
+}  // namespace
+
 extern "C" {
 
 int ecadk_abi_version(void) { return ECADK_ABI_VERSION; }
@@ -569,6 +623,18 @@ int ecadk_cast_f32_bf16(const float* in, void* out, size_t n, ecadk_stream_t str
   cast_to_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       in, static_cast<__nv_bfloat16*>(out), n4);
   return check_launch("cast_to_bf16_kernel");
+}
+
+int ecadk_silu_f32_bf16(const float* in, void* out, size_t n, ecadk_stream_t stream) {
+  ECADK_REQUIRE(in && out && n % 4 == 0 && aligned16(in), "silu_f32_bf16: n must be a multiple of 4, 16B aligned");
+  ProfScope prof(ECADK_PROF_OTHER, 0.0, 0.0, static_cast<cudaStream_t>(stream));
+  const size_t n4 = n / 4;
+  size_t blocks = (n4 + 255) / 256;
+  if (blocks > static_cast<size_t>(num_sms()) * 16) blocks = static_cast<size_t>(num_sms()) * 16;
+  if (blocks == 0) return ECADK_OK;
+  silu_to_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, static_cast<__nv_bfloat16*>(out), n4);
+  return check_launch("silu_to_bf16_kernel");
 }
 
 int ecadk_average_halves(void* buf, size_t half_elems, ecadk_stream_t stream) {
@@ -698,6 +764,162 @@ int ecadk_gemm_bias_headmajor(const void* a, const void* w, const float* bias, v
 int ecadk_attention(const void* q, const void* k, const void* v, const float* bias, void* out, int samples,
                     int heads, int q_tokens, int n_keys, ecadk_stream_t stream) {
   return launch_attention(q, k, v, bias, out, samples, heads, q_tokens, n_keys, static_cast<cudaStream_t>(stream));
+}
+
+int ecadk_flux_create(int device, const EcadkFluxDesc* desc, const EcadkFluxDoubleWeights* dbl,
+                      const EcadkFluxSingleWeights* sgl, ecadk_flux_handle_t* out) {
+  ECADK_REQUIRE(desc && dbl && sgl && out, "flux_create: null argument");
+  ECADK_REQUIRE(desc->dim == desc->heads * 128, "flux_create: dim must be heads*128");
+  ECADK_REQUIRE(desc->dim == 512 || desc->dim == 3072, "flux_create: dim=%d (supported: 3072, 512 for tests)", desc->dim);
+  int rc = ecadk_device_check(device);
+  if (rc) return rc;
+  auto* h = new EcadkFluxHandle_();
+  h->device = device;
+  h->desc = *desc;
+  h->dbl.assign(dbl, dbl + desc->num_layers);
+  h->sgl.assign(sgl, sgl + desc->num_single_layers);
+  *out = h;
+  return ECADK_OK;
+}
+
+int ecadk_flux_destroy(ecadk_flux_handle_t h) {
+  delete h;
+  return ECADK_OK;
+}
+
+int ecadk_flux_blocks(ecadk_flux_handle_t h, const EcadkFluxArgs* a, const uint8_t* executed, int* n_launches,
+                      ecadk_stream_t stream_) {
+  ECADK_REQUIRE(h && a && executed, "flux_blocks: null argument");
+  const EcadkFluxDesc& d = h->desc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int D = d.dim, H = d.heads, B = a->samples, N = a->img_tokens, T = a->txt_tokens, S = T + N, F = 4 * D;
+  ECADK_REQUIRE(N % 32 == 0 && T % 32 == 0 && S % 256 == 0, "flux_blocks: tokens N=%d T=%d (N, T %% 32, N+T %% 256)", N, T);
+  int launches = 0;
+  int rc;
+  const int MS = a->mod_stride;
+  ECADK_REQUIRE(a->mod != nullptr && MS >= (d.num_layers * 12 + d.num_single_layers * 3) * D,
+                "flux_blocks: mod_stride=%d too small", MS);
+  FluxStream img{a->x_img, B * N, N, D, MS, d.eps, stream, &launches, {}};
+  FluxStream txt{a->x_txt, B * T, T, D, MS, d.eps, stream, &launches, {}};
+  img.reset();
+  txt.reset();
+
+  // ------------------------------------------------------------------ double-stream blocks
+  for (int b = 0; b < d.num_layers; ++b) {
+    const EcadkFluxDoubleWeights& w = h->dbl[b];
+    const float* mi = a->mod + static_cast<size_t>(b) * 12 * D;  // image stream modulation (row pitch MS)
+    const float* mt = mi + 6 * D;                                  // text stream
+    void* c_attn = a->cache_double[b * 4 + 0];
+    void* c_ctx = a->cache_double[b * 4 + 1];
+    void* c_ff = a->cache_double[b * 4 + 2];
+    void* c_ffc = a->cache_double[b * 4 + 3];
+    const bool ex_attn = executed[b * 3 + 0], ex_ff = executed[b * 3 + 1], ex_ffc = executed[b * 3 + 2];
+    // joint attention (cached_flux_transformer_block.py:170-201,247-256): chunks shift_msa 0, scale_msa 1, gate_msa 2
+    if (ex_attn) {
+      if ((rc = img.layer_norm(a->h_img, mi + 0 * D, mi + 1 * D))) return rc;
+      if ((rc = txt.layer_norm(a->h_txt, mt + 0 * D, mt + 1 * D))) return rc;
+      if ((rc = ecadk_gemm_bias_headmajor_ex(a->h_txt, w.w_qkv_ctx, w.b_qkv_ctx, a->q, a->k, a->v, 3, H, 128, 128, T, S,
+                                             0, B * T, D, stream_)))
+        return rc;
+      if ((rc = ecadk_gemm_bias_headmajor_ex(a->h_img, w.w_qkv, w.b_qkv, a->q, a->k, a->v, 3, H, 128, 128, N, S, T,
+                                             B * N, D, stream_)))
+        return rc;
+      if ((rc = ecadk_qk_norm_rope(a->q, a->k, w.norm_q, w.norm_k, w.norm_added_q, w.norm_added_k, a->rope_cos,
+                                   a->rope_sin, B, H, S, T, d.eps, stream_)))
+        return rc;
+      if ((rc = launch_attention_d128(a->q, a->k, a->v, a->attn_img, D, a->attn_txt, T, B, H, S, S, stream))) return rc;
+      if ((rc = ecadk_gemm_bias_gated_residual_cache(a->attn_img, w.w_out, w.b_out, a->x_img, nullptr, c_attn, nullptr,
+                                                     mi + 2 * D, MS, N, B * N, D, D, stream_)))
+        return rc;
+      if ((rc = ecadk_gemm_bias_gated_residual_cache(a->attn_txt, w.w_out_ctx, w.b_out_ctx, a->x_txt, nullptr, c_ctx,
+                                                     nullptr, mt + 2 * D, MS, T, B * T, D, D, stream_)))
+        return rc;
+      launches += 6;
+    } else {
+      if ((rc = img.push(c_attn, mi + 2 * D))) return rc;
+      if ((rc = txt.push(c_ctx, mt + 2 * D))) return rc;
+    }
+    // image feed-forward (:258-268): shift_mlp 3, scale_mlp 4, gate_mlp 5
+    if (ex_ff) {
+      if ((rc = img.layer_norm(a->h_img, mi + 3 * D, mi + 4 * D))) return rc;
+      if ((rc = ecadk_gemm_bias(a->h_img, w.w_ff1, w.b_ff1, a->ffh, B * N, F, D, F, 1, stream_))) return rc;
+      if ((rc = ecadk_gemm_bias_gated_residual_cache(a->ffh, w.w_ff2, w.b_ff2, a->x_img, nullptr, c_ff, nullptr,
+                                                     mi + 5 * D, MS, N, B * N, D, F, stream_)))
+        return rc;
+      launches += 2;
+    } else {
+      if ((rc = img.push(c_ff, mi + 5 * D))) return rc;
+    }
+    // text feed-forward (:272-287)
+    if (ex_ffc) {
+      if ((rc = txt.layer_norm(a->h_txt, mt + 3 * D, mt + 4 * D))) return rc;
+      if ((rc = ecadk_gemm_bias(a->h_txt, w.w_ff1_ctx, w.b_ff1_ctx, a->ffh, B * T, F, D, F, 1, stream_))) return rc;
+      if ((rc = ecadk_gemm_bias_gated_residual_cache(a->ffh, w.w_ff2_ctx, w.b_ff2_ctx, a->x_txt, nullptr, c_ffc,
+                                                     nullptr, mt + 5 * D, MS, T, B * T, D, F, stream_)))
+        return rc;
+      launches += 2;
+    } else {
+      if ((rc = txt.push(c_ffc, mt + 5 * D))) return rc;
+    }
+  }
+  if ((rc = img.flush())) return rc;
+  if ((rc = txt.flush())) return rc;
+
+  // ------------------------------------------------------------------ concat [text; image] (:205-207)
+  const size_t row_bytes = static_cast<size_t>(D) * sizeof(float);
+  ECADK_CHECK_CUDA(cudaMemcpy2DAsync(a->x_cat, S * row_bytes, a->x_txt, T * row_bytes, T * row_bytes, B,
+                                     cudaMemcpyDeviceToDevice, stream));
+  ECADK_CHECK_CUDA(cudaMemcpy2DAsync(a->x_cat + static_cast<size_t>(T) * D, S * row_bytes, a->x_img, N * row_bytes,
+                                     N * row_bytes, B, cudaMemcpyDeviceToDevice, stream));
+
+  // ------------------------------------------------------------------ single-stream blocks (:99-130)
+  FluxStream cat{a->x_cat, B * S, S, D, MS, d.eps, stream, &launches, {}};
+  cat.reset();
+  for (int b = 0; b < d.num_single_layers; ++b) {
+    const EcadkFluxSingleWeights& w = h->sgl[b];
+    const float* ms = a->mod + (static_cast<size_t>(d.num_layers) * 12 + static_cast<size_t>(b) * 3) * D;  // shift|scale|gate
+    void* c_attn = a->cache_single[b * 3 + 0];
+    void* c_mlp = a->cache_single[b * 3 + 1];
+    void* c_out = a->cache_single[b * 3 + 2];
+    const int r = (d.num_layers + b) * 3;
+    const bool ex_attn = executed[r + 0], ex_mlp = executed[r + 1], ex_out = executed[r + 2];
+    if (ex_attn || ex_mlp) {
+      if ((rc = cat.layer_norm(a->h_cat, ms + 0 * D, ms + 1 * D))) return rc;
+    }
+    if (ex_mlp) {  // proj_mlp, cached PRE-activation
+      if ((rc = ecadk_gemm_bias(a->h_cat, w.w_mlp, w.b_mlp, c_mlp, B * S, F, D, F, 0, stream_))) return rc;
+      ++launches;
+    }
+    if (ex_attn) {
+      if ((rc = ecadk_gemm_bias_headmajor_ex(a->h_cat, w.w_qkv, w.b_qkv, a->q, a->k, a->v, 3, H, 128, 128, S, S, 0,
+                                             B * S, D, stream_)))
+        return rc;
+      if ((rc = ecadk_qk_norm_rope(a->q, a->k, w.norm_q, w.norm_k, nullptr, nullptr, a->rope_cos, a->rope_sin, B, H, S,
+                                   0, d.eps, stream_)))
+        return rc;
+      if ((rc = launch_attention_d128(a->q, a->k, a->v, c_attn, D, nullptr, 0, B, H, S, S, stream))) return rc;
+      launches += 3;
+    }
+    if (ex_out) {
+      // cat = [attn | GELU(proj_mlp)] from the (fresh or reused) cached tensors, then proj_out + gated residual
+      if ((rc = ecadk_strided_unary(c_attn, a->cat, B * S, D, D, 5 * D, 0, stream_))) return rc;
+      if ((rc = ecadk_strided_unary(c_mlp, static_cast<__nv_bfloat16*>(a->cat) + D, B * S, F, F, 5 * D, 1, stream_)))
+        return rc;
+      if ((rc = cat.flush())) return rc;  // the epilogue below updates x in place: pending reuses must land first
+      if ((rc = ecadk_gemm_bias_gated_residual_cache(a->cat, w.w_out, w.b_out, a->x_cat, nullptr, c_out, nullptr,
+                                                     ms + 2 * D, MS, S, B * S, D, 5 * D, stream_)))
+        return rc;
+      launches += 3;
+    } else {
+      if ((rc = cat.push(c_out, ms + 2 * D))) return rc;
+    }
+  }
+  if ((rc = cat.flush())) return rc;
+  // image rows of the concatenated stream -> x_img (the slice at flux_transformer_2d_edited.py:314)
+  ECADK_CHECK_CUDA(cudaMemcpy2DAsync(a->x_img, N * row_bytes, a->x_cat + static_cast<size_t>(T) * D, S * row_bytes,
+                                     N * row_bytes, B, cudaMemcpyDeviceToDevice, stream));
+  if (n_launches) *n_launches = launches;
+  return ECADK_OK;
 }
 
 int ecadk_profile_start(void) {

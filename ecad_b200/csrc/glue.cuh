@@ -318,6 +318,20 @@ __global__ void cast_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16*
   }
 }
 
+// out = bf16(SiLU(in)): the activation in front of every AdaLayerNormZero / ZeroSingle / Continuous linear of FLUX; the
+// result is the A operand of ONE stacked modulation GEMM per step
+__global__ void silu_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n4) {
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (; i < n4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(in) + i);
+    uint2 o;
+    o.x = pack_bf16x2(v.x / (1.0f + __expf(-v.x)), v.y / (1.0f + __expf(-v.y)));
+    o.y = pack_bf16x2(v.z / (1.0f + __expf(-v.z)), v.w / (1.0f + __expf(-v.w)));
+    reinterpret_cast<uint2*>(out)[i] = o;
+  }
+}
+
 // TGATE: cache[0:n] = (cache[0:n] + cache[n:2n]) / 2 (bf16, in place) - the averaged cross-attention output that
 // replaces the CFG pair from the gate step on (cached_transformer_block.py:443-449)
 __global__ void average_halves_kernel(__nv_bfloat16* buf, size_t n8) {

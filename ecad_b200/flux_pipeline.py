@@ -1,0 +1,145 @@
+"""FLUX denoising loop around B200FluxTransformer2D - the contract of diffusers' ``FluxPipeline.__call__`` as the
+reference drives it (/root/reference/ecad/image_generators/flux_image_generator.py:330-352): packed 2x2 latents,
+position ids, FlowMatchEulerDiscreteScheduler with FLUX's resolution-dependent time shift, distilled guidance (no CFG
+pair), ``callback_on_step_end(pipeline, step, timestep, callback_kwargs)``.  Text encoders and the VAE are out of scope:
+the inputs are prompt embeddings, the output is the packed latents (``output_type="latent"``).
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Callable
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def calculate_shift(image_seq_len: int, base_seq_len: int = 256, max_seq_len: int = 4096, base_shift: float = 0.5,
+                    max_shift: float = 1.16) -> float:
+    """diffusers pipeline_flux.calculate_shift."""
+    m = (max_shift - base_shift) / (max_seq_len - base_seq_len)
+    return image_seq_len * m + (base_shift - m * base_seq_len)
+
+
+class FlowMatchEulerDiscrete:
+    """FlowMatchEulerDiscreteScheduler under FLUX.1-dev's scheduler_config (use_dynamic_shifting: sigma' =
+    e^mu / (e^mu + (1/sigma - 1))); ``step`` is x += (sigma_next - sigma) * v, run by ``ecadk_axpy_f32``."""
+
+    order = 1
+    num_train_timesteps = 1000
+
+    def __init__(self):
+        self.sigmas = np.zeros(0, dtype=np.float32)
+        self.timesteps = torch.empty(0)
+        self.step_index = 0
+
+    def set_timesteps(self, num_inference_steps: int | None = None, device=None, sigmas=None, mu: float | None = None):
+        if sigmas is None:
+            sigmas = np.linspace(1.0, 1 / num_inference_steps, num_inference_steps)
+        sigmas = np.asarray(sigmas, dtype=np.float64)
+        if mu is None:
+            raise ValueError("you have to pass a value for `mu` when `use_dynamic_shifting` is set to be `True`")
+        sigmas = math.exp(mu) / (math.exp(mu) + (1 / sigmas - 1))
+        sig32 = sigmas.astype(np.float32)
+        self.timesteps = torch.from_numpy(sig32 * self.num_train_timesteps)
+        self.sigmas = np.concatenate([sig32, np.zeros(1, dtype=np.float32)])
+        self.step_index = 0
+
+    def step_coefficient(self) -> float:
+        return float(self.sigmas[self.step_index + 1]) - float(self.sigmas[self.step_index])
+
+    def advance(self) -> None:
+        self.step_index += 1
+
+
+def pack_latents(latents: torch.Tensor) -> torch.Tensor:
+    """FluxPipeline._pack_latents: [B, C, H, W] -> [B, (H/2)*(W/2), C*4]."""
+    b, c, h, w = latents.shape
+    latents = latents.view(b, c, h // 2, 2, w // 2, 2).permute(0, 2, 4, 1, 3, 5)
+    return latents.reshape(b, (h // 2) * (w // 2), c * 4)
+
+
+def latent_image_ids(batch: int, h2: int, w2: int) -> torch.Tensor:
+    """FluxPipeline._prepare_latent_image_ids (diffusers 0.30.3: repeated over the batch): [B, h2*w2, 3]."""
+    ids = torch.zeros(h2, w2, 3)
+    ids[..., 1] = ids[..., 1] + torch.arange(h2)[:, None]
+    ids[..., 2] = ids[..., 2] + torch.arange(w2)[None, :]
+    return ids.reshape(1, h2 * w2, 3).repeat(batch, 1, 1)
+
+
+class B200FluxPipeline:
+    vae_scale_factor = 16  # FluxPipeline: 2 ** len(vae.config.block_out_channels) for the FLUX VAE
+
+    def __init__(self, transformer, scheduler: FlowMatchEulerDiscrete | None = None):
+        self.transformer = transformer
+        self.scheduler = scheduler if scheduler is not None else FlowMatchEulerDiscrete()
+        self.device = transformer.device
+
+    def prepare_latents(self, batch_size, num_channels_latents, height, width, generator, latents=None):
+        h = 2 * (int(height) // self.vae_scale_factor)
+        w = 2 * (int(width) // self.vae_scale_factor)
+        ids = latent_image_ids(batch_size, h // 2, w // 2)
+        if latents is not None:
+            return latents.to(device=self.device, dtype=torch.float32), ids
+        gen_dev = generator.device if generator is not None else torch.device("cpu")
+        latents = torch.randn((batch_size, num_channels_latents, h, w), generator=generator, device=gen_dev,
+                              dtype=torch.float32)
+        return pack_latents(latents).to(self.device).contiguous(), ids
+
+    @torch.no_grad()
+    def __call__(
+        self,
+        prompt=None,
+        prompt_2=None,
+        prompt_embeds: torch.Tensor | None = None,
+        pooled_prompt_embeds: torch.Tensor | None = None,
+        num_images_per_prompt: int = 1,
+        num_inference_steps: int = 20,
+        generator: torch.Generator | None = None,
+        latents: torch.Tensor | None = None,
+        guidance_scale: float = 5.0,
+        height: int = 256,
+        width: int = 256,
+        callback_on_step_end: Callable[..., dict[str, torch.Tensor]] | None = None,
+        callback_on_step_end_tensor_inputs: list[str] | None = None,
+        output_type: str = "latent",
+        return_dict: bool = False,
+        **kwargs: Any,
+    ):
+        if prompt is not None or prompt_2 is not None:
+            raise ValueError("text encoding is out of scope: pass prompt_embeds / pooled_prompt_embeds")
+        if prompt_embeds is None or pooled_prompt_embeds is None:
+            raise ValueError("prompt_embeds and pooled_prompt_embeds are required")
+        if output_type != "latent":
+            raise NotImplementedError("VAE decode is out of scope; use output_type='latent'")
+        if num_images_per_prompt != 1:
+            raise NotImplementedError("the reference always calls with num_images_per_prompt=1")
+        tr, dev, sched = self.transformer, self.device, self.scheduler
+        batch_size = prompt_embeds.shape[0]
+        prompt_embeds = prompt_embeds.to(dev)
+        pooled_prompt_embeds = pooled_prompt_embeds.to(dev)
+        text_ids = torch.zeros(batch_size, prompt_embeds.shape[1], 3)
+        latents, img_ids = self.prepare_latents(batch_size, tr.config.in_channels // 4, height, width, generator, latents)
+        n_tokens = latents.shape[1]
+        sched.set_timesteps(num_inference_steps, device=dev, mu=calculate_shift(n_tokens))
+        guidance = torch.full((batch_size,), float(guidance_scale), dtype=torch.float32, device=dev) \
+            if tr.config.guidance_embeds else None
+        lib = _lib.load()
+        for i, t in enumerate(sched.timesteps):
+            timestep = t.expand(batch_size).to(dev)
+            noise_pred = tr(hidden_states=latents, timestep=timestep / 1000, guidance=guidance,
+                            pooled_projections=pooled_prompt_embeds, encoder_hidden_states=prompt_embeds,
+                            txt_ids=text_ids, img_ids=img_ids, joint_attention_kwargs=None, return_dict=False)[0]
+            _lib.check(lib.ecadk_axpy_f32(latents.data_ptr(), noise_pred.data_ptr(), sched.step_coefficient(),
+                                          latents.numel(), _lib.stream_ptr()), "euler_step")
+            tr.launches += 1
+            sched.advance()
+            if callback_on_step_end is not None:
+                cb_kwargs = {"latents": latents, "prompt_embeds": prompt_embeds}
+                out = callback_on_step_end(self, i, t, cb_kwargs)
+                latents = out.pop("latents", latents)
+                prompt_embeds = out.pop("prompt_embeds", prompt_embeds)
+        if not return_dict:
+            return (latents,)
+        return {"images": latents}

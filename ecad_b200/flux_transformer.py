@@ -1,0 +1,456 @@
+"""B200FluxTransformer2D - drop-in for the reference's ``FluxTransformer2DEdited`` on the hot path.
+
+Same call surface as /root/reference/ecad/transformer_2d_models/flux_transformer_2d_edited.py:
+``forward(hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids, guidance,
+joint_attention_kwargs, return_dict)`` (:220-231), ``reset_cache()`` (:183-189), attributes ``cache_schedule`` /
+``dit_scheduler`` / ``config`` / ``dtype``.  The per-component rule is the reference's ``recompute or no_cache``
+(ecad/transformer_blocks/cached_flux_transformer_block.py:49-98,170-226), evaluated on the host into one
+``uint8[57][3]`` decision row per step; ``ecadk_flux_blocks`` executes the 19 double-stream + 38 single-stream blocks
+under that row.  Everything numerical runs in libecad_b200.so; PyTorch owns the buffers only.  No CPU path.
+
+HBM layout (B samples - FLUX is guidance-distilled, no CFG pair; N image tokens, T text tokens, S = T + N, D = 3072):
+  x_img / x_txt / x_cat  fp32 [B*N|B*T|B*S, D]   residual streams (fp32, same precision policy as the PixArt path)
+  h_*                    bf16                     LayerNorm+modulate outputs (GEMM A operands)
+  q, k, v                bf16 [B, 24, S, 128]     head-major joint sequence, text tokens first
+  mod                    fp32 [B, 344*D]          every block's adaLN-zero vectors, one stacked GEMM per step
+  caches                 bf16                     4 per double block, 3 per single block (proj_mlp is PRE-GELU)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from types import SimpleNamespace
+from typing import Any, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .schedule import FluxCacheSchedule
+from .transformer import SequentialDiTScheduler, Transformer2DModelOutput
+from .weights import FluxConfig, flux_random_init_state_dict
+
+
+def rope_tables(ids: torch.Tensor, axes_dim: tuple[int, ...], theta: float = 10000.0) -> tuple[torch.Tensor, torch.Tensor]:
+    """EmbedND (diffusers 0.30.3 ``FluxPosEmbed``/``rope``): ids [S, n_axes] -> cos, sin fp32 [S, sum(axes_dim)/2];
+    angles in float64 like the reference."""
+    ids = ids.detach().double().cpu()
+    ang = []
+    for i, d in enumerate(axes_dim):
+        omega = 1.0 / (theta ** (torch.arange(0, d, 2, dtype=torch.float64) / d))
+        ang.append(ids[:, i:i + 1] * omega[None, :])
+    ang = torch.cat(ang, dim=1)
+    return torch.cos(ang).float().contiguous(), torch.sin(ang).float().contiguous()
+
+
+class B200FluxTransformer2D:
+    """FLUX.1 MMDiT with component-wise feature caching, executed by libecad_b200.so."""
+
+    def __init__(
+        self,
+        state_dict: dict[str, torch.Tensor] | None,
+        config: FluxConfig = FluxConfig(),
+        dit_scheduler: SequentialDiTScheduler | None = None,
+        cache_schedule: FluxCacheSchedule | None = None,
+        device: str | torch.device = "cuda:0",
+        device_init_seed: int | None = None,
+    ):
+        if dit_scheduler is None:
+            # flux_transformer_2d_edited.py:62-63
+            raise ValueError("A DiTScheduler object must be provided.")
+        if not torch.cuda.is_available():
+            raise RuntimeError("B200FluxTransformer2D needs a CUDA device; there is no CPU path")
+        self.device = torch.device(device)
+        self._lib = _lib.load()
+        _lib.check(self._lib.ecadk_device_check(self.device.index or 0), "device_check")
+        if config.attention_head_dim != 128:
+            raise ValueError("the FLUX kernels are specialised for attention_head_dim = 128")
+        if sum(config.axes_dims_rope) != config.attention_head_dim:
+            raise ValueError("axes_dims_rope must sum to attention_head_dim")
+        self.cfg = config
+        self.config = SimpleNamespace(
+            in_channels=config.in_channels, num_layers=config.num_layers, num_single_layers=config.num_single_layers,
+            attention_head_dim=config.attention_head_dim, num_attention_heads=config.num_attention_heads,
+            joint_attention_dim=config.joint_attention_dim, pooled_projection_dim=config.pooled_projection_dim,
+            guidance_embeds=config.guidance_embeds, axes_dims_rope=tuple(config.axes_dims_rope),
+        )
+        self.dtype = torch.bfloat16
+        self.dit_scheduler = dit_scheduler
+        self.cache_schedule = cache_schedule if cache_schedule is not None else FluxCacheSchedule.from_numpy(
+            np.ones((dit_scheduler.num_inference_steps, config.num_layers + config.num_single_layers, 3), bool),
+            dit_scheduler.num_inference_steps, config.num_layers, config.num_single_layers, "default")
+        self.eps = 1e-6
+        if state_dict is None:
+            if device_init_seed is None:
+                raise ValueError("either a state dict or device_init_seed is required")
+            self._pack_weights(_DeviceInit(config, self.device, device_init_seed))
+        else:
+            self._pack_weights(state_dict)
+        self._ws: dict[str, Any] = {}
+        self._ws_key: tuple | None = None
+        rows = config.num_layers + config.num_single_layers
+        self._has_cache = np.zeros((rows, 3), dtype=np.bool_)
+        self._text_key: tuple | None = None
+        self._rope_key: tuple | None = None
+        self.last_executed: np.ndarray | None = None
+        self.warnings: list[str] = []
+        self.launches = 0
+
+    @classmethod
+    def from_random_init(cls, dit_scheduler, cache_schedule=None, config: FluxConfig = FluxConfig(), seed: int = 0,
+                         device="cuda:0", on_device: bool = False) -> "B200FluxTransformer2D":
+        """``on_device=True`` draws the constructor-scale weights directly in HBM (the 12 B-parameter FLUX.1-dev does
+        not fit in host RAM as an fp32 state dict); otherwise the CPU state dict of ``flux_random_init_state_dict``
+        (the one the oracle uses) is packed."""
+        if on_device:
+            return cls(None, config, dit_scheduler, cache_schedule, device, device_init_seed=seed)
+        return cls(flux_random_init_state_dict(config, seed), config, dit_scheduler, cache_schedule, device)
+
+    # ------------------------------------------------------------------------------------------------
+    def _pack_weights(self, sd) -> None:
+        dev, cfg = self.device, self.cfg
+        D = cfg.inner_dim
+
+        def f32(t):
+            return t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+        def bf16(t):
+            return t.detach().to(device=dev, dtype=torch.bfloat16).contiguous()
+
+        def cat_w(names):
+            return bf16(torch.cat([sd[n + ".weight"] for n in names], 0))
+
+        def cat_b(names):
+            return f32(torch.cat([sd[n + ".bias"] for n in names], 0))
+
+        w: dict[str, torch.Tensor] = {}
+        w["x_w"], w["x_b"] = bf16(sd["x_embedder.weight"]), f32(sd["x_embedder.bias"])
+        w["ctx_w"], w["ctx_b"] = bf16(sd["context_embedder.weight"]), f32(sd["context_embedder.bias"])
+        embs = ["timestep_embedder"] + (["guidance_embedder"] if cfg.guidance_embeds else []) + ["text_embedder"]
+        for nm in embs:
+            for i, lin in enumerate(("linear_1", "linear_2")):
+                w[f"{nm}_w{i}"] = f32(sd[f"time_text_embed.{nm}.{lin}.weight"])
+                w[f"{nm}_b{i}"] = f32(sd[f"time_text_embed.{nm}.{lin}.bias"])
+        # proj_out zero-padded to 128 output rows (GEMM tile width)
+        n_out = sd["proj_out.weight"].shape[0]
+        pw = torch.zeros(128, D, dtype=torch.float32, device=sd["proj_out.weight"].device)
+        pw[:n_out] = sd["proj_out.weight"].detach().float()
+        pb = torch.zeros(128, dtype=torch.float32, device=sd["proj_out.bias"].device)
+        pb[:n_out] = sd["proj_out.bias"].detach().float()
+        w["out_w"], w["out_b"] = bf16(pw), f32(pb)
+        self.out_channels = n_out
+
+        # every adaLN linear of the model stacked into one [344*D, D] operand: double blocks (norm1 | norm1_context),
+        # single blocks (norm), then norm_out (scale | shift) - the column layout EcadkFluxArgs.mod documents
+        mod_names = []
+        for b in range(cfg.num_layers):
+            mod_names += [f"transformer_blocks.{b}.norm1.linear", f"transformer_blocks.{b}.norm1_context.linear"]
+        mod_names += [f"single_transformer_blocks.{b}.norm.linear" for b in range(cfg.num_single_layers)]
+        mod_names.append("norm_out.linear")
+        w["mod_w"], w["mod_b"] = cat_w(mod_names), cat_b(mod_names)
+        self.mod_cols = w["mod_w"].shape[0]
+        self.mod_out_off = (cfg.num_layers * 12 + cfg.num_single_layers * 3) * D
+        assert self.mod_cols == self.mod_out_off + 2 * D
+        self.w = w
+
+        self._keep: list[torch.Tensor] = []
+        dbl = (_lib.EcadkFluxDoubleWeights * cfg.num_layers)()
+        for b in range(cfg.num_layers):
+            pre = f"transformer_blocks.{b}"
+            bw = {
+                "w_qkv": cat_w([f"{pre}.attn.to_{n}" for n in "qkv"]),
+                "b_qkv": cat_b([f"{pre}.attn.to_{n}" for n in "qkv"]),
+                "w_qkv_ctx": cat_w([f"{pre}.attn.add_{n}_proj" for n in "qkv"]),
+                "b_qkv_ctx": cat_b([f"{pre}.attn.add_{n}_proj" for n in "qkv"]),
+                "w_out": bf16(sd[f"{pre}.attn.to_out.0.weight"]), "b_out": f32(sd[f"{pre}.attn.to_out.0.bias"]),
+                "w_out_ctx": bf16(sd[f"{pre}.attn.to_add_out.weight"]), "b_out_ctx": f32(sd[f"{pre}.attn.to_add_out.bias"]),
+                "w_ff1": bf16(sd[f"{pre}.ff.net.0.proj.weight"]), "b_ff1": f32(sd[f"{pre}.ff.net.0.proj.bias"]),
+                "w_ff2": bf16(sd[f"{pre}.ff.net.2.weight"]), "b_ff2": f32(sd[f"{pre}.ff.net.2.bias"]),
+                "w_ff1_ctx": bf16(sd[f"{pre}.ff_context.net.0.proj.weight"]),
+                "b_ff1_ctx": f32(sd[f"{pre}.ff_context.net.0.proj.bias"]),
+                "w_ff2_ctx": bf16(sd[f"{pre}.ff_context.net.2.weight"]),
+                "b_ff2_ctx": f32(sd[f"{pre}.ff_context.net.2.bias"]),
+                "norm_q": f32(sd[f"{pre}.attn.norm_q.weight"]), "norm_k": f32(sd[f"{pre}.attn.norm_k.weight"]),
+                "norm_added_q": f32(sd[f"{pre}.attn.norm_added_q.weight"]),
+                "norm_added_k": f32(sd[f"{pre}.attn.norm_added_k.weight"]),
+            }
+            for name, t in bw.items():
+                setattr(dbl[b], name, t.data_ptr())
+                self._keep.append(t)
+        sgl = (_lib.EcadkFluxSingleWeights * max(cfg.num_single_layers, 1))()
+        for b in range(cfg.num_single_layers):
+            pre = f"single_transformer_blocks.{b}"
+            bw = {
+                "w_qkv": cat_w([f"{pre}.attn.to_{n}" for n in "qkv"]),
+                "b_qkv": cat_b([f"{pre}.attn.to_{n}" for n in "qkv"]),
+                "w_mlp": bf16(sd[f"{pre}.proj_mlp.weight"]), "b_mlp": f32(sd[f"{pre}.proj_mlp.bias"]),
+                "w_out": bf16(sd[f"{pre}.proj_out.weight"]), "b_out": f32(sd[f"{pre}.proj_out.bias"]),
+                "norm_q": f32(sd[f"{pre}.attn.norm_q.weight"]), "norm_k": f32(sd[f"{pre}.attn.norm_k.weight"]),
+            }
+            for name, t in bw.items():
+                setattr(sgl[b], name, t.data_ptr())
+                self._keep.append(t)
+        desc = _lib.EcadkFluxDesc(cfg.num_layers, cfg.num_single_layers, D, cfg.num_attention_heads, self.eps)
+        handle = C.c_void_p()
+        _lib.check(self._lib.ecadk_flux_create(self.device.index or 0, C.byref(desc), dbl, sgl, C.byref(handle)),
+                   "flux_create")
+        self._handle = handle
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h:
+            try:
+                self._lib.ecadk_flux_destroy(h)
+            except Exception:
+                pass
+
+    # ------------------------------------------------------------------------------------------------
+    def _workspace(self, B: int, N: int, T: int) -> dict[str, Any]:
+        key = (B, N, T)
+        if self._ws_key == key:
+            return self._ws
+        cfg, dev = self.cfg, self.device
+        D, H = cfg.inner_dim, cfg.num_attention_heads
+        S = N + T
+        bf, f32 = torch.bfloat16, torch.float32
+        self._ws = {}
+        ws: dict[str, Any] = {}
+        ws["x_img"] = torch.empty(B * N, D, device=dev, dtype=f32)
+        ws["x_txt"] = torch.empty(B * T, D, device=dev, dtype=f32)
+        ws["x_txt0"] = torch.empty(B * T, D, device=dev, dtype=f32)  # context_embedder output, once per generation
+        ws["x_cat"] = torch.empty(B * S, D, device=dev, dtype=f32)
+        ws["h_img"] = torch.empty(B * N, D, device=dev, dtype=bf)
+        ws["h_txt"] = torch.empty(B * T, D, device=dev, dtype=bf)
+        ws["h_cat"] = torch.empty(B * S, D, device=dev, dtype=bf)
+        for n in ("q", "k", "v"):
+            ws[n] = torch.empty(B, H, S, 128, device=dev, dtype=bf)
+        ws["attn_img"] = torch.empty(B * N, D, device=dev, dtype=bf)
+        ws["attn_txt"] = torch.empty(B * T, D, device=dev, dtype=bf)
+        ws["ffh"] = torch.empty(B * max(N, T), 4 * D, device=dev, dtype=bf)
+        ws["cat"] = torch.empty(B * S, 5 * D, device=dev, dtype=bf)
+        ws["mod"] = torch.empty(B, self.mod_cols, device=dev, dtype=f32)
+        ws["lat_bf"] = torch.empty(B * N, cfg.in_channels, device=dev, dtype=bf)
+        ws["enc_bf"] = torch.empty(B * T, cfg.joint_attention_dim, device=dev, dtype=bf)
+        ws["t_proj"] = torch.empty(B, 256, device=dev, dtype=f32)
+        ws["t_e1"] = torch.empty(B, D, device=dev, dtype=f32)
+        ws["temb"] = torch.empty(B, D, device=dev, dtype=f32)
+        ws["temb_silu"] = torch.empty(B, D, device=dev, dtype=bf)
+        ws["out"] = torch.empty(B * N, self.out_channels, device=dev, dtype=f32)
+        cd, cs = [], []
+        for _ in range(cfg.num_layers):
+            cd += [torch.empty(B * N, D, device=dev, dtype=bf), torch.empty(B * T, D, device=dev, dtype=bf),
+                   torch.empty(B * N, D, device=dev, dtype=bf), torch.empty(B * T, D, device=dev, dtype=bf)]
+        for _ in range(cfg.num_single_layers):
+            cs += [torch.empty(B * S, D, device=dev, dtype=bf), torch.empty(B * S, 4 * D, device=dev, dtype=bf),
+                   torch.empty(B * S, D, device=dev, dtype=bf)]
+        ws["cache_double"], ws["cache_single"] = cd, cs
+        ws["cd_ptrs"] = (C.c_void_p * max(len(cd), 1))(*[t.data_ptr() for t in cd])
+        ws["cs_ptrs"] = (C.c_void_p * max(len(cs), 1))(*[t.data_ptr() for t in cs])
+        a = _lib.EcadkFluxArgs()
+        a.samples, a.img_tokens, a.txt_tokens = B, N, T
+        for n in ("x_img", "x_txt", "x_cat", "h_img", "h_txt", "h_cat", "q", "k", "v", "attn_img", "attn_txt", "ffh",
+                  "cat", "mod"):
+            setattr(a, n, ws[n].data_ptr())
+        a.mod_stride = self.mod_cols
+        a.cache_double = C.cast(ws["cd_ptrs"], C.POINTER(C.c_void_p))
+        a.cache_single = C.cast(ws["cs_ptrs"], C.POINTER(C.c_void_p))
+        ws["args"] = a
+        self._ws, self._ws_key = ws, key
+        self._has_cache[:] = False
+        self._text_key = None
+        self._rope_key = None
+        return ws
+
+    # ------------------------------------------------------------------------------------------------
+    def reset_cache(self) -> None:
+        """flux_transformer_2d_edited.py:183-189: drop every cached tensor (validity bits only; HBM slots stay)."""
+        self._has_cache[:] = False
+        self._text_key = None
+
+    def _decide(self) -> np.ndarray:
+        """``recompute or no_cache`` per component (cached_flux_transformer_block.py:52-61,81-91,173-186,207-216)."""
+        sched, cfg = self.cache_schedule, self.cfg
+        rows = cfg.num_layers + cfg.num_single_layers
+        executed = np.zeros((rows, 3), dtype=np.uint8)
+        full = ("full_attn", "full_ff", "full_ff_context")
+        single = ("single_attn", "single_proj_mlp", "single_proj_out")
+        what = {"full_attn": "attn", "full_ff": "ff", "full_ff_context": "ff_context", "single_attn": "attn",
+                "single_proj_mlp": "proj_mlp", "single_proj_out": "proj_out"}
+        for r in range(rows):
+            key, names = (str(r), full) if r < cfg.num_layers else (f"single_{r - cfg.num_layers}", single)
+            for c, comp in enumerate(names):
+                recompute = bool(sched.get_recompute(key, comp))
+                no_cache = not self._has_cache[r, c]
+                if not recompute and no_cache:
+                    self.warnings.append(f"WARNING: No cached {what[comp]} found. Recomputing.")
+                executed[r, c] = recompute or no_cache
+        return executed
+
+    # ------------------------------------------------------------------------------------------------
+    def _small_linear(self, x, ldx, w, b, y, rows, k, o, ldy, act_in, accumulate, what):
+        _lib.check(self._lib.ecadk_small_linear(x.data_ptr(), ldx, w.data_ptr(), b.data_ptr(), y.data_ptr(), rows, k, o,
+                                                ldy, 0, act_in, accumulate, _lib.stream_ptr()), what)
+
+    @torch.no_grad()
+    def forward(
+        self,
+        hidden_states: torch.Tensor,
+        encoder_hidden_states: Optional[torch.Tensor] = None,
+        pooled_projections: Optional[torch.Tensor] = None,
+        timestep: Optional[torch.Tensor] = None,
+        img_ids: Optional[torch.Tensor] = None,
+        txt_ids: Optional[torch.Tensor] = None,
+        guidance: Optional[torch.Tensor] = None,
+        joint_attention_kwargs: dict[str, Any] | None = None,
+        return_dict: bool = True,
+    ):
+        cfg, lib, w, dev = self.cfg, self._lib, self.w, self.device
+        if encoder_hidden_states is None or pooled_projections is None or timestep is None:
+            raise ValueError("encoder_hidden_states, pooled_projections and timestep are required")
+        if img_ids is None or txt_ids is None:
+            raise ValueError("img_ids and txt_ids are required")
+        if cfg.guidance_embeds and guidance is None:
+            raise ValueError("this model embeds guidance (FLUX.1-dev): `guidance` is required")
+        B, N, Cin = hidden_states.shape
+        T = encoder_hidden_states.shape[1]
+        D = cfg.inner_dim
+        S = N + T
+        if N % 32 or T % 32 or S % 256:
+            raise NotImplementedError(f"N={N} image / T={T} text tokens: need N, T % 32 == 0 and (N+T) % 256 == 0")
+        ws = self._workspace(B, N, T)
+        st = _lib.stream_ptr()
+        launches = 0
+
+        # x_embedder (:275)
+        lat = hidden_states.to(device=dev)
+        if lat.dtype == torch.float32:
+            lat = lat.contiguous()
+            _lib.check(lib.ecadk_cast_f32_bf16(lat.data_ptr(), ws["lat_bf"].data_ptr(), lat.numel(), st), "cast")
+            launches += 1
+        else:
+            ws["lat_bf"].copy_(lat.reshape(B * N, Cin))
+        _lib.check(lib.ecadk_gemm_bias_f32(ws["lat_bf"].data_ptr(), w["x_w"].data_ptr(), w["x_b"].data_ptr(),
+                                           ws["x_img"].data_ptr(), B * N, D, Cin, D, D, st), "x_embedder")
+        launches += 1
+
+        # time_text_embed (:277-286): timestep (+ guidance) sinusoid MLPs + pooled-text MLP, summed
+        def scalar_embed(values, name, accumulate):
+            v = (values.to(device=dev, dtype=torch.float32).reshape(-1) * 1000.0).contiguous()
+            if v.numel() != B:
+                raise ValueError(f"{name} has {v.numel()} entries for a batch of {B}")
+            _lib.check(lib.ecadk_timestep_sinusoid(v.data_ptr(), ws["t_proj"].data_ptr(), B, 256, st), "sinusoid")
+            self._small_linear(ws["t_proj"], 256, w[f"{name}_w0"], w[f"{name}_b0"], ws["t_e1"], B, 256, D, D, 0, 0,
+                               name + ".linear_1")
+            self._small_linear(ws["t_e1"], D, w[f"{name}_w1"], w[f"{name}_b1"], ws["temb"], B, D, D, D, 1, accumulate,
+                               name + ".linear_2")
+
+        scalar_embed(timestep, "timestep_embedder", 0)
+        launches += 3
+        if cfg.guidance_embeds:
+            scalar_embed(guidance, "guidance_embedder", 1)
+            launches += 3
+        pooled = pooled_projections.to(device=dev, dtype=torch.float32).contiguous()
+        P = cfg.pooled_projection_dim
+        self._small_linear(pooled, P, w["text_embedder_w0"], w["text_embedder_b0"], ws["t_e1"], B, P, D, D, 0, 0,
+                           "text_embedder.linear_1")
+        self._small_linear(ws["t_e1"], D, w["text_embedder_w1"], w["text_embedder_b1"], ws["temb"], B, D, D, D, 1, 1,
+                           "text_embedder.linear_2")
+        # every adaLN linear of the step in one GEMM: mod = Linear(SiLU(temb)) (AdaLayerNormZero/ZeroSingle/Continuous)
+        _lib.check(lib.ecadk_silu_f32_bf16(ws["temb"].data_ptr(), ws["temb_silu"].data_ptr(), B * D, st), "silu")
+        _lib.check(lib.ecadk_gemm_bias_f32(ws["temb_silu"].data_ptr(), w["mod_w"].data_ptr(), w["mod_b"].data_ptr(),
+                                           ws["mod"].data_ptr(), B, self.mod_cols, D, self.mod_cols, self.mod_cols,
+                                           st), "modulation")
+        launches += 4
+
+        # context_embedder (:288) - step-invariant, once per generation
+        text_key = (encoder_hidden_states.data_ptr(), tuple(encoder_hidden_states.shape))
+        if self._text_key != text_key or self.cache_schedule.curr_step == 0:
+            enc = encoder_hidden_states.to(device=dev)
+            if enc.dtype == torch.float32:
+                enc = enc.contiguous()
+                _lib.check(lib.ecadk_cast_f32_bf16(enc.data_ptr(), ws["enc_bf"].data_ptr(), enc.numel(), st), "cast")
+                launches += 1
+            else:
+                ws["enc_bf"].copy_(enc.reshape(B * T, -1))
+            _lib.check(lib.ecadk_gemm_bias_f32(ws["enc_bf"].data_ptr(), w["ctx_w"].data_ptr(), w["ctx_b"].data_ptr(),
+                                               ws["x_txt0"].data_ptr(), B * T, D, cfg.joint_attention_dim, D, D, st),
+                       "context_embedder")
+            launches += 1
+            self._text_key = text_key
+        ws["x_txt"].copy_(ws["x_txt0"])
+
+        # pos_embed (:290-291): rotation tables of the joint [text; image] sequence, shared by the batch
+        rope_key = (img_ids.data_ptr(), tuple(img_ids.shape), txt_ids.data_ptr(), tuple(txt_ids.shape))
+        if self._rope_key != rope_key:
+            ii, ti = img_ids, txt_ids
+            if ii.ndim == 3:
+                if bool((ii != ii[:1]).any()) or bool((ti != ti[:1]).any()):
+                    raise NotImplementedError("per-sample position ids are not supported (one resolution per batch)")
+                ii, ti = ii[0], ti[0]
+            cos, sin = rope_tables(torch.cat([ti, ii], dim=0), cfg.axes_dims_rope)
+            ws["rope_cos"], ws["rope_sin"] = cos.to(dev), sin.to(dev)
+            ws["args"].rope_cos, ws["args"].rope_sin = ws["rope_cos"].data_ptr(), ws["rope_sin"].data_ptr()
+            self._rope_key = rope_key
+
+        # blocks under the decision row of the current step
+        executed = self._decide()
+        self.last_executed = executed
+        ex = np.ascontiguousarray(executed.reshape(-1))
+        n_l = C.c_int(0)
+        _lib.check(lib.ecadk_flux_blocks(self._handle, C.byref(ws["args"]), ex.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                         C.byref(n_l), st), "flux_blocks")
+        launches += n_l.value
+        self._has_cache |= executed.astype(np.bool_)
+
+        # norm_out (AdaLayerNormContinuous: scale first, then shift) + proj_out (:316-317)
+        mo = ws["mod"][:, self.mod_out_off:]
+        _lib.residual_ln(ws["x_img"], N, h=ws["h_img"], shift_temb=mo[:, D:], scale_temb=mo, temb_stride=self.mod_cols,
+                         eps=self.eps)
+        _lib.check(lib.ecadk_gemm_bias_f32(ws["h_img"].data_ptr(), w["out_w"].data_ptr(), w["out_b"].data_ptr(),
+                                           ws["out"].data_ptr(), B * N, 128, D, self.out_channels, self.out_channels,
+                                           st), "proj_out")
+        launches += 2
+        self.launches += launches
+        out = ws["out"].view(B, N, self.out_channels)
+        if hidden_states.dtype != torch.float32:
+            out = out.to(hidden_states.dtype)
+        if not return_dict:
+            return (out,)
+        return Transformer2DModelOutput(sample=out)
+
+    __call__ = forward
+
+
+class _DeviceInit:
+    """Mapping that draws constructor-scale tensors on the device on demand (see ``from_random_init(on_device=True)``):
+    U(+-1/sqrt(fan_in)) for Linear weight/bias, ones for the q/k RMSNorm weights."""
+
+    def __init__(self, cfg: FluxConfig, device: torch.device, seed: int):
+        self.cfg, self.device = cfg, device
+        self.gen = torch.Generator(device=device).manual_seed(seed)
+        D = cfg.inner_dim
+        self._fan_in = {"x_embedder": cfg.in_channels, "context_embedder": cfg.joint_attention_dim,
+                        "text_embedder.linear_1": cfg.pooled_projection_dim, "timestep_embedder.linear_1": 256,
+                        "guidance_embedder.linear_1": 256, "ff.net.2": 4 * D, "ff_context.net.2": 4 * D,
+                        "proj_out": None}
+        self._out = {"norm1.linear": 6 * D, "norm1_context.linear": 6 * D, "norm.linear": 3 * D, "norm_out.linear": 2 * D,
+                     "net.0.proj": 4 * D, "proj_mlp": 4 * D}
+
+    def __getitem__(self, key: str) -> torch.Tensor:
+        cfg, D = self.cfg, self.cfg.inner_dim
+        stem, kind = key.rsplit(".", 1)
+        if ".norm_" in key:  # attn.norm_q / norm_k / norm_added_*
+            return torch.ones(cfg.attention_head_dim, device=self.device)
+        fan_in, out = D, D
+        for pat, v in self._fan_in.items():
+            if stem.endswith(pat):
+                fan_in = v if v is not None else fan_in
+        if stem.startswith("single_transformer_blocks") and stem.endswith("proj_out"):
+            fan_in = 5 * D
+        elif stem == "proj_out":
+            out = cfg.in_channels
+        for pat, v in self._out.items():
+            if stem.endswith(pat):
+                out = v
+        bound = 1.0 / fan_in**0.5
+        shape = (out, fan_in) if kind == "weight" else (out,)
+        return (torch.rand(shape, device=self.device, generator=self.gen, dtype=torch.float32) * 2 - 1) * bound

@@ -150,3 +150,140 @@ class B200PixArtImageGenerator:
 @ImageGeneratorRegistry.register("b200_pixart_alpha")
 class B200PixArtAlphaImageGenerator(B200PixArtImageGenerator):
     """Selected by ``config.image_generator = "b200_pixart_alpha"`` in a schedule JSON (ecad/types.py:43-47)."""
+
+
+@ImageGeneratorRegistry.register("b200_flux")
+class B200FluxImageGenerator:
+    """FLUX.1 counterpart (/root/reference/ecad/image_generators/flux_image_generator.py:29-418): same defaults
+    (256x256, guidance 5, 20 steps), same callback protocol - the pipeline calls
+    ``_call_callbacks_wrapper(pipeline, step, timestep, callback_kwargs)`` which advances the step counters, runs the
+    extra callbacks, resets LAST, and hands ``latents`` / ``prompt_embeds`` back (:79-101)."""
+
+    DEFAULT_HEIGHT = 256
+    DEFAULT_WIDTH = 256
+    DEFAULT_GUIDANCE_SCALE = 5
+    DEFAULT_NUM_INFERENCE_STEPS = 20
+    default_pipeline_name = "flux"
+
+    def __init__(self, schedule_path: Path | str | None = None, start_seed: int = 0, seed_step: int = 1,
+                 additional_callbacks: list[Callable[..., None]] | None = None,
+                 state_dict: dict[str, torch.Tensor] | None = None, model_config=None, weight_seed: int = 0,
+                 device: str = "cuda:0", cache_schedule=None, weights_on_device: bool = False):
+        from .weights import FluxConfig
+
+        if not torch.cuda.is_available():
+            # flux_image_generator.py:45-46
+            raise ValueError("CUDA is required for image generation.")
+        self.device = device
+        self.start_seed, self.seed_step = start_seed, seed_step
+        self.additional_callbacks = list(additional_callbacks or [])
+        self.model_config = model_config if model_config is not None else FluxConfig()
+        self._state_dict, self._weight_seed, self._weights_on_device = state_dict, weight_seed, weights_on_device
+        self.height, self.width = self.DEFAULT_HEIGHT, self.DEFAULT_WIDTH
+        self.guidance_scale = self.DEFAULT_GUIDANCE_SCALE
+        self.diffusion_pipeline = None
+        self.random_generator = torch.Generator(device="cpu")
+        self.random_generator.manual_seed(self.start_seed)
+        self._load_schedule(schedule_path, cache_schedule)
+
+    def _load_schedule(self, schedule_path, cache_schedule) -> None:
+        import json
+
+        import numpy as np
+
+        from .schedule import FluxCacheSchedule
+
+        cfg = self.model_config
+        if cache_schedule is None and schedule_path is not None:
+            data = json.loads(Path(schedule_path).read_text())
+            if "dit_schedule" in data:
+                raise NotImplementedError("non-default DiT block graphs are out of scope (no shipped schedule uses one)")
+            if "cache_schedule" in data:
+                cache_schedule = FluxCacheSchedule.from_dict(data)
+        if cache_schedule is None:  # _default_cache_schedule (:74-77): everything recomputed
+            n = self.DEFAULT_NUM_INFERENCE_STEPS
+            cache_schedule = FluxCacheSchedule.from_numpy(
+                np.ones((n, cfg.num_layers + cfg.num_single_layers, 3), bool), n, cfg.num_layers,
+                cfg.num_single_layers, "default")
+        self.cache_schedule = cache_schedule
+        self.num_inference_steps = cache_schedule.num_inference_steps
+        self.dit_scheduler = SequentialDiTScheduler(self.num_inference_steps)
+        self.config = cache_schedule.top_level_config or {}
+        # _load_subclass_config_defaults (:62-69)
+        self.height = self.config.get("height", self.DEFAULT_HEIGHT)
+        self.width = self.config.get("width", self.DEFAULT_WIDTH)
+        self.guidance_scale = self.config.get("guidance_scale", self.DEFAULT_GUIDANCE_SCALE)
+        self.callbacks = [self.dit_scheduler.per_step_callback, self.cache_schedule.per_step_callback]
+        self.callbacks.extend(self.additional_callbacks)
+        self.callbacks.append(self._reset_schedules_callback)  # MUST be last (image_generator.py:156-159)
+        if self.diffusion_pipeline is not None:
+            tr = self.diffusion_pipeline.transformer
+            tr.cache_schedule, tr.dit_scheduler = self.cache_schedule, self.dit_scheduler
+            tr.reset_cache()
+
+    def set_schedule(self, cache_schedule) -> None:
+        self._load_schedule(None, cache_schedule)
+
+    def _reset_schedules_callback(self, step: int, timestep: Any, **kwargs: Any) -> None:
+        if step >= self.num_inference_steps - 1:
+            self.dit_scheduler.reset_step()
+            self.cache_schedule.reset_step()
+            if self.diffusion_pipeline is not None:
+                self.diffusion_pipeline.transformer.reset_cache()
+
+    def _call_callbacks(self, step: int, timestep: Any, **kwargs: Any) -> None:
+        for cb in self.callbacks:
+            cb(step, timestep, **kwargs)
+
+    # flux_image_generator.py:79-101
+    def _call_callbacks_wrapper(self, _pipeline, step: int, timestep: Any,
+                                callback_kwargs: dict[str, Any]) -> dict[str, torch.Tensor]:
+        if "latents" not in callback_kwargs or "prompt_embeds" not in callback_kwargs:
+            print("WARNING: Callback kwargs missing latents or prompt embeds. This will likley cause a crash.")
+        self._call_callbacks(step, timestep)
+        return {"latents": callback_kwargs["latents"], "prompt_embeds": callback_kwargs["prompt_embeds"]}
+
+    def create_diffusion_pipeline(self, skip_transformer_block_init: bool = False):
+        from .flux_pipeline import B200FluxPipeline
+        from .flux_transformer import B200FluxTransformer2D
+
+        if self.diffusion_pipeline is None:
+            if self._state_dict is None:
+                tr = B200FluxTransformer2D.from_random_init(self.dit_scheduler, self.cache_schedule, self.model_config,
+                                                            self._weight_seed, self.device, self._weights_on_device)
+            else:
+                tr = B200FluxTransformer2D(self._state_dict, self.model_config, self.dit_scheduler, self.cache_schedule,
+                                           self.device)
+            self.diffusion_pipeline = B200FluxPipeline(tr)
+        return self.diffusion_pipeline
+
+    # flux_image_generator.py:285-363 (returns packed latents [images_per_prompt][B, N, 64] instead of PIL images)
+    @torch.inference_mode()
+    def generate_images(self, prompt_embeds: dict[str, torch.Tensor], images_per_prompt: int = 1,
+                        height: int | None = None, width: int | None = None, guidance_scale: float | None = None,
+                        **kwargs) -> list[torch.Tensor]:
+        pipe = self.create_diffusion_pipeline()
+        out = []
+        for i in range(images_per_prompt):
+            self.random_generator.manual_seed(self.start_seed + i * self.seed_step)
+            lat = pipe(
+                prompt=None, prompt_2=None,
+                prompt_embeds=prompt_embeds["prompt_embeds"], pooled_prompt_embeds=prompt_embeds["pooled_prompt_embeds"],
+                num_images_per_prompt=1, num_inference_steps=self.num_inference_steps, generator=self.random_generator,
+                return_dict=False, height=height or self.height, width=width or self.width,
+                guidance_scale=guidance_scale or self.guidance_scale,
+                callback_on_step_end=self._call_callbacks_wrapper,
+                callback_on_step_end_tensor_inputs=["latents", "prompt_embeds"],
+            )[0]
+            out.append(lat.clone())
+        return out
+
+    # flux_image_generator.py:365-418: CUDA-event ms per image of one pipeline call
+    @torch.inference_mode()
+    def generate_images_timed(self, prompt_embeds: dict[str, torch.Tensor], **kwargs) -> float:
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        self.generate_images(prompt_embeds, images_per_prompt=1, **kwargs)
+        end.record()
+        torch.cuda.synchronize()
+        return start.elapsed_time(end) / prompt_embeds["prompt_embeds"].shape[0]

@@ -190,6 +190,11 @@ int ecadk_strided_unary(const void* src, void* dst, int rows, int cols, int ld_s
 /* y += a * x (fp32): FlowMatchEulerDiscreteScheduler.step, latents += (sigma_next - sigma) * model_output. */
 int ecadk_axpy_f32(float* y, const float* x, float a, size_t n, ecadk_stream_t stream);
 
+/* out = bf16(SiLU(in)).  Replaces the nn.SiLU in front of AdaLayerNormZero / AdaLayerNormZeroSingle /
+ * AdaLayerNormContinuous .linear (diffusers 0.30.3, called from cached_flux_transformer_block.py:101,234-243); the
+ * result feeds ONE stacked modulation GEMM per step (every block's norm*.linear at once). */
+int ecadk_silu_f32_bf16(const float* in, void* out, size_t n, ecadk_stream_t stream);
+
 /* fp32 out[row, 0:out_cols] = A W^T + bias (row pitch ldo); W may be zero-padded to N % 128 == 0 rows.
  * Replaces x_embedder / context_embedder / proj_out of FluxTransformer2DModel
  * (ecad/transformer_2d_models/flux_transformer_2d_edited.py:275,288,317). */
@@ -264,6 +269,77 @@ int ecadk_pixart_blocks(ecadk_handle_t h, const EcadkBlocksArgs* args, const uin
  * (cached_transformer_block.py:348-353 with encoder_hidden_states). */
 int ecadk_pixart_text_kv(ecadk_handle_t h, const void* enc, int samples, int text_tokens, int text_pad,
                          void* const* k2, void* const* v2, int* n_launches, ecadk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * FLUX step-level executor: 19 double-stream + 38 single-stream blocks of one forward under one decision row.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+typedef struct {
+  int num_layers;        /* 19 double-stream blocks */
+  int num_single_layers; /* 38 single-stream blocks */
+  int dim;               /* 3072 = heads * 128 */
+  int heads;             /* 24 */
+  float eps;             /* 1e-6 (LayerNorm and q/k RMSNorm) */
+} EcadkFluxDesc;
+
+typedef struct { /* FluxTransformerBlock; weights bf16 [out, in], biases / norm weights fp32 */
+  const void* w_qkv;     const float* b_qkv;     /* attn.to_q|to_k|to_v stacked [3*dim, dim] (image stream) */
+  const void* w_qkv_ctx; const float* b_qkv_ctx; /* attn.add_q_proj|add_k_proj|add_v_proj (text stream) */
+  const void* w_out;     const float* b_out;     /* attn.to_out.0 */
+  const void* w_out_ctx; const float* b_out_ctx; /* attn.to_add_out */
+  const void* w_ff1;     const float* b_ff1;     /* ff.net.0.proj [4*dim, dim] */
+  const void* w_ff2;     const float* b_ff2;     /* ff.net.2 [dim, 4*dim] */
+  const void* w_ff1_ctx; const float* b_ff1_ctx; /* ff_context */
+  const void* w_ff2_ctx; const float* b_ff2_ctx;
+  const float* norm_q; const float* norm_k; const float* norm_added_q; const float* norm_added_k; /* [128] each */
+} EcadkFluxDoubleWeights;
+
+typedef struct { /* FluxSingleTransformerBlock */
+  const void* w_qkv; const float* b_qkv; /* attn.to_q|to_k|to_v stacked [3*dim, dim] */
+  const void* w_mlp; const float* b_mlp; /* proj_mlp [4*dim, dim] */
+  const void* w_out; const float* b_out; /* proj_out [dim, 5*dim] */
+  const float* norm_q; const float* norm_k;
+} EcadkFluxSingleWeights;
+
+typedef struct EcadkFluxHandle_* ecadk_flux_handle_t;
+int ecadk_flux_create(int device, const EcadkFluxDesc* desc, const EcadkFluxDoubleWeights* dbl,
+                      const EcadkFluxSingleWeights* sgl, ecadk_flux_handle_t* out);
+int ecadk_flux_destroy(ecadk_flux_handle_t h);
+
+typedef struct {
+  int samples;     /* B (FLUX runs without classifier-free guidance) */
+  int img_tokens;  /* N = (H/16)*(W/16), multiple of 32 */
+  int txt_tokens;  /* T (512), multiple of 32; T + N must be a multiple of 256 */
+  float* x_img;    /* fp32 [B*N, dim]  image residual stream (in: embedded latents; out: image rows after all blocks) */
+  float* x_txt;    /* fp32 [B*T, dim]  text residual stream (in: context_embedder output) */
+  float* x_cat;    /* fp32 scratch [B*(T+N), dim]: the concatenated stream of the single-stream phase */
+  void* h_img;     /* bf16 scratch [B*N, dim] */
+  void* h_txt;     /* bf16 scratch [B*T, dim] */
+  void* h_cat;     /* bf16 scratch [B*(T+N), dim] */
+  void* q; void* k; void* v; /* bf16 scratch [B, heads, T+N, 128] */
+  void* attn_img;  /* bf16 scratch [B*N, dim] */
+  void* attn_txt;  /* bf16 scratch [B*T, dim] */
+  void* ffh;       /* bf16 scratch [B*max(N,T), 4*dim] */
+  void* cat;       /* bf16 scratch [B*(T+N), 5*dim]: [attn | GELU(mlp)] of the single-stream blocks */
+  const float* mod;  /* fp32 [B, mod_stride]: all modulation vectors of this step, one row per sample.  Column layout:
+                      * double block b: [b*12*dim, +6*dim) image stream (norm1.linear), then +6*dim text stream
+                      * (norm1_context.linear), each = shift_msa|scale_msa|gate_msa|shift_mlp|scale_mlp|gate_mlp;
+                      * single block b: [num_layers*12*dim + b*3*dim, +3*dim) = shift|scale|gate (norm.linear). */
+  int mod_stride;
+  const float* rope_cos;   /* fp32 [T+N, 64] */
+  const float* rope_sin;
+  void* const* cache_double; /* host array [num_layers*4]: attn [B*N,dim], context_attn [B*T,dim], ff [B*N,dim], ff_context [B*T,dim] */
+  void* const* cache_single; /* host array [num_single_layers*3]: attn [B*(T+N),dim], proj_mlp (pre-GELU) [B*(T+N),4*dim], proj_out [B*(T+N),dim] */
+} EcadkFluxArgs;
+
+/* executed[(b)*3 + c]: rows 0..num_layers-1 = double blocks with c in {full_attn, full_ff, full_ff_context}, rows
+ * num_layers.. = single blocks with c in {single_attn, single_proj_mlp, single_proj_out} (FluxCacheSchedule order;
+ * the caller has applied "flag or cache is None").  HOST array.
+ * Replaces _dit_scheduler_forward_short_circuit + CachedFluxTransformerBlock / CachedFluxSingleTransformerBlock.forward
+ * (ecad/transformer_2d_models/flux_transformer_2d_edited.py:191-218,
+ *  ecad/transformer_blocks/cached_flux_transformer_block.py:99-130,228-291). */
+int ecadk_flux_blocks(ecadk_flux_handle_t h, const EcadkFluxArgs* args, const uint8_t* executed, int* n_launches,
+                      ecadk_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * In-situ kernel timing (measurement support for bench.py; no reference counterpart - the reference only times
