@@ -295,6 +295,56 @@ __device__ __forceinline__ void softmax_chunk_exp(const uint32_t (&v)[32], uint3
   }
 }
 
+// Register-resident rows (the whole score row of a thread stays in registers between the two steps):
+// prep: with a key bias the scaled+biased score replaces the raw one in place (so the bias is read once); without, the
+// raw maximum is taken and scaled by the caller.  exp: p = exp2(t - m) resp. exp2(score * scale - m).
+template <bool HAS_BIAS>
+__device__ __forceinline__ float softmax_chunk_prep(uint32_t (&v)[32], float mx, float scale_log2e, uint32_t bias_a) {
+  if constexpr (!HAS_BIAS) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) mx = fmax3(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+  } else {
+    const uint64_t sc2 = pack_f2(scale_log2e, scale_log2e);
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 b4 = lds_f4(bias_a + i * 4);
+      float t0, t1, t2, t3;
+      unpack_f2(ffma2(pack_f2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, pack_f2(b4.x, b4.y)), t0, t1);
+      unpack_f2(ffma2(pack_f2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])), sc2, pack_f2(b4.z, b4.w)), t2, t3);
+      v[i] = __float_as_uint(t0);
+      v[i + 1] = __float_as_uint(t1);
+      v[i + 2] = __float_as_uint(t2);
+      v[i + 3] = __float_as_uint(t3);
+      mx = fmax3(mx, t0, t1);
+      mx = fmax3(mx, t2, t3);
+    }
+  }
+  return mx;
+}
+
+template <bool HAS_BIAS>
+__device__ __forceinline__ void softmax_chunk_exp_reg(const uint32_t (&v)[32], uint32_t (&pk)[16], uint64_t& sum2, float m,
+                                                      float scale_log2e) {
+  const uint64_t sc2 = pack_f2(scale_log2e, scale_log2e);
+  const uint64_t nm2 = pack_f2(-m, -m);
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    float t0, t1, t2, t3;
+    if constexpr (HAS_BIAS) {
+      unpack_f2(fadd2(pack_f2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), nm2), t0, t1);
+      unpack_f2(fadd2(pack_f2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])), nm2), t2, t3);
+    } else {
+      unpack_f2(ffma2(pack_f2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, nm2), t0, t1);
+      unpack_f2(ffma2(pack_f2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])), sc2, nm2), t2, t3);
+    }
+    const float e0 = fast_exp2(t0), e1 = fast_exp2(t1), e2 = fast_exp2(t2), e3 = fast_exp2(t3);
+    sum2 = fadd2(sum2, pack_f2(e0, e1));
+    sum2 = fadd2(sum2, pack_f2(e2, e3));
+    pk[i / 2] = pack_bf16x2(e0, e1);
+    pk[i / 2 + 1] = pack_bf16x2(e2, e3);
+  }
+}
+
 // =====================================================================================================
 // Persistent pipelined variant: one work item = all 256 queries of one (sample, head) against NK keys.
 //
@@ -490,6 +540,8 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_consta
       }
       mbar_wait(&s_full[t], par);
       tc_fence_after();
+      // (measured: keeping the row in registers / double-buffering the TMEM loads is SLOWER here - 141 vs 117 us for
+      // the self-attention shape; this kernel is bound by the per-thread exp chain, not by TMEM latency)
       float mx = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < NK / 32; ++c) {
@@ -791,14 +843,16 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
         }
         mbar_wait(&s_full[t], nb & 1);
         tc_fence_after();
+        // the whole 128-score row of this thread stays in registers: ONE TMEM read pass (four loads in flight, one
+        // wait), maximum and exponentials from registers, P written back over the consumed S columns
+        uint32_t v[kFlashKB / 32][32];
+#pragma unroll
+        for (int c = 0; c < kFlashKB / 32; ++c) tmem_ld_32x32(t_row + c * 32, v[c]);
+        tmem_ld_wait();
         float mx = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < kFlashKB / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(t_row + c * 32, v);
-          tmem_ld_wait();
-          mx = softmax_chunk_max<HAS_BIAS>(v, mx, p.scale_log2e, bias_a + c * 128);
-        }
+#pragma unroll
+        for (int c = 0; c < kFlashKB / 32; ++c)
+          mx = softmax_chunk_prep<HAS_BIAS>(v[c], mx, p.scale_log2e, bias_a + c * 128);
         if constexpr (!HAS_BIAS) mx *= p.scale_log2e;
         // lazy rescale: move the reference maximum only when the block maximum exceeds it by > 8 (log2 units).
         // tcgen05.ld/st are warp-collective (.sync.aligned): the TMEM round trip runs for the whole warp as soon as
@@ -821,13 +875,10 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
         if (need) m_used = mx;
         const float m_eff = m_used == -INFINITY ? 0.f : m_used;  // a fully masked prefix must not produce NaN
         uint64_t sum2 = pack_f2(0.f, 0.f);
-#pragma unroll 1
+#pragma unroll
         for (int c = 0; c < kFlashKB / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(t_row + c * 32, v);
-          tmem_ld_wait();
           uint32_t pk[16];
-          softmax_chunk_exp<HAS_BIAS>(v, pk, sum2, m_eff, p.scale_log2e, bias_a + c * 128);
+          softmax_chunk_exp_reg<HAS_BIAS>(v[c], pk, sum2, m_eff, p.scale_log2e);
           tmem_st_32x16(t_row + c * 16, pk);
         }
         {

@@ -116,6 +116,17 @@ class FluxShape:
         single = [3 * S * D * D, 4 * S * D * D, 5 * S * D * D]
         return np.array([full] * self.num_blocks + [single] * self.num_single_blocks, dtype=np.int64)
 
+    def flops_components(self) -> np.ndarray:
+        """Algorithmic FLOPs per sample = 2 * MACs + the SDPA matmuls (2 * S^2 * D MACs per joint attention), the
+        convention SURVEY.md section 8d uses for every roofline figure."""
+        S, D = self.tokens + self.text_tokens, self.dim
+        f = 2 * self.macs_components()
+        f[:, 0] += 4 * S * S * D
+        return f
+
+    def flops_always(self) -> int:
+        return 2 * self.macs_always()
+
     def macs_always(self) -> int:
         """Modulation linears that run even when every component is reused + the embedders / output head."""
         N, T, D = self.tokens, self.text_tokens, self.dim

@@ -40,3 +40,30 @@ for name, S, nq, nk, bias in [("c2 self", 200, 256, 256, False), ("c2 cross", 20
     fl = 4.0 * S * H * nq * nk * 72
     print(f"{name:9s} S={S:3d} Nq={nq:4d} Nk={nk:4d}: {ms*1e3:8.1f} us  {fl/ms/1e9:7.1f} TFLOP/s (real d=72)  "
           f"{fl/ms/1e9*80/72:7.1f} incl. padding")
+
+# FLUX joint attention (head_dim 128): config 5 shape and the 256x256 shape
+for name, S, Hh, n in [("c5 joint", 4, 24, 4608), ("flux256", 16, 24, 768)]:
+    g = torch.Generator(device="cuda").manual_seed(0)
+    q, k, v = (torch.randn(S, Hh, n, 128, device="cuda", generator=g).to(torch.bfloat16) for _ in range(3))
+    out = torch.empty(S, n, Hh * 128, device="cuda", dtype=torch.bfloat16)
+    lib = _lib.load()
+
+    def run():
+        _lib.check(lib.ecadk_attention_d128(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), Hh * 128, None, 0,
+                                            S, Hh, n, n, _lib.stream_ptr()), "attention_d128")
+
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            run()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(e) / 3)
+    ms = statistics.mean(ts)
+    fl = 4.0 * S * Hh * n * n * 128
+    print(f"{name:9s} S={S:3d} N={n:4d} d=128: {ms*1e3:8.1f} us  {fl/ms/1e9:7.1f} TFLOP/s")
