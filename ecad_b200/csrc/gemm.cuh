@@ -416,15 +416,18 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer (both CTAs) =====================
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int m0 = (tile / num_n) * (2 * kGemmBM) + cta * kGemmBM;
-        const int n_idx = tile % num_n;
-        const bool is_tail = n_idx >= num_n_full;
-        const int bn_cur = is_tail ? tail : BN;
+    // ===================== TMA producer (both CTAs) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int m0 = (tile / num_n) * (2 * kGemmBM) + cta * kGemmBM;
+      const int n_idx = tile % num_n;
+      const bool is_tail = n_idx >= num_n_full;
+      const int bn_cur = is_tail ? tail : BN;
+      // (measured: an L2 bulk prefetch of this tile's residual-stream block issued here does NOT help - out-projection
+      // 197 -> 202 us, FF2 427 -> 488 us: the epilogue is not exposed-latency-bound and the prefetch competes with the
+      // operand stream for L2)
+      if (lane == 0) {
         const int n0 = n_idx * BN + cta * (bn_cur / 2);
         const CUtensorMap* tb = is_tail ? &tmap_b_tail : &tmap_b;
         const uint32_t stage_bytes = 2 * (Cfg::kStageA + (bn_cur / 2) * kGemmBK * 2);
@@ -441,8 +444,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           }
         }
       }
+      __syncwarp();  // lanes 1..31 must not run ahead: the prefetch distance stays one tile
     }
-    __syncwarp();
   } else if (warp == 1) {
     if (lane == 0 && cta == 0) {
       // ===================== MMA issuer (leader CTA only) =====================

@@ -73,6 +73,11 @@ __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const void* tma
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
       : "memory");
 }
+// asynchronous prefetch of `bytes` (multiple of 16, 16-byte aligned) of global memory into L2
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, uint64_t* bar, int32_t c0, int32_t c1,
                                             int32_t c2) {
   asm volatile(

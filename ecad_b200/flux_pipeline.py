@@ -71,7 +71,11 @@ def latent_image_ids(batch: int, h2: int, w2: int) -> torch.Tensor:
 class B200FluxPipeline:
     vae_scale_factor = 16  # FluxPipeline: 2 ** len(vae.config.block_out_channels) for the FLUX VAE
 
-    def __init__(self, transformer, scheduler: FlowMatchEulerDiscrete | None = None):
+    def __init__(self, transformer, scheduler: FlowMatchEulerDiscrete | None = None, use_cuda_graph: bool = False):
+        from .graphs import GenerationGraphs
+
+        self.use_cuda_graph = use_cuda_graph
+        self._graphs = GenerationGraphs()
         self.transformer = transformer
         self.scheduler = scheduler if scheduler is not None else FlowMatchEulerDiscrete()
         self.device = transformer.device
@@ -86,6 +90,28 @@ class B200FluxPipeline:
         latents = torch.randn((batch_size, num_channels_latents, h, w), generator=generator, device=gen_dev,
                               dtype=torch.float32)
         return pack_latents(latents).to(self.device).contiguous(), ids
+
+    def _denoise(self, inp: dict[str, torch.Tensor], text_ids, img_ids, callback_on_step_end) -> torch.Tensor:
+        """The loop of FluxPipeline.__call__; all tensors already on the device (recordable into one CUDA graph)."""
+        tr, sched = self.transformer, self.scheduler
+        latents, prompt_embeds = inp["latents"], inp["prompt_embeds"]
+        batch_size = latents.shape[0]
+        lib = _lib.load()
+        sched.step_index = 0
+        for i, t in enumerate(sched.timesteps):
+            timestep = inp["timesteps"][i:i + 1].expand(batch_size)
+            noise_pred = tr(hidden_states=latents, timestep=timestep, guidance=inp["guidance"],
+                            pooled_projections=inp["pooled_prompt_embeds"], encoder_hidden_states=prompt_embeds,
+                            txt_ids=text_ids, img_ids=img_ids, joint_attention_kwargs=None, return_dict=False)[0]
+            _lib.check(lib.ecadk_axpy_f32(latents.data_ptr(), noise_pred.data_ptr(), sched.step_coefficient(),
+                                          latents.numel(), _lib.stream_ptr()), "euler_step")
+            tr.launches += 1
+            sched.advance()
+            if callback_on_step_end is not None:
+                out = callback_on_step_end(self, i, t, {"latents": latents, "prompt_embeds": prompt_embeds})
+                latents = out.pop("latents", latents)
+                prompt_embeds = out.pop("prompt_embeds", prompt_embeds)
+        return latents
 
     @torch.no_grad()
     def __call__(
@@ -105,6 +131,7 @@ class B200FluxPipeline:
         callback_on_step_end_tensor_inputs: list[str] | None = None,
         output_type: str = "latent",
         return_dict: bool = False,
+        capture_callback: Callable[..., dict[str, torch.Tensor]] | None = None,
         **kwargs: Any,
     ):
         if prompt is not None or prompt_2 is not None:
@@ -125,21 +152,21 @@ class B200FluxPipeline:
         sched.set_timesteps(num_inference_steps, device=dev, mu=calculate_shift(n_tokens))
         guidance = torch.full((batch_size,), float(guidance_scale), dtype=torch.float32, device=dev) \
             if tr.config.guidance_embeds else None
-        lib = _lib.load()
-        for i, t in enumerate(sched.timesteps):
-            timestep = t.expand(batch_size).to(dev)
-            noise_pred = tr(hidden_states=latents, timestep=timestep / 1000, guidance=guidance,
-                            pooled_projections=pooled_prompt_embeds, encoder_hidden_states=prompt_embeds,
-                            txt_ids=text_ids, img_ids=img_ids, joint_attention_kwargs=None, return_dict=False)[0]
-            _lib.check(lib.ecadk_axpy_f32(latents.data_ptr(), noise_pred.data_ptr(), sched.step_coefficient(),
-                                          latents.numel(), _lib.stream_ptr()), "euler_step")
-            tr.launches += 1
-            sched.advance()
+        inputs = {"latents": latents.contiguous(), "prompt_embeds": prompt_embeds,
+                  "pooled_prompt_embeds": pooled_prompt_embeds, "guidance": guidance,
+                  "timesteps": (sched.timesteps / 1000).to(dev)}
+        if self.use_cuda_graph:
+            key = ("flux", id(tr.cache_schedule), getattr(tr.cache_schedule, "name", None), tuple(latents.shape),
+                   tuple(prompt_embeds.shape), num_inference_steps, float(guidance_scale))
+            latents = self._graphs.run(
+                key, inputs, lambda st, cb: self._denoise(st, text_ids, img_ids, cb),
+                capture_callback if capture_callback is not None else callback_on_step_end, tr)
             if callback_on_step_end is not None:
-                cb_kwargs = {"latents": latents, "prompt_embeds": prompt_embeds}
-                out = callback_on_step_end(self, i, t, cb_kwargs)
-                latents = out.pop("latents", latents)
-                prompt_embeds = out.pop("prompt_embeds", prompt_embeds)
+                for i, t in enumerate(sched.timesteps):
+                    out = callback_on_step_end(self, i, t, {"latents": latents, "prompt_embeds": prompt_embeds})
+                    latents = out.pop("latents", latents)
+        else:
+            latents = self._denoise(inputs, text_ids, img_ids, callback_on_step_end)
         if not return_dict:
             return (latents,)
         return {"images": latents}

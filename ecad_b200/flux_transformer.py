@@ -334,7 +334,7 @@ class B200FluxTransformer2D:
 
         # time_text_embed (:277-286): timestep (+ guidance) sinusoid MLPs + pooled-text MLP, summed
         def scalar_embed(values, name, accumulate):
-            v = (values.to(device=dev, dtype=torch.float32).reshape(-1) * 1000.0).contiguous()
+            v = (values.to(device=dev, dtype=torch.float32) * 1000.0).reshape(-1).contiguous()
             if v.numel() != B:
                 raise ValueError(f"{name} has {v.numel()} entries for a batch of {B}")
             _lib.check(lib.ecadk_timestep_sinusoid(v.data_ptr(), ws["t_proj"].data_ptr(), B, 256, st), "sinusoid")
@@ -379,7 +379,9 @@ class B200FluxTransformer2D:
         ws["x_txt"].copy_(ws["x_txt0"])
 
         # pos_embed (:290-291): rotation tables of the joint [text; image] sequence, shared by the batch
-        rope_key = (img_ids.data_ptr(), tuple(img_ids.shape), txt_ids.data_ptr(), tuple(txt_ids.shape))
+        # host ids (our pipeline) are identified by content, device ids (diffusers' pipeline) by address
+        rope_key = tuple((tuple(t.shape), t.data_ptr() if t.is_cuda else hash(t.numpy().tobytes()))
+                         for t in (img_ids, txt_ids))
         if self._rope_key != rope_key:
             ii, ti = img_ids, txt_ids
             if ii.ndim == 3:

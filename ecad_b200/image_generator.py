@@ -36,11 +36,15 @@ class B200PixArtImageGenerator:
         weight_seed: int = 0,
         device: str = "cuda:0",
         cache_schedule: PixArtCacheSchedule | None = None,
+        use_cuda_graph: bool = False,
     ):
         if not torch.cuda.is_available():
             # pixart_image_generator.py:55-56
             raise ValueError("CUDA is not available.")
         self.device = device
+        # one CUDA graph per (schedule, shape) replays a whole generation with a single launch (ecad_b200/graphs.py);
+        # in that mode the additional callbacks see the FINAL latents at every step
+        self.use_cuda_graph = use_cuda_graph
         self.start_seed = start_seed
         self.seed_step = seed_step
         self.additional_callbacks = list(additional_callbacks or [])
@@ -106,12 +110,19 @@ class B200PixArtImageGenerator:
     def _call_callbacks_wrapper(self, step: int, timestep: Any, latents: torch.Tensor) -> None:
         self._call_callbacks(step, timestep, latents=latents)
 
+    def _call_core_callbacks(self, step: int, timestep: Any, latents: torch.Tensor | None = None) -> None:
+        """Step counters + reset only (what a graph capture pass needs; never touches device memory)."""
+        self.dit_scheduler.per_step_callback(step, timestep)
+        self.cache_schedule.per_step_callback(step, timestep)
+        self._reset_schedules_callback(step, timestep)
+
     # pixart_image_generator.py:128-150
     def create_diffusion_pipeline(self) -> B200PixArtPipeline:
         if self.diffusion_pipeline is None:
             tr = B200PixArtTransformer2D(self._state_dict, self.model_config, self.dit_scheduler, self.cache_schedule,
                                          self.device)
-            self.diffusion_pipeline = B200PixArtPipeline(tr, gate_step=self.gate_step)
+            self.diffusion_pipeline = B200PixArtPipeline(tr, gate_step=self.gate_step,
+                                                         use_cuda_graph=self.use_cuda_graph)
         return self.diffusion_pipeline
 
     # pixart_image_generator.py:314-393 (returns latents [images_per_prompt][B,4,h,w] instead of PIL images)
@@ -132,6 +143,7 @@ class B200PixArtImageGenerator:
                 generator=self.random_generator, return_dict=False, guidance_scale=4.5,
                 height=height or self.height, width=width or self.width,
                 callback=self._call_callbacks_wrapper, callback_steps=1,
+                capture_callback=self._call_core_callbacks,
             )[0]
             out.append(lat.clone())
         return out
@@ -168,8 +180,11 @@ class B200FluxImageGenerator:
     def __init__(self, schedule_path: Path | str | None = None, start_seed: int = 0, seed_step: int = 1,
                  additional_callbacks: list[Callable[..., None]] | None = None,
                  state_dict: dict[str, torch.Tensor] | None = None, model_config=None, weight_seed: int = 0,
-                 device: str = "cuda:0", cache_schedule=None, weights_on_device: bool = False):
+                 device: str = "cuda:0", cache_schedule=None, weights_on_device: bool = False,
+                 use_cuda_graph: bool = False):
         from .weights import FluxConfig
+
+        self.use_cuda_graph = use_cuda_graph
 
         if not torch.cuda.is_available():
             # flux_image_generator.py:45-46
@@ -243,6 +258,12 @@ class B200FluxImageGenerator:
         self._call_callbacks(step, timestep)
         return {"latents": callback_kwargs["latents"], "prompt_embeds": callback_kwargs["prompt_embeds"]}
 
+    def _call_core_callbacks(self, _pipeline, step: int, timestep: Any, callback_kwargs: dict[str, Any]):
+        self.dit_scheduler.per_step_callback(step, timestep)
+        self.cache_schedule.per_step_callback(step, timestep)
+        self._reset_schedules_callback(step, timestep)
+        return callback_kwargs
+
     def create_diffusion_pipeline(self, skip_transformer_block_init: bool = False):
         from .flux_pipeline import B200FluxPipeline
         from .flux_transformer import B200FluxTransformer2D
@@ -254,7 +275,7 @@ class B200FluxImageGenerator:
             else:
                 tr = B200FluxTransformer2D(self._state_dict, self.model_config, self.dit_scheduler, self.cache_schedule,
                                            self.device)
-            self.diffusion_pipeline = B200FluxPipeline(tr)
+            self.diffusion_pipeline = B200FluxPipeline(tr, use_cuda_graph=self.use_cuda_graph)
         return self.diffusion_pipeline
 
     # flux_image_generator.py:285-363 (returns packed latents [images_per_prompt][B, N, 64] instead of PIL images)
@@ -274,6 +295,7 @@ class B200FluxImageGenerator:
                 guidance_scale=guidance_scale or self.guidance_scale,
                 callback_on_step_end=self._call_callbacks_wrapper,
                 callback_on_step_end_tensor_inputs=["latents", "prompt_embeds"],
+                capture_callback=self._call_core_callbacks,
             )[0]
             out.append(lat.clone())
         return out

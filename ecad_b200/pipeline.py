@@ -92,7 +92,13 @@ class B200PixArtPipeline:
     ``gate_step`` enables the TGATE loop variant (ecad/pipelines/tgate.py:329-341,382-389).
     """
 
-    def __init__(self, transformer, scheduler: DPMSolverPP2M | None = None, gate_step: int | None = None):
+    def __init__(self, transformer, scheduler: DPMSolverPP2M | None = None, gate_step: int | None = None,
+                 use_cuda_graph: bool = False):
+        from .graphs import GenerationGraphs
+
+        self.use_cuda_graph = use_cuda_graph
+        self._graphs = GenerationGraphs()
+        self._ts_cache = None
         self.transformer = transformer
         self.scheduler = scheduler if scheduler is not None else DPMSolverPP2M()
         self.gate_step = gate_step
@@ -107,6 +113,55 @@ class B200PixArtPipeline:
             latents = torch.randn(shape, generator=generator, device=gen_dev, dtype=torch.float32)
         latents = latents.to(device=device, dtype=torch.float32)
         return latents * self.scheduler.init_noise_sigma
+
+    def _denoise(self, inp: dict[str, torch.Tensor], batch_size: int, do_cfg: bool, guidance_scale: float, height: int,
+                 width: int, callback, callback_steps: int) -> torch.Tensor:
+        """The denoising loop proper (pass_through.py:296-380); every tensor it touches is already on the device, so
+        the whole loop can be recorded into one CUDA graph."""
+        tr, sched, dev = self.transformer, self.scheduler, self.device
+        cfgm = tr.config
+        latents, embeds, mask = inp["latents"], inp["embeds"], inp["mask"]
+        negative_prompt_embeds = inp["negative_prompt_embeds"]
+        negative_prompt_attention_mask = inp["negative_prompt_attention_mask"]
+        sched.step_index, sched.lower_order_nums = 0, 0
+        latent_channels = cfgm.in_channels
+        x0_prev = torch.zeros_like(latents)
+        added_cond_kwargs = {"resolution": inp.get("resolution"), "aspect_ratio": inp.get("aspect_ratio")}
+        lib = _lib.load()
+        hw = latents.shape[-2] * latents.shape[-1]
+        timesteps = sched.timesteps
+        timesteps_dev = self._timesteps_on_device(timesteps)
+        for i, t in enumerate(timesteps):
+            gated = self.gate_step is not None and i >= self.gate_step
+            cond_in = added_cond_kwargs
+            if gated:
+                model_in, e_in, m_in = latents, negative_prompt_embeds, negative_prompt_attention_mask
+                cond_in = {k: (v[:batch_size] if v is not None else None) for k, v in added_cond_kwargs.items()}
+            else:
+                model_in = torch.cat([latents] * 2) if do_cfg else latents
+                e_in, m_in = embeds, mask
+            model_in = sched.scale_model_input(model_in, t)
+            current_timestep = timesteps_dev[i:i + 1].expand(model_in.shape[0])
+            noise_pred = tr(model_in, encoder_hidden_states=e_in, encoder_attention_mask=m_in,
+                            timestep=current_timestep, added_cond_kwargs=cond_in, return_dict=False)[0]
+            c = sched.coefficients()
+            _lib.check(
+                lib.ecadk_cfg_dpm_step(noise_pred.data_ptr(), latents.data_ptr(), x0_prev.data_ptr(), batch_size,
+                                       latent_channels, hw, int(do_cfg and not gated), float(guidance_scale),
+                                       c["sigma_s"], c["alpha_s"], c["c_x"], c["c_d0"], c["c_d1"],
+                                       _lib.stream_ptr()),
+                "cfg_dpm_step")
+            tr.launches += 1
+            sched.advance()
+            if callback is not None and i % callback_steps == 0:
+                callback(i // getattr(sched, "order", 1), t, latents)
+        return latents
+
+    def _timesteps_on_device(self, timesteps: torch.Tensor) -> torch.Tensor:
+        key = tuple(int(t) for t in timesteps)
+        if self._ts_cache is None or self._ts_cache[0] != key:
+            self._ts_cache = (key, timesteps.to(self.device))
+        return self._ts_cache[1]
 
     @torch.no_grad()
     def __call__(
@@ -128,6 +183,7 @@ class B200PixArtPipeline:
         callback_steps: int = 1,
         output_type: str = "latent",
         return_dict: bool = False,
+        capture_callback: Callable[[int, Any, torch.Tensor], None] | None = None,
         **kwargs: Any,
     ):
         if prompt is not None or negative_prompt is not None:
@@ -157,12 +213,14 @@ class B200PixArtPipeline:
 
         sched = self.scheduler
         sched.set_timesteps(num_inference_steps, device=dev)
-        timesteps = sched.timesteps
         latent_channels = cfgm.in_channels
         latents = self.prepare_latents(batch_size, latent_channels, height, width, torch.float32, dev, generator,
                                        latents).contiguous()
-        x0_prev = torch.zeros_like(latents)
-        added_cond_kwargs = {"resolution": None, "aspect_ratio": None}
+        if cfgm.out_channels // 2 != latent_channels:
+            raise NotImplementedError("only learned-sigma PixArt heads (out_channels = 2*in_channels) are supported")
+        inputs = {"latents": latents, "embeds": embeds, "mask": mask, "negative_prompt_embeds": negative_prompt_embeds,
+                  "negative_prompt_attention_mask": negative_prompt_attention_mask, "resolution": None,
+                  "aspect_ratio": None}
         if cfgm.sample_size == 128 and getattr(tr.cfg, "resolved_additional_conditions", False):
             # 6.1 micro-conditions of the 1024-MS checkpoints (pass_through.py:268-290)
             resolution = torch.tensor([float(height), float(width)]).repeat(batch_size, 1)
@@ -170,37 +228,19 @@ class B200PixArtPipeline:
             if do_cfg:
                 resolution = torch.cat([resolution, resolution], dim=0)
                 aspect_ratio = torch.cat([aspect_ratio, aspect_ratio], dim=0)
-            added_cond_kwargs = {"resolution": resolution.to(dev), "aspect_ratio": aspect_ratio.to(dev)}
-        lib = _lib.load()
-        hw = latents.shape[-2] * latents.shape[-1]
-        learned_sigma = cfgm.out_channels // 2 == latent_channels
-        if not learned_sigma:
-            raise NotImplementedError("only learned-sigma PixArt heads (out_channels = 2*in_channels) are supported")
-
-        for i, t in enumerate(timesteps):
-            gated = self.gate_step is not None and i >= self.gate_step
-            cond_in = added_cond_kwargs
-            if gated:
-                model_in, e_in, m_in = latents, negative_prompt_embeds, negative_prompt_attention_mask
-                cond_in = {k: (v[:batch_size] if v is not None else None) for k, v in added_cond_kwargs.items()}
-            else:
-                model_in = torch.cat([latents] * 2) if do_cfg else latents
-                e_in, m_in = embeds, mask
-            model_in = sched.scale_model_input(model_in, t)
-            current_timestep = t[None].to(dev).expand(model_in.shape[0])
-            noise_pred = tr(model_in, encoder_hidden_states=e_in, encoder_attention_mask=m_in,
-                            timestep=current_timestep, added_cond_kwargs=cond_in, return_dict=False)[0]
-            c = sched.coefficients()
-            _lib.check(
-                lib.ecadk_cfg_dpm_step(noise_pred.data_ptr(), latents.data_ptr(), x0_prev.data_ptr(), batch_size,
-                                       latent_channels, hw, int(do_cfg and not gated), float(guidance_scale),
-                                       c["sigma_s"], c["alpha_s"], c["c_x"], c["c_d0"], c["c_d1"],
-                                       _lib.stream_ptr()),
-                "cfg_dpm_step")
-            tr.launches += 1
-            sched.advance()
-            if callback is not None and i % callback_steps == 0:
-                callback(i // getattr(sched, "order", 1), t, latents)
+            inputs["resolution"], inputs["aspect_ratio"] = resolution.to(dev), aspect_ratio.to(dev)
+        if self.use_cuda_graph:
+            key = ("pixart", id(tr.cache_schedule), getattr(tr.cache_schedule, "name", None), tuple(latents.shape),
+                   tuple(embeds.shape), num_inference_steps, float(guidance_scale), self.gate_step, height, width)
+            latents = self._graphs.run(
+                key, inputs, lambda st, cb: self._denoise(st, batch_size, do_cfg, guidance_scale, height, width, cb, 1),
+                capture_callback if capture_callback is not None else callback, tr)
+            if callback is not None:  # user-visible per-step protocol (counters, extra callbacks, reset LAST)
+                for i, t in enumerate(sched.timesteps):
+                    if i % callback_steps == 0:
+                        callback(i // getattr(sched, "order", 1), t, latents)
+        else:
+            latents = self._denoise(inputs, batch_size, do_cfg, guidance_scale, height, width, callback, callback_steps)
         if not return_dict:
             return (latents,)
         return {"images": latents}

@@ -16,7 +16,8 @@ from ecad_b200.weights import synthetic_prompt_embeddings  # noqa: E402
 rows = load_packed_schedules(ROOT / "tests" / "golden" / "pixart_schedules.json.gz")
 row = [r for r in rows if r["path"] == "schedules_in_paper/pixart_alpha_256/ours_fast.json"][0]
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 1
-gen = B200PixArtAlphaImageGenerator(cache_schedule=schedule_from_packed(row))
+graph = len(sys.argv) > 2 and sys.argv[2] == "graph"
+gen = B200PixArtAlphaImageGenerator(cache_schedule=schedule_from_packed(row), use_cuda_graph=graph)
 emb = {k: v.cuda() for k, v in synthetic_prompt_embeddings(batch).items()}
 import contextlib
 import io
@@ -35,5 +36,5 @@ with contextlib.redirect_stdout(io.StringIO()):
         torch.cuda.synchronize()
         times.append(a.elapsed_time(b))
 launches = (gen.diffusion_pipeline.transformer.launches - l0) / 5
-print(json.dumps({"config": "c1", "batch": batch, "ms_per_generation": statistics.mean(times),
+print(json.dumps({"config": "c1", "batch": batch, "cuda_graph": graph, "ms_per_generation": statistics.mean(times),
                   "ms_per_image": statistics.mean(times) / batch, "launches_per_generation": launches}))
