@@ -165,12 +165,13 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not _LIB_PATH.exists():
+    path = Path(os.environ.get("ECAD_B200_LIB", _LIB_PATH))  # instrumented / A-B builds of the same ABI
+    if not path.exists():
         raise RuntimeError(
-            f"{_LIB_PATH} is missing - build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"{path} is missing - build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(there is no CPU or PyTorch fallback for the ECAD B200 hot path)"
         )
-    lib = C.CDLL(os.fspath(_LIB_PATH))
+    lib = C.CDLL(os.fspath(path))
     lib.ecadk_abi_version.restype = C.c_int
     lib.ecadk_last_error.restype = C.c_char_p
     i, f, p, sz = C.c_int, C.c_float, C.c_void_p, C.c_size_t

@@ -35,6 +35,16 @@ struct AttnParams {
   int split_tokens;
 };
 
+// Phase timing of the flash kernel (instrumented builds only: -DECADK_ATTN_TIMING; tools/micro/attn_phase_timing.py)
+#ifdef ECADK_ATTN_TIMING
+__device__ unsigned int g_attn_dbg[148 * 32];
+#define ATTN_T(var) const unsigned int var = clock()
+#define ATTN_ACC(slot, a, b) dbg_acc[slot] += (b) - (a)
+#else
+#define ATTN_T(var)
+#define ATTN_ACC(slot, a, b)
+#endif
+
 template <int NK>
 struct AttnCfg {
   // shared-memory map (bytes); every chunk base is a multiple of 1024
@@ -436,8 +446,11 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_consta
         mbar_wait(&v_empty[vb], ((n >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&v_full[vb], Cfg::kBytesV);
         uint8_t* vdst = smem + Cfg::kV + vb * Cfg::kVBuf;
-        tma_load_2d(vdst, &tm_v64, &v_full[vb], 0, k_row);
-        tma_load_2d(vdst + NK * 128, &tm_v16, &v_full[vb], 64, k_row);
+        // V lands as FIVE 16-column (32-byte-swizzled) atoms so that the whole 80-column head is one MN-major operand:
+        // P V is ONE N = 80 instruction per 16-key step instead of an N = 64 plus an N = 16 one, and a narrow
+        // tcgen05.mma costs about as much as a wide one (measured with ECADK_ATTN_TIMING)
+#pragma unroll
+        for (int a = 0; a < kHeadPad / 16; ++a) tma_load_2d(vdst + a * (NK * 32), &tm_v16, &v_full[vb], a * 16, k_row);
       }
     }
     __syncwarp();
@@ -445,8 +458,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_consta
     if (lane == 0) {
       // ===================== MMA issuer =====================
       constexpr uint32_t idesc_s = make_idesc_bf16(kAttnBM, NK);
-      constexpr uint32_t idesc_o64 = make_idesc_bf16(kAttnBM, 64, 0, 1);
-      constexpr uint32_t idesc_o16 = make_idesc_bf16(kAttnBM, 16, 0, 1);
+      constexpr uint32_t idesc_o80 = make_idesc_bf16(kAttnBM, kHeadPad, 0, 1);
       const uint32_t sbase = smem_u32(smem);
       // Issue order is software-pipelined so that the two query tiles run in anti-phase: while tile 0's warps are in
       // softmax(i), the tensor core serves tile 1's PV(i-1) and QK^T(i), and vice versa.  Each tile's chain
@@ -468,10 +480,8 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_consta
         const uint32_t o_tmem = tmem + 256 * t + 128;
 #pragma unroll
         for (int ks = 0; ks < NK / 16; ++ks) {
-          const uint64_t dv64 = make_smem_desc(vbase + ks * 16 * 128, NK * 128, 1024, kLayoutSW128);
-          const uint64_t dv16 = make_smem_desc(vbase + NK * 128 + ks * 16 * 32, NK * 32, 256, kLayoutSW32);
-          umma_bf16_ts(o_tmem, p_tmem + ks * 8, dv64, idesc_o64, ks != 0);
-          umma_bf16_ts(o_tmem + 64, p_tmem + ks * 8, dv16, idesc_o16, ks != 0);
+          const uint64_t dv = make_smem_desc(vbase + ks * 16 * 32, NK * 32, 256, kLayoutSW32);
+          umma_bf16_ts(o_tmem, p_tmem + ks * 8, dv, idesc_o80, ks != 0);
         }
         umma_commit(&o_full[t]);
       };
@@ -630,6 +640,11 @@ namespace ecadk {
 // than 8 (log2 units), so P entries stay <= 2^8 and the TMEM round trip  O *= 2^(m_old - m_new)  is rare.
 // =====================================================================================================
 constexpr int kFlashKB = 128;  // keys per block
+// warp 0 TMA, warp 1 MMA, warps 2..17 softmax: EIGHT warps per query tile - every score row is shared by two threads
+// (the two warps that own the same TMEM lane quarter), each taking 64 of the 128 keys of a block.  A tile's softmax is
+// a serial chain per thread (~17 clk per exponential per warp), and the chain - not MUFU throughput - bounds the kernel:
+// halving the per-thread row halves the chain.
+constexpr int kFlashThreads = 576;
 
 // HD = real head dim: 72 (PixArt; stored padded to 80 = 64 + 16 columns) or 128 (FLUX; 64 + 64 columns).  The head is
 // always staged as a 64-column 128B-swizzled chunk plus a second chunk of kC2 columns (32B- or 128B-swizzled).
@@ -645,8 +660,9 @@ struct AttnFlashCfg {
   static constexpr int kKStage = kFlashKB * (128 + kRow2);
   static constexpr int kK = kQ2 + 256 * kRow2;        // 2 stages
   static constexpr int kV = kK + 2 * kKStage;         // 2 stages
-  static constexpr int kBias = kV + 2 * kKStage;      // 8 warps x 128 floats
-  static constexpr int kBars = kBias + 8 * kFlashKB * 4;
+  static constexpr int kBias = kV + 2 * kKStage;      // 16 warps x 64 floats
+  static constexpr int kXch = kBias + 8 * kFlashKB * 4;  // row-maximum exchange [2 buffers][16 warps][32] + row-sum [16][32]
+  static constexpr int kBars = kXch + 3 * 16 * 32 * 4;
   static constexpr int kSmemBytes = kBars + 256 + 1024;
   static constexpr uint32_t kBytesQ = 256 * kPad * 2;
   static constexpr uint32_t kBytesKV = kFlashKB * kPad * 2;
@@ -655,8 +671,12 @@ struct AttnFlashCfg {
                 "attn_flash_kernel must be alone on its SM (it owns all 512 TMEM columns) and fit in shared memory");
 };
 
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
 template <int HD, bool HAS_BIAS>
-__global__ void __launch_bounds__(kAttnPairThreads, 1)
+__global__ void __launch_bounds__(kFlashThreads, 1)
 attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_constant__ CUtensorMap tm_q16,
                   const __grid_constant__ CUtensorMap tm_k64, const __grid_constant__ CUtensorMap tm_k16,
                   const __grid_constant__ CUtensorMap tm_v64, const __grid_constant__ CUtensorMap tm_v16,
@@ -691,9 +711,9 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);
+      mbar_init(&p_full[i], 8);
       mbar_init(&o_full[i], 1);
-      mbar_init(&s_empty[i], 4);
+      mbar_init(&s_empty[i], 8);
     }
     fence_barrier_init();
   }
@@ -729,8 +749,14 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
           tma_load_2d(kd + kFlashKB * 128, &tm_k16, &k_full[st], 64, k_row);
           mbar_wait(&v_empty[st], ph);
           mbar_arrive_expect_tx(&v_full[st], Cfg::kBytesKV);
-          tma_load_2d(vd, &tm_v64, &v_full[st], 0, k_row);
-          tma_load_2d(vd + kFlashKB * 128, &tm_v16, &v_full[st], 64, k_row);
+          if constexpr (HD == 128) {
+            tma_load_2d(vd, &tm_v64, &v_full[st], 0, k_row);
+            tma_load_2d(vd + kFlashKB * 128, &tm_v16, &v_full[st], 64, k_row);
+          } else {  // five 16-column SW32 atoms: the 80-column head is one MN-major operand (see attn_pair_kernel)
+#pragma unroll
+            for (int a = 0; a < Cfg::kPad / 16; ++a)
+              tma_load_2d(vd + a * (kFlashKB * 32), &tm_v16, &v_full[st], a * 16, k_row);
+          }
         }
       }
     }
@@ -739,8 +765,8 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
     if (lane == 0) {
       // ===================== MMA issuer =====================
       constexpr uint32_t idesc_s = make_idesc_bf16(kAttnBM, kFlashKB);
-      constexpr uint32_t idesc_o64 = make_idesc_bf16(kAttnBM, 64, 0, 1);
-      constexpr uint32_t idesc_o2 = make_idesc_bf16(kAttnBM, Cfg::kC2, 0, 1);
+      constexpr uint32_t idesc_o80 = make_idesc_bf16(kAttnBM, 80, 0, 1);
+      constexpr uint32_t idesc_o128 = make_idesc_bf16(kAttnBM, 128, 0, 1);
       const uint32_t sbase = smem_u32(smem);
       auto issue_qk = [&](int t, int st) {
         const uint32_t d = tmem + 256 * t;
@@ -762,11 +788,15 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
 #pragma unroll
         for (int ks = 0; ks < kFlashKB / 16; ++ks) {
           const uint64_t dv64 = make_smem_desc(vb + ks * 16 * 128, kFlashKB * 128, 1024, kLayoutSW128);
-          const uint64_t dv2 = make_smem_desc(vb + kFlashKB * 128 + ks * 16 * Cfg::kRow2, kFlashKB * Cfg::kRow2,
-                                              Cfg::kSBO2, Cfg::kLayout2);
           const uint32_t acc = (accumulate || ks != 0) ? 1u : 0u;
-          umma_bf16_ts(o_tmem, p_tmem + ks * 8, dv64, idesc_o64, acc);
-          umma_bf16_ts(o_tmem + 64, p_tmem + ks * 8, dv2, idesc_o2, acc);
+          if constexpr (HD == 128) {
+            // both 64-column swizzle atoms of V in ONE N = 128 instruction (LBO = atom stride along the head dim):
+            // two N = 64 instructions cost about as much as two N = 128 ones (measured with ECADK_ATTN_TIMING)
+            umma_bf16_ts(o_tmem, p_tmem + ks * 8, dv64, idesc_o128, acc);
+          } else {
+            const uint64_t dv = make_smem_desc(vb + ks * 16 * 32, kFlashKB * 32, 256, kLayoutSW32);
+            umma_bf16_ts(o_tmem, p_tmem + ks * 8, dv, idesc_o80, acc);
+          }
         }
       };
       // tile 1's PV of block nb-1 is deferred by one block so the two tiles run in anti-phase
@@ -783,25 +813,42 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
         pend = false;
       };
       int n = 0, nb = 0;
+#ifdef ECADK_ATTN_TIMING
+      unsigned int dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      const unsigned int t_begin = clock();
+#endif
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++n) {
         mbar_wait(q_full, n & 1);
         for (int j = 0; j < nkb; ++j, ++nb) {
           const int st = nb & 1;
           const uint32_t ring_ph = (nb >> 1) & 1;
           const uint32_t blk_par = nb & 1;
+          ATTN_T(m0);
           mbar_wait(&k_full[st], ring_ph);
           if (j == 0) mbar_wait(&s_empty[0], (n & 1) ^ 1);  // previous item's O_0 read out
           tc_fence_after();
+          ATTN_T(m1);
           issue_qk(0, st);
+          ATTN_T(m2);
           flush_pending();  // tile 1: PV of the previous block (its QK^T for this block comes next)
+          ATTN_T(m3);
           if (j == 0) mbar_wait(&s_empty[1], (n & 1) ^ 1);
           tc_fence_after();
           issue_qk(1, st);
           umma_commit(&k_empty[st]);
           if (j == nkb - 1) umma_commit(q_empty);
+          ATTN_T(m4);
           mbar_wait(&v_full[st], ring_ph);
+          ATTN_T(m5);
           mbar_wait(&p_full[0], blk_par);
           tc_fence_after();
+          ATTN_T(m6);
+          ATTN_ACC(0, m0, m1);  // wait K (+ s_empty at item start)
+          ATTN_ACC(1, m1, m2);  // issue QK0
+          ATTN_ACC(2, m2, m3);  // wait P1 + issue PV1
+          ATTN_ACC(3, m3, m4);  // issue QK1
+          ATTN_ACC(4, m4, m5);  // wait V
+          ATTN_ACC(5, m5, m6);  // wait P0
           issue_pv(0, st, j != 0);
           if (j == nkb - 1) umma_commit(&o_full[0]);
           pend = true;
@@ -812,63 +859,86 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
         }
       }
       flush_pending();
+#ifdef ECADK_ATTN_TIMING
+      dbg_acc[6] = clock() - t_begin;
+      dbg_acc[7] = nb;
+      for (int i = 0; i < 8; ++i) g_attn_dbg[blockIdx.x * 32 + i] = dbg_acc[i];
+#endif
     }
     __syncwarp();
   } else {
     // ===================== softmax + correction + epilogue =====================
-    const int t = (warp - 2) >> 2;
-    const int quarter = warp & 3;
+    const int sw = warp - 2;
+    const int t = sw >> 3;            // query tile
+    const int half = (sw >> 2) & 1;   // which 64 keys of a block / which output columns this thread owns
+    const int quarter = warp & 3;     // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
     const uint32_t t_row = tmem + 256 * t + (static_cast<uint32_t>(quarter * 32) << 16);
-    const uint32_t bias_a = smem_u32(smem + Cfg::kBias) + (warp - 2) * kFlashKB * 4;
+    const uint32_t bias_a = smem_u32(smem + Cfg::kBias) + sw * (kFlashKB / 2) * 4;
+    // exchange slots of this thread and of its partner (same tile, same quarter, other half)
+    const uint32_t xch = smem_u32(smem + Cfg::kXch);
+    const uint32_t my_slot = xch + (sw * 32 + lane) * 4;
+    const uint32_t peer_slot = xch + ((sw ^ 4) * 32 + lane) * 4;
+    const int bar_id = 1 + t * 4 + quarter;  // named barrier of the two partner warps
     constexpr float kLog2e = 1.4426950408889634f;
-    float breg[kFlashKB / 32];
+    constexpr int kOSplit = Cfg::kPad == 128 ? 64 : 48;  // O columns [0, kOSplit) -> half 0, [kOSplit, kPad) -> half 1
+    float breg[2];
     auto fetch_bias = [&](int sample, int j) {
-      const float* b = p.bias + static_cast<size_t>(sample) * n_keys + j * kFlashKB;
-#pragma unroll
-      for (int i = 0; i < kFlashKB / 32; ++i) breg[i] = __ldg(b + lane + 32 * i) * kLog2e;
+      const float* b = p.bias + static_cast<size_t>(sample) * n_keys + j * kFlashKB + half * 64;
+      breg[0] = __ldg(b + lane) * kLog2e;
+      breg[1] = __ldg(b + lane + 32) * kLog2e;
     };
     int n = 0, nb = 0;
+#ifdef ECADK_ATTN_TIMING
+    unsigned int dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const unsigned int t_begin = clock();
+#endif
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++n) {
       const int sh = item / pairs, pr = item - sh * pairs;
       const int sample = sh / p.heads, head = sh - sample * p.heads;
-      float m_used = -INFINITY, l_sum = 0.f;
+      float m_used = -INFINITY, l_sum = 0.f;  // l_sum: this thread's 64-key share of the row sum
       if constexpr (HAS_BIAS) fetch_bias(sample, 0);
       for (int j = 0; j < nkb; ++j, ++nb) {
         if constexpr (HAS_BIAS) {
-#pragma unroll
-          for (int i = 0; i < kFlashKB / 32; ++i) sts_f1(bias_a + (lane + 32 * i) * 4, breg[i]);
+          sts_f1(bias_a + lane * 4, breg[0]);
+          sts_f1(bias_a + (lane + 32) * 4, breg[1]);
           __syncwarp();
           if (j + 1 < nkb) fetch_bias(sample, j + 1);
         }
+        ATTN_T(s0);
         mbar_wait(&s_full[t], nb & 1);
         tc_fence_after();
-        // the whole 128-score row of this thread stays in registers: ONE TMEM read pass (four loads in flight, one
-        // wait), maximum and exponentials from registers, P written back over the consumed S columns
-        uint32_t v[kFlashKB / 32][32];
-#pragma unroll
-        for (int c = 0; c < kFlashKB / 32; ++c) tmem_ld_32x32(t_row + c * 32, v[c]);
+        ATTN_T(s1);
+        // this thread's 64 scores stay in registers: ONE TMEM read pass, both loads in flight
+        uint32_t v[2][32];
+        tmem_ld_32x32(t_row + half * 64, v[0]);
+        tmem_ld_32x32(t_row + half * 64 + 32, v[1]);
         tmem_ld_wait();
-        float mx = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < kFlashKB / 32; ++c)
-          mx = softmax_chunk_prep<HAS_BIAS>(v[c], mx, p.scale_log2e, bias_a + c * 128);
+        ATTN_T(s2);
+        float mx = softmax_chunk_prep<HAS_BIAS>(v[0], -INFINITY, p.scale_log2e, bias_a);
+        mx = softmax_chunk_prep<HAS_BIAS>(v[1], mx, p.scale_log2e, bias_a + 128);
         if constexpr (!HAS_BIAS) mx *= p.scale_log2e;
-        // lazy rescale: move the reference maximum only when the block maximum exceeds it by > 8 (log2 units).
-        // tcgen05.ld/st are warp-collective (.sync.aligned): the TMEM round trip runs for the whole warp as soon as
-        // ANY row needs it; rows that do not need it use alpha = 1.
+        // row maximum over both halves; the barrier also orders "partner has read its S columns" before any P write
+        const uint32_t buf = (nb & 1) * (16 * 32 * 4);
+        sts_f1(my_slot + buf, mx);
+        named_bar_sync(bar_id, 64);
+        mx = fmaxf(mx, lds_f1(peer_slot + buf));
+        ATTN_T(s3);
+        // lazy rescale: move the reference maximum only when the block maximum exceeds it by > 8 (log2 units).  Both
+        // partners see the same mx / m_used, so they take the same decisions; each rescales its own O columns.
+        // tcgen05.ld/st are warp-collective: the TMEM round trip runs for the whole warp as soon as ANY row needs it.
         const bool need = mx > m_used + 8.0f;
         const bool rescale = need && j > 0 && m_used != -INFINITY;
         const float alpha = rescale ? fast_exp2(m_used - mx) : 1.0f;
         if (__any_sync(0xffffffffu, rescale)) {
 #pragma unroll
-          for (int c = 0; c < Cfg::kPad / 16; ++c) {  // O_t: kPad fp32 columns
+          for (int c = (half ? kOSplit : 0); c < (half ? Cfg::kPad : kOSplit); c += 16) {
             uint32_t o[16];
-            tmem_ld_32x16(t_row + 128 + c * 16, o);
+            tmem_ld_32x16(t_row + 128 + c, o);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_32x16(t_row + 128 + c * 16, o);
+            tmem_st_32x16(t_row + 128 + c, o);
           }
         }
         l_sum *= alpha;
@@ -876,25 +946,34 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
         const float m_eff = m_used == -INFINITY ? 0.f : m_used;  // a fully masked prefix must not produce NaN
         uint64_t sum2 = pack_f2(0.f, 0.f);
 #pragma unroll
-        for (int c = 0; c < kFlashKB / 32; ++c) {
+        for (int c = 0; c < 2; ++c) {
           uint32_t pk[16];
           softmax_chunk_exp_reg<HAS_BIAS>(v[c], pk, sum2, m_eff, p.scale_log2e);
-          tmem_st_32x16(t_row + c * 16, pk);
+          tmem_st_32x16(t_row + half * 32 + c * 16, pk);  // P of keys [64*half + 32c, +32) as bf16 pairs
         }
         {
           float s_lo, s_hi;
           unpack_f2(sum2, s_lo, s_hi);
           l_sum += s_lo + s_hi;
         }
+        ATTN_T(s4);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[t]);
+        ATTN_T(s5);
+        ATTN_ACC(0, s0, s1);  // wait S
+        ATTN_ACC(1, s1, s2);  // TMEM load
+        ATTN_ACC(2, s2, s3);  // max + exchange
+        ATTN_ACC(3, s3, s4);  // exp + P store issue
+        ATTN_ACC(4, s4, s5);  // st wait + fence + arrive
       }
-      // ---- item done: O_t / l -> bf16 -> global
+      // ---- item done: O_t / l -> bf16 -> global; each partner writes its own output columns
+      sts_f1(my_slot + 2 * (16 * 32 * 4), l_sum);
       mbar_wait(&o_full[t], n & 1);
       tc_fence_after();
-      const float inv = 1.0f / l_sum;
+      named_bar_sync(bar_id, 64);
+      const float inv = 1.0f / (l_sum + lds_f1(peer_slot + 2 * (16 * 32 * 4)));
       const int q = pr * 256 + t * kAttnBM + row;
       __nv_bfloat16* dst;
       if (p.split_tokens > 0) {
@@ -905,36 +984,50 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
         dst = p.out + (static_cast<size_t>(sample) * p.q_tokens + q) * p.out_ld;
       }
       dst += head * HD;
-#pragma unroll
-      for (int c = 0; c < HD / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_row + 128 + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 o;
-          o.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]) * inv, __uint_as_float(v[g * 8 + 1]) * inv);
-          o.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]) * inv, __uint_as_float(v[g * 8 + 3]) * inv);
-          o.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]) * inv, __uint_as_float(v[g * 8 + 5]) * inv);
-          o.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]) * inv, __uint_as_float(v[g * 8 + 7]) * inv);
-          *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = o;
-        }
-      }
-      if constexpr (HD % 32 != 0) {  // HD = 72: columns 64..71 (72..79 are padding)
-        uint32_t v[16];
-        tmem_ld_32x16(t_row + 128 + 64, v);
-        tmem_ld_wait();
+      auto store8 = [&](const uint32_t* w, __nv_bfloat16* d) {
         uint4 o;
-        o.x = pack_bf16x2(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
-        o.y = pack_bf16x2(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
-        o.z = pack_bf16x2(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
-        o.w = pack_bf16x2(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
-        *reinterpret_cast<uint4*>(dst + 64) = o;
+        o.x = pack_bf16x2(__uint_as_float(w[0]) * inv, __uint_as_float(w[1]) * inv);
+        o.y = pack_bf16x2(__uint_as_float(w[2]) * inv, __uint_as_float(w[3]) * inv);
+        o.z = pack_bf16x2(__uint_as_float(w[4]) * inv, __uint_as_float(w[5]) * inv);
+        o.w = pack_bf16x2(__uint_as_float(w[6]) * inv, __uint_as_float(w[7]) * inv);
+        *reinterpret_cast<uint4*>(d) = o;
+      };
+      if constexpr (HD == 128) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          const int col = half * 64 + c * 32;
+          tmem_ld_32x32(t_row + 128 + col, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) store8(v + g * 8, dst + col + g * 8);
+        }
+      } else {  // HD = 72 stored as 80 columns: half 0 -> columns 0..47, half 1 -> 48..71 (72..79 are padding)
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + 128 + half * 48, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 3; ++g) store8(v + g * 8, dst + half * 48 + g * 8);
+        if (half == 0) {
+          store8(v + 24, dst + 24);
+          uint32_t w[16];
+          tmem_ld_32x16(t_row + 128 + 32, w);
+          tmem_ld_wait();
+          store8(w, dst + 32);
+          store8(w + 8, dst + 40);
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[t]);
     }
+#ifdef ECADK_ATTN_TIMING
+    if (lane == 0 && (sw == 0 || sw == 12)) {
+      dbg_acc[6] = clock() - t_begin;
+      dbg_acc[7] = nb;
+      for (int i = 0; i < 8; ++i) g_attn_dbg[blockIdx.x * 32 + (sw == 0 ? 8 : 16) + i] = dbg_acc[i];
+    }
+#endif
   }
 
   tc_fence_before();

@@ -333,7 +333,7 @@ int launch_attn_flash_inst(const CUtensorMap* tq, const CUtensorMap* tkv, const 
     configured = true;
   }
   const int grid = items < num_sms() ? items : num_sms();
-  kern<<<grid, kAttnPairThreads, Cfg::kSmemBytes, stream>>>(tq[0], tq[1], tkv[0], tkv[1], tkv[2], tkv[3], p, n_keys,
+  kern<<<grid, kFlashThreads, Cfg::kSmemBytes, stream>>>(tq[0], tq[1], tkv[0], tkv[1], tkv[2], tkv[3], p, n_keys,
                                                             items);
   return check_launch("attn_flash_kernel");
 }
@@ -921,6 +921,15 @@ int ecadk_flux_blocks(ecadk_flux_handle_t h, const EcadkFluxArgs* a, const uint8
   if (n_launches) *n_launches = launches;
   return ECADK_OK;
 }
+
+#ifdef ECADK_ATTN_TIMING
+// instrumented builds only: copies the phase-clock accumulators of the last attn_flash_kernel launch to the host
+int ecadk_debug_attn_timing(unsigned int* out_host) {
+  ECADK_CHECK_CUDA(cudaDeviceSynchronize());
+  ECADK_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_attn_dbg, sizeof(unsigned int) * 148 * 32));
+  return ECADK_OK;
+}
+#endif
 
 int ecadk_profile_start(void) {
   g_prof.used = 0;

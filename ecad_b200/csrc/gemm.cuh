@@ -94,8 +94,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
       row_off[i] = (sample * p.heads * p.tokens_pad + tok + p.hm_tok_off) * p.head_pad;
     }
   }
-  // residual-stream prefetch: the x values of chunk c+2 are requested while chunk c is being processed
-  float4 xin[8];
+  // residual-stream prefetch: the x values of this warp's NEXT chunk (c+2) are requested before chunk c is processed.
+  // The two register sets ping-pong (the chunk loop is unrolled by two): copying "next" into "current" at the end of
+  // an iteration would make the warp wait for the prefetch right there and expose the whole DRAM latency per chunk.
   auto load_x = [&](int c, float4 (&dst)[8]) {
     const int col = n0 + c * 32 + cg * 4;
 #pragma unroll
@@ -105,23 +106,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
                          : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
-  if constexpr (EPI == EPI_GATED_RESIDUAL) load_x(parity, xin);
-#pragma unroll 1
-  for (int c = parity; c < n_chunks; c += 2) {
+  auto process = [&](const int c, const float4 (&xin)[8]) {
     const int col = n0 + c * 32 + cg * 4;
-    if constexpr (EPI == EPI_UNPATCHIFY) {
-      if (n0 + c * 32 >= p.unp_cols) break;  // zero-padded weight rows: nothing to store
-    }
-    if constexpr (EPI == EPI_BIAS_F32) {
-      if (n0 + c * 32 >= p.f32_cols) break;
-    }
     uint32_t v[32];
     tmem_ld_32x32(t_row + c * 32, v);
-    float4 xnext[8];
     float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
     if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
     if constexpr (EPI == EPI_GATED_RESIDUAL) {
-      if (c + 2 < n_chunks) load_x(c + 2, xnext);
       if (p.gate_table != nullptr || p.gate_temb != nullptr) {
         g4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.gate_table != nullptr) g4 = __ldg(reinterpret_cast<const float4*>(p.gate_table + col));
@@ -202,11 +193,27 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
         }
       }
     }
-    if constexpr (EPI == EPI_GATED_RESIDUAL) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) xin[i] = xnext[i];
-    }
     __syncwarp();  // the stage tile is overwritten by the next chunk
+  };
+  int limit = n_chunks;  // chunks past the real output columns of the zero-padded heads carry nothing to store
+  if constexpr (EPI == EPI_UNPATCHIFY) limit = min(n_chunks, (p.unp_cols - n0 + 31) / 32);
+  if constexpr (EPI == EPI_BIAS_F32) limit = min(n_chunks, (p.f32_cols - n0 + 31) / 32);
+  if constexpr (EPI == EPI_GATED_RESIDUAL) {
+    float4 xa[8], xb_[8];
+    if (parity < limit) load_x(parity, xa);
+#pragma unroll 1
+    for (int c = parity; c < limit; c += 4) {
+      if (c + 2 < limit) load_x(c + 2, xb_);
+      process(c, xa);
+      if (c + 2 < limit) {
+        if (c + 4 < limit) load_x(c + 4, xa);
+        process(c + 2, xb_);
+      }
+    }
+  } else {
+    const float4 none[8] = {};
+#pragma unroll 1
+    for (int c = parity; c < limit; c += 2) process(c, none);
   }
 }
 
