@@ -366,7 +366,11 @@ __device__ __forceinline__ void softmax_chunk_exp_reg(const uint32_t (&v)[32], u
 // TMEM map (512 columns): tile t owns columns [256t, 256t+256): S_t fp32 in [0,NK); P_t (bf16 pairs) is written IN
 // PLACE over the already-consumed low half of S_t; O_t accumulates in [128,208).  No shared memory is spent on P.
 // =====================================================================================================
-constexpr int kAttnPairThreads = 320;
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+constexpr int kAttnPairThreads = 576;  // warp 0 TMA, warp 1 MMA, 16 softmax warps (two threads per score row)
 
 template <int NK>
 struct AttnPairCfg {
@@ -376,8 +380,15 @@ struct AttnPairCfg {
   static constexpr int kK16 = kK64 + NK * 128;
   static constexpr int kV = kK16 + NK * 32;         // 2 buffers of (NK*128 + NK*32)
   static constexpr int kVBuf = NK * 160;
-  static constexpr int kBias = kV + 2 * kVBuf;      // 8 warps x NK floats
-  static constexpr int kBars = kBias + 8 * NK * 4;
+  static constexpr int kBias = kV + 2 * kVBuf;      // 16 warps x NK/2 floats
+  static constexpr int kXch = kBias + 8 * NK * 4;   // row-maximum / row-sum exchange between partner warps: 2 x [16][32]
+  static constexpr int kBars = kXch + 2 * 16 * 32 * 4;
+  // TMEM columns inside a tile's 256: with 256 keys S fills all of them, so P and O live over consumed S columns -
+  // P of keys 0..127 in [0,64) (written by the threads that own S[0,128)), O in [64,144), P of keys 128..255 in
+  // [144,208) (written by the threads that own S[128,256), always behind their own reads).  With 128 keys the row is
+  // register-resident, S is dead after the exchange barrier, and the layout is simply P [0,64), O [128,208).
+  static constexpr int kPHi = NK == 256 ? 144 : 32;  // column of the P half written by the "half 1" threads
+  static constexpr int kO = NK == 256 ? 64 : 128;
   // the kernel allocates all 512 TMEM columns, so it must be alone on its SM: ask for more than half the smem
   static constexpr int kSmemBytes = (kBars + 256 + 1024) > 120 * 1024 ? (kBars + 256 + 1024) : 120 * 1024;
   static constexpr uint32_t kBytesQK = (256 + NK) * kHeadPad * 2;
@@ -414,9 +425,9 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_consta
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);
+      mbar_init(&p_full[i], 8);
       mbar_init(&o_full[i], 1);
-      mbar_init(&s_empty[i], 4);
+      mbar_init(&s_empty[i], 8);
     }
     fence_barrier_init();
   }
@@ -477,22 +488,31 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_consta
       auto issue_pv = [&](int t, int vb) {
         const uint32_t vbase = sbase + Cfg::kV + vb * Cfg::kVBuf;
         const uint32_t p_tmem = tmem + 256 * t;  // bf16 pairs: 8 columns per 16-key step
-        const uint32_t o_tmem = tmem + 256 * t + 128;
+        const uint32_t o_tmem = tmem + 256 * t + Cfg::kO;
 #pragma unroll
         for (int ks = 0; ks < NK / 16; ++ks) {
           const uint64_t dv = make_smem_desc(vbase + ks * 16 * 32, NK * 32, 256, kLayoutSW32);
-          umma_bf16_ts(o_tmem, p_tmem + ks * 8, dv, idesc_o80, ks != 0);
+          const uint32_t pa = ks < NK / 32 ? p_tmem + ks * 8 : p_tmem + Cfg::kPHi + (ks - NK / 32) * 8;
+          umma_bf16_ts(o_tmem, pa, dv, idesc_o80, ks != 0);
         }
         umma_commit(&o_full[t]);
       };
       int n = 0;
+#ifdef ECADK_ATTN_TIMING
+      unsigned int dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      const unsigned int t_begin = clock();
+#endif
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++n) {
         const uint32_t par = n & 1;
+        ATTN_T(m0);
         mbar_wait(qk_full, par);
+        ATTN_T(m1);
         // tile 0: S(i)
         mbar_wait(&s_empty[0], par ^ 1);  // previous item's O_0 has been read out of TMEM
         tc_fence_after();
+        ATTN_T(m2);
         issue_qk(0);
+        ATTN_T(m3);
         // tile 1: PV(i-1)  (V(i-1) sits in buffer (n-1)&1 and was waited for in the previous iteration)
         if (n > 0) {
           mbar_wait(&p_full[1], par ^ 1);
@@ -500,17 +520,33 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_consta
           issue_pv(1, (n - 1) & 1);
           umma_commit(&v_empty[(n - 1) & 1]);
         }
+        ATTN_T(m4);
         // tile 1: S(i)
         mbar_wait(&s_empty[1], par ^ 1);
         tc_fence_after();
         issue_qk(1);
         umma_commit(qk_empty);  // Q/K smem may be refilled with the next item
+        ATTN_T(m5);
         // tile 0: PV(i)
         mbar_wait(&v_full[n & 1], (n >> 1) & 1);
         mbar_wait(&p_full[0], par);
         tc_fence_after();
+        ATTN_T(m6);
         issue_pv(0, n & 1);
+        ATTN_T(m7);
+        ATTN_ACC(0, m0, m1);  // wait Q/K
+        ATTN_ACC(1, m1, m2);  // wait O_0 read out
+        ATTN_ACC(2, m2, m3);  // issue QK0
+        ATTN_ACC(3, m3, m4);  // wait P1 + issue PV1
+        ATTN_ACC(4, m4, m5);  // wait O_1 read out + issue QK1
+        ATTN_ACC(5, m5, m6);  // wait V + P0
+        ATTN_ACC(6, m6, m7);  // issue PV0
       }
+#ifdef ECADK_ATTN_TIMING
+      dbg_acc[7] = n;
+      for (int i = 0; i < 8; ++i) g_attn_dbg[blockIdx.x * 32 + i] = dbg_acc[i];
+      g_attn_dbg[blockIdx.x * 32 + 24] = clock() - t_begin;
+#endif
       if (n > 0) {  // drain: tile 1's PV of the last item
         mbar_wait(&p_full[1], (n - 1) & 1);
         tc_fence_after();
@@ -520,101 +556,150 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_consta
     }
     __syncwarp();
   } else {
-    // ===================== softmax + epilogue: warps 2..5 -> tile 0, warps 6..9 -> tile 1 =====================
-    const int t = (warp - 2) >> 2;
+    // ===================== softmax + epilogue: warps 2..9 -> tile 0, warps 10..17 -> tile 1 =====================
+    // Every score row is shared by two threads (the two warps of a tile that own the same TMEM lane quarter): "half 0"
+    // takes keys [0, NK/2) and output columns 0..47, "half 1" keys [NK/2, NK) and columns 48..71.  The per-thread
+    // exponential chain (~17 clk each) bounded this kernel; halving the row halves it.
+    const int sw = warp - 2;
+    const int t = sw >> 3;
+    const int half = (sw >> 2) & 1;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
     const uint32_t t_row = tmem + 256 * t + (static_cast<uint32_t>(quarter * 32) << 16);
-    const uint32_t bias_a = smem_u32(smem + Cfg::kBias) + (warp - 2) * NK * 4;  // per-warp bias slice (shared space)
+    const uint32_t s_col = t_row + half * (NK / 2);                    // this thread's score columns
+    const uint32_t p_col = t_row + (half ? Cfg::kPHi : 0);             // ... and where its P goes
+    const uint32_t bias_a = smem_u32(smem + Cfg::kBias) + sw * (NK / 2) * 4;  // per-warp bias slice (shared space)
+    const uint32_t xch = smem_u32(smem + Cfg::kXch);
+    const uint32_t my_slot = xch + (sw * 32 + lane) * 4;
+    const uint32_t peer_slot = xch + ((sw ^ 4) * 32 + lane) * 4;
+    const int bar_id = 1 + t * 4 + quarter;
+    constexpr int NC = NK / 64;  // 32-column chunks per thread
     constexpr float kLog2e = 1.4426950408889634f;
     // key bias of the NEXT item is fetched one item ahead (registers), so its global latency is off the chain
-    float breg[NK / 32];
+    float breg[NC];
     auto fetch_bias = [&](int it) {
-      const float* b = p.bias + static_cast<size_t>(it / p.heads) * NK;
+      const float* b = p.bias + static_cast<size_t>(it / p.heads) * NK + half * (NK / 2);
 #pragma unroll
-      for (int j = 0; j < NK / 32; ++j) breg[j] = __ldg(b + lane + 32 * j) * kLog2e;
+      for (int j = 0; j < NC; ++j) breg[j] = __ldg(b + lane + 32 * j) * kLog2e;
     };
     if constexpr (HAS_BIAS) {
       if (static_cast<int>(blockIdx.x) < num_items) fetch_bias(blockIdx.x);
     }
     int n = 0;
+#ifdef ECADK_ATTN_TIMING
+    unsigned int dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++n) {
       const uint32_t par = n & 1;
       const int sample = item / p.heads;
       const int head = item - sample * p.heads;
       if constexpr (HAS_BIAS) {
 #pragma unroll
-        for (int j = 0; j < NK / 32; ++j) sts_f1(bias_a + (lane + 32 * j) * 4, breg[j]);
+        for (int j = 0; j < NC; ++j) sts_f1(bias_a + (lane + 32 * j) * 4, breg[j]);
         __syncwarp();
         if (item + static_cast<int>(gridDim.x) < num_items) fetch_bias(item + gridDim.x);
       }
+      ATTN_T(s0);
       mbar_wait(&s_full[t], par);
       tc_fence_after();
-      // (measured: keeping the row in registers / double-buffering the TMEM loads is SLOWER here - 141 vs 117 us for
-      // the self-attention shape; this kernel is bound by the per-thread exp chain, not by TMEM latency)
+      ATTN_T(s1);
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < NK / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_row + c * 32, v);
-        tmem_ld_wait();
-        mx = softmax_chunk_max<HAS_BIAS>(v, mx, p.scale_log2e, bias_a + c * 128);
-      }
-      if constexpr (!HAS_BIAS) mx *= p.scale_log2e;
       uint64_t sum2 = pack_f2(0.f, 0.f);
-#pragma unroll 1
-      for (int c = 0; c < NK / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_row + c * 32, v);
+      if constexpr (NK == 128) {
+        // 64 scores per thread stay in registers: one TMEM read pass
+        uint32_t v[NC][32];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) tmem_ld_32x32(s_col + c * 32, v[c]);
         tmem_ld_wait();
-        uint32_t pk[16];
-        softmax_chunk_exp<HAS_BIAS>(v, pk, sum2, mx, p.scale_log2e, bias_a + c * 128);
-        // P chunk c (keys 32c..32c+31) -> packed columns [16c, 16c+16): inside the already-read part of S
-        tmem_st_32x16(t_row + c * 16, pk);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) mx = softmax_chunk_prep<HAS_BIAS>(v[c], mx, p.scale_log2e, bias_a + c * 128);
+        if constexpr (!HAS_BIAS) mx *= p.scale_log2e;
+        sts_f1(my_slot, mx);
+        named_bar_sync(bar_id, 64);  // also: the partner has finished reading its S columns
+        mx = fmaxf(mx, lds_f1(peer_slot));
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          uint32_t pk[16];
+          softmax_chunk_exp_reg<HAS_BIAS>(v[c], pk, sum2, mx, p.scale_log2e);
+          tmem_st_32x16(p_col + c * 16, pk);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < NC; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(s_col + c * 32, v);
+          tmem_ld_wait();
+          mx = softmax_chunk_max<HAS_BIAS>(v, mx, p.scale_log2e, bias_a + c * 128);
+        }
+        if constexpr (!HAS_BIAS) mx *= p.scale_log2e;
+        sts_f1(my_slot, mx);
+        named_bar_sync(bar_id, 64);
+        mx = fmaxf(mx, lds_f1(peer_slot));
+#pragma unroll 1
+        for (int c = 0; c < NC; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(s_col + c * 32, v);
+          tmem_ld_wait();
+          uint32_t pk[16];
+          softmax_chunk_exp<HAS_BIAS>(v, pk, sum2, mx, p.scale_log2e, bias_a + c * 128);
+          // P chunk c of this thread -> packed columns [16c, 16c+16) of ITS P region: always behind its own S reads
+          tmem_st_32x16(p_col + c * 16, pk);
+        }
       }
       float sum_lo, sum_hi;
       unpack_f2(sum2, sum_lo, sum_hi);
       const float sum = sum_lo + sum_hi;
+      sts_f1(my_slot + 16 * 32 * 4, sum);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[t]);
-
+      ATTN_T(s2);
       mbar_wait(&o_full[t], par);
       tc_fence_after();
-      const float inv = 1.0f / sum;
+      named_bar_sync(bar_id, 64);
+      ATTN_T(s3);
+      const float inv = 1.0f / (sum + lds_f1(peer_slot + 16 * 32 * 4));
       const int q = t * kAttnBM + row;
       __nv_bfloat16* dst = p.out + (static_cast<size_t>(sample) * p.q_tokens + q) * p.out_ld + head * kHeadDim;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_row + 128 + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 o;
-          o.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]) * inv, __uint_as_float(v[g * 8 + 1]) * inv);
-          o.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]) * inv, __uint_as_float(v[g * 8 + 3]) * inv);
-          o.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]) * inv, __uint_as_float(v[g * 8 + 5]) * inv);
-          o.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]) * inv, __uint_as_float(v[g * 8 + 7]) * inv);
-          *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = o;
-        }
-      }
-      {
-        uint32_t v[16];
-        tmem_ld_32x16(t_row + 128 + 64, v);  // columns 64..79 of O; 72..79 are padding
-        tmem_ld_wait();
+      auto store8 = [&](const uint32_t* w, __nv_bfloat16* d) {
         uint4 o;
-        o.x = pack_bf16x2(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
-        o.y = pack_bf16x2(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
-        o.z = pack_bf16x2(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
-        o.w = pack_bf16x2(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
-        *reinterpret_cast<uint4*>(dst + 64) = o;
+        o.x = pack_bf16x2(__uint_as_float(w[0]) * inv, __uint_as_float(w[1]) * inv);
+        o.y = pack_bf16x2(__uint_as_float(w[2]) * inv, __uint_as_float(w[3]) * inv);
+        o.z = pack_bf16x2(__uint_as_float(w[4]) * inv, __uint_as_float(w[5]) * inv);
+        o.w = pack_bf16x2(__uint_as_float(w[6]) * inv, __uint_as_float(w[7]) * inv);
+        *reinterpret_cast<uint4*>(d) = o;
+      };
+      {
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + Cfg::kO + half * 48, v);  // half 0: columns 0..31, half 1: 48..79 (72..79 are padding)
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 3; ++g) store8(v + g * 8, dst + half * 48 + g * 8);
+        if (half == 0) {
+          store8(v + 24, dst + 24);
+          uint32_t w[16];
+          tmem_ld_32x16(t_row + Cfg::kO + 32, w);
+          tmem_ld_wait();
+          store8(w, dst + 32);
+          store8(w + 8, dst + 40);
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[t]);  // TMEM columns of tile t are free for the next item
+      ATTN_T(s4);
+      ATTN_ACC(0, s0, s1);  // wait S
+      ATTN_ACC(1, s1, s2);  // softmax (max, exchange, exp, P store)
+      ATTN_ACC(2, s2, s3);  // wait O
+      ATTN_ACC(3, s3, s4);  // O read-out + global stores
     }
+#ifdef ECADK_ATTN_TIMING
+    if (lane == 0 && (sw == 0 || sw == 12)) {
+      dbg_acc[7] = n;
+      for (int i = 0; i < 8; ++i) g_attn_dbg[blockIdx.x * 32 + (sw == 0 ? 8 : 16) + i] = dbg_acc[i];
+    }
+#endif
   }
 
   tc_fence_before();
@@ -670,10 +755,6 @@ struct AttnFlashCfg {
   static_assert(kSmemBytes > 114 * 1024 && kSmemBytes <= 227 * 1024,
                 "attn_flash_kernel must be alone on its SM (it owns all 512 TMEM columns) and fit in shared memory");
 };
-
-__device__ __forceinline__ void named_bar_sync(int id, int threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
 
 template <int HD, bool HAS_BIAS>
 __global__ void __launch_bounds__(kFlashThreads, 1)

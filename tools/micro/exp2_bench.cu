@@ -74,10 +74,19 @@ __global__ void __launch_bounds__(256) bench(float* out, long long* clocks, int 
           exp2_poly2(v[i + 2], v[i + 3], c, d);
         }
         acc += a + b + c + d;
-      } else {
+      } else if constexpr (MODE == 5) {
         float a = fast_exp2(v[i]), b = fast_exp2(v[i + 1]), c, d;
         exp2_poly2(v[i + 2], v[i + 3], c, d);
         acc += a + b + c + d;
+      } else if constexpr (MODE == 6) {  // what the softmax loop does: MUFU + cvt.rn.bf16x2 pack
+        const float a = fast_exp2(v[i]), b = fast_exp2(v[i + 1]), c = fast_exp2(v[i + 2]), d = fast_exp2(v[i + 3]);
+        acc += a + b + c + d;
+        acc2 ^= pack_bf16x2(a, b) ^ pack_bf16x2(c, d);
+      } else {  // MUFU + integer round-to-nearest pack (IADD, IADD, PRMT) instead of F2FP
+        const float a = fast_exp2(v[i]), b = fast_exp2(v[i + 1]), c = fast_exp2(v[i + 2]), d = fast_exp2(v[i + 3]);
+        acc += a + b + c + d;
+        acc2 ^= __byte_perm(__float_as_uint(a) + 0x8000u, __float_as_uint(b) + 0x8000u, 0x7632) ^
+                __byte_perm(__float_as_uint(c) + 0x8000u, __float_as_uint(d) + 0x8000u, 0x7632);
       }
     }
 #pragma unroll
@@ -121,6 +130,8 @@ int main() {
     run<3>("D polynomial fp32x2", bps);
     run<4>("E 3/4 MUFU + 1/4 polynomial", bps);
     run<5>("F 1/2 MUFU + 1/2 polynomial", bps);
+    run<6>("G MUFU + cvt.rn.bf16x2 pack", bps);
+    run<7>("H MUFU + integer-rounded PRMT pack", bps);
   }
   return 0;
 }
