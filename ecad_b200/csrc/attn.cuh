@@ -671,6 +671,8 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_consta
         *reinterpret_cast<uint4*>(d) = o;
       };
       {
+        // (measured: handing the TMEM columns back BEFORE the row-strided global stores - O parked in registers -
+        // is slower for the d = 72 kernels, 110 -> 138 us at the config-2 shape, although it helps the d = 128 one)
         uint32_t v[32];
         tmem_ld_32x32(t_row + Cfg::kO + half * 48, v);  // half 0: columns 0..31, half 1: 48..79 (72..79 are padding)
         tmem_ld_wait();
@@ -1073,15 +1075,20 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
         o.w = pack_bf16x2(__uint_as_float(w[6]) * inv, __uint_as_float(w[7]) * inv);
         *reinterpret_cast<uint4*>(d) = o;
       };
+      // O leaves TMEM into registers and the tile's columns go back to the MMA warp BEFORE the (slow, row-strided)
+      // global stores, so the next item's QK^T does not wait for them
       if constexpr (HD == 128) {
+        uint32_t v[2][32];
+        tmem_ld_32x32(t_row + 128 + half * 64, v[0]);
+        tmem_ld_32x32(t_row + 128 + half * 64 + 32, v[1]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[t]);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          uint32_t v[32];
-          const int col = half * 64 + c * 32;
-          tmem_ld_32x32(t_row + 128 + col, v);
-          tmem_ld_wait();
 #pragma unroll
-          for (int g = 0; g < 4; ++g) store8(v + g * 8, dst + col + g * 8);
+          for (int g = 0; g < 4; ++g) store8(v[c] + g * 8, dst + half * 64 + c * 32 + g * 8);
         }
       } else {  // HD = 72 stored as 80 columns: half 0 -> columns 0..47, half 1 -> 48..71 (72..79 are padding)
         uint32_t v[32];
@@ -1097,10 +1104,10 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
           store8(w, dst + 32);
           store8(w + 8, dst + 40);
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[t]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[t]);
     }
 #ifdef ECADK_ATTN_TIMING
     if (lane == 0 && (sw == 0 || sw == 12)) {
