@@ -114,6 +114,7 @@ class EcadkBlocksArgs(C.Structure):
         ("k2", C.POINTER(C.c_void_p)),
         ("v2", C.POINTER(C.c_void_p)),
         ("cache", C.POINTER(C.c_void_p)),
+        ("cache_dead", C.POINTER(C.c_uint8)),
     ]
 
 
@@ -143,7 +144,8 @@ class EcadkFluxArgs(C.Structure):
         + [(n, C.c_void_p) for n in ("x_img", "x_txt", "x_cat", "h_img", "h_txt", "h_cat", "q", "k", "v", "attn_img",
                                      "attn_txt", "ffh", "cat", "mod")]
         + [("mod_stride", C.c_int), ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p),
-           ("cache_double", C.POINTER(C.c_void_p)), ("cache_single", C.POINTER(C.c_void_p))]
+           ("cache_double", C.POINTER(C.c_void_p)), ("cache_single", C.POINTER(C.c_void_p)),
+           ("cache_dead", C.POINTER(C.c_uint8))]
     )
 
 

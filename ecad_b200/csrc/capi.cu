@@ -721,8 +721,8 @@ int ecadk_gemm_bias(const void* a, const void* w, const float* bias, void* out, 
 int ecadk_gemm_bias_gated_residual_cache(const void* a, const void* w, const float* bias, float* x, void* xb,
                                          void* cache, const float* gate_table, const float* gate_temb,
                                          int temb_stride, int tokens, int m, int n, int k, ecadk_stream_t stream) {
-  ECADK_REQUIRE(x && cache && aligned16(x) && aligned16(cache) && (xb == nullptr || aligned16(xb)),
-                "gemm_gated_residual: bad x/cache");
+  ECADK_REQUIRE(x && aligned16(x) && (cache == nullptr || aligned16(cache)) && (xb == nullptr || aligned16(xb)),
+                "gemm_gated_residual: bad x/cache/xb");
   ECADK_REQUIRE(tokens > 0 && tokens % 32 == 0, "gemm_gated_residual: tokens=%d must be a multiple of 32", tokens);
   ECADK_REQUIRE(gate_table == nullptr || gate_temb != nullptr || temb_stride == 0,
                 "gemm_gated_residual: a gate table without a per-sample vector needs temb_stride = 0");
@@ -814,6 +814,11 @@ int ecadk_flux_blocks(ecadk_flux_handle_t h, const EcadkFluxArgs* a, const uint8
     void* c_ff = a->cache_double[b * 4 + 2];
     void* c_ffc = a->cache_double[b * 4 + 3];
     const bool ex_attn = executed[b * 3 + 0], ex_ff = executed[b * 3 + 1], ex_ffc = executed[b * 3 + 2];
+    const uint8_t* dead = a->cache_dead;  // dead-store elimination (see EcadkFluxArgs.cache_dead)
+    void* s_attn = (dead && dead[b * 3 + 0]) ? nullptr : c_attn;
+    void* s_ctx = (dead && dead[b * 3 + 0]) ? nullptr : c_ctx;
+    void* s_ff = (dead && dead[b * 3 + 1]) ? nullptr : c_ff;
+    void* s_ffc = (dead && dead[b * 3 + 2]) ? nullptr : c_ffc;
     // joint attention (cached_flux_transformer_block.py:170-201,247-256): chunks shift_msa 0, scale_msa 1, gate_msa 2
     if (ex_attn) {
       if ((rc = img.layer_norm(a->h_img, mi + 0 * D, mi + 1 * D))) return rc;
@@ -828,10 +833,10 @@ int ecadk_flux_blocks(ecadk_flux_handle_t h, const EcadkFluxArgs* a, const uint8
                                    a->rope_sin, B, H, S, T, d.eps, stream_)))
         return rc;
       if ((rc = launch_attention_d128(a->q, a->k, a->v, a->attn_img, D, a->attn_txt, T, B, H, S, S, stream))) return rc;
-      if ((rc = ecadk_gemm_bias_gated_residual_cache(a->attn_img, w.w_out, w.b_out, a->x_img, nullptr, c_attn, nullptr,
+      if ((rc = ecadk_gemm_bias_gated_residual_cache(a->attn_img, w.w_out, w.b_out, a->x_img, nullptr, s_attn, nullptr,
                                                      mi + 2 * D, MS, N, B * N, D, D, stream_)))
         return rc;
-      if ((rc = ecadk_gemm_bias_gated_residual_cache(a->attn_txt, w.w_out_ctx, w.b_out_ctx, a->x_txt, nullptr, c_ctx,
+      if ((rc = ecadk_gemm_bias_gated_residual_cache(a->attn_txt, w.w_out_ctx, w.b_out_ctx, a->x_txt, nullptr, s_ctx,
                                                      nullptr, mt + 2 * D, MS, T, B * T, D, D, stream_)))
         return rc;
       launches += 6;
@@ -843,7 +848,7 @@ int ecadk_flux_blocks(ecadk_flux_handle_t h, const EcadkFluxArgs* a, const uint8
     if (ex_ff) {
       if ((rc = img.layer_norm(a->h_img, mi + 3 * D, mi + 4 * D))) return rc;
       if ((rc = ecadk_gemm_bias(a->h_img, w.w_ff1, w.b_ff1, a->ffh, B * N, F, D, F, 1, stream_))) return rc;
-      if ((rc = ecadk_gemm_bias_gated_residual_cache(a->ffh, w.w_ff2, w.b_ff2, a->x_img, nullptr, c_ff, nullptr,
+      if ((rc = ecadk_gemm_bias_gated_residual_cache(a->ffh, w.w_ff2, w.b_ff2, a->x_img, nullptr, s_ff, nullptr,
                                                      mi + 5 * D, MS, N, B * N, D, F, stream_)))
         return rc;
       launches += 2;
@@ -854,7 +859,7 @@ int ecadk_flux_blocks(ecadk_flux_handle_t h, const EcadkFluxArgs* a, const uint8
     if (ex_ffc) {
       if ((rc = txt.layer_norm(a->h_txt, mt + 3 * D, mt + 4 * D))) return rc;
       if ((rc = ecadk_gemm_bias(a->h_txt, w.w_ff1_ctx, w.b_ff1_ctx, a->ffh, B * T, F, D, F, 1, stream_))) return rc;
-      if ((rc = ecadk_gemm_bias_gated_residual_cache(a->ffh, w.w_ff2_ctx, w.b_ff2_ctx, a->x_txt, nullptr, c_ffc,
+      if ((rc = ecadk_gemm_bias_gated_residual_cache(a->ffh, w.w_ff2_ctx, w.b_ff2_ctx, a->x_txt, nullptr, s_ffc,
                                                      nullptr, mt + 5 * D, MS, T, B * T, D, F, stream_)))
         return rc;
       launches += 2;
@@ -906,7 +911,8 @@ int ecadk_flux_blocks(ecadk_flux_handle_t h, const EcadkFluxArgs* a, const uint8
       if ((rc = ecadk_strided_unary(c_mlp, static_cast<__nv_bfloat16*>(a->cat) + D, B * S, F, F, 5 * D, 1, stream_)))
         return rc;
       if ((rc = cat.flush())) return rc;  // the epilogue below updates x in place: pending reuses must land first
-      if ((rc = ecadk_gemm_bias_gated_residual_cache(a->cat, w.w_out, w.b_out, a->x_cat, nullptr, c_out, nullptr,
+      void* s_out = (a->cache_dead && a->cache_dead[r + 2]) ? nullptr : c_out;
+      if ((rc = ecadk_gemm_bias_gated_residual_cache(a->cat, w.w_out, w.b_out, a->x_cat, nullptr, s_out, nullptr,
                                                      ms + 2 * D, MS, S, B * S, D, 5 * D, stream_)))
         return rc;
       launches += 3;
@@ -1121,6 +1127,11 @@ int ecadk_pixart_blocks(ecadk_handle_t h, const EcadkBlocksArgs* a, const uint8_
     void* c1 = a->cache[b * 3 + 0];
     void* c2 = a->cache[b * 3 + 1];
     void* c3 = a->cache[b * 3 + 2];
+    // dead-store elimination: an executed sub-block whose cache slot is overwritten before any step reads it
+    const uint8_t* dead = a->cache_dead;
+    void* s1 = (dead && dead[b * 3 + 0]) ? nullptr : c1;
+    void* s2 = (dead && dead[b * 3 + 1]) ? nullptr : c2;
+    void* s3 = (dead && dead[b * 3 + 2]) ? nullptr : c3;
     bool xb_valid = false;
 
     // ---- attn1 (cached_transformer_block.py:208-246)
@@ -1137,7 +1148,7 @@ int ecadk_pixart_blocks(ecadk_handle_t h, const EcadkBlocksArgs* a, const uint8_
       if ((rc = launch_attention(a->q, a->k, a->v, nullptr, a->attn_o, a->samples, d.heads, a->tokens, a->tokens,
                                  stream)))
         return rc;
-      if ((rc = ecadk_gemm_bias_gated_residual_cache(a->attn_o, w.w_out1, w.b_out1, a->x, ex2 ? a->xb : nullptr, c1,
+      if ((rc = ecadk_gemm_bias_gated_residual_cache(a->attn_o, w.w_out1, w.b_out1, a->x, ex2 ? a->xb : nullptr, s1,
                                                      tab + 2 * D, a->temb6 + 2 * D, S6, a->tokens, M, D, D, stream_)))
         return rc;
       launches += 3;
@@ -1158,7 +1169,7 @@ int ecadk_pixart_blocks(ecadk_handle_t h, const EcadkBlocksArgs* a, const uint8_
       if ((rc = launch_attention(a->q, a->k2[b], a->v2[b], a->text_bias, a->attn_o, a->samples, d.heads, a->tokens,
                                  a->text_pad, stream)))
         return rc;
-      if ((rc = ecadk_gemm_bias_gated_residual_cache(a->attn_o, w.w_out2, w.b_out2, a->x, nullptr, c2, nullptr,
+      if ((rc = ecadk_gemm_bias_gated_residual_cache(a->attn_o, w.w_out2, w.b_out2, a->x, nullptr, s2, nullptr,
                                                      nullptr, S6, a->tokens, M, D, D, stream_)))
         return rc;
       launches += 3;
@@ -1175,7 +1186,7 @@ int ecadk_pixart_blocks(ecadk_handle_t h, const EcadkBlocksArgs* a, const uint8_
       pend.scale_temb = a->temb6 + 4 * D;
       if ((rc = flush())) return rc;
       if ((rc = ecadk_gemm_bias(a->h, w.w_ff1, w.b_ff1, a->ffh, M, d.ff_dim, D, d.ff_dim, 1, stream_))) return rc;
-      if ((rc = ecadk_gemm_bias_gated_residual_cache(a->ffh, w.w_ff2, w.b_ff2, a->x, nullptr, c3, tab + 5 * D,
+      if ((rc = ecadk_gemm_bias_gated_residual_cache(a->ffh, w.w_ff2, w.b_ff2, a->x, nullptr, s3, tab + 5 * D,
                                                      a->temb6 + 5 * D, S6, a->tokens, M, D, d.ff_dim, stream_)))
         return rc;
       launches += 2;

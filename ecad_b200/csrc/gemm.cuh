@@ -155,10 +155,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
           *reinterpret_cast<uint2*>(p.out + static_cast<size_t>(row) * p.ldo + col) = w;
         } else if constexpr (EPI == EPI_GATED_RESIDUAL) {
           const size_t off = static_cast<size_t>(row) * p.N + col;
-          uint2 cv;
-          cv.x = pack_bf16x2(o.x, o.y);
-          cv.y = pack_bf16x2(o.z, o.w);
-          *reinterpret_cast<uint2*>(p.cache + off) = cv;
+          if (p.cache != nullptr) {  // null: the caller knows this slot is overwritten before anyone reads it
+            uint2 cv;
+            cv.x = pack_bf16x2(o.x, o.y);
+            cv.y = pack_bf16x2(o.z, o.w);
+            *reinterpret_cast<uint2*>(p.cache + off) = cv;
+          }
           float4 x = xin[i];
           x.x = fmaf(g4.x, o.x, x.x); x.y = fmaf(g4.y, o.y, x.y);
           x.z = fmaf(g4.z, o.z, x.z); x.w = fmaf(g4.w, o.w, x.w);

@@ -92,6 +92,9 @@ class B200FluxTransformer2D:
         self._text_key: tuple | None = None
         self._rope_key: tuple | None = None
         self.last_executed: np.ndarray | None = None
+        self.skip_dead_cache_stores = True  # see B200PixArtTransformer2D
+        self._cache_written = np.zeros((rows, 3), dtype=np.bool_)
+        self.last_dead: np.ndarray | None = None
         self.warnings: list[str] = []
         self.launches = 0
 
@@ -256,6 +259,7 @@ class B200FluxTransformer2D:
         ws["args"] = a
         self._ws, self._ws_key = ws, key
         self._has_cache[:] = False
+        self._cache_written[:] = False
         self._text_key = None
         self._rope_key = None
         return ws
@@ -264,7 +268,36 @@ class B200FluxTransformer2D:
     def reset_cache(self) -> None:
         """flux_transformer_2d_edited.py:183-189: drop every cached tensor (validity bits only; HBM slots stay)."""
         self._has_cache[:] = False
+        self._cache_written[:] = False
         self._text_key = None
+
+    def _dead_stores(self, executed: np.ndarray) -> np.ndarray:
+        """1 where an executed component's cache store is dead (overwritten next step or dropped at the end of the
+        generation before anything reads it).  single_attn / single_proj_mlp are produced in place and always kept."""
+        sched, cfg = self.cache_schedule, self.cfg
+        rows = cfg.num_layers + cfg.num_single_layers
+        dead = np.zeros((rows, 3), dtype=np.uint8)
+        if not self.skip_dead_cache_stores:
+            return dead
+        step = sched.curr_step
+        last = step >= sched.num_inference_steps - 1
+        if last:
+            nxt_flags = np.ones((rows, 3), dtype=np.bool_)
+        else:
+            nxt = sched.schedule.get(step + 1)
+            if nxt is None:
+                return dead
+            nxt_flags = np.zeros((rows, 3), dtype=np.bool_)
+            for r in range(rows):
+                if r < cfg.num_layers:
+                    e = nxt[str(r)]
+                    nxt_flags[r] = [e["full_attn"], e["full_ff"], e["full_ff_context"]]
+                else:
+                    e = nxt[f"single_{r - cfg.num_layers}"]
+                    nxt_flags[r] = [e["single_attn"], e["single_proj_mlp"], e["single_proj_out"]]
+        dead[:] = executed.astype(np.bool_) & nxt_flags
+        dead[cfg.num_layers:, 0:2] = 0
+        return dead
 
     def _decide(self) -> np.ndarray:
         """``recompute or no_cache`` per component (cached_flux_transformer_block.py:52-61,81-91,173-186,207-216)."""
@@ -397,11 +430,19 @@ class B200FluxTransformer2D:
         executed = self._decide()
         self.last_executed = executed
         ex = np.ascontiguousarray(executed.reshape(-1))
+        dead = self._dead_stores(executed)
+        if (~executed.astype(np.bool_) & self._has_cache & ~self._cache_written).any():
+            raise RuntimeError("a cache slot whose store was skipped as dead is being reused: the schedule changed "
+                               "mid-generation (set skip_dead_cache_stores = False for such flows)")
+        self.last_dead = dead
+        self._dead_flat = np.ascontiguousarray(dead.reshape(-1))
+        ws["args"].cache_dead = self._dead_flat.ctypes.data_as(C.POINTER(C.c_uint8))
         n_l = C.c_int(0)
         _lib.check(lib.ecadk_flux_blocks(self._handle, C.byref(ws["args"]), ex.ctypes.data_as(C.POINTER(C.c_uint8)),
                                          C.byref(n_l), st), "flux_blocks")
         launches += n_l.value
         self._has_cache |= executed.astype(np.bool_)
+        self._cache_written = np.where(executed.astype(np.bool_), ~dead.astype(np.bool_), self._cache_written)
 
         # norm_out (AdaLayerNormContinuous: scale first, then shift) + proj_out (:316-317)
         mo = ws["mod"][:, self.mod_out_off:]

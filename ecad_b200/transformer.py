@@ -123,6 +123,12 @@ class B200PixArtTransformer2D:
         self._has_cache = np.zeros((config.num_layers, 3), dtype=np.bool_)
         self._text_key: tuple | None = None
         self.last_executed: np.ndarray | None = None
+        # Dead-store elimination: an executed sub-block does not store its cache slot when the schedule shows that the
+        # slot is overwritten (next step recomputes it) or dropped (generation ends) before anything reads it.
+        # `_cache_written` tracks which slots really hold data; a reuse of an unwritten slot raises.
+        self.skip_dead_cache_stores = True
+        self._cache_written = np.zeros((config.num_layers, 3), dtype=np.bool_)
+        self.last_dead: np.ndarray | None = None
         self.launches = 0  # kernels of libecad_b200 enqueued so far (bench.py's gpu_launches)
 
     # ------------------------------------------------------------------------------------------------
@@ -281,6 +287,7 @@ class B200PixArtTransformer2D:
         self._ws, self._ws_key = ws, key
         # a new workspace means new (empty) cache tensors
         self._has_cache[:] = False
+        self._cache_written[:] = False
         self._text_key = None
         return ws
 
@@ -289,7 +296,43 @@ class B200PixArtTransformer2D:
         """pixart_transformer_2d_edited.py:155-158 + cached_transformer_block.py:120-123: drop every cached tensor.
         The HBM slots are kept (no allocator churn); only their validity is cleared."""
         self._has_cache[:] = False
+        self._cache_written[:] = False
         self._text_key = None
+
+    def _dead_stores(self, executed: np.ndarray) -> np.ndarray:
+        """1 where an executed sub-block's cache store is dead: the generation ends after this step (reset callback,
+        image_generator.py:193-202) or the next step's flag recomputes the sub-block through the default decision
+        functions.  Custom / TGATE decision functions keep their stores (their next decision is not a pure flag)."""
+        sched = self.cache_schedule
+        step = sched.curr_step
+        L = self.cfg.num_layers
+        dead = np.zeros((L, 3), dtype=np.uint8)
+        if not self.skip_dead_cache_stores:
+            return dead
+        last = step >= sched.num_inference_steps - 1
+        nxt = None if last else sched.schedule.get(step + 1)
+        if not last and nxt is None:
+            return dead
+        default_attn, default_ff = ComputeAttnRegistry.default(), ComputeFFRegistry.default()
+
+        def is_default(entry) -> tuple[bool, bool]:
+            a = ComputeAttnRegistry.get((entry.get("custom_compute_attn") or {}).get("name"), False)
+            f = ComputeFFRegistry.get((entry.get("custom_compute_ff") or {}).get("name"), False)
+            return a is default_attn, f is default_ff
+
+        row = sched.schedule[step]
+        for b in range(L):
+            cur_a, cur_f = is_default(row[str(b)])
+            if last:
+                nxt_a, nxt_f, flags = True, True, (True, True, True)
+            else:
+                e = nxt[str(b)]
+                nxt_a, nxt_f = is_default(e)
+                flags = (bool(e["attn1"]), bool(e["attn2"]), bool(e["ff"]))
+            ok = (cur_a and nxt_a, cur_a and nxt_a, cur_f and nxt_f)
+            for c in range(3):
+                dead[b, c] = executed[b, c] and ok[c] and flags[c] and b not in self._tgate_average
+        return dead
 
     def _decide(self) -> np.ndarray:
         """Decision row of the current step: the reference's per-sub-block rule, evaluated through the same
@@ -450,11 +493,19 @@ class B200PixArtTransformer2D:
         executed = self._decide()
         self.last_executed = executed
         ex = np.ascontiguousarray(executed.reshape(-1))
+        dead = self._dead_stores(executed)
+        if (~executed.astype(np.bool_) & self._has_cache & ~self._cache_written).any():
+            raise RuntimeError("a cache slot whose store was skipped as dead is being reused: the schedule changed "
+                               "mid-generation (set skip_dead_cache_stores = False for such flows)")
+        self.last_dead = dead
+        self._dead_flat = np.ascontiguousarray(dead.reshape(-1))
+        ws["args"].cache_dead = self._dead_flat.ctypes.data_as(C.POINTER(C.c_uint8))
         n_l = C.c_int(0)
         _lib.check(lib.ecadk_pixart_blocks(self._handle, C.byref(ws["args"]),
                                            ex.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(n_l), st), "pixart_blocks")
         launches += n_l.value
         self._has_cache |= executed.astype(np.bool_)
+        self._cache_written = np.where(executed.astype(np.bool_), ~dead.astype(np.bool_), self._cache_written)
         if self._tgate_average:
             # cached_transformer_block.py:443-449: at gate_step - 1 the cache keeps (uncond + text) / 2
             if S % 2:

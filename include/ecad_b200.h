@@ -135,7 +135,7 @@ int ecadk_gemm_bias(const void* a, const void* w, const float* bias, void* out, 
                     int gelu, ecadk_stream_t stream);
 
 /* o = A W^T + bias;  cache = bf16(o);  x += gate * o  (gate = gate_table + gate_temb[sample], or 1 if NULL);
- * optional xb = bf16(x).  x fp32 [M,N] in place.
+ * optional xb = bf16(x).  x fp32 [M,N] in place.  cache may be NULL (store skipped).
  * Replaces attn.to_out[0] / ff.net[2] + "update the cache" + gated residual
  * (cached_transformer_block.py:357-358,388-389 and :244-246, :289, :318-320). */
 int ecadk_gemm_bias_gated_residual_cache(const void* a, const void* w, const float* bias, float* x, void* xb,
@@ -253,6 +253,11 @@ typedef struct {
   void* const* k2;       /* host array [num_layers]: bf16 [samples, heads, text_pad, 80] projected caption keys */
   void* const* v2;       /* host array [num_layers] */
   void* const* cache;    /* host array [num_layers*3]: bf16 [samples*tokens, dim] cached attn1/attn2/ff outputs */
+  const uint8_t* cache_dead; /* host array [num_layers*3] or NULL.  cache_dead[b*3+c] != 0: the caller knows (from the
+                          * schedule) that this slot is overwritten before any later step reads it - the next step
+                          * recomputes the sub-block, or the generation ends - so an EXECUTED sub-block skips the cache
+                          * store (the reference's `self.cached_* = out`, cached_transformer_block.py:357-358,388-389,
+                          * is a dead store then).  Ignored for reused sub-blocks. */
 } EcadkBlocksArgs;
 
 /* Runs blocks 0..num_layers-1.  executed[b*3 + c] != 0 -> compute sub-block c in {attn1, attn2, ff} of block b and
@@ -330,6 +335,10 @@ typedef struct {
   const float* rope_sin;
   void* const* cache_double; /* host array [num_layers*4]: attn [B*N,dim], context_attn [B*T,dim], ff [B*N,dim], ff_context [B*T,dim] */
   void* const* cache_single; /* host array [num_single_layers*3]: attn [B*(T+N),dim], proj_mlp (pre-GELU) [B*(T+N),4*dim], proj_out [B*(T+N),dim] */
+  const uint8_t* cache_dead; /* host array, same indexing as `executed`, or NULL: slots that are overwritten before any
+                              * later read.  Honoured for the epilogue side-stores (double blocks: attn pair, ff,
+                              * ff_context; single blocks: proj_out); single_attn / single_proj_mlp are produced straight
+                              * into their cache slots and are always written. */
 } EcadkFluxArgs;
 
 /* executed[(b)*3 + c]: rows 0..num_layers-1 = double blocks with c in {full_attn, full_ff, full_ff_context}, rows

@@ -65,3 +65,44 @@ def test_flux_graph_replay_equals_eager(cuda_device):
         a, b = eager.generate_images(emb)[0], graphed.generate_images(emb)[0]
         assert torch.equal(a, b), float((a - b).abs().max())
     assert graphed.diffusion_pipeline._graphs.captures == 1
+
+
+def test_dead_cache_store_elimination_is_invisible(cuda_device):
+    """Skipping the cache store of an executed sub-block whose slot is overwritten (or dropped) before any read must not
+    change a single bit of the result - for the paper's schedule, a TGATE schedule and a FLUX schedule."""
+    from ecad_b200.image_generator import B200FluxImageGenerator, B200PixArtAlphaImageGenerator
+    from ecad_b200.schedule import FluxCacheSchedule, schedule_from_packed
+    from ecad_b200.weights import (FluxConfig, PixArtConfig, flux_random_init_state_dict, random_init_state_dict,
+                                   synthetic_prompt_embeddings)
+    from golden_util import rows, row_by_path
+    from test_gpu_flux_parity import SMALL, _embeds, _schedule_flags
+
+    sd = random_init_state_dict(PixArtConfig(), 0)
+    emb = synthetic_prompt_embeddings(2, seed=2)
+    tgate = [r for r in rows() if (r.get("config") or {}).get("pipeline", {}).get("name") == "tgate" and r["NB"] == 28
+             and r["tokens"] == 256][0]
+    for row in (row_by_path("schedules_in_paper/pixart_alpha_256/ours_fast.json"), tgate):
+        outs, dead_total = [], []
+        for skip in (True, False):
+            seen = []
+            gen = B200PixArtAlphaImageGenerator(
+                cache_schedule=schedule_from_packed(row), state_dict=sd,
+                additional_callbacks=[lambda s, t, **kw: seen.append(int(gen.diffusion_pipeline.transformer.last_dead.sum()))])
+            gen.create_diffusion_pipeline().transformer.skip_dead_cache_stores = skip
+            outs.append(gen.generate_images(emb)[0])
+            dead_total.append(sum(seen))
+        assert torch.equal(outs[0], outs[1]), row["path"]
+        assert dead_total[0] > 0 and dead_total[1] == 0, (row["path"], dead_total)
+
+    cfg = FluxConfig(**SMALL)
+    steps, nrows = 6, cfg.num_layers + cfg.num_single_layers
+    fsd = flux_random_init_state_dict(cfg, seed=0)
+    femb = _embeds(2, 64, SMALL, seed=4)
+    outs = []
+    for skip in (True, False):
+        sched = FluxCacheSchedule.from_numpy(_schedule_flags(steps, nrows), steps, cfg.num_layers, cfg.num_single_layers,
+                                             "rand", top_level_config={"height": 256, "width": 192})
+        gen = B200FluxImageGenerator(cache_schedule=sched, state_dict=fsd, model_config=cfg)
+        gen.create_diffusion_pipeline().transformer.skip_dead_cache_stores = skip
+        outs.append(gen.generate_images(femb)[0])
+    assert torch.equal(outs[0], outs[1])
