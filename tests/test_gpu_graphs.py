@@ -106,3 +106,27 @@ def test_dead_cache_store_elimination_is_invisible(cuda_device):
         gen.create_diffusion_pipeline().transformer.skip_dead_cache_stores = skip
         outs.append(gen.generate_images(femb)[0])
     assert torch.equal(outs[0], outs[1])
+
+
+def test_latency_metrics_block(cuda_device, tmp_path):
+    """metrics.latency in the reference's layout (compute_latency.py:52-73), measured on the resident model."""
+    import json
+
+    from ecad_b200.image_generator import B200PixArtAlphaImageGenerator
+    from ecad_b200.metrics import annotate_schedule_file
+    from ecad_b200.schedule import schedule_from_packed
+    from ecad_b200.weights import synthetic_prompt_embeddings
+    from golden_util import row_by_path
+
+    row = row_by_path("schedules_in_paper/pixart_alpha_256/ours_fast.json")
+    sched = schedule_from_packed(row)
+    f = tmp_path / "ours_fast.json"
+    f.write_text(json.dumps(sched.to_dict()))
+    gen = B200PixArtAlphaImageGenerator(cache_schedule=sched)
+    emb = {k: v.cuda() for k, v in synthetic_prompt_embeddings(4).items()}
+    m = annotate_schedule_file(f, image_generator=gen, prompt_embeds=emb, num_samples=2, warmup_steps=1)
+    lat = m["latency"]
+    assert set(lat) == {"avg", "batch_size", "num_samples", "warmup_steps", "gpu", "warmups", "latencies"}
+    assert lat["batch_size"] == 4 and len(lat["latencies"]) == 2 and len(lat["warmups"]) == 1 and 0 < lat["avg"] < 1000
+    assert m["total_macs"] == row["total_macs"]
+    assert json.loads(f.read_text())["metrics"]["latency"]["gpu"] == lat["gpu"]
