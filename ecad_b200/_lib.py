@@ -39,6 +39,8 @@ EXPORTED_SYMBOLS = [
     "ecadk_axpy_f32",
     "ecadk_gemm_bias_f32",
     "ecadk_gemm_bias_headmajor_ex",
+    "ecadk_gemm2src_gated_residual_cache",
+    "ecadk_gemm_bias_dual",
     "ecadk_create",
     "ecadk_destroy",
     "ecadk_pixart_blocks",
@@ -198,6 +200,8 @@ def load() -> C.CDLL:
         "ecadk_axpy_f32": [p, p, f, sz, p],
         "ecadk_gemm_bias_f32": [p, p, p, p, i, i, i, i, i, p],
         "ecadk_gemm_bias_headmajor_ex": [p, p, p, p, p, p, i, i, i, i, i, i, i, i, i, p],
+        "ecadk_gemm2src_gated_residual_cache": [p, i, p, p, p, p, p, p, i, i, i, i, i, p],
+        "ecadk_gemm_bias_dual": [p, p, p, p, p, i, i, i, i, i, p],
         "ecadk_create": [i, C.POINTER(EcadkModelDesc), C.POINTER(EcadkBlockWeights), C.POINTER(p)],
         "ecadk_destroy": [p],
         "ecadk_pixart_blocks": [p, C.POINTER(EcadkBlocksArgs), C.POINTER(C.c_uint8), C.POINTER(i), p],

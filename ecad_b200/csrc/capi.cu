@@ -185,7 +185,8 @@ int num_sms() {
 // GEMM launcher
 // ---------------------------------------------------------------------------------------------------
 template <int BN, int EPI>
-int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const GemmParams& p,
+                     cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
   auto kern = gemm_bf16_kernel<BN, EPI>;
@@ -195,13 +196,13 @@ int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
   }
   const int tiles = ((p.M + kGemmBM - 1) / kGemmBM) * (p.N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, ta2, tb, p);
   return check_launch("gemm_bf16_kernel");
 }
 
 template <int BN, int EPI>
-int launch_gemm2_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tb_tail, const GemmParams& p,
-                      int tail, cudaStream_t stream) {
+int launch_gemm2_inst(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const CUtensorMap& tb_tail,
+                      const GemmParams& p, int tail, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<BN>;
   static bool configured = false;
   auto kern = gemm2_bf16_kernel<BN, EPI>;
@@ -212,7 +213,7 @@ int launch_gemm2_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
   const int tiles = ((p.M + 2 * kGemmBM - 1) / (2 * kGemmBM)) * ((p.N - tail) / BN + (tail ? 1 : 0));
   const int pairs = num_sms() / 2;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tb_tail, p, tail);
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, ta2, tb, tb_tail, p, tail);
   return check_launch("gemm2_bf16_kernel");
 }
 
@@ -255,9 +256,19 @@ int launch_gemm(const void* a, const void* w, GemmParams& p, cudaStream_t stream
   ECADK_REQUIRE(aligned16(a) && aligned16(w), "gemm: operands must be 16-byte aligned");
   const int group = gemm_cta_group(p.M, p.N);
   ProfScope prof(ECADK_PROF_GEMM, 2.0 * p.M * p.N * p.K, 0.0, stream);
-  CUtensorMap ta, tb;
-  int rc = make_tmap_bf16(&ta, a, p.M, p.K, p.K, kGemmBM, kGemmBK, 128);
-  if (rc) return rc;
+  CUtensorMap ta, ta2, tb;
+  int rc;
+  if (p.a2 != nullptr) {  // A = [a (k1 columns) | a2 (K - k1 columns)], each with its own row pitch
+    ECADK_REQUIRE(p.k1 > 0 && p.k1 < p.K && p.k1 % kGemmBK == 0 && aligned16(p.a2),
+                  "gemm: split A needs 0 < k1=%d < K=%d, a multiple of %d", p.k1, p.K, kGemmBK);
+    if ((rc = make_tmap_bf16(&ta, a, p.M, p.k1, p.k1, kGemmBM, kGemmBK, 128))) return rc;
+    if ((rc = make_tmap_bf16(&ta2, p.a2, p.M, p.K - p.k1, p.K - p.k1, kGemmBM, kGemmBK, 128))) return rc;
+    p.kb_split = p.k1 / kGemmBK;
+  } else {
+    if ((rc = make_tmap_bf16(&ta, a, p.M, p.K, p.K, kGemmBM, kGemmBK, 128))) return rc;
+    ta2 = ta;
+    p.kb_split = p.K / kGemmBK;
+  }
   if (group == 2) {
     // ECADK_GEMM_TAIL=0 disables the 256-wide + 128-wide-tail tiling (A/B measurements)
     static const bool use_tail = [] {
@@ -269,24 +280,24 @@ int launch_gemm(const void* a, const void* w, GemmParams& p, cudaStream_t stream
       CUtensorMap tb_tail;
       if ((rc = make_tmap_bf16(&tb, w, p.N, p.K, p.K, 128, kGemmBK, 128))) return rc;
       if ((rc = make_tmap_bf16(&tb_tail, w, p.N, p.K, p.K, 64, kGemmBK, 128))) return rc;
-      return launch_gemm2_inst<256, EPI>(ta, tb, tb_tail, p, 128, stream);
+      return launch_gemm2_inst<256, EPI>(ta, ta2, tb, tb_tail, p, 128, stream);
     }
     const int bn = pick_bn((p.M + 2 * kGemmBM - 1) / (2 * kGemmBM), p.N, num_sms() / 2);
     ECADK_REQUIRE(bn != 0, "gemm: no tile width divides N=%d", p.N);
     if ((rc = make_tmap_bf16(&tb, w, p.N, p.K, p.K, bn / 2, kGemmBK, 128))) return rc;
     switch (bn) {
-      case 256: return launch_gemm2_inst<256, EPI>(ta, tb, tb, p, 0, stream);
-      case 192: return launch_gemm2_inst<192, EPI>(ta, tb, tb, p, 0, stream);
-      default: return launch_gemm2_inst<128, EPI>(ta, tb, tb, p, 0, stream);
+      case 256: return launch_gemm2_inst<256, EPI>(ta, ta2, tb, tb, p, 0, stream);
+      case 192: return launch_gemm2_inst<192, EPI>(ta, ta2, tb, tb, p, 0, stream);
+      default: return launch_gemm2_inst<128, EPI>(ta, ta2, tb, tb, p, 0, stream);
     }
   }
   const int bn = pick_bn((p.M + kGemmBM - 1) / kGemmBM, p.N, num_sms());
   ECADK_REQUIRE(bn != 0, "gemm: no tile width divides N=%d", p.N);
   if ((rc = make_tmap_bf16(&tb, w, p.N, p.K, p.K, bn, kGemmBK, 128))) return rc;
   switch (bn) {
-    case 256: return launch_gemm_inst<256, EPI>(ta, tb, p, stream);
-    case 192: return launch_gemm_inst<192, EPI>(ta, tb, p, stream);
-    default: return launch_gemm_inst<128, EPI>(ta, tb, p, stream);
+    case 256: return launch_gemm_inst<256, EPI>(ta, ta2, tb, p, stream);
+    case 192: return launch_gemm_inst<192, EPI>(ta, ta2, tb, p, stream);
+    default: return launch_gemm_inst<128, EPI>(ta, ta2, tb, p, stream);
   }
 }
 
@@ -740,6 +751,43 @@ int ecadk_gemm_bias_gated_residual_cache(const void* a, const void* w, const flo
   return launch_gemm<EPI_GATED_RESIDUAL>(a, w, p, static_cast<cudaStream_t>(stream));
 }
 
+int ecadk_gemm2src_gated_residual_cache(const void* a, int k1, const void* a2, const void* w, const float* bias,
+                                        float* x, void* cache, const float* gate_temb, int temb_stride, int tokens,
+                                        int m, int n, int k, ecadk_stream_t stream) {
+  ECADK_REQUIRE(x && aligned16(x) && (cache == nullptr || aligned16(cache)) && a2 != nullptr,
+                "gemm2src_gated_residual: bad x/cache/a2");
+  ECADK_REQUIRE(tokens > 0 && tokens % 32 == 0, "gemm2src_gated_residual: tokens=%d must be a multiple of 32", tokens);
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = m; p.N = n; p.K = k;
+  p.a2 = a2;
+  p.k1 = k1;
+  p.bias = bias;
+  p.x = x;
+  p.cache = static_cast<__nv_bfloat16*>(cache);
+  p.gate_temb = gate_temb;
+  p.temb_stride = temb_stride;
+  p.tokens = tokens;
+  return launch_gemm<EPI_GATED_RESIDUAL>(a, w, p, static_cast<cudaStream_t>(stream));
+}
+
+int ecadk_gemm_bias_dual(const void* a, const void* w, const float* bias, void* out_pre, void* out_gelu, int m, int n,
+                         int k, int ldo_pre, int ldo_gelu, ecadk_stream_t stream) {
+  ECADK_REQUIRE(out_gelu != nullptr && aligned16(out_gelu) && (out_pre == nullptr || aligned16(out_pre)),
+                "gemm_bias_dual: bad outputs");
+  ECADK_REQUIRE(ldo_gelu >= n && ldo_gelu % 8 == 0 && (out_pre == nullptr || (ldo_pre >= n && ldo_pre % 8 == 0)),
+                "gemm_bias_dual: row pitches must be >= n and multiples of 8");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = m; p.N = n; p.K = k;
+  p.bias = bias;
+  p.out = static_cast<__nv_bfloat16*>(out_pre);
+  p.ldo = ldo_pre;
+  p.out2 = static_cast<__nv_bfloat16*>(out_gelu);
+  p.ldo2 = ldo_gelu;
+  return launch_gemm<EPI_BIAS_DUAL>(a, w, p, static_cast<cudaStream_t>(stream));
+}
+
 int ecadk_gemm_bias_headmajor(const void* a, const void* w, const float* bias, void* out0, void* out1, void* out2,
                               int n_parts, int heads, int tokens, int tokens_pad, int m, int k,
                               ecadk_stream_t stream) {
@@ -891,8 +939,12 @@ int ecadk_flux_blocks(ecadk_flux_handle_t h, const EcadkFluxArgs* a, const uint8
     if (ex_attn || ex_mlp) {
       if ((rc = cat.layer_norm(a->h_cat, ms + 0 * D, ms + 1 * D))) return rc;
     }
-    if (ex_mlp) {  // proj_mlp, cached PRE-activation
-      if ((rc = ecadk_gemm_bias(a->h_cat, w.w_mlp, w.b_mlp, c_mlp, B * S, F, D, F, 0, stream_))) return rc;
+    const uint8_t* dead = a->cache_dead;
+    if (ex_mlp) {
+      // proj_mlp: ONE GEMM writes the pre-activation into its cache slot (what the reference caches; skipped when
+      // that store is dead) and GELU(tanh) of it into the operand buffer proj_out reads
+      void* s_mlp = (dead && dead[r + 1]) ? nullptr : c_mlp;
+      if ((rc = ecadk_gemm_bias_dual(a->h_cat, w.w_mlp, w.b_mlp, s_mlp, a->cat, B * S, F, D, F, F, stream_))) return rc;
       ++launches;
     }
     if (ex_attn) {
@@ -906,16 +958,18 @@ int ecadk_flux_blocks(ecadk_flux_handle_t h, const EcadkFluxArgs* a, const uint8
       launches += 3;
     }
     if (ex_out) {
-      // cat = [attn | GELU(proj_mlp)] from the (fresh or reused) cached tensors, then proj_out + gated residual
-      if ((rc = ecadk_strided_unary(c_attn, a->cat, B * S, D, D, 5 * D, 0, stream_))) return rc;
-      if ((rc = ecadk_strided_unary(c_mlp, static_cast<__nv_bfloat16*>(a->cat) + D, B * S, F, F, 5 * D, 1, stream_)))
-        return rc;
+      // proj_out over [attn | GELU(proj_mlp)]: the A operand is read from the two buffers directly (split along K), no
+      // concatenated copy.  A reused proj_mlp is re-activated from its pre-GELU cache.
+      if (!ex_mlp) {
+        if ((rc = ecadk_strided_unary(c_mlp, a->cat, B * S, F, F, F, 1, stream_))) return rc;
+        ++launches;
+      }
       if ((rc = cat.flush())) return rc;  // the epilogue below updates x in place: pending reuses must land first
-      void* s_out = (a->cache_dead && a->cache_dead[r + 2]) ? nullptr : c_out;
-      if ((rc = ecadk_gemm_bias_gated_residual_cache(a->cat, w.w_out, w.b_out, a->x_cat, nullptr, s_out, nullptr,
-                                                     ms + 2 * D, MS, S, B * S, D, 5 * D, stream_)))
+      void* s_out = (dead && dead[r + 2]) ? nullptr : c_out;
+      if ((rc = ecadk_gemm2src_gated_residual_cache(c_attn, D, a->cat, w.w_out, w.b_out, a->x_cat, s_out, ms + 2 * D, MS,
+                                                    S, B * S, D, 5 * D, stream_)))
         return rc;
-      launches += 3;
+      ++launches;
     } else {
       if ((rc = cat.push(c_out, ms + 2 * D))) return rc;
     }

@@ -21,14 +21,22 @@ enum GemmEpilogue : int {
   EPI_HEADMAJOR = 3,       // out[part][sample][head][token][head_pad] = bf16(acc + bias)   (Q/K/V scatter)
   EPI_UNPATCHIFY = 4,      // fp32 out[s][c][2i+p][2j+q] = acc + bias for the first unp_cols columns (final layer)
   EPI_BIAS_F32 = 5,        // fp32 out[row, col] = acc + bias for col < f32_cols, row pitch ldo (embedders, FLUX head)
+  EPI_BIAS_DUAL = 6,       // o = acc + bias; out = bf16(o) (optional: the pre-activation cache); out2 = bf16(gelu_tanh(o))
 };
 
 struct GemmParams {
   int M, N, K;
   const float* bias;  // [N] fp32 (may be null)
-  // EPI_BIAS / EPI_BIAS_GELU
+  // A operand split along K: k-blocks [0, kb_split) come from the first tensor map, the rest from a second matrix
+  // (FLUX single-stream proj_out reads [attn | GELU(mlp)] from two buffers instead of a concatenated copy)
+  int kb_split;
+  const void* a2;  // host side only: second A matrix [M, K - k1] (row pitch K - k1), or null
+  int k1;          // host side only: columns taken from the first A matrix
+  // EPI_BIAS / EPI_BIAS_GELU / EPI_BIAS_DUAL
   __nv_bfloat16* out;
   int ldo;
+  __nv_bfloat16* out2;  // EPI_BIAS_DUAL: GELU(tanh) of the same values
+  int ldo2;
   // EPI_GATED_RESIDUAL
   float* x;                 // [M,N] fp32 residual stream, updated in place
   __nv_bfloat16* xb;        // optional bf16 shadow of the updated stream (feeds the next projection), or null
@@ -153,6 +161,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
           w.x = pack_bf16x2(o.x, o.y);
           w.y = pack_bf16x2(o.z, o.w);
           *reinterpret_cast<uint2*>(p.out + static_cast<size_t>(row) * p.ldo + col) = w;
+        } else if constexpr (EPI == EPI_BIAS_DUAL) {
+          uint2 w;
+          if (p.out != nullptr) {
+            w.x = pack_bf16x2(o.x, o.y);
+            w.y = pack_bf16x2(o.z, o.w);
+            *reinterpret_cast<uint2*>(p.out + static_cast<size_t>(row) * p.ldo + col) = w;
+          }
+          w.x = pack_bf16x2(gelu_tanh(o.x), gelu_tanh(o.y));
+          w.y = pack_bf16x2(gelu_tanh(o.z), gelu_tanh(o.w));
+          *reinterpret_cast<uint2*>(p.out2 + static_cast<size_t>(row) * p.ldo2 + col) = w;
         } else if constexpr (EPI == EPI_GATED_RESIDUAL) {
           const size_t off = static_cast<size_t>(row) * p.N + col;
           if (p.cache != nullptr) {  // null: the caller knows this slot is overwritten before anyone reads it
@@ -221,8 +239,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const GemmParams p) {
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
+                 const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -276,7 +294,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           uint8_t* sa = smem + stage * Cfg::kStage;
           uint8_t* sb = sa + Cfg::kStageA;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStage);
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kGemmBK, m0);
+          if (kb < p.kb_split) {
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kGemmBK, m0);
+          } else {
+            tma_load_2d(sa, &tmap_a2, &full_bar[stage], (kb - p.kb_split) * kGemmBK, m0);
+          }
           tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kGemmBK, n0);
           if (++stage == STAGES) {
             stage = 0;
@@ -375,8 +397,9 @@ struct Gemm2Cfg {
 
 template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
-gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                  const __grid_constant__ CUtensorMap tmap_b_tail, const GemmParams p, const int tail) {
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
+                  const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_b_tail,
+                  const GemmParams p, const int tail) {
   // `tail` (0 or 128, only with BN = 256): N = k*256 + 128 is covered by k full-width tiles plus one 128-wide tile per
   // row block, so N = 1152 / 3456 run at the L2->SM traffic per FLOP of 256-wide tiles instead of 192-wide ones.
   using Cfg = Gemm2Cfg<BN>;
@@ -445,7 +468,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           uint8_t* sa = smem + stage * Cfg::kStage;
           uint8_t* sb = sa + Cfg::kStageA;
           if (cta == 0) mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
-          tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], kb * kGemmBK, m0);
+          if (kb < p.kb_split) {
+            tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], kb * kGemmBK, m0);
+          } else {
+            tma_load_2d_2sm(sa, &tmap_a2, &full_bar[stage], (kb - p.kb_split) * kGemmBK, m0);
+          }
           tma_load_2d_2sm(sb, tb, &full_bar[stage], kb * kGemmBK, n0);
           if (++stage == STAGES) {
             stage = 0;

@@ -229,7 +229,7 @@ class B200FluxTransformer2D:
         ws["attn_img"] = torch.empty(B * N, D, device=dev, dtype=bf)
         ws["attn_txt"] = torch.empty(B * T, D, device=dev, dtype=bf)
         ws["ffh"] = torch.empty(B * max(N, T), 4 * D, device=dev, dtype=bf)
-        ws["cat"] = torch.empty(B * S, 5 * D, device=dev, dtype=bf)
+        ws["cat"] = torch.empty(B * S, 4 * D, device=dev, dtype=bf)  # GELU(proj_mlp) operand of proj_out
         ws["mod"] = torch.empty(B, self.mod_cols, device=dev, dtype=f32)
         ws["lat_bf"] = torch.empty(B * N, cfg.in_channels, device=dev, dtype=bf)
         ws["enc_bf"] = torch.empty(B * T, cfg.joint_attention_dim, device=dev, dtype=bf)

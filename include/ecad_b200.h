@@ -201,6 +201,19 @@ int ecadk_silu_f32_bf16(const float* in, void* out, size_t n, ecadk_stream_t str
 int ecadk_gemm_bias_f32(const void* a, const void* w, const float* bias, float* out, int m, int n, int k, int ldo,
                         int out_cols, ecadk_stream_t stream);
 
+/* ecadk_gemm_bias_gated_residual_cache (per-sample gate vector only) whose A operand is split along K between two
+ * matrices: columns [0, k1) from a [M, k1], columns [k1, k) from a2 [M, k - k1] (k1 % 64 == 0).  Replaces
+ * torch.cat([attn_output, mlp_hidden_states], dim=2) + proj_out + gate + residual of the FLUX single-stream block
+ * (cached_flux_transformer_block.py:113-124) without materialising the concatenation. */
+int ecadk_gemm2src_gated_residual_cache(const void* a, int k1, const void* a2, const void* w, const float* bias,
+                                        float* x, void* cache, const float* gate_temb, int temb_stride, int tokens,
+                                        int m, int n, int k, ecadk_stream_t stream);
+
+/* o = A W^T + bias; out_pre = bf16(o) (may be NULL); out_gelu = bf16(GELU_tanh(o)).  Replaces proj_mlp + act_mlp of the
+ * FLUX single-stream block, whose cache holds the PRE-activation (cached_flux_transformer_block.py:107-110). */
+int ecadk_gemm_bias_dual(const void* a, const void* w, const float* bias, void* out_pre, void* out_gelu, int m, int n,
+                         int k, int ldo_pre, int ldo_gelu, ecadk_stream_t stream);
+
 /* ecadk_gemm_bias_headmajor with explicit head geometry and a token offset inside the head-major sequence:
  * row r -> sample r / tokens, token (r % tokens) + tok_offset of a sequence of pitch tokens_pad. */
 int ecadk_gemm_bias_headmajor_ex(const void* a, const void* w, const float* bias, void* out0, void* out1, void* out2,
@@ -325,7 +338,7 @@ typedef struct {
   void* attn_img;  /* bf16 scratch [B*N, dim] */
   void* attn_txt;  /* bf16 scratch [B*T, dim] */
   void* ffh;       /* bf16 scratch [B*max(N,T), 4*dim] */
-  void* cat;       /* bf16 scratch [B*(T+N), 5*dim]: [attn | GELU(mlp)] of the single-stream blocks */
+  void* cat;       /* bf16 scratch [B*(T+N), 4*dim]: GELU(proj_mlp) of the single-stream block being executed */
   const float* mod;  /* fp32 [B, mod_stride]: all modulation vectors of this step, one row per sample.  Column layout:
                       * double block b: [b*12*dim, +6*dim) image stream (norm1.linear), then +6*dim text stream
                       * (norm1_context.linear), each = shift_msa|scale_msa|gate_msa|shift_mlp|scale_mlp|gate_mlp;

@@ -144,3 +144,52 @@ def test_headmajor_ex_joint_sequence_and_vector_only_gate(cuda_device):
     ref_h = torch.nn.functional.layer_norm(x, (D,), eps=1e-6) * (1 + mod[:, D:2 * D].repeat_interleave(N, 0)) + \
         mod[:, :D].repeat_interleave(N, 0)
     assert _rel(h, ref_h) < 6e-3
+
+
+@pytest.mark.parametrize("m", [300, 20480])  # 1-CTA and 2-CTA (cta_group::2) GEMM kernels
+def test_dual_output_gemm_and_split_a_gemm(cuda_device, m):
+    from ecad_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(m)
+    D, F = 512, 2048
+    st = _lib.stream_ptr()
+    # proj_mlp: pre-activation into the cache + GELU into the proj_out operand, from one GEMM
+    a = _bf(torch.randn(m, D, device="cuda", generator=g))
+    w = _bf(torch.randn(F, D, device="cuda", generator=g) / math.sqrt(D))
+    b = torch.randn(F, device="cuda", generator=g)
+    pre = torch.full((m, F), float("nan"), device="cuda", dtype=torch.bfloat16)
+    act = torch.full((m, F), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.ecadk_gemm_bias_dual(a.data_ptr(), w.data_ptr(), b.data_ptr(), pre.data_ptr(), act.data_ptr(), m, F, D,
+                                        F, F, st))
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().T + b
+    assert _rel(pre, ref) < 1e-2 and _rel(act, torch.nn.functional.gelu(ref, approximate="tanh")) < 1e-2
+    act2 = torch.zeros_like(act)
+    _lib.check(lib.ecadk_gemm_bias_dual(a.data_ptr(), w.data_ptr(), b.data_ptr(), None, act2.data_ptr(), m, F, D, F, F, st))
+    torch.cuda.synchronize()
+    assert torch.equal(act, act2)  # the pre-activation store is optional (dead cache slot)
+    # proj_out over [attn | GELU(mlp)] read from two buffers, gated residual + cache
+    tokens, samples = (m // 4, 4) if m % 128 == 0 else (m // 3 // 32 * 32 or 32, 0)
+    if samples == 0:
+        m2 = 288
+        tokens, samples = 96, 3
+    else:
+        m2 = m
+    a1 = _bf(torch.randn(m2, D, device="cuda", generator=g))
+    a2 = _bf(torch.randn(m2, F, device="cuda", generator=g))
+    wo = _bf(torch.randn(D, D + F, device="cuda", generator=g) / math.sqrt(D + F))
+    bo = torch.randn(D, device="cuda", generator=g)
+    x = torch.randn(m2, D, device="cuda", generator=g)
+    x0 = x.clone()
+    gate = torch.randn(samples, 3 * D, device="cuda", generator=g)
+    cache = torch.zeros(m2, D, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.ecadk_gemm2src_gated_residual_cache(a1.data_ptr(), D, a2.data_ptr(), wo.data_ptr(), bo.data_ptr(),
+                                                       x.data_ptr(), cache.data_ptr(), gate[:, 2 * D:].data_ptr(), 3 * D,
+                                                       tokens, m2, D, D + F, st))
+    torch.cuda.synchronize()
+    o = torch.cat([a1, a2], dim=1).float() @ wo.float().T + bo
+    assert _rel(cache, o) < 1e-2
+    assert _rel(x, x0 + gate[:, 2 * D:].repeat_interleave(tokens, 0) * o) < 2e-5 * max(1.0, float(o.abs().max()))
+    rc = lib.ecadk_gemm2src_gated_residual_cache(a1.data_ptr(), 100, a2.data_ptr(), wo.data_ptr(), bo.data_ptr(),
+                                                 x.data_ptr(), None, gate.data_ptr(), 3 * D, tokens, m2, D, D + F, st)
+    assert rc != 0 and b"k1" in lib.ecadk_last_error()
