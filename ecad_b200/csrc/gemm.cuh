@@ -218,22 +218,32 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
   int limit = n_chunks;  // chunks past the real output columns of the zero-padded heads carry nothing to store
   if constexpr (EPI == EPI_UNPATCHIFY) limit = min(n_chunks, (p.unp_cols - n0 + 31) / 32);
   if constexpr (EPI == EPI_BIAS_F32) limit = min(n_chunks, (p.f32_cols - n0 + 31) / 32);
+  // Chunk assignment: the two warps of a lane quarter split the tile's columns into two CONTIGUOUS halves (ECADK_EPI_
+  // INTERLEAVE=1 at build time restores the every-second-chunk split): a warp then walks adjacent 128-byte pieces of
+  // the same 32 rows, which keeps its DRAM pages open across iterations.
+#ifdef ECADK_EPI_INTERLEAVE
+  const int c_begin = parity, c_step = 2, c_end = limit;
+#else
+  const int half_chunks = (n_chunks + 1) / 2;
+  const int c_begin = parity * half_chunks, c_step = 1;
+  const int c_end = min(limit, c_begin + half_chunks);
+#endif
   if constexpr (EPI == EPI_GATED_RESIDUAL) {
     float4 xa[8], xb_[8];
-    if (parity < limit) load_x(parity, xa);
+    if (c_begin < c_end) load_x(c_begin, xa);
 #pragma unroll 1
-    for (int c = parity; c < limit; c += 4) {
-      if (c + 2 < limit) load_x(c + 2, xb_);
+    for (int c = c_begin; c < c_end; c += 2 * c_step) {
+      if (c + c_step < c_end) load_x(c + c_step, xb_);
       process(c, xa);
-      if (c + 2 < limit) {
-        if (c + 4 < limit) load_x(c + 4, xa);
-        process(c + 2, xb_);
+      if (c + c_step < c_end) {
+        if (c + 2 * c_step < c_end) load_x(c + 2 * c_step, xa);
+        process(c + c_step, xb_);
       }
     }
   } else {
     const float4 none[8] = {};
 #pragma unroll 1
-    for (int c = parity; c < limit; c += 2) process(c, none);
+    for (int c = c_begin; c < c_end; c += c_step) process(c, none);
   }
 }
 
