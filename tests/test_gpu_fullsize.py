@@ -97,3 +97,51 @@ def test_config5_flux_full_size_reuse_step_reproduces_dense_step(cuda_device):
     assert torch.equal(outs[2], outs[0])                 # recomputing everything again is deterministic
     assert torch.equal(outs[0][:2], outs[0][2:])         # sample independence at full size
     assert int(model.last_dead.sum()) > 0                # last step: every epilogue cache store is dead
+
+
+@pytest.mark.parametrize("name,sample_size,batch,text_tokens", [("config3", 64, 16, 120), ("config4", 128, 8, 300)])
+def test_config3_config4_full_model_forward_matches_oracle_on_sampled_rows(cuda_device, name, sample_size, batch,
+                                                                            text_tokens):
+    """BASELINE configs 3 (PixArt-alpha 512x512, batch 16) and 4 (PixArt-sigma 1024x1024, 300-token captions, batch 8)
+    at FULL model depth and batch: a dense forward, then a forward that reuses everything.  The oracle runs only the
+    CFG pair of one prompt (samples are independent); the other rows are covered by the repeat/independence check."""
+    from ecad_b200.schedule import PixArtCacheSchedule
+    from ecad_b200.transformer import B200PixArtTransformer2D, SequentialDiTScheduler
+    from ecad_b200.weights import PixArtConfig, random_init_state_dict, synthetic_prompt_embeddings
+    from oracle.pixart_oracle import OracleConfig, OracleSchedule, PixArtOracle
+
+    cfg = PixArtConfig(sample_size=sample_size, use_additional_conditions=False)
+    sd = random_init_state_dict(cfg, seed=5)
+    emb = synthetic_prompt_embeddings(batch, text_tokens=text_tokens, seed=6)
+    lat = torch.randn(batch, 4, sample_size, sample_size, generator=torch.Generator().manual_seed(7))
+    lat[batch - 1] = lat[0]                                  # last prompt repeats prompt 0 (independence check)
+    for k in emb:
+        emb[k][batch - 1] = emb[k][0]
+    x_in = torch.cat([lat, lat])
+    e_in = torch.cat([emb["negative_prompt_embeds"], emb["prompt_embeds"]])
+    m_in = torch.cat([emb["negative_prompt_attention_mask"], emb["prompt_attention_mask"]])
+    S = 2 * batch
+    ts = torch.full((S,), 649, dtype=torch.int64)
+    flags = np.ones((2, 28, 3), bool)
+    flags[1] = False
+    sched = PixArtCacheSchedule.from_numpy(flags, 2, 28, "dense_then_reuse")
+    tr = B200PixArtTransformer2D(sd, cfg, SequentialDiTScheduler(2), sched)
+    kw = dict(encoder_hidden_states=e_in.cuda(), encoder_attention_mask=m_in.cuda(), timestep=ts.cuda(),
+              added_cond_kwargs={"resolution": None, "aspect_ratio": None}, return_dict=False)
+    out0 = tr(x_in.cuda(), **kw)[0].cpu()
+    assert tr.last_executed.all()
+    sched.per_step_callback(0)
+    out1 = tr(x_in.cuda(), **kw)[0].cpu()
+    assert not tr.last_executed.any()
+
+    rows = [0, batch]                                        # uncond + cond sample of prompt 0
+    ocfg = OracleConfig(sample_size=sample_size, use_additional_conditions=False)
+    oracle = PixArtOracle(sd, ocfg, OracleSchedule.from_flags(flags))
+    ref0 = oracle.forward(x_in[rows], e_in[rows], ts[rows], None, m_in[rows])
+    oracle.cache_schedule.per_step_callback(0)
+    ref1 = oracle.forward(x_in[rows], e_in[rows], ts[rows], None, m_in[rows])
+    for got, ref in ((out0, ref0), (out1, ref1)):
+        rel = float((got[rows] - ref).abs().max() / ref.abs().max())
+        assert rel <= 1e-2 and _cos(got[rows], ref) >= 0.9999, (name, rel, _cos(got[rows], ref))
+    assert torch.isfinite(out0).all() and torch.isfinite(out1).all()
+    assert torch.equal(out0[batch - 1], out0[0]) and torch.equal(out0[S - 1], out0[batch])  # repeated prompt, same result
