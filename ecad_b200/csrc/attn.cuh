@@ -778,7 +778,8 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
   uint64_t* p_full = bars + 12;   // [2]
   uint64_t* o_full = bars + 14;   // [2] one phase per item
   uint64_t* s_empty = bars + 16;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* p_half = bars + 18;   // [2] the first 32 keys of both row halves of P are in TMEM (P V can start on them)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -795,6 +796,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 8);
+      mbar_init(&p_half[i], 8);
       mbar_init(&o_full[i], 1);
       mbar_init(&s_empty[i], 8);
     }
@@ -864,17 +866,21 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
         for (int k = 0; k < Cfg::kC2 / 16; ++k) umma_bf16_ss(d, dq2 + 2 * k, dk2 + 2 * k, idesc_s, 1);
         umma_commit(&s_full[t]);
       };
-      auto issue_pv = [&](int t, int st, bool accumulate) {
+      // P V of one key block in two parts: part 0 covers the 16-key steps whose P is written FIRST by the softmax warps
+      // (keys 0..31 by the "half 0" threads, 64..95 by the "half 1" threads), part 1 the rest - so the tensor core
+      // starts on a tile's P V while the second half of its exponentials is still being computed
+      auto issue_pv = [&](int t, int st, bool accumulate, int part) {
         const uint32_t vb = sbase + Cfg::kV + st * Cfg::kKStage;
         const uint32_t p_tmem = tmem + 256 * t;
         const uint32_t o_tmem = tmem + 256 * t + 128;
 #pragma unroll
-        for (int ks = 0; ks < kFlashKB / 16; ++ks) {
-          const uint64_t dv64 = make_smem_desc(vb + ks * 16 * 128, kFlashKB * 128, 1024, kLayoutSW128);
-          const uint32_t acc = (accumulate || ks != 0) ? 1u : 0u;
+        for (int i = 0; i < 4; ++i) {
+          const int ks = (i >> 1) * 4 + part * 2 + (i & 1);  // part 0: 0,1,4,5   part 1: 2,3,6,7
+          const uint32_t acc = (accumulate || part != 0 || i != 0) ? 1u : 0u;
           if constexpr (HD == 128) {
             // both 64-column swizzle atoms of V in ONE N = 128 instruction (LBO = atom stride along the head dim):
             // two N = 64 instructions cost about as much as two N = 128 ones (measured with ECADK_ATTN_TIMING)
+            const uint64_t dv64 = make_smem_desc(vb + ks * 16 * 128, kFlashKB * 128, 1024, kLayoutSW128);
             umma_bf16_ts(o_tmem, p_tmem + ks * 8, dv64, idesc_o128, acc);
           } else {
             const uint64_t dv = make_smem_desc(vb + ks * 16 * 32, kFlashKB * 32, 256, kLayoutSW32);
@@ -888,9 +894,12 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
       uint32_t pend_par = 0;
       auto flush_pending = [&]() {
         if (!pend) return;
+        mbar_wait(&p_half[1], pend_par);
+        tc_fence_after();
+        issue_pv(1, pend_st, pend_acc, 0);
         mbar_wait(&p_full[1], pend_par);
         tc_fence_after();
-        issue_pv(1, pend_st, pend_acc);
+        issue_pv(1, pend_st, true, 1);
         umma_commit(&v_empty[pend_st]);
         if (pend_last) umma_commit(&o_full[1]);
         pend = false;
@@ -923,6 +932,9 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
           ATTN_T(m4);
           mbar_wait(&v_full[st], ring_ph);
           ATTN_T(m5);
+          mbar_wait(&p_half[0], blk_par);
+          tc_fence_after();
+          issue_pv(0, st, j != 0, 0);
           mbar_wait(&p_full[0], blk_par);
           tc_fence_after();
           ATTN_T(m6);
@@ -932,7 +944,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
           ATTN_ACC(3, m3, m4);  // issue QK1
           ATTN_ACC(4, m4, m5);  // wait V
           ATTN_ACC(5, m5, m6);  // wait P0
-          issue_pv(0, st, j != 0);
+          issue_pv(0, st, true, 1);
           if (j == nkb - 1) umma_commit(&o_full[0]);
           pend = true;
           pend_st = st;
@@ -1033,6 +1045,12 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
           uint32_t pk[16];
           softmax_chunk_exp_reg<HAS_BIAS>(v[c], pk, sum2, m_eff, p.scale_log2e);
           tmem_st_32x16(t_row + half * 32 + c * 16, pk);  // P of keys [64*half + 32c, +32) as bf16 pairs
+          if (c == 0) {  // first 32 keys of this half are in TMEM: let the MMA warp start P V on them
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_half[t]);
+          }
         }
         {
           float s_lo, s_hi;
