@@ -108,6 +108,15 @@ class B200FluxTransformer2D:
             return cls(None, config, dit_scheduler, cache_schedule, device, device_init_seed=seed)
         return cls(flux_random_init_state_dict(config, seed), config, dit_scheduler, cache_schedule, device)
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, dit_scheduler=None, cache_schedule=None, **kwargs):
+        """Keyword surface of the reference's from_pretrained (flux_transformer_2d_edited.py:104-150); loads a local
+        diffusers-format (sharded) safetensors checkpoint."""
+        from .weights import load_diffusers_state_dict
+
+        sd = load_diffusers_state_dict(pretrained_model_name_or_path)
+        return cls(sd, kwargs.get("config", FluxConfig()), dit_scheduler, cache_schedule, kwargs.get("device", "cuda:0"))
+
     # ------------------------------------------------------------------------------------------------
     def _pack_weights(self, sd) -> None:
         dev, cfg = self.device, self.cfg

@@ -140,17 +140,11 @@ class B200PixArtTransformer2D:
     @classmethod
     def from_pretrained(cls, pretrained_model_name_or_path, dit_scheduler=None, cache_schedule=None, **kwargs):
         """Same keyword surface as the reference's from_pretrained (:104-117); loads a diffusers-format state dict
-        (``diffusion_pytorch_model.safetensors`` / ``.bin``) from a local directory - there is no network here."""
-        from pathlib import Path
+        (``diffusion_pytorch_model*.safetensors`` incl. sharded checkpoints, or ``.bin``) from a local directory."""
+        from .weights import load_diffusers_state_dict
 
-        path = Path(pretrained_model_name_or_path)
-        cand = [path / "diffusion_pytorch_model.bin", path / "transformer" / "diffusion_pytorch_model.bin"]
-        for f in cand:
-            if f.exists():
-                sd = torch.load(f, map_location="cpu")
-                return cls(sd, kwargs.get("config", PixArtConfig()), dit_scheduler, cache_schedule,
-                           kwargs.get("device", "cuda:0"))
-        raise FileNotFoundError(f"no diffusers-format transformer weights under {path}")
+        sd = load_diffusers_state_dict(pretrained_model_name_or_path)
+        return cls(sd, kwargs.get("config", PixArtConfig()), dit_scheduler, cache_schedule, kwargs.get("device", "cuda:0"))
 
     def _pack_weights(self, sd: dict[str, torch.Tensor]) -> None:
         dev, cfg = self.device, self.cfg

@@ -165,3 +165,31 @@ def flux_random_init_state_dict(cfg: FluxConfig = FluxConfig(), seed: int = 0) -
     _linear(sd, "norm_out.linear", 2 * D, D, gen)
     _linear(sd, "proj_out", cfg.in_channels, D, gen)
     return sd
+
+
+def load_diffusers_state_dict(path) -> dict[str, torch.Tensor]:
+    """State dict of a diffusers-format transformer directory (or its parent pipeline directory): single or sharded
+    ``diffusion_pytorch_model*.safetensors`` (with ``.index.json``) or a ``.bin``.  Local files only - the reference's
+    ``from_pretrained`` (pixart_transformer_2d_edited.py:104-117, flux_transformer_2d_edited.py:104-150) resolves hub
+    names, which needs a network this environment does not have."""
+    import json
+    from pathlib import Path
+
+    root = Path(path)
+    for d in (root, root / "transformer"):
+        if not d.is_dir():
+            continue
+        index = d / "diffusion_pytorch_model.safetensors.index.json"
+        single = d / "diffusion_pytorch_model.safetensors"
+        legacy = d / "diffusion_pytorch_model.bin"
+        if index.exists() or single.exists():
+            from safetensors.torch import load_file
+
+            files = sorted(set(json.loads(index.read_text())["weight_map"].values())) if index.exists() else [single.name]
+            sd: dict[str, torch.Tensor] = {}
+            for f in files:
+                sd.update(load_file(str(d / f), device="cpu"))
+            return sd
+        if legacy.exists():
+            return torch.load(legacy, map_location="cpu")
+    raise FileNotFoundError(f"no diffusers-format transformer weights under {root}")
