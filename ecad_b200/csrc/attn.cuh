@@ -358,13 +358,15 @@ __device__ __forceinline__ void softmax_chunk_exp_reg(const uint32_t (&v)[32], u
 // =====================================================================================================
 // Persistent pipelined variant: one work item = all 256 queries of one (sample, head) against NK keys.
 //
-//   warp 0      TMA producer: Q (2 tiles) + K of item i+1 are prefetched as soon as item i's QK^T has retired;
-//               V is double-buffered.  K/V are read ONCE per (sample, head).
-//   warp 1      MMA issuer:  S_t = Q_t K^T (SS), then O_t = P_t V with P_t read straight from TMEM (TS form).
-//   warps 2..5  softmax + epilogue of query tile 0;  warps 6..9 of query tile 1 (thread = one query row).
+//   warp 0       TMA producer: Q (2 tiles) + K of item i+1 are prefetched as soon as item i's QK^T has retired;
+//                V is double-buffered.  K/V are read ONCE per (sample, head).  (Measured: double-buffering Q/K as well
+//                does not help, 110 -> 114 us at the config-2 shape - the ~2000 clk the MMA thread waits for Q/K per
+//                item are the HBM transfer itself, not buffer availability.)
+//   warp 1       MMA issuer:  S_t = Q_t K^T (SS), then O_t = P_t V with P_t read straight from TMEM (TS form).
+//   warps 2..9   softmax + epilogue of query tile 0;  warps 10..17 of query tile 1 (two threads per query row).
 //
-// TMEM map (512 columns): tile t owns columns [256t, 256t+256): S_t fp32 in [0,NK); P_t (bf16 pairs) is written IN
-// PLACE over the already-consumed low half of S_t; O_t accumulates in [128,208).  No shared memory is spent on P.
+// TMEM map (512 columns): tile t owns columns [256t, 256t+256): S_t fp32 in [0,NK); P_t (bf16 pairs) and O_t are
+// written over consumed S columns (AttnPairCfg::kPHi / kO).  No shared memory is spent on P.
 // =====================================================================================================
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
