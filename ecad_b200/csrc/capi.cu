@@ -983,6 +983,75 @@ int ecadk_flux_blocks(ecadk_flux_handle_t h, const EcadkFluxArgs* a, const uint8
 }
 
 #ifdef ECADK_ATTN_TIMING
+// instrumented builds only: how fast can TMA stream head-major [rows, 80] bf16 tensors the way the attention kernels
+// read them (64-column + 16-column boxes, or five 16-column boxes) versus fully contiguous boxes of the same bytes?
+__global__ void __launch_bounds__(64, 1) tma_stream_kernel(const __grid_constant__ CUtensorMap t64,
+                                                            const __grid_constant__ CUtensorMap t16,
+                                                            const __grid_constant__ CUtensorMap tflat, int tensors,
+                                                            int mode) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kStages = 4, kStage = 256 * 160;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStage);
+  uint64_t* empty = full + kStages;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int t = blockIdx.x; t < tensors; t += gridDim.x, ++n) {
+      const int st = n % kStages;
+      mbar_wait(&empty[st], ((n / kStages) & 1) ^ 1);
+      mbar_arrive_expect_tx(&full[st], kStage);
+      uint8_t* d = smem + st * kStage;
+      const int row = t * 256;
+      if (mode == 0) {  // 64 + 16 columns (Q, K)
+        tma_load_2d(d, &t64, &full[st], 0, row);
+        tma_load_2d(d + 256 * 128, &t16, &full[st], 64, row);
+      } else if (mode == 1) {  // five 16-column atoms (V)
+        for (int a = 0; a < 5; ++a) tma_load_2d(d + a * 256 * 32, &t16, &full[st], a * 16, row);
+      } else {  // the same 40 KB as one contiguous block: 320 rows of 128 B
+        tma_load_2d(d, &tflat, &full[st], 0, t * 320);
+        tma_load_2d(d + 160 * 128, &tflat, &full[st], 0, t * 320 + 160);
+      }
+    }
+  } else if (threadIdx.x == 32) {
+    int n = 0;
+    for (int t = blockIdx.x; t < tensors; t += gridDim.x, ++n) {
+      const int st = n % kStages;
+      mbar_wait(&full[st], (n / kStages) & 1);
+      mbar_arrive(&empty[st]);
+    }
+  }
+}
+
+int ecadk_debug_tma_stream(const void* buf, int tensors, int mode, float* ms_out) {
+  CUtensorMap t64, t16, tflat;
+  int rc;
+  const uint64_t rows = static_cast<uint64_t>(tensors) * 256;
+  if ((rc = make_tmap_bf16(&t64, buf, rows, 80, 80, 256, 64, 128))) return rc;
+  if ((rc = make_tmap_bf16(&t16, buf, rows, 80, 80, 256, 16, 32))) return rc;
+  if ((rc = make_tmap_bf16(&tflat, buf, static_cast<uint64_t>(tensors) * 320, 64, 64, 160, 64, 128))) return rc;
+  const int smem = 4 * 256 * 160 + 1024 + 256;
+  ECADK_CHECK_CUDA(cudaFuncSetAttribute(tma_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaEvent_t a, b;
+  ECADK_CHECK_CUDA(cudaEventCreate(&a));
+  ECADK_CHECK_CUDA(cudaEventCreate(&b));
+  tma_stream_kernel<<<num_sms(), 64, smem>>>(t64, t16, tflat, tensors, mode);
+  ECADK_CHECK_CUDA(cudaEventRecord(a));
+  for (int i = 0; i < 5; ++i) tma_stream_kernel<<<num_sms(), 64, smem>>>(t64, t16, tflat, tensors, mode);
+  ECADK_CHECK_CUDA(cudaEventRecord(b));
+  ECADK_CHECK_CUDA(cudaEventSynchronize(b));
+  ECADK_CHECK_CUDA(cudaEventElapsedTime(ms_out, a, b));
+  *ms_out /= 5;
+  return check_launch("tma_stream_kernel");
+}
+
 // instrumented builds only: copies the phase-clock accumulators of the last attn_flash_kernel launch to the host
 int ecadk_debug_attn_timing(unsigned int* out_host) {
   ECADK_CHECK_CUDA(cudaDeviceSynchronize());
