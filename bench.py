@@ -268,14 +268,14 @@ def main():
         ev0.record()
         host_out = None
         results = []
-        for i in range(first, first + count):
-            if through_host:
-                e = {k: v.to(device, non_blocking=True) for k, v in emb_host.items()}  # pinned host -> device
-                lat = one_step(i, e)
-                host_out = lat.to("cpu")  # device -> host read of the step's result
-            else:
-                lat = one_step(i, emb)
-            results.append(lat)
+        if through_host:
+            # the repo's public population API: every step's inputs come from pinned host memory and its latents go
+            # back to pinned host memory, with the copies pipelined on a side stream (ecad_b200/population.py)
+            out = evaluator.run_from_host(range(first, first + count), one_step, emb_host)
+            results, host_out = out["device"], out["host"][-1]
+        else:
+            for i in range(first, first + count):
+                results.append(one_step(i, emb))
         # the search driver needs every candidate's latents: gather over NCCL (no-op at N=1)
         parts = [[r_ * count + j for j in range(count)] for r_ in range(world)]
         evaluator.gather(results, parts, world * count)

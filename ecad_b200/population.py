@@ -63,6 +63,61 @@ class PopulationEvaluator:
             out["results"] = self.gather(local, parts, n_units)
         return out
 
+    def run_from_host(self, unit_indices: Sequence[int], run_unit: Callable[[int, dict], torch.Tensor],
+                      host_inputs: Callable[[int], dict] | dict, keep_device_results: bool = True) -> dict:
+        """Runs this rank's units with their inputs coming from (pinned) HOST memory and their results going back to
+        pinned host memory, software-pipelined on a copy stream: the host->device copy of unit k+1 and the
+        device->host copy of unit k-1 overlap the generation of unit k (two device input buffers).
+
+        ``host_inputs`` is a dict of host tensors used for every unit (the ECAD search evaluates every candidate on
+        the same prompt set) or a callable ``i -> dict``.  ``run_unit(i, device_inputs)`` returns the unit's result
+        on the device.  Returns ``{"host": [pinned tensors], "device": [device tensors]}`` in unit order."""
+        if self.device.type != "cuda":
+            raise RuntimeError("run_from_host pipelines CUDA copies; use evaluate() on CPU")
+        get = host_inputs if callable(host_inputs) else (lambda _i: host_inputs)
+        cur = torch.cuda.current_stream(self.device)
+        copy = torch.cuda.Stream(self.device)
+        units = list(unit_indices)
+        bufs: list[dict | None] = [None, None]
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        host_out: list[torch.Tensor] = []
+        dev_out: list[torch.Tensor] = []
+
+        def upload(k: int) -> None:
+            slot = k & 1
+            src = get(units[k])
+            with torch.cuda.stream(copy):
+                if k >= 2:
+                    copy.wait_event(consumed[slot])  # unit k-2 has finished reading this buffer
+                if bufs[slot] is None:
+                    bufs[slot] = {n: torch.empty(t.shape, dtype=t.dtype, device=self.device) for n, t in src.items()}
+                for n, t in src.items():
+                    bufs[slot][n].copy_(t, non_blocking=True)
+                ready[slot].record(copy)
+
+        if units:
+            upload(0)
+        for k, i in enumerate(units):
+            slot = k & 1
+            if k + 1 < len(units):
+                upload(k + 1)
+            cur.wait_event(ready[slot])
+            res = run_unit(i, bufs[slot])
+            consumed[slot].record(cur)
+            done = torch.cuda.Event()
+            done.record(cur)
+            pinned = torch.empty(res.shape, dtype=res.dtype, pin_memory=True)
+            with torch.cuda.stream(copy):
+                copy.wait_event(done)
+                pinned.copy_(res, non_blocking=True)
+            res.record_stream(copy)
+            host_out.append(pinned)
+            if keep_device_results:
+                dev_out.append(res)
+        copy.synchronize()
+        return {"host": host_out, "device": dev_out}
+
     def gather(self, local: list[torch.Tensor], parts: list[list[int]], n_units: int) -> list[torch.Tensor | None]:
         """All ranks receive every unit's result, ordered by unit index."""
         if self.world_size == 1:

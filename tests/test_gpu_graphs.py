@@ -130,3 +130,31 @@ def test_latency_metrics_block(cuda_device, tmp_path):
     assert lat["batch_size"] == 4 and len(lat["latencies"]) == 2 and len(lat["warmups"]) == 1 and 0 < lat["avg"] < 1000
     assert m["total_macs"] == row["total_macs"]
     assert json.loads(f.read_text())["metrics"]["latency"]["gpu"] == lat["gpu"]
+
+
+def test_population_run_from_host_pipelines_copies_and_keeps_results(cuda_device):
+    """PopulationEvaluator.run_from_host: inputs from pinned host memory, results to pinned host memory, copies on a
+    side stream - results must equal the plain per-unit path."""
+    from ecad_b200.image_generator import B200PixArtAlphaImageGenerator
+    from ecad_b200.population import PopulationEvaluator
+    from ecad_b200.schedule import schedule_from_packed
+    from ecad_b200.weights import PixArtConfig, random_init_state_dict, synthetic_prompt_embeddings
+    from golden_util import row_by_path
+
+    rows = [row_by_path(f"population_initialization/pixart_alpha_256x256/gen_000/candidates/cand_{i:03d}.json")
+            for i in (1, 2, 5)]
+    sd = random_init_state_dict(PixArtConfig(), 0)
+    gen = B200PixArtAlphaImageGenerator(cache_schedule=schedule_from_packed(rows[0]), state_dict=sd)
+    emb_host = {k: v.pin_memory() for k, v in synthetic_prompt_embeddings(3, seed=5).items()}
+
+    def run_unit(i, emb):
+        gen.set_schedule(schedule_from_packed(rows[i]))
+        return gen.generate_images(emb)[0]
+
+    ev = PopulationEvaluator(0, 1, cuda_device)
+    out = ev.run_from_host(range(3), run_unit, emb_host)
+    ref = [run_unit(i, {k: v.cuda() for k, v in emb_host.items()}).cpu() for i in range(3)]
+    assert len(out["host"]) == 3 and all(t.is_pinned() for t in out["host"])
+    for got, dev, want in zip(out["host"], out["device"], ref):
+        assert torch.equal(got, want) and torch.equal(dev.cpu(), want)
+    assert not torch.equal(ref[0], ref[1])  # different candidates really produce different latents
