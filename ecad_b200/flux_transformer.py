@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .schedule import FluxCacheSchedule
+from .schedule import FluxCacheSchedule, flux_dead_store_mask
 from .transformer import SequentialDiTScheduler, Transformer2DModelOutput
 from .weights import FluxConfig, flux_random_init_state_dict
 
@@ -281,32 +281,11 @@ class B200FluxTransformer2D:
         self._text_key = None
 
     def _dead_stores(self, executed: np.ndarray) -> np.ndarray:
-        """1 where an executed component's cache store is dead (overwritten next step or dropped at the end of the
-        generation before anything reads it).  single_attn / single_proj_mlp are produced in place and always kept."""
-        sched, cfg = self.cache_schedule, self.cfg
-        rows = cfg.num_layers + cfg.num_single_layers
-        dead = np.zeros((rows, 3), dtype=np.uint8)
+        """Cache stores of this step that nothing will read (ecad_b200.schedule.flux_dead_store_mask)."""
+        rows = self.cfg.num_layers + self.cfg.num_single_layers
         if not self.skip_dead_cache_stores:
-            return dead
-        step = sched.curr_step
-        last = step >= sched.num_inference_steps - 1
-        if last:
-            nxt_flags = np.ones((rows, 3), dtype=np.bool_)
-        else:
-            nxt = sched.schedule.get(step + 1)
-            if nxt is None:
-                return dead
-            nxt_flags = np.zeros((rows, 3), dtype=np.bool_)
-            for r in range(rows):
-                if r < cfg.num_layers:
-                    e = nxt[str(r)]
-                    nxt_flags[r] = [e["full_attn"], e["full_ff"], e["full_ff_context"]]
-                else:
-                    e = nxt[f"single_{r - cfg.num_layers}"]
-                    nxt_flags[r] = [e["single_attn"], e["single_proj_mlp"], e["single_proj_out"]]
-        dead[:] = executed.astype(np.bool_) & nxt_flags
-        dead[cfg.num_layers:, 0:2] = 0
-        return dead
+            return np.zeros((rows, 3), dtype=np.uint8)
+        return flux_dead_store_mask(self.cache_schedule, self.cache_schedule.curr_step, executed)
 
     def _decide(self) -> np.ndarray:
         """``recompute or no_cache`` per component (cached_flux_transformer_block.py:52-61,81-91,173-186,207-216)."""

@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import json
 from pathlib import Path
-from typing import Any, Iterable
+from typing import Any, Sequence, Iterable
 
 import numpy as np
 
@@ -318,3 +318,72 @@ class FluxCacheSchedule(CacheSchedule):
             sched[s] = blocks
         return cls(num_blocks, num_inference_steps, name, sched, top_level_config, attributes, metrics,
                    num_single_blocks=num_single_blocks)
+
+
+# ---- dead cache stores ------------------------------------------------------------------------------------------
+def pixart_dead_store_mask(schedule: "PixArtCacheSchedule", step: int, executed: np.ndarray,
+                           keep_attn2_blocks: Sequence[int] = ()) -> np.ndarray:
+    """``uint8[NB][3]``: 1 where an EXECUTED sub-block's cache store at ``step`` is dead - the slot is overwritten or
+    dropped before anything reads it - so the GEMM epilogue may skip the reference's ``self.cached_* = out``
+    (cached_transformer_block.py:357-358,388-389).  Rule (one step of look-ahead, conservative):
+
+      * last step of the generation: every slot is dropped by the reset callback (image_generator.py:193-202);
+      * otherwise the next step's flag recomputes the sub-block AND both steps decide through the default functions
+        (``compute_attn_cached`` / ``compute_ff_cached``): then ``flag or cache is None`` executes it whatever the
+        cache holds.  Custom / TGATE decision functions keep their stores (their next decision is not a pure flag),
+        and so do the blocks whose attn2 cache is averaged after this forward (``keep_attn2_blocks``).
+    """
+    from .registry import ComputeAttnRegistry, ComputeFFRegistry
+
+    nb = schedule.num_blocks
+    dead = np.zeros((nb, 3), dtype=np.uint8)
+    last = step >= schedule.num_inference_steps - 1
+    nxt = None if last else schedule.schedule.get(step + 1)
+    if not last and nxt is None:
+        return dead
+    default_attn, default_ff = ComputeAttnRegistry.default(), ComputeFFRegistry.default()
+
+    def is_default(entry) -> tuple[bool, bool]:
+        a = ComputeAttnRegistry.get((entry.get("custom_compute_attn") or {}).get("name"), False)
+        f = ComputeFFRegistry.get((entry.get("custom_compute_ff") or {}).get("name"), False)
+        return a is default_attn, f is default_ff
+
+    row = schedule.schedule[step]
+    keep = set(keep_attn2_blocks)
+    for b in range(nb):
+        cur_a, cur_f = is_default(row[str(b)])
+        if last:
+            nxt_a, nxt_f, flags = True, True, (True, True, True)
+        else:
+            e = nxt[str(b)]
+            nxt_a, nxt_f = is_default(e)
+            flags = (bool(e["attn1"]), bool(e["attn2"]), bool(e["ff"]))
+        ok = (cur_a and nxt_a, cur_a and nxt_a and b not in keep, cur_f and nxt_f)
+        for c in range(3):
+            dead[b, c] = bool(executed[b, c]) and ok[c] and flags[c]
+    return dead
+
+
+def flux_dead_store_mask(schedule: "FluxCacheSchedule", step: int, executed: np.ndarray) -> np.ndarray:
+    """FLUX counterpart (``uint8[NB + NS][3]``, FluxCacheSchedule.dense() order).  single_attn / single_proj_mlp are
+    produced straight into their cache slots by the kernels and are never skipped."""
+    rows = schedule.num_blocks + schedule.num_single_blocks
+    dead = np.zeros((rows, 3), dtype=np.uint8)
+    last = step >= schedule.num_inference_steps - 1
+    if last:
+        nxt_flags = np.ones((rows, 3), dtype=np.bool_)
+    else:
+        nxt = schedule.schedule.get(step + 1)
+        if nxt is None:
+            return dead
+        nxt_flags = np.zeros((rows, 3), dtype=np.bool_)
+        for r in range(rows):
+            if r < schedule.num_blocks:
+                e = nxt[str(r)]
+                nxt_flags[r] = [e[c] for c in FLUX_FULL_COMPONENTS]
+            else:
+                e = nxt[f"single_{r - schedule.num_blocks}"]
+                nxt_flags[r] = [e[c] for c in FLUX_SINGLE_COMPONENTS]
+    dead[:] = np.asarray(executed).astype(np.bool_) & nxt_flags
+    dead[schedule.num_blocks:, 0:2] = 0
+    return dead

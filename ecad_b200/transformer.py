@@ -31,7 +31,7 @@ import torch
 
 from . import _lib
 from .registry import ComputeAttnRegistry, ComputeFFRegistry, DecisionContext
-from .schedule import PixArtCacheSchedule
+from .schedule import PixArtCacheSchedule, pixart_dead_store_mask
 from .weights import PixArtConfig, random_init_state_dict
 
 
@@ -294,39 +294,10 @@ class B200PixArtTransformer2D:
         self._text_key = None
 
     def _dead_stores(self, executed: np.ndarray) -> np.ndarray:
-        """1 where an executed sub-block's cache store is dead: the generation ends after this step (reset callback,
-        image_generator.py:193-202) or the next step's flag recomputes the sub-block through the default decision
-        functions.  Custom / TGATE decision functions keep their stores (their next decision is not a pure flag)."""
-        sched = self.cache_schedule
-        step = sched.curr_step
-        L = self.cfg.num_layers
-        dead = np.zeros((L, 3), dtype=np.uint8)
+        """Cache stores of this step that nothing will read (ecad_b200.schedule.pixart_dead_store_mask)."""
         if not self.skip_dead_cache_stores:
-            return dead
-        last = step >= sched.num_inference_steps - 1
-        nxt = None if last else sched.schedule.get(step + 1)
-        if not last and nxt is None:
-            return dead
-        default_attn, default_ff = ComputeAttnRegistry.default(), ComputeFFRegistry.default()
-
-        def is_default(entry) -> tuple[bool, bool]:
-            a = ComputeAttnRegistry.get((entry.get("custom_compute_attn") or {}).get("name"), False)
-            f = ComputeFFRegistry.get((entry.get("custom_compute_ff") or {}).get("name"), False)
-            return a is default_attn, f is default_ff
-
-        row = sched.schedule[step]
-        for b in range(L):
-            cur_a, cur_f = is_default(row[str(b)])
-            if last:
-                nxt_a, nxt_f, flags = True, True, (True, True, True)
-            else:
-                e = nxt[str(b)]
-                nxt_a, nxt_f = is_default(e)
-                flags = (bool(e["attn1"]), bool(e["attn2"]), bool(e["ff"]))
-            ok = (cur_a and nxt_a, cur_a and nxt_a, cur_f and nxt_f)
-            for c in range(3):
-                dead[b, c] = executed[b, c] and ok[c] and flags[c] and b not in self._tgate_average
-        return dead
+            return np.zeros((self.cfg.num_layers, 3), dtype=np.uint8)
+        return pixart_dead_store_mask(self.cache_schedule, self.cache_schedule.curr_step, executed, self._tgate_average)
 
     def _decide(self) -> np.ndarray:
         """Decision row of the current step: the reference's per-sub-block rule, evaluated through the same
