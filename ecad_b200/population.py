@@ -14,7 +14,6 @@ from __future__ import annotations
 
 from typing import Callable, Sequence
 
-import numpy as np
 import torch
 import torch.distributed as dist
 

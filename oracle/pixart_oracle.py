@@ -18,7 +18,7 @@ Everything is plain fp32 PyTorch on CPU; weights come in as a ``state_dict`` key
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Any, Callable
 
 import numpy as np
