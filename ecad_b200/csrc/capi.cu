@@ -481,31 +481,37 @@ int launch_residual_ln(const EcadkResidualLnArgs& a, cudaStream_t stream) {
   p.eps = a.eps;
   ECADK_REQUIRE(a.tokens % kRlnRowsPerBlock == 0, "residual_ln: tokens=%d must be a multiple of %d", a.tokens,
                 kRlnRowsPerBlock);
-  const int grid = (a.rows + kRlnRowsPerBlock - 1) / kRlnRowsPerBlock;
+  // small problems (batch-1 latency configuration): 8 rows per block so that the grid still covers the SMs
+  const bool small = (a.rows + kRlnRowsPerBlock - 1) / kRlnRowsPerBlock < 2 * num_sms();
+  const int rpb = small ? 8 : kRlnRowsPerBlock;
+  const int grid = (a.rows + rpb - 1) / rpb;
   const int smem = (2 + a.n_reuse) * a.dim * 4;
   const double elems = static_cast<double>(a.rows) * a.dim;
   ProfScope prof(ECADK_PROF_GLUE, 0.0,
                  elems * (4.0 + (a.n_reuse > 0 ? 4.0 : 0.0) + 2.0 * a.n_reuse + (a.xb ? 2.0 : 0.0) + (a.h ? 2.0 : 0.0)),
                  stream);
-  if (a.dim == 512) {
-    residual_ln_kernel<4><<<grid, 256, smem, stream>>>(p);
-  } else if (a.dim == 1152) {
-    static bool configured9 = false;
-    if (!configured9) {  // up to (2 + 12) staged vectors = 63 KB > the 48 KB default
-      ECADK_CHECK_CUDA(cudaFuncSetAttribute(residual_ln_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (2 + ECADK_MAX_REUSE) * 1152 * 4));
-      configured9 = true;
-    }
-    residual_ln_kernel<9><<<grid, 256, smem, stream>>>(p);
-  } else {
-    static bool configured = false;
-    if (!configured) {
-      ECADK_CHECK_CUDA(cudaFuncSetAttribute(residual_ln_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (2 + ECADK_MAX_REUSE) * 3072 * 4));
+  auto launch = [&](auto kern, int max_smem, bool& configured) -> int {
+    if (!configured && max_smem > 48 * 1024) {
+      ECADK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
       configured = true;
     }
-    residual_ln_kernel<24><<<grid, 256, smem, stream>>>(p);
+    kern<<<grid, 256, smem, stream>>>(p);
+    return ECADK_OK;
+  };
+  int rc;
+  if (a.dim == 512) {
+    static bool c0 = false, c1 = false;
+    rc = small ? launch(residual_ln_kernel<4, 8>, 0, c0) : launch(residual_ln_kernel<4>, 0, c1);
+  } else if (a.dim == 1152) {  // up to (2 + 12) staged vectors = 63 KB > the 48 KB default
+    static bool c0 = false, c1 = false;
+    const int mx = (2 + ECADK_MAX_REUSE) * 1152 * 4;
+    rc = small ? launch(residual_ln_kernel<9, 8>, mx, c0) : launch(residual_ln_kernel<9>, mx, c1);
+  } else {
+    static bool c0 = false, c1 = false;
+    const int mx = (2 + ECADK_MAX_REUSE) * 3072 * 4;
+    rc = small ? launch(residual_ln_kernel<24, 8>, mx, c0) : launch(residual_ln_kernel<24>, mx, c1);
   }
+  if (rc) return rc;
   return check_launch("residual_ln_kernel");
 }
 

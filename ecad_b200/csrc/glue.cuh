@@ -149,21 +149,29 @@ __device__ __forceinline__ void rln_load_row(const ResidualLnParams& p, const in
   for (int i = 0; i < VPL; ++i) v[i] = xr[lane + 32 * i];
 }
 
-template <int VPL>
+// RPB = rows per block: 32 for large problems (the modulation vectors are staged once per 32 rows); 8 when the whole
+// problem has fewer than ~2 waves of 32-row blocks (batch-1 latency configuration: M = 512 rows would be 16 blocks of
+// four serial row-pairs per warp - 14 us per launch, 25 % of a batch-1 generation; 64 blocks of one row per warp
+// take the latency of a single HBM round trip).
+template <int VPL, int RPB = kRlnRowsPerBlock>
 __global__ void __launch_bounds__(256, (VPL <= 12) ? 2 : 1) residual_ln_kernel(const ResidualLnParams p) {
   extern __shared__ float4 rln_sm[];  // [(2 + n_reuse)][D/4]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = blockIdx.x * kRlnRowsPerBlock;
+  const int row0 = blockIdx.x * RPB;
   const int sample = row0 / p.tokens;
-  if constexpr (VPL > 12) {  // wide rows (D = 3072): one row per warp at a time keeps the row in registers
+  if constexpr (VPL > 12 || RPB == 8) {  // one row per warp at a time (wide rows: the row fills the registers)
+    float4 va[VPL];
+    int ra = row0 + warp;
+    if constexpr (RPB == 8) {
+      if (ra < p.M) rln_load_row<VPL>(p, ra, lane, va);  // requested before the vectors are staged
+    }
     rln_stage_vectors<VPL>(p, rln_sm, sample);
     __syncthreads();
 #pragma unroll 1
-    for (int j = 0; j < kRlnRowsPerBlock / 8; ++j) {
-      const int ra = row0 + warp + 8 * j;
+    for (int j = 0; j < RPB / 8; ++j) {
+      ra = row0 + warp + 8 * j;
       if (ra >= p.M) break;
-      float4 va[VPL];
-      rln_load_row<VPL>(p, ra, lane, va);
+      if constexpr (RPB != 8) rln_load_row<VPL>(p, ra, lane, va);
       rln_row<VPL>(p, rln_sm, ra, lane, va);
     }
   } else {
@@ -176,7 +184,7 @@ __global__ void __launch_bounds__(256, (VPL <= 12) ? 2 : 1) residual_ln_kernel(c
     rln_stage_vectors<VPL>(p, rln_sm, sample);
     __syncthreads();
 #pragma unroll 1
-    for (int j = 0; j < kRlnRowsPerBlock / 8; j += 2) {
+    for (int j = 0; j < RPB / 8; j += 2) {
       if (j > 0) {
         ra = row0 + warp + 8 * j;
         rb = ra + 8;
