@@ -143,7 +143,8 @@ class B200PixArtPipeline:
             model_in = sched.scale_model_input(model_in, t)
             current_timestep = timesteps_dev[i:i + 1].expand(model_in.shape[0])
             noise_pred = tr(model_in, encoder_hidden_states=e_in, encoder_attention_mask=m_in,
-                            timestep=current_timestep, added_cond_kwargs=cond_in, return_dict=False)[0]
+                            timestep=current_timestep, added_cond_kwargs=cond_in, return_dict=False,
+                            timestep_host=float(t))[0]
             c = sched.coefficients()
             _lib.check(
                 lib.ecadk_cfg_dpm_step(noise_pred.data_ptr(), latents.data_ptr(), x0_prev.data_ptr(), batch_size,

@@ -122,6 +122,7 @@ class B200PixArtTransformer2D:
         self._ws_key: tuple | None = None
         self._has_cache = np.zeros((config.num_layers, 3), dtype=np.bool_)
         self._text_key: tuple | None = None
+        self._temb_cache: dict[float, tuple[torch.Tensor, torch.Tensor]] = {}  # timestep -> (emb, adaLN table)
         self.last_executed: np.ndarray | None = None
         # Dead-store elimination: an executed sub-block does not store its cache slot when the schedule shows that the
         # slot is overwritten (next step recomputes it) or dropped (generation ends) before anything reads it.
@@ -339,7 +340,11 @@ class B200PixArtTransformer2D:
         attention_mask: Optional[torch.Tensor] = None,
         encoder_attention_mask: Optional[torch.Tensor] = None,
         return_dict: bool = True,
+        timestep_host: float | None = None,
     ):
+        """``timestep_host`` (optional, not in the reference signature): the value of a batch-shared timestep as a host
+        number.  The adaLN-single tables depend on nothing but the timestep and the weights, so with it they are
+        computed once per distinct timestep and reused by every later step / generation without a device read-back."""
         cfg, lib, w = self.cfg, self._lib, self.w
         if attention_mask is not None:
             raise NotImplementedError("self-attention masks are never passed on the PixArt path")
@@ -377,45 +382,60 @@ class B200PixArtTransformer2D:
         t32 = timestep.reshape(-1)[:1] if shared_t else timestep.reshape(-1)
         if not shared_t and t32.numel() != S:
             raise ValueError(f"timestep has {t32.numel()} entries for a batch of {S}")
-        t32 = t32.to(device=dev, dtype=torch.float32).contiguous()
         temb_stride = 0 if shared_t else 6 * D
         emb_stride = 0 if shared_t else D
         ws["args"].temb_stride = temb_stride
-        _lib.check(lib.ecadk_timestep_sinusoid(t32.data_ptr(), ws["t_proj"].data_ptr(), St, 256, st), "sinusoid")
-        _lib.check(lib.ecadk_small_linear(ws["t_proj"].data_ptr(), 256, w["t_w0"].data_ptr(), w["t_b0"].data_ptr(),
-                                          ws["t_e1"].data_ptr(), St, 256, D, D, 0, 0, 0, st), "t_mlp1")
-        _lib.check(lib.ecadk_small_linear(ws["t_e1"].data_ptr(), D, w["t_w1"].data_ptr(), w["t_b1"].data_ptr(),
-                                          ws["t_emb"].data_ptr(), St, D, D, D, 0, 1, 0, st), "t_mlp2")
-        if addc:
-            # PixArtAlphaCombinedTimestepSizeEmbeddings: emb += cat([res_emb(h), res_emb(w), ar_emb]) with each
-            # micro-condition through its own sinusoid -> Linear(256,384) -> SiLU -> Linear(384,384)
-            E = D // 3
-            res = added_cond_kwargs["resolution"].to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
-            ar = added_cond_kwargs["aspect_ratio"].to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
-            if res.numel() != 2 * S or ar.numel() != S:
-                raise ValueError("resolution must be (batch, 2) and aspect_ratio (batch, 1)")
-            c_proj = torch.empty(3 * S, 256, device=dev, dtype=torch.float32)
-            c_e1 = torch.empty(3 * S, E, device=dev, dtype=torch.float32)
-            _lib.check(lib.ecadk_timestep_sinusoid(res.data_ptr(), c_proj.data_ptr(), 2 * S, 256, st), "res_sin")
-            _lib.check(lib.ecadk_timestep_sinusoid(ar.data_ptr(), c_proj[2 * S:].data_ptr(), S, 256, st), "ar_sin")
-            _lib.check(lib.ecadk_small_linear(c_proj.data_ptr(), 256, w["resolution_embedder_w0"].data_ptr(),
-                                              w["resolution_embedder_b0"].data_ptr(), c_e1.data_ptr(), 2 * S, 256, E,
-                                              E, 0, 0, 0, st), "res_mlp1")
-            _lib.check(lib.ecadk_small_linear(c_proj[2 * S:].data_ptr(), 256, w["aspect_ratio_embedder_w0"].data_ptr(),
-                                              w["aspect_ratio_embedder_b0"].data_ptr(), c_e1[2 * S:].data_ptr(), S,
-                                              256, E, E, 0, 0, 0, st), "ar_mlp1")
-            # second linears accumulate straight into the three thirds of the timestep embedding
-            for part in range(2):  # (height, width) rows of c_e1 are interleaved per sample: row pitch 2*E
-                _lib.check(lib.ecadk_small_linear(c_e1[part:].data_ptr(), 2 * E, w["resolution_embedder_w1"].data_ptr(),
-                                                  w["resolution_embedder_b1"].data_ptr(), ws["t_emb"].data_ptr(), S,
-                                                  E, E, D, part * E, 1, 1, st), "res_mlp2")
-            _lib.check(lib.ecadk_small_linear(c_e1[2 * S:].data_ptr(), E, w["aspect_ratio_embedder_w1"].data_ptr(),
-                                              w["aspect_ratio_embedder_b1"].data_ptr(), ws["t_emb"].data_ptr(), S, E,
-                                              E, D, 2 * E, 1, 1, st), "ar_mlp2")
-            launches += 7
-        _lib.check(lib.ecadk_small_linear(ws["t_emb"].data_ptr(), D, w["ada_w"].data_ptr(), w["ada_b"].data_ptr(),
-                                          ws["temb6"].data_ptr(), St, D, 6 * D, 6 * D, 0, 1, 0, st), "adaln_linear")
-        launches += 5
+        cached = None
+        if shared_t and timestep_host is not None:
+            cached = self._temb_cache.get(float(timestep_host))
+        if cached is not None:
+            t_emb_buf, temb6_buf = cached
+        else:
+            if shared_t and timestep_host is not None:  # compute into tensors that stay alive in the cache
+                t_emb_buf = torch.empty(1, D, device=dev, dtype=torch.float32)
+                temb6_buf = torch.empty(1, 6 * D, device=dev, dtype=torch.float32)
+                if len(self._temb_cache) >= 256:
+                    self._temb_cache.clear()
+                self._temb_cache[float(timestep_host)] = (t_emb_buf, temb6_buf)
+            else:
+                t_emb_buf, temb6_buf = ws["t_emb"], ws["temb6"]
+            t32 = t32.to(device=dev, dtype=torch.float32).contiguous()
+            _lib.check(lib.ecadk_timestep_sinusoid(t32.data_ptr(), ws["t_proj"].data_ptr(), St, 256, st), "sinusoid")
+            _lib.check(lib.ecadk_small_linear(ws["t_proj"].data_ptr(), 256, w["t_w0"].data_ptr(), w["t_b0"].data_ptr(),
+                                              ws["t_e1"].data_ptr(), St, 256, D, D, 0, 0, 0, st), "t_mlp1")
+            _lib.check(lib.ecadk_small_linear(ws["t_e1"].data_ptr(), D, w["t_w1"].data_ptr(), w["t_b1"].data_ptr(),
+                                              t_emb_buf.data_ptr(), St, D, D, D, 0, 1, 0, st), "t_mlp2")
+            if addc:
+                # PixArtAlphaCombinedTimestepSizeEmbeddings: emb += cat([res_emb(h), res_emb(w), ar_emb]) with each
+                # micro-condition through its own sinusoid -> Linear(256,384) -> SiLU -> Linear(384,384)
+                E = D // 3
+                res = added_cond_kwargs["resolution"].to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+                ar = added_cond_kwargs["aspect_ratio"].to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+                if res.numel() != 2 * S or ar.numel() != S:
+                    raise ValueError("resolution must be (batch, 2) and aspect_ratio (batch, 1)")
+                c_proj = torch.empty(3 * S, 256, device=dev, dtype=torch.float32)
+                c_e1 = torch.empty(3 * S, E, device=dev, dtype=torch.float32)
+                _lib.check(lib.ecadk_timestep_sinusoid(res.data_ptr(), c_proj.data_ptr(), 2 * S, 256, st), "res_sin")
+                _lib.check(lib.ecadk_timestep_sinusoid(ar.data_ptr(), c_proj[2 * S:].data_ptr(), S, 256, st), "ar_sin")
+                _lib.check(lib.ecadk_small_linear(c_proj.data_ptr(), 256, w["resolution_embedder_w0"].data_ptr(),
+                                                  w["resolution_embedder_b0"].data_ptr(), c_e1.data_ptr(), 2 * S, 256, E,
+                                                  E, 0, 0, 0, st), "res_mlp1")
+                _lib.check(lib.ecadk_small_linear(c_proj[2 * S:].data_ptr(), 256, w["aspect_ratio_embedder_w0"].data_ptr(),
+                                                  w["aspect_ratio_embedder_b0"].data_ptr(), c_e1[2 * S:].data_ptr(), S,
+                                                  256, E, E, 0, 0, 0, st), "ar_mlp1")
+                # second linears accumulate straight into the three thirds of the timestep embedding
+                for part in range(2):  # (height, width) rows of c_e1 are interleaved per sample: row pitch 2*E
+                    _lib.check(lib.ecadk_small_linear(c_e1[part:].data_ptr(), 2 * E, w["resolution_embedder_w1"].data_ptr(),
+                                                      w["resolution_embedder_b1"].data_ptr(), t_emb_buf.data_ptr(), S,
+                                                      E, E, D, part * E, 1, 1, st), "res_mlp2")
+                _lib.check(lib.ecadk_small_linear(c_e1[2 * S:].data_ptr(), E, w["aspect_ratio_embedder_w1"].data_ptr(),
+                                                  w["aspect_ratio_embedder_b1"].data_ptr(), t_emb_buf.data_ptr(), S, E,
+                                                  E, D, 2 * E, 1, 1, st), "ar_mlp2")
+                launches += 7
+            _lib.check(lib.ecadk_small_linear(t_emb_buf.data_ptr(), D, w["ada_w"].data_ptr(), w["ada_b"].data_ptr(),
+                                              temb6_buf.data_ptr(), St, D, 6 * D, 6 * D, 0, 1, 0, st), "adaln_linear")
+            launches += 5
+        ws["args"].temb6 = temb6_buf.data_ptr()
 
         # caption projection + per-block K/V: step-invariant, done once per generation (:315-321; hoisted)
         mask = encoder_attention_mask
@@ -481,7 +501,7 @@ class B200PixArtTransformer2D:
             launches += len(self._tgate_average)
 
         # 3. output (:332-376)
-        _lib.check(lib.ecadk_final_layer(ws["x"].data_ptr(), w["final_table"].data_ptr(), ws["t_emb"].data_ptr(),
+        _lib.check(lib.ecadk_final_layer(ws["x"].data_ptr(), w["final_table"].data_ptr(), t_emb_buf.data_ptr(),
                                          emb_stride, w["final_w"].data_ptr(), w["final_b"].data_ptr(),
                                          ws["h"].data_ptr(), ws["out"].data_ptr(), S,
                                          hp, wp, D, cfg.out_channels, cfg.norm_eps, st), "final_layer")
