@@ -102,6 +102,8 @@ attn_tile_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  griddep_launch_dependents();  // programmatic dependent launch: see gemm_bf16_kernel
+  griddep_wait();
 
   if (warp == 4) {
     if (lane == 0) {
@@ -441,6 +443,8 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  griddep_launch_dependents();  // programmatic dependent launch: see gemm_bf16_kernel
+  griddep_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -812,6 +816,8 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  griddep_launch_dependents();  // programmatic dependent launch: see gemm_bf16_kernel
+  griddep_wait();
 
   if (warp == 0) {
     if (lane == 0) {

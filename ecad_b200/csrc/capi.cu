@@ -182,6 +182,35 @@ int num_sms() {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Launch with programmatic stream serialization (PDL): the kernel may be scheduled while its predecessor is still
+// running; every kernel launched this way executes griddepcontrol.wait before its first global-memory access.
+// ECADK_PDL=0 falls back to plain stream order.
+// ---------------------------------------------------------------------------------------------------
+bool use_pdl() {
+  static const bool on = [] {
+    const char* e = getenv("ECADK_PDL");
+    return !(e != nullptr && atoi(e) == 0);
+  }();
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // GEMM launcher
 // ---------------------------------------------------------------------------------------------------
 template <int BN, int EPI>
@@ -196,7 +225,7 @@ int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtens
   }
   const int tiles = ((p.M + kGemmBM - 1) / kGemmBM) * (p.N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, ta2, tb, p);
+  launch_pdl(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, ta, ta2, tb, p);
   return check_launch("gemm_bf16_kernel");
 }
 
@@ -213,7 +242,7 @@ int launch_gemm2_inst(const CUtensorMap& ta, const CUtensorMap& ta2, const CUten
   const int tiles = ((p.M + 2 * kGemmBM - 1) / (2 * kGemmBM)) * ((p.N - tail) / BN + (tail ? 1 : 0));
   const int pairs = num_sms() / 2;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, ta2, tb, tb_tail, p, tail);
+  launch_pdl(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, ta, ta2, tb, tb_tail, p, tail);
   return check_launch("gemm2_bf16_kernel");
 }
 
@@ -329,7 +358,8 @@ int launch_attn_pair_inst(const CUtensorMap* tq, const CUtensorMap* tm, const At
     configured = true;
   }
   const int grid = items < num_sms() ? items : num_sms();
-  kern<<<grid, kAttnPairThreads, Cfg::kSmemBytes, stream>>>(tq[0], tq[1], tm[2], tm[3], tm[4], tm[5], p, items);
+  launch_pdl(kern, dim3(grid), dim3(kAttnPairThreads), Cfg::kSmemBytes, stream, tq[0], tq[1], tm[2], tm[3], tm[4], tm[5], p,
+             items);
   return check_launch("attn_pair_kernel");
 }
 
@@ -344,8 +374,8 @@ int launch_attn_flash_inst(const CUtensorMap* tq, const CUtensorMap* tkv, const 
     configured = true;
   }
   const int grid = items < num_sms() ? items : num_sms();
-  kern<<<grid, kFlashThreads, Cfg::kSmemBytes, stream>>>(tq[0], tq[1], tkv[0], tkv[1], tkv[2], tkv[3], p, n_keys,
-                                                            items);
+  launch_pdl(kern, dim3(grid), dim3(kFlashThreads), Cfg::kSmemBytes, stream, tq[0], tq[1], tkv[0], tkv[1], tkv[2], tkv[3], p,
+             n_keys, items);
   return check_launch("attn_flash_kernel");
 }
 
@@ -495,7 +525,7 @@ int launch_residual_ln(const EcadkResidualLnArgs& a, cudaStream_t stream) {
       ECADK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
       configured = true;
     }
-    kern<<<grid, 256, smem, stream>>>(p);
+    launch_pdl(kern, dim3(grid), dim3(256), smem, stream, p);
     return ECADK_OK;
   };
   int rc;

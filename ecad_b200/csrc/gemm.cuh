@@ -290,6 +290,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: the prologue above may have overlapped the previous kernel's tail; nothing below
+  // touches global memory before that kernel has completed.  This grid is persistent (<= one CTA per SM), so the next
+  // kernel's CTAs are released right away to set themselves up on the idle SMs.
+  griddep_launch_dependents();
+  griddep_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -456,6 +461,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   cluster_sync();  // barriers of both CTAs initialised before any remote arrive / TMA credit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();  // see gemm_bf16_kernel
+  griddep_wait();
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================

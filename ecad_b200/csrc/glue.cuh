@@ -156,6 +156,10 @@ __device__ __forceinline__ void rln_load_row(const ResidualLnParams& p, const in
 template <int VPL, int RPB = kRlnRowsPerBlock>
 __global__ void __launch_bounds__(256, (VPL <= 12) ? 2 : 1) residual_ln_kernel(const ResidualLnParams p) {
   extern __shared__ float4 rln_sm[];  // [(2 + n_reuse)][D/4]
+  // programmatic dependent launch: a small grid releases the next kernel at once (its CTAs set up on idle SMs); a
+  // multi-wave grid keeps the SM slots for its own blocks and lets the implicit trigger at exit do it
+  if (gridDim.x <= 296) griddep_launch_dependents();
+  griddep_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * RPB;
   const int sample = row0 / p.tokens;
