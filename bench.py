@@ -302,7 +302,12 @@ def main():
         sampler.start()
     secs, launches, flops, _, prof = run_region(W, K, emb_dev, through_host=False, profile=True)
     clocks = sampler.stop() if rank == 0 else None
+    run_region(W, K, None, through_host=True)  # untimed: allocates the evaluator's pinned / device staging buffers
+    sampler_e2e = ClockSampler(local_rank)
+    if rank == 0:
+        sampler_e2e.start()
     secs_e2e, _, _, host_out, _ = run_region(W, K, None, through_host=True)
+    clocks_e2e = sampler_e2e.stop() if rank == 0 else None
 
     images = world * K * B
     value = images / secs
@@ -356,7 +361,8 @@ def main():
                 "algorithmic_tflop_per_image": flops / images / 1e12,
             },
             "roofline": roof, "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "sm_mhz": clocks_e2e["sm_mhz"] if clocks_e2e else None},
             "gpu_launches": launches, "clocks": clocks,
         }
     if world > 1:

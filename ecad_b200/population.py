@@ -48,6 +48,10 @@ class PopulationEvaluator:
         self.rank, self.world_size = rank, world_size
         self.device = torch.device(device)
         self.group = group
+        # persistent staging buffers of run_from_host: page-locking host memory (cudaHostAlloc) and cudaMalloc are slow
+        # and can stall the launching thread behind the running GPU work, so they must not happen per unit
+        self._pinned_pool: dict[tuple, list[torch.Tensor]] = {}
+        self._dev_inputs: dict[tuple, list[dict]] = {}
         if world_size > 1 and not dist.is_initialized():
             raise RuntimeError("torch.distributed must be initialised for world_size > 1")
 
@@ -70,14 +74,19 @@ class PopulationEvaluator:
 
         ``host_inputs`` is a dict of host tensors used for every unit (the ECAD search evaluates every candidate on
         the same prompt set) or a callable ``i -> dict``.  ``run_unit(i, device_inputs)`` returns the unit's result
-        on the device.  Returns ``{"host": [pinned tensors], "device": [device tensors]}`` in unit order."""
+        on the device.  Returns ``{"host": [pinned tensors], "device": [device tensors]}`` in unit order.  The pinned
+        result buffers and the two device input buffers belong to the evaluator and are REUSED by the next call:
+        consume (or copy) the host results before calling again."""
         if self.device.type != "cuda":
             raise RuntimeError("run_from_host pipelines CUDA copies; use evaluate() on CPU")
         get = host_inputs if callable(host_inputs) else (lambda _i: host_inputs)
         cur = torch.cuda.current_stream(self.device)
         copy = torch.cuda.Stream(self.device)
+        copy.wait_stream(cur)  # the staging buffers are reused: earlier work on this stream may still read them
         units = list(unit_indices)
-        bufs: list[dict | None] = [None, None]
+        sig = tuple((n, tuple(t.shape), t.dtype) for n, t in get(units[0]).items()) if units else ()
+        bufs: list[dict | None] = self._dev_inputs.setdefault(sig, [None, None])
+        taken: dict[tuple, int] = {}
         ready = [torch.cuda.Event(), torch.cuda.Event()]
         consumed = [torch.cuda.Event(), torch.cuda.Event()]
         host_out: list[torch.Tensor] = []
@@ -106,7 +115,13 @@ class PopulationEvaluator:
             consumed[slot].record(cur)
             done = torch.cuda.Event()
             done.record(cur)
-            pinned = torch.empty(res.shape, dtype=res.dtype, pin_memory=True)
+            pkey = (tuple(res.shape), res.dtype)
+            pool = self._pinned_pool.setdefault(pkey, [])
+            j = taken.get(pkey, 0)
+            taken[pkey] = j + 1
+            if j >= len(pool):
+                pool.append(torch.empty(res.shape, dtype=res.dtype, pin_memory=True))
+            pinned = pool[j]
             with torch.cuda.stream(copy):
                 copy.wait_event(done)
                 pinned.copy_(res, non_blocking=True)
