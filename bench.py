@@ -42,7 +42,7 @@ METRIC = "PixArt-alpha 256x256 20-step cached images/s (NSGA-II population eval,
 PROMPTS_PER_STEP = 100
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant GEMM instance (FF up-projection,
 # M=51200 N=4608 K=1152) from the committed `ncu --set full` capture profiles/r1_kernels_ncu_full.csv
-NCU_TRAFFIC_BYTES_PER_LAUNCH = int((128.65 + 425.48) * 1e6)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = int((128.69 + 427.45) * 1e6)
 
 
 def load_candidates():
