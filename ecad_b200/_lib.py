@@ -44,6 +44,7 @@ EXPORTED_SYMBOLS = [
     "ecadk_create",
     "ecadk_destroy",
     "ecadk_pixart_blocks",
+    "ecadk_pixart_blocks_range",
     "ecadk_pixart_text_kv",
     "ecadk_silu_f32_bf16",
     "ecadk_flux_create",
@@ -205,6 +206,7 @@ def load() -> C.CDLL:
         "ecadk_create": [i, C.POINTER(EcadkModelDesc), C.POINTER(EcadkBlockWeights), C.POINTER(p)],
         "ecadk_destroy": [p],
         "ecadk_pixart_blocks": [p, C.POINTER(EcadkBlocksArgs), C.POINTER(C.c_uint8), C.POINTER(i), p],
+        "ecadk_pixart_blocks_range": [p, C.POINTER(EcadkBlocksArgs), C.POINTER(C.c_uint8), i, i, C.POINTER(i), p],
         "ecadk_pixart_text_kv": [p, p, i, i, i, C.POINTER(p), C.POINTER(p), C.POINTER(i), p],
         "ecadk_silu_f32_bf16": [p, p, sz, p],
         "ecadk_flux_create": [i, C.POINTER(EcadkFluxDesc), C.POINTER(EcadkFluxDoubleWeights),

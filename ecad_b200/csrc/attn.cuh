@@ -718,6 +718,414 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_consta
   }
 }
 
+
+// =====================================================================================================
+// Second-generation 256-query kernel (round 2): same math, TMEM map and softmax as attn_pair_kernel, but every stage
+// of an item is decoupled so that HBM streams continuously while MUFU and the tensor core stay busy:
+//
+//   * K and V are double-buffered PER ITEM, the two 128-query Q tiles have their own slots that are refilled as soon
+//     as their S = Q K^T has retired - every TMA load is issued a full item period before it is consumed (the first
+//     kernel waited ~2000 clk per item for Q/K: its single Q/K buffer could only be refilled half an item ahead);
+//   * the output leaves through shared memory and ONE TMA store per tile (warp 18) instead of row-strided 16-byte
+//     stores from the softmax threads: a warp store used to touch 32 different 128-byte lines (32 LSU passes per
+//     instruction, ~2000 clk of read-out per tile per item), now the softmax warps write conflict-free 16-byte pieces
+//     of dense 144-byte rows into smem, hand the tile's TMEM columns back at once and go on to the next item;
+//   * with 256 keys the staged output tiles live in the K buffer of the SAME item: K is dead once both S tiles have
+//     retired, which every o_full commit implies; the producer refills that buffer only after the stores have read it.
+// =====================================================================================================
+constexpr int kPair2Threads = 608;  // warp 0 TMA loads, warp 1 MMA, warps 2..17 softmax, warp 18 TMA stores
+
+template <int NK>
+struct AttnPair2Cfg {
+  static constexpr int kQTile = kAttnBM * 160;        // [128 x 128 B SW128][128 x 32 B SW32]
+  static constexpr int kQ = 0;                        // 2 tile slots
+  static constexpr int kKBuf = NK * 160;              // [NK x 128 B SW128][NK x 32 B SW32]
+  static constexpr int kK = kQ + 2 * kQTile;          // 2 buffers
+  static constexpr int kVBuf = NK * 160;              // five [NK x 32 B] SW32 atoms
+  static constexpr int kV = kK + 2 * kKBuf;           // 2 buffers
+  static constexpr int kOTile = kAttnBM * kHeadDim * 2;  // 18432: dense [128 x 72] bf16
+  static constexpr bool kAliasO = 2 * kOTile <= kKBuf;   // staged O tiles of item i live in K buffer (i & 1)
+  static constexpr int kO = kV + 2 * kVBuf;           // own staging (only when not aliased): [parity][tile]
+  static constexpr int kBias = kAliasO ? kO : kO + 4 * kOTile;  // 16 warps x NK/2 floats
+  static constexpr int kXch = kBias + 8 * NK * 4;
+  static constexpr int kBars = kXch + 2 * 16 * 32 * 4;
+  static constexpr int kPHi = NK == 256 ? 144 : 32;   // TMEM map: see AttnPairCfg
+  static constexpr int kOCol = NK == 256 ? 64 : 128;
+  static constexpr int kSmemNeed = kBars + 256 + 1024;
+  static constexpr int kSmemBytes = kSmemNeed > 120 * 1024 ? kSmemNeed : 120 * 1024;  // alone on its SM (512 TMEM columns)
+  static constexpr uint32_t kBytesQ = kAttnBM * kHeadPad * 2;
+  static constexpr uint32_t kBytesKV = NK * kHeadPad * 2;
+  static_assert(kSmemBytes <= 227 * 1024, "attn_pair2_kernel: shared memory");
+  static_assert(kOTile % 128 == 0 && kKBuf % 1024 == 0 && kQTile % 1024 == 0, "alignment");
+};
+
+template <int NK, bool HAS_BIAS>
+__global__ void __launch_bounds__(kPair2Threads, 1)
+attn_pair2_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_constant__ CUtensorMap tm_q16,
+                  const __grid_constant__ CUtensorMap tm_k64, const __grid_constant__ CUtensorMap tm_k16,
+                  const __grid_constant__ CUtensorMap tm_v16, const __grid_constant__ CUtensorMap tm_o,
+                  const AttnParams p, const int num_items) {
+  using Cfg = AttnPair2Cfg<NK>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBars);
+  uint64_t* q_full = bars + 0;     // [2] per query-tile slot, one phase per item
+  uint64_t* q_empty = bars + 2;    // [2]
+  uint64_t* k_full = bars + 4;     // [2] per buffer, one phase per two items
+  uint64_t* k_empty = bars + 6;    // [2]
+  uint64_t* v_full = bars + 8;     // [2]
+  uint64_t* v_empty = bars + 10;   // [2]
+  uint64_t* s_full = bars + 12;    // [2] per query tile, one phase per item
+  uint64_t* p_full = bars + 14;    // [2]
+  uint64_t* o_full = bars + 16;    // [2]
+  uint64_t* s_empty = bars + 18;   // [2]
+  uint64_t* o_free = bars + 20;    // [2] per item parity: both TMA stores of the item have read their staging
+  // [4] per (item parity, query tile), one phase per TWO items: the bf16 output tile is in shared memory.  (Per tile
+  // only - one phase per item - a tile that runs ahead could complete two phases between two probes of the store warp,
+  // which then waits for a parity that never shows: staging (b, t) again needs o_free[b], so per-buffer barriers
+  // cannot overrun.)
+  uint64_t* o_staged = bars + 22;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_q64);
+    tma_prefetch_desc(&tm_k64);
+    tma_prefetch_desc(&tm_v16);
+    tma_prefetch_desc(&tm_o);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 8);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&s_empty[i], 8);
+      mbar_init(&o_staged[i], 8);
+      mbar_init(&o_staged[2 + i], 8);
+      mbar_init(&o_free[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  griddep_launch_dependents();  // programmatic dependent launch: see gemm_bf16_kernel
+  griddep_wait();
+
+  // staging address of item parity b, query tile t
+  auto stage_off = [](int b, int t) -> int {
+    return Cfg::kAliasO ? Cfg::kK + b * Cfg::kKBuf + t * Cfg::kOTile : Cfg::kO + (b * 2 + t) * Cfg::kOTile;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer: runs one item ahead of the MMA warp =====================
+      int n = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++n) {
+        const int b = n & 1;
+        const uint32_t ph2 = ((n >> 1) & 1) ^ 1;  // "slot is free" parity of the per-buffer barriers
+        const int q_row = item * 256;
+        const int k_row = item * NK;
+        mbar_wait(&k_empty[b], ph2);
+        if constexpr (Cfg::kAliasO) mbar_wait(&o_free[b], ph2);  // item n-2's output tiles were staged in this buffer
+        uint8_t* kd = smem + Cfg::kK + b * Cfg::kKBuf;
+        mbar_arrive_expect_tx(&k_full[b], Cfg::kBytesKV);
+        tma_load_2d(kd, &tm_k64, &k_full[b], 0, k_row);
+        tma_load_2d(kd + NK * 128, &tm_k16, &k_full[b], 64, k_row);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&q_empty[t], (n & 1) ^ 1);
+          uint8_t* qd = smem + Cfg::kQ + t * Cfg::kQTile;
+          mbar_arrive_expect_tx(&q_full[t], Cfg::kBytesQ);
+          tma_load_2d(qd, &tm_q64, &q_full[t], 0, q_row + t * kAttnBM);
+          tma_load_2d(qd + kAttnBM * 128, &tm_q16, &q_full[t], 64, q_row + t * kAttnBM);
+        }
+        mbar_wait(&v_empty[b], ph2);
+        uint8_t* vd = smem + Cfg::kV + b * Cfg::kVBuf;
+        mbar_arrive_expect_tx(&v_full[b], Cfg::kBytesKV);
+        // V lands as FIVE 16-column (32-byte-swizzled) atoms: the 80-column head is one MN-major operand (N = 80)
+#pragma unroll
+        for (int a = 0; a < kHeadPad / 16; ++a) tma_load_2d(vd + a * (NK * 32), &tm_v16, &v_full[b], a * 16, k_row);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      // Static anti-phase order QK0(i), PV1(i-1), QK1(i), PV0(i) with blocking (hardware-suspended) barrier waits.
+      // Measured and rejected (round 2): a dynamic order in which this thread polls both tiles' barriers and issues
+      // whatever is ready - 128 keys 83 -> 88 us, 256 keys 99 -> 120 us: the probe loop shares its SM sub-partition's
+      // issue port with four softmax warps (with a nanosleep back-off it is no better); starting P V on the first half
+      // of the probabilities (128 keys only - with 256 keys O lives over S columns that are consumed last) and issuing
+      // the next S = Q K^T before the read-out: no gain either.
+      constexpr uint32_t idesc_s = make_idesc_bf16(kAttnBM, NK);
+      constexpr uint32_t idesc_o80 = make_idesc_bf16(kAttnBM, kHeadPad, 0, 1);
+      const uint32_t sbase = smem_u32(smem);
+      auto issue_qk = [&](int t, int b) {
+        const uint32_t d = tmem + 256 * t;
+        const uint32_t kb = sbase + Cfg::kK + b * Cfg::kKBuf;
+        const uint32_t qb = sbase + Cfg::kQ + t * Cfg::kQTile;
+        const uint64_t dk = make_smem_desc(kb, 16, 1024, kLayoutSW128);
+        const uint64_t dk2 = make_smem_desc(kb + NK * 128, 16, 256, kLayoutSW32);
+        const uint64_t dq = make_smem_desc(qb, 16, 1024, kLayoutSW128);
+        const uint64_t dq2 = make_smem_desc(qb + kAttnBM * 128, 16, 256, kLayoutSW32);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(d, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+        umma_bf16_ss(d, dq2, dk2, idesc_s, 1);
+        umma_commit(&s_full[t]);
+        umma_commit(&q_empty[t]);
+      };
+      auto issue_pv = [&](int t, int b) {
+        const uint32_t vbase = sbase + Cfg::kV + b * Cfg::kVBuf;
+        const uint32_t p_tmem = tmem + 256 * t;  // bf16 pairs: 8 columns per 16-key step
+        const uint32_t o_tmem = tmem + 256 * t + Cfg::kOCol;
+#pragma unroll
+        for (int ks = 0; ks < NK / 16; ++ks) {
+          const uint64_t dv = make_smem_desc(vbase + ks * 16 * 32, NK * 32, 256, kLayoutSW32);
+          const uint32_t pa = ks < NK / 32 ? p_tmem + ks * 8 : p_tmem + Cfg::kPHi + (ks - NK / 32) * 8;
+          umma_bf16_ts(o_tmem, pa, dv, idesc_o80, ks != 0);
+        }
+        umma_commit(&o_full[t]);
+      };
+      int n = 0;
+#ifdef ECADK_ATTN_TIMING
+      unsigned int dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      const unsigned int t_begin = clock();
+#endif
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++n) {
+        const int b = n & 1;
+        const uint32_t par = n & 1;
+        const uint32_t ph2 = (n >> 1) & 1;
+        ATTN_T(m0);
+        mbar_wait(&k_full[b], ph2);
+        mbar_wait(&q_full[0], par);
+        ATTN_T(m1);
+        mbar_wait(&s_empty[0], par ^ 1);  // previous item's O_0 has left TMEM
+        tc_fence_after();
+        ATTN_T(m2);
+        issue_qk(0, b);
+        ATTN_T(m3);
+        if (n > 0) {  // tile 1: PV of the previous item (anti-phase with tile 0)
+          mbar_wait(&p_full[1], par ^ 1);
+          tc_fence_after();
+          issue_pv(1, b ^ 1);
+          umma_commit(&v_empty[b ^ 1]);
+        }
+        ATTN_T(m4);
+        mbar_wait(&q_full[1], par);
+        mbar_wait(&s_empty[1], par ^ 1);
+        tc_fence_after();
+        issue_qk(1, b);
+        umma_commit(&k_empty[b]);
+        ATTN_T(m5);
+        mbar_wait(&v_full[b], ph2);
+        mbar_wait(&p_full[0], par);
+        tc_fence_after();
+        ATTN_T(m6);
+        issue_pv(0, b);
+        ATTN_T(m7);
+        ATTN_ACC(0, m0, m1);  // wait K + Q0
+        ATTN_ACC(1, m1, m2);  // wait O_0 read out
+        ATTN_ACC(2, m2, m3);  // issue QK0
+        ATTN_ACC(3, m3, m4);  // wait P1 + issue PV1
+        ATTN_ACC(4, m4, m5);  // wait Q1 + O_1 read out + issue QK1
+        ATTN_ACC(5, m5, m6);  // wait V + P0
+        ATTN_ACC(6, m6, m7);  // issue PV0
+      }
+#ifdef ECADK_ATTN_TIMING
+      dbg_acc[7] = n;
+      for (int i = 0; i < 8; ++i) g_attn_dbg[blockIdx.x * 32 + i] = dbg_acc[i];
+      g_attn_dbg[blockIdx.x * 32 + 24] = clock() - t_begin;
+#endif
+      if (n > 0) {  // drain: tile 1's PV of the last item
+        const int b = (n - 1) & 1;
+        mbar_wait(&p_full[1], (n - 1) & 1);
+        tc_fence_after();
+        issue_pv(1, b);
+        umma_commit(&v_empty[b]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 18) {
+    if (lane == 0) {
+      // ===================== TMA stores of the staged output tiles =====================
+      int n = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++n) {
+        const int b = n & 1;
+        const int sample = item / p.heads;
+        const int head = item - sample * p.heads;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&o_staged[b * 2 + t], (n >> 1) & 1);
+          tma_store_2d(&tm_o, smem + stage_off(b, t), head * kHeadDim, sample * 256 + t * kAttnBM);
+          tma_store_commit();
+        }
+        tma_store_wait_read0();  // both tiles have been read out of shared memory
+        mbar_arrive(&o_free[b]);
+      }
+      tma_store_wait_all0();
+    }
+    __syncwarp();
+  } else {
+    // ===================== softmax + read-out: warps 2..9 -> tile 0, warps 10..17 -> tile 1 =====================
+    // (two threads per score row, see attn_pair_kernel)
+    const int sw = warp - 2;
+    const int t = sw >> 3;
+    const int half = (sw >> 2) & 1;
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;
+    const uint32_t t_row = tmem + 256 * t + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t s_col = t_row + half * (NK / 2);
+    const uint32_t p_col = t_row + (half ? Cfg::kPHi : 0);
+    const uint32_t bias_a = smem_u32(smem + Cfg::kBias) + sw * (NK / 2) * 4;
+    const uint32_t xch = smem_u32(smem + Cfg::kXch);
+    const uint32_t my_slot = xch + (sw * 32 + lane) * 4;
+    const uint32_t peer_slot = xch + ((sw ^ 4) * 32 + lane) * 4;
+    const int bar_id = 1 + t * 4 + quarter;
+    constexpr int NC = NK / 64;  // 32-column chunks per thread
+    constexpr float kLog2e = 1.4426950408889634f;
+    float breg[NC];
+    auto fetch_bias = [&](int it) {
+      const float* bp = p.bias + static_cast<size_t>(it / p.heads) * NK + half * (NK / 2);
+#pragma unroll
+      for (int j = 0; j < NC; ++j) breg[j] = __ldg(bp + lane + 32 * j) * kLog2e;
+    };
+    if constexpr (HAS_BIAS) {
+      if (static_cast<int>(blockIdx.x) < num_items) fetch_bias(blockIdx.x);
+    }
+    int n = 0;
+#ifdef ECADK_ATTN_TIMING
+    unsigned int dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++n) {
+      const uint32_t par = n & 1;
+      const int b = n & 1;
+      if constexpr (HAS_BIAS) {
+#pragma unroll
+        for (int j = 0; j < NC; ++j) sts_f1(bias_a + (lane + 32 * j) * 4, breg[j]);
+        __syncwarp();
+        if (item + static_cast<int>(gridDim.x) < num_items) fetch_bias(item + gridDim.x);
+      }
+      ATTN_T(s0);
+      mbar_wait(&s_full[t], par);
+      tc_fence_after();
+      ATTN_T(s1);
+      float mx = -INFINITY;
+      uint64_t sum2 = pack_f2(0.f, 0.f);
+      if constexpr (NK == 128) {
+        uint32_t v[NC][32];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) tmem_ld_32x32(s_col + c * 32, v[c]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < NC; ++c) mx = softmax_chunk_prep<HAS_BIAS>(v[c], mx, p.scale_log2e, bias_a + c * 128);
+        if constexpr (!HAS_BIAS) mx *= p.scale_log2e;
+        sts_f1(my_slot, mx);
+        named_bar_sync(bar_id, 64);  // also: the partner has finished reading its S columns
+        mx = fmaxf(mx, lds_f1(peer_slot));
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          uint32_t pk[16];
+          softmax_chunk_exp_reg<HAS_BIAS>(v[c], pk, sum2, mx, p.scale_log2e);
+          tmem_st_32x16(p_col + c * 16, pk);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < NC; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(s_col + c * 32, v);
+          tmem_ld_wait();
+          mx = softmax_chunk_max<HAS_BIAS>(v, mx, p.scale_log2e, bias_a + c * 128);
+        }
+        if constexpr (!HAS_BIAS) mx *= p.scale_log2e;
+        sts_f1(my_slot, mx);
+        named_bar_sync(bar_id, 64);
+        mx = fmaxf(mx, lds_f1(peer_slot));
+#pragma unroll 1
+        for (int c = 0; c < NC; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(s_col + c * 32, v);
+          tmem_ld_wait();
+          uint32_t pk[16];
+          softmax_chunk_exp<HAS_BIAS>(v, pk, sum2, mx, p.scale_log2e, bias_a + c * 128);
+          tmem_st_32x16(p_col + c * 16, pk);  // always behind this thread's own S reads
+        }
+      }
+      float sum_lo, sum_hi;
+      unpack_f2(sum2, sum_lo, sum_hi);
+      const float sum = sum_lo + sum_hi;
+      sts_f1(my_slot + 16 * 32 * 4, sum);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t]);
+      ATTN_T(s2);
+      mbar_wait(&o_full[t], par);
+      tc_fence_after();
+      named_bar_sync(bar_id, 64);
+      ATTN_T(s3);
+      const float inv = 1.0f / (sum + lds_f1(peer_slot + 16 * 32 * 4));
+      // O_t leaves TMEM into registers; the tile's columns go straight back to the MMA warp
+      uint32_t v[32], w[16];
+      tmem_ld_32x32(t_row + Cfg::kOCol + half * 48, v);  // half 0: columns 0..31, half 1: 48..79 (72..79 are padding)
+      if (half == 0) tmem_ld_32x16(t_row + Cfg::kOCol + 32, w);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[t]);
+      // staging of item n is free once the stores of item n-2 have read it (with the K alias the producer has waited
+      // for that already before loading K(n); the wait is then immediately true)
+      mbar_wait(&o_free[b], ((n >> 1) & 1) ^ 1);
+      const uint32_t srow = smem_u32(smem + stage_off(b, t)) + row * (kHeadDim * 2) + half * 96;
+      auto stage8 = [&](const uint32_t* x, uint32_t addr) {
+        sts_u4(addr, pack_bf16x2(__uint_as_float(x[0]) * inv, __uint_as_float(x[1]) * inv),
+               pack_bf16x2(__uint_as_float(x[2]) * inv, __uint_as_float(x[3]) * inv),
+               pack_bf16x2(__uint_as_float(x[4]) * inv, __uint_as_float(x[5]) * inv),
+               pack_bf16x2(__uint_as_float(x[6]) * inv, __uint_as_float(x[7]) * inv));
+      };
+#pragma unroll
+      for (int g = 0; g < 3; ++g) stage8(v + g * 8, srow + g * 16);
+      if (half == 0) {
+        stage8(v + 24, srow + 48);
+        stage8(w, srow + 64);
+        stage8(w + 8, srow + 80);
+      }
+      fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_staged[b * 2 + t]);
+      ATTN_T(s4);
+      ATTN_ACC(0, s0, s1);  // wait S
+      ATTN_ACC(1, s1, s2);  // softmax (max, exchange, exp, P store)
+      ATTN_ACC(2, s2, s3);  // wait O
+      ATTN_ACC(3, s3, s4);  // O read-out + staging
+    }
+#ifdef ECADK_ATTN_TIMING
+    if (lane == 0 && (sw == 0 || sw == 12)) {
+      dbg_acc[7] = n;
+      for (int i = 0; i < 8; ++i) g_attn_dbg[blockIdx.x * 32 + (sw == 0 ? 8 : 16) + i] = dbg_acc[i];
+    }
+#endif
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 }  // namespace ecadk
 
 namespace ecadk {

@@ -363,6 +363,22 @@ int launch_attn_pair_inst(const CUtensorMap* tq, const CUtensorMap* tm, const At
   return check_launch("attn_pair_kernel");
 }
 
+template <int NK, bool HAS_BIAS>
+int launch_attn_pair2_inst(const CUtensorMap* tq, const CUtensorMap* tm, const CUtensorMap& to, const AttnParams& p,
+                           int items, cudaStream_t stream) {
+  using Cfg = AttnPair2Cfg<NK>;
+  static bool configured = false;
+  auto kern = attn_pair2_kernel<NK, HAS_BIAS>;
+  if (!configured) {
+    ECADK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int grid = items < num_sms() ? items : num_sms();
+  launch_pdl(kern, dim3(grid), dim3(kPair2Threads), Cfg::kSmemBytes, stream, tq[0], tq[1], tm[2], tm[3], tm[5], to, p,
+             items);
+  return check_launch("attn_pair2_kernel");
+}
+
 template <int HD, bool HAS_BIAS>
 int launch_attn_flash_inst(const CUtensorMap* tq, const CUtensorMap* tkv, const AttnParams& p, int n_keys, int items,
                            cudaStream_t stream) {
@@ -429,7 +445,7 @@ int launch_attention(const void* q, const void* k, const void* v, const float* b
   static const int forced = [] {
     const char* e = getenv("ECADK_ATTN_MODE");
     if (e == nullptr) return 0;
-    return strcmp(e, "tile") == 0 ? 1 : (strcmp(e, "flash") == 0 ? 2 : 0);
+    return strcmp(e, "tile") == 0 ? 1 : (strcmp(e, "flash") == 0 ? 2 : (strcmp(e, "pair1") == 0 ? 3 : 0));
   }();
   AttnParams p;
   p.heads = heads;
@@ -467,6 +483,21 @@ int launch_attention(const void* q, const void* k, const void* v, const float* b
     if ((rc = make_tmap_bf16(&tq[0], q, q_rows, kHeadPad, kHeadPad, 256, 64, 128))) return rc;
     if ((rc = make_tmap_bf16(&tq[1], q, q_rows, kHeadPad, kHeadPad, 256, 16, 32))) return rc;
     const int items = samples * heads;
+    if (forced != 3) {
+      // second-generation kernel: per-tile Q slots, per-item K/V double buffering, output through smem + TMA store
+      CUtensorMap tq1[2], to;
+      if ((rc = make_tmap_bf16(&tq1[0], q, q_rows, kHeadPad, kHeadPad, kAttnBM, 64, 128))) return rc;
+      if ((rc = make_tmap_bf16(&tq1[1], q, q_rows, kHeadPad, kHeadPad, kAttnBM, 16, 32))) return rc;
+      if ((rc = make_tmap_bf16(&to, out, static_cast<uint64_t>(samples) * q_tokens, heads * kHeadDim, p.out_ld, kAttnBM,
+                               kHeadDim, 0)))
+        return rc;
+      if (n_keys == 256) {
+        return bias ? launch_attn_pair2_inst<256, true>(tq1, tm, to, p, items, stream)
+                    : launch_attn_pair2_inst<256, false>(tq1, tm, to, p, items, stream);
+      }
+      return bias ? launch_attn_pair2_inst<128, true>(tq1, tm, to, p, items, stream)
+                  : launch_attn_pair2_inst<128, false>(tq1, tm, to, p, items, stream);
+    }
     if (n_keys == 256) {
       return bias ? launch_attn_pair_inst<256, true>(tq, tm, p, items, stream)
                   : launch_attn_pair_inst<256, false>(tq, tm, p, items, stream);
@@ -1240,8 +1271,16 @@ int ecadk_pixart_text_kv(ecadk_handle_t h, const void* enc, int samples, int tex
 
 int ecadk_pixart_blocks(ecadk_handle_t h, const EcadkBlocksArgs* a, const uint8_t* executed, int* n_launches,
                         ecadk_stream_t stream_) {
+  ECADK_REQUIRE(h, "pixart_blocks: null handle");
+  return ecadk_pixart_blocks_range(h, a, executed, 0, h->desc.num_layers, n_launches, stream_);
+}
+
+int ecadk_pixart_blocks_range(ecadk_handle_t h, const EcadkBlocksArgs* a, const uint8_t* executed, int block_begin,
+                              int block_end, int* n_launches, ecadk_stream_t stream_) {
   ECADK_REQUIRE(h && a && executed, "pixart_blocks: null argument");
   const EcadkModelDesc& d = h->desc;
+  ECADK_REQUIRE(block_begin >= 0 && block_begin <= block_end && block_end <= d.num_layers,
+                "pixart_blocks: block range [%d, %d) outside [0, %d]", block_begin, block_end, d.num_layers);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int D = d.dim, M = a->samples * a->tokens, S6 = a->temb_stride;
   ECADK_REQUIRE(S6 == 0 || S6 == 6 * D, "pixart_blocks: temb_stride must be 0 or 6*dim");
@@ -1279,7 +1318,7 @@ int ecadk_pixart_blocks(ecadk_handle_t h, const EcadkBlocksArgs* a, const uint8_
     return ECADK_OK;
   };
 
-  for (int b = 0; b < d.num_layers; ++b) {
+  for (int b = block_begin; b < block_end; ++b) {
     const EcadkBlockWeights& w = h->blocks[b];
     const float* tab = w.scale_shift_table;
     const bool ex1 = executed[b * 3 + 0], ex2 = executed[b * 3 + 1], ex3 = executed[b * 3 + 2];

@@ -38,15 +38,42 @@ class PromptEmbeddingDataset:
             out[key] = value.squeeze() if isinstance(value, torch.Tensor) else value
         return out
 
-    def batches(self, batch_size: int, pin_memory: bool = False) -> Iterator[dict[str, torch.Tensor | list[str]]]:
-        """Stack consecutive prompts into PixArtPromptEmbedding batches (drop nothing; the last batch may be short)."""
-        for start in range(0, len(self), batch_size):
-            items = [self[i] for i in range(start, min(start + batch_size, len(self)))]
-            batch: dict[str, torch.Tensor | list[str]] = {
-                "name": [it["name"] for it in items],
-                "relative_path": [it["relative_path"] for it in items],
-            }
-            for key in PIXART_KEYS:
-                t = torch.stack([it[key] for it in items])
-                batch[key] = t.pin_memory() if pin_memory and torch.cuda.is_available() else t
+    def batches(self, batch_size: int, pin_memory: bool = False, shuffle: bool = False,
+                seed: int | None = None) -> "EmbeddingBatches":
+        """What the reference gets from ``DataLoader(dataset, batch_size, shuffle, pin_memory=True)``
+        (image_generator.py:278-300): every tensor key of the per-prompt dicts stacked along a new batch dimension
+        (PixArt: the four PIXART_KEYS; FLUX: prompt_embeds / pooled_prompt_embeds), string keys collected into lists;
+        nothing is dropped, the last batch may be short.  The result has a ``len()`` like a DataLoader."""
+        return EmbeddingBatches(self, batch_size, pin_memory, shuffle, seed)
+
+
+class EmbeddingBatches:
+    def __init__(self, dataset: PromptEmbeddingDataset, batch_size: int, pin_memory: bool = False,
+                 shuffle: bool = False, seed: int | None = None):
+        if batch_size < 1:
+            raise ValueError("batch_size must be >= 1")
+        self.dataset, self.batch_size, self.pin_memory, self.shuffle, self.seed = (dataset, batch_size, pin_memory,
+                                                                                   shuffle, seed)
+
+    def __len__(self) -> int:
+        return (len(self.dataset) + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self) -> Iterator[dict[str, torch.Tensor | list[str]]]:
+        order = list(range(len(self.dataset)))
+        if self.shuffle:
+            g = torch.Generator()
+            if self.seed is not None:
+                g.manual_seed(self.seed)
+            order = torch.randperm(len(order), generator=g).tolist()
+        pin = self.pin_memory and torch.cuda.is_available()
+        for start in range(0, len(order), self.batch_size):
+            items = [self.dataset[i] for i in order[start:start + self.batch_size]]
+            batch: dict[str, torch.Tensor | list[str]] = {}
+            for key in items[0]:
+                vals = [it[key] for it in items]
+                if isinstance(vals[0], torch.Tensor):
+                    t = torch.stack(vals)
+                    batch[key] = t.pin_memory() if pin else t
+                else:
+                    batch[key] = vals
             yield batch

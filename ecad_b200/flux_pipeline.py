@@ -24,12 +24,23 @@ def calculate_shift(image_seq_len: int, base_seq_len: int = 256, max_seq_len: in
 
 class FlowMatchEulerDiscrete:
     """FlowMatchEulerDiscreteScheduler under FLUX.1-dev's scheduler_config (use_dynamic_shifting: sigma' =
-    e^mu / (e^mu + (1/sigma - 1))); ``step`` is x += (sigma_next - sigma) * v, run by ``ecadk_axpy_f32``."""
+    e^mu / (e^mu + (1/sigma - 1))); ``step`` is x += (sigma_next - sigma) * v, run by ``ecadk_axpy_f32``.
+
+    ``config`` carries the values diffusers' FluxPipeline hands to ``calculate_shift`` (``scheduler.config.*``):
+    FLUX.1-dev's scheduler_config.json = base_shift 0.5, max_shift 1.15, base_image_seq_len 256, max_image_seq_len 4096
+    (also the constructor defaults of FlowMatchEulerDiscreteScheduler; the 1.16 in ``calculate_shift``'s signature is
+    never used by the pipeline).  Recalled, not verifiable here: the reference ships no scheduler config."""
 
     order = 1
     num_train_timesteps = 1000
 
-    def __init__(self):
+    def __init__(self, base_shift: float = 0.5, max_shift: float = 1.15, base_image_seq_len: int = 256,
+                 max_image_seq_len: int = 4096):
+        from types import SimpleNamespace
+
+        self.config = SimpleNamespace(base_shift=base_shift, max_shift=max_shift,
+                                      base_image_seq_len=base_image_seq_len, max_image_seq_len=max_image_seq_len,
+                                      num_train_timesteps=self.num_train_timesteps, use_dynamic_shifting=True)
         self.sigmas = np.zeros(0, dtype=np.float32)
         self.timesteps = torch.empty(0)
         self.step_index = 0
@@ -149,18 +160,26 @@ class B200FluxPipeline:
         text_ids = torch.zeros(batch_size, prompt_embeds.shape[1], 3)
         latents, img_ids = self.prepare_latents(batch_size, tr.config.in_channels // 4, height, width, generator, latents)
         n_tokens = latents.shape[1]
-        sched.set_timesteps(num_inference_steps, device=dev, mu=calculate_shift(n_tokens))
+        sc = sched.config
+        mu = calculate_shift(n_tokens, sc.base_image_seq_len, sc.max_image_seq_len, sc.base_shift, sc.max_shift)
+        sched.set_timesteps(num_inference_steps, device=dev, mu=mu)
         guidance = torch.full((batch_size,), float(guidance_scale), dtype=torch.float32, device=dev) \
             if tr.config.guidance_embeds else None
         inputs = {"latents": latents.contiguous(), "prompt_embeds": prompt_embeds,
                   "pooled_prompt_embeds": pooled_prompt_embeds, "guidance": guidance,
                   "timesteps": (sched.timesteps / 1000).to(dev)}
         if self.use_cuda_graph:
-            key = ("flux", id(tr.cache_schedule), getattr(tr.cache_schedule, "name", None), tuple(latents.shape),
-                   tuple(prompt_embeds.shape), num_inference_steps, float(guidance_scale))
+            # keyed on the schedule's CONTENT (not its id/name: a freed candidate's address can be reused) and on the
+            # transformer's buffer epoch (a recorded graph holds raw pointers into its workspace)
+            if getattr(tr, "buffer_epoch", 0) != getattr(self, "_graph_epoch", None):
+                self._graphs.clear()
+                self._graph_epoch = getattr(tr, "buffer_epoch", 0)
+            key = ("flux", tr.cache_schedule.content_key(), tuple(latents.shape), tuple(prompt_embeds.shape),
+                   num_inference_steps, float(guidance_scale), float(mu))
             latents = self._graphs.run(
                 key, inputs, lambda st, cb: self._denoise(st, text_ids, img_ids, cb),
                 capture_callback if capture_callback is not None else callback_on_step_end, tr)
+            self._graph_epoch = getattr(tr, "buffer_epoch", 0)  # buffers created by the run's own eager warm-up
             if callback_on_step_end is not None:
                 for i, t in enumerate(sched.timesteps):
                     out = callback_on_step_end(self, i, t, {"latents": latents, "prompt_embeds": prompt_embeds})

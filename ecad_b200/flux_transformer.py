@@ -97,6 +97,7 @@ class B200FluxTransformer2D:
         self.last_dead: np.ndarray | None = None
         self.warnings: list[str] = []
         self.launches = 0
+        self.buffer_epoch = 0  # bumped when the workspace moves: recorded CUDA graphs point into it (see pipelines)
 
     @classmethod
     def from_random_init(cls, dit_scheduler, cache_schedule=None, config: FluxConfig = FluxConfig(), seed: int = 0,
@@ -225,6 +226,7 @@ class B200FluxTransformer2D:
         S = N + T
         bf, f32 = torch.bfloat16, torch.float32
         self._ws = {}
+        self.buffer_epoch += 1
         ws: dict[str, Any] = {}
         ws["x_img"] = torch.empty(B * N, D, device=dev, dtype=f32)
         ws["x_txt"] = torch.empty(B * T, D, device=dev, dtype=f32)
@@ -441,9 +443,9 @@ class B200FluxTransformer2D:
                                            st), "proj_out")
         launches += 2
         self.launches += launches
+        # a fresh tensor like the reference returns (the workspace buffer is overwritten by the next forward)
         out = ws["out"].view(B, N, self.out_channels)
-        if hidden_states.dtype != torch.float32:
-            out = out.to(hidden_states.dtype)
+        out = out.clone() if hidden_states.dtype == torch.float32 else out.to(hidden_states.dtype)
         if not return_dict:
             return (out,)
         return Transformer2DModelOutput(sample=out)

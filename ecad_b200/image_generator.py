@@ -21,7 +21,75 @@ from .transformer import B200PixArtTransformer2D, SequentialDiTScheduler
 from .weights import PixArtConfig, random_init_state_dict
 
 
-class B200PixArtImageGenerator:
+class _SavedPromptMixin:
+    """The file-driven half of the reference's ImageGenerator base class, shared by the PixArt and FLUX generators:
+    ``load_and_batch_embeddings`` (image_generator.py:278-300), ``generate_from_saved_prompts`` (:366-421),
+    ``save_image`` (:423-440), ``time_image_generation`` (:442-487), ``free_diffusion_pipeline`` (:262-276).
+    Same argument names and file naming; the saved artefact is the latent tensor (``.pt``) because the VAE / PIL stage
+    is out of scope."""
+
+    def load_and_batch_embeddings(self, embedding_dir: Path | str, batch_size: int, shuffle: bool = False):
+        from .dataset import PromptEmbeddingDataset
+
+        return PromptEmbeddingDataset(embedding_dir).batches(batch_size, pin_memory=True, shuffle=shuffle)
+
+    def free_diffusion_pipeline(self) -> None:
+        import gc
+
+        if self.diffusion_pipeline is not None:
+            self.diffusion_pipeline = None
+            gc.collect()
+            torch.cuda.empty_cache()
+        else:
+            print("WARNING: No diffusion pipeline to free.")
+
+    def save_image(self, image: torch.Tensor, output_path: Path | str) -> None:
+        output_path = Path(output_path)
+        if output_path.suffix != ".pt":
+            output_path = Path(f"{output_path}.pt")
+        output_path.parent.mkdir(parents=True, exist_ok=True)
+        torch.save(image.detach().cpu().clone(), output_path)
+
+    @torch.inference_mode()
+    def generate_from_saved_prompts(self, input_dir: Path | str, output_dir: Path | str, batch_size: int = 1,
+                                    images_per_prompt: int = 1, free_after: bool = False,
+                                    include_seed_in_name: bool = True, **kwargs: Any) -> None:
+        if self.diffusion_pipeline is None:
+            self.create_diffusion_pipeline()
+        output_dir = Path(output_dir)
+        for embeds in self.load_and_batch_embeddings(input_dir, batch_size, False):
+            # generate_images returns [images_per_prompt] tensors of [batch, ...]; the reference's nesting is
+            # [prompt][seed] - same files either way
+            images = self.generate_images(embeds, images_per_prompt, **kwargs)
+            for j, (name, rel_path) in enumerate(zip(embeds["name"], embeds["relative_path"])):
+                for i in range(images_per_prompt):
+                    image_seed = self.start_seed + i * self.seed_step
+                    name_with_seed = f"{name}__image_seed:{image_seed:03}" if include_seed_in_name else name
+                    self.save_image(images[i][j], output_dir / rel_path / name_with_seed)
+        if free_after:
+            self.free_diffusion_pipeline()
+
+    @torch.inference_mode()
+    def time_image_generation(self, input_dir: Path | str, batch_size: int = 1, num_batches: int = 1,
+                              free_after: bool = False, **kwargs: Any) -> list[float]:
+        """ms per image of ``num_batches`` timed pipeline calls, cycling over the directory as often as needed."""
+        if self.diffusion_pipeline is None:
+            self.create_diffusion_pipeline()
+        all_times: list[float] = []
+        while len(all_times) < num_batches:
+            loader = self.load_and_batch_embeddings(input_dir, batch_size, False)
+            if len(loader) == 0:
+                raise ValueError(f"no *.pt prompt embeddings under {input_dir}")
+            for embeds in loader:
+                all_times.append(self.generate_images_timed(embeds, **kwargs))
+                if len(all_times) >= num_batches:
+                    break
+        if free_after:
+            self.free_diffusion_pipeline()
+        return all_times
+
+
+class B200PixArtImageGenerator(_SavedPromptMixin):
     default_pipeline_name = "pixart_alpha"
     text_tokens = 120
 
@@ -164,8 +232,28 @@ class B200PixArtAlphaImageGenerator(B200PixArtImageGenerator):
     """Selected by ``config.image_generator = "b200_pixart_alpha"`` in a schedule JSON (ecad/types.py:43-47)."""
 
 
+@ImageGeneratorRegistry.register("b200_pixart_sigma")
+@ImageGeneratorRegistry.register("PixArtSigmaImageGenerator")
+class B200PixArtSigmaImageGenerator(B200PixArtImageGenerator):
+    """PixArt-sigma (ecad/image_generators/pixart_sigma_image_generator.py:8-40): same transformer blocks, 300 text
+    tokens instead of 120, no micro-conditions at any resolution.  Registered under the reference's own class name too,
+    so a schedule JSON with ``config.image_generator = "PixArtSigmaImageGenerator"`` selects it."""
+
+    default_pipeline_name = "pixart_sigma"
+    text_tokens = 300
+
+    def __init__(self, *args, model_config: PixArtConfig | None = None, **kwargs):
+        if model_config is None:
+            model_config = PixArtConfig(use_additional_conditions=False)
+        super().__init__(*args, model_config=model_config, **kwargs)
+
+
+ImageGeneratorRegistry.registry.setdefault("PixArtAlphaImageGenerator", B200PixArtAlphaImageGenerator)
+
+
 @ImageGeneratorRegistry.register("b200_flux")
-class B200FluxImageGenerator:
+@ImageGeneratorRegistry.register("FluxImageGenerator")
+class B200FluxImageGenerator(_SavedPromptMixin):
     """FLUX.1 counterpart (/root/reference/ecad/image_generators/flux_image_generator.py:29-418): same defaults
     (256x256, guidance 5, 20 steps), same callback protocol - the pipeline calls
     ``_call_callbacks_wrapper(pipeline, step, timestep, callback_kwargs)`` which advances the step counters, runs the

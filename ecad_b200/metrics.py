@@ -27,8 +27,15 @@ def executed_trace(schedule: CacheSchedule) -> np.ndarray:
     rule for attn2 when the schedule carries it)."""
     if isinstance(schedule, FluxCacheSchedule):
         return trace_decisions(schedule.dense())
-    gate = schedule.gate_step() if isinstance(schedule, PixArtCacheSchedule) else None
-    return trace_decisions(schedule.to_numpy(), attn2_tgate_gate_step=gate)
+    gates = None
+    if isinstance(schedule, PixArtCacheSchedule):
+        # what the runtime decides from: the gate_step kwarg of each block's compute_attn_tgate entry
+        # (cached_transformer_block.py:393-454); a schedule that only carries the pipeline-level TGATE config (no block
+        # entry names the function) falls back to that value for every block
+        gates = schedule.block_gate_steps()
+        if (gates < 0).all():
+            gates = schedule.gate_step()
+    return trace_decisions(schedule.to_numpy(), attn2_tgate_gate_step=gates)
 
 
 def macs_metrics(schedule: CacheSchedule, tokens: int = 256, text_tokens: int | None = None,

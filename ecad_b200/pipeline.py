@@ -142,9 +142,10 @@ class B200PixArtPipeline:
                 e_in, m_in = embeds, mask
             model_in = sched.scale_model_input(model_in, t)
             current_timestep = timesteps_dev[i:i + 1].expand(model_in.shape[0])
+            if hasattr(tr, "hint_timestep"):
+                tr.hint_timestep(float(t))  # host value of the shared timestep (table cache key), not an argument
             noise_pred = tr(model_in, encoder_hidden_states=e_in, encoder_attention_mask=m_in,
-                            timestep=current_timestep, added_cond_kwargs=cond_in, return_dict=False,
-                            timestep_host=float(t))[0]
+                            timestep=current_timestep, added_cond_kwargs=cond_in, return_dict=False)[0]
             c = sched.coefficients()
             _lib.check(
                 lib.ecadk_cfg_dpm_step(noise_pred.data_ptr(), latents.data_ptr(), x0_prev.data_ptr(), batch_size,
@@ -231,11 +232,19 @@ class B200PixArtPipeline:
                 aspect_ratio = torch.cat([aspect_ratio, aspect_ratio], dim=0)
             inputs["resolution"], inputs["aspect_ratio"] = resolution.to(dev), aspect_ratio.to(dev)
         if self.use_cuda_graph:
-            key = ("pixart", id(tr.cache_schedule), getattr(tr.cache_schedule, "name", None), tuple(latents.shape),
-                   tuple(embeds.shape), num_inference_steps, float(guidance_scale), self.gate_step, height, width)
+            # keyed on the schedule's CONTENT (not its id/name: in a set_schedule() loop over GA candidates a freed
+            # schedule's address is reused) and dropped whenever the transformer's buffers moved (a recorded graph
+            # holds raw pointers into the workspace and the per-timestep tables)
+            if getattr(tr, "buffer_epoch", 0) != getattr(self, "_graph_epoch", None):
+                self._graphs.clear()
+                self._graph_epoch = getattr(tr, "buffer_epoch", 0)
+            key = ("pixart", tr.cache_schedule.content_key(), tuple(latents.shape), tuple(embeds.shape),
+                   num_inference_steps, float(guidance_scale), self.gate_step, height, width,
+                   bool(getattr(tr, "skip_dead_cache_stores", True)))
             latents = self._graphs.run(
                 key, inputs, lambda st, cb: self._denoise(st, batch_size, do_cfg, guidance_scale, height, width, cb, 1),
                 capture_callback if capture_callback is not None else callback, tr)
+            self._graph_epoch = getattr(tr, "buffer_epoch", 0)  # buffers created by the run's own eager warm-up
             if callback is not None:  # user-visible per-step protocol (counters, extra callbacks, reset LAST)
                 for i, t in enumerate(sched.timesteps):
                     if i % callback_steps == 0:

@@ -60,10 +60,26 @@ class PopulationEvaluator:
         parts = (partition_lpt(costs, self.world_size) if costs is not None
                  else partition_round_robin(n_units, self.world_size))
         mine = parts[self.rank]
+        timed = self.device.type == "cuda"
+        if timed:  # device-side clock of this rank's own work and of the whole call (incl. the gather)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
         local = [run_unit(i) for i in mine]
+        if timed:
+            ev[1].record()
         out = {"assignment": parts, "local_indices": mine, "local": local}
         if gather:
             out["results"] = self.gather(local, parts, n_units)
+        if timed:
+            ev[2].record()
+            torch.cuda.synchronize(self.device)
+            out["busy_s"] = ev[0].elapsed_time(ev[1]) * 1e-3
+            out["total_s"] = ev[0].elapsed_time(ev[2]) * 1e-3
+        if costs is not None:
+            loads = [sum(float(costs[i]) for i in p) for p in parts]
+            out["planned_load"] = loads
+            # what the cost model predicts for this split: mean load / max load (1.0 = perfectly balanced)
+            out["planned_efficiency"] = (sum(loads) / len(loads)) / max(loads) if max(loads) > 0 else 1.0
         return out
 
     def run_from_host(self, unit_indices: Sequence[int], run_unit: Callable[[int, dict], torch.Tensor],

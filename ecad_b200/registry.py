@@ -26,10 +26,36 @@ class DecisionContext:
 
 
 class ComputeRegistry:
-    """custom_attn_ff.py:6-49 - register by lower-cased function name; unknown/None name -> DEFAULT."""
+    """custom_attn_ff.py:6-49 - register by lower-cased function name; unknown/None name -> DEFAULT.
+
+    Two kinds of entries share the name space:
+      * decision policies ``policy(ctx) -> bool`` (``register``): the fast path - the host only decides run / reuse and
+        the C executor does the rest;
+      * tensor functions with the REFERENCE's signature (``register_tensor``):
+        ``f(block, attn, hidden_states, encoder_hidden_states, attention_mask, **kwargs) -> Tensor`` for attention and
+        ``f(block, norm_hidden_states, **kwargs) -> Tensor`` for the feed-forward
+        (cached_transformer_block.py:141-149,161-165).  ``block`` is a `B200BlockProxy`: ``block.attn1`` / ``attn2`` /
+        ``ff`` run the sm_100a kernels of that block, ``block.cached_attn1_output`` etc. are the HBM cache slots,
+        ``block.cache_schedule`` / ``block.block_num`` as in the reference.  A block that names a tensor function at a
+        step is executed sub-block by sub-block from Python at that step (the other blocks stay in the C executor).
+    """
 
     _registry: dict[str, Callable[[DecisionContext], bool]] = {}
+    _tensor_registry: dict[str, Callable[..., Any]] = {}
     DEFAULT: str = ""
+
+    @classmethod
+    def register_tensor(cls, func: Callable[..., Any]) -> Callable[..., Any]:
+        """Decorator with the reference's registration rule (custom_attn_ff.py:10-20: lower-cased ``__name__``)."""
+        name = func.__name__.lower()
+        if name in cls._registry:
+            raise ValueError(f"'{name}' is a built-in decision policy; pick another name for a tensor function")
+        cls._tensor_registry[name] = func
+        return func
+
+    @classmethod
+    def get_tensor(cls, key: str | None):
+        return cls._tensor_registry.get(key.lower()) if key is not None else None
 
     @classmethod
     def register(cls, func: Callable[[DecisionContext], bool]) -> Callable[[DecisionContext], bool]:
@@ -56,12 +82,46 @@ class ComputeRegistry:
 
 class ComputeAttnRegistry(ComputeRegistry):
     _registry: dict[str, Callable[[DecisionContext], bool]] = {}
+    _tensor_registry: dict[str, Callable[..., Any]] = {}
     DEFAULT = "compute_attn_cached"
 
 
 class ComputeFFRegistry(ComputeRegistry):
     _registry: dict[str, Callable[[DecisionContext], bool]] = {}
+    _tensor_registry: dict[str, Callable[..., Any]] = {}
     DEFAULT = "compute_ff_cached"
+
+
+# Tensor-level restatements of the reference defaults, for use INSIDE user functions and for the sub-blocks of a
+# Python-executed block that keep the default behaviour (cached_transformer_block.py:326-391).
+def compute_attn_cached_tensor(block, attn: str, hidden_states, encoder_hidden_states=None, attention_mask=None,
+                               **cross_attention_kwargs):
+    if attn not in ("attn1", "attn2"):
+        raise ValueError(f"Invalid attention type: {attn}. Must be attn1 or attn2")
+    recompute = block.cache_schedule.get_recompute(block.block_num, attn)
+    cached = getattr(block, f"cached_{attn}_output")
+    if recompute or cached is None:
+        if not recompute:
+            print(f"WARNING: No cached {attn} found. Recomputing.")
+        out = getattr(block, attn)(hidden_states, encoder_hidden_states=encoder_hidden_states,
+                                   attention_mask=attention_mask, **cross_attention_kwargs)
+    else:
+        out = cached
+    setattr(block, f"cached_{attn}_output", out)
+    return out
+
+
+def compute_ff_cached_tensor(block, norm_hidden_states, **kwargs):
+    recompute = block.cache_schedule.get_recompute(block.block_num, "ff")
+    cached = block.cached_ff_output
+    if recompute or cached is None:
+        if not recompute:
+            print("WARNING: No cached ff found. Recomputing.")
+        out = block.ff(norm_hidden_states)
+    else:
+        out = cached
+    block.cached_ff_output = out
+    return out
 
 
 def _warn_no_cache(ctx: DecisionContext) -> None:
@@ -115,7 +175,28 @@ class ImageGeneratorRegistry:
         return deco
 
     @classmethod
-    def get(cls, name: str) -> type:
-        if name not in cls.registry:
-            raise ValueError(f"Image generator {name} not found. Available: {sorted(cls.registry)}")
-        return cls.registry[name]
+    def get(cls, name: str, default_name: str | None = None) -> type | None:
+        """load_image_generator.py:23-40: the class registered under ``name``, else the one under ``default_name``,
+        else ``None`` (the callers raise, see get_image_generator_type)."""
+        klass = cls.registry.get(name, None)
+        if klass is None and default_name is not None:
+            klass = cls.registry.get(default_name, None)
+        return klass
+
+
+def get_image_generator_type_from_config(config: dict, default_name: str = "PixArtImageGenerator") -> type:
+    """load_image_generator.py:43-66."""
+    klass = None
+    if "image_generator" in config:
+        klass = ImageGeneratorRegistry.get(config["image_generator"], default_name)
+    if klass is None:
+        raise ValueError(f"Image generator not found in config: {config}.")
+    return klass
+
+
+def get_image_generator_type(name: str, default_name: str = "PixArtImageGenerator") -> type:
+    """load_image_generator.py:69-84."""
+    klass = ImageGeneratorRegistry.get(name, default_name)
+    if klass is None:
+        raise ValueError(f"Image generator not found: {name}.")
+    return klass

@@ -93,6 +93,19 @@ class CacheSchedule:
             self._flags = arr
         return self._flags
 
+    def content_key(self) -> str:
+        """Digest of everything that decides what a generation executes (flags, custom decision functions and their
+        kwargs, the pipeline/config block).  Two schedules with the same key replay the same recorded work, whatever
+        their names or object identities are - the key of the whole-generation CUDA-graph cache."""
+        import hashlib
+
+        h = hashlib.sha1()
+        h.update(type(self).__name__.encode())
+        h.update(repr((self.num_blocks, self.num_inference_steps, getattr(self, "num_single_blocks", None))).encode())
+        h.update(json.dumps(self.schedule, sort_keys=True, default=str).encode())
+        h.update(json.dumps(self.top_level_config, sort_keys=True, default=str).encode())
+        return h.hexdigest()
+
     # ---- JSON (cache_schedule.py:75-112) ----------------------------------------------------------
     def to_dict(self) -> dict[str, Any]:
         return {
@@ -198,7 +211,8 @@ class PixArtCacheSchedule(CacheSchedule):
         return out
 
     def gate_step(self) -> int | None:
-        """TGATE gate step, from the pipeline config (ecad/pipelines/tgate.py:329-341) or the block kwargs."""
+        """TGATE gate step of the PIPELINE (``config.pipeline``, ecad/pipelines/tgate.py:329-341): from this step on
+        the loop drops the CFG pair.  The per-block decision rule is `block_gate_steps`."""
         pipe = (self.top_level_config or {}).get("pipeline") or {}
         if pipe.get("name") == "tgate":
             g = (pipe.get("kwargs") or {}).get("gate_step")
@@ -206,10 +220,25 @@ class PixArtCacheSchedule(CacheSchedule):
                 return int(g)
         return None
 
+    def block_gate_steps(self) -> np.ndarray:
+        """``int32[S][NB]``: the ``gate_step`` kwarg of every (step, block) whose ``custom_compute_attn`` resolves to
+        ``compute_attn_tgate`` (cached_transformer_block.py:393-454), -1 elsewhere - what the runtime decides from.
+        A block entry that names TGATE without a ``gate_step`` raises like the reference (:438-440)."""
+        out = np.full((self.num_inference_steps, self.num_blocks), -1, dtype=np.int32)
+        for step, blocks in self.schedule.items():
+            for key, entry in blocks.items():
+                cfg = entry.get("custom_compute_attn") or {}
+                if (cfg.get("name") or "").lower() == ATTN_TGATE:
+                    g = (cfg.get("kwargs") or {}).get("gate_step")
+                    if g is None:
+                        raise ValueError("gate_step must be provided as a kwarg to commpute_attn_tgate.")
+                    out[step, int(key)] = int(g)
+        return out
+
 
 def trace_decisions(
     flags: np.ndarray,
-    attn2_tgate_gate_step: int | None = None,
+    attn2_tgate_gate_step: int | np.ndarray | None = None,
 ) -> np.ndarray:
     """Executed/reused decision of every (step, block, component) over one generation.
 
@@ -218,19 +247,28 @@ def trace_decisions(
     ecad/image_generators/image_generator.py:197-202) and are filled by the first pass through a sub-block.
     TGATE attn2 (``compute_attn_tgate``, :393-454): the flag rule applies while ``curr_step <= gate_step-1``;
     from ``gate_step`` on attn2 is never executed (the reference asserts the cache exists).
+    ``attn2_tgate_gate_step``: one gate step for every block, or ``int[S][NB]`` per (step, block) with -1 = the block
+    decides through ``compute_attn_cached`` (`PixArtCacheSchedule.block_gate_steps`).
 
     Returns ``uint8[S][NB][3]``: 1 = execute, 0 = reuse the cached tensor.
     """
     flags = np.asarray(flags, dtype=np.bool_)
     S, NB, C = flags.shape
+    if attn2_tgate_gate_step is None:
+        gates = np.full((S, NB), -1, dtype=np.int64)
+    elif np.ndim(attn2_tgate_gate_step) == 0:
+        gates = np.full((S, NB), int(attn2_tgate_gate_step), dtype=np.int64)
+    else:
+        gates = np.asarray(attn2_tgate_gate_step, dtype=np.int64).reshape(S, NB)
     executed = np.zeros((S, NB, C), dtype=np.uint8)
     have_cache = np.zeros((NB, C), dtype=np.bool_)
     for s in range(S):
         run = flags[s] | ~have_cache
-        if attn2_tgate_gate_step is not None and s >= attn2_tgate_gate_step:
-            if not have_cache[:, 1].all():
+        gated = (gates[s] >= 0) & (s >= gates[s])
+        if gated.any():
+            if not have_cache[gated, 1].all():
                 raise AssertionError("Cross-Attention must be cached at gate step for TGATE.")
-            run[:, 1] = False
+            run[gated, 1] = False
         executed[s] = run
         have_cache |= run
     return executed
@@ -344,9 +382,13 @@ def pixart_dead_store_mask(schedule: "PixArtCacheSchedule", step: int, executed:
     default_attn, default_ff = ComputeAttnRegistry.default(), ComputeFFRegistry.default()
 
     def is_default(entry) -> tuple[bool, bool]:
-        a = ComputeAttnRegistry.get((entry.get("custom_compute_attn") or {}).get("name"), False)
-        f = ComputeFFRegistry.get((entry.get("custom_compute_ff") or {}).get("name"), False)
-        return a is default_attn, f is default_ff
+        an = (entry.get("custom_compute_attn") or {}).get("name")
+        fn = (entry.get("custom_compute_ff") or {}).get("name")
+        a = ComputeAttnRegistry.get(an, False)
+        f = ComputeFFRegistry.get(fn, False)
+        # a user-registered tensor function may read any slot of its block whatever the flags say
+        tensor = ComputeAttnRegistry.get_tensor(an) is not None or ComputeFFRegistry.get_tensor(fn) is not None
+        return a is default_attn and not tensor, f is default_ff and not tensor
 
     row = schedule.schedule[step]
     keep = set(keep_attn2_blocks)

@@ -84,8 +84,107 @@ def _sincos_pos_embed(dim: int, grid_hw: tuple[int, int], base_size: int, interp
     return torch.from_numpy(np.concatenate([axis(col), axis(row)], axis=1)).float()
 
 
-class B200PixArtTransformer2D:
-    """PixArt-alpha/sigma transformer with layer-wise feature caching, executed by libecad_b200.so."""
+class B200BlockProxy:
+    """What a tensor-level custom compute function receives as ``block`` (the reference passes the
+    CachedTransformerBlock itself, cached_transformer_block.py:141-149,161-165).  Same attribute names:
+
+      ``block_num`` (str), ``cache_schedule``, ``attn1(hidden_states, encoder_hidden_states=None, attention_mask=None)``,
+      ``attn2(hidden_states, encoder_hidden_states=..., attention_mask=...)``, ``ff(hidden_states)`` - the block's own
+      modules, executed by the sm_100a kernels through the C ABI (QKV projection + attention + output projection /
+      GEMM + GELU + GEMM) and returning a fresh bf16 tensor ``[S, N, D]``;
+      ``cached_attn1_output`` / ``cached_attn2_output`` / ``cached_ff_output`` - ``None`` while the slot is empty, else
+      a bf16 view of the HBM cache slot; assigning a tensor copies it into the slot, assigning ``None`` empties it.
+
+    ``attn2`` uses the caption keys / values the transformer projected for this generation: ``encoder_hidden_states`` and
+    ``attention_mask`` are accepted for signature compatibility and must be the ones the forward was called with."""
+
+    _SLOT = {"attn1": 0, "attn2": 1, "ff": 2}
+
+    def __init__(self, owner: "B200PixArtTransformer2D", b: int, ws: dict, S: int, N: int):
+        self._o, self._b, self._ws, self._S, self._N = owner, b, ws, S, N
+        self.ran = np.zeros(3, dtype=np.uint8)  # which of the block's own modules a function actually executed
+        self.block_num = str(b)
+        self.cache_schedule = owner.cache_schedule
+
+    # ---- cache slots --------------------------------------------------------------------------------
+    def _get(self, comp: str):
+        c = self._SLOT[comp]
+        if not self._o._has_cache[self._b, c]:
+            return None
+        D = self._o.cfg.inner_dim
+        return self._ws["cache"][self._b * 3 + c][: self._S * self._N].view(self._S, self._N, D)
+
+    def _set(self, comp: str, value) -> None:
+        c = self._SLOT[comp]
+        o = self._o
+        if value is None:
+            o._has_cache[self._b, c] = False
+            o._cache_written[self._b, c] = False
+            return
+        D = o.cfg.inner_dim
+        slot = self._ws["cache"][self._b * 3 + c][: self._S * self._N].view(self._S, self._N, D)
+        if value.data_ptr() != slot.data_ptr():
+            slot.copy_(value.reshape(self._S, self._N, D))
+        o._has_cache[self._b, c] = True
+        o._cache_written[self._b, c] = True
+
+    cached_attn1_output = property(lambda self: self._get("attn1"), lambda self, v: self._set("attn1", v))
+    cached_attn2_output = property(lambda self: self._get("attn2"), lambda self, v: self._set("attn2", v))
+    cached_ff_output = property(lambda self: self._get("ff"), lambda self, v: self._set("ff", v))
+
+    # ---- the block's modules ------------------------------------------------------------------------
+    def _as_operand(self, hidden_states: torch.Tensor) -> torch.Tensor:
+        D = self._o.cfg.inner_dim
+        if hidden_states.shape[-1] != D or hidden_states.numel() != self._S * self._N * D:
+            raise ValueError(f"expected hidden_states [{self._S}, {self._N}, {D}], got {tuple(hidden_states.shape)}")
+        return hidden_states.reshape(self._S * self._N, D).to(torch.bfloat16).contiguous()
+
+    def attn1(self, hidden_states, encoder_hidden_states=None, attention_mask=None, **kwargs) -> torch.Tensor:
+        if encoder_hidden_states is not None or attention_mask is not None:
+            raise NotImplementedError("attn1 is plain self-attention on the PixArt path")
+        o, ws, w = self._o, self._ws, self._o.blocks_w[self._b]
+        S, N, H = self._S, self._N, o.cfg.num_attention_heads
+        a = self._as_operand(hidden_states)
+        _lib.gemm_headmajor(a, w["w_qkv1"], w["b_qkv1"], (ws["q"], ws["k"], ws["v"]), H, N, N)
+        _lib.attention(ws["q"], ws["k"], ws["v"], None, ws["attn_o"], S, H, N, N)
+        out = torch.empty(S * N, o.cfg.inner_dim, device=o.device, dtype=torch.bfloat16)
+        _lib.gemm_bias(ws["attn_o"][: S * N], w["w_out1"], w["b_out1"], out)
+        o.launches += 3
+        self.ran[0] = 1
+        return out.view(S, N, -1)
+
+    def attn2(self, hidden_states, encoder_hidden_states=None, attention_mask=None, **kwargs) -> torch.Tensor:
+        o, ws, w = self._o, self._ws, self._o.blocks_w[self._b]
+        S, N, H = self._S, self._N, o.cfg.num_attention_heads
+        a = self._as_operand(hidden_states)
+        _lib.gemm_headmajor(a, w["w_q2"], w["b_q2"], (ws["q"],), H, N, N)
+        _lib.attention(ws["q"], ws["k2"][self._b], ws["v2"][self._b], ws["text_bias"], ws["attn_o"], S, H, N,
+                       ws["text_pad"])
+        out = torch.empty(S * N, o.cfg.inner_dim, device=o.device, dtype=torch.bfloat16)
+        _lib.gemm_bias(ws["attn_o"][: S * N], w["w_out2"], w["b_out2"], out)
+        o.launches += 3
+        self.ran[1] = 1
+        return out.view(S, N, -1)
+
+    def ff(self, hidden_states, **kwargs) -> torch.Tensor:
+        o, ws, w = self._o, self._ws, self._o.blocks_w[self._b]
+        S, N = self._S, self._N
+        a = self._as_operand(hidden_states)
+        _lib.gemm_bias(a, w["w_ff1"], w["b_ff1"], ws["ffh"][: S * N], gelu=True)
+        out = torch.empty(S * N, o.cfg.inner_dim, device=o.device, dtype=torch.bfloat16)
+        _lib.gemm_bias(ws["ffh"][: S * N], w["w_ff2"], w["b_ff2"], out)
+        o.launches += 2
+        self.ran[2] = 1
+        return out.view(S, N, -1)
+
+
+class B200PixArtTransformer2D(torch.nn.Module):
+    """PixArt-alpha/sigma transformer with layer-wise feature caching, executed by libecad_b200.so.
+
+    An ``nn.Module`` shell like the reference's model (a diffusers pipeline can hold it: ``.config``, ``.dtype``,
+    ``.device``, ``.eval()``, ``.buffers()`` / ``.state_dict()`` of the packed bf16 / fp32 weights); there are no
+    trainable parameters.  The C handle keeps raw device pointers to the packed weights, so ``.to()`` / ``.cuda()`` /
+    ``.half()`` to another device or dtype raise instead of silently moving them."""
 
     def __init__(
         self,
@@ -100,6 +199,7 @@ class B200PixArtTransformer2D:
             raise ValueError("A DiTScheduler object must be provided.")
         if not torch.cuda.is_available():
             raise RuntimeError("B200PixArtTransformer2D needs a CUDA device; there is no CPU path")
+        super().__init__()
         self.device = torch.device(device)
         self._lib = _lib.load()
         _lib.check(self._lib.ecadk_device_check(self.device.index or 0), "device_check")
@@ -131,6 +231,19 @@ class B200PixArtTransformer2D:
         self._cache_written = np.zeros((config.num_layers, 3), dtype=np.bool_)
         self.last_dead: np.ndarray | None = None
         self.launches = 0  # kernels of libecad_b200 enqueued so far (bench.py's gpu_launches)
+        # bumped whenever device buffers that recorded CUDA graphs point into are re-allocated or dropped (workspace,
+        # per-timestep tables): the pipelines drop their graphs when it changes
+        self.buffer_epoch = 0
+        self._timestep_host_hint: float | None = None
+        # tensor-signature custom compute functions (registry.TensorComputeAttnRegistry / TensorComputeFFRegistry)
+        self.eval()
+
+    def _apply(self, fn, recurse=True):  # .to() / .cuda() / .half() / .float() all funnel through here
+        probe = fn(torch.empty(1, device=self.device, dtype=torch.bfloat16))
+        if probe.device != self.device or probe.dtype != torch.bfloat16:
+            raise RuntimeError("B200PixArtTransformer2D is bound to its device and precision policy (the C handle "
+                               "holds raw pointers to the packed weights); construct it on the target device instead")
+        return self
 
     # ------------------------------------------------------------------------------------------------
     @classmethod
@@ -141,11 +254,17 @@ class B200PixArtTransformer2D:
     @classmethod
     def from_pretrained(cls, pretrained_model_name_or_path, dit_scheduler=None, cache_schedule=None, **kwargs):
         """Same keyword surface as the reference's from_pretrained (:104-117); loads a diffusers-format state dict
-        (``diffusion_pytorch_model*.safetensors`` incl. sharded checkpoints, or ``.bin``) from a local directory."""
-        from .weights import load_diffusers_state_dict
+        (``diffusion_pytorch_model*.safetensors`` incl. sharded checkpoints, or ``.bin``) from a local directory and
+        the architecture from its ``config.json`` (``<dir>/config.json`` or ``<dir>/transformer/config.json``), so a
+        512 px / 1024-MS / sigma checkpoint gets its own sample_size, interpolation scale and micro-condition
+        embedders.  An explicit ``config=PixArtConfig(...)`` wins; unsupported architecture fields raise."""
+        from .weights import load_diffusers_state_dict, pixart_config_from_pretrained
 
         sd = load_diffusers_state_dict(pretrained_model_name_or_path)
-        return cls(sd, kwargs.get("config", PixArtConfig()), dit_scheduler, cache_schedule, kwargs.get("device", "cuda:0"))
+        config = kwargs.get("config")
+        if config is None:
+            config = pixart_config_from_pretrained(pretrained_model_name_or_path)
+        return cls(sd, config, dit_scheduler, cache_schedule, kwargs.get("device", "cuda:0"))
 
     def _pack_weights(self, sd: dict[str, torch.Tensor]) -> None:
         dev, cfg = self.device, self.cfg
@@ -185,6 +304,8 @@ class B200PixArtTransformer2D:
         w["final_w"] = bf16(fw)
         w["final_b"] = f32(fb)
         self.w = w
+        for name, t in w.items():
+            self.register_buffer(f"w_{name}", t, persistent=True)
         self.blocks_w: list[dict[str, torch.Tensor]] = []
         arr = (_lib.EcadkBlockWeights * cfg.num_layers)()
         for b in range(cfg.num_layers):
@@ -209,6 +330,7 @@ class B200PixArtTransformer2D:
             self.blocks_w.append(bw)
             for name, t in bw.items():
                 setattr(arr[b], name, t.data_ptr())
+                self.register_buffer(f"block{b}_{name}", t, persistent=True)
         desc = _lib.EcadkModelDesc(cfg.num_layers, D, cfg.num_attention_heads, 4 * D, cfg.norm_eps)
         handle = C.c_void_p()
         _lib.check(self._lib.ecadk_create(self.device.index or 0, C.byref(desc), arr, C.byref(handle)), "create")
@@ -245,6 +367,7 @@ class B200PixArtTransformer2D:
         D, H, L = cfg.inner_dim, cfg.num_attention_heads, cfg.num_layers
         bf, f32 = torch.bfloat16, torch.float32
         self._ws = {}  # drop the old workspace before allocating the new one
+        self.buffer_epoch += 1
         ws: dict[str, Any] = {}
         M = S * N
         TEXT_PAD = ((T + 127) // 128) * 128  # 120 -> 128 (alpha), 300 -> 384 (sigma)
@@ -309,10 +432,19 @@ class B200PixArtTransformer2D:
         executed = np.zeros((L, 3), dtype=np.uint8)
         row = sched.schedule[step]
         self._tgate_average = []  # blocks whose attn2 cache is averaged after this forward (TGATE, gate_step - 1)
+        self._tensor_blocks = {}  # block -> (attn tensor fn | None, attn kwargs, ff tensor fn | None, ff kwargs)
         for b in range(L):
             entry = row[str(b)]
             attn_cfg = entry.get("custom_compute_attn", {}) or {}
             ff_cfg = entry.get("custom_compute_ff", {}) or {}
+            t_attn = ComputeAttnRegistry.get_tensor(attn_cfg.get("name"))
+            t_ff = ComputeFFRegistry.get_tensor(ff_cfg.get("name"))
+            if t_attn is not None or t_ff is not None:
+                # a user-registered tensor-level function (cached_transformer_block.py:125-165): this block is run
+                # sub-block by sub-block from Python at this step; its executed flags are observed, not decided
+                self._tensor_blocks[b] = (t_attn, dict(attn_cfg.get("kwargs", {}) or {}), t_ff,
+                                          dict(ff_cfg.get("kwargs", {}) or {}))
+                continue
             attn_fn = ComputeAttnRegistry.get(attn_cfg.get("name"), False)
             ff_fn = ComputeFFRegistry.get(ff_cfg.get("name"), False)
             if attn_fn.__name__ == "compute_attn_tgate":
@@ -340,12 +472,14 @@ class B200PixArtTransformer2D:
         attention_mask: Optional[torch.Tensor] = None,
         encoder_attention_mask: Optional[torch.Tensor] = None,
         return_dict: bool = True,
-        timestep_host: float | None = None,
     ):
-        """``timestep_host`` (optional, not in the reference signature): the value of a batch-shared timestep as a host
-        number.  The adaLN-single tables depend on nothing but the timestep and the weights, so with it they are
-        computed once per distinct timestep and reused by every later step / generation without a device read-back."""
+        """Same signature as the reference (pixart_transformer_2d_edited.py:160-170).  Side channel (not an argument):
+        ``hint_timestep(value)`` before the call tells the module the host value of a batch-shared timestep; the
+        adaLN-single tables depend on nothing but the timestep and the weights, so with the hint they are computed once
+        per distinct timestep and reused by every later step / generation without a device read-back.  The returned
+        sample is a fresh tensor (the reference returns fresh tensors; the workspace buffer is reused every call)."""
         cfg, lib, w = self.cfg, self._lib, self.w
+        timestep_host, self._timestep_host_hint = self._timestep_host_hint, None
         if attention_mask is not None:
             raise NotImplementedError("self-attention masks are never passed on the PixArt path")
         if encoder_hidden_states is None or timestep is None:
@@ -396,6 +530,7 @@ class B200PixArtTransformer2D:
                 temb6_buf = torch.empty(1, 6 * D, device=dev, dtype=torch.float32)
                 if len(self._temb_cache) >= 256:
                     self._temb_cache.clear()
+                    self.buffer_epoch += 1
                 self._temb_cache[float(timestep_host)] = (t_emb_buf, temb6_buf)
             else:
                 t_emb_buf, temb6_buf = ws["t_emb"], ws["temb6"]
@@ -486,11 +621,33 @@ class B200PixArtTransformer2D:
         self._dead_flat = np.ascontiguousarray(dead.reshape(-1))
         ws["args"].cache_dead = self._dead_flat.ctypes.data_as(C.POINTER(C.c_uint8))
         n_l = C.c_int(0)
-        _lib.check(lib.ecadk_pixart_blocks(self._handle, C.byref(ws["args"]),
-                                           ex.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(n_l), st), "pixart_blocks")
-        launches += n_l.value
+        if not self._tensor_blocks:
+            _lib.check(lib.ecadk_pixart_blocks(self._handle, C.byref(ws["args"]),
+                                               ex.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(n_l), st),
+                       "pixart_blocks")
+            launches += n_l.value
+        else:
+            # C executor for the runs of ordinary blocks, Python composition for the blocks with tensor functions
+            self._tensor_ran = {}
+            begin = 0
+            for b in sorted(self._tensor_blocks) + [cfg.num_layers]:
+                if b > begin:
+                    _lib.check(lib.ecadk_pixart_blocks_range(self._handle, C.byref(ws["args"]),
+                                                             ex.ctypes.data_as(C.POINTER(C.c_uint8)), begin, b,
+                                                             C.byref(n_l), st), "pixart_blocks_range")
+                    launches += n_l.value
+                if b < cfg.num_layers:
+                    l0 = self.launches
+                    self._run_tensor_block(b, ws, S, N, temb6_buf, temb_stride, encoder_hidden_states, mask)
+                    launches += self.launches - l0
+                    self.launches = l0
+                begin = b + 1
         self._has_cache |= executed.astype(np.bool_)
         self._cache_written = np.where(executed.astype(np.bool_), ~dead.astype(np.bool_), self._cache_written)
+        if self._tensor_blocks:
+            self.last_executed = executed.copy()
+            for b, ran in self._tensor_ran.items():
+                self.last_executed[b] = ran
         if self._tgate_average:
             # cached_transformer_block.py:443-449: at gate_step - 1 the cache keeps (uncond + text) / 2
             if S % 2:
@@ -508,10 +665,50 @@ class B200PixArtTransformer2D:
         launches += 2
         self.launches += launches
         out = ws["out"][:S]
-        if hidden_states.dtype != torch.float32:
-            out = out.to(hidden_states.dtype)
+        out = out.clone() if hidden_states.dtype == torch.float32 else out.to(hidden_states.dtype)
         if not return_dict:
             return (out,)
         return Transformer2DModelOutput(sample=out)
 
-    __call__ = forward
+    def _run_tensor_block(self, b: int, ws: dict, S: int, N: int, temb6: torch.Tensor, temb_stride: int,
+                          encoder_hidden_states, mask) -> None:
+        """One block executed sub-block by sub-block, restating CachedTransformerBlock.forward
+        (cached_transformer_block.py:208-324) around user tensor functions: LN + adaLN modulate -> compute_attn("attn1")
+        -> gate * out + x -> compute_attn("attn2") on the un-normalised stream -> out + x -> LN + modulate ->
+        compute_ff -> gate * out + x.  Sub-blocks without a user function go through the tensor-level defaults."""
+        from .registry import compute_attn_cached_tensor, compute_ff_cached_tensor
+
+        D, M = self.cfg.inner_dim, S * N
+        t_attn, attn_kw, t_ff, ff_kw = self._tensor_blocks[b]
+        attn_fn = t_attn if t_attn is not None else compute_attn_cached_tensor
+        ff_fn = t_ff if t_ff is not None else compute_ff_cached_tensor
+        tab = self.blocks_w[b]["scale_shift_table"]  # [6, D] fp32: shift/scale/gate msa, shift/scale/gate mlp
+        x, h, xb = ws["x"][:M], ws["h"][:M], ws["xb"][:M]
+        proxy = B200BlockProxy(self, b, ws, S, N)
+
+        def as_bf16(t):
+            if t.numel() != M * D:
+                raise ValueError(f"custom compute function of block {b} returned {tuple(t.shape)}, expected [{S}, {N}, {D}]")
+            return t.reshape(M, D).to(torch.bfloat16).contiguous()
+
+        # attn1 on LN1 + modulate (:208-246)
+        _lib.residual_ln(x, N, h=h, shift_table=tab[0], scale_table=tab[1], shift_temb=temb6[:, 0 * D:],
+                         scale_temb=temb6[:, 1 * D:], temb_stride=temb_stride, eps=self.cfg.norm_eps)
+        o1 = as_bf16(attn_fn(proxy, "attn1", h.view(S, N, D), None, None, **attn_kw))
+        # x += gate_msa * out; the bf16 shadow of the updated stream is attn2's input (:264-289: no norm for PixArt)
+        _lib.residual_ln(x, N, reuse=[(o1, tab[2], temb6[:, 2 * D:])], xb=xb, temb_stride=temb_stride,
+                         eps=self.cfg.norm_eps)
+        o2 = as_bf16(attn_fn(proxy, "attn2", xb.view(S, N, D), encoder_hidden_states, mask, **attn_kw))
+        # x += out; LN2 + modulate (:306-310)
+        _lib.residual_ln(x, N, reuse=[(o2, None, None)], h=h, shift_table=tab[3], scale_table=tab[4],
+                         shift_temb=temb6[:, 3 * D:], scale_temb=temb6[:, 4 * D:], temb_stride=temb_stride,
+                         eps=self.cfg.norm_eps)
+        o3 = as_bf16(ff_fn(proxy, h.view(S, N, D), **ff_kw))
+        _lib.residual_ln(x, N, reuse=[(o3, tab[5], temb6[:, 5 * D:])], temb_stride=temb_stride, eps=self.cfg.norm_eps)
+        self.launches += 4
+        # decisions are observed, not made, for this block: "executed" = the function ran the block's own module
+        self._tensor_ran[b] = proxy.ran
+
+    def hint_timestep(self, value: float | None) -> None:
+        """Host value of the (batch-shared) timestep of the NEXT forward; consumed by that forward."""
+        self._timestep_host_hint = None if value is None else float(value)

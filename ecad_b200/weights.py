@@ -193,3 +193,37 @@ def load_diffusers_state_dict(path) -> dict[str, torch.Tensor]:
         if legacy.exists():
             return torch.load(legacy, map_location="cpu")
     raise FileNotFoundError(f"no diffusers-format transformer weights under {root}")
+
+
+def pixart_config_from_pretrained(path) -> PixArtConfig:
+    """``config.json`` of a diffusers PixArtTransformer2DModel directory (or its parent pipeline directory) ->
+    PixArtConfig.  Fields this implementation is specialised for must hold their PixArt values; anything else raises
+    instead of silently building the wrong model (position table scale, micro-condition embedders)."""
+    import json
+    from pathlib import Path
+
+    root = Path(path)
+    for d in (root, root / "transformer"):
+        f = d / "config.json"
+        if f.is_file() and ((d / "diffusion_pytorch_model.safetensors").exists()
+                            or (d / "diffusion_pytorch_model.safetensors.index.json").exists()
+                            or (d / "diffusion_pytorch_model.bin").exists()):
+            raw = json.loads(f.read_text())
+            break
+    else:
+        raise FileNotFoundError(f"no transformer config.json next to the weights under {root}")
+    required = {"norm_type": "ada_norm_single", "activation_fn": "gelu-approximate", "attention_bias": True,
+                "norm_elementwise_affine": False, "dropout": 0.0}
+    for key, want in required.items():
+        if key in raw and raw[key] != want:
+            raise ValueError(f"unsupported PixArt config: {key} = {raw[key]!r} (this path implements {want!r})")
+    for key in ("num_embeds_ada_norm", "attention_type"):
+        if key in raw and raw[key] not in (None, 1000, "default"):
+            raise ValueError(f"unsupported PixArt config: {key} = {raw[key]!r}")
+    fields = {"num_attention_heads", "attention_head_dim", "in_channels", "out_channels", "num_layers",
+              "cross_attention_dim", "sample_size", "patch_size", "norm_eps", "caption_channels",
+              "interpolation_scale", "use_additional_conditions"}
+    cfg = PixArtConfig(**{k: v for k, v in raw.items() if k in fields})
+    if cfg.cross_attention_dim != cfg.inner_dim:
+        raise ValueError("cross_attention_dim must equal heads * head_dim on the PixArt path")
+    return cfg

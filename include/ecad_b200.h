@@ -282,6 +282,13 @@ typedef struct {
 int ecadk_pixart_blocks(ecadk_handle_t h, const EcadkBlocksArgs* args, const uint8_t* executed, int* n_launches,
                         ecadk_stream_t stream);
 
+/* Same for blocks [block_begin, block_end) only; `executed` / `args->cache_dead` are still indexed by absolute block
+ * number.  Pending cached-residual reuses are flushed before returning, so `args->x` is complete when the call ends.
+ * This is what lets a caller run a user-registered tensor-level compute function
+ * (custom_compute_attn / custom_compute_ff of one block, cached_transformer_block.py:125-165) between two ranges. */
+int ecadk_pixart_blocks_range(ecadk_handle_t h, const EcadkBlocksArgs* args, const uint8_t* executed, int block_begin,
+                              int block_end, int* n_launches, ecadk_stream_t stream);
+
 /* Projects caption embeddings once per generation: enc bf16 [samples*text_tokens, dim] -> k2[b], v2[b] for every
  * block (head-major, zero padding preserved).  Hoists attn2.to_k/to_v, which the reference recomputes every step
  * (cached_transformer_block.py:348-353 with encoder_hidden_states). */

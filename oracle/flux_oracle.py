@@ -263,10 +263,14 @@ class FluxOracle:
 
 
 # ---- FlowMatchEulerDiscreteScheduler with FLUX's dynamic shifting + the denoising loop ------------------------------
-def flux_sigmas(num_inference_steps: int, image_seq_len: int) -> np.ndarray:
+def flux_sigmas(num_inference_steps: int, image_seq_len: int, base_shift: float = 0.5, max_shift: float = 1.15,
+                base_image_seq_len: int = 256, max_image_seq_len: int = 4096) -> np.ndarray:
+    """diffusers 0.30.3 FluxPipeline.__call__: mu = calculate_shift(seq_len, scheduler.config.base_image_seq_len,
+    .max_image_seq_len, .base_shift, .max_shift) with FLUX.1-dev's scheduler_config.json (0.5 / 1.15 / 256 / 4096 -
+    the defaults of FlowMatchEulerDiscreteScheduler; recalled, the reference ships no scheduler config)."""
     sigmas = np.linspace(1.0, 1 / num_inference_steps, num_inference_steps)
-    m = (1.16 - 0.5) / (4096 - 256)
-    mu = image_seq_len * m + (0.5 - m * 256)
+    m = (max_shift - base_shift) / (max_image_seq_len - base_image_seq_len)
+    mu = image_seq_len * m + (base_shift - m * base_image_seq_len)
     sigmas = math.exp(mu) / (math.exp(mu) + (1 / sigmas - 1))
     return np.concatenate([sigmas, [0.0]]).astype(np.float32)
 

@@ -73,6 +73,9 @@ class OracleSchedule:
     def get_custom_compute_attn(self, block_num: str) -> dict:  # pixart_cache_schedule.py:29-32
         return self.schedule[self.curr_step][block_num].get("custom_compute_attn", {})
 
+    def get_custom_compute_ff(self, block_num: str) -> dict:  # pixart_cache_schedule.py:34-37
+        return self.schedule[self.curr_step][block_num].get("custom_compute_ff", {})
+
 
 # ------------------------------------------------------------------------------------------------
 # model config
@@ -211,8 +214,50 @@ class Trace:
         return out
 
 
+class OracleBlockProxy:
+    """The ``block`` a registered custom compute function sees on the oracle side - the attribute surface of the
+    reference's CachedTransformerBlock that such functions use (cached_transformer_block.py:116-123,141-149,161-165):
+    ``block_num``, ``cache_schedule``, the modules ``attn1`` / ``attn2`` / ``ff`` and the ``cached_*_output`` slots."""
+
+    def __init__(self, oracle: "PixArtOracle", b: int):
+        self._o, self._b = oracle, b
+        self.block_num = str(b)
+        self.cache_schedule = oracle.cache_schedule
+
+    def _mod(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, **kw):
+        o = self._o
+        o.trace.mark(o.cache_schedule.curr_step, self._b, 0 if attn == "attn1" else 1, True)
+        return attention(o.sd, f"transformer_blocks.{self._b}.{attn}", o.cfg.num_attention_heads, hidden_states,
+                         encoder_hidden_states, attention_mask, o.qa)
+
+    def attn1(self, hidden_states, encoder_hidden_states=None, attention_mask=None, **kw):
+        return self._mod("attn1", hidden_states, encoder_hidden_states, attention_mask)
+
+    def attn2(self, hidden_states, encoder_hidden_states=None, attention_mask=None, **kw):
+        return self._mod("attn2", hidden_states, encoder_hidden_states, attention_mask)
+
+    def ff(self, hidden_states, **kw):
+        o = self._o
+        o.trace.mark(o.cache_schedule.curr_step, self._b, 2, True)
+        return feed_forward(o.sd, f"transformer_blocks.{self._b}.ff", hidden_states, o.qa)
+
+    cached_attn1_output = property(lambda self: self._o.caches[self._b].attn1,
+                                   lambda self, v: setattr(self._o.caches[self._b], "attn1", v))
+    cached_attn2_output = property(lambda self: self._o.caches[self._b].attn2,
+                                   lambda self, v: setattr(self._o.caches[self._b], "attn2", v))
+    cached_ff_output = property(lambda self: self._o.caches[self._b].ff,
+                                lambda self, v: setattr(self._o.caches[self._b], "ff", v))
+
+
 class PixArtOracle:
-    """fp32 CPU restatement of PixArtTransformer2DEdited + CachedTransformerBlock."""
+    """fp32 CPU restatement of PixArtTransformer2DEdited + CachedTransformerBlock.
+
+    ``custom_attn_fns`` / ``custom_ff_fns`` play the role of ComputeAttnRegistry / ComputeFFRegistry for user-registered
+    functions (custom_attn_ff.py:10-35): lower-cased name -> ``f(block, attn, hidden_states, encoder_hidden_states,
+    attention_mask, **kwargs)`` resp. ``f(block, norm_hidden_states, **kwargs)`` with ``block`` an OracleBlockProxy."""
+
+    custom_attn_fns: dict[str, Callable] = {}
+    custom_ff_fns: dict[str, Callable] = {}
 
     def __init__(self, state_dict: dict[str, torch.Tensor], cfg: OracleConfig, cache_schedule: OracleSchedule,
                  round_act: Callable[[torch.Tensor], torch.Tensor] | None = None,
@@ -301,7 +346,19 @@ class PixArtOracle:
         kwargs = cfg.get("kwargs", {})
         if name == "compute_attn_tgate":
             return self.compute_attn_tgate(b, attn, hidden, enc, bias, **kwargs)
+        if name in self.custom_attn_fns:
+            self.trace.mark(self.cache_schedule.curr_step, b, 0 if attn == "attn1" else 1, False)  # until a module runs
+            return self.custom_attn_fns[name](OracleBlockProxy(self, b), attn, hidden, enc, bias, **kwargs)
         return self.compute_attn_cached(b, attn, hidden, enc, bias)
+
+    # cached_transformer_block.py:151-165
+    def compute_ff(self, b: int, norm_hidden):
+        cfg = self.cache_schedule.get_custom_compute_ff(str(b))
+        name = (cfg.get("name") or "compute_ff_cached").lower()
+        if name in self.custom_ff_fns:
+            self.trace.mark(self.cache_schedule.curr_step, b, 2, False)
+            return self.custom_ff_fns[name](OracleBlockProxy(self, b), norm_hidden, **cfg.get("kwargs", {}))
+        return self.compute_ff_cached(b, norm_hidden)
 
     # ---- cached_transformer_block.py:167-324, ada_norm_single branch --------------------------------
     def block_forward(self, b: int, hidden, enc, enc_bias, timestep6):
@@ -322,7 +379,7 @@ class PixArtOracle:
         hidden = qr(attn_out + hidden)  # :289
         norm = F.layer_norm(hidden, (D,), eps=self.cfg.norm_eps)  # norm2 (:306-307)
         norm = qa(norm * (1 + scale_mlp) + shift_mlp)  # :308-310
-        ff_out = qa(self.compute_ff_cached(b, norm))  # :313
+        ff_out = qa(self.compute_ff(b, norm))  # :313
         ff_out = gate_mlp * ff_out  # :318
         hidden = qr(ff_out + hidden)  # :320
         return hidden

@@ -14,7 +14,8 @@ from oracle.flux_oracle import embed_nd, flux_sigmas
 def test_flow_match_sigmas_match_oracle():
     for steps, n in ((20, 256), (20, 4096), (7, 192)):
         s = FlowMatchEulerDiscrete()
-        s.set_timesteps(steps, mu=calculate_shift(n))
+        c = s.config
+        s.set_timesteps(steps, mu=calculate_shift(n, c.base_image_seq_len, c.max_image_seq_len, c.base_shift, c.max_shift))
         ref = flux_sigmas(steps, n)
         assert np.array_equal(s.sigmas, ref)
         assert np.allclose(s.timesteps.numpy(), ref[:-1] * 1000)
@@ -22,6 +23,27 @@ def test_flow_match_sigmas_match_oracle():
             assert s.step_coefficient() == float(ref[i + 1]) - float(ref[i])
             s.advance()
     assert s.sigmas[-1] == 0.0
+
+
+def test_flow_match_shift_known_answers():
+    """FLUX.1-dev scheduler_config: base_shift 0.5 at 256 image tokens, max_shift 1.15 at 4096 (NOT the 1.16 default of
+    calculate_shift's signature, which the pipeline never uses); linear in between."""
+    import math
+
+    c = FlowMatchEulerDiscrete().config
+    assert (c.base_shift, c.max_shift, c.base_image_seq_len, c.max_image_seq_len) == (0.5, 1.15, 256, 4096)
+
+    def mu(n):
+        return calculate_shift(n, c.base_image_seq_len, c.max_image_seq_len, c.base_shift, c.max_shift)
+
+    assert abs(mu(256) - 0.5) < 1e-12 and abs(mu(4096) - 1.15) < 1e-12
+    assert abs(mu(1024) - (0.5 + 768 * 0.65 / 3840)) < 1e-12
+    s = FlowMatchEulerDiscrete()
+    s.set_timesteps(20, mu=mu(4096))
+    # sigma' = e^mu / (e^mu + 1/sigma - 1): first sigma stays 1, the last one is e^1.15 / (e^1.15 + 19)
+    assert s.sigmas[0] == 1.0
+    assert abs(float(s.sigmas[19]) - math.exp(1.15) / (math.exp(1.15) + 19.0)) < 1e-7
+    assert abs(float(s.sigmas[9]) - math.exp(1.15) / (math.exp(1.15) + (1 / 0.55 - 1))) < 1e-7
 
 
 def test_pack_latents_and_ids():

@@ -134,6 +134,37 @@ def test_attention(cuda_device, samples, nk, use_bias):
     assert float((out.float() - ref).abs().mean() / ref.abs().mean()) < 6e-3
 
 
+@pytest.mark.parametrize("nk,use_bias", [(256, False), (128, True), (256, True), (128, False)])
+def test_attention_many_items_per_cta(cuda_device, nk, use_bias):
+    """50 samples x 16 heads = 800 work items on 148 persistent CTAs: five to six items per CTA, so every ring
+    (per-tile Q slots, K/V double buffers, staged output tiles, TMEM tiles) wraps several times."""
+    from ecad_b200 import _lib
+    samples, q_tokens = 50, 256
+    g = torch.Generator(device="cuda").manual_seed(77 + nk)
+
+    def mk(tokens, scale):
+        t = torch.zeros(samples, H, tokens, HP, device="cuda", dtype=torch.bfloat16)
+        t[..., :HD] = _bf(torch.randn(samples, H, tokens, HD, device="cuda", generator=g) * scale)
+        return t
+
+    q, k, v = mk(q_tokens, 2.0), mk(nk, 2.0), mk(nk, 1.0)
+    bias = None
+    if use_bias:
+        bias = torch.zeros(samples, nk, device="cuda")
+        lens = torch.randint(1, nk - 8, (samples,), generator=torch.Generator().manual_seed(1))
+        for s in range(samples):
+            bias[s, int(lens[s]):nk - 8] = -10000.0
+            bias[s, nk - 8:] = float("-inf")
+    out = torch.full((samples, q_tokens, H * HD), float("nan"), device="cuda", dtype=torch.bfloat16)
+    for _ in range(2):  # back-to-back launches (programmatic dependent launch between them)
+        _lib.attention(q, k, v, bias, out, samples, H, q_tokens, nk)
+    torch.cuda.synchronize()
+    ref = _attn_ref(q[..., :HD], k[..., :HD], v[..., :HD], bias)
+    assert torch.isfinite(out.float()).all()
+    err = (out.float() - ref).abs().amax(dim=(1, 2)) / ref.abs().amax(dim=(1, 2))  # per sample
+    assert float(err.max()) < 1.5e-2, err
+
+
 @pytest.mark.parametrize("samples,q_tokens,nk,real_keys", [
     (1, 512, 512, None),     # self-attention, 4 key blocks, two query pairs
     (2, 1024, 1024, None),   # PixArt 512x512 self-attention shape

@@ -79,8 +79,58 @@ def test_registries_mirror_reference_lookup_rules():
     assert ComputeFFRegistry.get(None).__name__ == "compute_ff_cached"
     import ecad_b200.image_generator  # noqa: F401  (registers the generator)
     assert "b200_pixart_alpha" in ImageGeneratorRegistry.registry
+    # load_image_generator.py:23-40: unknown name -> the default's class, else None; the helper functions raise
+    from ecad_b200.registry import get_image_generator_type, get_image_generator_type_from_config
+    assert ImageGeneratorRegistry.get("missing") is None
+    alpha = ImageGeneratorRegistry.get("b200_pixart_alpha")
+    assert ImageGeneratorRegistry.get("missing", "b200_pixart_alpha") is alpha
+    assert ImageGeneratorRegistry.get("missing", "also_missing") is None
+    # the reference's own class names select the B200 generators (a schedule JSON's config.image_generator)
+    assert ImageGeneratorRegistry.get("PixArtAlphaImageGenerator") is alpha
+    sigma = ImageGeneratorRegistry.get("PixArtSigmaImageGenerator")
+    assert sigma.text_tokens == 300 and sigma.default_pipeline_name == "pixart_sigma" and issubclass(sigma, alpha.__mro__[1])
+    assert ImageGeneratorRegistry.get("FluxImageGenerator") is ImageGeneratorRegistry.get("b200_flux")
     with pytest.raises(ValueError):
-        ImageGeneratorRegistry.get("missing")
+        get_image_generator_type("missing")  # default "PixArtImageGenerator" is not registered (as in the reference)
+    assert get_image_generator_type("missing", "b200_pixart_sigma") is sigma
+    assert get_image_generator_type_from_config({"image_generator": "PixArtSigmaImageGenerator"}) is sigma
+    with pytest.raises(ValueError):
+        get_image_generator_type_from_config({})
+
+
+def test_block_gate_steps_drive_the_trace():
+    """The TGATE attn2 rule is taken per block from custom_compute_attn kwargs (what the runtime decides from), not
+    from one pipeline-level value: two blocks with different gate steps, one block without TGATE."""
+    S, NB = 6, 3
+    flags = np.ones((S, NB, 3), bool)
+    sched = PixArtCacheSchedule.from_numpy(flags, S, NB, "mixed")
+    for s in range(S):
+        sched.schedule[s]["0"]["custom_compute_attn"] = {"name": "compute_attn_tgate", "kwargs": {"gate_step": 2}}
+        sched.schedule[s]["1"]["custom_compute_attn"] = {"name": "Compute_Attn_TGATE", "kwargs": {"gate_step": 4}}
+    gates = sched.block_gate_steps()
+    assert gates.shape == (S, NB) and (gates[:, 0] == 2).all() and (gates[:, 1] == 4).all() and (gates[:, 2] == -1).all()
+    assert sched.gate_step() is None  # no pipeline-level entry
+    from ecad_b200.metrics import executed_trace
+    ex = executed_trace(sched)
+    assert ex[:2, 0, 1].all() and not ex[2:, 0, 1].any()
+    assert ex[:4, 1, 1].all() and not ex[4:, 1, 1].any()
+    assert ex[:, 2, 1].all() and ex[:, :, 0].all() and ex[:, :, 2].all()
+    sched.schedule[0]["0"]["custom_compute_attn"] = {"name": "compute_attn_tgate", "kwargs": {}}
+    with pytest.raises(ValueError):
+        sched.block_gate_steps()
+
+
+def test_content_key_tracks_content_not_identity():
+    a = PixArtCacheSchedule.from_numpy(np.ones((4, 2, 3), bool), 4, 2, "x")
+    b = PixArtCacheSchedule.from_numpy(np.ones((4, 2, 3), bool), 4, 2, "y")
+    assert a.content_key() == b.content_key()
+    f = np.ones((4, 2, 3), bool)
+    f[2, 1, 0] = False
+    c = PixArtCacheSchedule.from_numpy(f, 4, 2, "x")
+    assert c.content_key() != a.content_key()
+    d = PixArtCacheSchedule.from_numpy(np.ones((4, 2, 3), bool), 4, 2, "x",
+                                       top_level_config={"pipeline": {"name": "tgate", "kwargs": {"gate_step": 2}}})
+    assert d.content_key() != a.content_key()
 
 
 def test_trace_resets_between_generations():

@@ -61,8 +61,8 @@ mma, s0, s1 = a[:, 0:8], a[:, 8:16], a[:, 16:24]
 if mode.startswith("c2"):
     items = mma[:, 7].mean()
     print(f"{mode}: items per CTA {items:.1f}; clocks per item (mean over CTAs); whole MMA loop {a[:, 24].mean() / items:.0f}")
-    for i, nm in enumerate(["wait Q/K", "wait O_0 read out", "issue QK0", "wait P1 + issue PV1",
-                            "wait O_1 read out + QK1", "wait V + P0", "issue PV0"]):
+    for i, nm in enumerate(["wait K + Q0", "wait O_0 read out", "issue QK0", "wait P1 + issue PV1",
+                            "wait Q1 + O_1 read out + QK1", "wait V + P0", "issue PV0"]):
         print(f"  MMA thread   {nm:26s} {mma[:, i].mean() / items:8.1f}")
     for tile, arr in ((0, s0), (1, s1)):
         for i, nm in enumerate(["wait S", "softmax", "wait O", "O read-out + stores"]):
