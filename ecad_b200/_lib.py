@@ -35,6 +35,7 @@ EXPORTED_SYMBOLS = [
     "ecadk_attention",
     "ecadk_attention_d128",
     "ecadk_qk_norm_rope",
+    "ecadk_qk_norm_rope_batched",
     "ecadk_strided_unary",
     "ecadk_axpy_f32",
     "ecadk_gemm_bias_f32",
@@ -148,7 +149,7 @@ class EcadkFluxArgs(C.Structure):
                                      "attn_txt", "ffh", "cat", "mod")]
         + [("mod_stride", C.c_int), ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p),
            ("cache_double", C.POINTER(C.c_void_p)), ("cache_single", C.POINTER(C.c_void_p)),
-           ("cache_dead", C.POINTER(C.c_uint8))]
+           ("cache_dead", C.POINTER(C.c_uint8)), ("rope_sample_stride", C.c_int)]
     )
 
 
@@ -197,6 +198,7 @@ def load() -> C.CDLL:
         "ecadk_attention": [p, p, p, p, p, i, i, i, i, p],
         "ecadk_attention_d128": [p, p, p, p, i, p, i, i, i, i, i, p],
         "ecadk_qk_norm_rope": [p, p, p, p, p, p, p, p, i, i, i, i, f, p],
+        "ecadk_qk_norm_rope_batched": [p, p, p, p, p, p, p, p, i, i, i, i, i, f, p],
         "ecadk_strided_unary": [p, p, i, i, i, i, i, p],
         "ecadk_axpy_f32": [p, p, f, sz, p],
         "ecadk_gemm_bias_f32": [p, p, p, p, i, i, i, i, i, p],

@@ -730,12 +730,14 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_consta
 //     stores from the softmax threads: a warp store used to touch 32 different 128-byte lines (32 LSU passes per
 //     instruction, ~2000 clk of read-out per tile per item), now the softmax warps write conflict-free 16-byte pieces
 //     of dense 144-byte rows into smem, hand the tile's TMEM columns back at once and go on to the next item;
-//   * with 256 keys the staged output tiles live in the K buffer of the SAME item: K is dead once both S tiles have
-//     retired, which every o_full commit implies; the producer refills that buffer only after the stores have read it.
+//   * ONE staged output tile (18 KB) is shared by the two query tiles, which run in anti-phase; the store warp hands it
+//     back as soon as the TMA store has read it.  (First version: with 256 keys the staged tiles lived in the retired
+//     K buffer of the same item - that made the NEXT K load wait for the item's stores, which queue behind the loads
+//     in the TMA unit; the MMA thread then waited ~900 clk per item for K.)
 // =====================================================================================================
 constexpr int kPair2Threads = 608;  // warp 0 TMA loads, warp 1 MMA, warps 2..17 softmax, warp 18 TMA stores
 
-template <int NK>
+template <int NK, bool HAS_BIAS>
 struct AttnPair2Cfg {
   static constexpr int kQTile = kAttnBM * 160;        // [128 x 128 B SW128][128 x 32 B SW32]
   static constexpr int kQ = 0;                        // 2 tile slots
@@ -744,10 +746,9 @@ struct AttnPair2Cfg {
   static constexpr int kVBuf = NK * 160;              // five [NK x 32 B] SW32 atoms
   static constexpr int kV = kK + 2 * kKBuf;           // 2 buffers
   static constexpr int kOTile = kAttnBM * kHeadDim * 2;  // 18432: dense [128 x 72] bf16
-  static constexpr bool kAliasO = 2 * kOTile <= kKBuf;   // staged O tiles of item i live in K buffer (i & 1)
-  static constexpr int kO = kV + 2 * kVBuf;           // own staging (only when not aliased): [parity][tile]
-  static constexpr int kBias = kAliasO ? kO : kO + 4 * kOTile;  // 16 warps x NK/2 floats
-  static constexpr int kXch = kBias + 8 * NK * 4;
+  static constexpr int kO = kV + 2 * kVBuf;           // ONE staged output tile, shared by both query tiles
+  static constexpr int kBias = kO + kOTile;           // 16 warps x NK/2 floats (only with a key bias)
+  static constexpr int kXch = kBias + (HAS_BIAS ? 8 * NK * 4 : 0);
   static constexpr int kBars = kXch + 2 * 16 * 32 * 4;
   static constexpr int kPHi = NK == 256 ? 144 : 32;   // TMEM map: see AttnPairCfg
   static constexpr int kOCol = NK == 256 ? 64 : 128;
@@ -756,7 +757,7 @@ struct AttnPair2Cfg {
   static constexpr uint32_t kBytesQ = kAttnBM * kHeadPad * 2;
   static constexpr uint32_t kBytesKV = NK * kHeadPad * 2;
   static_assert(kSmemBytes <= 227 * 1024, "attn_pair2_kernel: shared memory");
-  static_assert(kOTile % 128 == 0 && kKBuf % 1024 == 0 && kQTile % 1024 == 0, "alignment");
+  static_assert(kOTile % 1024 == 0 && kKBuf % 1024 == 0 && kQTile % 1024 == 0, "alignment");
 };
 
 template <int NK, bool HAS_BIAS>
@@ -765,7 +766,7 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
                   const __grid_constant__ CUtensorMap tm_k64, const __grid_constant__ CUtensorMap tm_k16,
                   const __grid_constant__ CUtensorMap tm_v16, const __grid_constant__ CUtensorMap tm_o,
                   const AttnParams p, const int num_items) {
-  using Cfg = AttnPair2Cfg<NK>;
+  using Cfg = AttnPair2Cfg<NK, HAS_BIAS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBars);
@@ -779,13 +780,9 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
   uint64_t* p_full = bars + 14;    // [2]
   uint64_t* o_full = bars + 16;    // [2]
   uint64_t* s_empty = bars + 18;   // [2]
-  uint64_t* o_free = bars + 20;    // [2] per item parity: both TMA stores of the item have read their staging
-  // [4] per (item parity, query tile), one phase per TWO items: the bf16 output tile is in shared memory.  (Per tile
-  // only - one phase per item - a tile that runs ahead could complete two phases between two probes of the store warp,
-  // which then waits for a parity that never shows: staging (b, t) again needs o_free[b], so per-buffer barriers
-  // cannot overrun.)
-  uint64_t* o_staged = bars + 22;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+  uint64_t* o_staged = bars + 20;  // [2] per query tile, one phase per item: the bf16 output tile is in shared memory
+  uint64_t* stage_free = bars + 22;  // one phase per STORE (tile 0 and tile 1 alternate): the store has read the staging
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -807,9 +804,8 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
       mbar_init(&o_full[i], 1);
       mbar_init(&s_empty[i], 8);
       mbar_init(&o_staged[i], 8);
-      mbar_init(&o_staged[2 + i], 8);
-      mbar_init(&o_free[i], 1);
     }
+    mbar_init(stage_free, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -823,11 +819,6 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
   griddep_launch_dependents();  // programmatic dependent launch: see gemm_bf16_kernel
   griddep_wait();
 
-  // staging address of item parity b, query tile t
-  auto stage_off = [](int b, int t) -> int {
-    return Cfg::kAliasO ? Cfg::kK + b * Cfg::kKBuf + t * Cfg::kOTile : Cfg::kO + (b * 2 + t) * Cfg::kOTile;
-  };
-
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer: runs one item ahead of the MMA warp =====================
@@ -838,7 +829,6 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
         const int q_row = item * 256;
         const int k_row = item * NK;
         mbar_wait(&k_empty[b], ph2);
-        if constexpr (Cfg::kAliasO) mbar_wait(&o_free[b], ph2);  // item n-2's output tiles were staged in this buffer
         uint8_t* kd = smem + Cfg::kK + b * Cfg::kKBuf;
         mbar_arrive_expect_tx(&k_full[b], Cfg::kBytesKV);
         tma_load_2d(kd, &tm_k64, &k_full[b], 0, k_row);
@@ -960,19 +950,19 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
   } else if (warp == 18) {
     if (lane == 0) {
       // ===================== TMA stores of the staged output tiles =====================
+      // store k = 2 n + t (the MMA order makes the tiles alternate: O_0(n), O_1(n), O_0(n+1), ...)
       int n = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++n) {
-        const int b = n & 1;
         const int sample = item / p.heads;
         const int head = item - sample * p.heads;
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
-          mbar_wait(&o_staged[b * 2 + t], (n >> 1) & 1);
-          tma_store_2d(&tm_o, smem + stage_off(b, t), head * kHeadDim, sample * 256 + t * kAttnBM);
+          mbar_wait(&o_staged[t], n & 1);
+          tma_store_2d(&tm_o, smem + Cfg::kO, head * kHeadDim, sample * 256 + t * kAttnBM);
           tma_store_commit();
+          tma_store_wait_read0();  // the staging tile has been read: the other query tile may overwrite it
+          mbar_arrive(stage_free);
         }
-        tma_store_wait_read0();  // both tiles have been read out of shared memory
-        mbar_arrive(&o_free[b]);
       }
       tma_store_wait_all0();
     }
@@ -1041,25 +1031,33 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
           tmem_st_32x16(p_col + c * 16, pk);
         }
       } else {
+        // 256 keys: 128 scores per thread do not fit in registers - two passes over TMEM, two 32-column loads in flight
+        // per wait (halves the exposed TMEM latencies of the chunk-at-a-time loop: 95 -> 93 us at the config-2 shape)
 #pragma unroll 1
-        for (int c = 0; c < NC; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(s_col + c * 32, v);
+        for (int c = 0; c < NC; c += 2) {
+          uint32_t v[2][32];
+          tmem_ld_32x32(s_col + c * 32, v[0]);
+          tmem_ld_32x32(s_col + c * 32 + 32, v[1]);
           tmem_ld_wait();
-          mx = softmax_chunk_max<HAS_BIAS>(v, mx, p.scale_log2e, bias_a + c * 128);
+          mx = softmax_chunk_max<HAS_BIAS>(v[0], mx, p.scale_log2e, bias_a + c * 128);
+          mx = softmax_chunk_max<HAS_BIAS>(v[1], mx, p.scale_log2e, bias_a + c * 128 + 128);
         }
         if constexpr (!HAS_BIAS) mx *= p.scale_log2e;
         sts_f1(my_slot, mx);
         named_bar_sync(bar_id, 64);
         mx = fmaxf(mx, lds_f1(peer_slot));
 #pragma unroll 1
-        for (int c = 0; c < NC; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(s_col + c * 32, v);
+        for (int c = 0; c < NC; c += 2) {
+          uint32_t v[2][32];
+          tmem_ld_32x32(s_col + c * 32, v[0]);
+          tmem_ld_32x32(s_col + c * 32 + 32, v[1]);
           tmem_ld_wait();
-          uint32_t pk[16];
-          softmax_chunk_exp<HAS_BIAS>(v, pk, sum2, mx, p.scale_log2e, bias_a + c * 128);
-          tmem_st_32x16(p_col + c * 16, pk);  // always behind this thread's own S reads
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            uint32_t pk[16];
+            softmax_chunk_exp<HAS_BIAS>(v[j], pk, sum2, mx, p.scale_log2e, bias_a + (c + j) * 128);
+            tmem_st_32x16(p_col + (c + j) * 16, pk);  // always behind this thread's own S reads
+          }
         }
       }
       float sum_lo, sum_hi;
@@ -1084,10 +1082,11 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[t]);
-      // staging of item n is free once the stores of item n-2 have read it (with the K alias the producer has waited
-      // for that already before loading K(n); the wait is then immediately true)
-      mbar_wait(&o_free[b], ((n >> 1) & 1) ^ 1);
-      const uint32_t srow = smem_u32(smem + stage_off(b, t)) + row * (kHeadDim * 2) + half * 96;
+      ATTN_T(s3a);
+      // the shared staging tile is free once store k - 1 has read it (k = 2 n + t; phase k - 1 has parity (t ^ 1))
+      mbar_wait(stage_free, t ^ 1);
+      ATTN_T(s3b);
+      const uint32_t srow = smem_u32(smem + Cfg::kO) + row * (kHeadDim * 2) + half * 96;
       auto stage8 = [&](const uint32_t* x, uint32_t addr) {
         sts_u4(addr, pack_bf16x2(__uint_as_float(x[0]) * inv, __uint_as_float(x[1]) * inv),
                pack_bf16x2(__uint_as_float(x[2]) * inv, __uint_as_float(x[3]) * inv),
@@ -1103,12 +1102,14 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
       }
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store (async proxy)
       __syncwarp();
-      if (lane == 0) mbar_arrive(&o_staged[b * 2 + t]);
+      if (lane == 0) mbar_arrive(&o_staged[t]);
       ATTN_T(s4);
       ATTN_ACC(0, s0, s1);  // wait S
       ATTN_ACC(1, s1, s2);  // softmax (max, exchange, exp, P store)
       ATTN_ACC(2, s2, s3);  // wait O
-      ATTN_ACC(3, s3, s4);  // O read-out + staging
+      ATTN_ACC(3, s3, s3a);   // O out of TMEM (tile handed back)
+      ATTN_ACC(4, s3a, s3b);  // wait for the staging tile
+      ATTN_ACC(5, s3b, s4);   // staging writes + proxy fence
     }
 #ifdef ECADK_ATTN_TIMING
     if (lane == 0 && (sw == 0 || sw == 12)) {

@@ -366,7 +366,7 @@ int launch_attn_pair_inst(const CUtensorMap* tq, const CUtensorMap* tm, const At
 template <int NK, bool HAS_BIAS>
 int launch_attn_pair2_inst(const CUtensorMap* tq, const CUtensorMap* tm, const CUtensorMap& to, const AttnParams& p,
                            int items, cudaStream_t stream) {
-  using Cfg = AttnPair2Cfg<NK>;
+  using Cfg = AttnPair2Cfg<NK, HAS_BIAS>;
   static bool configured = false;
   auto kern = attn_pair2_kernel<NK, HAS_BIAS>;
   if (!configured) {
@@ -483,7 +483,9 @@ int launch_attention(const void* q, const void* k, const void* v, const float* b
     if ((rc = make_tmap_bf16(&tq[0], q, q_rows, kHeadPad, kHeadPad, 256, 64, 128))) return rc;
     if ((rc = make_tmap_bf16(&tq[1], q, q_rows, kHeadPad, kHeadPad, 256, 16, 32))) return rc;
     const int items = samples * heads;
-    if (forced != 3) {
+    // (256 keys WITH a key bias - text lengths in (128, 256], no shipped configuration - stays on the first kernel: the
+    // second one has no shared memory left for the bias slices there)
+    if (forced != 3 && !(n_keys == 256 && bias != nullptr)) {
       // second-generation kernel: per-tile Q slots, per-item K/V double buffering, output through smem + TMA store
       CUtensorMap tq1[2], to;
       if ((rc = make_tmap_bf16(&tq1[0], q, q_rows, kHeadPad, kHeadPad, kAttnBM, 64, 128))) return rc;
@@ -491,10 +493,7 @@ int launch_attention(const void* q, const void* k, const void* v, const float* b
       if ((rc = make_tmap_bf16(&to, out, static_cast<uint64_t>(samples) * q_tokens, heads * kHeadDim, p.out_ld, kAttnBM,
                                kHeadDim, 0)))
         return rc;
-      if (n_keys == 256) {
-        return bias ? launch_attn_pair2_inst<256, true>(tq1, tm, to, p, items, stream)
-                    : launch_attn_pair2_inst<256, false>(tq1, tm, to, p, items, stream);
-      }
+      if (n_keys == 256) return launch_attn_pair2_inst<256, false>(tq1, tm, to, p, items, stream);
       return bias ? launch_attn_pair2_inst<128, true>(tq1, tm, to, p, items, stream)
                   : launch_attn_pair2_inst<128, false>(tq1, tm, to, p, items, stream);
     }
@@ -944,8 +943,8 @@ int ecadk_flux_blocks(ecadk_flux_handle_t h, const EcadkFluxArgs* a, const uint8
       if ((rc = ecadk_gemm_bias_headmajor_ex(a->h_img, w.w_qkv, w.b_qkv, a->q, a->k, a->v, 3, H, 128, 128, N, S, T,
                                              B * N, D, stream_)))
         return rc;
-      if ((rc = ecadk_qk_norm_rope(a->q, a->k, w.norm_q, w.norm_k, w.norm_added_q, w.norm_added_k, a->rope_cos,
-                                   a->rope_sin, B, H, S, T, d.eps, stream_)))
+      if ((rc = ecadk_qk_norm_rope_batched(a->q, a->k, w.norm_q, w.norm_k, w.norm_added_q, w.norm_added_k, a->rope_cos,
+                                           a->rope_sin, a->rope_sample_stride, B, H, S, T, d.eps, stream_)))
         return rc;
       if ((rc = launch_attention_d128(a->q, a->k, a->v, a->attn_img, D, a->attn_txt, T, B, H, S, S, stream))) return rc;
       if ((rc = ecadk_gemm_bias_gated_residual_cache(a->attn_img, w.w_out, w.b_out, a->x_img, nullptr, s_attn, nullptr,
@@ -1018,8 +1017,8 @@ int ecadk_flux_blocks(ecadk_flux_handle_t h, const EcadkFluxArgs* a, const uint8
       if ((rc = ecadk_gemm_bias_headmajor_ex(a->h_cat, w.w_qkv, w.b_qkv, a->q, a->k, a->v, 3, H, 128, 128, S, S, 0,
                                              B * S, D, stream_)))
         return rc;
-      if ((rc = ecadk_qk_norm_rope(a->q, a->k, w.norm_q, w.norm_k, nullptr, nullptr, a->rope_cos, a->rope_sin, B, H, S,
-                                   0, d.eps, stream_)))
+      if ((rc = ecadk_qk_norm_rope_batched(a->q, a->k, w.norm_q, w.norm_k, nullptr, nullptr, a->rope_cos, a->rope_sin,
+                                           a->rope_sample_stride, B, H, S, 0, d.eps, stream_)))
         return rc;
       if ((rc = launch_attention_d128(a->q, a->k, a->v, c_attn, D, nullptr, 0, B, H, S, S, stream))) return rc;
       launches += 3;
@@ -1162,11 +1161,20 @@ int ecadk_attention_d128(const void* q, const void* k, const void* v, void* out,
 int ecadk_qk_norm_rope(void* q, void* k, const float* wq, const float* wk, const float* wq_add, const float* wk_add,
                        const float* rope_cos, const float* rope_sin, int samples, int heads, int seq, int split,
                        float eps, ecadk_stream_t stream) {
+  return ecadk_qk_norm_rope_batched(q, k, wq, wk, wq_add, wk_add, rope_cos, rope_sin, 0, samples, heads, seq, split, eps,
+                                    stream);
+}
+
+int ecadk_qk_norm_rope_batched(void* q, void* k, const float* wq, const float* wk, const float* wq_add,
+                               const float* wk_add, const float* rope_cos, const float* rope_sin, int rope_sample_stride,
+                               int samples, int heads, int seq, int split, float eps, ecadk_stream_t stream) {
   ECADK_REQUIRE(q && k && wq && wk && rope_cos && rope_sin, "qk_norm_rope: null pointer");
   ECADK_REQUIRE(split == 0 || (wq_add && wk_add), "qk_norm_rope: split > 0 needs the added-stream norm weights");
+  ECADK_REQUIRE(rope_sample_stride == 0 || rope_sample_stride >= seq * 64,
+                "qk_norm_rope: rope_sample_stride=%d must be 0 (shared table) or >= seq*64", rope_sample_stride);
   ProfScope prof(ECADK_PROF_OTHER, 0.0, 0.0, static_cast<cudaStream_t>(stream));
   QkNormRopeParams p{static_cast<__nv_bfloat16*>(q), static_cast<__nv_bfloat16*>(k), wq, wk, wq_add, wk_add,
-                     rope_cos, rope_sin, samples * heads * seq, seq, split, eps};
+                     rope_cos, rope_sin, samples * heads * seq, seq, split, eps, heads * seq, rope_sample_stride};
   qk_norm_rope_kernel<<<(p.rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   return check_launch("qk_norm_rope_kernel");
 }

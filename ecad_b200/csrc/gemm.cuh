@@ -57,6 +57,9 @@ struct GemmParams {
   int unp_wp, unp_hp, unp_c, unp_cols;
 };
 
+#ifndef ECADK_EPI_X_L2_PREFETCH
+#define ECADK_EPI_X_L2_PREFETCH 1  // gated-residual epilogue: pull the NEXT tile's residual-stream rows into L2 early
+#endif
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;
 constexpr int kGemmThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
@@ -105,6 +108,29 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
   // residual-stream prefetch: the x values of this warp's NEXT chunk (c+2) are requested before chunk c is processed.
   // The two register sets ping-pong (the chunk loop is unrolled by two): copying "next" into "current" at the end of
   // an iteration would make the warp wait for the prefetch right there and expose the whole DRAM latency per chunk.
+  // The chunk's bias / gate vectors travel with it: loaded inside process() they sat on the critical path of every
+  // chunk (ncu source page, round 1: 52 % of the kernel's stall samples were long-scoreboard waits, the top one the
+  // FADD that combines the two gate loads).
+  struct Vecs {
+    float4 b4, g4;
+  };
+  auto load_vecs = [&](int c, Vecs& v) {
+    const int col = n0 + c * 32 + cg * 4;
+    v.b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    v.g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (p.bias != nullptr) v.b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+    if constexpr (EPI == EPI_GATED_RESIDUAL) {
+      if (p.gate_table != nullptr || p.gate_temb != nullptr) {
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.gate_table != nullptr) g = __ldg(reinterpret_cast<const float4*>(p.gate_table + col));
+        if (p.gate_temb != nullptr) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.gate_temb + static_cast<size_t>(sample0) * p.temb_stride + col));
+          g = make_float4(g.x + b.x, g.y + b.y, g.z + b.z, g.w + b.w);
+        }
+        v.g4 = g;
+      }
+    }
+  };
   auto load_x = [&](int c, float4 (&dst)[8]) {
     const int col = n0 + c * 32 + cg * 4;
 #pragma unroll
@@ -114,23 +140,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
                          : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
-  auto process = [&](const int c, const float4 (&xin)[8]) {
+  auto process = [&](const int c, const float4 (&xin)[8], const Vecs& vec, const uint32_t (&v)[32]) {
     const int col = n0 + c * 32 + cg * 4;
-    uint32_t v[32];
-    tmem_ld_32x32(t_row + c * 32, v);
-    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-    if constexpr (EPI == EPI_GATED_RESIDUAL) {
-      if (p.gate_table != nullptr || p.gate_temb != nullptr) {
-        g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.gate_table != nullptr) g4 = __ldg(reinterpret_cast<const float4*>(p.gate_table + col));
-        if (p.gate_temb != nullptr) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(p.gate_temb + static_cast<size_t>(sample0) * p.temb_stride + col));
-          g4 = make_float4(g4.x + b.x, g4.y + b.y, g4.z + b.z, g4.w + b.w);
-        }
-      }
-    }
-    tmem_ld_wait();
+    const float4 b4 = vec.b4, g4 = vec.g4;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       sts_u4(stage_s + (lane * kEpiPitch + 4 * j) * 4, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -228,22 +240,56 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
   const int c_begin = parity * half_chunks, c_step = 1;
   const int c_end = min(limit, c_begin + half_chunks);
 #endif
+  // (measured and rejected, round 2: requesting accumulator chunk c+1 from TMEM while chunk c is processed - two more
+  // register sets - changes nothing for the bf16-output epilogues and makes the gated-residual one slower, 197 -> 254 us)
+  uint32_t ta[32];
+  auto acc_ready = [&](const int c) {
+    tmem_ld_32x32(t_row + c * 32, ta);
+    tmem_ld_wait();
+  };
   if constexpr (EPI == EPI_GATED_RESIDUAL) {
     float4 xa[8], xb_[8];
-    if (c_begin < c_end) load_x(c_begin, xa);
+    Vecs va, vb;
+    if (c_begin < c_end) {
+      load_vecs(c_begin, va);
+      load_x(c_begin, xa);
+    }
 #pragma unroll 1
     for (int c = c_begin; c < c_end; c += 2 * c_step) {
-      if (c + c_step < c_end) load_x(c + c_step, xb_);
-      process(c, xa);
-      if (c + c_step < c_end) {
-        if (c + 2 * c_step < c_end) load_x(c + 2 * c_step, xa);
-        process(c + c_step, xb_);
+      const bool more = c + c_step < c_end;
+      if (more) {
+        load_vecs(c + c_step, vb);
+        load_x(c + c_step, xb_);
+      }
+      acc_ready(c);
+      process(c, xa, va, ta);
+      if (more) {
+        const bool more2 = c + 2 * c_step < c_end;
+        if (more2) {
+          load_vecs(c + 2 * c_step, va);
+          load_x(c + 2 * c_step, xa);
+        }
+        acc_ready(c + c_step);
+        process(c + c_step, xb_, vb, ta);
       }
     }
   } else {
     const float4 none[8] = {};
+    Vecs va, vb;
+    if (c_begin < c_end) load_vecs(c_begin, va);
 #pragma unroll 1
-    for (int c = c_begin; c < c_end; c += c_step) process(c, none);
+    for (int c = c_begin; c < c_end; c += 2 * c_step) {
+      const bool more = c + c_step < c_end;
+      if (more) load_vecs(c + c_step, vb);
+      acc_ready(c);
+      process(c, none, va, ta);
+      if (more) {
+        const bool more2 = c + 2 * c_step < c_end;
+        if (more2) load_vecs(c + 2 * c_step, va);
+        acc_ready(c + c_step);
+        process(c + c_step, none, vb, ta);
+      }
+    }
   }
 }
 
@@ -548,6 +594,23 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int n_idx = tile % num_n;
       const int n0 = n_idx * BN;
       const int n_chunks = (n_idx >= num_n_full ? tail : BN) / 32;
+      if constexpr (EPI == EPI_GATED_RESIDUAL && ECADK_EPI_X_L2_PREFETCH) {
+        // The epilogue of this kernel is bound by the latency of its residual-stream reads (one 4 KB chunk per warp in
+        // flight: tools/micro/epi2_sensitivity.py shows the side traffic ADDS to the MMA time instead of hiding under
+        // it).  While this tile's MMAs finish, every lane asks L2 for the row piece its warp will read in the NEXT
+        // tile - one 512-byte request per lane, no registers, no shared memory - so those reads become L2 hits.
+        const int nt = tile + num_pairs;
+        if (nt < num_tiles) {
+          const int nn = nt % num_n;
+          const int chunks = (nn >= num_n_full ? tail : BN) / 32;
+          const int half_chunks = (chunks + 1) / 2;
+          const int c0 = ((warp - 2) >> 2) * half_chunks;
+          const int cols = (min(chunks, c0 + half_chunks) - c0) * 32;
+          const int row = (nt / num_n) * (2 * kGemmBM) + cta * kGemmBM + quarter * 32 + lane;
+          if (cols > 0 && row < p.M)
+            prefetch_l2_bulk(p.x + static_cast<size_t>(row) * p.N + nn * BN + c0 * 32, cols * 4);
+        }
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int row_base = m0 + quarter * 32;

@@ -375,11 +375,13 @@ struct QkNormRopeParams {
   const float* wk;       // [128] norm_k.weight
   const float* wq_add;   // [128] norm_added_q.weight (text tokens), or null
   const float* wk_add;   // [128]
-  const float* cos_t;    // [S, 64]
-  const float* sin_t;    // [S, 64]
+  const float* cos_t;    // [S, 64], or [B, S, 64] with sample_stride = S * 64
+  const float* sin_t;
   int rows;              // B * H * S
   int S, split;
   float eps;
+  int rows_per_sample;   // H * S
+  int sample_stride;     // floats between the rotation tables of two samples; 0 = one table for the batch
 };
 __global__ void __launch_bounds__(256) qk_norm_rope_kernel(const QkNormRopeParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -387,8 +389,9 @@ __global__ void __launch_bounds__(256) qk_norm_rope_kernel(const QkNormRopeParam
   if (row >= p.rows) return;
   const int s = row % p.S;
   const bool added = s < p.split;
-  const float2 c2 = __ldg(reinterpret_cast<const float2*>(p.cos_t + static_cast<size_t>(s) * 64) + lane);
-  const float2 s2 = __ldg(reinterpret_cast<const float2*>(p.sin_t + static_cast<size_t>(s) * 64) + lane);
+  const size_t tab = static_cast<size_t>(row / p.rows_per_sample) * p.sample_stride + static_cast<size_t>(s) * 64;
+  const float2 c2 = __ldg(reinterpret_cast<const float2*>(p.cos_t + tab) + lane);
+  const float2 s2 = __ldg(reinterpret_cast<const float2*>(p.sin_t + tab) + lane);
 #pragma unroll
   for (int which = 0; which < 2; ++which) {
     __nv_bfloat16* base = (which == 0 ? p.q : p.k) + static_cast<size_t>(row) * 128;

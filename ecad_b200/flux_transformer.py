@@ -407,13 +407,23 @@ class B200FluxTransformer2D:
                          for t in (img_ids, txt_ids))
         if self._rope_key != rope_key:
             ii, ti = img_ids, txt_ids
+            stride = 0
             if ii.ndim == 3:
+                if ii.shape[0] != B or ti.shape[0] != B:
+                    raise ValueError(f"batched position ids must have {B} samples")
                 if bool((ii != ii[:1]).any()) or bool((ti != ti[:1]).any()):
-                    raise NotImplementedError("per-sample position ids are not supported (one resolution per batch)")
-                ii, ti = ii[0], ti[0]
-            cos, sin = rope_tables(torch.cat([ti, ii], dim=0), cfg.axes_dims_rope)
+                    # per-sample ids (EmbedND is applied to the batched [B, S, 3] ids): one table per sample
+                    tabs = [rope_tables(torch.cat([ti[b_], ii[b_]], dim=0).cpu(), cfg.axes_dims_rope) for b_ in range(B)]
+                    cos = torch.stack([c for c, _ in tabs]).contiguous()
+                    sin = torch.stack([s_ for _, s_ in tabs]).contiguous()
+                    stride = S * 64
+                else:
+                    ii, ti = ii[0], ti[0]
+            if stride == 0:
+                cos, sin = rope_tables(torch.cat([ti, ii], dim=0), cfg.axes_dims_rope)
             ws["rope_cos"], ws["rope_sin"] = cos.to(dev), sin.to(dev)
             ws["args"].rope_cos, ws["args"].rope_sin = ws["rope_cos"].data_ptr(), ws["rope_sin"].data_ptr()
+            ws["args"].rope_sample_stride = stride
             self._rope_key = rope_key
 
         # blocks under the decision row of the current step

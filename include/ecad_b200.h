@@ -181,6 +181,13 @@ int ecadk_qk_norm_rope(void* q, void* k, const float* wq, const float* wk, const
                        const float* rope_cos, const float* rope_sin, int samples, int heads, int seq, int split,
                        float eps, ecadk_stream_t stream);
 
+/* Same with one rotation table per sample: rope_cos / rope_sin fp32 [samples, seq, 64] with `rope_sample_stride`
+ * floats between samples (0 = one [seq, 64] table shared by the batch).  diffusers' EmbedND takes batched ids
+ * [B, S, 3] (flux_transformer_2d_edited.py:290-291), so per-sample position ids are part of the interface. */
+int ecadk_qk_norm_rope_batched(void* q, void* k, const float* wq, const float* wk, const float* wq_add,
+                               const float* wk_add, const float* rope_cos, const float* rope_sin, int rope_sample_stride,
+                               int samples, int heads, int seq, int split, float eps, ecadk_stream_t stream);
+
 /* dst[r, 0:cols] = op(src[r, 0:cols]) on bf16 rows with independent pitches; op 0 = copy, 1 = GELU(tanh).
  * Replaces act_mlp(...) on the (possibly cached, pre-activation) proj_mlp output and the torch.cat of the
  * single-stream block (cached_flux_transformer_block.py:107-117). */
@@ -351,7 +358,7 @@ typedef struct {
                       * (norm1_context.linear), each = shift_msa|scale_msa|gate_msa|shift_mlp|scale_mlp|gate_mlp;
                       * single block b: [num_layers*12*dim + b*3*dim, +3*dim) = shift|scale|gate (norm.linear). */
   int mod_stride;
-  const float* rope_cos;   /* fp32 [T+N, 64] */
+  const float* rope_cos;   /* fp32 [T+N, 64] (or [B, T+N, 64], see rope_sample_stride) */
   const float* rope_sin;
   void* const* cache_double; /* host array [num_layers*4]: attn [B*N,dim], context_attn [B*T,dim], ff [B*N,dim], ff_context [B*T,dim] */
   void* const* cache_single; /* host array [num_single_layers*3]: attn [B*(T+N),dim], proj_mlp (pre-GELU) [B*(T+N),4*dim], proj_out [B*(T+N),dim] */
@@ -359,6 +366,8 @@ typedef struct {
                               * later read.  Honoured for the epilogue side-stores (double blocks: attn pair, ff,
                               * ff_context; single blocks: proj_out); single_attn / single_proj_mlp are produced straight
                               * into their cache slots and are always written. */
+  int rope_sample_stride;    /* floats between the rotation tables of two samples ([B, T+N, 64] tables), 0 = one
+                              * [T+N, 64] table for the whole batch */
 } EcadkFluxArgs;
 
 /* executed[(b)*3 + c]: rows 0..num_layers-1 = double blocks with c in {full_attn, full_ff, full_ff_context}, rows

@@ -67,7 +67,7 @@ def test_rope_tables_match_embed_nd():
 
 def test_flux_args_struct_layout():
     # mirrors include/ecad_b200.h: 3 ints (+pad), 14 pointers, int (+pad), 2 pointers, 2 pointer arrays, dead mask
-    assert C.sizeof(_lib.EcadkFluxArgs) == 16 + 14 * 8 + 8 + 5 * 8
+    assert C.sizeof(_lib.EcadkFluxArgs) == 16 + 14 * 8 + 8 + 5 * 8 + 8  # ... + rope_sample_stride (+pad)
     assert C.sizeof(_lib.EcadkFluxDesc) == 20
     assert C.sizeof(_lib.EcadkFluxDoubleWeights) == 20 * 8 and C.sizeof(_lib.EcadkFluxSingleWeights) == 8 * 8
     assert _lib.EcadkFluxArgs.mod_stride.offset == 16 + 14 * 8

@@ -124,3 +124,68 @@ def test_flux_full_width_forward_matches_oracle(cuda_device):
         assert _rel(got, ref) <= 1e-2 and _cos(got, ref) >= 0.9999, (step, _rel(got, ref), _cos(got, ref))
         sched.per_step_callback(step)
         oracle.cache_schedule.per_step_callback(step)
+
+
+def test_flux_full_width_shipped_schedule_generation(cuda_device):
+    """FLUX.1-dev WIDTH (24 heads x 128 = 3072, T5 4096 channels, 512 text tokens) with 4 double-stream + 8 single-stream
+    blocks, a cached generation under the decision rows of the paper's shipped schedule
+    (schedules/schedules_in_paper/flux_256/ours_fast.json: rows of double blocks 0-3 and single blocks 0-7, first 5
+    steps) at 256x256 so the CPU oracle finishes, batch 2 with PER-SAMPLE img_ids (the second sample's positions are a
+    shifted crop): decisions bit-exact, every step's model output and the final latents within the bf16 bars."""
+    import gzip
+    import json
+    from pathlib import Path
+
+    from ecad_b200.flux_pipeline import FlowMatchEulerDiscrete, calculate_shift, latent_image_ids, pack_latents
+    from ecad_b200.flux_transformer import B200FluxTransformer2D
+    from ecad_b200.schedule import FluxCacheSchedule
+    from ecad_b200.transformer import SequentialDiTScheduler
+    from ecad_b200.weights import FluxConfig, flux_random_init_state_dict
+    from oracle.flux_oracle import FluxOracle, FluxOracleConfig, FluxOracleSchedule
+
+    rows = json.loads(gzip.open(Path(__file__).parent / "golden" / "flux_schedules.json.gz").read())["rows"]
+    r = [r for r in rows if r["path"] == "schedules_in_paper/flux_256/ours_fast.json"][0]
+    full = (np.unpackbits(np.frombuffer(bytes.fromhex(r["bits"]), np.uint8))[: r["S"] * 57 * 3]
+            .reshape(r["S"], 57, 3).astype(bool))
+    ND, NS, steps = 4, 8, 5
+    flags = np.concatenate([full[:steps, :ND], full[:steps, 19:19 + NS]], axis=1)
+    assert 0.2 < flags[1:].mean() < 0.9  # the slice really mixes executed and reused components
+
+    kw = dict(num_layers=ND, num_single_layers=NS)
+    cfg = FluxConfig(**kw)
+    sd = flux_random_init_state_dict(cfg, seed=2)
+    B, T, hw = 2, 512, 16  # 256x256 px -> 16 x 16 = 256 image tokens
+    N = hw * hw
+    emb = _embeds(B, T, dict(joint_attention_dim=4096, pooled_projection_dim=768), seed=4)
+    lat = pack_latents(torch.randn(B, 16, 2 * hw, 2 * hw, generator=torch.Generator().manual_seed(6)))
+    ids = latent_image_ids(B, hw, hw)
+    ids[1, :, 1] += 7.0   # sample 1: another crop of the position grid -> its own rotation table
+    ids[1, :, 2] += 3.0
+    tids = torch.zeros(B, T, 3)
+    guid = torch.full((B,), 3.5)
+    sched_host = FlowMatchEulerDiscrete()
+    c = sched_host.config
+    sched_host.set_timesteps(steps, mu=calculate_shift(N, c.base_image_seq_len, c.max_image_seq_len, c.base_shift,
+                                                      c.max_shift))
+    sig = sched_host.sigmas
+
+    sched = FluxCacheSchedule.from_numpy(flags, steps, ND, NS, "ours_fast[4+8 blocks, 5 steps]")
+    model = B200FluxTransformer2D(sd, cfg, SequentialDiTScheduler(steps), sched)
+    oracle = FluxOracle(sd, FluxOracleConfig(**kw), FluxOracleSchedule.from_flags(flags, ND, NS))
+    x_gpu, x_ref = lat.clone(), lat.clone()
+    for s in range(steps):
+        t = torch.full((B,), float(sig[s]))
+        got = model(x_gpu.cuda(), emb["prompt_embeds"].cuda(), emb["pooled_prompt_embeds"].cuda(), t.cuda(), ids, tids,
+                    guid.cuda(), return_dict=False)[0].float().cpu()
+        ref = oracle.forward(x_ref, emb["prompt_embeds"], emb["pooled_prompt_embeds"], t, ids, tids, guid)
+        assert np.array_equal(model.last_executed, oracle.trace.to_numpy(steps, ND + NS)[s]), s
+        assert _rel(got, ref) <= 1e-2, (s, _rel(got, ref))
+        for b in range(B):  # per sample: a wrong rotation table for sample 1 must not hide behind sample 0
+            assert _rel(got[b], ref[b]) <= 1e-2, (s, b)
+        dt = float(sig[s + 1]) - float(sig[s])
+        x_gpu, x_ref = x_gpu + dt * got, x_ref + dt * ref
+        sched.per_step_callback(s)
+        oracle.cache_schedule.per_step_callback(s)
+    assert _cos(x_gpu, x_ref) >= 0.999 and _rel(x_gpu, x_ref) <= 1e-2
+    # the per-sample tables matter: the two samples use different rotations
+    assert model._ws["args"].rope_sample_stride == (N + T) * 64

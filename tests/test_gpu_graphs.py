@@ -161,3 +161,95 @@ def test_population_run_from_host_pipelines_copies_and_keeps_results(cuda_device
     for got, dev, want in zip(out["host"], out["device"], ref):
         assert torch.equal(got, want) and torch.equal(dev.cpu(), want)
     assert not torch.equal(ref[0], ref[1])  # different candidates really produce different latents
+
+
+def test_graph_cache_is_keyed_on_schedule_content(cuda_device):
+    """A set_schedule() loop over GA candidates creates many short-lived schedule objects that all carry the same name
+    ("from_numpy") and whose addresses get reused: the graph cache must key on what the schedule SAYS.  Same content
+    (another object) -> the recorded graph is replayed; different content under the same name -> a new recording, and
+    the replayed latents equal the eager ones in both cases."""
+    from ecad_b200.image_generator import B200PixArtAlphaImageGenerator
+    from ecad_b200.schedule import PixArtCacheSchedule
+    from ecad_b200.weights import PixArtConfig, random_init_state_dict, synthetic_prompt_embeddings
+
+    L, steps = 4, 4
+    cfg = PixArtConfig(num_layers=L)
+    sd = random_init_state_dict(cfg, 0)
+    rng = np.random.default_rng(0)
+    fa = rng.random((steps, L, 3)) < 0.5
+    fb = fa.copy()
+    fb[2, 1, 2] = not fb[2, 1, 2]
+    eager = B200PixArtAlphaImageGenerator(cache_schedule=PixArtCacheSchedule.from_numpy(fa, steps, L), state_dict=sd,
+                                          model_config=cfg)
+    graphed = B200PixArtAlphaImageGenerator(cache_schedule=PixArtCacheSchedule.from_numpy(fa, steps, L), state_dict=sd,
+                                            model_config=cfg, use_cuda_graph=True)
+    emb = synthetic_prompt_embeddings(2, seed=4)
+    outs = {}
+    for tag, f in (("a", fa), ("b", fb), ("a again", fa), ("b again", fb)):
+        # a NEW object every time, all named "from_numpy"
+        eager.set_schedule(PixArtCacheSchedule.from_numpy(f, steps, L))
+        graphed.set_schedule(PixArtCacheSchedule.from_numpy(f, steps, L))
+        e, g = eager.generate_images(emb)[0], graphed.generate_images(emb)[0]
+        assert torch.equal(e, g), tag
+        outs[tag] = g
+    assert not torch.equal(outs["a"], outs["b"])
+    assert torch.equal(outs["a"], outs["a again"]) and torch.equal(outs["b"], outs["b again"])
+    gg = graphed.diffusion_pipeline._graphs
+    assert gg.captures == 2 and gg.replays == 4
+    # a larger batch re-allocates the transformer workspace: the recorded graphs (raw pointers into it) are dropped
+    emb3 = synthetic_prompt_embeddings(3, seed=4)
+    eager.set_schedule(PixArtCacheSchedule.from_numpy(fa, steps, L))
+    graphed.set_schedule(PixArtCacheSchedule.from_numpy(fa, steps, L))
+    assert torch.equal(eager.generate_images(emb3)[0], graphed.generate_images(emb3)[0])
+    assert torch.equal(eager.generate_images(emb)[0], graphed.generate_images(emb)[0])  # back to the small batch
+
+
+def test_generate_from_saved_prompts_and_module_shell(cuda_device, tmp_path):
+    """The file-driven generator API on the GPU (image_generator.py:366-421,442-487): a directory of saved prompt
+    embeddings -> one latent file per (prompt, seed) equal to a direct generate_images call; time_image_generation
+    returns one ms-per-image figure per batch.  Also: the transformer is an nn.Module shell a pipeline can hold."""
+    from ecad_b200.dataset import PIXART_KEYS
+    from ecad_b200.image_generator import B200PixArtAlphaImageGenerator
+    from ecad_b200.schedule import PixArtCacheSchedule
+    from ecad_b200.weights import PixArtConfig, random_init_state_dict, synthetic_prompt_embeddings
+
+    L, steps = 3, 3
+    cfg = PixArtConfig(num_layers=L)
+    sd = random_init_state_dict(cfg, 1)
+    flags = np.random.default_rng(1).random((steps, L, 3)) < 0.6
+    emb = synthetic_prompt_embeddings(3, seed=8)
+    src, dst = tmp_path / "prompts", tmp_path / "latents"
+    for i in range(3):
+        d = src / ("x" if i < 2 else "y")
+        d.mkdir(parents=True, exist_ok=True)
+        torch.save({k: emb[k][i:i + 1] for k in PIXART_KEYS}, d / f"p{i}.pt")
+    gen = B200PixArtAlphaImageGenerator(cache_schedule=PixArtCacheSchedule.from_numpy(flags, steps, L), start_seed=5,
+                                        seed_step=3, state_dict=sd, model_config=cfg)
+    gen.generate_from_saved_prompts(src, dst, batch_size=2, images_per_prompt=2)
+    files = sorted(p.relative_to(dst).as_posix() for p in dst.glob("**/*.pt"))
+    assert files == sorted(f"{'x' if i < 2 else 'y'}/p{i}__image_seed:{s:03}.pt" for i in range(3) for s in (5, 8))
+    direct = gen.generate_images({k: emb[k][:2] for k in PIXART_KEYS}, images_per_prompt=2)
+    assert torch.equal(torch.load(dst / "x" / "p1__image_seed:008.pt"), direct[1][1].cpu())
+    times = gen.time_image_generation(src, batch_size=2, num_batches=3)
+    assert len(times) == 3 and all(t > 0 for t in times)
+
+    tr = gen.diffusion_pipeline.transformer
+    assert isinstance(tr, torch.nn.Module) and not tr.training and list(tr.parameters()) == []
+    names = dict(tr.named_buffers())
+    assert "block0_w_qkv1" in names and names["block0_w_qkv1"].dtype == torch.bfloat16 and len(tr.state_dict()) > 15 * L
+    assert tr.to("cuda:0") is tr and tr.eval() is tr
+    with pytest.raises(RuntimeError, match="bound to its device"):
+        tr.to("cpu")
+    with pytest.raises(RuntimeError, match="bound to its device"):
+        tr.half()
+    holder = torch.nn.ModuleDict({"transformer": tr})  # what a diffusers pipeline's register_modules needs
+    assert holder["transformer"] is tr
+    # the forward returns fresh tensors: two outputs kept across calls do not alias
+    x = torch.randn(2, 4, 32, 32, device="cuda")
+    kw = dict(encoder_hidden_states=emb["prompt_embeds"][:2].cuda(), encoder_attention_mask=emb["prompt_attention_mask"][:2].cuda(),
+              timestep=torch.full((2,), 500, device="cuda"), added_cond_kwargs={"resolution": None, "aspect_ratio": None},
+              return_dict=False)
+    o1 = tr(x, **kw)[0]
+    keep = o1.clone()
+    o2 = tr(x * 0.5, **kw)[0]
+    assert o1.data_ptr() != o2.data_ptr() and torch.equal(o1, keep)

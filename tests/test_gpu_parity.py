@@ -4,8 +4,8 @@ CPU fp32 oracle on identical random-init weights, synthetic caption embeddings a
 Bars (BASELINE.json north_star):
   * per-step / per-block compute-or-reuse decisions: BIT-EXACT
   * latents: bf16 tensor-core operands + fp32 accumulators / fp32 residual stream vs the fp32 oracle:
-      per-step   max|x - x_ref| / max|x_ref| <= 1e-2
-      final      cosine similarity >= 0.999   (measured ~0.99999)
+      per-step   max|x - x_ref| / max|x_ref| <= 1e-2   (asserted at 5e-3; measured 3.5e-3)
+      final      cosine similarity >= 0.999            (asserted at 0.9999; measured ~0.99999)
 """
 import numpy as np
 import pytest
@@ -15,8 +15,10 @@ from golden_util import flags_of, row_by_path, schedule_of
 
 pytestmark = pytest.mark.gpu
 
-PER_STEP_REL_MAXABS = 1e-2
-FINAL_COS = 0.999
+# north_star's bars are 1e-2 per step / cosine 0.999; the assertions are held tighter (measured on B200: 3.5e-3 per
+# step, cosine 0.99999) so that a numerical regression is caught long before it reaches the stated tolerance
+PER_STEP_REL_MAXABS = 5e-3
+FINAL_COS = 0.9999
 
 
 @pytest.fixture(scope="module")
@@ -197,13 +199,18 @@ def test_cached_generation_512px_small_model(cuda_device):
     assert _cos(got, ref) >= FINAL_COS
 
 
-def test_tgate_generation_matches_oracle(cuda_device, weights):
+@pytest.mark.parametrize("schedule_file,want_gate", [
+    ("alpha_cache_schedules/gen_tgate/tgate_m_010_sp_003_fi_001_warmup_002.json", 10),
+    ("alpha_cache_schedules/gen_tgate_m_k_expanded/tgate_m_006_sp_001_fi_001_warmup_002.json", 6),
+    ("alpha_cache_schedules/gen_tgate/tgate_m_015_sp_005_fi_001_warmup_002.json", 15)])
+def test_tgate_generation_matches_oracle(cuda_device, weights, schedule_file, want_gate):
     """TGATE (ecad/pipelines/tgate.py + compute_attn_tgate): CFG pair until the gate step, the cross-attention cache
-    averaged at gate_step - 1, then the null embedding alone with attn2 always served from the averaged cache."""
+    averaged at gate_step - 1, then the null embedding alone with attn2 always served from the averaged cache.  Three
+    shipped schedules with different gate steps and self-attention / feed-forward sharing periods."""
     from ecad_b200.image_generator import B200PixArtAlphaImageGenerator
     from ecad_b200.weights import synthetic_prompt_embeddings
 
-    row = row_by_path("alpha_cache_schedules/gen_tgate/tgate_m_010_sp_003_fi_001_warmup_002.json")
+    row = row_by_path(schedule_file)
     flags = flags_of(row)
     gate = row["config"]["pipeline"]["kwargs"]["gate_step"]
     custom = {"name": row["custom"]["attn"], "kwargs": {"gate_step": row["custom"]["gate_step"]}}
@@ -216,7 +223,7 @@ def test_tgate_generation_matches_oracle(cuda_device, weights):
 
     gen = B200PixArtAlphaImageGenerator(cache_schedule=schedule_of(row), start_seed=0, state_dict=weights,
                                         additional_callbacks=[spy])
-    assert gen.gate_step == gate == 10
+    assert gen.gate_step == gate == want_gate
     got = gen.generate_images(emb, images_per_prompt=1)[0].cpu()
     noise = torch.randn(2, 4, 32, 32, generator=torch.Generator().manual_seed(0))
     ref, ref_trace = _oracle_run(weights, flags, emb, noise, custom=custom, gate_step=gate)
@@ -333,3 +340,74 @@ def test_tensor_level_custom_compute_functions(cuda_device, weights):
         ComputeAttnRegistry._tensor_registry.pop("compute_attn_blend", None)
         ComputeFFRegistry._tensor_registry.pop("compute_ff_every_other", None)
         PixArtOracle.custom_attn_fns, PixArtOracle.custom_ff_fns = {}, {}
+
+
+def test_sigma_cached_generation_shipped_schedule(cuda_device, weights):
+    """PixArt-sigma 256x256 (BASELINE config 4's model family: 300 text tokens -> cross-attention keys padded to 384,
+    streamed), a full 20-step generation under the paper's shipped schedule
+    schedules/schedules_in_paper/pixart_sigma_256/ours_fast.json, through the sigma generator entry."""
+    from ecad_b200.image_generator import B200PixArtSigmaImageGenerator
+    from ecad_b200.weights import synthetic_prompt_embeddings
+
+    row = row_by_path("schedules_in_paper/pixart_sigma_256/ours_fast.json")
+    flags = flags_of(row)
+    emb = synthetic_prompt_embeddings(1, text_tokens=B200PixArtSigmaImageGenerator.text_tokens, seed=11)
+    traces, per_step = [], []
+
+    def spy(step, timestep, latents=None, **kw):
+        traces.append(gen.diffusion_pipeline.transformer.last_executed.copy())
+        per_step.append(latents.detach().cpu().clone())
+
+    gen = B200PixArtSigmaImageGenerator(cache_schedule=schedule_of(row), start_seed=0, state_dict=weights,
+                                        additional_callbacks=[spy])
+    assert gen.text_tokens == 300 and not gen.model_config.resolved_additional_conditions
+    got = gen.generate_images(emb, images_per_prompt=1)[0].cpu()
+    noise = torch.randn(1, 4, 32, 32, generator=torch.Generator().manual_seed(0))
+    ref, ref_trace = _oracle_run(weights, flags, emb, noise)
+    assert np.array_equal(np.stack(traces), ref_trace)
+    assert 0.2 < ref_trace[1:].mean() < 0.8  # a genuinely cached run
+    for s, (a, b) in enumerate(zip(per_step, ref["per_step"])):
+        rel = float((a - b).abs().max() / b.abs().max())
+        assert rel <= PER_STEP_REL_MAXABS, (s, rel)
+    assert _cos(got, ref["latents"]) >= FINAL_COS
+
+
+def test_sigma_1024px_cached_multistep_reduced_depth(cuda_device):
+    """BASELINE config 4 shape (PixArt-sigma 1024x1024: N = 4096 image tokens, 300 text tokens, no micro-conditions) on
+    a reduced-depth model (3 blocks) so the CPU oracle finishes: a 4-step CACHED run - dense first step, then reuse /
+    recompute mixes incl. a step that reuses everything - with the 4096-key streamed self-attention, the 384-key
+    streamed cross-attention and the lazy reuse path all at the full token count."""
+    from ecad_b200.image_generator import B200PixArtSigmaImageGenerator
+    from ecad_b200.schedule import PixArtCacheSchedule
+    from ecad_b200.weights import PixArtConfig, random_init_state_dict, synthetic_prompt_embeddings
+    from oracle.pixart_oracle import OracleConfig, OracleSchedule, PixArtOracle, generate_latents
+
+    L, steps = 3, 4
+    cfg = PixArtConfig(sample_size=128, num_layers=L, use_additional_conditions=False)
+    sd = random_init_state_dict(cfg, seed=6)
+    flags = np.ones((steps, L, 3), bool)
+    flags[1] = [[False, True, False], [True, False, True], [False, False, True]]
+    flags[2] = False
+    flags[3] = [[True, False, False], [False, True, False], [True, True, True]]
+    emb = synthetic_prompt_embeddings(1, text_tokens=300, seed=12)
+    traces, per_step = [], []
+
+    def spy(step, timestep, latents=None, **kw):
+        traces.append(gen.diffusion_pipeline.transformer.last_executed.copy())
+        per_step.append(latents.detach().cpu().clone())
+
+    gen = B200PixArtSigmaImageGenerator(cache_schedule=PixArtCacheSchedule.from_numpy(flags, steps, L, "sigma1024"),
+                                        start_seed=0, state_dict=sd, model_config=cfg, additional_callbacks=[spy])
+    got = gen.generate_images(emb, images_per_prompt=1)[0].cpu()
+    assert got.shape == (1, 4, 128, 128)
+    ocfg = OracleConfig(sample_size=128, num_layers=L, use_additional_conditions=False)
+    model = PixArtOracle(sd, ocfg, OracleSchedule.from_flags(flags))
+    noise = torch.randn(1, 4, 128, 128, generator=torch.Generator().manual_seed(0))
+    ref = generate_latents(model, emb["prompt_embeds"], emb["prompt_attention_mask"], emb["negative_prompt_embeds"],
+                           emb["negative_prompt_attention_mask"], noise, steps, record_steps=True)
+    assert np.array_equal(np.stack(traces), model.trace.to_numpy(steps, L))
+    assert np.array_equal(np.stack(traces)[1:], flags[1:].astype(np.uint8))  # caches exist after step 0
+    for s, (a, b) in enumerate(zip(per_step, ref["per_step"])):
+        rel = float((a - b).abs().max() / b.abs().max())
+        assert rel <= PER_STEP_REL_MAXABS, (s, rel)
+    assert _cos(got, ref["latents"]) >= FINAL_COS

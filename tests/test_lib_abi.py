@@ -50,8 +50,10 @@ def test_struct_layouts_match_header(lib):
 #include <stdio.h>
 #include "ecad_b200.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu\n", sizeof(EcadkReuse), sizeof(EcadkResidualLnArgs), sizeof(EcadkModelDesc),
-         sizeof(EcadkBlockWeights), sizeof(EcadkBlocksArgs));
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(EcadkReuse), sizeof(EcadkResidualLnArgs),
+         sizeof(EcadkModelDesc), sizeof(EcadkBlockWeights), sizeof(EcadkBlocksArgs), sizeof(EcadkFluxDesc),
+         sizeof(EcadkFluxDoubleWeights), sizeof(EcadkFluxSingleWeights), sizeof(EcadkFluxArgs),
+         sizeof(EcadkProfileRecord));
   return 0;
 }
 '''
@@ -62,7 +64,9 @@ int main(void) {
         subprocess.run(["gcc", "-I", str(ROOT / "include"), str(c), "-o", str(exe)], check=True)
         sizes = list(map(int, subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()))
     mine = [ctypes.sizeof(t) for t in (_lib.EcadkReuse, _lib.EcadkResidualLnArgs, _lib.EcadkModelDesc,
-                                        _lib.EcadkBlockWeights, _lib.EcadkBlocksArgs)]
+                                        _lib.EcadkBlockWeights, _lib.EcadkBlocksArgs, _lib.EcadkFluxDesc,
+                                        _lib.EcadkFluxDoubleWeights, _lib.EcadkFluxSingleWeights, _lib.EcadkFluxArgs,
+                                        _lib.EcadkProfileRecord)]
     assert mine == sizes
 
 

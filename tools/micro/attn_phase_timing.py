@@ -65,7 +65,7 @@ if mode.startswith("c2"):
                             "wait Q1 + O_1 read out + QK1", "wait V + P0", "issue PV0"]):
         print(f"  MMA thread   {nm:26s} {mma[:, i].mean() / items:8.1f}")
     for tile, arr in ((0, s0), (1, s1)):
-        for i, nm in enumerate(["wait S", "softmax", "wait O", "O read-out + stores"]):
+        for i, nm in enumerate(["wait S", "softmax", "wait O", "O out of TMEM", "wait staging tile", "staging writes + fence"]):
             print(f"  softmax t{tile}   {nm:26s} {arr[:, i].mean() / items:8.1f}")
     sys.exit(0)
 nb = mma[:, 7].mean()
