@@ -97,9 +97,16 @@ std::mutex g_tmap_mu;
 std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
 
 // 2-D bf16 tensor [rows, cols] with row pitch `pitch` elements; box = [box_rows, box_cols]; swizzle in bytes.
+int make_tmap(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_rows,
+              uint32_t box_cols, uint32_t swizzle_bytes, uint32_t elem_bytes);
 int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch,
                    uint32_t box_rows, uint32_t box_cols, uint32_t swizzle_bytes) {
-  TmapKey key{ptr, rows, cols, pitch, box_rows, box_cols, swizzle_bytes};
+  return make_tmap(out, ptr, rows, cols, pitch, box_rows, box_cols, swizzle_bytes, 2);
+}
+// elem_bytes: 2 = bf16, 4 = fp32 (the residual stream, stored by the gated-residual epilogue)
+int make_tmap(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_rows,
+              uint32_t box_cols, uint32_t swizzle_bytes, uint32_t elem_bytes) {
+  TmapKey key{ptr, rows, cols, pitch, box_rows, box_cols, swizzle_bytes | (elem_bytes << 16)};
   {
     std::lock_guard<std::mutex> lk(g_tmap_mu);
     auto it = g_tmap_cache.find(key);
@@ -111,14 +118,15 @@ int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t co
   EncodeFn encode = get_encode_fn();
   if (encode == nullptr) return fail(ECADK_EDRIVER, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {pitch * 2};
+  cuuint64_t gstride[1] = {pitch * elem_bytes};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                           : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                           : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
                                                 : CU_TENSOR_MAP_SWIZZLE_NONE;
-  CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+  CUresult r = encode(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                      const_cast<void*>(ptr), gdim, gstride, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -213,10 +221,15 @@ void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cuda
 // ---------------------------------------------------------------------------------------------------
 // GEMM launcher
 // ---------------------------------------------------------------------------------------------------
+// tensor maps of the gated-residual epilogue's bulk stores (dummies for the other epilogues)
+struct EpiMaps {
+  CUtensorMap x, cache, xb;
+};
+
 template <int BN, int EPI>
-int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const GemmParams& p,
-                     cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const EpiMaps& em,
+                     const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, EPI>;
   static bool configured = false;
   auto kern = gemm_bf16_kernel<BN, EPI>;
   if (!configured) {
@@ -225,14 +238,14 @@ int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtens
   }
   const int tiles = ((p.M + kGemmBM - 1) / kGemmBM) * (p.N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  launch_pdl(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, ta, ta2, tb, p);
+  launch_pdl(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, ta, ta2, tb, em.x, em.cache, em.xb, p);
   return check_launch("gemm_bf16_kernel");
 }
 
 template <int BN, int EPI>
 int launch_gemm2_inst(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const CUtensorMap& tb_tail,
-                      const GemmParams& p, int tail, cudaStream_t stream) {
-  using Cfg = Gemm2Cfg<BN>;
+                      const EpiMaps& em, const GemmParams& p, int tail, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BN, EPI>;
   static bool configured = false;
   auto kern = gemm2_bf16_kernel<BN, EPI>;
   if (!configured) {
@@ -242,7 +255,8 @@ int launch_gemm2_inst(const CUtensorMap& ta, const CUtensorMap& ta2, const CUten
   const int tiles = ((p.M + 2 * kGemmBM - 1) / (2 * kGemmBM)) * ((p.N - tail) / BN + (tail ? 1 : 0));
   const int pairs = num_sms() / 2;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
-  launch_pdl(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, ta, ta2, tb, tb_tail, p, tail);
+  launch_pdl(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, ta, ta2, tb, tb_tail, em.x, em.cache, em.xb, p,
+             tail);
   return check_launch("gemm2_bf16_kernel");
 }
 
@@ -287,6 +301,18 @@ int launch_gemm(const void* a, const void* w, GemmParams& p, cudaStream_t stream
   ProfScope prof(ECADK_PROF_GEMM, 2.0 * p.M * p.N * p.K, 0.0, stream);
   CUtensorMap ta, ta2, tb;
   int rc;
+  EpiMaps em;
+  memset(&em, 0, sizeof(em));
+  if constexpr (EPI == EPI_GATED_RESIDUAL && ECADK_EPI_TMA_STORE) {
+    // bulk-store maps of one 32 x 32 chunk: fp32 residual stream (128-byte rows, 128B swizzle), bf16 cache / shadow
+    // (64-byte rows, 64B swizzle)
+    ECADK_REQUIRE(p.x != nullptr && aligned16(p.x), "gemm: residual stream must be 16-byte aligned");
+    if ((rc = make_tmap(&em.x, p.x, p.M, p.N, p.N, 32, 32, 128, 4))) return rc;
+    em.cache = em.x;
+    em.xb = em.x;
+    if (p.cache != nullptr && (rc = make_tmap(&em.cache, p.cache, p.M, p.N, p.N, 32, 32, 64, 2))) return rc;
+    if (p.xb != nullptr && (rc = make_tmap(&em.xb, p.xb, p.M, p.N, p.N, 32, 32, 64, 2))) return rc;
+  }
   if (p.a2 != nullptr) {  // A = [a (k1 columns) | a2 (K - k1 columns)], each with its own row pitch
     ECADK_REQUIRE(p.k1 > 0 && p.k1 < p.K && p.k1 % kGemmBK == 0 && aligned16(p.a2),
                   "gemm: split A needs 0 < k1=%d < K=%d, a multiple of %d", p.k1, p.K, kGemmBK);
@@ -309,24 +335,24 @@ int launch_gemm(const void* a, const void* w, GemmParams& p, cudaStream_t stream
       CUtensorMap tb_tail;
       if ((rc = make_tmap_bf16(&tb, w, p.N, p.K, p.K, 128, kGemmBK, 128))) return rc;
       if ((rc = make_tmap_bf16(&tb_tail, w, p.N, p.K, p.K, 64, kGemmBK, 128))) return rc;
-      return launch_gemm2_inst<256, EPI>(ta, ta2, tb, tb_tail, p, 128, stream);
+      return launch_gemm2_inst<256, EPI>(ta, ta2, tb, tb_tail, em, p, 128, stream);
     }
     const int bn = pick_bn((p.M + 2 * kGemmBM - 1) / (2 * kGemmBM), p.N, num_sms() / 2);
     ECADK_REQUIRE(bn != 0, "gemm: no tile width divides N=%d", p.N);
     if ((rc = make_tmap_bf16(&tb, w, p.N, p.K, p.K, bn / 2, kGemmBK, 128))) return rc;
     switch (bn) {
-      case 256: return launch_gemm2_inst<256, EPI>(ta, ta2, tb, tb, p, 0, stream);
-      case 192: return launch_gemm2_inst<192, EPI>(ta, ta2, tb, tb, p, 0, stream);
-      default: return launch_gemm2_inst<128, EPI>(ta, ta2, tb, tb, p, 0, stream);
+      case 256: return launch_gemm2_inst<256, EPI>(ta, ta2, tb, tb, em, p, 0, stream);
+      case 192: return launch_gemm2_inst<192, EPI>(ta, ta2, tb, tb, em, p, 0, stream);
+      default: return launch_gemm2_inst<128, EPI>(ta, ta2, tb, tb, em, p, 0, stream);
     }
   }
   const int bn = pick_bn((p.M + kGemmBM - 1) / kGemmBM, p.N, num_sms());
   ECADK_REQUIRE(bn != 0, "gemm: no tile width divides N=%d", p.N);
   if ((rc = make_tmap_bf16(&tb, w, p.N, p.K, p.K, bn, kGemmBK, 128))) return rc;
   switch (bn) {
-    case 256: return launch_gemm_inst<256, EPI>(ta, ta2, tb, p, stream);
-    case 192: return launch_gemm_inst<192, EPI>(ta, ta2, tb, p, stream);
-    default: return launch_gemm_inst<128, EPI>(ta, ta2, tb, p, stream);
+    case 256: return launch_gemm_inst<256, EPI>(ta, ta2, tb, em, p, stream);
+    case 192: return launch_gemm_inst<192, EPI>(ta, ta2, tb, em, p, stream);
+    default: return launch_gemm_inst<128, EPI>(ta, ta2, tb, em, p, stream);
   }
 }
 

@@ -57,8 +57,9 @@ struct GemmParams {
   int unp_wp, unp_hp, unp_c, unp_cols;
 };
 
-#ifndef ECADK_EPI_X_L2_PREFETCH
-#define ECADK_EPI_X_L2_PREFETCH 1  // gated-residual epilogue: pull the NEXT tile's residual-stream rows into L2 early
+// timing experiments only (results are wrong): -DECADK_EPI_DBG=1 no residual-stream loads, 2 no stores, 3 neither
+#ifndef ECADK_EPI_DBG
+#define ECADK_EPI_DBG 0
 #endif
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;
@@ -66,16 +67,33 @@ constexpr int kGemmThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilog
 constexpr int kEpiWarps = 8;
 constexpr int kEpiPitch = 36;                           // floats; see epilogue_chunk
 constexpr int kEpiStageBytes = kEpiWarps * 32 * kEpiPitch * 4;  // one 32x32 fp32 transpose tile per epilogue warp
+// Gated-residual epilogue with TMA stores: per warp one 128B-swizzled fp32 tile (transpose tile AND staging of the updated
+// residual chunk) + two 64B-swizzled bf16 tiles (cache, bf16 shadow) = 8 KB
+#ifndef ECADK_EPI_TMA_STORE
+#define ECADK_EPI_TMA_STORE 1
+#endif
+constexpr int kEpiTmaWarpBytes = 8192;
+constexpr int kEpiTmaStageBytes = kEpiWarps * kEpiTmaWarpBytes;
+constexpr int kSmemLimit = 227 * 1024;
+__host__ __device__ constexpr int epi_stage_bytes(int epi) {
+  return (epi == 2 /*EPI_GATED_RESIDUAL*/ && ECADK_EPI_TMA_STORE) ? kEpiTmaStageBytes : kEpiStageBytes;
+}
+__host__ __device__ constexpr int fit_stages(int want, int stage_bytes, int epi) {
+  const int room = (kSmemLimit - epi_stage_bytes(epi) - 1024 - 256) / stage_bytes;
+  return want < room ? want : room;
+}
 
-template <int BN>
+template <int BN, int EPI = 0>
 struct GemmCfg {
   static constexpr int kStageA = kGemmBM * kGemmBK * 2;  // 16 KB
   static constexpr int kStageB = BN * kGemmBK * 2;
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = (BN <= 128) ? 5 : (BN <= 192 ? 4 : 3);
+  static constexpr int kEpiBytes = epi_stage_bytes(EPI);
+  static constexpr int kStages = fit_stages((BN <= 128) ? 5 : (BN <= 192 ? 4 : 3), kStage, EPI);
   static constexpr int kAccStride = 256;  // TMEM column offset between the two accumulators
   static constexpr int kTmemCols = 512;
-  static constexpr int kSmemBytes = kStages * kStage + kEpiStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStage + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(kStages >= 3, "GEMM pipeline depth");
 };
 
 
@@ -112,22 +130,22 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
   // chunk (ncu source page, round 1: 52 % of the kernel's stall samples were long-scoreboard waits, the top one the
   // FADD that combines the two gate loads).
   struct Vecs {
-    float4 b4, g4;
+    float4 b4, g4, t4;
   };
   auto load_vecs = [&](int c, Vecs& v) {
     const int col = n0 + c * 32 + cg * 4;
     v.b4 = make_float4(0.f, 0.f, 0.f, 0.f);
     v.g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+    v.t4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.bias != nullptr) v.b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
     if constexpr (EPI == EPI_GATED_RESIDUAL) {
       if (p.gate_table != nullptr || p.gate_temb != nullptr) {
-        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.gate_table != nullptr) g = __ldg(reinterpret_cast<const float4*>(p.gate_table + col));
-        if (p.gate_temb != nullptr) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(p.gate_temb + static_cast<size_t>(sample0) * p.temb_stride + col));
-          g = make_float4(g.x + b.x, g.y + b.y, g.z + b.z, g.w + b.w);
-        }
-        v.g4 = g;
+        // the two halves of the gate are summed in process(): an FADD here would wait for both loads on the spot
+        v.g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        v.t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.gate_table != nullptr) v.g4 = __ldg(reinterpret_cast<const float4*>(p.gate_table + col));
+        if (p.gate_temb != nullptr)
+          v.t4 = __ldg(reinterpret_cast<const float4*>(p.gate_temb + static_cast<size_t>(sample0) * p.temb_stride + col));
       }
     }
   };
@@ -136,13 +154,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int row = row_base + i * 4 + rs;
-      dst[i] = row < p.M ? *reinterpret_cast<const float4*>(p.x + static_cast<size_t>(row) * p.N + col)
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
+      dst[i] = (row < p.M && !(ECADK_EPI_DBG & 1)) ? *reinterpret_cast<const float4*>(p.x + static_cast<size_t>(row) * p.N + col)
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
   auto process = [&](const int c, const float4 (&xin)[8], const Vecs& vec, const uint32_t (&v)[32]) {
     const int col = n0 + c * 32 + cg * 4;
-    const float4 b4 = vec.b4, g4 = vec.g4;
+    const float4 b4 = vec.b4;
+    const float4 g4 = make_float4(vec.g4.x + vec.t4.x, vec.g4.y + vec.t4.y, vec.g4.z + vec.t4.z, vec.g4.w + vec.t4.w);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       sts_u4(stage_s + (lane * kEpiPitch + 4 * j) * 4, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -185,6 +204,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
           *reinterpret_cast<uint2*>(p.out2 + static_cast<size_t>(row) * p.ldo2 + col) = w;
         } else if constexpr (EPI == EPI_GATED_RESIDUAL) {
           const size_t off = static_cast<size_t>(row) * p.N + col;
+          if ((ECADK_EPI_DBG & 2) && o.x != 12345.678f) continue;
           if (p.cache != nullptr) {  // null: the caller knows this slot is overwritten before anyone reads it
             uint2 cv;
             cv.x = pack_bf16x2(o.x, o.y);
@@ -293,16 +313,134 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
   }
 }
 
+// Gated-residual epilogue, TMA-store form (round 2).
+//
+// tools/micro/epi2_sensitivity.py (out-projection, M = 51200, N = K = 1152) showed where the old epilogue's time went:
+// MMA + operands alone 95 us; + the residual-stream reads 118 us; + the 472 MB of per-thread stores 148 us; both 195 us -
+// the side traffic added to the MMA time instead of hiding under it, and the stores were the larger part: 3072 row-
+// strided STG transactions per tile (a warp store touches 4 rows) drained at ~21 GB/s per SM.  Here every 32 x 32
+// chunk leaves through shared memory as THREE bulk tensor stores (updated fp32 residual, bf16 cache, bf16 shadow):
+//
+//   * the fp32 tile is the transpose tile itself: the accumulator chunk is written row-per-thread into a 128B-swizzled
+//     [32 x 128 B] tile (conflict-free both ways - the XOR swizzle replaces the pitch-36 padding), read back in the
+//     coalesced (row group, 4-column) layout, combined with the prefetched residual registers, and written back IN PLACE
+//     (each element is read and rewritten by the same lane);
+//   * the bf16 tiles are [32 x 64 B] with the 64B swizzle; one lane issues cp.async.bulk.tensor stores with matching
+//     tensor maps; the staging is reused by the next chunk once `cp.async.bulk.wait_group.read` says it has been read.
+__device__ __forceinline__ void epilogue_tile_residual_tma(const GemmParams& p, const CUtensorMap* tm_x,
+                                                           const CUtensorMap* tm_cache, const CUtensorMap* tm_xb,
+                                                           const uint32_t t_row, uint8_t* stage, const int lane,
+                                                           const int parity, const int row_base, const int n0,
+                                                           const int n_chunks) {
+  const int cg = lane & 7, rs = lane >> 3;
+  const uint32_t tile_x = smem_u32(stage);           // fp32 [32 rows x 128 B], SWIZZLE_128B
+  const uint32_t tile_c = tile_x + 4096;              // bf16 [32 rows x 64 B], SWIZZLE_64B: un-gated output (cache)
+  const uint32_t tile_b = tile_x + 6144;              // bf16 shadow of the updated stream
+  const int sample0 = row_base / p.tokens;            // tokens % 32 == 0: one sample per 32-row chunk
+  struct Vecs {
+    float4 b4, g4, t4;
+  };
+  auto load_vecs = [&](int c, Vecs& v) {
+    const int col = n0 + c * 32 + cg * 4;
+    v.b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    v.g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+    v.t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias != nullptr) v.b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+    if (p.gate_table != nullptr || p.gate_temb != nullptr) {
+      v.g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.gate_table != nullptr) v.g4 = __ldg(reinterpret_cast<const float4*>(p.gate_table + col));
+      if (p.gate_temb != nullptr)
+        v.t4 = __ldg(reinterpret_cast<const float4*>(p.gate_temb + static_cast<size_t>(sample0) * p.temb_stride + col));
+    }
+  };
+  auto load_x = [&](int c, float4 (&dst)[8]) {
+    const int col = n0 + c * 32 + cg * 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = row_base + i * 4 + rs;
+      dst[i] = row < p.M ? *reinterpret_cast<const float4*>(p.x + static_cast<size_t>(row) * p.N + col)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto process = [&](const int c, const float4 (&xin)[8], const Vecs& vec) {
+    uint32_t v[32];
+    tmem_ld_32x32(t_row + c * 32, v);
+    const float4 b4 = vec.b4;
+    const float4 g4 = make_float4(vec.g4.x + vec.t4.x, vec.g4.y + vec.t4.y, vec.g4.z + vec.t4.z, vec.g4.w + vec.t4.w);
+    // the previous chunk's bulk stores must have read the staging tiles before they are overwritten
+    if (lane == 0) tma_store_wait_read0();
+    __syncwarp();
+    tmem_ld_wait();
+    // row-per-thread -> 128B-swizzled tile: 16-byte piece j of row `lane` lives at piece (j ^ (lane & 7))
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      sts_u4(tile_x + lane * 128 + ((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 4 + rs;
+      const uint32_t ax = tile_x + r * 128 + ((cg ^ (r & 7)) << 4);
+      float4 o = lds_f4(ax);
+      o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+      // bf16 tiles: 8-byte half (cg & 1) of 16-byte piece (cg >> 1), 64B swizzle = piece ^ ((r >> 1) & 3)
+      const uint32_t ob = r * 64 + ((((cg >> 1) ^ ((r >> 1) & 3)) << 4) | ((cg & 1) << 3));
+      if (p.cache != nullptr) sts_u2(tile_c + ob, pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+      float4 x = xin[i];
+      x.x = fmaf(g4.x, o.x, x.x); x.y = fmaf(g4.y, o.y, x.y);
+      x.z = fmaf(g4.z, o.z, x.z); x.w = fmaf(g4.w, o.w, x.w);
+      sts_u4(ax, __float_as_uint(x.x), __float_as_uint(x.y), __float_as_uint(x.z), __float_as_uint(x.w));
+      if (p.xb != nullptr) sts_u2(tile_b + ob, pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+    }
+    fence_proxy_async_smem();  // generic-proxy tile writes -> visible to the bulk stores (async proxy)
+    __syncwarp();
+    if (lane == 0) {
+      const int col0 = n0 + c * 32;
+      tma_store_2d(tm_x, stage, col0, row_base);  // rows past M are clipped by the tensor map
+      if (p.cache != nullptr) tma_store_2d(tm_cache, stage + 4096, col0, row_base);
+      if (p.xb != nullptr) tma_store_2d(tm_xb, stage + 6144, col0, row_base);
+      tma_store_commit();
+    }
+  };
+  const int half_chunks = (n_chunks + 1) / 2;
+  const int c_begin = parity * half_chunks;
+  const int c_end = min(n_chunks, c_begin + half_chunks);
+  float4 xa[8], xb_[8];
+  Vecs va, vb;
+  if (c_begin < c_end) {
+    load_vecs(c_begin, va);
+    load_x(c_begin, xa);
+  }
+#pragma unroll 1
+  for (int c = c_begin; c < c_end; c += 2) {
+    const bool more = c + 1 < c_end;
+    if (more) {
+      load_vecs(c + 1, vb);
+      load_x(c + 1, xb_);
+    }
+    process(c, xa, va);
+    if (more) {
+      if (c + 2 < c_end) {
+        load_vecs(c + 2, va);
+        load_x(c + 2, xa);
+      }
+      process(c + 1, xb_, vb);
+    }
+  }
+}
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
-                 const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+                 const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_x,
+                 const __grid_constant__ CUtensorMap tmap_cache, const __grid_constant__ CUtensorMap tmap_xb,
+                 const GemmParams p) {
+  using Cfg = GemmCfg<BN, EPI>;
+  constexpr bool kTmaEpi = EPI == EPI_GATED_RESIDUAL && ECADK_EPI_TMA_STORE;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* epi_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::kStage);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStage + kEpiStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStage + Cfg::kEpiBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -417,8 +555,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tc_fence_after();
       const int row_base = m0 + quarter * 32;
       const uint32_t t_row = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(quarter * 32) << 16);
-      float* stage = epi_stage + (warp - 2) * 32 * kEpiPitch;
-      epilogue_tile<EPI>(p, t_row, stage, lane, (warp - 2) >> 2, row_base, n0, BN / 32);
+      if constexpr (kTmaEpi) {
+        epilogue_tile_residual_tma(p, &tmap_x, &tmap_cache, &tmap_xb, t_row,
+                                   reinterpret_cast<uint8_t*>(epi_stage) + (warp - 2) * kEpiTmaWarpBytes, lane,
+                                   (warp - 2) >> 2, row_base, n0, BN / 32);
+      } else {
+        float* stage = epi_stage + (warp - 2) * 32 * kEpiPitch;
+        epilogue_tile<EPI>(p, t_row, stage, lane, (warp - 2) >> 2, row_base, n0, BN / 32);
+      }
       // accumulator drained: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -427,6 +571,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         acc = 0;
         acc_phase ^= 1;
       }
+    }
+    if constexpr (kTmaEpi) {
+      if (lane == 0) tma_store_wait_all0();  // this lane's bulk stores have landed before the CTA exits
     }
   }
 
@@ -445,30 +592,34 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 // pair; tcgen05.commit multicasts the "slot free" / "accumulator ready" arrivals to both CTAs; every CTA's epilogue
 // warps drain their own 128 TMEM lanes.
 // =====================================================================================================
-template <int BN>
+template <int BN, int EPI = 0>
 struct Gemm2Cfg {
   static constexpr int kStageA = kGemmBM * kGemmBK * 2;        // this CTA's 128 rows of A: 16 KB
   static constexpr int kStageB = (BN / 2) * kGemmBK * 2;       // this CTA's half of W
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = (BN <= 128) ? 7 : (BN <= 192 ? 6 : 5);
+  static constexpr int kEpiBytes = epi_stage_bytes(EPI);
+  static constexpr int kStages = fit_stages((BN <= 128) ? 7 : (BN <= 192 ? 6 : 5), kStage, EPI);
   static constexpr int kAccStride = 256;
   static constexpr int kTmemCols = 512;
-  static constexpr int kSmemBytes = kStages * kStage + kEpiStageBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * kStage + kEpiBytes + 1024 + 256;
+  static_assert(kStages >= 4, "GEMM pipeline depth");
 };
 
 template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
                   const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_b_tail,
-                  const GemmParams p, const int tail) {
+                  const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_cache,
+                  const __grid_constant__ CUtensorMap tmap_xb, const GemmParams p, const int tail) {
   // `tail` (0 or 128, only with BN = 256): N = k*256 + 128 is covered by k full-width tiles plus one 128-wide tile per
   // row block, so N = 1152 / 3456 run at the L2->SM traffic per FLOP of 256-wide tiles instead of 192-wide ones.
-  using Cfg = Gemm2Cfg<BN>;
+  using Cfg = Gemm2Cfg<BN, EPI>;
+  constexpr bool kTmaEpi = EPI == EPI_GATED_RESIDUAL && ECADK_EPI_TMA_STORE;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* epi_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::kStage);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStage + kEpiStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStage + Cfg::kEpiBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -594,29 +745,21 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int n_idx = tile % num_n;
       const int n0 = n_idx * BN;
       const int n_chunks = (n_idx >= num_n_full ? tail : BN) / 32;
-      if constexpr (EPI == EPI_GATED_RESIDUAL && ECADK_EPI_X_L2_PREFETCH) {
-        // The epilogue of this kernel is bound by the latency of its residual-stream reads (one 4 KB chunk per warp in
-        // flight: tools/micro/epi2_sensitivity.py shows the side traffic ADDS to the MMA time instead of hiding under
-        // it).  While this tile's MMAs finish, every lane asks L2 for the row piece its warp will read in the NEXT
-        // tile - one 512-byte request per lane, no registers, no shared memory - so those reads become L2 hits.
-        const int nt = tile + num_pairs;
-        if (nt < num_tiles) {
-          const int nn = nt % num_n;
-          const int chunks = (nn >= num_n_full ? tail : BN) / 32;
-          const int half_chunks = (chunks + 1) / 2;
-          const int c0 = ((warp - 2) >> 2) * half_chunks;
-          const int cols = (min(chunks, c0 + half_chunks) - c0) * 32;
-          const int row = (nt / num_n) * (2 * kGemmBM) + cta * kGemmBM + quarter * 32 + lane;
-          if (cols > 0 && row < p.M)
-            prefetch_l2_bulk(p.x + static_cast<size_t>(row) * p.N + nn * BN + c0 * 32, cols * 4);
-        }
-      }
+      // (measured and rejected, round 2: an L2 prefetch of the row pieces this warp reads in the NEXT tile, one 512-byte
+      // cp.async.bulk.prefetch.L2 per lane issued here - out-projection 196 -> 200 us and DRAM reads 363 -> 500 MB under
+      // ncu: the residual-stream reads are not what the epilogue waits for)
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int row_base = m0 + quarter * 32;
       const uint32_t t_row = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(quarter * 32) << 16);
-      float* stage = epi_stage + (warp - 2) * 32 * kEpiPitch;
-      epilogue_tile<EPI>(p, t_row, stage, lane, (warp - 2) >> 2, row_base, n0, n_chunks);
+      if constexpr (kTmaEpi) {
+        epilogue_tile_residual_tma(p, &tmap_x, &tmap_cache, &tmap_xb, t_row,
+                                   reinterpret_cast<uint8_t*>(epi_stage) + (warp - 2) * kEpiTmaWarpBytes, lane,
+                                   (warp - 2) >> 2, row_base, n0, n_chunks);
+      } else {
+        float* stage = epi_stage + (warp - 2) * 32 * kEpiPitch;
+        epilogue_tile<EPI>(p, t_row, stage, lane, (warp - 2) >> 2, row_base, n0, n_chunks);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);  // the leader's barrier collects both CTAs
@@ -624,6 +767,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         acc = 0;
         acc_phase ^= 1;
       }
+    }
+    if constexpr (kTmaEpi) {
+      if (lane == 0) tma_store_wait_all0();
     }
   }
 

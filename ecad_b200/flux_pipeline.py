@@ -179,7 +179,11 @@ class B200FluxPipeline:
             latents = self._graphs.run(
                 key, inputs, lambda st, cb: self._denoise(st, text_ids, img_ids, cb),
                 capture_callback if capture_callback is not None else callback_on_step_end, tr)
-            self._graph_epoch = getattr(tr, "buffer_epoch", 0)  # buffers created by the run's own eager warm-up
+            if getattr(tr, "buffer_epoch", 0) != self._graph_epoch:
+                # the run's own eager warm-up re-allocated the workspace / per-timestep tables: the graph just recorded
+                # points into the new buffers, every OLDER graph into freed memory
+                self._graphs.keep_only(key)
+                self._graph_epoch = getattr(tr, "buffer_epoch", 0)
             if callback_on_step_end is not None:
                 for i, t in enumerate(sched.timesteps):
                     out = callback_on_step_end(self, i, t, {"latents": latents, "prompt_embeds": prompt_embeds})

@@ -25,6 +25,11 @@ class GenerationGraphs:
     def clear(self) -> None:
         self._entries.clear()
 
+    def keep_only(self, key: Any) -> None:
+        """Drop every recorded graph except ``key`` (the buffers the others point into have just been re-allocated)."""
+        for k in [k for k in self._entries if k != key]:
+            del self._entries[k]
+
     def run(self, key: Any, inputs: dict[str, Any], body: Callable[[dict[str, Any], Any], torch.Tensor],
             capture_callback, transformer) -> torch.Tensor:
         """``body(static_inputs, callback)`` runs the denoising loop in place on ``static_inputs["latents"]`` and

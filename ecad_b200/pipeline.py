@@ -244,7 +244,11 @@ class B200PixArtPipeline:
             latents = self._graphs.run(
                 key, inputs, lambda st, cb: self._denoise(st, batch_size, do_cfg, guidance_scale, height, width, cb, 1),
                 capture_callback if capture_callback is not None else callback, tr)
-            self._graph_epoch = getattr(tr, "buffer_epoch", 0)  # buffers created by the run's own eager warm-up
+            if getattr(tr, "buffer_epoch", 0) != self._graph_epoch:
+                # the run's own eager warm-up re-allocated the workspace / per-timestep tables: the graph just recorded
+                # points into the new buffers, every OLDER graph into freed memory
+                self._graphs.keep_only(key)
+                self._graph_epoch = getattr(tr, "buffer_epoch", 0)
             if callback is not None:  # user-visible per-step protocol (counters, extra callbacks, reset LAST)
                 for i, t in enumerate(sched.timesteps):
                     if i % callback_steps == 0:

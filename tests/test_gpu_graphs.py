@@ -251,5 +251,6 @@ def test_generate_from_saved_prompts_and_module_shell(cuda_device, tmp_path):
               return_dict=False)
     o1 = tr(x, **kw)[0]
     keep = o1.clone()
+    tr.reset_cache()  # the step counter did not advance: start the second forward from empty caches too
     o2 = tr(x * 0.5, **kw)[0]
     assert o1.data_ptr() != o2.data_ptr() and torch.equal(o1, keep)
