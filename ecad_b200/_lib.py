@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = [
     "ecadk_gemm_bias_gated_residual_cache",
     "ecadk_gemm_bias_headmajor",
     "ecadk_attention",
+    "ecadk_attention_ex",
     "ecadk_attention_d128",
     "ecadk_qk_norm_rope",
     "ecadk_qk_norm_rope_batched",
@@ -119,6 +120,7 @@ class EcadkBlocksArgs(C.Structure):
         ("v2", C.POINTER(C.c_void_p)),
         ("cache", C.POINTER(C.c_void_p)),
         ("cache_dead", C.POINTER(C.c_uint8)),
+        ("qkv", C.c_void_p),
     ]
 
 
@@ -196,6 +198,7 @@ def load() -> C.CDLL:
         "ecadk_gemm_bias_gated_residual_cache": [p, p, p, p, p, p, p, p, i, i, i, i, i, p],
         "ecadk_gemm_bias_headmajor": [p, p, p, p, p, p, i, i, i, i, i, i, p],
         "ecadk_attention": [p, p, p, p, p, i, i, i, i, p],
+        "ecadk_attention_ex": [p, i, p, p, i, p, p, i, i, i, i, p],
         "ecadk_attention_d128": [p, p, p, p, i, p, i, i, i, i, i, p],
         "ecadk_qk_norm_rope": [p, p, p, p, p, p, p, p, i, i, i, i, f, p],
         "ecadk_qk_norm_rope_batched": [p, p, p, p, p, p, p, p, i, i, i, i, i, f, p],
@@ -277,6 +280,13 @@ def gemm_headmajor(a, w, bias, outs, heads, tokens, tokens_pad):
 def attention(q, k, v, bias, out, samples, heads, q_tokens, n_keys):
     check(load().ecadk_attention(ptr(q), ptr(k), ptr(v), ptr(bias), ptr(out), samples, heads, q_tokens, n_keys,
                                  stream_ptr()), "attention")
+    return out
+
+
+def attention_ex(q, q_ld, k, v, kv_ld, bias, out, samples, heads, q_tokens, n_keys):
+    """q_ld / kv_ld = 0: head-major operands; > 0: row-major [samples*tokens, ld] (see ecadk_attention_ex)."""
+    check(load().ecadk_attention_ex(ptr(q), q_ld, ptr(k), ptr(v), kv_ld, ptr(bias), ptr(out), samples, heads, q_tokens,
+                                    n_keys, stream_ptr()), "attention_ex")
     return out
 
 

@@ -33,6 +33,12 @@ struct AttnParams {
   // out_lo [samples, split_tokens, out_ld], the others to out [samples, q_tokens - split_tokens, out_ld]
   __nv_bfloat16* out_lo;
   int split_tokens;
+  // Operand layout seen through the (3-D) tensor maps: 0 = head-major [sample*heads + head][token][80] (the middle
+  // coordinate is always 0), 1 = ROW-major [sample*tokens + token][head][72] - the plain output of the projection GEMM,
+  // head = middle coordinate; the 8 padding columns of the 80-wide shared-memory tiles are the tensor map's
+  // out-of-bounds zero fill.  attn_pair2_kernel / attn_flash_kernel<72> only.
+  int q_rowmajor;
+  int kv_rowmajor;
 };
 
 // Phase timing of the flash kernel (instrumented builds only: -DECADK_ATTN_TIMING; tools/micro/attn_phase_timing.py)
@@ -826,27 +832,29 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++n) {
         const int b = n & 1;
         const uint32_t ph2 = ((n >> 1) & 1) ^ 1;  // "slot is free" parity of the per-buffer barriers
-        const int q_row = item * 256;
-        const int k_row = item * NK;
+        const int sample = item / p.heads, hd = item - sample * p.heads;
+        const int q_mid = p.q_rowmajor ? hd : 0, kv_mid = p.kv_rowmajor ? hd : 0;
+        const int q_row = (p.q_rowmajor ? sample : item) * 256;
+        const int k_row = (p.kv_rowmajor ? sample : item) * NK;
         mbar_wait(&k_empty[b], ph2);
         uint8_t* kd = smem + Cfg::kK + b * Cfg::kKBuf;
         mbar_arrive_expect_tx(&k_full[b], Cfg::kBytesKV);
-        tma_load_2d(kd, &tm_k64, &k_full[b], 0, k_row);
-        tma_load_2d(kd + NK * 128, &tm_k16, &k_full[b], 64, k_row);
+        tma_load_3d(kd, &tm_k64, &k_full[b], 0, kv_mid, k_row);
+        tma_load_3d(kd + NK * 128, &tm_k16, &k_full[b], 64, kv_mid, k_row);
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           mbar_wait(&q_empty[t], (n & 1) ^ 1);
           uint8_t* qd = smem + Cfg::kQ + t * Cfg::kQTile;
           mbar_arrive_expect_tx(&q_full[t], Cfg::kBytesQ);
-          tma_load_2d(qd, &tm_q64, &q_full[t], 0, q_row + t * kAttnBM);
-          tma_load_2d(qd + kAttnBM * 128, &tm_q16, &q_full[t], 64, q_row + t * kAttnBM);
+          tma_load_3d(qd, &tm_q64, &q_full[t], 0, q_mid, q_row + t * kAttnBM);
+          tma_load_3d(qd + kAttnBM * 128, &tm_q16, &q_full[t], 64, q_mid, q_row + t * kAttnBM);
         }
         mbar_wait(&v_empty[b], ph2);
         uint8_t* vd = smem + Cfg::kV + b * Cfg::kVBuf;
         mbar_arrive_expect_tx(&v_full[b], Cfg::kBytesKV);
         // V lands as FIVE 16-column (32-byte-swizzled) atoms: the 80-column head is one MN-major operand (N = 80)
 #pragma unroll
-        for (int a = 0; a < kHeadPad / 16; ++a) tma_load_2d(vd + a * (NK * 32), &tm_v16, &v_full[b], a * 16, k_row);
+        for (int a = 0; a < kHeadPad / 16; ++a) tma_load_3d(vd + a * (NK * 32), &tm_v16, &v_full[b], a * 16, kv_mid, k_row);
       }
     }
     __syncwarp();
@@ -1234,30 +1242,32 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
       int n = 0, nb = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++n) {
         const int sh = item / pairs, pr = item - sh * pairs;
-        const int q_row = sh * p.q_tokens + pr * 256;
+        const int smp = sh / p.heads, hd = sh - smp * p.heads;
+        const int q_mid = p.q_rowmajor ? hd : 0, kv_mid = p.kv_rowmajor ? hd : 0;
+        const int q_row = (p.q_rowmajor ? smp : sh) * p.q_tokens + pr * 256;
         mbar_wait(q_empty, (n & 1) ^ 1);
         mbar_arrive_expect_tx(q_full, Cfg::kBytesQ);
-        tma_load_2d(smem + Cfg::kQ64, &tm_q64, q_full, 0, q_row);
-        tma_load_2d(smem + Cfg::kQ2, &tm_q16, q_full, 64, q_row);
+        tma_load_3d(smem + Cfg::kQ64, &tm_q64, q_full, 0, q_mid, q_row);
+        tma_load_3d(smem + Cfg::kQ2, &tm_q16, q_full, 64, q_mid, q_row);
         for (int j = 0; j < nkb; ++j, ++nb) {
           const int st = nb & 1;
           const uint32_t ph = ((nb >> 1) & 1) ^ 1;
-          const int k_row = sh * n_keys + j * kFlashKB;
+          const int k_row = (p.kv_rowmajor ? smp : sh) * n_keys + j * kFlashKB;
           uint8_t* kd = smem + Cfg::kK + st * Cfg::kKStage;
           uint8_t* vd = smem + Cfg::kV + st * Cfg::kKStage;
           mbar_wait(&k_empty[st], ph);
           mbar_arrive_expect_tx(&k_full[st], Cfg::kBytesKV);
-          tma_load_2d(kd, &tm_k64, &k_full[st], 0, k_row);
-          tma_load_2d(kd + kFlashKB * 128, &tm_k16, &k_full[st], 64, k_row);
+          tma_load_3d(kd, &tm_k64, &k_full[st], 0, kv_mid, k_row);
+          tma_load_3d(kd + kFlashKB * 128, &tm_k16, &k_full[st], 64, kv_mid, k_row);
           mbar_wait(&v_empty[st], ph);
           mbar_arrive_expect_tx(&v_full[st], Cfg::kBytesKV);
           if constexpr (HD == 128) {
-            tma_load_2d(vd, &tm_v64, &v_full[st], 0, k_row);
-            tma_load_2d(vd + kFlashKB * 128, &tm_v16, &v_full[st], 64, k_row);
+            tma_load_3d(vd, &tm_v64, &v_full[st], 0, kv_mid, k_row);
+            tma_load_3d(vd + kFlashKB * 128, &tm_v16, &v_full[st], 64, kv_mid, k_row);
           } else {  // five 16-column SW32 atoms: the 80-column head is one MN-major operand (see attn_pair_kernel)
 #pragma unroll
             for (int a = 0; a < Cfg::kPad / 16; ++a)
-              tma_load_2d(vd + a * (kFlashKB * 32), &tm_v16, &v_full[st], a * 16, k_row);
+              tma_load_3d(vd + a * (kFlashKB * 32), &tm_v16, &v_full[st], a * 16, kv_mid, k_row);
           }
         }
       }

@@ -140,6 +140,57 @@ int make_tmap(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, u
   return ECADK_OK;
 }
 
+// 3-D bf16 tensor [rows][mids][inner] (inner contiguous) with box [box_rows][1][box_cols]: the attention operands.
+//   head-major  q/k/v [S*H*tokens][80]:              inner = 80, mids = 1
+//   row-major   projection output [S*tokens][ld]:    inner = 72 (the head), mids = heads (144-byte stride), rows = S*tokens
+// A 16-column box at inner offset 64 of a 72-wide head reads 8 real columns and 8 out-of-bounds ones, which TMA fills
+// with zeros - exactly the zero padding the 80-wide shared-memory tiles need.
+int make_tmap3_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t mids, uint64_t rows, uint64_t mid_stride,
+                    uint64_t row_stride, uint32_t box_rows, uint32_t box_cols, uint32_t swizzle_bytes) {
+  TmapKey key{ptr, rows, inner | (mids << 20) | (mid_stride << 32), row_stride, box_rows, box_cols,
+              swizzle_bytes | (3u << 24)};
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) {
+      *out = it->second;
+      return ECADK_OK;
+    }
+  }
+  EncodeFn encode = get_encode_fn();
+  if (encode == nullptr) return fail(ECADK_EDRIVER, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t gdim[3] = {inner, mids, rows};
+  cuuint64_t gstride[2] = {mid_stride * 2, row_stride * 2};
+  cuuint32_t box[3] = {box_cols, 1, box_rows};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    return fail(ECADK_EINVAL, "cuTensorMapEncodeTiled(3d) failed (%d) inner=%llu mids=%llu rows=%llu strides=%llu,%llu box=%ux%u",
+                static_cast<int>(r), (unsigned long long)inner, (unsigned long long)mids, (unsigned long long)rows,
+                (unsigned long long)mid_stride, (unsigned long long)row_stride, box_rows, box_cols);
+  }
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  if (g_tmap_cache.size() > 65536) g_tmap_cache.clear();
+  g_tmap_cache.emplace(key, *out);
+  return ECADK_OK;
+}
+
+// attention operand seen through a 3-D map: ld == 0 -> head-major [S*H*tokens][80]; else row-major [S*tokens][ld]
+int make_attn_tmap(CUtensorMap* out, const void* ptr, int ld, int samples, int heads, int tokens, uint32_t box_rows,
+                   uint32_t box_cols, uint32_t swizzle_bytes) {
+  if (ld == 0)
+    return make_tmap3_bf16(out, ptr, kHeadPad, 1, static_cast<uint64_t>(samples) * heads * tokens, kHeadPad, kHeadPad,
+                           box_rows, box_cols, swizzle_bytes);
+  return make_tmap3_bf16(out, ptr, kHeadDim, heads, static_cast<uint64_t>(samples) * tokens, kHeadDim, ld, box_rows,
+                         box_cols, swizzle_bytes);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // in-situ profiler: CUDA event pairs around every launch while enabled
 // ---------------------------------------------------------------------------------------------------
@@ -446,19 +497,33 @@ int launch_attention_d128(const void* q, const void* k, const void* v, void* out
   p.split_tokens = split_tokens;
   CUtensorMap tq[2], tkv[4];
   int rc;
-  if ((rc = make_tmap_bf16(&tq[0], q, q_rows, 128, 128, 256, 64, 128))) return rc;
+  // the streaming kernel addresses its operands through 3-D maps (see make_tmap3_bf16): head-major, middle extent 1
+  p.q_rowmajor = 0;
+  p.kv_rowmajor = 0;
+  if ((rc = make_tmap3_bf16(&tq[0], q, 128, 1, q_rows, 128, 128, 256, 64, 128))) return rc;
   tq[1] = tq[0];
-  if ((rc = make_tmap_bf16(&tkv[0], k, k_rows, 128, 128, kFlashKB, 64, 128))) return rc;
+  if ((rc = make_tmap3_bf16(&tkv[0], k, 128, 1, k_rows, 128, 128, kFlashKB, 64, 128))) return rc;
   tkv[1] = tkv[0];
-  if ((rc = make_tmap_bf16(&tkv[2], v, k_rows, 128, 128, kFlashKB, 64, 128))) return rc;
+  if ((rc = make_tmap3_bf16(&tkv[2], v, 128, 1, k_rows, 128, 128, kFlashKB, 64, 128))) return rc;
   tkv[3] = tkv[2];
   const int items = samples * heads * (q_tokens / 256);
   return launch_attn_flash_inst<128, false>(tq, tkv, p, n_keys, items, stream);
 }
 
+int launch_attention_ex(const void* q, int q_ld, const void* k, const void* v, int kv_ld, const float* bias, void* out,
+                        int samples, int heads, int q_tokens, int n_keys, cudaStream_t stream);
 int launch_attention(const void* q, const void* k, const void* v, const float* bias, void* out, int samples,
                      int heads, int q_tokens, int n_keys, cudaStream_t stream) {
+  return launch_attention_ex(q, 0, k, v, 0, bias, out, samples, heads, q_tokens, n_keys, stream);
+}
+
+// q_ld / kv_ld: 0 = head-major operand [S, H, tokens, 80]; > 0 = row-major [S*tokens, ld] (the plain output of the
+// projection GEMM; the pointer addresses the first column of head 0 of THIS operand, e.g. qkv + 1152 for K)
+int launch_attention_ex(const void* q, int q_ld, const void* k, const void* v, int kv_ld, const float* bias, void* out,
+                        int samples, int heads, int q_tokens, int n_keys, cudaStream_t stream) {
   ECADK_REQUIRE(q && k && v && out, "attention: null pointer");
+  ECADK_REQUIRE(q_ld == 0 || (q_ld >= heads * kHeadDim && q_ld % 8 == 0), "attention: q_ld=%d", q_ld);
+  ECADK_REQUIRE(kv_ld == 0 || (kv_ld >= heads * kHeadDim && kv_ld % 8 == 0), "attention: kv_ld=%d", kv_ld);
   ECADK_REQUIRE(n_keys > 0 && n_keys % 128 == 0, "attention: n_keys=%d must be a multiple of 128", n_keys);
   ECADK_REQUIRE(q_tokens > 0 && q_tokens % kAttnBM == 0, "attention: q_tokens=%d must be a multiple of 128", q_tokens);
   ECADK_REQUIRE(n_keys <= 256 || q_tokens % 256 == 0,
@@ -482,20 +547,44 @@ int launch_attention(const void* q, const void* k, const void* v, const float* b
   p.out = static_cast<__nv_bfloat16*>(out);
   p.out_lo = nullptr;
   p.split_tokens = 0;
+  p.q_rowmajor = q_ld != 0;
+  p.kv_rowmajor = kv_ld != 0;
   int rc;
   const bool use_flash = (n_keys > 256 || q_tokens > 256 || forced == 2) && q_tokens % 256 == 0;
   if (use_flash) {
     // long key sequences: stream 128-key blocks with an online softmax
     CUtensorMap tq[2], tkv[4];
-    if ((rc = make_tmap_bf16(&tq[0], q, q_rows, kHeadPad, kHeadPad, 256, 64, 128))) return rc;
-    if ((rc = make_tmap_bf16(&tq[1], q, q_rows, kHeadPad, kHeadPad, 256, 16, 32))) return rc;
-    if ((rc = make_tmap_bf16(&tkv[0], k, k_rows, kHeadPad, kHeadPad, kFlashKB, 64, 128))) return rc;
-    if ((rc = make_tmap_bf16(&tkv[1], k, k_rows, kHeadPad, kHeadPad, kFlashKB, 16, 32))) return rc;
-    if ((rc = make_tmap_bf16(&tkv[2], v, k_rows, kHeadPad, kHeadPad, kFlashKB, 64, 128))) return rc;
-    if ((rc = make_tmap_bf16(&tkv[3], v, k_rows, kHeadPad, kHeadPad, kFlashKB, 16, 32))) return rc;
+    if ((rc = make_attn_tmap(&tq[0], q, q_ld, samples, heads, q_tokens, 256, 64, 128))) return rc;
+    if ((rc = make_attn_tmap(&tq[1], q, q_ld, samples, heads, q_tokens, 256, 16, 32))) return rc;
+    if ((rc = make_attn_tmap(&tkv[0], k, kv_ld, samples, heads, n_keys, kFlashKB, 64, 128))) return rc;
+    if ((rc = make_attn_tmap(&tkv[1], k, kv_ld, samples, heads, n_keys, kFlashKB, 16, 32))) return rc;
+    if ((rc = make_attn_tmap(&tkv[2], v, kv_ld, samples, heads, n_keys, kFlashKB, 64, 128))) return rc;
+    if ((rc = make_attn_tmap(&tkv[3], v, kv_ld, samples, heads, n_keys, kFlashKB, 16, 32))) return rc;
     const int items = samples * heads * (q_tokens / 256);
     return bias ? launch_attn_flash_inst<72, true>(tq, tkv, p, n_keys, items, stream)
                 : launch_attn_flash_inst<72, false>(tq, tkv, p, n_keys, items, stream);
+  }
+  const bool pair2 = q_tokens == 256 && forced != 1 && forced != 3 && !(n_keys == 256 && bias != nullptr);
+  ECADK_REQUIRE(pair2 || (q_ld == 0 && kv_ld == 0),
+                "attention: row-major operands need the 256-query or the streaming kernel (q_tokens=%d n_keys=%d)",
+                q_tokens, n_keys);
+  if (pair2) {
+    // second-generation 256-query kernel: per-tile Q slots, per-item K/V double buffering, output through smem + TMA
+    // store (256 keys WITH a key bias - text lengths in (128, 256], no shipped configuration - stays on the first kernel:
+    // the second one has no shared memory left for the bias slices there)
+    CUtensorMap tq1[2], tk[6], to;
+    if ((rc = make_attn_tmap(&tq1[0], q, q_ld, samples, heads, q_tokens, kAttnBM, 64, 128))) return rc;
+    if ((rc = make_attn_tmap(&tq1[1], q, q_ld, samples, heads, q_tokens, kAttnBM, 16, 32))) return rc;
+    if ((rc = make_attn_tmap(&tk[2], k, kv_ld, samples, heads, n_keys, n_keys, 64, 128))) return rc;
+    if ((rc = make_attn_tmap(&tk[3], k, kv_ld, samples, heads, n_keys, n_keys, 16, 32))) return rc;
+    if ((rc = make_attn_tmap(&tk[5], v, kv_ld, samples, heads, n_keys, n_keys, 16, 32))) return rc;
+    if ((rc = make_tmap_bf16(&to, out, static_cast<uint64_t>(samples) * q_tokens, heads * kHeadDim, p.out_ld, kAttnBM,
+                             kHeadDim, 0)))
+      return rc;
+    const int items = samples * heads;
+    if (n_keys == 256) return launch_attn_pair2_inst<256, false>(tq1, tk, to, p, items, stream);
+    return bias ? launch_attn_pair2_inst<128, true>(tq1, tk, to, p, items, stream)
+                : launch_attn_pair2_inst<128, false>(tq1, tk, to, p, items, stream);
   }
   CUtensorMap tm[6];
   if ((rc = make_tmap_bf16(&tm[0], q, q_rows, kHeadPad, kHeadPad, kAttnBM, 64, 128))) return rc;
@@ -509,20 +598,6 @@ int launch_attention(const void* q, const void* k, const void* v, const float* b
     if ((rc = make_tmap_bf16(&tq[0], q, q_rows, kHeadPad, kHeadPad, 256, 64, 128))) return rc;
     if ((rc = make_tmap_bf16(&tq[1], q, q_rows, kHeadPad, kHeadPad, 256, 16, 32))) return rc;
     const int items = samples * heads;
-    // (256 keys WITH a key bias - text lengths in (128, 256], no shipped configuration - stays on the first kernel: the
-    // second one has no shared memory left for the bias slices there)
-    if (forced != 3 && !(n_keys == 256 && bias != nullptr)) {
-      // second-generation kernel: per-tile Q slots, per-item K/V double buffering, output through smem + TMA store
-      CUtensorMap tq1[2], to;
-      if ((rc = make_tmap_bf16(&tq1[0], q, q_rows, kHeadPad, kHeadPad, kAttnBM, 64, 128))) return rc;
-      if ((rc = make_tmap_bf16(&tq1[1], q, q_rows, kHeadPad, kHeadPad, kAttnBM, 16, 32))) return rc;
-      if ((rc = make_tmap_bf16(&to, out, static_cast<uint64_t>(samples) * q_tokens, heads * kHeadDim, p.out_ld, kAttnBM,
-                               kHeadDim, 0)))
-        return rc;
-      if (n_keys == 256) return launch_attn_pair2_inst<256, false>(tq1, tm, to, p, items, stream);
-      return bias ? launch_attn_pair2_inst<128, true>(tq1, tm, to, p, items, stream)
-                  : launch_attn_pair2_inst<128, false>(tq1, tm, to, p, items, stream);
-    }
     if (n_keys == 256) {
       return bias ? launch_attn_pair_inst<256, true>(tq, tm, p, items, stream)
                   : launch_attn_pair_inst<256, false>(tq, tm, p, items, stream);
@@ -899,6 +974,12 @@ int ecadk_gemm_bias_headmajor(const void* a, const void* w, const float* bias, v
   p.tokens = tokens;
   p.tokens_pad = tokens_pad;
   return launch_gemm<EPI_HEADMAJOR>(a, w, p, static_cast<cudaStream_t>(stream));
+}
+
+int ecadk_attention_ex(const void* q, int q_ld, const void* k, const void* v, int kv_ld, const float* bias, void* out,
+                       int samples, int heads, int q_tokens, int n_keys, ecadk_stream_t stream) {
+  return launch_attention_ex(q, q_ld, k, v, kv_ld, bias, out, samples, heads, q_tokens, n_keys,
+                             static_cast<cudaStream_t>(stream));
 }
 
 int ecadk_attention(const void* q, const void* k, const void* v, const float* bias, void* out, int samples,
@@ -1374,12 +1455,22 @@ int ecadk_pixart_blocks_range(ecadk_handle_t h, const EcadkBlocksArgs* a, const 
       pend.shift_temb = a->temb6 + 0 * D;
       pend.scale_temb = a->temb6 + 1 * D;
       if ((rc = flush())) return rc;
-      if ((rc = ecadk_gemm_bias_headmajor(a->h, w.w_qkv1, w.b_qkv1, a->q, a->k, a->v, 3, d.heads, a->tokens,
-                                          a->tokens, M, D, stream_)))
-        return rc;
-      if ((rc = launch_attention(a->q, a->k, a->v, nullptr, a->attn_o, a->samples, d.heads, a->tokens, a->tokens,
-                                 stream)))
-        return rc;
+      if (a->qkv != nullptr) {
+        // plain [M, 3*dim] projection output; the attention kernel gathers its (sample, head) tiles from it through
+        // 3-D tensor maps (no head-major scatter epilogue, no padded copies of Q/K/V in HBM)
+        __nv_bfloat16* qkv = static_cast<__nv_bfloat16*>(a->qkv);
+        if ((rc = ecadk_gemm_bias(a->h, w.w_qkv1, w.b_qkv1, qkv, M, 3 * D, D, 3 * D, 0, stream_))) return rc;
+        if ((rc = launch_attention_ex(qkv, 3 * D, qkv + D, qkv + 2 * D, 3 * D, nullptr, a->attn_o, a->samples, d.heads,
+                                      a->tokens, a->tokens, stream)))
+          return rc;
+      } else {
+        if ((rc = ecadk_gemm_bias_headmajor(a->h, w.w_qkv1, w.b_qkv1, a->q, a->k, a->v, 3, d.heads, a->tokens,
+                                            a->tokens, M, D, stream_)))
+          return rc;
+        if ((rc = launch_attention(a->q, a->k, a->v, nullptr, a->attn_o, a->samples, d.heads, a->tokens, a->tokens,
+                                   stream)))
+          return rc;
+      }
       if ((rc = ecadk_gemm_bias_gated_residual_cache(a->attn_o, w.w_out1, w.b_out1, a->x, ex2 ? a->xb : nullptr, s1,
                                                      tab + 2 * D, a->temb6 + 2 * D, S6, a->tokens, M, D, D, stream_)))
         return rc;
@@ -1395,12 +1486,20 @@ int ecadk_pixart_blocks_range(ecadk_handle_t h, const EcadkBlocksArgs* a, const 
         pend.xb = a->xb;
         if ((rc = flush())) return rc;
       }
-      if ((rc = ecadk_gemm_bias_headmajor(a->xb, w.w_q2, w.b_q2, a->q, nullptr, nullptr, 1, d.heads, a->tokens,
-                                          a->tokens, M, D, stream_)))
-        return rc;
-      if ((rc = launch_attention(a->q, a->k2[b], a->v2[b], a->text_bias, a->attn_o, a->samples, d.heads, a->tokens,
-                                 a->text_pad, stream)))
-        return rc;
+      if (a->qkv != nullptr && a->text_pad != 256) {  // (256 padded text keys + bias run on the first-generation kernel)
+        __nv_bfloat16* q2 = static_cast<__nv_bfloat16*>(a->qkv);  // the query projection reuses the first dim columns
+        if ((rc = ecadk_gemm_bias(a->xb, w.w_q2, w.b_q2, q2, M, D, D, 3 * D, 0, stream_))) return rc;
+        if ((rc = launch_attention_ex(q2, 3 * D, a->k2[b], a->v2[b], 0, a->text_bias, a->attn_o, a->samples, d.heads,
+                                      a->tokens, a->text_pad, stream)))
+          return rc;
+      } else {
+        if ((rc = ecadk_gemm_bias_headmajor(a->xb, w.w_q2, w.b_q2, a->q, nullptr, nullptr, 1, d.heads, a->tokens,
+                                            a->tokens, M, D, stream_)))
+          return rc;
+        if ((rc = launch_attention(a->q, a->k2[b], a->v2[b], a->text_bias, a->attn_o, a->samples, d.heads, a->tokens,
+                                   a->text_pad, stream)))
+          return rc;
+      }
       if ((rc = ecadk_gemm_bias_gated_residual_cache(a->attn_o, w.w_out2, w.b_out2, a->x, nullptr, s2, nullptr,
                                                      nullptr, S6, a->tokens, M, D, D, stream_)))
         return rc;

@@ -377,6 +377,9 @@ class B200PixArtTransformer2D(torch.nn.Module):
             ws[n] = torch.empty(M, D, device=dev, dtype=bf)
         for n in ("q", "k", "v"):
             ws[n] = torch.zeros(S, H, N, _lib.HEAD_PAD, device=dev, dtype=bf)  # padding columns stay zero
+        # plain [M, 3D] output of the fused q|k|v projection (and, in its first D columns, of attn2's query projection):
+        # the attention kernels gather their (sample, head) tiles from it through 3-D tensor maps
+        ws["qkv"] = torch.empty(M, 3 * D, device=dev, dtype=bf)
         ws["ffh"] = torch.empty(M, 4 * D, device=dev, dtype=bf)
         ws["cache"] = torch.empty(L * 3, M, D, device=dev, dtype=bf)
         ws["k2"] = torch.zeros(L, S, H, TEXT_PAD, _lib.HEAD_PAD, device=dev, dtype=bf)
@@ -396,7 +399,7 @@ class B200PixArtTransformer2D(torch.nn.Module):
         ws["cache_ptrs"] = (C.c_void_p * (L * 3))(*[ws["cache"][i].data_ptr() for i in range(L * 3)])
         args = _lib.EcadkBlocksArgs()
         args.samples, args.tokens, args.text_pad = S, N, TEXT_PAD
-        for n in ("x", "xb", "h", "q", "k", "v", "attn_o", "ffh", "temb6", "text_bias"):
+        for n in ("x", "xb", "h", "q", "k", "v", "attn_o", "ffh", "temb6", "text_bias", "qkv"):
             setattr(args, n, ws[n].data_ptr())
         args.k2 = C.cast(ws["k2_ptrs"], C.POINTER(C.c_void_p))
         args.v2 = C.cast(ws["v2_ptrs"], C.POINTER(C.c_void_p))

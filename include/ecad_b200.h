@@ -159,6 +159,14 @@ int ecadk_gemm_bias_headmajor(const void* a, const void* w, const float* bias, v
 int ecadk_attention(const void* q, const void* k, const void* v, const float* bias, void* out, int samples,
                     int heads, int q_tokens, int n_keys, ecadk_stream_t stream);
 
+/* Same with the operand layout stated per operand: q_ld / kv_ld == 0 -> head-major [samples, heads, tokens, 80] as
+ * above; > 0 -> ROW-major [samples*tokens, ld] bf16 - the plain output of the projection GEMM - where the pointer
+ * addresses column 0 of head 0 of that operand (for a fused [M, 3*dim] q|k|v buffer: k = base + dim, v = base + 2*dim)
+ * and head h occupies columns [72 h, 72 h + 72).  Row-major operands need q_tokens % 256 == 0 (the 256-query and the
+ * streaming kernels gather them through 3-D tensor maps whose out-of-bounds zero fill supplies the 72 -> 80 padding). */
+int ecadk_attention_ex(const void* q, int q_ld, const void* k, const void* v, int kv_ld, const float* bias, void* out,
+                       int samples, int heads, int q_tokens, int n_keys, ecadk_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * FLUX building blocks (kernel level; the FLUX step executor is built on them)
  * ---------------------------------------------------------------------------------------------------------- */
@@ -278,6 +286,10 @@ typedef struct {
                           * recomputes the sub-block, or the generation ends - so an EXECUTED sub-block skips the cache
                           * store (the reference's `self.cached_* = out`, cached_transformer_block.py:357-358,388-389,
                           * is a dead store then).  Ignored for reused sub-blocks. */
+  void* qkv;             /* bf16 [samples*tokens, 3*dim] or NULL.  When given, the q/k/v projections are written as plain
+                          * row-major GEMM outputs into it and the attention kernels gather their (sample, head) tiles
+                          * through 3-D tensor maps (ecadk_attention_ex); q / k / v above are then unused.  NULL keeps
+                          * the head-major scatter path. */
 } EcadkBlocksArgs;
 
 /* Runs blocks 0..num_layers-1.  executed[b*3 + c] != 0 -> compute sub-block c in {attn1, attn2, ff} of block b and

@@ -198,6 +198,47 @@ def test_attention_streaming(cuda_device, samples, q_tokens, nk, real_keys):
     assert float((out.float() - ref).abs().mean() / ref.abs().mean()) < 8e-3
 
 
+@pytest.mark.parametrize("samples,q_tokens,nk,cross", [(20, 256, 256, False), (20, 256, 128, True), (2, 1024, 1024, False),
+                                                         (2, 1024, 384, True)])
+def test_attention_rowmajor_operands(cuda_device, samples, q_tokens, nk, cross):
+    """ecadk_attention_ex: Q (and for self-attention K, V) read straight from the plain row-major projection output
+    [samples*tokens, 3*1152] through 3-D tensor maps - the 72 -> 80 column padding of the shared-memory tiles is the
+    maps' out-of-bounds zero fill.  Must equal the head-major path bit for bit (same tiles reach the same MMAs)."""
+    from ecad_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(41 + nk + q_tokens)
+    D = H * HD
+    qkv = _bf(torch.randn(samples * q_tokens, 3 * D, device="cuda", generator=g) * 1.5)
+
+    def headmajor(cols, tokens):  # [S*tokens, D] -> [S, H, tokens, 80] zero padded
+        t = torch.zeros(samples, H, tokens, HP, device="cuda", dtype=torch.bfloat16)
+        t[..., :HD] = cols.reshape(samples, tokens, H, HD).permute(0, 2, 1, 3)
+        return t
+
+    q_hm = headmajor(qkv[:, :D], q_tokens)
+    out_rm = torch.full((samples, q_tokens, D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    out_hm = torch.full_like(out_rm, float("nan"))
+    if cross:
+        real = nk - 9
+        k_hm = torch.zeros(samples, H, nk, HP, device="cuda", dtype=torch.bfloat16)
+        v_hm = torch.zeros_like(k_hm)
+        k_hm[:, :, :real, :HD] = _bf(torch.randn(samples, H, real, HD, device="cuda", generator=g) * 1.5)
+        v_hm[:, :, :real, :HD] = _bf(torch.randn(samples, H, real, HD, device="cuda", generator=g))
+        bias = torch.zeros(samples, nk, device="cuda")
+        bias[:, real - 5:real] = -10000.0
+        bias[:, real:] = float("-inf")
+        _lib.attention_ex(qkv, 3 * D, k_hm, v_hm, 0, bias, out_rm, samples, H, q_tokens, nk)
+    else:
+        assert nk == q_tokens
+        k_hm, v_hm, bias = headmajor(qkv[:, D:2 * D], nk), headmajor(qkv[:, 2 * D:], nk), None
+        _lib.attention_ex(qkv, 3 * D, qkv[:, D:], qkv[:, 2 * D:], 3 * D, None, out_rm, samples, H, q_tokens, nk)
+    _lib.attention(q_hm, k_hm, v_hm, bias, out_hm, samples, H, q_tokens, nk)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out_rm.float()).all()
+    assert torch.equal(out_rm, out_hm)
+    ref = _attn_ref(q_hm[..., :HD], k_hm[..., :HD], v_hm[..., :HD], bias)
+    assert _rel_err(out_rm, ref) < 2e-2
+
+
 def test_attention_all_masked_row_is_uniform(cuda_device):
     """mask of all zeros -> every real key gets -10000 -> softmax is uniform over the REAL keys (reference
     semantics of the additive -10000 bias, pixart_transformer_2d_edited.py:282-289), padding keys excluded."""

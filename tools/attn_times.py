@@ -39,7 +39,27 @@ for name, S, nq, nk, bias in [("c2 self", 200, 256, 256, False), ("c2 cross", 20
     ms = statistics.mean(ts)
     fl = 4.0 * S * H * nq * nk * 72
     print(f"{name:9s} S={S:3d} Nq={nq:4d} Nk={nk:4d}: {ms*1e3:8.1f} us  {fl/ms/1e9:7.1f} TFLOP/s (real d=72)  "
-          f"{fl/ms/1e9*80/72:7.1f} incl. padding")
+          f"{fl/ms/1e9*80/72:7.1f} incl. padding", flush=True)
+    # row-major operands (the executor's path): Q (+ K, V for self-attention) gathered from the [M, 3456] projection output
+    qkv = torch.randn(S * nq, 3 * H * 72, device="cuda", generator=g).to(torch.bfloat16)
+    if bias:
+        run_rm = lambda: _lib.attention_ex(qkv, 3 * H * 72, k, v, 0, b, out, S, H, nq, nk)  # noqa: E731
+    else:
+        run_rm = lambda: _lib.attention_ex(qkv, 3 * H * 72, qkv[:, H * 72:], qkv[:, 2 * H * 72:], 3 * H * 72, None, out,  # noqa: E731
+                                           S, H, nq, nk)
+    for _ in range(3):
+        run_rm()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            run_rm()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(e) / 3)
+    print(f"{'':9s} row-major operands:        {statistics.mean(ts)*1e3:8.1f} us", flush=True)
 
 # FLUX joint attention (head_dim 128): config 5 shape and the 256x256 shape
 for name, S, Hh, n in [("c5 joint", 4, 24, 4608), ("flux256", 16, 24, 768)]:
