@@ -34,6 +34,12 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+# torchrun exports OMP_NUM_THREADS=1 to every rank.  Rank 0 also times the CPU baseline (the oracle on ALL host cores),
+# so it gets the cores back BEFORE torch / OpenMP / MKL initialise their thread pools; the other ranks keep 1.
+if os.environ.get("RANK", "0") == "0":
+    for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
@@ -528,10 +534,14 @@ def main():
         print(json.dumps(line), file=_REAL_STDOUT, flush=True)
 
 
-# The host mirrors the reference's `print("WARNING: No cached ... found. Recomputing.")` on stdout; the bench contract is
-# ONE JSON line on stdout, so everything else goes to stderr.
+# The host mirrors the reference's `print("WARNING: No cached ... found. Recomputing.")` on stdout and NCCL prints its
+# version banner with C-level stdio; the bench contract is ONE JSON line on stdout, so file descriptor 1 itself is
+# pointed at stderr and the JSON line goes out through a private duplicate of the original stdout.
 _REAL_STDOUT = sys.stdout
 
 if __name__ == "__main__":
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     sys.stdout = sys.stderr
     main()

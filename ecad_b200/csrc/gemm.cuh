@@ -327,6 +327,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
 //     (each element is read and rewritten by the same lane);
 //   * the bf16 tiles are [32 x 64 B] with the 64B swizzle; one lane issues cp.async.bulk.tensor stores with matching
 //     tensor maps; the staging is reused by the next chunk once `cp.async.bulk.wait_group.read` says it has been read.
+//     (Measured and rejected: separate transpose / staging tiles - 12 KB per warp, one pipeline stage less - so that
+//     the wait for the previous chunk's stores sits behind the next chunk's TMEM load and transpose: 180 -> 183 us.
+//     Decomposition with -DECADK_EPI_DBG builds: MMA + operands 98 us, + residual reads 125 us, + the three bulk
+//     stores 152 us, all 180 us; each bulk store costs ~17 us per launch whatever its size.)
 __device__ __forceinline__ void epilogue_tile_residual_tma(const GemmParams& p, const CUtensorMap* tm_x,
                                                            const CUtensorMap* tm_cache, const CUtensorMap* tm_xb,
                                                            const uint32_t t_row, uint8_t* stage, const int lane,

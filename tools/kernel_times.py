@@ -85,17 +85,24 @@ report("residual_ln 3 reuse + LN", timed(lambda: _lib.residual_ln(
 report("residual_ln 3 reuse only", timed(lambda: _lib.residual_ln(
     x, N, reuse=[(cache[0], table[2], temb[:, 2 * D:]), (cache[1], None, None), (cache[2], table[5], temb[:, 5 * D:])],
     temb_stride=6 * D)), bytes_=M * D * (4 + 4 + 6))
-report("gemm QKV headmajor [M,1152]x[3456,1152]", timed(lambda: _lib.gemm_headmajor(h, w_qkv, b_qkv, [q, k, v], H, N, N)),
+qkv = torch.empty(M, 3 * D, device=dev, dtype=bf)
+report("gemm QKV plain -> row-major [M,1152]x[3456,1152] (executor path)", timed(lambda: _lib.gemm_bias(h, w_qkv, b_qkv, qkv)),
        flops=2.0 * M * 3 * D * D)
-report("attention self NK=256", timed(lambda: _lib.attention(q, k, v, None, attn_o, S, H, N, 256)),
+report("attention self NK=256, row-major operands (executor path)", timed(lambda: _lib.attention_ex(
+    qkv, 3 * D, qkv[:, D:], qkv[:, 2 * D:], 3 * D, None, attn_o, S, H, N, 256)),
+    flops=4.0 * S * H * N * N * 72, bytes_=M * D * 2 * 4)
+report("  gemm QKV head-major scatter (round-1 path)", timed(lambda: _lib.gemm_headmajor(h, w_qkv, b_qkv, [q, k, v], H, N, N)),
+       flops=2.0 * M * 3 * D * D)
+report("  attention self NK=256, head-major operands", timed(lambda: _lib.attention(q, k, v, None, attn_o, S, H, N, 256)),
        flops=4.0 * S * H * N * N * 72, bytes_=S * H * N * 80 * 2 * 3 + M * D * 2)
 report("gemm out1 gated-residual+cache+xb [M,1152]x[1152,1152]", timed(lambda: _lib.gemm_gated_residual(
     attn_o, w_d, b_d, x, cache[0], N, xb=xb, gate_table=table[2], gate_temb=temb[:, 2 * D:], temb_stride=6 * D)),
     flops=2.0 * M * D * D, bytes_=M * D * (2 + 4 + 4 + 2 + 2))
-report("gemm Q2 headmajor [M,1152]x[1152,1152]", timed(lambda: _lib.gemm_headmajor(xb, w_d, b_d, [q], H, N, N)),
+report("gemm Q2 plain -> first D columns of the row-major buffer", timed(lambda: _lib.gemm_bias(xb, w_d, b_d, qkv)),
        flops=2.0 * M * D * D)
-report("attention cross NK=128 bias", timed(lambda: _lib.attention(q, k2, v2, bias2, attn_o, S, H, N, 128)),
-       flops=4.0 * S * H * N * 128 * 72, bytes_=S * H * (N + 256) * 80 * 2 + M * D * 2)
+report("attention cross NK=128 bias, row-major Q", timed(lambda: _lib.attention_ex(
+    qkv, 3 * D, k2, v2, 0, bias2, attn_o, S, H, N, 128)),
+    flops=4.0 * S * H * N * 128 * 72, bytes_=M * D * 2 * 2 + S * H * 256 * 80 * 2)
 report("gemm out2 residual+cache (no gate)", timed(lambda: _lib.gemm_gated_residual(
     attn_o, w_d, b_d, x, cache[1], N)), flops=2.0 * M * D * D, bytes_=M * D * (2 + 4 + 4 + 2))
 report("gemm FF1 bias+gelu [M,1152]x[4608,1152]", timed(lambda: _lib.gemm_bias(h, w_f1, b_f1, ffh, gelu=True)),
@@ -127,7 +134,7 @@ for n_, k_ in [(1152, 1152), (3456, 1152), (4608, 1152), (1152, 4608)]:
     report(f"gemm plain bias [M,{k_}]x[{n_},{k_}]", timed(lambda: _lib.gemm_bias(a_, w_, None, o_)),
            flops=2.0 * M * n_ * k_)
     report(f"  torch.matmul same shape (cuBLAS)", timed(lambda: torch.matmul(a_, w_.t(), out=o_)), flops=2.0 * M * n_ * k_)
-total = sum(r["us"] for r in rows[:11] if "reuse" not in r["kernel"]) + rows[0]["us"]
+total = sum(r["us"] for r in rows[:13] if "reuse" not in r["kernel"] and not r["kernel"].startswith("  ")) + rows[0]["us"]
 print(f"sum of one dense block (2 LN + 7 GEMM/attn kernels): {total:.0f} us; x28 = {total * 28 / 1e3:.1f} ms per forward")
 out = ROOT / "gpurun_out" / "kernel_times.json"
 out.parent.mkdir(exist_ok=True)

@@ -33,6 +33,7 @@ bias2 = torch.zeros(S, 128, device=dev)
 bias2[:, 120:] = float("-inf")
 attn_o = torch.empty(M, D, device=dev, dtype=bf)
 ffh = torch.empty(M, 4 * D, device=dev, dtype=bf)
+qkv = torch.empty(M, 3 * D, device=dev, dtype=bf)
 w_qkv, b_qkv = rnd(3 * D, D, scale=1 / math.sqrt(D)), torch.randn(3 * D, device=dev, generator=g)
 w_d, b_d = rnd(D, D, scale=1 / math.sqrt(D)), torch.randn(D, device=dev, generator=g)
 w_f1, b_f1 = rnd(4 * D, D, scale=1 / math.sqrt(D)), torch.randn(4 * D, device=dev, generator=g)
@@ -43,12 +44,12 @@ ln = dict(shift_table=table[0], scale_table=table[1], shift_temb=temb, scale_tem
 for _ in range(2):
     _lib.residual_ln(x, N, h=h, **ln)
     _lib.residual_ln(x, N, reuse=reuse3, h=h, **ln)
-    _lib.gemm_headmajor(h, w_qkv, b_qkv, [q, k, v], H, N, N)
-    _lib.attention(q, k, v, None, attn_o, S, H, N, 256)
+    _lib.gemm_bias(h, w_qkv, b_qkv, qkv)  # executor path: plain row-major q|k|v, gathered by the attention kernel
+    _lib.attention_ex(qkv, 3 * D, qkv[:, D:], qkv[:, 2 * D:], 3 * D, None, attn_o, S, H, N, 256)
     _lib.gemm_gated_residual(attn_o, w_d, b_d, x, cache[0], N, xb=xb, gate_table=table[2], gate_temb=temb[:, 2 * D:],
                              temb_stride=6 * D)
-    _lib.gemm_headmajor(xb, w_d, b_d, [q], H, N, N)
-    _lib.attention(q, k2, v2, bias2, attn_o, S, H, N, 128)
+    _lib.gemm_bias(xb, w_d, b_d, qkv)
+    _lib.attention_ex(qkv, 3 * D, k2, v2, 0, bias2, attn_o, S, H, N, 128)
     _lib.gemm_gated_residual(attn_o, w_d, b_d, x, cache[1], N)
     _lib.gemm_bias(h, w_f1, b_f1, ffh, gelu=True)
     _lib.gemm_gated_residual(ffh, w_f2, b_d, x, cache[2], N, gate_table=table[5], gate_temb=temb[:, 5 * D:],
