@@ -29,6 +29,8 @@ EXPORTED_SYMBOLS = [
     "ecadk_average_halves",
     "ecadk_final_layer",
     "ecadk_cfg_dpm_step",
+    "ecadk_set_splitk_workspace",
+    "ecadk_splitk_launches",
     "ecadk_gemm_bias",
     "ecadk_gemm_bias_gated_residual_cache",
     "ecadk_gemm_bias_headmajor",
@@ -194,6 +196,8 @@ def load() -> C.CDLL:
         "ecadk_average_halves": [p, sz, p],
         "ecadk_final_layer": [p, p, p, i, p, p, p, p, i, i, i, i, i, f, p],
         "ecadk_cfg_dpm_step": [p, p, p, i, i, i, i, f, f, f, f, f, f, p],
+        "ecadk_set_splitk_workspace": [p, sz],
+        "ecadk_splitk_launches": [],
         "ecadk_gemm_bias": [p, p, p, p, i, i, i, i, i, p],
         "ecadk_gemm_bias_gated_residual_cache": [p, p, p, p, p, p, p, p, i, i, i, i, i, p],
         "ecadk_gemm_bias_headmajor": [p, p, p, p, p, p, i, i, i, i, i, i, p],
@@ -225,6 +229,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = C.c_int
+    lib.ecadk_splitk_launches.restype = C.c_longlong
     if lib.ecadk_abi_version() != 1:
         raise RuntimeError(f"libecad_b200.so ABI version {lib.ecadk_abi_version()} != 1")
     _lib = lib
@@ -281,6 +286,19 @@ def attention(q, k, v, bias, out, samples, heads, q_tokens, n_keys):
     check(load().ecadk_attention(ptr(q), ptr(k), ptr(v), ptr(bias), ptr(out), samples, heads, q_tokens, n_keys,
                                  stream_ptr()), "attention")
     return out
+
+
+def set_splitk_workspace(buf):
+    """Install ``buf`` (a CUDA tensor, or None to remove it) as the split-K workspace of this thread's stand-alone GEMM
+    calls (see ecadk_set_splitk_workspace).  The caller keeps the tensor alive while it is installed."""
+    if buf is None:
+        check(load().ecadk_set_splitk_workspace(None, 0), "set_splitk_workspace")
+    else:
+        check(load().ecadk_set_splitk_workspace(ptr(buf), buf.numel() * buf.element_size()), "set_splitk_workspace")
+
+
+def splitk_launches() -> int:
+    return int(load().ecadk_splitk_launches())
 
 
 def attention_ex(q, q_ld, k, v, kv_ld, bias, out, samples, heads, q_tokens, n_keys):

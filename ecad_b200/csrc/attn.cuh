@@ -1008,7 +1008,6 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
 #endif
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++n) {
       const uint32_t par = n & 1;
-      const int b = n & 1;
       if constexpr (HAS_BIAS) {
 #pragma unroll
         for (int j = 0; j < NC; ++j) sts_f1(bias_a + (lane + 32 * j) * 4, breg[j]);

@@ -7,9 +7,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <unordered_map>
+#include <atomic>
 #include <vector>
 
 #include "../../include/ecad_b200.h"
@@ -293,6 +295,115 @@ int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtens
   return check_launch("gemm_bf16_kernel");
 }
 
+// Split-K workspace of the calling thread: the executor entry points install their handle's buffer for the duration
+// of the call (SplitWsScope); ecadk_set_splitk_workspace installs one for stand-alone GEMM calls.  No workspace, no
+// split: launch_gemm then takes the ordinary kernels.
+struct SplitWs {
+  void* ptr;
+  size_t bytes;
+};
+thread_local SplitWs g_split_ws = {nullptr, 0};
+std::atomic<long long> g_splitk_launches{0};  // process-wide count of gemm_splitk_kernel launches (tests, bench)
+struct SplitWsScope {
+  SplitWs saved;
+  SplitWsScope(void* ptr, size_t bytes) : saved(g_split_ws) {
+    if (ptr != nullptr) g_split_ws = SplitWs{ptr, bytes};
+  }
+  ~SplitWsScope() { g_split_ws = saved; }
+};
+constexpr size_t kSplitWsBytes = 16u << 20;  // per handle: 36 tiles x 4 CTAs x 64 KB = 9.4 MB at M = 512, N = 1152
+
+template <typename... KArgs, typename... Args>
+void launch_pdl_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, int cluster, cudaStream_t stream,
+                        Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl() ? 2 : 1;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// clusters of `split` CTAs of gemm_splitk_kernel<BN, EPI> that can be resident at once (0 on error); cached
+template <int BN, int EPI>
+int splitk_max_clusters(int split) {
+  using Cfg = GemmCfg<BN, EPI>;
+  static int cached[kSplitMax + 1] = {-1, -1, -1, -1, -1};
+  if (cached[split] >= 0) return cached[split];
+  auto kern = gemm_splitk_kernel<BN, EPI>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) {
+    cudaGetLastError();
+    return cached[split] = 0;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(split * num_sms());
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = split;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  return cached[split] = n;
+}
+
+template <int BN, int EPI>
+int launch_gemm_splitk_inst(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const EpiMaps& em,
+                            const GemmParams& p, int split, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, EPI>;
+  const int tiles = ((p.M + kGemmBM - 1) / kGemmBM) * (p.N / BN);
+  launch_pdl_cluster(gemm_splitk_kernel<BN, EPI>, dim3(tiles * split), dim3(kGemmThreads), Cfg::kSmemBytes, split, stream,
+                     ta, ta2, tb, em.x, em.cache, em.xb, p, static_cast<float4*>(g_split_ws.ptr));
+  g_splitk_launches.fetch_add(1, std::memory_order_relaxed);
+  return check_launch("gemm_splitk_kernel");
+}
+
+// Split-K plan for a small problem: (BN, split) with the smallest per-CTA operand stream, ~ (128 + BN) / split, whose
+// clusters are all resident at once and fit the workspace; split = 1 means "no split".
+template <int EPI>
+void plan_splitk(const GemmParams& p, int* bn_out, int* split_out) {
+  *split_out = 1;
+  static const bool allow = [] {
+    const char* e = getenv("ECADK_GEMM_SPLITK");
+    return !(e != nullptr && atoi(e) == 0);
+  }();
+  if (!allow || g_split_ws.ptr == nullptr) return;
+  const int m_tiles = (p.M + kGemmBM - 1) / kGemmBM;
+  const int num_kb = p.K / kGemmBK;
+  const int cand[3][2] = {{128, 4}, {64, 2}, {128, 2}};
+  for (const auto& c : cand) {
+    const int bn = c[0], split = c[1];
+    if (p.N % bn != 0 || num_kb < 2 * split) continue;
+    const int tiles = m_tiles * (p.N / bn);
+    if (2 * tiles > num_sms()) continue;  // enough tiles for the ordinary kernels
+    const size_t need = static_cast<size_t>(tiles) * split * bn * 128 * sizeof(float);
+    if (need > g_split_ws.bytes) continue;
+    const int resident = bn == 128 ? splitk_max_clusters<128, EPI>(split) : splitk_max_clusters<64, EPI>(split);
+    if (tiles > resident) continue;
+    *bn_out = bn;
+    *split_out = split;
+    return;
+  }
+}
+
 template <int BN, int EPI>
 int launch_gemm2_inst(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const CUtensorMap& tb_tail,
                       const EpiMaps& em, const GemmParams& p, int tail, cudaStream_t stream) {
@@ -397,10 +508,28 @@ int launch_gemm(const void* a, const void* w, GemmParams& p, cudaStream_t stream
       default: return launch_gemm2_inst<128, EPI>(ta, ta2, tb, tb, em, p, 0, stream);
     }
   }
-  const int bn = pick_bn((p.M + kGemmBM - 1) / kGemmBM, p.N, num_sms());
+  int bn = pick_bn((p.M + kGemmBM - 1) / kGemmBM, p.N, num_sms());
   ECADK_REQUIRE(bn != 0, "gemm: no tile width divides N=%d", p.N);
+  {
+    int split = 1, sbn = 0;
+    plan_splitk<EPI>(p, &sbn, &split);
+    if (split > 1) {
+      if ((rc = make_tmap_bf16(&tb, w, p.N, p.K, p.K, sbn, kGemmBK, 128))) return rc;
+      return sbn == 128 ? launch_gemm_splitk_inst<128, EPI>(ta, ta2, tb, em, p, split, stream)
+                        : launch_gemm_splitk_inst<64, EPI>(ta, ta2, tb, em, p, split, stream);
+    }
+  }
+  // small problems (batch-1 latency configuration): when even 128-wide tiles leave more than half of the SMs idle,
+  // 64-wide tiles double the CTAs - each streams its own W slice, so the per-SM operand stream (what bounds a lone
+  // 128 x K strip, e.g. FF2 at M = 512: 2.3 MB through each of 36 SMs) halves.  ECADK_GEMM_BN64=0 disables it.
+  static const bool allow64 = [] {
+    const char* e = getenv("ECADK_GEMM_BN64");
+    return !(e != nullptr && atoi(e) == 0);
+  }();
+  if (allow64 && bn == 128 && p.N % 64 == 0 && 2 * ((p.M + kGemmBM - 1) / kGemmBM) * (p.N / 128) <= num_sms()) bn = 64;
   if ((rc = make_tmap_bf16(&tb, w, p.N, p.K, p.K, bn, kGemmBK, 128))) return rc;
   switch (bn) {
+    case 64: return launch_gemm_inst<64, EPI>(ta, ta2, tb, em, p, stream);
     case 256: return launch_gemm_inst<256, EPI>(ta, ta2, tb, em, p, stream);
     case 192: return launch_gemm_inst<192, EPI>(ta, ta2, tb, em, p, stream);
     default: return launch_gemm_inst<128, EPI>(ta, ta2, tb, em, p, stream);
@@ -685,6 +814,7 @@ struct EcadkHandle_ {
   int device;
   EcadkModelDesc desc;
   std::vector<EcadkBlockWeights> blocks;
+  void* split_ws = nullptr;  // split-K partial tiles of the small-batch GEMMs (gemm_splitk_kernel), kSplitWsBytes
 };
 
 struct EcadkFluxHandle_ {
@@ -1359,18 +1489,37 @@ int ecadk_create(int device, const EcadkModelDesc* desc, const EcadkBlockWeights
   h->device = device;
   h->desc = *desc;
   h->blocks.assign(blocks, blocks + desc->num_layers);
+  int cur = -1;
+  if (cudaGetDevice(&cur) == cudaSuccess && cur == device) {
+    // optional: without it the small-batch GEMMs simply do not split
+    if (cudaMalloc(&h->split_ws, kSplitWsBytes) != cudaSuccess) {
+      cudaGetLastError();
+      h->split_ws = nullptr;
+    }
+  }
   *out = h;
   return ECADK_OK;
 }
 
 int ecadk_destroy(ecadk_handle_t h) {
+  if (h != nullptr && h->split_ws != nullptr) cudaFree(h->split_ws);
   delete h;
+  return ECADK_OK;
+}
+
+long long ecadk_splitk_launches(void) { return g_splitk_launches.load(std::memory_order_relaxed); }
+
+int ecadk_set_splitk_workspace(void* workspace, size_t bytes) {
+  ECADK_REQUIRE((workspace == nullptr) == (bytes == 0), "set_splitk_workspace: pointer and size must agree");
+  ECADK_REQUIRE(workspace == nullptr || aligned16(workspace), "set_splitk_workspace: 16-byte alignment");
+  g_split_ws = SplitWs{workspace, bytes};
   return ECADK_OK;
 }
 
 int ecadk_pixart_text_kv(ecadk_handle_t h, const void* enc, int samples, int text_tokens, int text_pad,
                          void* const* k2, void* const* v2, int* n_launches, ecadk_stream_t stream) {
   ECADK_REQUIRE(h && enc && k2 && v2, "text_kv: null argument");
+  SplitWsScope split_scope(h->split_ws, kSplitWsBytes);
   const EcadkModelDesc& d = h->desc;
   int launches = 0;
   for (int b = 0; b < d.num_layers; ++b) {
@@ -1393,6 +1542,7 @@ int ecadk_pixart_blocks(ecadk_handle_t h, const EcadkBlocksArgs* a, const uint8_
 int ecadk_pixart_blocks_range(ecadk_handle_t h, const EcadkBlocksArgs* a, const uint8_t* executed, int block_begin,
                               int block_end, int* n_launches, ecadk_stream_t stream_) {
   ECADK_REQUIRE(h && a && executed, "pixart_blocks: null argument");
+  SplitWsScope split_scope(h->split_ws, kSplitWsBytes);  // small-batch GEMMs of this call may split along K
   const EcadkModelDesc& d = h->desc;
   ECADK_REQUIRE(block_begin >= 0 && block_begin <= block_end && block_end <= d.num_layers,
                 "pixart_blocks: block range [%d, %d) outside [0, %d]", block_begin, block_end, d.num_layers);

@@ -590,6 +590,201 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 }
 
 // =====================================================================================================
+// Split-K variant for SMALL problems (the batch-1 latency configuration, M = 512 rows): a thread-block cluster of
+// S = 2 or 4 CTAs shares one 128 x BN output tile, CTA r multiplying the r-th slice of the K range.
+//
+// Why: with fewer tiles than SMs a GEMM is one CTA's serial operand stream - 128 x K of A plus BN x K of W through a
+// single SM's ~64 B/clk L2 port (FF2 at M = 512: 1.8 MB per CTA, 21 us of a kernel whose MMAs take 2 us; 20 % of a
+// batch-1 generation, profiles/r2_launches_c1_batch1.md).  More, narrower tiles re-read A; more CTAs per tile divide
+// BOTH operand streams.
+//
+// Reduction = reduce-scatter through an L2-resident workspace: column chunk c (32 columns) of the tile is OWNED by
+// CTA c / (chunks / S).  After its MMAs every CTA writes the accumulator chunks it does not own to the workspace
+// (fragment layout, one coalesced 512-byte store per warp instruction), the cluster barrier (release / acquire)
+// publishes them, and each CTA adds the S - 1 foreign partials of its own chunks into its TMEM accumulator
+// (tcgen05.ld + add + tcgen05.st) - after which the UNCHANGED epilogue functions run on the owned column range, so the
+// epilogue's latency chain (residual-stream read -> FMA -> stores) is divided by S as well.
+//
+// grid = tiles * S, cluster (S, 1, 1); one tile per cluster, no persistence (the launcher checks that all clusters
+// are co-resident).  Workspace: [tile][source rank][chunk][lane quarter][8][32] float4.
+// =====================================================================================================
+constexpr int kSplitMax = 4;
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
+                   const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_x,
+                   const __grid_constant__ CUtensorMap tmap_cache, const __grid_constant__ CUtensorMap tmap_xb,
+                   const GemmParams p, float4* __restrict__ ws) {
+  using Cfg = GemmCfg<BN, EPI>;
+  constexpr bool kTmaEpi = EPI == EPI_GATED_RESIDUAL && ECADK_EPI_TMA_STORE;
+  constexpr int STAGES = Cfg::kStages;
+  constexpr int kChunks = BN / 32;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::kStage);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStage + Cfg::kEpiBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int S = static_cast<int>(cluster_nctarank());
+  const int rank = static_cast<int>(cluster_ctarank());
+  const int tile = blockIdx.x / S;
+  const int num_n = p.N / BN;
+  const int m0 = (tile / num_n) * kGemmBM;
+  const int n0 = (tile % num_n) * BN;
+  const int num_kb = p.K / kGemmBK;
+  const int kb_begin = rank * num_kb / S, kb_end = (rank + 1) * num_kb / S;  // >= 1 k-block each (launcher)
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(&tmem_full[0], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();  // programmatic dependent launch: see gemm_bf16_kernel
+  griddep_wait();
+
+  const int quarter = warp & 3;
+  const int par = (warp - 2) >> 2;
+  const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+  const int per = kChunks / S;      // chunks owned by each CTA
+  const int own0 = rank * per;
+  float4* const ws_tile = ws + static_cast<size_t>(tile) * S * kChunks * 1024;
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::kStage;
+        uint8_t* sb = sa + Cfg::kStageA;
+        mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStage);
+        if (kb < p.kb_split) {
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kGemmBK, m0);
+        } else {
+          tma_load_2d(sa, &tmap_a2, &full_bar[stage], (kb - p.kb_split) * kGemmBK, m0);
+        }
+        tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kGemmBK, n0);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc = make_idesc_bf16(kGemmBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * Cfg::kStage);
+        const uint32_t sb = sa + Cfg::kStageA;
+        const uint64_t da = make_smem_desc(sa, 0, 1024, kLayoutSW128);
+        const uint64_t db = make_smem_desc(sb, 0, 1024, kLayoutSW128);
+#pragma unroll
+        for (int k = 0; k < kGemmBK / 16; ++k)
+          umma_bf16_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb != kb_begin) || (k != 0));
+        umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(&tmem_full[0]);  // this CTA's partial accumulator is complete
+    }
+  } else {
+    // ===================== partials out: the chunks owned by the other CTAs =====================
+    mbar_wait(&tmem_full[0], 0);
+    tc_fence_after();
+    for (int c = par; c < kChunks; c += 2) {
+      if (c / per == rank) continue;
+      uint32_t v[32];
+      tmem_ld_32x32(t_row + c * 32, v);
+      tmem_ld_wait();
+      float4* dst = ws_tile + (static_cast<size_t>(rank * kChunks + c) * 4 + quarter) * 256 + lane;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        __stcg(dst + j * 32, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                         __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+    }
+  }
+  // every thread of every CTA of the cluster: the partials above are released, the peers' acquired
+  __syncwarp();
+  cluster_sync();
+  if (warp >= 2) {
+    // ===================== reduce the owned chunks into TMEM, then the ordinary epilogue on them =====================
+    const int half = (per + 1) / 2;  // the epilogue's own split of a column range between the two warps of a quarter
+    const int c_begin = par * half, c_end = min(per, c_begin + half);
+    for (int c = c_begin; c < c_end; ++c) {
+      const int cc = own0 + c;
+      uint32_t v[32];
+      tmem_ld_32x32(t_row + cc * 32, v);
+      float4 pr[kSplitMax - 1][8];
+#pragma unroll
+      for (int i = 0; i < kSplitMax - 1; ++i) {
+        int src = rank + 1 + i;
+        src = src >= S ? src - S : src;
+        const float4* sp = ws_tile + (static_cast<size_t>(src * kChunks + cc) * 4 + quarter) * 256 + lane;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pr[i][j] = (i < S - 1) ? __ldcg(sp + j * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 a = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                               __uint_as_float(v[4 * j + 3]));
+#pragma unroll
+        for (int i = 0; i < kSplitMax - 1; ++i) {
+          a.x += pr[i][j].x; a.y += pr[i][j].y; a.z += pr[i][j].z; a.w += pr[i][j].w;
+        }
+        v[4 * j] = __float_as_uint(a.x);
+        v[4 * j + 1] = __float_as_uint(a.y);
+        v[4 * j + 2] = __float_as_uint(a.z);
+        v[4 * j + 3] = __float_as_uint(a.w);
+      }
+      tmem_st_32x32(t_row + cc * 32, v);
+    }
+    tmem_st_wait();
+    const int row_base = m0 + quarter * 32;
+    if constexpr (kTmaEpi) {
+      epilogue_tile_residual_tma(p, &tmap_x, &tmap_cache, &tmap_xb, t_row + own0 * 32,
+                                 reinterpret_cast<uint8_t*>(epi_stage) + (warp - 2) * kEpiTmaWarpBytes, lane, par,
+                                 row_base, n0 + own0 * 32, per);
+      if (lane == 0) tma_store_wait_all0();
+    } else {
+      float* stage = epi_stage + (warp - 2) * 32 * kEpiPitch;
+      epilogue_tile<EPI>(p, t_row + own0 * 32, stage, lane, par, row_base, n0 + own0 * 32, per);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// =====================================================================================================
 // 2-CTA variant (cta_group::2): a CTA pair on one TPC computes a 256 x BN tile.  Each CTA stages ITS 128 rows of A
 // and ITS half (BN/2 rows) of W, so the L2->SM traffic per FLOP drops by 1/3 (BN = 256) versus the 1-CTA kernel,
 // which is L2-bandwidth-bound on B200.  The leader CTA's single MMA thread issues tcgen05.mma.cta_group::2 for the

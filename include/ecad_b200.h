@@ -128,6 +128,17 @@ int ecadk_cfg_dpm_step(const float* noise, float* latents, float* x0_prev, int b
  * Requirements: K % 64 == 0, N % 128 == 0, pointers 16-byte aligned.
  * ---------------------------------------------------------------------------------------------------------- */
 
+/* Small problems (fewer than half as many 128-wide output tiles as SMs: the batch-1 latency configuration, BASELINE
+ * config 1) run a split-K form: a thread-block cluster of 2 or 4 CTAs shares one output tile and reduces its partial
+ * accumulators through an L2-resident workspace before the ordinary epilogue.  The executor entry points
+ * (ecadk_pixart_blocks*, ecadk_pixart_text_kv) use a workspace owned by their handle; this call installs one for the
+ * stand-alone GEMM calls of the CALLING THREAD (bytes >= tiles * 4 * 128 * BN * 4; 16 MiB covers every PixArt shape),
+ * NULL / 0 removes it.  Without a workspace the GEMMs do not split.  Same results up to fp32 summation order.
+ * No reference counterpart (torch.nn.Linear -> cuBLAS picks its own split-K). */
+int ecadk_set_splitk_workspace(void* workspace, size_t bytes);
+/* Process-wide number of split-K GEMM launches so far (tests and the bench use it to show which kernel ran). */
+long long ecadk_splitk_launches(void);
+
 /* out bf16 [M, ldo].  gelu != 0 applies GELU(tanh) (diffusers GELU(approximate="tanh")).
  * Replaces FeedForward.net[0] (cached_transformer_block.py:382) and PixArtAlphaTextProjection
  * (pixart_transformer_2d_edited.py:315-321). */

@@ -23,11 +23,33 @@ def _bf(t):
     return t.to(torch.bfloat16)
 
 
+@pytest.fixture(params=[False, True], ids=["plain", "splitk"])
+def splitk(request, cuda_device):
+    """Run a GEMM test twice: without and with a split-K workspace installed (small problems then take the cluster
+    split-K kernel; the large shapes of the same test stay on the ordinary kernels either way)."""
+    from ecad_b200 import _lib
+    if not request.param:
+        _lib.set_splitk_workspace(None)
+        yield False
+        return
+    ws = torch.empty(16 << 20, dtype=torch.uint8, device="cuda")
+    _lib.set_splitk_workspace(ws)
+    yield True
+    torch.cuda.synchronize()
+    _lib.set_splitk_workspace(None)
+
+
+# shapes the split-K planner takes (fewer than half as many 128-wide tiles as SMs): (m, n) -> expected
+def _splits(m, n):
+    return 2 * ((m + 127) // 128) * (n // 128) <= 148
+
+
 @pytest.mark.parametrize("m,n,k", [(512, 1152, 1152), (384, 4608, 1152), (1000, 2304, 1152), (256, 1152, 4608),
                                    (130, 3456, 1152), (20480, 1152, 1152), (256, 1152, 4096)])
 @pytest.mark.parametrize("gelu", [False, True])
-def test_gemm_bias(cuda_device, m, n, k, gelu):
+def test_gemm_bias(cuda_device, splitk, m, n, k, gelu):
     from ecad_b200 import _lib
+    n_split0 = _lib.splitk_launches()
     g = torch.Generator(device="cuda").manual_seed(m + n + k)
     a = _bf(torch.randn(m, k, device="cuda", generator=g))
     w = _bf(torch.randn(n, k, device="cuda", generator=g) / math.sqrt(k))
@@ -35,6 +57,7 @@ def test_gemm_bias(cuda_device, m, n, k, gelu):
     out = torch.full((m, n), float("nan"), device="cuda", dtype=torch.bfloat16)
     _lib.gemm_bias(a, w, bias, out, gelu=gelu)
     torch.cuda.synchronize()
+    assert _lib.splitk_launches() - n_split0 == (1 if splitk and _splits(m, n) else 0)
     ref = a.float() @ w.float().T + bias
     if gelu:
         ref = torch.nn.functional.gelu(ref, approximate="tanh")
@@ -47,8 +70,9 @@ def test_gemm_bias(cuda_device, m, n, k, gelu):
 
 @pytest.mark.parametrize("samples,tokens,k,gated,with_xb", [(2, 256, 1152, True, True), (3, 256, 4608, True, False),
                                                             (2, 256, 1152, False, False)])
-def test_gemm_gated_residual_cache(cuda_device, samples, tokens, k, gated, with_xb):
+def test_gemm_gated_residual_cache(cuda_device, splitk, samples, tokens, k, gated, with_xb):
     from ecad_b200 import _lib
+    n_split0 = _lib.splitk_launches()
     g = torch.Generator(device="cuda").manual_seed(7)
     m = samples * tokens
     a = _bf(torch.randn(m, k, device="cuda", generator=g))
@@ -64,6 +88,7 @@ def test_gemm_gated_residual_cache(cuda_device, samples, tokens, k, gated, with_
                              gate_table=table[2] if gated else None,
                              gate_temb=temb[:, 2 * D:] if gated else None, temb_stride=6 * D)
     torch.cuda.synchronize()
+    assert _lib.splitk_launches() - n_split0 == (1 if splitk and _splits(m, D) else 0)
     o = a.float() @ w.float().T + bias
     gate = (table[2][None] + temb[:, 2 * D:3 * D]).repeat_interleave(tokens, dim=0) if gated else 1.0
     x_ref = x0 + gate * o
@@ -74,7 +99,7 @@ def test_gemm_gated_residual_cache(cuda_device, samples, tokens, k, gated, with_
 
 
 @pytest.mark.parametrize("parts,samples,tokens,tokens_pad", [(3, 2, 256, 256), (1, 2, 256, 256), (2, 3, 120, 128)])
-def test_gemm_headmajor(cuda_device, parts, samples, tokens, tokens_pad):
+def test_gemm_headmajor(cuda_device, splitk, parts, samples, tokens, tokens_pad):
     from ecad_b200 import _lib
     g = torch.Generator(device="cuda").manual_seed(11)
     m = samples * tokens
