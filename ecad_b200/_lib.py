@@ -31,6 +31,7 @@ EXPORTED_SYMBOLS = [
     "ecadk_cfg_dpm_step",
     "ecadk_set_splitk_workspace",
     "ecadk_splitk_launches",
+    "ecadk_set_splitk_force",
     "ecadk_gemm_bias",
     "ecadk_gemm_bias_gated_residual_cache",
     "ecadk_gemm_bias_headmajor",
@@ -198,6 +199,7 @@ def load() -> C.CDLL:
         "ecadk_cfg_dpm_step": [p, p, p, i, i, i, i, f, f, f, f, f, f, p],
         "ecadk_set_splitk_workspace": [p, sz],
         "ecadk_splitk_launches": [],
+        "ecadk_set_splitk_force": [i, i],
         "ecadk_gemm_bias": [p, p, p, p, i, i, i, i, i, p],
         "ecadk_gemm_bias_gated_residual_cache": [p, p, p, p, p, p, p, p, i, i, i, i, i, p],
         "ecadk_gemm_bias_headmajor": [p, p, p, p, p, p, i, i, i, i, i, i, p],
@@ -295,6 +297,11 @@ def set_splitk_workspace(buf):
         check(load().ecadk_set_splitk_workspace(None, 0), "set_splitk_workspace")
     else:
         check(load().ecadk_set_splitk_workspace(ptr(buf), buf.numel() * buf.element_size()), "set_splitk_workspace")
+
+
+def set_splitk_force(bn: int = 0, split: int = 0) -> None:
+    """Force the split-K plan (tests / measurements); (0, 0) restores the planner."""
+    check(load().ecadk_set_splitk_force(bn, split), "set_splitk_force")
 
 
 def splitk_launches() -> int:

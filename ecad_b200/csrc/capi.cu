@@ -376,8 +376,29 @@ int launch_gemm_splitk_inst(const CUtensorMap& ta, const CUtensorMap& ta2, const
   return check_launch("gemm_splitk_kernel");
 }
 
-// Split-K plan for a small problem: (BN, split) with the smallest per-CTA operand stream, ~ (128 + BN) / split, whose
-// clusters are all resident at once and fit the workspace; split = 1 means "no split".
+// Split-K plan for a small problem.  A GEMM with fewer tiles than SMs is bound by ONE CTA's operand stream through its
+// SM's L2 port - (128 + BN) * (K / split) * 2 bytes at ~88 B/ns - plus ~3.2 us of fixed cost, not by MMAs, HBM or the
+// chip-wide L2 rate (tools/micro/small_gemm_cold_hot.py, M = 512, PDL-chained graph replays, weights cold / in L2):
+//     FF2  K = 4608:  BN 64 unsplit 19.6 / 18.4 us;  BN 64 x 2  12.8 / 12.2;  BN 128 x 3  12.2 / 11.4
+//     out  K = 1152:  BN 64 unsplit  8.2 /  7.7 us;  BN 64 x 2   7.1 /  6.8;  BN 128 x 3   8.1 /  7.6
+// The reduction costs ~1.3 us when every warp moves one chunk (BN 64 x 2) and ~2.7 us at BN 128 x 3 (three chunks out,
+// two partials in), which eats the smaller stream at K = 1152; BN 128 x 4 would stream a third of BN 64 x 2 but only 33
+// clusters of 4 are resident on 148 SMs (GPC granularity) and a tile row needs 36.  The plan therefore considers the
+// two-way splits only; ecadk_set_splitk_force overrides it (tests and measurements cover 3 and 4).
+struct SplitForce {
+  int bn, split;
+};
+SplitForce g_split_force = {0, 0};
+
+inline double splitk_cost_ns(int K, int bn, int split) {
+  return (128.0 + bn) * (static_cast<double>(K) / split) * 2.0 / 88.0 + (split > 1 ? 1300.0 : 0.0);
+}
+
+template <int EPI>
+int splitk_resident(int bn, int split) {
+  return bn == 128 ? splitk_max_clusters<128, EPI>(split) : splitk_max_clusters<64, EPI>(split);
+}
+
 template <int EPI>
 void plan_splitk(const GemmParams& p, int* bn_out, int* split_out) {
   *split_out = 1;
@@ -388,19 +409,35 @@ void plan_splitk(const GemmParams& p, int* bn_out, int* split_out) {
   if (!allow || g_split_ws.ptr == nullptr) return;
   const int m_tiles = (p.M + kGemmBM - 1) / kGemmBM;
   const int num_kb = p.K / kGemmBK;
-  const int cand[3][2] = {{128, 4}, {64, 2}, {128, 2}};
-  for (const auto& c : cand) {
-    const int bn = c[0], split = c[1];
-    if (p.N % bn != 0 || num_kb < 2 * split) continue;
+  if (2 * m_tiles * (p.N / 128) > num_sms()) return;  // enough 128-wide tiles for the ordinary kernels
+  auto feasible = [&](int bn, int split) {
+    if ((bn != 64 && bn != 128) || split < 2 || split > kSplitMax) return false;
+    if (p.N % bn != 0 || num_kb < 2 * split || (bn / 32) < split) return false;
     const int tiles = m_tiles * (p.N / bn);
-    if (2 * tiles > num_sms()) continue;  // enough tiles for the ordinary kernels
-    const size_t need = static_cast<size_t>(tiles) * split * bn * 128 * sizeof(float);
-    if (need > g_split_ws.bytes) continue;
-    const int resident = bn == 128 ? splitk_max_clusters<128, EPI>(split) : splitk_max_clusters<64, EPI>(split);
-    if (tiles > resident) continue;
-    *bn_out = bn;
-    *split_out = split;
+    if (static_cast<size_t>(tiles) * split * bn * 128 * sizeof(float) > g_split_ws.bytes) return false;
+    return tiles <= splitk_resident<EPI>(bn, split);
+  };
+  if (g_split_force.split != 0) {
+    if (feasible(g_split_force.bn, g_split_force.split)) {
+      *bn_out = g_split_force.bn;
+      *split_out = g_split_force.split;
+    }
     return;
+  }
+  double best = splitk_cost_ns(p.K, 64, 1);  // what the ordinary path would do with this problem (see launch_gemm)
+  const int cand[2][2] = {{64, 2}, {128, 2}};
+  for (const auto& c : cand) {
+    const double cost = splitk_cost_ns(p.K, c[0], c[1]);
+    if (cost >= best || !feasible(c[0], c[1])) continue;
+    best = cost;
+    *bn_out = c[0];
+    *split_out = c[1];
+  }
+  static const bool debug = getenv("ECADK_DEBUG_PLAN") != nullptr;
+  if (debug) {
+    fprintf(stderr, "[ecadk] gemm EPI %d M=%d N=%d K=%d -> BN=%d split=%d (resident clusters of 2/3/4: %d/%d/%d)\n", EPI,
+            p.M, p.N, p.K, *split_out > 1 ? *bn_out : 0, *split_out, splitk_resident<EPI>(128, 2),
+            splitk_resident<EPI>(128, 3), splitk_resident<EPI>(128, 4));
   }
 }
 
@@ -1504,6 +1541,13 @@ int ecadk_create(int device, const EcadkModelDesc* desc, const EcadkBlockWeights
 int ecadk_destroy(ecadk_handle_t h) {
   if (h != nullptr && h->split_ws != nullptr) cudaFree(h->split_ws);
   delete h;
+  return ECADK_OK;
+}
+
+int ecadk_set_splitk_force(int bn, int split) {
+  ECADK_REQUIRE((bn == 0 && split == 0) || ((bn == 64 || bn == 128) && split >= 2 && split <= kSplitMax),
+                "set_splitk_force: bn=%d split=%d (bn 64|128, split 2..%d, or 0, 0)", bn, split, kSplitMax);
+  g_split_force = SplitForce{bn, split};
   return ECADK_OK;
 }
 

@@ -591,15 +591,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
 // =====================================================================================================
 // Split-K variant for SMALL problems (the batch-1 latency configuration, M = 512 rows): a thread-block cluster of
-// S = 2 or 4 CTAs shares one 128 x BN output tile, CTA r multiplying the r-th slice of the K range.
+// S = 2, 3 or 4 CTAs shares one 128 x BN output tile, CTA r multiplying the r-th slice of the K range.
 //
 // Why: with fewer tiles than SMs a GEMM is one CTA's serial operand stream - 128 x K of A plus BN x K of W through a
 // single SM's ~64 B/clk L2 port (FF2 at M = 512: 1.8 MB per CTA, 21 us of a kernel whose MMAs take 2 us; 20 % of a
 // batch-1 generation, profiles/r2_launches_c1_batch1.md).  More, narrower tiles re-read A; more CTAs per tile divide
 // BOTH operand streams.
 //
-// Reduction = reduce-scatter through an L2-resident workspace: column chunk c (32 columns) of the tile is OWNED by
-// CTA c / (chunks / S).  After its MMAs every CTA writes the accumulator chunks it does not own to the workspace
+// Reduction = reduce-scatter through an L2-resident workspace: the tile's 32-column chunks are dealt out in contiguous
+// ranges, CTA r OWNING chunks [r * chunks / S, (r + 1) * chunks / S).  After its MMAs every CTA writes the accumulator chunks it does not own to the workspace
 // (fragment layout, one coalesced 512-byte store per warp instruction), the cluster barrier (release / acquire)
 // publishes them, and each CTA adds the S - 1 foreign partials of its own chunks into its TMEM accumulator
 // (tcgen05.ld + add + tcgen05.st) - after which the UNCHANGED epilogue functions run on the owned column range, so the
@@ -662,8 +662,8 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   const int quarter = warp & 3;
   const int par = (warp - 2) >> 2;
   const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-  const int per = kChunks / S;      // chunks owned by each CTA
-  const int own0 = rank * per;
+  const int own0 = rank * kChunks / S, own1 = (rank + 1) * kChunks / S;  // column chunks owned by this CTA
+  const int per = own1 - own0;
   float4* const ws_tile = ws + static_cast<size_t>(tile) * S * kChunks * 1024;
   if (warp == 0) {
     if (lane == 0) {
@@ -716,7 +716,7 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     mbar_wait(&tmem_full[0], 0);
     tc_fence_after();
     for (int c = par; c < kChunks; c += 2) {
-      if (c / per == rank) continue;
+      if (c >= own0 && c < own1) continue;
       uint32_t v[32];
       tmem_ld_32x32(t_row + c * 32, v);
       tmem_ld_wait();

@@ -49,29 +49,64 @@ __device__ __forceinline__ float warp_sum(float v) {
 // cache) are in flight per warp.
 constexpr int kRlnRowsPerBlock = 32;
 
-template <int VPL>
-__device__ __forceinline__ void rln_row(const ResidualLnParams& p, const float4* __restrict__ sm, const int row,
-                                        const int lane, float4 (&v)[VPL]) {
-  constexpr int D = 128 * VPL;
-  constexpr int DV = D / 4;
-  const size_t roff = static_cast<size_t>(row) * D;
-  if (p.n_reuse > 0) {
-    for (int r = 0; r < p.n_reuse; ++r) {
-      const uint2* cr = reinterpret_cast<const uint2*>(p.reuse[r].cache + roff);
-      const float4* g = sm + (2 + r) * DV;
-      uint2 c[VPL];
+// cached rows of reuse entries [r0, r0 + RB) of one token row, all requested before any is used
+template <int VPL, int RB>
+__device__ __forceinline__ void rln_load_reuse(const ResidualLnParams& p, const int r0, const int row, const int lane,
+                                               uint2 (&c)[RB][VPL]) {
+  const size_t roff = static_cast<size_t>(row) * (128 * VPL);
 #pragma unroll
-      for (int i = 0; i < VPL; ++i) c[i] = __ldg(cr + lane + 32 * i);
+  for (int u = 0; u < RB; ++u) {
+    if (r0 + u < p.n_reuse) {
+      const uint2* cr = reinterpret_cast<const uint2*>(p.reuse[r0 + u].cache + roff);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) c[u][i] = __ldg(cr + lane + 32 * i);
+    }
+  }
+}
+
+template <int VPL, int RB>
+__device__ __forceinline__ void rln_add_reuse(const ResidualLnParams& p, const float4* __restrict__ sm, const int r0,
+                                              const int lane, const uint2 (&c)[RB][VPL], float4 (&v)[VPL]) {
+  constexpr int DV = 32 * VPL;
+#pragma unroll
+  for (int u = 0; u < RB; ++u) {
+    if (r0 + u < p.n_reuse) {
+      const float4* g = sm + (2 + r0 + u) * DV;
 #pragma unroll
       for (int i = 0; i < VPL; ++i) {
-        const float2 c01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&c[i].x));
-        const float2 c23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&c[i].y));
+        const float2 c01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&c[u][i].x));
+        const float2 c23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&c[u][i].y));
         const float4 gg = g[lane + 32 * i];
         v[i].x = fmaf(gg.x, c01.x, v[i].x);
         v[i].y = fmaf(gg.y, c01.y, v[i].y);
         v[i].z = fmaf(gg.z, c23.x, v[i].z);
         v[i].w = fmaf(gg.w, c23.y, v[i].w);
       }
+    }
+  }
+}
+
+// RB = reuse entries whose cached rows are in flight together (1 in the streaming configuration, where many rows per
+// SM hide the latency; 3 in the small-batch one, where a row's reuse chain IS the kernel's latency: 6 serial round
+// trips made the batch-1 flush kernels 17-20 us instead of 4.5).  PRE: the first group was requested by the caller.
+template <int VPL, int RB = 1, bool PRE = false>
+__device__ __forceinline__ void rln_row(const ResidualLnParams& p, const float4* __restrict__ sm, const int row,
+                                        const int lane, float4 (&v)[VPL], uint2 (*pre)[VPL] = nullptr) {
+  constexpr int D = 128 * VPL;
+  constexpr int DV = D / 4;
+  const size_t roff = static_cast<size_t>(row) * D;
+  if (p.n_reuse > 0) {
+    for (int r = 0; r < p.n_reuse; r += RB) {
+      uint2 c[RB][VPL];
+      if (PRE && r == 0) {
+#pragma unroll
+        for (int u = 0; u < RB; ++u)
+#pragma unroll
+          for (int i = 0; i < VPL; ++i) c[u][i] = pre[u][i];
+      } else {
+        rln_load_reuse<VPL, RB>(p, r, row, lane, c);
+      }
+      rln_add_reuse<VPL, RB>(p, sm, r, lane, c, v);
     }
     float4* xw = reinterpret_cast<float4*>(p.x + roff);
 #pragma unroll
@@ -113,7 +148,7 @@ __device__ __forceinline__ void rln_row(const ResidualLnParams& p, const float4*
   }
 }
 
-template <int VPL>
+template <int VPL, int GB = 1>
 __device__ __forceinline__ void rln_stage_vectors(const ResidualLnParams& p, float4* rln_sm, const int sample) {
   constexpr int DV = 32 * VPL;
   for (int k = threadIdx.x; k < DV; k += blockDim.x) {
@@ -126,18 +161,29 @@ __device__ __forceinline__ void rln_stage_vectors(const ResidualLnParams& p, flo
       rln_sm[k] = make_float4(1.f + (ca.x + cb.x), 1.f + (ca.y + cb.y), 1.f + (ca.z + cb.z), 1.f + (ca.w + cb.w));
       rln_sm[DV + k] = make_float4(sa.x + sb.x, sa.y + sb.y, sa.z + sb.z, sa.w + sb.w);
     }
-    for (int r = 0; r < p.n_reuse; ++r) {
-      // gate = table + per-sample vector (PixArt adaLN-single), per-sample vector alone (FLUX), or 1 (no gate)
-      float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
-      if (p.reuse[r].gate_table != nullptr || p.reuse[r].gate_temb != nullptr) {
-        g = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.reuse[r].gate_table != nullptr) g = __ldg(reinterpret_cast<const float4*>(p.reuse[r].gate_table) + k);
-        if (p.reuse[r].gate_temb != nullptr) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(p.reuse[r].gate_temb + static_cast<size_t>(sample) * p.temb_stride) + k);
-          g = make_float4(g.x + b.x, g.y + b.y, g.z + b.z, g.w + b.w);
+    // gate = table + per-sample vector (PixArt adaLN-single), per-sample vector alone (FLUX), or 1 (no gate); the
+    // loads of GB reuse entries are in flight together
+    for (int r0 = 0; r0 < p.n_reuse; r0 += GB) {
+      float4 ga[GB], gb[GB];
+#pragma unroll
+      for (int u = 0; u < GB; ++u) {
+        ga[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+        gb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r0 + u < p.n_reuse) {
+          const ReuseEntry& e = p.reuse[r0 + u];
+          if (e.gate_table != nullptr || e.gate_temb != nullptr) {
+            ga[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e.gate_table != nullptr) ga[u] = __ldg(reinterpret_cast<const float4*>(e.gate_table) + k);
+            if (e.gate_temb != nullptr)
+              gb[u] = __ldg(reinterpret_cast<const float4*>(e.gate_temb + static_cast<size_t>(sample) * p.temb_stride) + k);
+          }
         }
       }
-      rln_sm[(2 + r) * DV + k] = g;
+#pragma unroll
+      for (int u = 0; u < GB; ++u) {
+        if (r0 + u < p.n_reuse)
+          rln_sm[(2 + r0 + u) * DV + k] = make_float4(ga[u].x + gb[u].x, ga[u].y + gb[u].y, ga[u].z + gb[u].z, ga[u].w + gb[u].w);
+      }
     }
   }
 }
@@ -154,7 +200,7 @@ __device__ __forceinline__ void rln_load_row(const ResidualLnParams& p, const in
 // four serial row-pairs per warp - 14 us per launch, 25 % of a batch-1 generation; 64 blocks of one row per warp
 // take the latency of a single HBM round trip).
 template <int VPL, int RPB = kRlnRowsPerBlock>
-__global__ void __launch_bounds__(256, (VPL <= 12) ? 2 : 1) residual_ln_kernel(const ResidualLnParams p) {
+__global__ void __launch_bounds__(256, (VPL <= 12 && RPB != 8) ? 2 : 1) residual_ln_kernel(const ResidualLnParams p) {
   extern __shared__ float4 rln_sm[];  // [(2 + n_reuse)][D/4]
   // programmatic dependent launch: a small grid releases the next kernel at once (its CTAs set up on idle SMs); a
   // multi-wave grid keeps the SM slots for its own blocks and lets the implicit trigger at exit do it
@@ -167,16 +213,26 @@ __global__ void __launch_bounds__(256, (VPL <= 12) ? 2 : 1) residual_ln_kernel(c
     float4 va[VPL];
     int ra = row0 + warp;
     if constexpr (RPB == 8) {
-      if (ra < p.M) rln_load_row<VPL>(p, ra, lane, va);  // requested before the vectors are staged
-    }
-    rln_stage_vectors<VPL>(p, rln_sm, sample);
-    __syncthreads();
+      // one row per warp, once: the row and its first three cached rows are requested before the vectors are staged
+      constexpr int RB = VPL <= 12 ? 3 : 1;
+      uint2 pre[RB][VPL];
+      if (ra < p.M) {
+        rln_load_row<VPL>(p, ra, lane, va);
+        rln_load_reuse<VPL, RB>(p, 0, ra, lane, pre);
+      }
+      rln_stage_vectors<VPL, 4>(p, rln_sm, sample);
+      __syncthreads();
+      if (ra < p.M) rln_row<VPL, RB, true>(p, rln_sm, ra, lane, va, pre);
+    } else {
+      rln_stage_vectors<VPL>(p, rln_sm, sample);
+      __syncthreads();
 #pragma unroll 1
-    for (int j = 0; j < RPB / 8; ++j) {
-      ra = row0 + warp + 8 * j;
-      if (ra >= p.M) break;
-      if constexpr (RPB != 8) rln_load_row<VPL>(p, ra, lane, va);
-      rln_row<VPL>(p, rln_sm, ra, lane, va);
+      for (int j = 0; j < RPB / 8; ++j) {
+        ra = row0 + warp + 8 * j;
+        if (ra >= p.M) break;
+        rln_load_row<VPL>(p, ra, lane, va);
+        rln_row<VPL>(p, rln_sm, ra, lane, va);
+      }
     }
   } else {
     // rows row0 + warp + 8*j, two in flight per warp; the first pair is requested BEFORE the modulation vectors are

@@ -136,6 +136,10 @@ int ecadk_cfg_dpm_step(const float* noise, float* latents, float* x0_prev, int b
  * NULL / 0 removes it.  Without a workspace the GEMMs do not split.  Same results up to fp32 summation order.
  * No reference counterpart (torch.nn.Linear -> cuBLAS picks its own split-K). */
 int ecadk_set_splitk_workspace(void* workspace, size_t bytes);
+/* Measurements and tests: force the split-K plan to tiles of `bn` (64 | 128) columns shared by `split` (2..4) CTAs
+ * wherever that plan is feasible (all clusters resident, workspace large enough; otherwise no split); 0, 0 restores
+ * the planner.  Process-wide. */
+int ecadk_set_splitk_force(int bn, int split);
 /* Process-wide number of split-K GEMM launches so far (tests and the bench use it to show which kernel ran). */
 long long ecadk_splitk_launches(void);
 

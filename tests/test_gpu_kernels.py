@@ -23,25 +23,39 @@ def _bf(t):
     return t.to(torch.bfloat16)
 
 
-@pytest.fixture(params=[False, True], ids=["plain", "splitk"])
+@pytest.fixture(params=[None, "plan", (128, 2), (128, 3), (128, 4)],
+                ids=["plain", "splitk", "splitk128x2", "splitk128x3", "splitk128x4"])
 def splitk(request, cuda_device):
-    """Run a GEMM test twice: without and with a split-K workspace installed (small problems then take the cluster
-    split-K kernel; the large shapes of the same test stay on the ordinary kernels either way)."""
+    """Run a GEMM test without and with a split-K workspace installed (small problems then take the cluster split-K
+    kernel; the large shapes of the same test stay on the ordinary kernels either way), and with the plan forced to
+    3- and 4-way splits of 128-wide tiles (taken wherever all clusters are resident)."""
     from ecad_b200 import _lib
-    if not request.param:
+    if request.param is None:
         _lib.set_splitk_workspace(None)
-        yield False
+        yield None
         return
     ws = torch.empty(16 << 20, dtype=torch.uint8, device="cuda")
     _lib.set_splitk_workspace(ws)
-    yield True
+    if request.param != "plan":
+        _lib.set_splitk_force(*request.param)
+    yield request.param
     torch.cuda.synchronize()
+    _lib.set_splitk_force(0, 0)
     _lib.set_splitk_workspace(None)
 
 
-# shapes the split-K planner takes (fewer than half as many 128-wide tiles as SMs): (m, n) -> expected
+# shapes the split-K planner takes: fewer than half as many 128-wide tiles as SMs
 def _splits(m, n):
     return 2 * ((m + 127) // 128) * (n // 128) <= 148
+
+
+def _check_split_count(splitk, launched, m, n):
+    if splitk is None:
+        assert launched == 0
+    elif splitk == "plan":
+        assert launched == (1 if _splits(m, n) else 0)
+    elif ((m + 127) // 128) * (n // 128) <= 30:  # forced plan: every cluster of up to 4 is resident for <= 30 tiles
+        assert launched == 1
 
 
 @pytest.mark.parametrize("m,n,k", [(512, 1152, 1152), (384, 4608, 1152), (1000, 2304, 1152), (256, 1152, 4608),
@@ -57,7 +71,7 @@ def test_gemm_bias(cuda_device, splitk, m, n, k, gelu):
     out = torch.full((m, n), float("nan"), device="cuda", dtype=torch.bfloat16)
     _lib.gemm_bias(a, w, bias, out, gelu=gelu)
     torch.cuda.synchronize()
-    assert _lib.splitk_launches() - n_split0 == (1 if splitk and _splits(m, n) else 0)
+    _check_split_count(splitk, _lib.splitk_launches() - n_split0, m, n)
     ref = a.float() @ w.float().T + bias
     if gelu:
         ref = torch.nn.functional.gelu(ref, approximate="tanh")
@@ -88,7 +102,7 @@ def test_gemm_gated_residual_cache(cuda_device, splitk, samples, tokens, k, gate
                              gate_table=table[2] if gated else None,
                              gate_temb=temb[:, 2 * D:] if gated else None, temb_stride=6 * D)
     torch.cuda.synchronize()
-    assert _lib.splitk_launches() - n_split0 == (1 if splitk and _splits(m, D) else 0)
+    _check_split_count(splitk, _lib.splitk_launches() - n_split0, m, D)
     o = a.float() @ w.float().T + bias
     gate = (table[2][None] + temb[:, 2 * D:3 * D]).repeat_interleave(tokens, dim=0) if gated else 1.0
     x_ref = x0 + gate * o
