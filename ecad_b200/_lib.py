@@ -55,6 +55,14 @@ EXPORTED_SYMBOLS = [
     "ecadk_flux_create",
     "ecadk_flux_destroy",
     "ecadk_flux_blocks",
+    "ecadk_conv_nhwc",
+    "ecadk_groupnorm_nhwc",
+    "ecadk_groupnorm_scratch_bytes",
+    "ecadk_upsample2x_nhwc",
+    "ecadk_softmax_rows",
+    "ecadk_vae_prepare_latents",
+    "ecadk_vae_add_tokens",
+    "ecadk_vae_finish",
     "ecadk_profile_start",
     "ecadk_profile_stop",
 ]
@@ -224,6 +232,14 @@ def load() -> C.CDLL:
                               C.POINTER(EcadkFluxSingleWeights), C.POINTER(p)],
         "ecadk_flux_destroy": [p],
         "ecadk_flux_blocks": [p, C.POINTER(EcadkFluxArgs), C.POINTER(C.c_uint8), C.POINTER(i), p],
+        "ecadk_conv_nhwc": [p, p, p, p, p, i, i, i, i, i, i, i, i, p],
+        "ecadk_groupnorm_nhwc": [p, p, p, p, p, i, i, i, i, i, f, i, i, p],
+        "ecadk_groupnorm_scratch_bytes": [i, i, i, i],
+        "ecadk_upsample2x_nhwc": [p, p, i, i, i, i, p],
+        "ecadk_softmax_rows": [p, p, i, i, f, p],
+        "ecadk_vae_prepare_latents": [p, p, p, f, p, i, i, i, p],
+        "ecadk_vae_add_tokens": [p, p, p, i, i, i, i, p],
+        "ecadk_vae_finish": [p, p, i, i, i, i, p],
         "ecadk_profile_start": [],
         "ecadk_profile_stop": [C.POINTER(EcadkProfileRecord)],
     }
@@ -232,6 +248,7 @@ def load() -> C.CDLL:
         fn.argtypes = argtypes
         fn.restype = C.c_int
     lib.ecadk_splitk_launches.restype = C.c_longlong
+    lib.ecadk_groupnorm_scratch_bytes.restype = C.c_size_t
     if lib.ecadk_abi_version() != 1:
         raise RuntimeError(f"libecad_b200.so ABI version {lib.ecadk_abi_version()} != 1")
     _lib = lib
@@ -288,6 +305,55 @@ def attention(q, k, v, bias, out, samples, heads, q_tokens, n_keys):
     check(load().ecadk_attention(ptr(q), ptr(k), ptr(v), ptr(bias), ptr(out), samples, heads, q_tokens, n_keys,
                                  stream_ptr()), "attention")
     return out
+
+
+def conv_nhwc(x, w, bias, out, h, w_, taps, residual=None, out_cols=None):
+    """x bordered NHWC bf16 [B, h+2, w_+2, c_in]; w bf16 [c_out, taps*c_in]; out [B, h+2, w_+2, out_ld]."""
+    batch, c_in = x.shape[0], x.shape[-1]
+    c_out = w.shape[0]
+    check(load().ecadk_conv_nhwc(ptr(x), ptr(w), ptr(bias), ptr(residual), ptr(out), batch, h, w_, c_in, c_out,
+                                 out.shape[-1], c_out if out_cols is None else out_cols, taps, stream_ptr()), "conv_nhwc")
+    return out
+
+
+def groupnorm_nhwc(x, gamma, beta, out, scratch, h, w_, groups=32, eps=1e-6, silu=True, unpadded_out=False):
+    batch, c = x.shape[0], x.shape[-1]
+    check(load().ecadk_groupnorm_nhwc(ptr(x), ptr(gamma), ptr(beta), ptr(out), ptr(scratch), batch, h, w_, c, groups,
+                                      eps, int(silu), int(unpadded_out), stream_ptr()), "groupnorm_nhwc")
+    return out
+
+
+def groupnorm_scratch_bytes(batch, h, w_, groups=32) -> int:
+    return int(load().ecadk_groupnorm_scratch_bytes(batch, h, w_, groups))
+
+
+def upsample2x_nhwc(x, out, h, w_):
+    check(load().ecadk_upsample2x_nhwc(ptr(x), ptr(out), x.shape[0], h, w_, x.shape[-1], stream_ptr()), "upsample2x_nhwc")
+    return out
+
+
+def softmax_rows(scores, probs, scale):
+    rows, cols = scores.shape
+    check(load().ecadk_softmax_rows(ptr(scores), ptr(probs), rows, cols, scale, stream_ptr()), "softmax_rows")
+    return probs
+
+
+def vae_prepare_latents(z, pq_w, pq_b, inv_scaling, out):
+    batch, _, h, w_ = z.shape
+    check(load().ecadk_vae_prepare_latents(ptr(z), ptr(pq_w), ptr(pq_b), inv_scaling, ptr(out), batch, h, w_,
+                                           stream_ptr()), "vae_prepare_latents")
+    return out
+
+
+def vae_add_tokens(x, tokens, out, h, w_):
+    check(load().ecadk_vae_add_tokens(ptr(x), ptr(tokens), ptr(out), x.shape[0], h, w_, x.shape[-1], stream_ptr()),
+          "vae_add_tokens")
+    return out
+
+
+def vae_finish(y, image, h, w_, denormalize=False):
+    check(load().ecadk_vae_finish(ptr(y), ptr(image), image.shape[0], h, w_, int(denormalize), stream_ptr()), "vae_finish")
+    return image
 
 
 def set_splitk_workspace(buf):

@@ -18,6 +18,7 @@
 #include "attn.cuh"
 #include "gemm.cuh"
 #include "glue.cuh"
+#include "vae.cuh"
 
 namespace {
 
@@ -519,7 +520,9 @@ int launch_gemm(const void* a, const void* w, GemmParams& p, cudaStream_t stream
     if ((rc = make_tmap_bf16(&ta2, p.a2, p.M, p.K - p.k1, p.K - p.k1, kGemmBM, kGemmBK, 128))) return rc;
     p.kb_split = p.k1 / kGemmBK;
   } else {
-    if ((rc = make_tmap_bf16(&ta, a, p.M, p.K, p.K, kGemmBM, kGemmBK, 128))) return rc;
+    // implicit-GEMM convolution: the A matrix is the bordered NHWC image [M, C], K = taps * C (see GemmParams)
+    const int a_cols = p.conv_taps > 1 ? p.K / p.conv_taps : p.K;
+    if ((rc = make_tmap_bf16(&ta, a, p.M, a_cols, a_cols, kGemmBM, kGemmBK, 128))) return rc;
     ta2 = ta;
     p.kb_split = p.K / kGemmBK;
   }
@@ -1722,6 +1725,136 @@ int ecadk_pixart_blocks_range(ecadk_handle_t h, const EcadkBlocksArgs* a, const 
   if ((rc = flush())) return rc;
   if (n_launches) *n_launches = launches;
   return ECADK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// VAE decoder pieces (vae.cuh + the implicit-GEMM mode of the tcgen05 GEMMs)
+// ---------------------------------------------------------------------------------------------------
+int ecadk_conv_nhwc(const void* x, const void* w, const float* bias, const void* residual, void* out, int batch, int h,
+                    int w_, int c_in, int c_out, int out_ld, int out_cols, int taps, ecadk_stream_t stream) {
+  ECADK_REQUIRE(x && w && out, "conv_nhwc: null pointer");
+  ECADK_REQUIRE(batch > 0 && h > 0 && w_ > 0, "conv_nhwc: bad image size %d x %d x %d", batch, h, w_);
+  ECADK_REQUIRE(taps == 1 || taps == 9, "conv_nhwc: taps=%d (1 = 1x1, 9 = 3x3)", taps);
+  ECADK_REQUIRE(c_in > 0 && c_in % 64 == 0, "conv_nhwc: c_in=%d must be a multiple of 64 (pad with zero channels)", c_in);
+  ECADK_REQUIRE(c_out > 0 && c_out % 128 == 0, "conv_nhwc: c_out=%d must be a multiple of 128 (pad the weight rows)", c_out);
+  ECADK_REQUIRE(out_cols > 0 && out_cols <= c_out && out_ld % 8 == 0 && out_ld >= ((out_cols + 31) / 32) * 32,
+                "conv_nhwc: out_cols=%d out_ld=%d", out_cols, out_ld);
+  ECADK_REQUIRE(aligned16(out) && (residual == nullptr || aligned16(residual)), "conv_nhwc: 16-byte alignment");
+  const long long rows = static_cast<long long>(batch) * (h + 2) * (w_ + 2);
+  ECADK_REQUIRE(rows < (1ll << 31), "conv_nhwc: %lld rows", rows);
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = static_cast<int>(rows);
+  p.N = c_out;
+  p.K = taps * c_in;
+  p.bias = bias;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.ldo = out_ld;
+  p.out2 = static_cast<__nv_bfloat16*>(const_cast<void*>(residual));
+  p.ldo2 = out_ld;
+  p.tokens = 1;
+  p.conv_taps = taps;
+  p.conv_cblocks = c_in / kGemmBK;
+  p.conv_pitch = w_ + 2;
+  p.conv_h = h;
+  p.conv_w = w_;
+  p.conv_cols = out_cols;
+  return launch_gemm<EPI_CONV>(x, w, p, static_cast<cudaStream_t>(stream));
+}
+
+size_t ecadk_groupnorm_scratch_bytes(int batch, int h, int w_, int groups) {
+  const long long plane = static_cast<long long>(h + 2) * (w_ + 2);
+  const long long blocks = (plane + kGnPixelsPerBlock - 1) / kGnPixelsPerBlock;
+  return static_cast<size_t>(batch) * groups * sizeof(float2) * static_cast<size_t>(blocks + 1);
+}
+
+int ecadk_groupnorm_nhwc(const void* x, const float* gamma, const float* beta, void* out, void* scratch, int batch, int h,
+                         int w_, int c, int groups, float eps, int silu, int unpadded_out, ecadk_stream_t stream_) {
+  ECADK_REQUIRE(x && gamma && beta && out && scratch, "groupnorm_nhwc: null pointer");
+  ECADK_REQUIRE(batch > 0 && h > 0 && w_ > 0 && c > 0 && groups > 0 && c % groups == 0, "groupnorm_nhwc: bad shape");
+  const int cpg = c / groups;
+  ECADK_REQUIRE(cpg == 4 || cpg == 8 || cpg == 16, "groupnorm_nhwc: %d channels per group (supported: 4, 8, 16)", cpg);
+  ECADK_REQUIRE(c % 8 == 0 && c <= 2048 && 256 % (c / 8) == 0, "groupnorm_nhwc: c=%d", c);
+  ECADK_REQUIRE(aligned16(x) && aligned16(out) && aligned16(scratch) && aligned16(gamma) && aligned16(beta),
+                "groupnorm_nhwc: 16-byte alignment");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const long long plane = static_cast<long long>(h + 2) * (w_ + 2);
+  ProfScope prof(ECADK_PROF_OTHER, 0.0, 3.0 * batch * h * w_ * c * 2.0, stream);
+  const int blocks = static_cast<int>((plane + kGnPixelsPerBlock - 1) / kGnPixelsPerBlock);
+  GroupNormParams p;
+  p.x = static_cast<const __nv_bfloat16*>(x);
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.gamma = gamma;
+  p.beta = beta;
+  p.mean_rstd = static_cast<float2*>(scratch);
+  p.partial = p.mean_rstd + static_cast<size_t>(batch) * groups;
+  p.B = batch; p.H = h; p.W = w_; p.C = c; p.G = groups;
+  p.blocks = blocks;
+  p.eps = eps;
+  p.silu = silu;
+  p.unpadded_out = unpadded_out;
+  dim3 sgrid(blocks, batch);
+  gn_stats_kernel<<<sgrid, 256, 256 * 4 * sizeof(float), stream>>>(p);
+  gn_finalize_kernel<<<(batch * groups + 255) / 256, 256, 0, stream>>>(p);
+  const long long total = static_cast<long long>(batch) * plane * (c / 8);
+  gn_apply_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(p);
+  return check_launch("groupnorm_nhwc");
+}
+
+int ecadk_upsample2x_nhwc(const void* x, void* out, int batch, int h, int w_, int c, ecadk_stream_t stream_) {
+  ECADK_REQUIRE(x && out && batch > 0 && h > 0 && w_ > 0 && c > 0 && c % 8 == 0, "upsample2x_nhwc: bad arguments");
+  ECADK_REQUIRE(aligned16(x) && aligned16(out), "upsample2x_nhwc: 16-byte alignment");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ProfScope prof(ECADK_PROF_OTHER, 0.0, 5.0 * batch * h * w_ * c * 2.0, stream);
+  UpsampleParams p{static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), batch, h, w_, c};
+  const long long total = static_cast<long long>(batch) * (2 * h + 2) * (2 * w_ + 2) * (c / 8);
+  upsample2x_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(p);
+  return check_launch("upsample2x_kernel");
+}
+
+int ecadk_softmax_rows(const float* scores, void* probs, int rows, int cols, float scale, ecadk_stream_t stream_) {
+  ECADK_REQUIRE(scores && probs && rows > 0 && cols > 0 && cols % 4 == 0, "softmax_rows: bad arguments");
+  ECADK_REQUIRE(aligned16(scores) && aligned16(probs), "softmax_rows: 16-byte alignment");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ProfScope prof(ECADK_PROF_OTHER, 0.0, 6.0 * rows * cols, stream);
+  softmax_rows_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(scores, static_cast<__nv_bfloat16*>(probs), rows, cols,
+                                                         scale * 1.4426950408889634f);
+  return check_launch("softmax_rows_kernel");
+}
+
+int ecadk_vae_prepare_latents(const float* z, const float* pq_w, const float* pq_b, float inv_scaling, void* out,
+                              int batch, int h, int w_, ecadk_stream_t stream_) {
+  ECADK_REQUIRE(z && pq_w && pq_b && out && batch > 0 && h > 0 && w_ > 0, "vae_prepare_latents: bad arguments");
+  ECADK_REQUIRE(aligned16(out), "vae_prepare_latents: 16-byte alignment");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ProfScope prof(ECADK_PROF_OTHER, 0.0, 0.0, stream);
+  VaePrepParams p{z, pq_w, pq_b, static_cast<__nv_bfloat16*>(out), batch, h, w_, inv_scaling};
+  const long long total = static_cast<long long>(batch) * (h + 2) * (w_ + 2) * 8;
+  vae_prepare_latents_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(p);
+  return check_launch("vae_prepare_latents_kernel");
+}
+
+int ecadk_vae_add_tokens(const void* x, const void* tokens, void* out, int batch, int h, int w_, int c,
+                         ecadk_stream_t stream_) {
+  ECADK_REQUIRE(x && tokens && out && batch > 0 && h > 0 && w_ > 0 && c > 0 && c % 8 == 0, "vae_add_tokens: bad arguments");
+  ECADK_REQUIRE(aligned16(x) && aligned16(tokens) && aligned16(out), "vae_add_tokens: 16-byte alignment");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ProfScope prof(ECADK_PROF_OTHER, 0.0, 0.0, stream);
+  AddTokensParams p{static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(tokens),
+                    static_cast<__nv_bfloat16*>(out), batch, h, w_, c};
+  const long long total = static_cast<long long>(batch) * (h + 2) * (w_ + 2) * (c / 8);
+  vae_add_tokens_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(p);
+  return check_launch("vae_add_tokens_kernel");
+}
+
+int ecadk_vae_finish(const void* y, float* image, int batch, int h, int w_, int denormalize, ecadk_stream_t stream_) {
+  ECADK_REQUIRE(y && image && batch > 0 && h > 0 && w_ > 0, "vae_finish: bad arguments");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ProfScope prof(ECADK_PROF_OTHER, 0.0, 0.0, stream);
+  VaeFinishParams p{static_cast<const __nv_bfloat16*>(y), image, batch, h, w_, denormalize};
+  const long long total = static_cast<long long>(batch) * h * w_;
+  vae_finish_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(p);
+  return check_launch("vae_finish_kernel");
 }
 
 }  // extern "C"

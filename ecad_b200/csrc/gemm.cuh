@@ -22,6 +22,7 @@ enum GemmEpilogue : int {
   EPI_UNPATCHIFY = 4,      // fp32 out[s][c][2i+p][2j+q] = acc + bias for the first unp_cols columns (final layer)
   EPI_BIAS_F32 = 5,        // fp32 out[row, col] = acc + bias for col < f32_cols, row pitch ldo (embedders, FLUX head)
   EPI_BIAS_DUAL = 6,       // o = acc + bias; out = bf16(o) (optional: the pre-activation cache); out2 = bf16(gelu_tanh(o))
+  EPI_CONV = 7,            // out = bf16(acc + bias (+ residual)) on interior pixels of a zero-bordered NHWC image, 0 on the border
 };
 
 struct GemmParams {
@@ -52,6 +53,14 @@ struct GemmParams {
   // EPI_BIAS_F32
   float* f32_out;
   int f32_cols;
+  // Implicit-GEMM convolution (VAE decoder): A is a zero-bordered NHWC image [batch, H+2, W+2, C] seen as a matrix
+  // [M = batch*(H+2)*(W+2), C]; k-block kb covers tap kb / conv_cblocks (ky*3 + kx) and channels 64*(kb % conv_cblocks),
+  // its A rows are the output rows shifted by (ky-1)*conv_pitch + (kx-1) - a plain 2-D TMA load at a shifted row
+  // coordinate (rows outside the matrix are zero-filled).  W is [N, taps*C], tap-major.  conv_taps <= 1: ordinary GEMM.
+  int conv_taps, conv_cblocks, conv_pitch;
+  // EPI_CONV: border mask from (conv_h, conv_w); optional bf16 residual [M, ldo2] in out2; only chunks that start
+  // below conv_cols are stored (conv_out: 3 real output channels in a 32-column buffer)
+  int conv_h, conv_w, conv_cols;
   // EPI_UNPATCHIFY (column o = (p*2+q)*C + c of token n = i*Wp + j of sample s)
   float* unp_out;
   int unp_wp, unp_hp, unp_c, unp_cols;
@@ -81,6 +90,18 @@ __host__ __device__ constexpr int epi_stage_bytes(int epi) {
 __host__ __device__ constexpr int fit_stages(int want, int stage_bytes, int epi) {
   const int room = (kSmemLimit - epi_stage_bytes(epi) - 1024 - 256) / stage_bytes;
   return want < room ? want : room;
+}
+
+// TMA coordinates (column, row) of the A tile of k-block kb for output rows starting at m0 (see GemmParams::conv_taps)
+__device__ __forceinline__ void a_tile_coords(const GemmParams& p, const int kb, const int m0, int& col, int& row) {
+  col = kb * kGemmBK;
+  row = m0;
+  if (p.conv_taps > 1) {
+    const int tap = kb / p.conv_cblocks;
+    const int ky = tap / 3, kx = tap - 3 * ky;
+    col = (kb - tap * p.conv_cblocks) * kGemmBK;
+    row = m0 + (ky - 1) * p.conv_pitch + (kx - 1);
+  }
 }
 
 template <int BN, int EPI = 0>
@@ -114,6 +135,17 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
   int row_off[8];  // EPI_HEADMAJOR: element offset of (sample, token) inside one head-major tensor, head 0
   int sample0 = 0;
   if constexpr (EPI == EPI_GATED_RESIDUAL) sample0 = row_base / p.tokens;  // tokens % 32 == 0: one sample per chunk
+  uint32_t interior = 0;  // EPI_CONV: bit i = row i*4 + rs of this lane is an interior pixel of its image
+  if constexpr (EPI == EPI_CONV) {
+    const int plane = (p.conv_h + 2) * (p.conv_w + 2);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = row_base + i * 4 + rs;
+      const int r = row % plane;
+      const int y = r / (p.conv_w + 2), x = r - y * (p.conv_w + 2);
+      if (y >= 1 && y <= p.conv_h && x >= 1 && x <= p.conv_w) interior |= 1u << i;
+    }
+  }
   if constexpr (EPI == EPI_HEADMAJOR) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -226,6 +258,19 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
           w.x = pack_bf16x2(o.x, o.y);
           w.y = pack_bf16x2(o.z, o.w);
           *reinterpret_cast<uint2*>(hm_base + row_off[i] + hm_off) = w;
+        } else if constexpr (EPI == EPI_CONV) {
+          if (p.out2 != nullptr) {  // residual branch of the ResNet block, same layout
+            const uint2 rv = *reinterpret_cast<const uint2*>(p.out2 + static_cast<size_t>(row) * p.ldo2 + col);
+            const float2 r01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rv.x));
+            const float2 r23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rv.y));
+            o.x += r01.x; o.y += r01.y; o.z += r23.x; o.w += r23.y;
+          }
+          uint2 w = make_uint2(0u, 0u);  // border pixels stay zero: they are the next convolution's padding
+          if ((interior >> i) & 1u) {
+            w.x = pack_bf16x2(o.x, o.y);
+            w.y = pack_bf16x2(o.z, o.w);
+          }
+          *reinterpret_cast<uint2*>(p.out + static_cast<size_t>(row) * p.ldo + col) = w;
         } else if constexpr (EPI == EPI_BIAS_F32) {
           if (col < p.f32_cols) *reinterpret_cast<float4*>(p.f32_out + static_cast<size_t>(row) * p.ldo + col) = o;
         } else {  // EPI_UNPATCHIFY: 4 consecutive columns = 4 channels of one (p, q) sub-pixel
@@ -250,6 +295,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
   int limit = n_chunks;  // chunks past the real output columns of the zero-padded heads carry nothing to store
   if constexpr (EPI == EPI_UNPATCHIFY) limit = min(n_chunks, (p.unp_cols - n0 + 31) / 32);
   if constexpr (EPI == EPI_BIAS_F32) limit = min(n_chunks, (p.f32_cols - n0 + 31) / 32);
+  if constexpr (EPI == EPI_CONV) limit = max(0, min(n_chunks, (p.conv_cols - n0 + 31) / 32));
   // Chunk assignment: the two warps of a lane quarter split the tile's columns into two CONTIGUOUS halves (ECADK_EPI_
   // INTERLEAVE=1 at build time restores the every-second-chunk split): a warp then walks adjacent 128-byte pieces of
   // the same 32 rows, which keeps its DRAM pages open across iterations.
@@ -498,7 +544,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           uint8_t* sb = sa + Cfg::kStageA;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStage);
           if (kb < p.kb_split) {
-            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kGemmBK, m0);
+            int a_col, a_row;
+            a_tile_coords(p, kb, m0, a_col, a_row);
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], a_col, a_row);
           } else {
             tma_load_2d(sa, &tmap_a2, &full_bar[stage], (kb - p.kb_split) * kGemmBK, m0);
           }
@@ -676,7 +724,9 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         uint8_t* sb = sa + Cfg::kStageA;
         mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStage);
         if (kb < p.kb_split) {
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kGemmBK, m0);
+          int a_col, a_row;
+          a_tile_coords(p, kb, m0, a_col, a_row);
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], a_col, a_row);
         } else {
           tma_load_2d(sa, &tmap_a2, &full_bar[stage], (kb - p.kb_split) * kGemmBK, m0);
         }
@@ -882,7 +932,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           uint8_t* sb = sa + Cfg::kStageA;
           if (cta == 0) mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
           if (kb < p.kb_split) {
-            tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], kb * kGemmBK, m0);
+            int a_col, a_row;
+            a_tile_coords(p, kb, m0, a_col, a_row);
+            tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], a_col, a_row);
           } else {
             tma_load_2d_2sm(sa, &tmap_a2, &full_bar[stage], (kb - p.kb_split) * kGemmBK, m0);
           }

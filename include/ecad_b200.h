@@ -123,6 +123,53 @@ int ecadk_cfg_dpm_step(const float* noise, float* latents, float* x0_prev, int b
                        ecadk_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * VAE decoder (AutoencoderKL.decode of the reference's pipelines: `image = self.vae.decode(latents /
+ * self.vae.config.scaling_factor)`, ecad/pipelines/pass_through.py:382-385; the module itself is diffusers').
+ * Activation layout: ZERO-BORDERED NHWC bf16 [batch, h+2, w+2, c] - the border is the padding of the 3x3
+ * convolutions; every entry point below that writes such a tensor writes zeros on the border.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* Convolution as an implicit GEMM on the tensor cores: out[pixel, :] = bias + sum_taps x[pixel + tap] * W_tap^T
+ * (+ residual[pixel, :]) on interior pixels, 0 on the border.  taps = 9: 3x3, stride 1, padding 1; taps = 1: 1x1.
+ * x bf16 [batch, h+2, w+2, c_in] (c_in % 64 == 0); w bf16 [c_out, taps*c_in], K index = (ky*3 + kx)*c_in + c
+ * (c_out % 128 == 0: pad the rows); bias fp32 [c_out] or NULL; residual bf16, same layout as out, or NULL;
+ * out bf16 with row pitch out_ld; only 32-column chunks that start below out_cols are written.
+ * Replaces torch.nn.Conv2d inside diffusers ResnetBlock2D / Upsample2D / Decoder.conv_in / conv_out. */
+int ecadk_conv_nhwc(const void* x, const void* w, const float* bias, const void* residual, void* out, int batch, int h,
+                    int w_, int c_in, int c_out, int out_ld, int out_cols, int taps, ecadk_stream_t stream);
+
+/* GroupNorm (biased variance, eps inside the sqrt) + affine (+ SiLU when silu != 0) over a bordered NHWC tensor.
+ * channels per group in {4, 8, 16}.  unpadded_out != 0 writes plain tokens [batch, h*w, c] instead (the input of the
+ * mid-block attention).  scratch: >= ecadk_groupnorm_scratch_bytes(...) bytes, 16-byte aligned (per-block partial
+ * sums: every reduction runs in a fixed order, so the result is bit-reproducible).
+ * Replaces torch.nn.GroupNorm + SiLU (ResnetBlock2D.norm1/norm2, Decoder.conv_norm_out, Attention.group_norm). */
+size_t ecadk_groupnorm_scratch_bytes(int batch, int h, int w_, int groups);
+int ecadk_groupnorm_nhwc(const void* x, const float* gamma, const float* beta, void* out, void* scratch, int batch, int h,
+                         int w_, int c, int groups, float eps, int silu, int unpadded_out, ecadk_stream_t stream);
+
+/* Nearest-neighbour 2x upsampling: x [batch, h+2, w+2, c] -> out [batch, 2h+2, 2w+2, c].
+ * Replaces F.interpolate(scale_factor=2, mode="nearest") in Upsample2D. */
+int ecadk_upsample2x_nhwc(const void* x, void* out, int batch, int h, int w_, int c, ecadk_stream_t stream);
+
+/* probs bf16 [rows, cols] = softmax(scale * scores fp32 [rows, cols]) along each row (cols % 4 == 0).
+ * Replaces the softmax inside F.scaled_dot_product_attention of the single-head mid-block attention. */
+int ecadk_softmax_rows(const float* scores, void* probs, int rows, int cols, float scale, ecadk_stream_t stream);
+
+/* latents fp32 [batch, 4, h, w] -> post_quant_conv(z * inv_scaling) as bordered NHWC bf16 [batch, h+2, w+2, 64]
+ * (channels 4..63 zero: the operand of conv_in).  pq_w fp32 [4, 4] (out, in), pq_b fp32 [4].
+ * Replaces `latents / scaling_factor` + AutoencoderKL.post_quant_conv. */
+int ecadk_vae_prepare_latents(const float* z, const float* pq_w, const float* pq_b, float inv_scaling, void* out,
+                              int batch, int h, int w_, ecadk_stream_t stream);
+
+/* out (bordered) = x (bordered) + tokens [batch, h*w, c]: the residual connection of the mid-block attention. */
+int ecadk_vae_add_tokens(const void* x, const void* tokens, void* out, int batch, int h, int w_, int c,
+                         ecadk_stream_t stream);
+
+/* y bf16 [batch*(h+2)*(w+2), 32] (conv_out: channels 0..2 real) -> image fp32 [batch, 3, h, w];
+ * denormalize != 0 applies (x / 2 + 0.5).clamp(0, 1) (VaeImageProcessor.postprocess). */
+int ecadk_vae_finish(const void* y, float* image, int batch, int h, int w_, int denormalize, ecadk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Dense contractions (tcgen05 / TMEM / TMA)
  * All GEMMs: C[M,N] = A[M,K] * W[N,K]^T + bias;  A, W bf16 row-major (K contiguous, pitch = K), bias fp32 [N].
  * Requirements: K % 64 == 0, N % 128 == 0, pointers 16-byte aligned.

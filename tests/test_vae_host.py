@@ -1,0 +1,80 @@
+"""CPU checks of the VAE oracle and of the host-side weight packing (no GPU)."""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from ecad_b200.vae import B200VaeDecoder, VaeConfig, decoder_layer_names, random_init_vae_state_dict
+from oracle.vae_oracle import OracleVaeConfig, vae_decode
+
+
+def test_decoder_parameter_inventory():
+    names = decoder_layer_names()
+    # SD VAE decoder: 1 + 1 convs, 2 + 12 resnets (2 with a shortcut), 3 upsampler convs, 1 attention, out norm + conv
+    assert names["decoder.conv_in.weight"] == (512, 4, 3, 3)
+    assert names["decoder.conv_out.weight"] == (3, 128, 3, 3)
+    assert names["decoder.up_blocks.2.resnets.0.conv_shortcut.weight"] == (256, 512, 1, 1)
+    assert names["decoder.up_blocks.3.resnets.0.conv_shortcut.weight"] == (128, 256, 1, 1)
+    assert "decoder.up_blocks.0.resnets.0.conv_shortcut.weight" not in names
+    assert "decoder.up_blocks.3.upsamplers.0.conv.weight" not in names
+    assert sum(1 for n in names if n.endswith(".weight")) == 2 + 14 * 4 + 2 + 3 + 5 + 1 + 1
+    n_params = sum(math.prod(s) for s in names.values())
+    assert 49_000_000 < n_params < 50_000_000  # the SD decoder has 49.5 M parameters
+
+
+def test_oracle_shapes_and_determinism():
+    cfg = VaeConfig(block_out_channels=(32, 32, 64, 64))  # narrow: seconds on CPU
+    sd = random_init_vae_state_dict(cfg, seed=3)
+    assert set(sd) == set(decoder_layer_names(cfg))
+    lat = torch.randn(2, 4, 8, 8, generator=torch.Generator().manual_seed(0))
+    ocfg = OracleVaeConfig(block_out_channels=cfg.block_out_channels)
+    a = vae_decode(sd, lat, ocfg)
+    b = vae_decode(sd, lat, ocfg)
+    assert a.shape == (2, 3, 64, 64) and torch.equal(a, b) and torch.isfinite(a).all()
+    # samples are independent
+    c = vae_decode(sd, lat[1:], ocfg)
+    assert torch.allclose(a[1:], c, atol=1e-5)
+    d = vae_decode(sd, lat, ocfg, denormalize=True)
+    assert float(d.min()) >= 0 and float(d.max()) <= 1
+
+
+def test_conv_weight_packing_is_the_tap_major_gemm_operand():
+    """The packed [cout, (ky*3+kx)*cin + c] matrix times the shifted-row im2col of a bordered NHWC image equals
+    F.conv2d - the identity the implicit-GEMM kernel relies on (checked here with plain torch on the CPU)."""
+    g = torch.Generator().manual_seed(0)
+    b, cin, cout, h, w = 2, 8, 5, 6, 7
+    x = torch.randn(b, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g)
+    packed = wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin)
+    xb = torch.zeros(b, h + 2, w + 2, cin)
+    xb[:, 1:-1, 1:-1] = x.permute(0, 2, 3, 1)
+    rows = xb.reshape(-1, cin)
+    pitch = w + 2
+    m = rows.shape[0]
+    acc = torch.zeros(m, cout)
+    for tap in range(9):
+        ky, kx = divmod(tap, 3)
+        off = (ky - 1) * pitch + (kx - 1)
+        shifted = torch.zeros_like(rows)  # rows outside the matrix read as zero (TMA out-of-bounds fill)
+        lo, hi = max(0, -off), min(m, m - off)
+        shifted[lo:hi] = rows[lo + off:hi + off]
+        acc += shifted @ packed[:, tap * cin:(tap + 1) * cin].T
+    got = acc.view(b, h + 2, w + 2, cout)[:, 1:-1, 1:-1].permute(0, 3, 1, 2)
+    assert torch.allclose(got, F.conv2d(x, wt, padding=1), atol=1e-4)
+
+
+def test_decoder_refuses_to_run_without_cuda():
+    if torch.cuda.is_available():
+        return
+    try:
+        B200VaeDecoder(random_init_vae_state_dict(VaeConfig(block_out_channels=(32, 32, 64, 64))))
+    except RuntimeError as e:
+        assert "no CPU fallback" in str(e)
+    else:
+        raise AssertionError("expected RuntimeError")
+
+
+def test_flops_model_matches_published_order_of_magnitude():
+    # SD VAE decode of a 64 x 64 latent (512 x 512 image): ~1.24 TMACs = 2.5 TFLOP (widely quoted figure)
+    f = B200VaeDecoder.flops(1, 64, 64)
+    assert 2.3e12 < f < 2.7e12
