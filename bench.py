@@ -309,6 +309,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-population72", action="store_true", help="skip the 72-candidate LPT block")
     ap.add_argument("--no-flux", action="store_true", help="skip the FLUX.1-dev config-5 block (N = 1 only anyway)")
+    ap.add_argument("--no-vae", action="store_true", help="skip the VAE-decode block (N = 1 only anyway)")
     ap.add_argument("--fixed-schedule", action="store_true", help="every step runs ours_fast instead of a candidate")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -429,6 +430,48 @@ def main():
     run_region(0, 1, emb_dev, through_host=False, row=head_row)
     secs_of, _, flops_of_, _, _ = run_region(0, 3, emb_dev, through_host=False, row=head_row)
 
+    # ---- 4b. the step after the loop: VAE decode of the batch, alone and behind an
+    # ours_fast generation - the form the reference's published images/s include (VAE decode inside)
+    vae_blk = None
+    if world == 1 and not args.no_vae and not args.fixed_schedule:
+        from ecad_b200.vae import B200VaeDecoder
+
+        gen.set_schedule(from_packed(head_row))
+        dec = gen.create_vae()  # random-init SD-VAE decoder (49.5 M parameters), weights resident
+        lat = gen.generate_images(emb_dev)[0]
+        for _ in range(2):
+            dec.decode(lat, denormalize=True)
+        l0 = dec.launches
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        for _ in range(3):
+            dec.decode(lat, denormalize=True)
+        ev[1].record()
+        n_dec_launches = (dec.launches - l0) // 3
+        ev[2].record()
+        for _ in range(3):
+            img = gen.generate_images(emb_dev, output_type="pt")[0]
+        ev[3].record()
+        torch.cuda.synchronize()
+        ms_dec = ev[0].elapsed_time(ev[1]) / 3
+        ms_gen = ev[2].elapsed_time(ev[3]) / 3
+        f_dec = B200VaeDecoder.flops(B, lat.shape[2], lat.shape[3])
+        vae_blk = {
+            "what": f"AutoencoderKL.decode of {B} latents 32x32 -> {tuple(img.shape)} images in [0, 1] "
+                    "(random-init SD-VAE decoder; 3x3 convolutions as implicit GEMMs on the tcgen05 kernels)",
+            "decode_ms": ms_dec, "decode_images_per_s": B / ms_dec * 1e3,
+            "decode_algorithmic_tflop_per_image": f_dec / B / 1e12, "decode_tflops": f_dec / ms_dec / 1e9,
+            "decode_frac_of_sustained": f_dec / ms_dec / 1e9 / peaks["tf_sustained"],
+            "decode_launches": n_dec_launches,
+            "ours_fast_with_decode_images_per_s": B / ms_gen * 1e3,
+            "ours_fast_with_decode_ms_per_batch": ms_gen,
+            "note": "the reference's published 11.9 images/s (RTX A6000, ours_fast) includes the VAE decode; the "
+                    "headline `value` of this line does not (latents are the output, SURVEY section 8 (d))",
+        }
+        del dec, lat, img
+        gen.vae = None
+        torch.cuda.empty_cache()
+
     # ---- 5. population72: ALL 72 candidates x B prompts, LPT-partitioned over the ranks by their analytic FLOPs
     pop = None
     if not args.no_population72 and not args.fixed_schedule:
@@ -539,7 +582,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "sm_mhz": clocks_e2e["sm_mhz"] if clocks_e2e else None},
             "gpu_launches": launches, "clocks": clocks,
-            "ours_fast": ours_fast, "population72": pop, "flux_c5": flux,
+            "ours_fast": ours_fast, "vae_decode": vae_blk, "population72": pop, "flux_c5": flux,
         }
     if line is not None:
         print(json.dumps(line), file=_REAL_STDOUT, flush=True)

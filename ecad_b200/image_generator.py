@@ -5,19 +5,23 @@ Reference: /root/reference/ecad/image_generators/image_generator.py:29-495 (sche
 :128-150, generate_images :314-393, generate_images_timed :395-441).  What is kept: the schedule-JSON contract, the
 callback ORDER (step counters first, reset LAST), seeds, and the call surface.  What is different: one resident model
 serves any number of schedules (``set_schedule``) instead of reloading weights per schedule
-(ecad/benchmark/generate_images.py:48-51), and the result is latents (the VAE / PIL stage is out of scope).
+(ecad/benchmark/generate_images.py:48-51); by default the result is latents - ``output_type="pt" | "np" | "pil"``
+decodes them with the B200 VAE decoder (ecad_b200/vae.py) like the reference's pipelines do
+(ecad/pipelines/pass_through.py:382-396).
 """
 from __future__ import annotations
 
 from pathlib import Path
 from typing import Any, Callable
 
+import numpy as np
 import torch
 
 from .pipeline import B200PixArtPipeline
 from .registry import ImageGeneratorRegistry
 from .schedule import PixArtCacheSchedule
 from .transformer import B200PixArtTransformer2D, SequentialDiTScheduler
+from .vae import B200VaeDecoder, VaeConfig, random_init_vae_state_dict
 from .weights import PixArtConfig, random_init_state_dict
 
 
@@ -43,8 +47,17 @@ class _SavedPromptMixin:
         else:
             print("WARNING: No diffusion pipeline to free.")
 
-    def save_image(self, image: torch.Tensor, output_path: Path | str) -> None:
+    def save_image(self, image, output_path: Path | str) -> None:
+        """Latents / image tensors are saved as ``.pt``; PIL images as ``.jpg`` like the reference (:423-440)."""
         output_path = Path(output_path)
+        if not isinstance(image, torch.Tensor) and hasattr(image, "save"):
+            if output_path.suffix != ".jpg":
+                output_path = Path(f"{output_path}.jpg")
+            output_path.parent.mkdir(parents=True, exist_ok=True)
+            image.save(output_path)
+            return
+        if isinstance(image, np.ndarray):
+            image = torch.from_numpy(image)
         if output_path.suffix != ".pt":
             output_path = Path(f"{output_path}.pt")
         output_path.parent.mkdir(parents=True, exist_ok=True)
@@ -92,6 +105,7 @@ class _SavedPromptMixin:
 class B200PixArtImageGenerator(_SavedPromptMixin):
     default_pipeline_name = "pixart_alpha"
     text_tokens = 120
+    default_vae_config = VaeConfig()  # stabilityai/sd-vae-ft-ema: scaling_factor 0.18215
 
     def __init__(
         self,
@@ -105,11 +119,22 @@ class B200PixArtImageGenerator(_SavedPromptMixin):
         device: str = "cuda:0",
         cache_schedule: PixArtCacheSchedule | None = None,
         use_cuda_graph: bool = False,
+        output_type: str = "latent",
+        vae_state_dict: dict[str, torch.Tensor] | None = None,
+        vae_config: VaeConfig | None = None,
     ):
         if not torch.cuda.is_available():
             # pixart_image_generator.py:55-56
             raise ValueError("CUDA is not available.")
+        if output_type not in ("latent", "pt", "np", "pil"):
+            raise ValueError(f"output_type must be latent, pt, np or pil, got {output_type!r}")
         self.device = device
+        # "latent": what the denoising loop leaves (the default: the NSGA-II evaluation scores latents-decoded images
+        # elsewhere); "pt" / "np" / "pil": decoded by the B200 VAE decoder like pass_through.py:382-396
+        self.output_type = output_type
+        self._vae_state_dict = vae_state_dict
+        self.vae_config = vae_config if vae_config is not None else self.default_vae_config
+        self.vae: B200VaeDecoder | None = None
         # one CUDA graph per (schedule, shape) replays a whole generation with a single launch (ecad_b200/graphs.py);
         # in that mode the additional callbacks see the FINAL latents at every step
         self.use_cuda_graph = use_cuda_graph
@@ -193,11 +218,35 @@ class B200PixArtImageGenerator(_SavedPromptMixin):
                                                          use_cuda_graph=self.use_cuda_graph)
         return self.diffusion_pipeline
 
-    # pixart_image_generator.py:314-393 (returns latents [images_per_prompt][B,4,h,w] instead of PIL images)
+    def create_vae(self) -> B200VaeDecoder:
+        """The decoder behind ``output_type != "latent"``; random-init weights when no ``vae_state_dict`` was given
+        (there are no pretrained weights offline)."""
+        if self.vae is None:
+            sd = self._vae_state_dict if self._vae_state_dict is not None else random_init_vae_state_dict(self.vae_config)
+            self.vae = B200VaeDecoder(sd, self.vae_config, self.device)
+        return self.vae
+
+    def decode_latents(self, latents: torch.Tensor, output_type: str = "pt"):
+        """pass_through.py:382-396: ``vae.decode(latents / scaling_factor)`` + ``image_processor.postprocess``:
+        "pt" -> float [B, 3, H, W] in [0, 1]; "np" -> float32 [B, H, W, 3]; "pil" -> list of PIL images."""
+        image = self.create_vae().decode(latents, denormalize=True)
+        if output_type == "pt":
+            return image
+        arr = image.permute(0, 2, 3, 1).cpu().numpy()
+        if output_type == "np":
+            return arr
+        from PIL import Image
+
+        return [Image.fromarray((a * 255).round().astype("uint8")) for a in arr]
+
+    # pixart_image_generator.py:314-393 ([images_per_prompt] entries: latents [B,4,h,w] by default, decoded images with
+    # output_type "pt" / "np" / "pil")
     @torch.inference_mode()
     def generate_images(self, prompt_embeds: dict[str, torch.Tensor], images_per_prompt: int = 1,
-                        height: int | None = None, width: int | None = None, **kwargs) -> list[torch.Tensor]:
+                        height: int | None = None, width: int | None = None, output_type: str | None = None,
+                        **kwargs) -> list:
         pipe = self.create_diffusion_pipeline()
+        output_type = output_type or self.output_type
         out = []
         for i in range(images_per_prompt):
             self.random_generator.manual_seed(self.start_seed + i * self.seed_step)
@@ -213,7 +262,7 @@ class B200PixArtImageGenerator(_SavedPromptMixin):
                 callback=self._call_callbacks_wrapper, callback_steps=1,
                 capture_callback=self._call_core_callbacks,
             )[0]
-            out.append(lat.clone())
+            out.append(lat.clone() if output_type == "latent" else self.decode_latents(lat, output_type))
         return out
 
     # pixart_image_generator.py:395-441: CUDA-event time of one pipeline call / batch size -> ms per image
@@ -241,6 +290,7 @@ class B200PixArtSigmaImageGenerator(B200PixArtImageGenerator):
 
     default_pipeline_name = "pixart_sigma"
     text_tokens = 300
+    default_vae_config = VaeConfig(scaling_factor=0.13025)  # PixArt-sigma ships the SDXL VAE
 
     def __init__(self, *args, model_config: PixArtConfig | None = None, **kwargs):
         if model_config is None:

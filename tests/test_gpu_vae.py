@@ -172,3 +172,42 @@ def test_vae_decode_matches_oracle(cuda_device, hw, batch):
     # determinism, and the denormalised form
     img2 = dec.decode(lat.cuda(), denormalize=True)
     assert torch.allclose(img2, (img / 2 + 0.5).clamp(0, 1), atol=1e-6)
+
+
+def test_generator_output_types(cuda_device, tmp_path):
+    """`output_type` of the generators (pass_through.py:382-396): "latent" (default) / "pt" / "np" / "pil" from the same
+    seed; the decoded forms equal an explicit decode of the latents; generate_from_saved_prompts writes .jpg files for
+    PIL output like the reference (image_generator.py:423-440)."""
+    import numpy as np
+    from ecad_b200.dataset import PIXART_KEYS
+    from ecad_b200.image_generator import B200PixArtAlphaImageGenerator, B200PixArtSigmaImageGenerator
+    from ecad_b200.schedule import PixArtCacheSchedule
+    from ecad_b200.weights import PixArtConfig, random_init_state_dict, synthetic_prompt_embeddings
+
+    L, steps = 2, 3
+    cfg = PixArtConfig(num_layers=L)
+    flags = np.random.default_rng(2).random((steps, L, 3)) < 0.6
+    emb = synthetic_prompt_embeddings(2, seed=4)
+    gen = B200PixArtAlphaImageGenerator(cache_schedule=PixArtCacheSchedule.from_numpy(flags, steps, L), state_dict=random_init_state_dict(cfg, 1),
+                                        model_config=cfg)
+    lat = gen.generate_images(emb)[0]
+    assert lat.shape == (2, 4, 32, 32)
+    pt = gen.generate_images(emb, output_type="pt")[0]
+    assert pt.shape == (2, 3, 256, 256) and float(pt.min()) >= 0 and float(pt.max()) <= 1
+    assert torch.equal(pt, gen.create_vae().decode(lat, denormalize=True))
+    arr = gen.generate_images(emb, output_type="np")[0]
+    assert arr.shape == (2, 256, 256, 3) and np.allclose(arr, pt.permute(0, 2, 3, 1).cpu().numpy())
+    pil = gen.generate_images(emb, output_type="pil")[0]
+    assert len(pil) == 2 and pil[0].size == (256, 256)
+    assert gen.vae_config.scaling_factor == 0.18215
+    assert B200PixArtSigmaImageGenerator.default_vae_config.scaling_factor == 0.13025
+    # file-driven API with PIL output
+    src, dst = tmp_path / "prompts", tmp_path / "images"
+    src.mkdir()
+    for i in range(2):
+        torch.save({k: emb[k][i:i + 1] for k in PIXART_KEYS}, src / f"p{i}.pt")
+    gen.output_type = "pil"
+    gen.generate_from_saved_prompts(src, dst, batch_size=2)
+    assert sorted(p.name for p in dst.glob("**/*.jpg")) == ["p0__image_seed:000.jpg", "p1__image_seed:000.jpg"]
+    ms = gen.generate_images_timed(emb)  # timed INCLUDING the decode, like the reference's latency figures
+    assert ms > 0
