@@ -1772,6 +1772,8 @@ int ecadk_groupnorm_nhwc(const void* x, const float* gamma, const float* beta, v
                          int w_, int c, int groups, float eps, int silu, int unpadded_out, ecadk_stream_t stream_) {
   ECADK_REQUIRE(x && gamma && beta && out && scratch, "groupnorm_nhwc: null pointer");
   ECADK_REQUIRE(batch > 0 && h > 0 && w_ > 0 && c > 0 && groups > 0 && c % groups == 0, "groupnorm_nhwc: bad shape");
+  ECADK_REQUIRE(static_cast<long long>(h + 2) * (w_ + 2) * (c / 8) < (1ll << 31) && batch <= 65535,
+                "groupnorm_nhwc: image too large");
   const int cpg = c / groups;
   ECADK_REQUIRE(cpg == 4 || cpg == 8 || cpg == 16, "groupnorm_nhwc: %d channels per group (supported: 4, 8, 16)", cpg);
   ECADK_REQUIRE(c % 8 == 0 && c <= 2048 && 256 % (c / 8) == 0, "groupnorm_nhwc: c=%d", c);
@@ -1796,8 +1798,8 @@ int ecadk_groupnorm_nhwc(const void* x, const float* gamma, const float* beta, v
   dim3 sgrid(blocks, batch);
   gn_stats_kernel<<<sgrid, 256, 256 * 4 * sizeof(float), stream>>>(p);
   gn_finalize_kernel<<<(batch * groups + 255) / 256, 256, 0, stream>>>(p);
-  const long long total = static_cast<long long>(batch) * plane * (c / 8);
-  gn_apply_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(p);
+  dim3 agrid(static_cast<unsigned>(((plane + kGnApplyPix - 1) / kGnApplyPix * (c / 8) + 255) / 256), batch);
+  gn_apply_kernel<<<agrid, 256, 0, stream>>>(p);
   return check_launch("groupnorm_nhwc");
 }
 
@@ -1807,8 +1809,9 @@ int ecadk_upsample2x_nhwc(const void* x, void* out, int batch, int h, int w_, in
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ProfScope prof(ECADK_PROF_OTHER, 0.0, 5.0 * batch * h * w_ * c * 2.0, stream);
   UpsampleParams p{static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), batch, h, w_, c};
-  const long long total = static_cast<long long>(batch) * (2 * h + 2) * (2 * w_ + 2) * (c / 8);
-  upsample2x_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(p);
+  const long long per_sample = static_cast<long long>(2 * h + 2) * (2 * w_ + 2) * (c / 8);
+  ECADK_REQUIRE(per_sample < (1ll << 31), "upsample2x_nhwc: image too large");
+  upsample2x_kernel<<<dim3(static_cast<unsigned>((per_sample + 255) / 256), batch), 256, 0, stream>>>(p);
   return check_launch("upsample2x_kernel");
 }
 
@@ -1842,8 +1845,9 @@ int ecadk_vae_add_tokens(const void* x, const void* tokens, void* out, int batch
   ProfScope prof(ECADK_PROF_OTHER, 0.0, 0.0, stream);
   AddTokensParams p{static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(tokens),
                     static_cast<__nv_bfloat16*>(out), batch, h, w_, c};
-  const long long total = static_cast<long long>(batch) * (h + 2) * (w_ + 2) * (c / 8);
-  vae_add_tokens_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(p);
+  const long long per_sample = static_cast<long long>(h + 2) * (w_ + 2) * (c / 8);
+  ECADK_REQUIRE(per_sample < (1ll << 31), "vae_add_tokens: image too large");
+  vae_add_tokens_kernel<<<dim3(static_cast<unsigned>((per_sample + 255) / 256), batch), 256, 0, stream>>>(p);
   return check_launch("vae_add_tokens_kernel");
 }
 
