@@ -460,6 +460,24 @@ int launch_gemm2_inst(const CUtensorMap& ta, const CUtensorMap& ta2, const CUten
   return check_launch("gemm2_bf16_kernel");
 }
 
+// 3x3 convolution with C_out = 128: the taps of one kernel row share their A tile (gemm2_bf16_kernel, TAP3)
+template <int EPI>
+int launch_gemm2_tap3_inst(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, const GemmParams& p,
+                           cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<128, EPI, true>;
+  static bool configured = false;
+  auto kern = gemm2_bf16_kernel<128, EPI, true>;
+  if (!configured) {
+    ECADK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int tiles = ((p.M + 2 * kGemmBM - 1) / (2 * kGemmBM)) * (p.N / 128);
+  const int pairs = num_sms() / 2;
+  const int grid = 2 * (tiles < pairs ? tiles : pairs);
+  launch_pdl(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, ta, ta, tb, tb, em.x, em.cache, em.xb, p, 0);
+  return check_launch("gemm2_bf16_kernel<TAP3>");
+}
+
 // Tile-N choice: among the widths that divide N, minimise waves x per-tile time (~ BN + fixed overhead).
 int pick_bn(int m_tiles, int N, int workers) {
   const int cands[3] = {256, 192, 128};
@@ -525,6 +543,19 @@ int launch_gemm(const void* a, const void* w, GemmParams& p, cudaStream_t stream
     if ((rc = make_tmap_bf16(&ta, a, p.M, a_cols, a_cols, kGemmBM, kGemmBK, 128))) return rc;
     ta2 = ta;
     p.kb_split = p.K / kGemmBK;
+  }
+  if constexpr (EPI == EPI_CONV) {
+    // ECADK_CONV_TAP3=0 keeps the nine-loads-per-block form (A/B measurements)
+    static const bool tap3 = [] {
+      const char* e = getenv("ECADK_CONV_TAP3");
+      return !(e != nullptr && atoi(e) == 0);
+    }();
+    if (tap3 && group == 2 && p.conv_taps == 9 && p.N == 128) {
+      const int c_in = p.K / 9;
+      if ((rc = make_tmap_bf16(&ta, a, p.M, c_in, c_in, kTap3Rows, kGemmBK, 128))) return rc;
+      if ((rc = make_tmap_bf16(&tb, w, p.N, p.K, p.K, 64, kGemmBK, 128))) return rc;
+      return launch_gemm2_tap3_inst<EPI>(ta, tb, em, p, stream);
+    }
   }
   if (group == 2) {
     // ECADK_GEMM_TAIL=0 disables the 256-wide + 128-wide-tail tiling (A/B measurements)

@@ -193,6 +193,18 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
   auto process = [&](const int c, const float4 (&xin)[8], const Vecs& vec, const uint32_t (&v)[32]) {
     const int col = n0 + c * 32 + cg * 4;
     const float4 b4 = vec.b4;
+    uint2 conv_res[8];  // EPI_CONV: the residual values of this lane's 8 rows, requested before the transpose (the
+                        // residual never aliases `out`; loaded one by one between the stores they sat on the critical path)
+    if constexpr (EPI == EPI_CONV) {
+      if (p.out2 != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = row_base + i * 4 + rs;
+          conv_res[i] = row < p.M ? __ldg(reinterpret_cast<const uint2*>(p.out2 + static_cast<size_t>(row) * p.ldo2 + col))
+                                  : make_uint2(0u, 0u);
+        }
+      }
+    }
     const float4 g4 = make_float4(vec.g4.x + vec.t4.x, vec.g4.y + vec.t4.y, vec.g4.z + vec.t4.z, vec.g4.w + vec.t4.w);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -260,7 +272,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
           *reinterpret_cast<uint2*>(hm_base + row_off[i] + hm_off) = w;
         } else if constexpr (EPI == EPI_CONV) {
           if (p.out2 != nullptr) {  // residual branch of the ResNet block, same layout
-            const uint2 rv = *reinterpret_cast<const uint2*>(p.out2 + static_cast<size_t>(row) * p.ldo2 + col);
+            const uint2 rv = conv_res[i];
             const float2 r01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rv.x));
             const float2 r23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rv.y));
             o.x += r01.x; o.y += r01.y; o.z += r23.x; o.w += r23.y;
@@ -841,20 +853,32 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 // pair; tcgen05.commit multicasts the "slot free" / "accumulator ready" arrivals to both CTAs; every CTA's epilogue
 // warps drain their own 128 TMEM lanes.
 // =====================================================================================================
-template <int BN, int EPI = 0>
+// TAP3 (3x3 convolutions, see below): a stage holds ONE A tile of 128 + 8 rows that starts one pixel to the left of
+// the output rows, and the three W tiles of the taps (ky, 0..2) that read it.
+constexpr int kTap3Rows = kGemmBM + 8;
+template <int BN, int EPI = 0, bool TAP3 = false>
 struct Gemm2Cfg {
-  static constexpr int kStageA = kGemmBM * kGemmBK * 2;        // this CTA's 128 rows of A: 16 KB
-  static constexpr int kStageB = (BN / 2) * kGemmBK * 2;       // this CTA's half of W
+  static constexpr int kBytesA = (TAP3 ? kTap3Rows : kGemmBM) * kGemmBK * 2;  // this CTA's rows of A: 16 KB (17 KB)
+  static constexpr int kStageA = (kBytesA + 1023) / 1024 * 1024;
+  static constexpr int kTileB = (BN / 2) * kGemmBK * 2;        // this CTA's half of one W tile
+  static constexpr int kStageB = (TAP3 ? 3 : 1) * kTileB;
   static constexpr int kStage = kStageA + kStageB;
   static constexpr int kEpiBytes = epi_stage_bytes(EPI);
-  static constexpr int kStages = fit_stages((BN <= 128) ? 7 : (BN <= 192 ? 6 : 5), kStage, EPI);
+  static constexpr int kStages = fit_stages(TAP3 ? 4 : ((BN <= 128) ? 7 : (BN <= 192 ? 6 : 5)), kStage, EPI);
   static constexpr int kAccStride = 256;
   static constexpr int kTmemCols = 512;
   static constexpr int kSmemBytes = kStages * kStage + kEpiBytes + 1024 + 256;
   static_assert(kStages >= 4, "GEMM pipeline depth");
 };
 
-template <int BN, int EPI>
+// TAP3 = true (3x3 convolution, taps of one kernel row share their A tile): the implicit GEMM above fetches every A block
+// nine times, once per tap, and at C_out = 128 - the tile already spans all output channels - that alone is the SM's
+// whole L2 port (2 B of A per 256 FLOP; ncu: tensor pipe 31.6 % at the 256 x 256 layers of the VAE decoder).  The three
+// taps (ky, 0), (ky, 1), (ky, 2) read the SAME rows shifted by one pixel, so one TMA load of 128 + 8 rows starting at
+// `m0 + (ky-1)*pitch - 1` serves all three: the MMA of tap kx addresses the tile at row offset kx through its
+// shared-memory descriptor (start address + kx * 128 B; the 128B swizzle follows the absolute address, so the rows
+// land where TMA put them).  A traffic drops 3x; k-blocks are ordered (ky, channel block) with three W tiles per stage.
+template <int BN, int EPI, bool TAP3 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
                   const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_b_tail,
@@ -862,7 +886,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                   const __grid_constant__ CUtensorMap tmap_xb, const GemmParams p, const int tail) {
   // `tail` (0 or 128, only with BN = 256): N = k*256 + 128 is covered by k full-width tiles plus one 128-wide tile per
   // row block, so N = 1152 / 3456 run at the L2->SM traffic per FLOP of 256-wide tiles instead of 192-wide ones.
-  using Cfg = Gemm2Cfg<BN, EPI>;
+  using Cfg = Gemm2Cfg<BN, EPI, TAP3>;
   constexpr bool kTmaEpi = EPI == EPI_GATED_RESIDUAL && ECADK_EPI_TMA_STORE;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -883,7 +907,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int num_n_full = (p.N - tail) / BN;
   const int num_n = num_n_full + (tail ? 1 : 0);
   const int num_tiles = num_m * num_n;
-  const int num_kb = p.K / kGemmBK;
+  const int num_kb = TAP3 ? p.K / kGemmBK / 3 : p.K / kGemmBK;  // TAP3: (ky, channel block) steps of three taps each
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -925,20 +949,28 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       if (lane == 0) {
         const int n0 = n_idx * BN + cta * (bn_cur / 2);
         const CUtensorMap* tb = is_tail ? &tmap_b_tail : &tmap_b;
-        const uint32_t stage_bytes = 2 * (Cfg::kStageA + (bn_cur / 2) * kGemmBK * 2);
+        const uint32_t stage_bytes =
+            TAP3 ? 2 * (Cfg::kBytesA + Cfg::kStageB) : 2 * (Cfg::kStageA + (bn_cur / 2) * kGemmBK * 2);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStage;
           uint8_t* sb = sa + Cfg::kStageA;
           if (cta == 0) mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
-          if (kb < p.kb_split) {
+          if constexpr (TAP3) {
+            const int ky = kb / p.conv_cblocks, cb = kb - ky * p.conv_cblocks;
+            tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], cb * kGemmBK, m0 + (ky - 1) * p.conv_pitch - 1);
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+              tma_load_2d_2sm(sb + kx * Cfg::kTileB, tb, &full_bar[stage],
+                              ((ky * 3 + kx) * p.conv_cblocks + cb) * kGemmBK, n0);
+          } else if (kb < p.kb_split) {
             int a_col, a_row;
             a_tile_coords(p, kb, m0, a_col, a_row);
             tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], a_col, a_row);
           } else {
             tma_load_2d_2sm(sa, &tmap_a2, &full_bar[stage], (kb - p.kb_split) * kGemmBK, m0);
           }
-          tma_load_2d_2sm(sb, tb, &full_bar[stage], kb * kGemmBK, n0);
+          if constexpr (!TAP3) tma_load_2d_2sm(sb, tb, &full_bar[stage], kb * kGemmBK, n0);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -966,11 +998,25 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStage);
           const uint32_t sb = sa + Cfg::kStageA;
-          const uint64_t da = make_smem_desc(sa, 16, 1024, kLayoutSW128);
-          const uint64_t db = make_smem_desc(sb, 16, 1024, kLayoutSW128);
+          if constexpr (TAP3) {
 #pragma unroll
-          for (int k = 0; k < kGemmBK / 16; ++k) {
-            umma_bf16_ss_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            for (int kx = 0; kx < 3; ++kx) {
+              // rows kx .. kx + 127 of the 136-row tile: start address + kx rows.  The 128B swizzle is a function of
+              // the absolute shared-memory address bits (the tile base stays 1024-byte aligned), so the descriptor's
+              // matrix-base-offset field stays 0 (measured: setting it to kx reads the wrong 16-byte pieces)
+              const uint64_t da = make_smem_desc(sa + kx * 128, 16, 1024, kLayoutSW128);
+              const uint64_t db = make_smem_desc(sb + kx * Cfg::kTileB, 16, 1024, kLayoutSW128);
+#pragma unroll
+              for (int k = 0; k < kGemmBK / 16; ++k)
+                umma_bf16_ss_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | kx | k) != 0);
+            }
+          } else {
+            const uint64_t da = make_smem_desc(sa, 16, 1024, kLayoutSW128);
+            const uint64_t db = make_smem_desc(sb, 16, 1024, kLayoutSW128);
+#pragma unroll
+            for (int k = 0; k < kGemmBK / 16; ++k) {
+              umma_bf16_ss_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            }
           }
           umma_commit_2sm(&empty_bar[stage], 0b11);
           if (++stage == STAGES) {

@@ -132,7 +132,7 @@ int ecadk_cfg_dpm_step(const float* noise, float* latents, float* x0_prev, int b
 /* Convolution as an implicit GEMM on the tensor cores: out[pixel, :] = bias + sum_taps x[pixel + tap] * W_tap^T
  * (+ residual[pixel, :]) on interior pixels, 0 on the border.  taps = 9: 3x3, stride 1, padding 1; taps = 1: 1x1.
  * x bf16 [batch, h+2, w+2, c_in] (c_in % 64 == 0); w bf16 [c_out, taps*c_in], K index = (ky*3 + kx)*c_in + c
- * (c_out % 128 == 0: pad the rows); bias fp32 [c_out] or NULL; residual bf16, same layout as out, or NULL;
+ * (c_out % 128 == 0: pad the rows); bias fp32 [c_out] or NULL; residual bf16, same layout as out (must not alias out), or NULL;
  * out bf16 with row pitch out_ld; only 32-column chunks that start below out_cols are written.
  * Replaces torch.nn.Conv2d inside diffusers ResnetBlock2D / Upsample2D / Decoder.conv_in / conv_out. */
 int ecadk_conv_nhwc(const void* x, const void* w, const float* bias, const void* residual, void* out, int batch, int h,

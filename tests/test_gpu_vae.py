@@ -36,7 +36,9 @@ def _pack_conv(w):
     (3, 32, 32, 512, 512, 9, True),      # mid-block shape, residual
     (2, 40, 24, 128, 256, 9, False),     # non-square, rows not a multiple of 128
     (2, 32, 32, 512, 256, 1, False),     # 1x1 shortcut
-    (24, 64, 64, 128, 128, 9, True),     # enough rows for the 2-CTA kernels
+    (24, 64, 64, 128, 128, 9, True),     # enough rows for the 2-CTA kernels; C_out = 128: taps of a row share one A tile
+    (9, 64, 64, 256, 128, 9, False),     # same path, two channel blocks per tap
+    (24, 64, 64, 128, 256, 9, False),    # 2-CTA kernels, nine loads per block
 ])
 def test_conv_nhwc(cuda_device, b, h, w, cin, cout, taps, res):
     from ecad_b200 import _lib

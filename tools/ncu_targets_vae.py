@@ -60,7 +60,14 @@ def splitk(n, k):
     torch.cuda.synchronize()
 
 
-conv(16, 256, 256, 128, 128, res=True)   # up-block 3 (C_out = 128: L2 -> SM bound)
+only = sys.argv[1] if len(sys.argv) > 1 else ""
+if only == "conv128":  # the C_out = 128 layers alone, without / with the residual
+    conv(16, 256, 256, 128, 128, res=False)
+    conv(16, 256, 256, 128, 128, res=True)
+    conv(16, 256, 256, 256, 128, res=False)
+    print("done")
+    sys.exit(0)
+conv(16, 256, 256, 128, 128, res=True)   # up-block 3 (C_out = 128)
 conv(32, 128, 128, 256, 256)             # up-block 2
 conv(100, 64, 64, 512, 512)              # up-block 1
 conv(32, 128, 128, 512, 256, taps=1)     # 1x1 shortcut
