@@ -236,9 +236,9 @@ def load() -> C.CDLL:
         "ecadk_groupnorm_nhwc": [p, p, p, p, p, i, i, i, i, i, f, i, i, p],
         "ecadk_groupnorm_scratch_bytes": [i, i, i, i],
         "ecadk_upsample2x_nhwc": [p, p, i, i, i, i, p],
-        "ecadk_softmax_rows": [p, p, i, i, f, p],
-        "ecadk_vae_prepare_latents": [p, p, p, f, p, i, i, i, p],
-        "ecadk_vae_add_tokens": [p, p, p, i, i, i, i, p],
+        "ecadk_softmax_rows": [p, p, i, i, i, f, p],
+        "ecadk_vae_prepare_latents": [p, p, p, f, f, p, i, i, i, i, p],
+        "ecadk_vae_add_tokens": [p, p, i, p, i, i, i, i, p],
         "ecadk_vae_finish": [p, p, i, i, i, i, p],
         "ecadk_profile_start": [],
         "ecadk_profile_stop": [C.POINTER(EcadkProfileRecord)],
@@ -317,9 +317,10 @@ def conv_nhwc(x, w, bias, out, h, w_, taps, residual=None, out_cols=None):
 
 
 def groupnorm_nhwc(x, gamma, beta, out, scratch, h, w_, groups=32, eps=1e-6, silu=True, unpadded_out=False):
+    """unpadded_out: False -> bordered NHWC out; True -> tokens [B, out.shape[1], C] (out.shape[1] >= h*w_)."""
     batch, c = x.shape[0], x.shape[-1]
     check(load().ecadk_groupnorm_nhwc(ptr(x), ptr(gamma), ptr(beta), ptr(out), ptr(scratch), batch, h, w_, c, groups,
-                                      eps, int(silu), int(unpadded_out), stream_ptr()), "groupnorm_nhwc")
+                                      eps, int(silu), out.shape[1] if unpadded_out else 0, stream_ptr()), "groupnorm_nhwc")
     return out
 
 
@@ -332,22 +333,24 @@ def upsample2x_nhwc(x, out, h, w_):
     return out
 
 
-def softmax_rows(scores, probs, scale):
+def softmax_rows(scores, probs, scale, valid_cols=None):
     rows, cols = scores.shape
-    check(load().ecadk_softmax_rows(ptr(scores), ptr(probs), rows, cols, scale, stream_ptr()), "softmax_rows")
+    check(load().ecadk_softmax_rows(ptr(scores), ptr(probs), rows, cols, cols if valid_cols is None else valid_cols,
+                                    scale, stream_ptr()), "softmax_rows")
     return probs
 
 
-def vae_prepare_latents(z, pq_w, pq_b, inv_scaling, out):
-    batch, _, h, w_ = z.shape
-    check(load().ecadk_vae_prepare_latents(ptr(z), ptr(pq_w), ptr(pq_b), inv_scaling, ptr(out), batch, h, w_,
+def vae_prepare_latents(z, pq_w, pq_b, inv_scaling, out, shift=0.0):
+    batch, cl, h, w_ = z.shape
+    check(load().ecadk_vae_prepare_latents(ptr(z), ptr(pq_w), ptr(pq_b), inv_scaling, shift, ptr(out), batch, cl, h, w_,
                                            stream_ptr()), "vae_prepare_latents")
     return out
 
 
 def vae_add_tokens(x, tokens, out, h, w_):
-    check(load().ecadk_vae_add_tokens(ptr(x), ptr(tokens), ptr(out), x.shape[0], h, w_, x.shape[-1], stream_ptr()),
-          "vae_add_tokens")
+    """tokens [B, T, C] with T >= h*w_ (rows past h*w_ are padding)."""
+    check(load().ecadk_vae_add_tokens(ptr(x), ptr(tokens), tokens.shape[1], ptr(out), x.shape[0], h, w_, x.shape[-1],
+                                      stream_ptr()), "vae_add_tokens")
     return out
 
 

@@ -1803,6 +1803,8 @@ int ecadk_groupnorm_nhwc(const void* x, const float* gamma, const float* beta, v
                          int w_, int c, int groups, float eps, int silu, int unpadded_out, ecadk_stream_t stream_) {
   ECADK_REQUIRE(x && gamma && beta && out && scratch, "groupnorm_nhwc: null pointer");
   ECADK_REQUIRE(batch > 0 && h > 0 && w_ > 0 && c > 0 && groups > 0 && c % groups == 0, "groupnorm_nhwc: bad shape");
+  ECADK_REQUIRE(unpadded_out == 0 || unpadded_out >= h * w_, "groupnorm_nhwc: unpadded_out=%d must be 0 or >= h*w",
+                unpadded_out);
   ECADK_REQUIRE(static_cast<long long>(h + 2) * (w_ + 2) * (c / 8) < (1ll << 31) && batch <= 65535,
                 "groupnorm_nhwc: image too large");
   const int cpg = c / groups;
@@ -1846,36 +1848,43 @@ int ecadk_upsample2x_nhwc(const void* x, void* out, int batch, int h, int w_, in
   return check_launch("upsample2x_kernel");
 }
 
-int ecadk_softmax_rows(const float* scores, void* probs, int rows, int cols, float scale, ecadk_stream_t stream_) {
+int ecadk_softmax_rows(const float* scores, void* probs, int rows, int cols, int valid_cols, float scale,
+                       ecadk_stream_t stream_) {
   ECADK_REQUIRE(scores && probs && rows > 0 && cols > 0 && cols % 4 == 0, "softmax_rows: bad arguments");
+  ECADK_REQUIRE(valid_cols > 0 && valid_cols <= cols && valid_cols % 4 == 0, "softmax_rows: valid_cols=%d of %d", valid_cols,
+                cols);
   ECADK_REQUIRE(aligned16(scores) && aligned16(probs), "softmax_rows: 16-byte alignment");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ProfScope prof(ECADK_PROF_OTHER, 0.0, 6.0 * rows * cols, stream);
   softmax_rows_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(scores, static_cast<__nv_bfloat16*>(probs), rows, cols,
-                                                         scale * 1.4426950408889634f);
+                                                         valid_cols, scale * 1.4426950408889634f);
   return check_launch("softmax_rows_kernel");
 }
 
-int ecadk_vae_prepare_latents(const float* z, const float* pq_w, const float* pq_b, float inv_scaling, void* out,
-                              int batch, int h, int w_, ecadk_stream_t stream_) {
-  ECADK_REQUIRE(z && pq_w && pq_b && out && batch > 0 && h > 0 && w_ > 0, "vae_prepare_latents: bad arguments");
+int ecadk_vae_prepare_latents(const float* z, const float* pq_w, const float* pq_b, float inv_scaling, float shift,
+                              void* out, int batch, int latent_channels, int h, int w_, ecadk_stream_t stream_) {
+  ECADK_REQUIRE(z && out && batch > 0 && h > 0 && w_ > 0, "vae_prepare_latents: bad arguments");
+  ECADK_REQUIRE(latent_channels == 4 || latent_channels == 16, "vae_prepare_latents: latent_channels=%d (4 or 16)",
+                latent_channels);
+  ECADK_REQUIRE((pq_w == nullptr) == (pq_b == nullptr), "vae_prepare_latents: post_quant_conv weight and bias go together");
   ECADK_REQUIRE(aligned16(out), "vae_prepare_latents: 16-byte alignment");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ProfScope prof(ECADK_PROF_OTHER, 0.0, 0.0, stream);
-  VaePrepParams p{z, pq_w, pq_b, static_cast<__nv_bfloat16*>(out), batch, h, w_, inv_scaling};
+  VaePrepParams p{z, pq_w, pq_b, static_cast<__nv_bfloat16*>(out), batch, h, w_, latent_channels, inv_scaling, shift};
   const long long total = static_cast<long long>(batch) * (h + 2) * (w_ + 2) * 8;
   vae_prepare_latents_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(p);
   return check_launch("vae_prepare_latents_kernel");
 }
 
-int ecadk_vae_add_tokens(const void* x, const void* tokens, void* out, int batch, int h, int w_, int c,
-                         ecadk_stream_t stream_) {
+int ecadk_vae_add_tokens(const void* x, const void* tokens, int tokens_per_sample, void* out, int batch, int h, int w_,
+                         int c, ecadk_stream_t stream_) {
   ECADK_REQUIRE(x && tokens && out && batch > 0 && h > 0 && w_ > 0 && c > 0 && c % 8 == 0, "vae_add_tokens: bad arguments");
+  ECADK_REQUIRE(tokens_per_sample >= h * w_, "vae_add_tokens: tokens_per_sample=%d < %d", tokens_per_sample, h * w_);
   ECADK_REQUIRE(aligned16(x) && aligned16(tokens) && aligned16(out), "vae_add_tokens: 16-byte alignment");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ProfScope prof(ECADK_PROF_OTHER, 0.0, 0.0, stream);
   AddTokensParams p{static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(tokens),
-                    static_cast<__nv_bfloat16*>(out), batch, h, w_, c};
+                    static_cast<__nv_bfloat16*>(out), batch, h, w_, c, tokens_per_sample};
   const long long per_sample = static_cast<long long>(h + 2) * (w_ + 2) * (c / 8);
   ECADK_REQUIRE(per_sample < (1ll << 31), "vae_add_tokens: image too large");
   vae_add_tokens_kernel<<<dim3(static_cast<unsigned>((per_sample + 255) / 256), batch), 256, 0, stream>>>(p);

@@ -5,7 +5,8 @@
 // 3x3 convolutions, which run as implicit GEMMs on the tensor cores (gemm.cuh, GemmParams::conv_taps): every kernel
 // that writes such a tensor writes zeros on the border.
 //
-//   vae_prepare_latents_kernel  z / scaling_factor -> post_quant_conv (1x1, 4 -> 4) -> NHWC, channels padded to 64
+//   vae_prepare_latents_kernel  z / scaling_factor + shift_factor -> post_quant_conv (1x1, optional) -> NHWC, 4 or 16
+//                               latent channels padded to 64
 //   gn_stats_kernel             per (sample, block, group) sum and sum of squares, fixed-order reductions
 //   gn_finalize_kernel          block partials summed in fp64 -> (mean, 1/sqrt(var + eps)) per (sample, group)
 //   gn_apply_kernel             GroupNorm affine (+ SiLU) -> bordered NHWC, or -> plain [batch, H*W, C] tokens (attention)
@@ -19,12 +20,12 @@
 namespace ecadk {
 
 struct VaePrepParams {
-  const float* z;     // [B, 4, H, W] fp32 latents
-  const float* pq_w;  // [4, 4] post_quant_conv weight (out, in)
-  const float* pq_b;  // [4]
+  const float* z;     // [B, CL, H, W] fp32 latents, CL = 4 (SD / SDXL VAE) or 16 (FLUX VAE)
+  const float* pq_w;  // [CL, CL] post_quant_conv weight (out, in), or null (FLUX: use_post_quant_conv = False)
+  const float* pq_b;  // [CL]
   __nv_bfloat16* out; // [B, H+2, W+2, 64]
-  int B, H, W;
-  float inv_scaling;
+  int B, H, W, CL;
+  float inv_scaling, shift;  // z' = z * inv_scaling + shift
 };
 __global__ void __launch_bounds__(256) vae_prepare_latents_kernel(const VaePrepParams p) {
   // one thread per (pixel of the bordered image, 8-channel group): 8 groups of 8 channels = 64 channels
@@ -38,21 +39,36 @@ __global__ void __launch_bounds__(256) vae_prepare_latents_kernel(const VaePrepP
   const int r = static_cast<int>(pix - static_cast<long long>(b) * plane);
   const int y = r / (p.W + 2), x = r - y * (p.W + 2);
   uint4 o = make_uint4(0u, 0u, 0u, 0u);
-  if (cgp == 0 && y >= 1 && y <= p.H && x >= 1 && x <= p.W) {
-    float zin[4];
+  if (cgp * 8 < p.CL && y >= 1 && y <= p.H && x >= 1 && x <= p.W) {
+    float zin[16];
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
-      zin[c] = p.z[((static_cast<size_t>(b) * 4 + c) * p.H + (y - 1)) * p.W + (x - 1)] * p.inv_scaling;
-    float zo[4];
+    for (int c = 0; c < 16; ++c)
+      zin[c] = c < p.CL ? fmaf(p.z[((static_cast<size_t>(b) * p.CL + c) * p.H + (y - 1)) * p.W + (x - 1)], p.inv_scaling,
+                               p.shift)
+                        : 0.f;
+    float zo[8];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float a = p.pq_b[c];
+    for (int j = 0; j < 8; ++j) {
+      const int c = cgp * 8 + j;
+      float a = 0.f;
+      if (c < p.CL) {
+        if (p.pq_w != nullptr) {
+          a = p.pq_b[c];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) a = fmaf(p.pq_w[c * 4 + k], zin[k], a);
-      zo[c] = a;
+          for (int k = 0; k < 16; ++k)
+            if (k < p.CL) a = fmaf(p.pq_w[c * p.CL + k], zin[k], a);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            if (k == c) a = zin[k];
+        }
+      }
+      zo[j] = a;
     }
     o.x = pack_bf16x2(zo[0], zo[1]);
     o.y = pack_bf16x2(zo[2], zo[3]);
+    o.z = pack_bf16x2(zo[4], zo[5]);
+    o.w = pack_bf16x2(zo[6], zo[7]);
   }
   reinterpret_cast<uint4*>(p.out)[idx] = o;
 }
@@ -62,7 +78,7 @@ __global__ void __launch_bounds__(256) vae_prepare_latents_kernel(const VaePrepP
 // channels (one uint4), i.e. two groups, one group or half a group.
 struct GroupNormParams {
   const __nv_bfloat16* x;  // bordered NHWC
-  __nv_bfloat16* out;      // bordered NHWC, or [B, H*W, C] when unpadded_out
+  __nv_bfloat16* out;      // bordered NHWC, or tokens [B, unpadded_out, C] when unpadded_out > 0
   const float* gamma;      // [C]
   const float* beta;       // [C]
   float2* partial;         // [B, blocks, G] per-block (sum, sum of squares)
@@ -217,9 +233,9 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GroupNormParams p) 
         }
         o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
       }
-      if (p.unpadded_out) {
+      if (p.unpadded_out) {  // = tokens per sample in the output (>= H*W: rows past H*W are the caller's zero padding)
         if (inside) {
-          const size_t tok = (static_cast<size_t>(b) * p.H + (y - 1)) * p.W + (x - 1);
+          const size_t tok = static_cast<size_t>(b) * p.unpadded_out + (y - 1) * p.W + (x - 1);
           reinterpret_cast<uint4*>(p.out)[tok * slots + slot] = o;
         }
       } else {
@@ -262,13 +278,15 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const UpsampleParams p)
 
 // ---------------------------------------------------------------------------------------------------
 // softmax over rows of fp32 scores (cols % 128 == 0, cols <= 8192): p = softmax(scale * s) -> bf16; one warp per row
+// columns >= valid (padding keys; valid % 4 == 0) get probability 0
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ out,
-                                                           const int rows, const int cols, const float scale_log2e) {
+                                                           const int rows, const int cols, const int valid,
+                                                           const float scale_log2e) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const float4* sr = reinterpret_cast<const float4*>(s + static_cast<size_t>(row) * cols);
-  const int nv = cols >> 2;
+  const int nv = valid >> 2;
   float m = -INFINITY;
   for (int i = lane; i < nv; i += 32) {
     const float4 v = sr[i];
@@ -294,15 +312,17 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
     w.y = pack_bf16x2(exp2f(fmaf(v.z, scale_log2e, -mb)) * inv, exp2f(fmaf(v.w, scale_log2e, -mb)) * inv);
     orow[i] = w;
   }
+  for (int i = nv + lane; i < (cols >> 2); i += 32) orow[i] = make_uint2(0u, 0u);
 }
 
 // ---------------------------------------------------------------------------------------------------
-// out(bordered) = x(bordered) + tokens([B, H*W, C]) on interior pixels, 0 on the border
+// out(bordered) = x(bordered) + tokens([B, tokens_per_sample, C]) on interior pixels, 0 on the border
 struct AddTokensParams {
   const __nv_bfloat16* x;
   const __nv_bfloat16* tokens;
   __nv_bfloat16* out;
   int B, H, W, C;
+  int tokens_per_sample;  // row stride of `tokens` per sample (>= H*W)
 };
 __global__ void __launch_bounds__(256) vae_add_tokens_kernel(const AddTokensParams p) {
   const int plane = (p.H + 2) * (p.W + 2);
@@ -317,7 +337,7 @@ __global__ void __launch_bounds__(256) vae_add_tokens_kernel(const AddTokensPara
   uint4 o = make_uint4(0u, 0u, 0u, 0u);
   if (y >= 1 && y <= p.H && x >= 1 && x <= p.W) {
     const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.x) + idx);
-    const size_t tok = (static_cast<size_t>(b) * p.H + (y - 1)) * p.W + (x - 1);
+    const size_t tok = static_cast<size_t>(b) * p.tokens_per_sample + (y - 1) * p.W + (x - 1);
     const uint4 t = __ldg(reinterpret_cast<const uint4*>(p.tokens) + tok * slots + slot);
     const uint32_t av[4] = {a.x, a.y, a.z, a.w}, tv[4] = {t.x, t.y, t.z, t.w};
     uint32_t ov[4];

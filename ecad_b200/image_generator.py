@@ -319,10 +319,17 @@ class B200FluxImageGenerator(_SavedPromptMixin):
                  additional_callbacks: list[Callable[..., None]] | None = None,
                  state_dict: dict[str, torch.Tensor] | None = None, model_config=None, weight_seed: int = 0,
                  device: str = "cuda:0", cache_schedule=None, weights_on_device: bool = False,
-                 use_cuda_graph: bool = False):
+                 use_cuda_graph: bool = False, output_type: str = "latent",
+                 vae_state_dict: dict[str, torch.Tensor] | None = None, vae_config: VaeConfig | None = None):
         from .weights import FluxConfig
 
         self.use_cuda_graph = use_cuda_graph
+        if output_type not in ("latent", "pt", "np", "pil"):
+            raise ValueError(f"output_type must be latent, pt, np or pil, got {output_type!r}")
+        self.output_type = output_type
+        self._vae_state_dict = vae_state_dict
+        self.vae_config = vae_config if vae_config is not None else VaeConfig.flux()
+        self.vae: B200VaeDecoder | None = None
 
         if not torch.cuda.is_available():
             # flux_image_generator.py:45-46
@@ -416,12 +423,41 @@ class B200FluxImageGenerator(_SavedPromptMixin):
             self.diffusion_pipeline = B200FluxPipeline(tr, use_cuda_graph=self.use_cuda_graph)
         return self.diffusion_pipeline
 
-    # flux_image_generator.py:285-363 (returns packed latents [images_per_prompt][B, N, 64] instead of PIL images)
+    def create_vae(self) -> B200VaeDecoder:
+        """The FLUX VAE decoder (16 latent channels, shift factor, no post_quant_conv); random-init weights unless a
+        ``vae_state_dict`` was given."""
+        if self.vae is None:
+            sd = self._vae_state_dict if self._vae_state_dict is not None else random_init_vae_state_dict(self.vae_config)
+            self.vae = B200VaeDecoder(sd, self.vae_config, self.device)
+        return self.vae
+
+    def decode_latents(self, latents: torch.Tensor, height: int, width: int, output_type: str = "pt"):
+        """FluxPipeline.__call__ after the loop (diffusers 0.30.3): ``_unpack_latents`` ([B, N, 64] -> [B, 16, h, w]),
+        ``latents / scaling_factor + shift_factor``, ``vae.decode``, ``image_processor.postprocess``."""
+        from .flux_pipeline import B200FluxPipeline
+
+        b = latents.shape[0]
+        h = 2 * (int(height) // B200FluxPipeline.vae_scale_factor)
+        w = 2 * (int(width) // B200FluxPipeline.vae_scale_factor)
+        z = latents.view(b, h // 2, w // 2, 16, 2, 2).permute(0, 3, 1, 4, 2, 5).reshape(b, 16, h, w)
+        image = self.create_vae().decode(z, denormalize=True)
+        if output_type == "pt":
+            return image
+        arr = image.permute(0, 2, 3, 1).cpu().numpy()
+        if output_type == "np":
+            return arr
+        from PIL import Image
+
+        return [Image.fromarray((a * 255).round().astype("uint8")) for a in arr]
+
+    # flux_image_generator.py:285-363 ([images_per_prompt] entries: packed latents [B, N, 64] by default, decoded images
+    # with output_type "pt" / "np" / "pil")
     @torch.inference_mode()
     def generate_images(self, prompt_embeds: dict[str, torch.Tensor], images_per_prompt: int = 1,
                         height: int | None = None, width: int | None = None, guidance_scale: float | None = None,
-                        **kwargs) -> list[torch.Tensor]:
+                        output_type: str | None = None, **kwargs) -> list:
         pipe = self.create_diffusion_pipeline()
+        output_type = output_type or self.output_type
         out = []
         for i in range(images_per_prompt):
             self.random_generator.manual_seed(self.start_seed + i * self.seed_step)
@@ -435,7 +471,8 @@ class B200FluxImageGenerator(_SavedPromptMixin):
                 callback_on_step_end_tensor_inputs=["latents", "prompt_embeds"],
                 capture_callback=self._call_core_callbacks,
             )[0]
-            out.append(lat.clone())
+            out.append(lat.clone() if output_type == "latent"
+                       else self.decode_latents(lat, height or self.height, width or self.width, output_type))
         return out
 
     # flux_image_generator.py:365-418: CUDA-event ms per image of one pipeline call

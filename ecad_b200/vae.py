@@ -2,8 +2,8 @@
 
 Replaces ``image = self.vae.decode(latents / self.vae.config.scaling_factor, return_dict=False)[0]`` and
 ``image_processor.postprocess`` (/root/reference/ecad/pipelines/pass_through.py:382-396); the module behind
-``self.vae`` is diffusers' ``AutoencoderKL`` (SD VAE for PixArt-alpha, SDXL VAE for PixArt-sigma: same decoder
-architecture, different ``scaling_factor``).  ``B200VaeDecoder`` takes a state dict in diffusers' naming
+``self.vae`` is diffusers' ``AutoencoderKL`` (SD VAE for PixArt-alpha, SDXL VAE for PixArt-sigma, the 16-channel VAE
+for FLUX.1: same decoder architecture, different ``scaling_factor`` / ``shift_factor`` / latent width).  ``B200VaeDecoder`` takes a state dict in diffusers' naming
 (``post_quant_conv.*``, ``decoder.*``), keeps the weights resident as bf16 GEMM operands and runs every layer in
 libecad_b200.so - there is no torch fallback:
 
@@ -36,10 +36,17 @@ class VaeConfig:
     norm_num_groups: int = 32
     norm_eps: float = 1e-6
     scaling_factor: float = 0.18215
+    shift_factor: float = 0.0          # FLUX VAE: latents / scaling_factor + shift_factor
+    use_post_quant_conv: bool = True   # FLUX VAE: False
 
     @property
     def up_widths(self) -> tuple:
         return tuple(reversed(self.block_out_channels))
+
+    @staticmethod
+    def flux() -> "VaeConfig":
+        """black-forest-labs/FLUX.1-dev `vae/config.json`: 16 latent channels, no (post_)quant_conv."""
+        return VaeConfig(latent_channels=16, scaling_factor=0.3611, shift_factor=0.1159, use_post_quant_conv=False)
 
 
 def decoder_layer_names(cfg: VaeConfig = VaeConfig()) -> dict[str, tuple]:
@@ -68,7 +75,8 @@ def decoder_layer_names(cfg: VaeConfig = VaeConfig()) -> dict[str, tuple]:
 
     widths = cfg.up_widths
     top = widths[0]
-    conv("post_quant_conv", cfg.latent_channels, cfg.latent_channels, 1)
+    if cfg.use_post_quant_conv:
+        conv("post_quant_conv", cfg.latent_channels, cfg.latent_channels, 1)
     conv("decoder.conv_in", top, cfg.latent_channels, 3)
     resnet("decoder.mid_block.resnets.0", top, top)
     norm("decoder.mid_block.attentions.0.group_norm", top)
@@ -157,19 +165,18 @@ class B200VaeDecoder:
             else:
                 self._w[name] = f32(sd[name])
                 self._w[base + ".bias"] = f32(sd[base + ".bias"])
-        if cfg.latent_channels != 4 or cfg.out_channels != 3:
-            raise ValueError("the latent preparation / read-out kernels are written for 4 latent and 3 image channels")
+        if cfg.latent_channels not in (4, 16) or cfg.out_channels != 3:
+            raise ValueError("the latent preparation / read-out kernels are written for 4 or 16 latent and 3 image channels")
         self.launches = 0
 
     # ------------------------------------------------------------------------------------------------
     def _new(self, b, h, w, c):
         return torch.empty(b, h + 2, w + 2, c, device=self.device, dtype=torch.bfloat16)
 
-    def _gn(self, x, name, h, w, silu=True, unpadded=False):
-        b, c = x.shape[0], x.shape[-1]
-        out = (torch.empty(b, h * w, c, device=self.device, dtype=torch.bfloat16) if unpadded else torch.empty_like(x))
+    def _gn(self, x, name, h, w, silu=True):
+        out = torch.empty_like(x)
         _lib.groupnorm_nhwc(x, self._w[name + ".weight"], self._w[name + ".bias"], out, self._scratch, h, w,
-                            groups=self.cfg.norm_num_groups, eps=self.cfg.norm_eps, silu=silu, unpadded_out=unpadded)
+                            groups=self.cfg.norm_num_groups, eps=self.cfg.norm_eps, silu=silu)
         self.launches += 3
         return out
 
@@ -189,35 +196,39 @@ class B200VaeDecoder:
     def _attention(self, x, pre, h, w):
         b, c = x.shape[0], x.shape[-1]
         n = h * w
-        if n % 128:
-            raise ValueError(f"mid-block attention needs h*w % 128 == 0, got {h}x{w}")
+        if n % 4:
+            raise ValueError(f"mid-block attention needs h*w % 4 == 0, got {h}x{w}")
+        npad = _pad_to(n, 128)  # token rows per sample: zero rows pad the keys to the GEMM tile, masked in the softmax
         bf = torch.bfloat16
-        t = self._gn(x, pre + ".group_norm", h, w, silu=False, unpadded=True)  # [B, N, C]
-        t2 = t.view(b * n, c)
-        q = torch.empty(b * n, c, device=self.device, dtype=bf)
+        t = torch.zeros(b, npad, c, device=self.device, dtype=bf) if npad != n else \
+            torch.empty(b, n, c, device=self.device, dtype=bf)
+        _lib.groupnorm_nhwc(x, self._w[pre + ".group_norm.weight"], self._w[pre + ".group_norm.bias"], t, self._scratch, h,
+                            w, groups=self.cfg.norm_num_groups, eps=self.cfg.norm_eps, silu=False, unpadded_out=True)
+        t2 = t.view(b * npad, c)
+        q = torch.empty(b * npad, c, device=self.device, dtype=bf)
         k = torch.empty_like(q)
         _lib.gemm_bias(t2, self._w[pre + ".to_q.weight"], self._w[pre + ".to_q.bias"], q)
         _lib.gemm_bias(t2, self._w[pre + ".to_k.weight"], self._w[pre + ".to_k.bias"], k)
-        scores = torch.empty(n, n, device=self.device, dtype=torch.float32)
-        probs = torch.empty(n, n, device=self.device, dtype=bf)
-        vt = torch.empty(c, n, device=self.device, dtype=bf)
-        o = torch.empty(b * n, c, device=self.device, dtype=bf)
+        scores = torch.empty(npad, npad, device=self.device, dtype=torch.float32)
+        probs = torch.empty(npad, npad, device=self.device, dtype=bf)
+        vt = torch.empty(c, npad, device=self.device, dtype=bf)
+        o = torch.empty(b * npad, c, device=self.device, dtype=bf)
         lib = _lib.load()
         stream = _lib.stream_ptr()
         for s in range(b):
-            rows = slice(s * n, (s + 1) * n)
-            # scores = q k^T (fp32 out), probabilities in bf16
-            _lib.check(lib.ecadk_gemm_bias_f32(q[rows].data_ptr(), k[rows].data_ptr(), None, scores.data_ptr(), n, n, c,
-                                               n, n, stream), "vae attention scores")
-            _lib.softmax_rows(scores, probs, 1.0 / math.sqrt(c))
+            rows = slice(s * npad, (s + 1) * npad)
+            # scores = q k^T (fp32 out), probabilities in bf16 (padding keys get 0)
+            _lib.check(lib.ecadk_gemm_bias_f32(q[rows].data_ptr(), k[rows].data_ptr(), None, scores.data_ptr(), npad, npad,
+                                               c, npad, npad, stream), "vae attention scores")
+            _lib.softmax_rows(scores, probs, 1.0 / math.sqrt(c), valid_cols=n)
             # V^T = W_v H^T without the bias; out = P V + b_v (rows of P sum to one)
             _lib.gemm_bias(self._w[pre + ".to_v.weight"], t2[rows], None, vt)
             _lib.gemm_bias(probs, vt, self._w[pre + ".to_v.bias"], o[rows])
-        out_tok = torch.empty(b * n, c, device=self.device, dtype=bf)
-        _lib.gemm_bias(o, self._w[pre + ".to_out.0.weight"], self._w[pre + ".to_out.0.bias"], out_tok)
+        out_tok = torch.empty(b, npad, c, device=self.device, dtype=bf)
+        _lib.gemm_bias(o, self._w[pre + ".to_out.0.weight"], self._w[pre + ".to_out.0.bias"], out_tok.view(b * npad, c))
         out = torch.empty_like(x)
         _lib.vae_add_tokens(x, out_tok, out, h, w)
-        self.launches += 4 + 4 * b
+        self.launches += 7 + 4 * b
         return out
 
     @torch.no_grad()
@@ -233,8 +244,8 @@ class B200VaeDecoder:
         up = 2 ** (len(cfg.block_out_channels) - 1)
         self._scratch = torch.empty(_lib.groupnorm_scratch_bytes(b, h * up, w * up, cfg.norm_num_groups) + 64,
                                     device=self.device, dtype=torch.uint8)
-        x = _lib.vae_prepare_latents(z, self._w["post_quant_conv.weight"], self._w["post_quant_conv.bias"],
-                                     1.0 / cfg.scaling_factor, self._new(b, h, w, 64))
+        x = _lib.vae_prepare_latents(z, self._w.get("post_quant_conv.weight"), self._w.get("post_quant_conv.bias"),
+                                     1.0 / cfg.scaling_factor, self._new(b, h, w, 64), shift=cfg.shift_factor)
         self.launches += 1
         x = self._conv(x, "decoder.conv_in", h, w)
         x = self._resnet(x, "decoder.mid_block.resnets.0", h, w)
@@ -273,7 +284,7 @@ class B200VaeDecoder:
             m = conv(cin, cout, hh, ww) + conv(cout, cout, hh, ww)
             return m + (conv(cin, cout, hh, ww, 1) if cin != cout else 0.0)
 
-        macs += h * w * cfg.latent_channels**2 + conv(cfg.latent_channels, top, h, w)
+        macs += (h * w * cfg.latent_channels**2 if cfg.use_post_quant_conv else 0.0) + conv(cfg.latent_channels, top, h, w)
         macs += 2 * resnet(top, top, h, w)
         n = h * w
         macs += 4.0 * n * top * top + 2.0 * n * n * top

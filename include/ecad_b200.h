@@ -139,8 +139,8 @@ int ecadk_conv_nhwc(const void* x, const void* w, const float* bias, const void*
                     int w_, int c_in, int c_out, int out_ld, int out_cols, int taps, ecadk_stream_t stream);
 
 /* GroupNorm (biased variance, eps inside the sqrt) + affine (+ SiLU when silu != 0) over a bordered NHWC tensor.
- * channels per group in {4, 8, 16}.  unpadded_out != 0 writes plain tokens [batch, h*w, c] instead (the input of the
- * mid-block attention).  scratch: >= ecadk_groupnorm_scratch_bytes(...) bytes, 16-byte aligned (per-block partial
+ * channels per group in {4, 8, 16}.  unpadded_out > 0 writes plain tokens [batch, unpadded_out, c] instead (the input
+ * of the mid-block attention; unpadded_out >= h*w is the token count per sample incl. the caller's zero padding).  scratch: >= ecadk_groupnorm_scratch_bytes(...) bytes, 16-byte aligned (per-block partial
  * sums: every reduction runs in a fixed order, so the result is bit-reproducible).
  * Replaces torch.nn.GroupNorm + SiLU (ResnetBlock2D.norm1/norm2, Decoder.conv_norm_out, Attention.group_norm). */
 size_t ecadk_groupnorm_scratch_bytes(int batch, int h, int w_, int groups);
@@ -151,19 +151,24 @@ int ecadk_groupnorm_nhwc(const void* x, const float* gamma, const float* beta, v
  * Replaces F.interpolate(scale_factor=2, mode="nearest") in Upsample2D. */
 int ecadk_upsample2x_nhwc(const void* x, void* out, int batch, int h, int w_, int c, ecadk_stream_t stream);
 
-/* probs bf16 [rows, cols] = softmax(scale * scores fp32 [rows, cols]) along each row (cols % 4 == 0).
+/* probs bf16 [rows, cols] = softmax(scale * scores fp32 [rows, cols]) over the first valid_cols columns of each row,
+ * 0 in the others (padding keys); cols % 4 == 0, valid_cols % 4 == 0.
  * Replaces the softmax inside F.scaled_dot_product_attention of the single-head mid-block attention. */
-int ecadk_softmax_rows(const float* scores, void* probs, int rows, int cols, float scale, ecadk_stream_t stream);
+int ecadk_softmax_rows(const float* scores, void* probs, int rows, int cols, int valid_cols, float scale,
+                       ecadk_stream_t stream);
 
-/* latents fp32 [batch, 4, h, w] -> post_quant_conv(z * inv_scaling) as bordered NHWC bf16 [batch, h+2, w+2, 64]
- * (channels 4..63 zero: the operand of conv_in).  pq_w fp32 [4, 4] (out, in), pq_b fp32 [4].
- * Replaces `latents / scaling_factor` + AutoencoderKL.post_quant_conv. */
-int ecadk_vae_prepare_latents(const float* z, const float* pq_w, const float* pq_b, float inv_scaling, void* out,
-                              int batch, int h, int w_, ecadk_stream_t stream);
+/* latents fp32 [batch, latent_channels, h, w] (latent_channels 4: SD / SDXL VAE; 16: FLUX VAE) ->
+ * post_quant_conv(z * inv_scaling + shift) as bordered NHWC bf16 [batch, h+2, w+2, 64] (remaining channels zero: the
+ * operand of conv_in).  pq_w fp32 [latent_channels, latent_channels] (out, in) and pq_b fp32 [latent_channels], or both
+ * NULL when the VAE has no post_quant_conv (FLUX).
+ * Replaces `latents / scaling_factor (+ shift_factor)` + AutoencoderKL.post_quant_conv. */
+int ecadk_vae_prepare_latents(const float* z, const float* pq_w, const float* pq_b, float inv_scaling, float shift,
+                              void* out, int batch, int latent_channels, int h, int w_, ecadk_stream_t stream);
 
-/* out (bordered) = x (bordered) + tokens [batch, h*w, c]: the residual connection of the mid-block attention. */
-int ecadk_vae_add_tokens(const void* x, const void* tokens, void* out, int batch, int h, int w_, int c,
-                         ecadk_stream_t stream);
+/* out (bordered) = x (bordered) + tokens [batch, tokens_per_sample, c] (token y*w + x of a sample; tokens_per_sample
+ * >= h*w): the residual connection of the mid-block attention. */
+int ecadk_vae_add_tokens(const void* x, const void* tokens, int tokens_per_sample, void* out, int batch, int h, int w_,
+                         int c, ecadk_stream_t stream);
 
 /* y bf16 [batch*(h+2)*(w+2), 32] (conv_out: channels 0..2 real) -> image fp32 [batch, 3, h, w];
  * denormalize != 0 applies (x / 2 + 0.5).clamp(0, 1) (VaeImageProcessor.postprocess). */

@@ -42,6 +42,8 @@ class OracleVaeConfig:
     norm_num_groups: int = 32
     norm_eps: float = 1e-6
     scaling_factor: float = 0.18215
+    shift_factor: float = 0.0          # FLUX: latents / scaling_factor + shift_factor (FluxPipeline.__call__)
+    use_post_quant_conv: bool = True   # FLUX VAE config: use_post_quant_conv = False
 
 
 def _gn(x, sd, name, cfg, silu):
@@ -76,8 +78,9 @@ def _attention(x, sd, pre, cfg):
 def vae_decode(sd: dict, latents: torch.Tensor, cfg: OracleVaeConfig = OracleVaeConfig(), denormalize: bool = False):
     """latents fp32 [B, 4, h, w] (as the denoising loop leaves them) -> image fp32 [B, 3, 8h, 8w]."""
     sd = {k: v.float() for k, v in sd.items()}
-    x = latents.float() / cfg.scaling_factor
-    x = _conv(x, sd, "post_quant_conv", 0)
+    x = latents.float() / cfg.scaling_factor + cfg.shift_factor
+    if cfg.use_post_quant_conv:
+        x = _conv(x, sd, "post_quant_conv", 0)
     x = _conv(x, sd, "decoder.conv_in", 1)
     x = _resnet(x, sd, "decoder.mid_block.resnets.0", cfg)
     x = _attention(x, sd, "decoder.mid_block.attentions.0", cfg)

@@ -129,6 +129,10 @@ def test_upsample_softmax_prepare_add(cuda_device):
     _lib.softmax_rows(s, p, 1.0 / math.sqrt(512))
     ref = torch.softmax(s / math.sqrt(512), dim=-1)
     assert float((p.float() - ref).abs().max()) < 4e-3 * float(ref.max())
+    _lib.softmax_rows(s, p, 1.0 / math.sqrt(512), valid_cols=1000)  # 24 padding keys: probability 0
+    ref = torch.softmax(s[:, :1000] / math.sqrt(512), dim=-1)
+    assert float(p[:, 1000:].abs().max()) == 0
+    assert float((p[:, :1000].float() - ref).abs().max()) < 4e-3 * float(ref.max())
     # latent preparation
     z = torch.randn(b, 4, h, w, generator=g)
     pw = torch.randn(4, 4, generator=g)
@@ -213,3 +217,56 @@ def test_generator_output_types(cuda_device, tmp_path):
     assert sorted(p.name for p in dst.glob("**/*.jpg")) == ["p0__image_seed:000.jpg", "p1__image_seed:000.jpg"]
     ms = gen.generate_images_timed(emb)  # timed INCLUDING the decode, like the reference's latency figures
     assert ms > 0
+
+
+def test_flux_vae_variant(cuda_device):
+    """The FLUX.1 VAE: 16 latent channels, `latents / scaling_factor + shift_factor`, no post_quant_conv - latent
+    preparation alone, then the whole decoder against the oracle (128 x 96 image)."""
+    from ecad_b200 import _lib
+    from ecad_b200.vae import B200VaeDecoder, VaeConfig, decoder_layer_names, random_init_vae_state_dict
+    from oracle.vae_oracle import OracleVaeConfig, vae_decode
+    cfg = VaeConfig.flux()
+    assert cfg.latent_channels == 16 and not cfg.use_post_quant_conv
+    assert "post_quant_conv.weight" not in decoder_layer_names(cfg)
+    assert decoder_layer_names(cfg)["decoder.conv_in.weight"] == (512, 16, 3, 3)
+    g = torch.Generator().manual_seed(2)
+    z = torch.randn(2, 16, 16, 12, generator=g)
+    lat = torch.full((2, 18, 14, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+    _lib.vae_prepare_latents(z.cuda(), None, None, 1 / cfg.scaling_factor, lat, shift=cfg.shift_factor)
+    assert _border_is_zero(lat) and float(lat[..., 16:].abs().max()) == 0
+    ref = (z / cfg.scaling_factor + cfg.shift_factor).cuda()
+    assert float((_interior(lat)[:, :16] - ref).abs().max() / ref.abs().max()) < 1e-2
+    sd = random_init_vae_state_dict(cfg, seed=1)
+    sd = {k: (v.to(torch.bfloat16).float() if v.dim() >= 2 else v) for k, v in sd.items()}
+    img = B200VaeDecoder(sd, cfg).decode(z.cuda())
+    torch.cuda.synchronize()
+    oref = vae_decode(sd, z, OracleVaeConfig(latent_channels=16, scaling_factor=cfg.scaling_factor,
+                                             shift_factor=cfg.shift_factor, use_post_quant_conv=False))
+    assert img.shape == (2, 3, 128, 96) == tuple(oref.shape)
+    scale = float(oref.abs().max())
+    err = (img.cpu() - oref).abs()
+    assert float(err.max()) < 4e-2 * scale and float(err.mean()) < 6e-3 * scale
+    assert float(F.cosine_similarity(img.cpu().flatten(), oref.flatten(), dim=0)) > 0.999
+
+
+def test_flux_generator_decodes_packed_latents(cuda_device):
+    """B200FluxImageGenerator(output_type="pt"): packed latents [B, N, 64] -> unpack -> FLUX VAE decode, equal to an
+    explicit unpack + decode of the latent output of the same seed."""
+    from ecad_b200.image_generator import B200FluxImageGenerator
+    from ecad_b200.schedule import FluxCacheSchedule
+    from ecad_b200.weights import FluxConfig, flux_random_init_state_dict
+    from test_gpu_flux_parity import SMALL, _embeds, _schedule_flags
+
+    cfg = FluxConfig(**SMALL)
+    steps, rows = 3, cfg.num_layers + cfg.num_single_layers
+    sched = FluxCacheSchedule.from_numpy(_schedule_flags(steps, rows), steps, cfg.num_layers, cfg.num_single_layers,
+                                         "rand", top_level_config={"height": 256, "width": 192})
+    gen = B200FluxImageGenerator(cache_schedule=sched, state_dict=flux_random_init_state_dict(cfg, seed=0), model_config=cfg)
+    emb = _embeds(2, 64, SMALL, seed=4)
+    lat = gen.generate_images(emb)[0]
+    assert lat.shape == (2, 16 * 12, 64)
+    img = gen.generate_images(emb, output_type="pt")[0]
+    assert img.shape == (2, 3, 256, 192) and float(img.min()) >= 0 and float(img.max()) <= 1
+    z = lat.view(2, 16, 12, 16, 2, 2).permute(0, 3, 1, 4, 2, 5).reshape(2, 16, 32, 24)  # FluxPipeline._unpack_latents
+    assert torch.equal(img, gen.create_vae().decode(z, denormalize=True))
+    assert gen.vae_config.scaling_factor == 0.3611 and gen.vae_config.shift_factor == 0.1159
