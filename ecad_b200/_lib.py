@@ -56,6 +56,7 @@ EXPORTED_SYMBOLS = [
     "ecadk_flux_destroy",
     "ecadk_flux_blocks",
     "ecadk_conv_nhwc",
+    "ecadk_conv_up2x_nhwc",
     "ecadk_groupnorm_nhwc",
     "ecadk_groupnorm_scratch_bytes",
     "ecadk_upsample2x_nhwc",
@@ -233,6 +234,7 @@ def load() -> C.CDLL:
         "ecadk_flux_destroy": [p],
         "ecadk_flux_blocks": [p, C.POINTER(EcadkFluxArgs), C.POINTER(C.c_uint8), C.POINTER(i), p],
         "ecadk_conv_nhwc": [p, p, p, p, p, i, i, i, i, i, i, i, i, p],
+        "ecadk_conv_up2x_nhwc": [p, p, p, p, i, i, i, i, i, p],
         "ecadk_groupnorm_nhwc": [p, p, p, p, p, i, i, i, i, i, f, i, i, p],
         "ecadk_groupnorm_scratch_bytes": [i, i, i, i],
         "ecadk_upsample2x_nhwc": [p, p, i, i, i, i, p],
@@ -313,6 +315,13 @@ def conv_nhwc(x, w, bias, out, h, w_, taps, residual=None, out_cols=None):
     c_out = w.shape[0]
     check(load().ecadk_conv_nhwc(ptr(x), ptr(w), ptr(bias), ptr(residual), ptr(out), batch, h, w_, c_in, c_out,
                                  out.shape[-1], c_out if out_cols is None else out_cols, taps, stream_ptr()), "conv_nhwc")
+    return out
+
+
+def conv_up2x_nhwc(x, w4, bias, out, h, w_):
+    """nearest-2x upsample + 3x3 conv as four 4-tap convolutions of x; w4 [4, c_out, 4*c_in] (see the header)."""
+    check(load().ecadk_conv_up2x_nhwc(ptr(x), ptr(w4), ptr(bias), ptr(out), x.shape[0], h, w_, x.shape[-1], w4.shape[1],
+                                      stream_ptr()), "conv_up2x_nhwc")
     return out
 
 

@@ -1787,10 +1787,58 @@ int ecadk_conv_nhwc(const void* x, const void* w, const float* bias, const void*
   p.conv_taps = taps;
   p.conv_cblocks = c_in / kGemmBK;
   p.conv_pitch = w_ + 2;
+  for (int t = 0; t < 9; ++t) p.conv_off[t] = taps == 9 ? (t / 3 - 1) * (w_ + 2) + (t % 3 - 1) : 0;
   p.conv_h = h;
   p.conv_w = w_;
   p.conv_cols = out_cols;
   return launch_gemm<EPI_CONV>(x, w, p, static_cast<cudaStream_t>(stream));
+}
+
+int ecadk_conv_up2x_nhwc(const void* x, const void* w4, const float* bias, void* out, int batch, int h, int w_, int c_in,
+                         int c_out, ecadk_stream_t stream_) {
+  ECADK_REQUIRE(x && w4 && out, "conv_up2x_nhwc: null pointer");
+  ECADK_REQUIRE(batch > 0 && h > 0 && w_ > 0, "conv_up2x_nhwc: bad image size %d x %d x %d", batch, h, w_);
+  ECADK_REQUIRE(c_in > 0 && c_in % 64 == 0 && c_out > 0 && c_out % 128 == 0, "conv_up2x_nhwc: c_in=%d c_out=%d", c_in, c_out);
+  ECADK_REQUIRE(aligned16(out) && aligned16(w4), "conv_up2x_nhwc: 16-byte alignment");
+  const long long rows = static_cast<long long>(batch) * (h + 2) * (w_ + 2);
+  const long long rows_out = static_cast<long long>(batch) * (2 * h + 2) * (2 * w_ + 2);
+  ECADK_REQUIRE(rows_out < (1ll << 31) && batch <= 65535, "conv_up2x_nhwc: %lld output rows", rows_out);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  {
+    ZeroBorderParams z{static_cast<__nv_bfloat16*>(out), batch, 2 * h, 2 * w_, c_out};
+    const int n = (2 * (2 * w_ + 2) + 2 * (2 * h)) * (c_out / 8);
+    zero_border_kernel<<<dim3((n + 255) / 256, batch), 256, 0, stream>>>(z);
+    int rc = check_launch("zero_border_kernel");
+    if (rc) return rc;
+  }
+  for (int a = 0; a < 2; ++a) {
+    for (int b = 0; b < 2; ++b) {
+      GemmParams p;
+      memset(&p, 0, sizeof(p));
+      p.M = static_cast<int>(rows);
+      p.N = c_out;
+      p.K = 4 * c_in;
+      p.bias = bias;
+      p.out = static_cast<__nv_bfloat16*>(out);
+      p.ldo = c_out;
+      p.tokens = 1;
+      p.conv_taps = 4;
+      p.conv_cblocks = c_in / kGemmBK;
+      p.conv_pitch = w_ + 2;
+      // taps (ry, rx): source rows {y-1, y} for output parity 0, {y, y+1} for parity 1 (same for columns)
+      for (int t = 0; t < 4; ++t) p.conv_off[t] = ((t >> 1) + a - 1) * (w_ + 2) + ((t & 1) + b - 1);
+      p.conv_h = h;
+      p.conv_w = w_;
+      p.conv_cols = c_out;
+      p.conv_up = 1;
+      p.conv_up_a = a;
+      p.conv_up_b = b;
+      const __nv_bfloat16* wp = static_cast<const __nv_bfloat16*>(w4) + static_cast<size_t>(a * 2 + b) * c_out * 4 * c_in;
+      int rc = launch_gemm<EPI_CONV>(x, wp, p, stream);
+      if (rc) return rc;
+    }
+  }
+  return ECADK_OK;
 }
 
 size_t ecadk_groupnorm_scratch_bytes(int batch, int h, int w_, int groups) {

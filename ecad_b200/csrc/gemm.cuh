@@ -58,9 +58,14 @@ struct GemmParams {
   // its A rows are the output rows shifted by (ky-1)*conv_pitch + (kx-1) - a plain 2-D TMA load at a shifted row
   // coordinate (rows outside the matrix are zero-filled).  W is [N, taps*C], tap-major.  conv_taps <= 1: ordinary GEMM.
   int conv_taps, conv_cblocks, conv_pitch;
+  int conv_off[9];  // row offset of every tap (3x3: (ky-1)*conv_pitch + (kx-1))
   // EPI_CONV: border mask from (conv_h, conv_w); optional bf16 residual [M, ldo2] in out2; only chunks that start
   // below conv_cols are stored (conv_out: 3 real output channels in a 32-column buffer)
   int conv_h, conv_w, conv_cols;
+  // conv_up != 0: the convolution of a nearest-2x-upsampled image, computed on the ORIGINAL image - this launch produces
+  // the output pixels of parity (conv_up_a, conv_up_b): input pixel (y, x) -> output pixel (2y-1+a, 2x-1+b) of the
+  // bordered [batch, 2h+2, 2w+2, N] output (bordered coordinates; see ecadk_conv_up2x_nhwc)
+  int conv_up, conv_up_a, conv_up_b;
   // EPI_UNPATCHIFY (column o = (p*2+q)*C + c of token n = i*Wp + j of sample s)
   float* unp_out;
   int unp_wp, unp_hp, unp_c, unp_cols;
@@ -98,9 +103,8 @@ __device__ __forceinline__ void a_tile_coords(const GemmParams& p, const int kb,
   row = m0;
   if (p.conv_taps > 1) {
     const int tap = kb / p.conv_cblocks;
-    const int ky = tap / 3, kx = tap - 3 * ky;
     col = (kb - tap * p.conv_cblocks) * kGemmBK;
-    row = m0 + (ky - 1) * p.conv_pitch + (kx - 1);
+    row = m0 + p.conv_off[tap];
   }
 }
 
@@ -141,9 +145,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int row = row_base + i * 4 + rs;
-      const int r = row % plane;
+      const int bimg = row / plane;
+      const int r = row - bimg * plane;
       const int y = r / (p.conv_w + 2), x = r - y * (p.conv_w + 2);
       if (y >= 1 && y <= p.conv_h && x >= 1 && x <= p.conv_w) interior |= 1u << i;
+      // the row this lane WRITES: itself, or its parity's pixel of the upsampled output
+      row_off[i] = p.conv_up ? (bimg * (2 * p.conv_h + 2) + (2 * y - 1 + p.conv_up_a)) * (2 * p.conv_w + 2) +
+                                   (2 * x - 1 + p.conv_up_b)
+                             : row;
     }
   }
   if constexpr (EPI == EPI_HEADMAJOR) {
@@ -278,11 +287,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
             o.x += r01.x; o.y += r01.y; o.z += r23.x; o.w += r23.y;
           }
           uint2 w = make_uint2(0u, 0u);  // border pixels stay zero: they are the next convolution's padding
-          if ((interior >> i) & 1u) {
+          const bool inside = (interior >> i) & 1u;
+          if (inside) {
             w.x = pack_bf16x2(o.x, o.y);
             w.y = pack_bf16x2(o.z, o.w);
           }
-          *reinterpret_cast<uint2*>(p.out + static_cast<size_t>(row) * p.ldo + col) = w;
+          // (upsampling form: border rows of the input map to nothing - the output's border is zeroed by the caller)
+          if (inside || !p.conv_up)
+            *reinterpret_cast<uint2*>(p.out + static_cast<size_t>(row_off[i]) * p.ldo + col) = w;
         } else if constexpr (EPI == EPI_BIAS_F32) {
           if (col < p.f32_cols) *reinterpret_cast<float4*>(p.f32_out + static_cast<size_t>(row) * p.ldo + col) = o;
         } else {  // EPI_UNPATCHIFY: 4 consecutive columns = 4 channels of one (p, q) sub-pixel

@@ -276,6 +276,32 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const UpsampleParams p)
   reinterpret_cast<uint4*>(p.out)[idx] = o;
 }
 
+// zero the one-pixel border of a bordered NHWC tensor (the upsampling convolution writes interior pixels only);
+// one thread per (border pixel, 8-channel slot), grid (ceil(border * slots / 256), B)
+struct ZeroBorderParams {
+  __nv_bfloat16* out;
+  int B, H, W, C;
+};
+__global__ void __launch_bounds__(256) zero_border_kernel(const ZeroBorderParams p) {
+  const int slots = p.C >> 3;
+  const int border = 2 * (p.W + 2) + 2 * p.H;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= border * slots) return;
+  const int k = i / slots, slot = i - k * slots;
+  int y, x;
+  if (k < p.W + 2) {
+    y = 0; x = k;
+  } else if (k < 2 * (p.W + 2)) {
+    y = p.H + 1; x = k - (p.W + 2);
+  } else {
+    const int j = k - 2 * (p.W + 2);
+    y = 1 + (j >> 1);
+    x = (j & 1) ? p.W + 1 : 0;
+  }
+  const size_t pix = (static_cast<size_t>(blockIdx.y) * (p.H + 2) + y) * (p.W + 2) + x;
+  reinterpret_cast<uint4*>(p.out)[pix * slots + slot] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // softmax over rows of fp32 scores (cols % 128 == 0, cols <= 8192): p = softmax(scale * s) -> bf16; one warp per row
 // columns >= valid (padding keys; valid % 4 == 0) get probability 0

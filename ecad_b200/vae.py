@@ -117,6 +117,27 @@ def _pad_to(n: int, m: int) -> int:
     return (n + m - 1) // m * m
 
 
+def pack_upsample_conv(w: torch.Tensor, cin_p: int, cout_p: int) -> torch.Tensor:
+    """3x3 kernel [cout, cin, 3, 3] of the convolution that follows a nearest 2x upsampling -> the four 2x2 kernels
+    ``[4 (a*2+b), cout_p, 4 (ry*2+rx) * cin_p + c]`` that act on the ORIGINAL image (ecadk_conv_up2x_nhwc): output row
+    ``2y + a`` reads upsampled rows ``2y + a + ky - 1``, i.e. source rows ``y - 1, y, y`` (a = 0) or ``y, y, y + 1``
+    (a = 1); kernel rows that land on the same source row are summed (in fp32, before the bf16 rounding)."""
+    cout, cin = w.shape[:2]
+    groups = {0: ([0], [1, 2]), 1: ([0, 1], [2])}  # parity -> kernel indices of source offsets (first, second)
+    out = torch.zeros(4, cout_p, 4, cin_p)
+    wf = w.detach().float()
+    for a in range(2):
+        for b in range(2):
+            for ry in range(2):
+                for rx in range(2):
+                    acc = torch.zeros(cout, cin)
+                    for ky in groups[a][ry]:
+                        for kx in groups[b][rx]:
+                            acc += wf[:, :, ky, kx]
+                    out[a * 2 + b, :cout, ry * 2 + rx, :cin] = acc
+    return out.reshape(4, cout_p, 4 * cin_p)
+
+
 class B200VaeDecoder:
     """``decode(latents) -> image``: AutoencoderKL.decode(latents / scaling_factor) on the GPU through the C ABI."""
 
@@ -150,10 +171,17 @@ class B200VaeDecoder:
             b[:cout] = sd[name + ".bias"].detach().float()
             self._w[name + ".bias"] = b.to(dev)
 
+        # Upsample2D convolutions run on the original image as four 2x2 kernels (16 instead of 36 tap-products per
+        # input pixel, no upsampled tensor); fused_upsample = False keeps upsample kernel + 3x3 convolution (A/B, tests)
+        self.fused_upsample = True
         for name, shape in decoder_layer_names(cfg).items():
             if not name.endswith(".weight"):
                 continue
             base = name[: -len(".weight")]
+            if ".upsamplers." in name:
+                cout, cin = shape[:2]
+                self._w[base + ".weight4"] = pack_upsample_conv(sd[name], _pad_to(cin, 64), _pad_to(cout, 128)).to(
+                    device=dev, dtype=torch.bfloat16).contiguous()
             if base == "post_quant_conv":
                 self._w[base + ".weight"] = f32(sd[name].reshape(cfg.latent_channels, cfg.latent_channels))
                 self._w[base + ".bias"] = f32(sd[base + ".bias"])
@@ -256,10 +284,17 @@ class B200VaeDecoder:
             for j in range(cfg.layers_per_block + 1):
                 x = self._resnet(x, f"decoder.up_blocks.{i}.resnets.{j}", h, w)
             if i < n_up - 1:
-                up = _lib.upsample2x_nhwc(x, self._new(b, 2 * h, 2 * w, x.shape[-1]), h, w)
-                h, w = 2 * h, 2 * w
-                self.launches += 1
-                x = self._conv(up, f"decoder.up_blocks.{i}.upsamplers.0.conv", h, w)
+                name = f"decoder.up_blocks.{i}.upsamplers.0.conv"
+                if self.fused_upsample:
+                    w4 = self._w[name + ".weight4"]
+                    x = _lib.conv_up2x_nhwc(x, w4, self._w[name + ".bias"], self._new(b, 2 * h, 2 * w, w4.shape[1]), h, w)
+                    h, w = 2 * h, 2 * w
+                    self.launches += 5
+                else:
+                    up = _lib.upsample2x_nhwc(x, self._new(b, 2 * h, 2 * w, x.shape[-1]), h, w)
+                    h, w = 2 * h, 2 * w
+                    self.launches += 1
+                    x = self._conv(up, name, h, w)
         x = self._gn(x, "decoder.conv_norm_out", h, w)
         y = torch.empty(b, h + 2, w + 2, 32, device=self.device, dtype=torch.bfloat16)
         _lib.conv_nhwc(x, self._w["decoder.conv_out.weight"], self._w["decoder.conv_out.bias"], y, h, w, 9,
@@ -294,7 +329,7 @@ class B200VaeDecoder:
                 macs += resnet(prev if j == 0 else wdt, wdt, hh, ww)
             if i < len(widths) - 1:
                 hh, ww = 2 * hh, 2 * ww
-                macs += conv(wdt, wdt, hh, ww)
+                macs += conv(wdt, wdt, hh, ww)  # the reference's count (3x3 on the upsampled image)
             prev = wdt
         macs += conv(widths[-1], cfg.out_channels, hh, ww)
         return 2.0 * macs * batch

@@ -138,6 +138,17 @@ int ecadk_cfg_dpm_step(const float* noise, float* latents, float* x0_prev, int b
 int ecadk_conv_nhwc(const void* x, const void* w, const float* bias, const void* residual, void* out, int batch, int h,
                     int w_, int c_in, int c_out, int out_ld, int out_cols, int taps, ecadk_stream_t stream);
 
+/* Upsample2D = nearest 2x + 3x3 convolution, computed WITHOUT materialising the upsampled image: an output pixel of
+ * parity (a, b) sees only a 2x2 neighbourhood of the original image (kernel rows / columns that fall on the same source
+ * pixel are pre-summed), so the layer is four 4-tap implicit GEMMs on x - 16 instead of 36 tap-products per input
+ * pixel.  x bf16 [batch, h+2, w+2, c_in]; out bf16 [batch, 2h+2, 2w+2, c_out] (border zeroed here);
+ * w4 bf16 [4 (a*2+b)][c_out][4 (ry*2+rx) * c_in + c]: for parity a the source rows are {y-1, y} (a = 0) or {y, y+1}
+ * (a = 1), with W'[ry] = sum of the kernel rows ky whose upsampled row (2y + a + ky - 1) / 2 is that source row; same
+ * for columns (ecad_b200/vae.py::pack_upsample_conv builds it).
+ * Replaces Upsample2D.forward (F.interpolate(scale_factor=2, mode="nearest") + conv) in UpDecoderBlock2D. */
+int ecadk_conv_up2x_nhwc(const void* x, const void* w4, const float* bias, void* out, int batch, int h, int w_, int c_in,
+                         int c_out, ecadk_stream_t stream);
+
 /* GroupNorm (biased variance, eps inside the sqrt) + affine (+ SiLU when silu != 0) over a bordered NHWC tensor.
  * channels per group in {4, 8, 16}.  unpadded_out > 0 writes plain tokens [batch, unpadded_out, c] instead (the input
  * of the mid-block attention; unpadded_out >= h*w is the token count per sample incl. the caller's zero padding).  scratch: >= ecadk_groupnorm_scratch_bytes(...) bytes, 16-byte aligned (per-block partial

@@ -62,6 +62,27 @@ def test_conv_nhwc(cuda_device, b, h, w, cin, cout, taps, res):
     assert err < 1e-2, err  # bf16 output rounding (2^-8 relative)
 
 
+@pytest.mark.parametrize("b,h,w,cin,cout", [(2, 16, 12, 128, 128), (3, 32, 32, 512, 512), (20, 64, 64, 256, 256)])
+def test_conv_up2x_nhwc(cuda_device, b, h, w, cin, cout):
+    """Upsample2D (nearest 2x + 3x3 conv) as four 2x2-tap convolutions of the original image."""
+    from ecad_b200 import _lib
+    from ecad_b200.vae import pack_upsample_conv
+    g = torch.Generator().manual_seed(b + h + cin)
+    x = torch.randn(b, cin, h, w, generator=g)
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9)).to(torch.bfloat16).float()
+    bias = torch.randn(cout, generator=g)
+    xb = _bordered(x)
+    w4 = pack_upsample_conv(wt, cin, cout).to(device="cuda", dtype=torch.bfloat16).contiguous()
+    out = torch.full((b, 2 * h + 2, 2 * w + 2, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+    _lib.conv_up2x_nhwc(xb, w4, bias.cuda(), out, h, w)
+    torch.cuda.synchronize()
+    ref = F.conv2d(F.interpolate(_interior(xb), scale_factor=2.0, mode="nearest"), wt.cuda(), bias.cuda(), padding=1)
+    assert torch.isfinite(out.float()).all() and _border_is_zero(out)
+    # the pre-summed 2x2 kernels are rounded to bf16 once more than the 3x3 kernel: 2^-8 relative on sums of <= 4 terms
+    err = float((_interior(out) - ref).abs().max() / ref.abs().max())
+    assert err < 1.5e-2, err
+
+
 def test_conv_nhwc_few_output_channels(cuda_device):
     """conv_out: 3 real channels out of 128 weight rows, written into a 32-column buffer."""
     from ecad_b200 import _lib
@@ -178,6 +199,10 @@ def test_vae_decode_matches_oracle(cuda_device, hw, batch):
     # determinism, and the denormalised form
     img2 = dec.decode(lat.cuda(), denormalize=True)
     assert torch.allclose(img2, (img / 2 + 0.5).clamp(0, 1), atol=1e-6)
+    # the un-fused form of Upsample2D (upsample kernel + 3x3 convolution) agrees with the fused one
+    dec.fused_upsample = False
+    img3 = dec.decode(lat.cuda())
+    assert float((img3 - img).abs().max()) < 4e-2 * scale and float((img3.cpu() - ref).abs().max()) < 4e-2 * scale
 
 
 def test_generator_output_types(cuda_device, tmp_path):

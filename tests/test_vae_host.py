@@ -78,3 +78,27 @@ def test_flops_model_matches_published_order_of_magnitude():
     # SD VAE decode of a 64 x 64 latent (512 x 512 image): ~1.24 TMACs = 2.5 TFLOP (widely quoted figure)
     f = B200VaeDecoder.flops(1, 64, 64)
     assert 2.3e12 < f < 2.7e12
+
+
+def test_upsample_conv_equals_four_2x2_convs_on_the_original_image():
+    """pack_upsample_conv: conv3x3(nearest_2x(x)) == interleave of four 2x2-tap convolutions of x (the identity
+    ecadk_conv_up2x_nhwc relies on), checked with plain torch on the CPU, including the image border."""
+    from ecad_b200.vae import pack_upsample_conv
+    g = torch.Generator().manual_seed(0)
+    b, cin, cout, h, w = 2, 5, 7, 6, 9
+    x = torch.randn(b, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), wt, padding=1)
+    w4 = pack_upsample_conv(wt, cin, cout).view(4, cout, 4, cin)
+    xp = F.pad(x, (1, 1, 1, 1))
+    got = torch.zeros(b, cout, 2 * h, 2 * w)
+    for a in range(2):
+        for bb in range(2):
+            acc = torch.zeros(b, cout, h, w)
+            for ry in range(2):
+                for rx in range(2):
+                    oy, ox = ry + a - 1, rx + bb - 1  # source offset of this tap
+                    src = xp[:, :, 1 + oy:1 + oy + h, 1 + ox:1 + ox + w]
+                    acc += torch.einsum("bchw,oc->bohw", src, w4[a * 2 + bb, :, ry * 2 + rx, :])
+            got[:, :, a::2, bb::2] = acc
+    assert torch.allclose(got, ref, atol=1e-4)

@@ -15,6 +15,8 @@ from ecad_b200.vae import B200VaeDecoder, VaeConfig, random_init_vae_state_dict 
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 hw = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 dec = B200VaeDecoder(random_init_vae_state_dict(VaeConfig(), 0))
+if len(sys.argv) > 3 and sys.argv[3] == "nofuse":  # Upsample2D as upsample kernel + 3x3 convolution
+    dec.fused_upsample = False
 lat = torch.randn(batch, 4, hw, hw, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
 for _ in range(2):
     dec.decode(lat)
