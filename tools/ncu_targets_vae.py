@@ -33,6 +33,18 @@ def conv(b, h, w, cin, cout, taps=9, res=False):
     torch.cuda.synchronize()
 
 
+def conv_up(b, h, w, cin, cout):
+    from ecad_b200.vae import pack_upsample_conv
+    x = bordered(b, h, w, cin)
+    wt = torch.randn(cout, cin, 3, 3, generator=torch.Generator().manual_seed(0)) / math.sqrt(9 * cin)
+    w4 = pack_upsample_conv(wt, cin, cout).to(device=dev, dtype=bf).contiguous()
+    bias = torch.randn(cout, device=dev, generator=g)
+    out = torch.empty(b, 2 * h + 2, 2 * w + 2, cout, device=dev, dtype=bf)
+    for _ in range(2):
+        _lib.conv_up2x_nhwc(x, w4, bias, out, h, w)
+    torch.cuda.synchronize()
+
+
 def groupnorm(b, h, w, c):
     x = bordered(b, h, w, c)
     gamma = torch.ones(c, device=dev)
@@ -71,6 +83,7 @@ conv(16, 256, 256, 128, 128, res=True)   # up-block 3 (C_out = 128)
 conv(32, 128, 128, 256, 256)             # up-block 2
 conv(100, 64, 64, 512, 512)              # up-block 1
 conv(32, 128, 128, 512, 256, taps=1)     # 1x1 shortcut
+conv_up(32, 64, 64, 512, 512)            # Upsample2D of up-block 1: four 2x2-tap GEMMs on the 64 x 64 image
 groupnorm(16, 256, 256, 128)
 ws = torch.empty(16 << 20, dtype=torch.uint8, device=dev)
 _lib.set_splitk_workspace(ws)
