@@ -259,12 +259,24 @@ class B200VaeDecoder:
         self.launches += 7 + 4 * b
         return out
 
+    # bytes of the largest activation a single decode pass may hold (bf16 [b, 8h+2, 8w+2, 2*C_last]); batches above it
+    # are decoded in slices (diffusers' `enable_slicing`, sized to the 180 GB of a B200: a pass keeps ~5 such tensors)
+    max_activation_bytes = 8 << 30
+
     @torch.no_grad()
     def decode(self, latents: torch.Tensor, denormalize: bool = False) -> torch.Tensor:
         """latents fp32 ``[B, 4, h, w]`` as the denoising loop leaves them (NOT yet divided by ``scaling_factor``) ->
         image fp32 ``[B, 3, 8h, 8w]``; ``denormalize`` applies ``(x / 2 + 0.5).clamp(0, 1)``."""
         if latents.dim() != 4 or latents.shape[1] != self.cfg.latent_channels:
             raise ValueError(f"latents must be [B, {self.cfg.latent_channels}, h, w], got {tuple(latents.shape)}")
+        up = 2 ** (len(self.cfg.block_out_channels) - 1)
+        per_sample = (latents.shape[2] * up + 2) * (latents.shape[3] * up + 2) * 2 * self.cfg.up_widths[-1] * 2
+        chunk = max(1, int(self.max_activation_bytes // per_sample))
+        if latents.shape[0] > chunk:
+            return torch.cat([self._decode(latents[i:i + chunk], denormalize) for i in range(0, latents.shape[0], chunk)])
+        return self._decode(latents, denormalize)
+
+    def _decode(self, latents: torch.Tensor, denormalize: bool) -> torch.Tensor:
         cfg = self.cfg
         z = latents.to(device=self.device, dtype=torch.float32).contiguous()
         b, _, h, w = z.shape

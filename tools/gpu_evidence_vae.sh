@@ -5,8 +5,8 @@ mkdir -p gpurun_out
 CS=/usr/local/cuda/bin/compute-sanitizer
 echo "=== ncu full"
 timeout 900 ncu --set full --clock-control none --import-source on -k "regex:gemm2_bf16|gemm_splitk|gn_stats|gn_apply|upsample2x" -s 0 -c 34 \
-  -o gpurun_out/prof_r2_vae_splitk -f python tools/ncu_targets_vae.py > gpurun_out/ncu_targets_vae.log 2>&1; tail -2 gpurun_out/ncu_targets_vae.log
-python tools/summarize_ncu.py gpurun_out/prof_r2_vae_splitk.ncu-rep gpurun_out/r2_vae_splitk_ncu_full 2>&1 | tail -30
+  -o /tmp/prof_r2_vae_splitk -f python tools/ncu_targets_vae.py > gpurun_out/ncu_targets_vae.log 2>&1; tail -2 gpurun_out/ncu_targets_vae.log
+python tools/summarize_ncu.py /tmp/prof_r2_vae_splitk.ncu-rep gpurun_out/r2_vae_splitk_ncu_full 2>&1 | tail -30
 echo "=== memcheck: VAE entry points (small shapes) + split-K GEMMs"
 timeout -s KILL 1200 $CS --tool memcheck --error-exitcode 7 --print-limit 20 \
   python -m pytest tests/test_gpu_vae.py tests/test_gpu_kernels.py -m gpu -q -x --tb=line -p no:cacheprovider \
