@@ -471,7 +471,8 @@ int launch_gemm2_tap3_inst(const CUtensorMap& ta, const CUtensorMap& tb, const E
     ECADK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
-  const int tiles = ((p.M + 2 * kGemmBM - 1) / (2 * kGemmBM)) * (p.N / 128);
+  const int rows_pair = 2 * Cfg::kSub * kGemmBM;
+  const int tiles = ((p.M + rows_pair - 1) / rows_pair) * (p.N / 128);
   const int pairs = num_sms() / 2;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
   launch_pdl(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, ta, ta, tb, tb, em.x, em.cache, em.xb, p, 0);

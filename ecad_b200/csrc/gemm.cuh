@@ -867,20 +867,27 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 // =====================================================================================================
 // TAP3 (3x3 convolutions, see below): a stage holds ONE A tile of 128 + 8 rows that starts one pixel to the left of
 // the output rows, and the three W tiles of the taps (ky, 0..2) that read it.
+// Each CTA computes TWO 128-row sub-tiles there (rows m0 .. m0+255), which share the stage's W tiles: with one sub-tile
+// the narrow (C_out = 128) tile is bound by its W stream - 24 KB of W per 17 KB of A per 768 MMA clocks is the SM's L2
+// port (ncu: tensor pipe 55-66 %).  The two accumulators sit side by side in one 256-column TMEM buffer.
 constexpr int kTap3Rows = kGemmBM + 8;
+constexpr int kTap3Sub = 2;
 template <int BN, int EPI = 0, bool TAP3 = false>
 struct Gemm2Cfg {
-  static constexpr int kBytesA = (TAP3 ? kTap3Rows : kGemmBM) * kGemmBK * 2;  // this CTA's rows of A: 16 KB (17 KB)
-  static constexpr int kStageA = (kBytesA + 1023) / 1024 * 1024;
+  static constexpr int kSub = TAP3 ? kTap3Sub : 1;             // 128-row sub-tiles per CTA
+  static constexpr int kBytesA = (TAP3 ? kTap3Rows : kGemmBM) * kGemmBK * 2;  // one A tile: 16 KB (17 KB)
+  static constexpr int kTileA = (kBytesA + 1023) / 1024 * 1024;
+  static constexpr int kStageA = kSub * kTileA;
   static constexpr int kTileB = (BN / 2) * kGemmBK * 2;        // this CTA's half of one W tile
   static constexpr int kStageB = (TAP3 ? 3 : 1) * kTileB;
   static constexpr int kStage = kStageA + kStageB;
   static constexpr int kEpiBytes = epi_stage_bytes(EPI);
-  static constexpr int kStages = fit_stages(TAP3 ? 4 : ((BN <= 128) ? 7 : (BN <= 192 ? 6 : 5)), kStage, EPI);
+  static constexpr int kStages = fit_stages(TAP3 ? 3 : ((BN <= 128) ? 7 : (BN <= 192 ? 6 : 5)), kStage, EPI);
+  static_assert(!TAP3 || kTap3Sub * BN <= 256, "the sub-tile accumulators share one 256-column TMEM buffer");
   static constexpr int kAccStride = 256;
   static constexpr int kTmemCols = 512;
   static constexpr int kSmemBytes = kStages * kStage + kEpiBytes + 1024 + 256;
-  static_assert(kStages >= 4, "GEMM pipeline depth");
+  static_assert(kStages >= (TAP3 ? 3 : 4), "GEMM pipeline depth");
 };
 
 // TAP3 = true (3x3 convolution, taps of one kernel row share their A tile): the implicit GEMM above fetches every A block
@@ -915,7 +922,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const uint32_t cta = cluster_ctarank();  // 0 = leader
   const int pair = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
-  const int num_m = (p.M + 2 * kGemmBM - 1) / (2 * kGemmBM);
+  constexpr int kRowsCta = Cfg::kSub * kGemmBM;  // rows of a tile per CTA (the pair's tile has twice as many)
+  const int num_m = (p.M + 2 * kRowsCta - 1) / (2 * kRowsCta);
   const int num_n_full = (p.N - tail) / BN;
   const int num_n = num_n_full + (tail ? 1 : 0);
   const int num_tiles = num_m * num_n;
@@ -951,7 +959,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-      const int m0 = (tile / num_n) * (2 * kGemmBM) + cta * kGemmBM;
+      const int m0 = (tile / num_n) * (2 * kRowsCta) + cta * kRowsCta;
       const int n_idx = tile % num_n;
       const bool is_tail = n_idx >= num_n_full;
       const int bn_cur = is_tail ? tail : BN;
@@ -962,7 +970,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int n0 = n_idx * BN + cta * (bn_cur / 2);
         const CUtensorMap* tb = is_tail ? &tmap_b_tail : &tmap_b;
         const uint32_t stage_bytes =
-            TAP3 ? 2 * (Cfg::kBytesA + Cfg::kStageB) : 2 * (Cfg::kStageA + (bn_cur / 2) * kGemmBK * 2);
+            TAP3 ? 2 * (Cfg::kSub * Cfg::kBytesA + Cfg::kStageB) : 2 * (Cfg::kStageA + (bn_cur / 2) * kGemmBK * 2);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStage;
@@ -970,7 +978,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (cta == 0) mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
           if constexpr (TAP3) {
             const int ky = kb / p.conv_cblocks, cb = kb - ky * p.conv_cblocks;
-            tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], cb * kGemmBK, m0 + (ky - 1) * p.conv_pitch - 1);
+#pragma unroll
+            for (int sub = 0; sub < Cfg::kSub; ++sub)
+              tma_load_2d_2sm(sa + sub * Cfg::kTileA, &tmap_a, &full_bar[stage], cb * kGemmBK,
+                              m0 + sub * kGemmBM + (ky - 1) * p.conv_pitch - 1);
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx)
               tma_load_2d_2sm(sb + kx * Cfg::kTileB, tb, &full_bar[stage],
@@ -1012,15 +1023,18 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           const uint32_t sb = sa + Cfg::kStageA;
           if constexpr (TAP3) {
 #pragma unroll
+            for (int sub = 0; sub < Cfg::kSub; ++sub) {
+#pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
               // rows kx .. kx + 127 of the 136-row tile: start address + kx rows.  The 128B swizzle is a function of
               // the absolute shared-memory address bits (the tile base stays 1024-byte aligned), so the descriptor's
               // matrix-base-offset field stays 0 (measured: setting it to kx reads the wrong 16-byte pieces)
-              const uint64_t da = make_smem_desc(sa + kx * 128, 16, 1024, kLayoutSW128);
+              const uint64_t da = make_smem_desc(sa + sub * Cfg::kTileA + kx * 128, 16, 1024, kLayoutSW128);
               const uint64_t db = make_smem_desc(sb + kx * Cfg::kTileB, 16, 1024, kLayoutSW128);
 #pragma unroll
               for (int k = 0; k < kGemmBK / 16; ++k)
-                umma_bf16_ss_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | kx | k) != 0);
+                umma_bf16_ss_2sm(d_tmem + sub * BN, da + 2 * k, db + 2 * k, idesc, (kb | kx | k) != 0);
+            }
             }
           } else {
             const uint64_t da = make_smem_desc(sa, 16, 1024, kLayoutSW128);
@@ -1050,7 +1064,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-      const int m0 = (tile / num_n) * (2 * kGemmBM) + cta * kGemmBM;
+      const int m0 = (tile / num_n) * (2 * kRowsCta) + cta * kRowsCta;
       const int n_idx = tile % num_n;
       const int n0 = n_idx * BN;
       const int n_chunks = (n_idx >= num_n_full ? tail : BN) / 32;
@@ -1067,7 +1081,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                                    (warp - 2) >> 2, row_base, n0, n_chunks);
       } else {
         float* stage = epi_stage + (warp - 2) * 32 * kEpiPitch;
-        epilogue_tile<EPI>(p, t_row, stage, lane, (warp - 2) >> 2, row_base, n0, n_chunks);
+#pragma unroll 1
+        for (int sub = 0; sub < Cfg::kSub; ++sub)  // TAP3: the second sub-tile's accumulator follows the first in TMEM
+          epilogue_tile<EPI>(p, t_row + sub * BN, stage, lane, (warp - 2) >> 2, row_base + sub * kGemmBM, n0, n_chunks);
       }
       tc_fence_before();
       __syncwarp();
