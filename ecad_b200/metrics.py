@@ -60,7 +60,9 @@ def macs_metrics(schedule: CacheSchedule, tokens: int = 256, text_tokens: int | 
 
 
 def latency_metrics(image_generator, prompt_embeds: dict, num_samples: int = 5, warmup_steps: int = 1) -> dict[str, Any]:
-    """compute_latency.py:52-73: ``warmup_steps + num_samples`` timed generations of one batch, ms per image."""
+    """compute_latency.py:52-73: ``warmup_steps + num_samples`` timed generations of one batch, ms per image.  The
+    reference's figure includes the VAE decode and the PIL conversion; a generator built with ``output_type="pt"`` /
+    ``"pil"`` times the same span (the default ``"latent"`` stops after the denoising loop) - the block records which."""
     import torch
 
     times = [float(image_generator.generate_images_timed(prompt_embeds)) for _ in range(warmup_steps + num_samples)]
@@ -71,6 +73,7 @@ def latency_metrics(image_generator, prompt_embeds: dict, num_samples: int = 5, 
         "num_samples": num_samples,
         "warmup_steps": warmup_steps,
         "gpu": torch.cuda.get_device_name(0),
+        "output_type": getattr(image_generator, "output_type", "latent"),
         "warmups": warmups,
         "latencies": latencies,
     }
