@@ -66,6 +66,8 @@ EXPORTED_SYMBOLS = [
     "ecadk_vae_finish",
     "ecadk_profile_start",
     "ecadk_profile_stop",
+    "ecadk_set_nvtx",
+    "ecadk_nvtx_ranges",
 ]
 
 
@@ -244,6 +246,8 @@ def load() -> C.CDLL:
         "ecadk_vae_finish": [p, p, i, i, i, i, p],
         "ecadk_profile_start": [],
         "ecadk_profile_stop": [C.POINTER(EcadkProfileRecord)],
+        "ecadk_set_nvtx": [i],
+        "ecadk_nvtx_ranges": [],
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)
@@ -251,6 +255,7 @@ def load() -> C.CDLL:
         fn.restype = C.c_int
     lib.ecadk_splitk_launches.restype = C.c_longlong
     lib.ecadk_groupnorm_scratch_bytes.restype = C.c_size_t
+    lib.ecadk_nvtx_ranges.restype = C.c_longlong
     if lib.ecadk_abi_version() != 1:
         raise RuntimeError(f"libecad_b200.so ABI version {lib.ecadk_abi_version()} != 1")
     _lib = lib
@@ -420,3 +425,47 @@ def profile_stop() -> dict[str, dict[str, float]]:
     check(load().ecadk_profile_stop(recs), "profile_stop")
     return {n: {"launches": int(r.launches), "total_ms": r.total_ms, "flops": r.flops, "bytes": r.bytes}
             for n, r in zip(PROF_CLASSES, recs)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# NVTX.  The library names one range per executor call and per executed sub-block
+# (include/ecad_b200.h: ecadk_set_nvtx); the host side adds the levels above it - denoising step, transformer forward,
+# VAE decoder stage - through torch's bundled NVTX.  Everything is off unless ECADK_NVTX=1 or set_nvtx(True).
+# ---------------------------------------------------------------------------------------------------
+_nvtx_on = os.environ.get("ECADK_NVTX", "0") not in ("", "0")
+
+
+def set_nvtx(on: bool) -> None:
+    global _nvtx_on
+    _nvtx_on = bool(on)
+    check(load().ecadk_set_nvtx(int(_nvtx_on)), "set_nvtx")
+
+
+def nvtx_enabled() -> bool:
+    return _nvtx_on
+
+
+def nvtx_ranges() -> int:
+    """Ranges the library has pushed so far."""
+    return int(load().ecadk_nvtx_ranges())
+
+
+class nvtx_range:
+    """``with nvtx_range("step 03"):`` - a host-side NVTX range when tracing is on, nothing otherwise."""
+
+    __slots__ = ("name", "live")
+
+    def __init__(self, name: str):
+        self.name = name
+        self.live = False
+
+    def __enter__(self):
+        if _nvtx_on:
+            torch.cuda.nvtx.range_push(self.name)
+            self.live = True
+        return self
+
+    def __exit__(self, *exc):
+        if self.live:
+            torch.cuda.nvtx.range_pop()
+        return False

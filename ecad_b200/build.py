@@ -10,7 +10,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libecad_b200.so"
 SOURCES = [CSRC / "capi.cu"]
-HEADERS = [CSRC / "ptx.cuh", CSRC / "gemm.cuh", CSRC / "attn.cuh", CSRC / "glue.cuh",
+HEADERS = [CSRC / "ptx.cuh", CSRC / "gemm.cuh", CSRC / "attn.cuh", CSRC / "glue.cuh", CSRC / "vae.cuh",
            PKG.parent / "include" / "ecad_b200.h"]
 
 NVCC_FLAGS = [

@@ -14,6 +14,8 @@
 #include <atomic>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges are no-ops unless a tool injects itself
+
 #include "../../include/ecad_b200.h"
 #include "attn.cuh"
 #include "gemm.cuh"
@@ -230,6 +232,42 @@ struct ProfScope {
   ~ProfScope() {
     if (active) cudaEventRecord(g_prof.events[g_prof.recs.back().ev + 1], stream);
   }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// NVTX ranges (one range per executor call and per sub-block, so a timeline or an
+// `ncu --nvtx --nvtx-include` capture can be cut at the reference's attn1 / attn2 / ff granularity).
+// Off by default (a push/pop pair per sub-block is host work on the launch path); ECADK_NVTX=1 or
+// ecadk_set_nvtx(1) turns them on.
+// ---------------------------------------------------------------------------------------------------
+std::atomic<int> g_nvtx{-1};
+bool nvtx_on() {
+  int v = g_nvtx.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("ECADK_NVTX");
+    v = (e != nullptr && atoi(e) != 0) ? 1 : 0;
+    g_nvtx.store(v, std::memory_order_relaxed);
+  }
+  return v > 0;
+}
+std::atomic<long long> g_nvtx_ranges{0};
+struct NvtxRange {
+  bool on;
+  explicit NvtxRange(const char* fmt, ...) : on(nvtx_on()) {
+    if (!on) return;
+    char buf[96];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    nvtxRangePushA(buf);
+    g_nvtx_ranges.fetch_add(1, std::memory_order_relaxed);
+  }
+  ~NvtxRange() {
+    if (on) nvtxRangePop();
+  }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
 };
 
 int g_num_sms = 0;
@@ -1222,6 +1260,7 @@ int ecadk_flux_blocks(ecadk_flux_handle_t h, const EcadkFluxArgs* a, const uint8
   const int MS = a->mod_stride;
   ECADK_REQUIRE(a->mod != nullptr && MS >= (d.num_layers * 12 + d.num_single_layers * 3) * D,
                 "flux_blocks: mod_stride=%d too small", MS);
+  NvtxRange nv_call("ecadk_flux_blocks B=%d N=%d T=%d", B, N, T);
   FluxStream img{a->x_img, B * N, N, D, MS, d.eps, stream, &launches, {}};
   FluxStream txt{a->x_txt, B * T, T, D, MS, d.eps, stream, &launches, {}};
   img.reset();
@@ -1244,6 +1283,7 @@ int ecadk_flux_blocks(ecadk_flux_handle_t h, const EcadkFluxArgs* a, const uint8
     void* s_ffc = (dead && dead[b * 3 + 2]) ? nullptr : c_ffc;
     // joint attention (cached_flux_transformer_block.py:170-201,247-256): chunks shift_msa 0, scale_msa 1, gate_msa 2
     if (ex_attn) {
+      NvtxRange nv("d%02d.attn", b);
       if ((rc = img.layer_norm(a->h_img, mi + 0 * D, mi + 1 * D))) return rc;
       if ((rc = txt.layer_norm(a->h_txt, mt + 0 * D, mt + 1 * D))) return rc;
       if ((rc = ecadk_gemm_bias_headmajor_ex(a->h_txt, w.w_qkv_ctx, w.b_qkv_ctx, a->q, a->k, a->v, 3, H, 128, 128, T, S,
@@ -1269,6 +1309,7 @@ int ecadk_flux_blocks(ecadk_flux_handle_t h, const EcadkFluxArgs* a, const uint8
     }
     // image feed-forward (:258-268): shift_mlp 3, scale_mlp 4, gate_mlp 5
     if (ex_ff) {
+      NvtxRange nv("d%02d.ff", b);
       if ((rc = img.layer_norm(a->h_img, mi + 3 * D, mi + 4 * D))) return rc;
       if ((rc = ecadk_gemm_bias(a->h_img, w.w_ff1, w.b_ff1, a->ffh, B * N, F, D, F, 1, stream_))) return rc;
       if ((rc = ecadk_gemm_bias_gated_residual_cache(a->ffh, w.w_ff2, w.b_ff2, a->x_img, nullptr, s_ff, nullptr,
@@ -1280,6 +1321,7 @@ int ecadk_flux_blocks(ecadk_flux_handle_t h, const EcadkFluxArgs* a, const uint8
     }
     // text feed-forward (:272-287)
     if (ex_ffc) {
+      NvtxRange nv("d%02d.ff_context", b);
       if ((rc = txt.layer_norm(a->h_txt, mt + 3 * D, mt + 4 * D))) return rc;
       if ((rc = ecadk_gemm_bias(a->h_txt, w.w_ff1_ctx, w.b_ff1_ctx, a->ffh, B * T, F, D, F, 1, stream_))) return rc;
       if ((rc = ecadk_gemm_bias_gated_residual_cache(a->ffh, w.w_ff2_ctx, w.b_ff2_ctx, a->x_txt, nullptr, s_ffc,
@@ -1316,6 +1358,7 @@ int ecadk_flux_blocks(ecadk_flux_handle_t h, const EcadkFluxArgs* a, const uint8
     }
     const uint8_t* dead = a->cache_dead;
     if (ex_mlp) {
+      NvtxRange nv("s%02d.proj_mlp", b);
       // proj_mlp: ONE GEMM writes the pre-activation into its cache slot (what the reference caches; skipped when
       // that store is dead) and GELU(tanh) of it into the operand buffer proj_out reads
       void* s_mlp = (dead && dead[r + 1]) ? nullptr : c_mlp;
@@ -1323,6 +1366,7 @@ int ecadk_flux_blocks(ecadk_flux_handle_t h, const EcadkFluxArgs* a, const uint8
       ++launches;
     }
     if (ex_attn) {
+      NvtxRange nv("s%02d.attn", b);
       if ((rc = ecadk_gemm_bias_headmajor_ex(a->h_cat, w.w_qkv, w.b_qkv, a->q, a->k, a->v, 3, H, 128, 128, S, S, 0,
                                              B * S, D, stream_)))
         return rc;
@@ -1333,6 +1377,7 @@ int ecadk_flux_blocks(ecadk_flux_handle_t h, const EcadkFluxArgs* a, const uint8
       launches += 3;
     }
     if (ex_out) {
+      NvtxRange nv("s%02d.proj_out", b);
       // proj_out over [attn | GELU(proj_mlp)]: the A operand is read from the two buffers directly (split along K), no
       // concatenated copy.  A reused proj_mlp is re-activated from its pre-GELU cache.
       if (!ex_mlp) {
@@ -1434,6 +1479,13 @@ int ecadk_debug_attn_timing(unsigned int* out_host) {
   return ECADK_OK;
 }
 #endif
+
+int ecadk_set_nvtx(int on) {
+  g_nvtx.store(on ? 1 : 0, std::memory_order_relaxed);
+  return ECADK_OK;
+}
+
+long long ecadk_nvtx_ranges(void) { return g_nvtx_ranges.load(std::memory_order_relaxed); }
 
 int ecadk_profile_start(void) {
   g_prof.used = 0;
@@ -1633,6 +1685,7 @@ int ecadk_pixart_blocks_range(ecadk_handle_t h, const EcadkBlocksArgs* a, const 
                 a->text_pad);
   int launches = 0;
   int rc;
+  NvtxRange nv_call("ecadk_pixart_blocks [%d,%d) rows=%d", block_begin, block_end, M);
 
   EcadkResidualLnArgs pend;  // pending cached-residual reuse, flushed lazily into the next kernel that reads x
   memset(&pend, 0, sizeof(pend));
@@ -1678,6 +1731,7 @@ int ecadk_pixart_blocks_range(ecadk_handle_t h, const EcadkBlocksArgs* a, const 
 
     // ---- attn1 (cached_transformer_block.py:208-246)
     if (ex1) {
+      NvtxRange nv("b%02d.attn1", b);
       pend.h = a->h;
       pend.shift_table = tab + 0 * D;
       pend.scale_table = tab + 1 * D;
@@ -1711,6 +1765,7 @@ int ecadk_pixart_blocks_range(ecadk_handle_t h, const EcadkBlocksArgs* a, const 
 
     // ---- attn2 on the un-normalised stream (:264-289)
     if (ex2) {
+      NvtxRange nv("b%02d.attn2", b);
       if (!xb_valid) {
         pend.xb = a->xb;
         if ((rc = flush())) return rc;
@@ -1739,6 +1794,7 @@ int ecadk_pixart_blocks_range(ecadk_handle_t h, const EcadkBlocksArgs* a, const 
 
     // ---- feed-forward (:306-320)
     if (ex3) {
+      NvtxRange nv("b%02d.ff", b);
       pend.h = a->h;
       pend.shift_table = tab + 3 * D;
       pend.scale_table = tab + 4 * D;

@@ -111,9 +111,10 @@ class B200FluxPipeline:
         sched.step_index = 0
         for i, t in enumerate(sched.timesteps):
             timestep = inp["timesteps"][i:i + 1].expand(batch_size)
-            noise_pred = tr(hidden_states=latents, timestep=timestep, guidance=inp["guidance"],
-                            pooled_projections=inp["pooled_prompt_embeds"], encoder_hidden_states=prompt_embeds,
-                            txt_ids=text_ids, img_ids=img_ids, joint_attention_kwargs=None, return_dict=False)[0]
+            with _lib.nvtx_range(f"step {i:02d} transformer"):
+                noise_pred = tr(hidden_states=latents, timestep=timestep, guidance=inp["guidance"],
+                                pooled_projections=inp["pooled_prompt_embeds"], encoder_hidden_states=prompt_embeds,
+                                txt_ids=text_ids, img_ids=img_ids, joint_attention_kwargs=None, return_dict=False)[0]
             _lib.check(lib.ecadk_axpy_f32(latents.data_ptr(), noise_pred.data_ptr(), sched.step_coefficient(),
                                           latents.numel(), _lib.stream_ptr()), "euler_step")
             tr.launches += 1

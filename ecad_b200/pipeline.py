@@ -144,8 +144,9 @@ class B200PixArtPipeline:
             current_timestep = timesteps_dev[i:i + 1].expand(model_in.shape[0])
             if hasattr(tr, "hint_timestep"):
                 tr.hint_timestep(float(t))  # host value of the shared timestep (table cache key), not an argument
-            noise_pred = tr(model_in, encoder_hidden_states=e_in, encoder_attention_mask=m_in,
-                            timestep=current_timestep, added_cond_kwargs=cond_in, return_dict=False)[0]
+            with _lib.nvtx_range(f"step {i:02d} transformer"):
+                noise_pred = tr(model_in, encoder_hidden_states=e_in, encoder_attention_mask=m_in,
+                                timestep=current_timestep, added_cond_kwargs=cond_in, return_dict=False)[0]
             c = sched.coefficients()
             _lib.check(
                 lib.ecadk_cfg_dpm_step(noise_pred.data_ptr(), latents.data_ptr(), x0_prev.data_ptr(), batch_size,

@@ -274,7 +274,8 @@ class B200VaeDecoder:
         chunk = max(1, int(self.max_activation_bytes // per_sample))
         if latents.shape[0] > chunk:
             return torch.cat([self._decode(latents[i:i + chunk], denormalize) for i in range(0, latents.shape[0], chunk)])
-        return self._decode(latents, denormalize)
+        with _lib.nvtx_range(f"vae decode B={latents.shape[0]}"):
+            return self._decode(latents, denormalize)
 
     def _decode(self, latents: torch.Tensor, denormalize: bool) -> torch.Tensor:
         cfg = self.cfg
@@ -294,7 +295,8 @@ class B200VaeDecoder:
         n_up = len(cfg.block_out_channels)
         for i in range(n_up):
             for j in range(cfg.layers_per_block + 1):
-                x = self._resnet(x, f"decoder.up_blocks.{i}.resnets.{j}", h, w)
+                with _lib.nvtx_range(f"up_blocks.{i}.resnets.{j} {h}x{w}"):
+                    x = self._resnet(x, f"decoder.up_blocks.{i}.resnets.{j}", h, w)
             if i < n_up - 1:
                 name = f"decoder.up_blocks.{i}.upsamplers.0.conv"
                 if self.fused_upsample:
