@@ -91,6 +91,11 @@ class B200FluxPipeline:
         self.scheduler = scheduler if scheduler is not None else FlowMatchEulerDiscrete()
         self.device = transformer.device
 
+    @classmethod
+    def from_pretrained(cls, transformer, **kwargs) -> "B200FluxPipeline":
+        """See B200PixArtPipeline.from_pretrained (load_pipeline.py:55-56)."""
+        return cls(transformer, **kwargs)
+
     def prepare_latents(self, batch_size, num_channels_latents, height, width, generator, latents=None):
         h = 2 * (int(height) // self.vae_scale_factor)
         w = 2 * (int(width) // self.vae_scale_factor)

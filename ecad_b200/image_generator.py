@@ -11,18 +11,19 @@ decodes them with the B200 VAE decoder (ecad_b200/vae.py) like the reference's p
 """
 from __future__ import annotations
 
+import dataclasses
 from pathlib import Path
 from typing import Any, Callable
 
 import numpy as np
 import torch
 
-from .pipeline import B200PixArtPipeline
-from .registry import ImageGeneratorRegistry
+from .pipeline import B200PixArtPipeline, B200TGATEPipeline
+from .registry import ImageGeneratorRegistry, pipeline_from_pretrained
 from .schedule import PixArtCacheSchedule
 from .transformer import B200PixArtTransformer2D, SequentialDiTScheduler
 from .vae import B200VaeDecoder, VaeConfig, random_init_vae_state_dict
-from .weights import PixArtConfig, random_init_state_dict
+from .weights import KNOWN_PIXART_WEIGHTS, PixArtConfig, random_init_state_dict
 
 
 class _SavedPromptMixin:
@@ -104,6 +105,9 @@ class _SavedPromptMixin:
 
 class B200PixArtImageGenerator(_SavedPromptMixin):
     default_pipeline_name = "pixart_alpha"
+    DEFAULT_WEIGHTS = "PixArt-alpha/PixArt-XL-2-256x256"  # pixart_alpha_image_generator.py:19
+    DEFAULT_HEIGHT = 256  # pixart_image_generator.py:41-42
+    DEFAULT_WIDTH = 256
     text_tokens = 120
     default_vae_config = VaeConfig()  # stabilityai/sd-vae-ft-ema: scaling_factor 0.18215
 
@@ -114,7 +118,7 @@ class B200PixArtImageGenerator(_SavedPromptMixin):
         seed_step: int = 1,
         additional_callbacks: list[Callable[..., None]] | None = None,
         state_dict: dict[str, torch.Tensor] | None = None,
-        model_config: PixArtConfig = PixArtConfig(),
+        model_config: PixArtConfig | None = None,
         weight_seed: int = 0,
         device: str = "cuda:0",
         cache_schedule: PixArtCacheSchedule | None = None,
@@ -141,12 +145,17 @@ class B200PixArtImageGenerator(_SavedPromptMixin):
         self.start_seed = start_seed
         self.seed_step = seed_step
         self.additional_callbacks = list(additional_callbacks or [])
-        self.model_config = model_config
-        self.height = self.width = model_config.sample_size * 8
-        self._state_dict = state_dict if state_dict is not None else random_init_state_dict(model_config, weight_seed)
+        # the architecture: an explicit ``model_config`` wins; with neither a config nor a state dict the schedule's
+        # ``config.transformer_weights`` selects one of the known checkpoints' configs (_load_config below)
+        self._explicit_model_config = model_config is not None or state_dict is not None
+        self.model_config = model_config if model_config is not None else self._default_model_config()
+        self._weight_seed = weight_seed
+        self._state_dict = state_dict
         self.diffusion_pipeline: B200PixArtPipeline | None = None
         self._initialize_random_generator()
         self._load_schedule(schedule_path, cache_schedule)
+        if self._state_dict is None:
+            self._state_dict = random_init_state_dict(self.model_config, weight_seed)
 
     # image_generator.py:89-97 - always a CPU generator for reproducibility
     def _initialize_random_generator(self) -> None:
@@ -170,19 +179,53 @@ class B200PixArtImageGenerator(_SavedPromptMixin):
         self.cache_schedule = cache_schedule
         self.num_inference_steps = cache_schedule.num_inference_steps
         self.dit_scheduler = SequentialDiTScheduler(self.num_inference_steps)
-        self.config = cache_schedule.top_level_config or {}
-        pipe = (self.config.get("pipeline") or {})
-        self.gate_step = (pipe.get("kwargs") or {}).get("gate_step") if pipe.get("name") == "tgate" else None
+        self._load_config(cache_schedule.top_level_config or {})
         self.callbacks = [self.dit_scheduler.per_step_callback, self.cache_schedule.per_step_callback]
         self.callbacks.extend(self.additional_callbacks)
         # IMPORTANT: reset MUST be LAST in the list (image_generator.py:156-159)
         self.callbacks.append(self._reset_schedules_callback)
         if self.diffusion_pipeline is not None:
+            if type(self.diffusion_pipeline) is not self.pipeline_from_pretrained.pipeline_class:
+                # the new schedule names another pipeline class: rebuild the (weightless) loop object around the
+                # resident transformer
+                tr = self.diffusion_pipeline.transformer
+                self.diffusion_pipeline = self.pipeline_from_pretrained(tr, use_cuda_graph=self.use_cuda_graph)
             tr = self.diffusion_pipeline.transformer
             tr.cache_schedule = self.cache_schedule
             tr.dit_scheduler = self.dit_scheduler
             tr.reset_cache()
             self.diffusion_pipeline.gate_step = self.gate_step
+
+    def _default_model_config(self) -> PixArtConfig:
+        return KNOWN_PIXART_WEIGHTS[self.DEFAULT_WEIGHTS]
+
+    # image_generator.py:172-191 + pixart_image_generator.py:78-82
+    def _load_config(self, config: dict[str, Any]) -> None:
+        """The schedule JSON's top-level ``config`` (ecad/types.py:43-47): ``transformer_weights``, ``pipeline``
+        ``{name, kwargs}``, ``height`` / ``width``."""
+        self.config = config
+        self.transformer_weights = config.get("transformer_weights", self.DEFAULT_WEIGHTS)
+        if self._state_dict is None and not self._explicit_model_config:
+            known = KNOWN_PIXART_WEIGHTS.get(self.transformer_weights)
+            if known is None:
+                raise ValueError(f"config.transformer_weights = {self.transformer_weights!r}: no checkpoint can be "
+                                 f"loaded offline and the name is none of {sorted(KNOWN_PIXART_WEIGHTS)}; pass "
+                                 f"model_config / state_dict")
+            if self.text_tokens == 300:  # PixArt-sigma never has the micro-condition embedders
+                known = dataclasses.replace(known, use_additional_conditions=False)
+            self.model_config = known
+        self.pipeline_from_pretrained = pipeline_from_pretrained(config.get("pipeline") or {}, self.default_pipeline_name)
+        self.gate_step = self.pipeline_from_pretrained.extra_kwargs.get("gate_step") \
+            if issubclass(self.pipeline_from_pretrained.pipeline_class, B200TGATEPipeline) else None
+        self._load_subclass_config_defaults(config)
+
+    def _load_subclass_config_defaults(self, config: dict[str, Any]) -> None:
+        """pixart_image_generator.py:78-82 reads ``height`` / ``width`` with a 256 default whatever the checkpoint;
+        here a config without them follows the model's native size (sample_size x 8) - the same value for every
+        shipped schedule, and the only sensible one for a 512 / 1024 px model built from an explicit config."""
+        native = self.model_config.sample_size * 8
+        self.height = int(config.get("height", native))
+        self.width = int(config.get("width", native))
 
     def set_schedule(self, cache_schedule: PixArtCacheSchedule) -> None:
         """Swap the candidate schedule on the resident model (no weight reload)."""
@@ -214,8 +257,8 @@ class B200PixArtImageGenerator(_SavedPromptMixin):
         if self.diffusion_pipeline is None:
             tr = B200PixArtTransformer2D(self._state_dict, self.model_config, self.dit_scheduler, self.cache_schedule,
                                          self.device)
-            self.diffusion_pipeline = B200PixArtPipeline(tr, gate_step=self.gate_step,
-                                                         use_cuda_graph=self.use_cuda_graph)
+            # load_pipeline.py:44-58: the class and the extra kwargs (TGATE's gate_step) come from config.pipeline
+            self.diffusion_pipeline = self.pipeline_from_pretrained(tr, use_cuda_graph=self.use_cuda_graph)
         return self.diffusion_pipeline
 
     def create_vae(self) -> B200VaeDecoder:
@@ -289,13 +332,9 @@ class B200PixArtSigmaImageGenerator(B200PixArtImageGenerator):
     so a schedule JSON with ``config.image_generator = "PixArtSigmaImageGenerator"`` selects it."""
 
     default_pipeline_name = "pixart_sigma"
+    DEFAULT_WEIGHTS = "PixArt-alpha/PixArt-Sigma-XL-2-256x256"  # pixart_sigma_image_generator.py:19
     text_tokens = 300
     default_vae_config = VaeConfig(scaling_factor=0.13025)  # PixArt-sigma ships the SDXL VAE
-
-    def __init__(self, *args, model_config: PixArtConfig | None = None, **kwargs):
-        if model_config is None:
-            model_config = PixArtConfig(use_additional_conditions=False)
-        super().__init__(*args, model_config=model_config, **kwargs)
 
 
 ImageGeneratorRegistry.registry.setdefault("PixArtAlphaImageGenerator", B200PixArtAlphaImageGenerator)
@@ -420,7 +459,9 @@ class B200FluxImageGenerator(_SavedPromptMixin):
             else:
                 tr = B200FluxTransformer2D(self._state_dict, self.model_config, self.dit_scheduler, self.cache_schedule,
                                            self.device)
-            self.diffusion_pipeline = B200FluxPipeline(tr, use_cuda_graph=self.use_cuda_graph)
+            # load_pipeline.py:44-58 ("flux" unless config.pipeline names a registered class)
+            make = pipeline_from_pretrained(self.config.get("pipeline") or {}, self.default_pipeline_name)
+            self.diffusion_pipeline = make(tr, use_cuda_graph=self.use_cuda_graph)
         return self.diffusion_pipeline
 
     def create_vae(self) -> B200VaeDecoder:

@@ -105,6 +105,13 @@ class B200PixArtPipeline:
         self.vae_scale_factor = 8
         self.device = transformer.device
 
+    @classmethod
+    def from_pretrained(cls, transformer, **kwargs) -> "B200PixArtPipeline":
+        """The constructor under the name the reference's registry calls (load_pipeline.py:55-56): the "checkpoint" of
+        this pipeline is the resident transformer - text encoder and tokenizer are out of scope, the VAE decoder
+        belongs to the image generator."""
+        return cls(transformer, **kwargs)
+
     def prepare_latents(self, batch_size, num_channels, height, width, dtype, device, generator, latents=None):
         shape = (batch_size, num_channels, height // self.vae_scale_factor, width // self.vae_scale_factor)
         if latents is None:
@@ -259,3 +266,19 @@ class B200PixArtPipeline:
         if not return_dict:
             return (latents,)
         return {"images": latents}
+
+
+class B200TGATEPipeline(B200PixArtPipeline):
+    """The pipeline a schedule selects with ``config.pipeline = {"name": "tgate", "kwargs": {"gate_step": k}}``
+    (/root/reference/ecad/pipelines/tgate.py:29-72): the same loop, with the half-batch variant from step ``k`` on.
+    Like the reference's ``_post_init`` it refuses to be built without a gate step."""
+
+    def __init__(self, transformer, scheduler: DPMSolverPP2M | None = None, gate_step: int | None = None,
+                 use_cuda_graph: bool = False):
+        if gate_step is None:
+            raise ValueError("gate_step must be provided")  # tgate.py:51-55
+        super().__init__(transformer, scheduler, gate_step=int(gate_step), use_cuda_graph=use_cuda_graph)
+
+    @classmethod
+    def from_pretrained(cls, transformer, gate_step: int | None = None, **kwargs) -> "B200TGATEPipeline":
+        return cls(transformer, gate_step=gate_step, **kwargs)

@@ -200,3 +200,64 @@ def get_image_generator_type(name: str, default_name: str = "PixArtImageGenerato
     if klass is None:
         raise ValueError(f"Image generator not found: {name}.")
     return klass
+
+
+class PipelineRegistry:
+    """/root/reference/ecad/pipelines/load_pipeline.py:16-41 - the third string-keyed plug-in point (SURVEY.md section
+    5): ``config.pipeline.name`` of a schedule JSON -> pipeline class, under the reference's own names.  The two stock
+    diffusers loops (``pixart_alpha`` / ``pixart_sigma``) and ``pass_through`` (a verbatim copy of the same loop,
+    pass_through.py:186-404) are one class here; ``tgate`` adds the gate step; ``flux`` is the flow-match loop.
+    ``register`` lets a user add a pipeline class of their own (anything with
+    ``from_pretrained(transformer, **kwargs)``)."""
+
+    _registry: dict[str, type] = {}
+    _builtin_loaded = False
+
+    @classmethod
+    def _builtin(cls) -> dict[str, type]:
+        if not cls._builtin_loaded:  # resolved lazily: the pipeline modules import this one
+            from .flux_pipeline import B200FluxPipeline
+            from .pipeline import B200PixArtPipeline, B200TGATEPipeline
+
+            for name, klass in (("pixart_alpha", B200PixArtPipeline), ("pixart_sigma", B200PixArtPipeline),
+                                ("tgate", B200TGATEPipeline), ("flux", B200FluxPipeline),
+                                ("pass_through", B200PixArtPipeline)):
+                cls._registry.setdefault(name, klass)
+            cls._builtin_loaded = True
+        return cls._registry
+
+    @classmethod
+    def register(cls, name: str):
+        def deco(klass: type) -> type:
+            cls._builtin()[name] = klass
+            return klass
+
+        return deco
+
+    @classmethod
+    def get(cls, name: str | None, default_name: str | None = None) -> type | None:
+        """load_pipeline.py:25-41: the class under ``name``, else the one under ``default_name``, else ``None``."""
+        reg = cls._builtin()
+        klass = reg.get(name, None)
+        if klass is None and default_name is not None:
+            klass = reg.get(default_name, None)
+        return klass
+
+
+def pipeline_from_pretrained(pipeline_config: dict | None, default_pipeline_name: str | None = None):
+    """load_pipeline.py:44-58: resolve ``{"name": ..., "kwargs": {...}}`` to a factory that forwards the extra kwargs
+    (TGATE's ``gate_step``).  As in the reference the default name applies when the config has no ``name`` key; an
+    unknown name is an error here (the reference fails one line later, calling ``None.from_pretrained``)."""
+    pipeline_config = pipeline_config or {}
+    name = pipeline_config.get("name", default_pipeline_name)
+    klass = PipelineRegistry.get(name)
+    if klass is None:
+        raise ValueError(f"Pipeline not found: {name!r}.")
+    extra_kwargs = dict(pipeline_config.get("kwargs") or {})
+
+    def from_pretrained(*args, **kwargs):
+        return klass.from_pretrained(*args, **kwargs, **extra_kwargs)
+
+    from_pretrained.pipeline_class = klass
+    from_pretrained.extra_kwargs = extra_kwargs
+    return from_pretrained

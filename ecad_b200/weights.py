@@ -47,6 +47,20 @@ class PixArtConfig:
         return self.use_additional_conditions
 
 
+# Hugging Face names a schedule JSON may carry in ``config.transformer_weights`` (the reference passes them to
+# ``from_pretrained``, image_generator.py:172-186) -> the architecture they denote.  There are no checkpoints offline:
+# the name selects the CONFIG a random-init model is built with (sample size -> position-table base size and
+# interpolation scale; micro-condition embedders only on PixArt-alpha 1024-MS).
+KNOWN_PIXART_WEIGHTS: dict[str, PixArtConfig] = {
+    "PixArt-alpha/PixArt-XL-2-256x256": PixArtConfig(sample_size=32),
+    "PixArt-alpha/PixArt-XL-2-512x512": PixArtConfig(sample_size=64),
+    "PixArt-alpha/PixArt-XL-2-1024-MS": PixArtConfig(sample_size=128),
+    "PixArt-alpha/PixArt-Sigma-XL-2-256x256": PixArtConfig(sample_size=32, use_additional_conditions=False),
+    "PixArt-alpha/PixArt-Sigma-XL-2-512-MS": PixArtConfig(sample_size=64, use_additional_conditions=False),
+    "PixArt-alpha/PixArt-Sigma-XL-2-1024-MS": PixArtConfig(sample_size=128, use_additional_conditions=False),
+}
+
+
 def _linear(sd, name, out_f, in_f, gen, fan_in=None):
     bound = 1.0 / math.sqrt(fan_in or in_f)
     sd[name + ".weight"] = (torch.rand(out_f, in_f, generator=gen) * 2 - 1) * bound

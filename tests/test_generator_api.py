@@ -112,3 +112,95 @@ def test_time_image_generation_cycles_the_directory(tmp_path):
     assert g.timed == [["p0", "p1"], ["p2"], ["p0", "p1"], ["p2"], ["p0", "p1"]]
     with pytest.raises(ValueError):
         g.time_image_generation(tmp_path / "empty_dir_that_does_not_exist", num_batches=1)
+
+
+# ---- the third plug-in point: PipelineRegistry (ecad/pipelines/load_pipeline.py:16-58) --------------------------
+def test_pipeline_registry_names_and_fallback():
+    from ecad_b200.flux_pipeline import B200FluxPipeline
+    from ecad_b200.pipeline import B200PixArtPipeline, B200TGATEPipeline
+    from ecad_b200.registry import PipelineRegistry, pipeline_from_pretrained
+
+    # the reference's five names
+    assert PipelineRegistry.get("pixart_alpha") is B200PixArtPipeline
+    assert PipelineRegistry.get("pixart_sigma") is B200PixArtPipeline
+    assert PipelineRegistry.get("pass_through") is B200PixArtPipeline
+    assert PipelineRegistry.get("tgate") is B200TGATEPipeline
+    assert PipelineRegistry.get("flux") is B200FluxPipeline
+    # load_pipeline.py:25-41: unknown -> default -> None
+    assert PipelineRegistry.get("nope") is None
+    assert PipelineRegistry.get("nope", "flux") is B200FluxPipeline
+    assert PipelineRegistry.get("nope", "neither") is None
+
+    # load_pipeline.py:44-58: the default applies when the config has no name; kwargs are forwarded
+    made = []
+
+    @PipelineRegistry.register("recording")
+    class Recording:
+        @classmethod
+        def from_pretrained(cls, *args, **kwargs):
+            made.append((args, kwargs))
+            return cls()
+
+    try:
+        f = pipeline_from_pretrained({"name": "recording", "kwargs": {"gate_step": 7}}, "pixart_alpha")
+        assert isinstance(f("transformer", use_cuda_graph=True), Recording)
+        assert made == [(("transformer",), {"use_cuda_graph": True, "gate_step": 7})]
+        assert pipeline_from_pretrained({}, "recording").pipeline_class is Recording
+        assert pipeline_from_pretrained(None, "pixart_sigma").pipeline_class is B200PixArtPipeline
+        with pytest.raises(ValueError):
+            pipeline_from_pretrained({"name": "nope"}, "pixart_alpha")  # a NAMED unknown pipeline does not fall back
+    finally:
+        PipelineRegistry._registry.pop("recording", None)
+
+
+def test_tgate_pipeline_needs_its_gate_step():
+    from ecad_b200.pipeline import B200TGATEPipeline
+
+    class Tr:
+        device = "cpu"
+
+    with pytest.raises(ValueError, match="gate_step must be provided"):  # tgate.py:51-55
+        B200TGATEPipeline.from_pretrained(Tr())
+    assert B200TGATEPipeline.from_pretrained(Tr(), gate_step=8).gate_step == 8
+
+
+def test_generator_reads_the_schedule_config(monkeypatch):
+    """image_generator.py:172-191 + pixart_image_generator.py:78-82: transformer_weights, pipeline, height / width."""
+    import numpy as np
+
+    from ecad_b200 import image_generator as ig
+    from ecad_b200.pipeline import B200PixArtPipeline, B200TGATEPipeline
+    from ecad_b200.schedule import PixArtCacheSchedule
+
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    built = []
+    monkeypatch.setattr(ig, "random_init_state_dict", lambda cfg, seed: built.append(cfg) or {})
+
+    def sched(config):
+        return PixArtCacheSchedule.from_numpy(np.ones((2, 28, 3), bool), 2, 28, top_level_config=config)
+
+    g = ig.B200PixArtAlphaImageGenerator(cache_schedule=sched({}))
+    assert (g.height, g.width) == (256, 256) and g.model_config.sample_size == 32 and g.gate_step is None
+    assert g.pipeline_from_pretrained.pipeline_class is B200PixArtPipeline
+
+    # the shipped gen_default_1024x1024 config block
+    g = ig.B200PixArtAlphaImageGenerator(cache_schedule=sched(
+        {"transformer_weights": "PixArt-alpha/PixArt-XL-2-1024-MS", "height": 1024, "width": 1024}))
+    assert (g.height, g.width) == (1024, 1024)
+    assert g.model_config.sample_size == 128 and g.model_config.resolved_additional_conditions
+    assert built[-1] is g.model_config  # the random-init weights are drawn for THAT architecture
+
+    g = ig.B200PixArtSigmaImageGenerator(cache_schedule=sched(
+        {"transformer_weights": "PixArt-alpha/PixArt-Sigma-XL-2-1024-MS"}))
+    assert g.model_config.sample_size == 128 and not g.model_config.resolved_additional_conditions
+    assert (g.height, g.width) == (1024, 1024) and g.text_tokens == 300
+
+    g = ig.B200PixArtAlphaImageGenerator(cache_schedule=sched({"pipeline": {"name": "tgate", "kwargs": {"gate_step": 1}}}))
+    assert g.gate_step == 1 and g.pipeline_from_pretrained.pipeline_class is B200TGATEPipeline
+
+    with pytest.raises(ValueError, match="transformer_weights"):
+        ig.B200PixArtAlphaImageGenerator(cache_schedule=sched({"transformer_weights": "someone/else"}))
+    # an explicit architecture wins over the name in the JSON
+    small = PixArtConfig(num_layers=28, sample_size=64)
+    g = ig.B200PixArtAlphaImageGenerator(cache_schedule=sched({"transformer_weights": "someone/else"}), model_config=small)
+    assert g.model_config is small and (g.height, g.width) == (512, 512)
