@@ -220,12 +220,18 @@ class B200PixArtImageGenerator(_SavedPromptMixin):
         self._load_subclass_config_defaults(config)
 
     def _load_subclass_config_defaults(self, config: dict[str, Any]) -> None:
-        """pixart_image_generator.py:78-82 reads ``height`` / ``width`` with a 256 default whatever the checkpoint;
-        here a config without them follows the model's native size (sample_size x 8) - the same value for every
-        shipped schedule, and the only sensible one for a 512 / 1024 px model built from an explicit config."""
+        """pixart_image_generator.py:78-82: ``height`` / ``width`` from the config.  They describe the checkpoint the
+        config names, so they are honoured when the config also chose the architecture; a generator built around an
+        explicit ``model_config`` / ``state_dict`` generates at that model's native size (sample_size x 8) whatever
+        the JSON says - the reference's own ``pixart_alpha_256x256`` seed population carries
+        ``{"transformer_weights": ".../PixArt-XL-2-1024-MS", "height": 1024, "width": 1024}`` - and
+        ``generate_images(height=, width=)`` overrides both."""
         native = self.model_config.sample_size * 8
-        self.height = int(config.get("height", native))
-        self.width = int(config.get("width", native))
+        if self._explicit_model_config:
+            self.height = self.width = native
+        else:
+            self.height = int(config.get("height", native))
+            self.width = int(config.get("width", native))
 
     def set_schedule(self, cache_schedule: PixArtCacheSchedule) -> None:
         """Swap the candidate schedule on the resident model (no weight reload)."""

@@ -496,7 +496,7 @@ int ecadk_profile_stop(EcadkProfileRecord* out /* [ECADK_PROF_CLASSES] */);
  * one named after the reference's component - "b07.attn1" / "b07.attn2" / "b07.ff"
  * (ecad/transformer_blocks/cached_transformer_block.py:208-320), "d03.attn" / "d03.ff" / "d03.ff_context",
  * "s11.attn" / "s11.proj_mlp" / "s11.proj_out" (cached_flux_transformer_block.py:99-130,228-291) - so that a timeline,
- * or `ncu --nvtx --nvtx-include "b07.ff/"`, can be cut at that granularity.  A reused sub-block launches nothing of
+ * or `ncu --nvtx --nvtx-include "b07.ff]"`, can be cut at that granularity.  A reused sub-block launches nothing of
  * its own (its cached residual is folded into the next kernel that reads the stream) and has no range.
  * Off by default; the environment variable ECADK_NVTX=1 turns it on at load time.  Ranges cost nothing on the device
  * and are no-ops on the host unless a tool has injected itself (NVTX v3, header-only). */

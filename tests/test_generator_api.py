@@ -204,3 +204,9 @@ def test_generator_reads_the_schedule_config(monkeypatch):
     small = PixArtConfig(num_layers=28, sample_size=64)
     g = ig.B200PixArtAlphaImageGenerator(cache_schedule=sched({"transformer_weights": "someone/else"}), model_config=small)
     assert g.model_config is small and (g.height, g.width) == (512, 512)
+    # ... and then the JSON's height / width (they describe the checkpoint IT names) do not apply either: the seed
+    # population `pixart_alpha_256x256/gen_000` carries the 1024-MS block and is evaluated on the 256 px model
+    g = ig.B200PixArtAlphaImageGenerator(
+        cache_schedule=sched({"transformer_weights": "PixArt-alpha/PixArt-XL-2-1024-MS", "height": 1024, "width": 1024}),
+        state_dict={})
+    assert (g.height, g.width) == (256, 256) and g.model_config.sample_size == 32

@@ -129,7 +129,8 @@ def test_latency_metrics_block(cuda_device, tmp_path):
     emb = {k: v.cuda() for k, v in synthetic_prompt_embeddings(4).items()}
     m = annotate_schedule_file(f, image_generator=gen, prompt_embeds=emb, num_samples=2, warmup_steps=1)
     lat = m["latency"]
-    assert set(lat) == {"avg", "batch_size", "num_samples", "warmup_steps", "gpu", "warmups", "latencies"}
+    assert set(lat) == {"avg", "batch_size", "num_samples", "warmup_steps", "gpu", "warmups", "latencies", "output_type"}
+    assert lat["output_type"] == "latent"  # the reference's figure includes the VAE decode: the block says what was timed
     assert lat["batch_size"] == 4 and len(lat["latencies"]) == 2 and len(lat["warmups"]) == 1 and 0 < lat["avg"] < 1000
     assert m["total_macs"] == row["total_macs"]
     assert json.loads(f.read_text())["metrics"]["latency"]["gpu"] == lat["gpu"]
