@@ -12,6 +12,7 @@ from pathlib import Path
 import torch
 
 _LIB_PATH = Path(__file__).resolve().parent / "libecad_b200.so"
+ABI_VERSION = 2  # include/ecad_b200.h: ECADK_ABI_VERSION (2: EcadkBlocksArgs.self_bias)
 MAX_REUSE = 12
 HEAD_DIM = 72
 HEAD_PAD = 80
@@ -22,12 +23,14 @@ EXPORTED_SYMBOLS = [
     "ecadk_device_check",
     "ecadk_residual_ln",
     "ecadk_patch_embed",
+    "ecadk_patch_embed_padded",
     "ecadk_timestep_sinusoid",
     "ecadk_small_linear",
     "ecadk_cast_f32_bf16",
     "ecadk_mask_bias",
     "ecadk_average_halves",
     "ecadk_final_layer",
+    "ecadk_final_layer_padded",
     "ecadk_cfg_dpm_step",
     "ecadk_set_splitk_workspace",
     "ecadk_splitk_launches",
@@ -135,6 +138,7 @@ class EcadkBlocksArgs(C.Structure):
         ("cache", C.POINTER(C.c_void_p)),
         ("cache_dead", C.POINTER(C.c_uint8)),
         ("qkv", C.c_void_p),
+        ("self_bias", C.c_void_p),
     ]
 
 
@@ -201,12 +205,14 @@ def load() -> C.CDLL:
         "ecadk_device_check": [i],
         "ecadk_residual_ln": [C.POINTER(EcadkResidualLnArgs), p],
         "ecadk_patch_embed": [p, p, p, p, p, i, i, i, i, i, p],
+        "ecadk_patch_embed_padded": [p, p, p, p, p, i, i, i, i, i, i, p],
         "ecadk_timestep_sinusoid": [p, p, i, i, p],
         "ecadk_small_linear": [p, i, p, p, p, i, i, i, i, i, i, i, p],
         "ecadk_cast_f32_bf16": [p, p, sz, p],
         "ecadk_mask_bias": [p, p, i, i, i, p],
         "ecadk_average_halves": [p, sz, p],
         "ecadk_final_layer": [p, p, p, i, p, p, p, p, i, i, i, i, i, f, p],
+        "ecadk_final_layer_padded": [p, p, p, i, p, p, p, p, i, i, i, i, i, i, f, p],
         "ecadk_cfg_dpm_step": [p, p, p, i, i, i, i, f, f, f, f, f, f, p],
         "ecadk_set_splitk_workspace": [p, sz],
         "ecadk_splitk_launches": [],
@@ -256,8 +262,8 @@ def load() -> C.CDLL:
     lib.ecadk_splitk_launches.restype = C.c_longlong
     lib.ecadk_groupnorm_scratch_bytes.restype = C.c_size_t
     lib.ecadk_nvtx_ranges.restype = C.c_longlong
-    if lib.ecadk_abi_version() != 1:
-        raise RuntimeError(f"libecad_b200.so ABI version {lib.ecadk_abi_version()} != 1")
+    if lib.ecadk_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"libecad_b200.so ABI version {lib.ecadk_abi_version()} != {ABI_VERSION}")
     _lib = lib
     return lib
 

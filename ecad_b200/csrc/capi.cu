@@ -789,7 +789,10 @@ int launch_attention_ex(const void* q, int q_ld, const void* k, const void* v, i
   p.q_rowmajor = q_ld != 0;
   p.kv_rowmajor = kv_ld != 0;
   int rc;
-  const bool use_flash = (n_keys > 256 || q_tokens > 256 || forced == 2) && q_tokens % 256 == 0;
+  // (256 keys WITH a key bias on row-major operands - a padded self-attention of fewer than 256 tokens - also streams:
+  // the 256-query kernel has no shared memory left for bias slices and the first-generation one reads head-major only)
+  const bool biased256 = bias != nullptr && n_keys == 256 && (q_ld != 0 || kv_ld != 0);
+  const bool use_flash = (n_keys > 256 || q_tokens > 256 || forced == 2 || biased256) && q_tokens % 256 == 0;
   if (use_flash) {
     // long key sequences: stream 128-key blocks with an online softmax
     CUtensorMap tq[2], tkv[4];
@@ -1002,15 +1005,32 @@ int ecadk_residual_ln(const EcadkResidualLnArgs* args, ecadk_stream_t stream) {
   return launch_residual_ln(*args, static_cast<cudaStream_t>(stream));
 }
 
-int ecadk_patch_embed(const float* latents, const float* wt, const float* bias, const float* pos, float* x,
-                      int samples, int channels, int hl, int wl, int dim, ecadk_stream_t stream) {
+int ecadk_patch_embed_padded(const float* latents, const float* wt, const float* bias, const float* pos, float* x,
+                             int samples, int channels, int hl, int wl, int dim, int tokens_pad,
+                             ecadk_stream_t stream_) {
   ECADK_REQUIRE(latents && wt && bias && pos && x, "patch_embed: null pointer");
   ECADK_REQUIRE(channels * 4 <= 64 && hl % 2 == 0 && wl % 2 == 0 && dim % 4 == 0, "patch_embed: bad shape");
-  ProfScope prof(ECADK_PROF_OTHER, 0.0, 0.0, static_cast<cudaStream_t>(stream));
-  PatchEmbedParams p{latents, wt, bias, pos, x, samples, channels, hl, wl, dim};
-  const int tokens = samples * (hl / 2) * (wl / 2);
-  patch_embed_kernel<<<(tokens + kPatchTokensPerBlock - 1) / kPatchTokensPerBlock, 288, 0, static_cast<cudaStream_t>(stream)>>>(p);
-  return check_launch("patch_embed_kernel");
+  const int n_real = (hl / 2) * (wl / 2);
+  ECADK_REQUIRE(tokens_pad >= n_real, "patch_embed: tokens_pad=%d < %d tokens", tokens_pad, n_real);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ProfScope prof(ECADK_PROF_OTHER, 0.0, 0.0, stream);
+  PatchEmbedParams p{latents, wt, bias, pos, x, samples, channels, hl, wl, dim, tokens_pad};
+  const int tokens = samples * n_real;
+  patch_embed_kernel<<<(tokens + kPatchTokensPerBlock - 1) / kPatchTokensPerBlock, 288, 0, stream>>>(p);
+  int rc = check_launch("patch_embed_kernel");
+  if (rc == ECADK_OK && tokens_pad > n_real) {
+    // padding rows of every sample start at zero: LayerNorm of a zero row is zero, every later value stays finite,
+    // and the self-attention masks them as keys (EcadkBlocksArgs.self_bias)
+    const size_t row = static_cast<size_t>(dim) * sizeof(float);
+    ECADK_CHECK_CUDA(cudaMemset2DAsync(x + static_cast<size_t>(n_real) * dim, tokens_pad * row, 0,
+                                       (tokens_pad - n_real) * row, samples, stream));
+  }
+  return rc;
+}
+
+int ecadk_patch_embed(const float* latents, const float* wt, const float* bias, const float* pos, float* x,
+                      int samples, int channels, int hl, int wl, int dim, ecadk_stream_t stream) {
+  return ecadk_patch_embed_padded(latents, wt, bias, pos, x, samples, channels, hl, wl, dim, (hl / 2) * (wl / 2), stream);
 }
 
 int ecadk_timestep_sinusoid(const float* t, float* out, int samples, int dim, ecadk_stream_t stream) {
@@ -1078,9 +1098,18 @@ int ecadk_mask_bias(const float* mask, float* bias, int samples, int t, int t_pa
 int ecadk_final_layer(const float* x, const float* table, const float* emb, int emb_stride, const void* w_pad,
                       const float* bias, void* h_scratch, float* out, int samples, int hp, int wp, int dim,
                       int out_channels, float eps, ecadk_stream_t stream) {
+  return ecadk_final_layer_padded(x, table, emb, emb_stride, w_pad, bias, h_scratch, out, samples, hp, wp, hp * wp, dim,
+                                  out_channels, eps, stream);
+}
+
+int ecadk_final_layer_padded(const float* x, const float* table, const float* emb, int emb_stride, const void* w_pad,
+                             const float* bias, void* h_scratch, float* out, int samples, int hp, int wp,
+                             int tokens_pad, int dim, int out_channels, float eps, ecadk_stream_t stream) {
   ECADK_REQUIRE(x && table && emb && w_pad && bias && h_scratch && out, "final_layer: null pointer");
   ECADK_REQUIRE(4 * out_channels <= 128 && out_channels % 4 == 0, "final_layer: out_channels=%d", out_channels);
-  const int tokens = hp * wp, M = samples * tokens;
+  ECADK_REQUIRE(tokens_pad >= hp * wp, "final_layer: tokens_pad=%d < %d tokens", tokens_pad, hp * wp);
+  // rows [hp*wp, tokens_pad) of every sample are padding: normalised like the rest, dropped by the unpatchify epilogue
+  const int tokens = tokens_pad, M = samples * tokens;
   // 1. h = LN(x) * (1 + scale) + shift with shift = table[0] + emb[s], scale = table[1] + emb[s]
   EcadkResidualLnArgs a;
   memset(&a, 0, sizeof(a));
@@ -1743,15 +1772,15 @@ int ecadk_pixart_blocks_range(ecadk_handle_t h, const EcadkBlocksArgs* a, const 
         // 3-D tensor maps (no head-major scatter epilogue, no padded copies of Q/K/V in HBM)
         __nv_bfloat16* qkv = static_cast<__nv_bfloat16*>(a->qkv);
         if ((rc = ecadk_gemm_bias(a->h, w.w_qkv1, w.b_qkv1, qkv, M, 3 * D, D, 3 * D, 0, stream_))) return rc;
-        if ((rc = launch_attention_ex(qkv, 3 * D, qkv + D, qkv + 2 * D, 3 * D, nullptr, a->attn_o, a->samples, d.heads,
-                                      a->tokens, a->tokens, stream)))
+        if ((rc = launch_attention_ex(qkv, 3 * D, qkv + D, qkv + 2 * D, 3 * D, a->self_bias, a->attn_o, a->samples,
+                                      d.heads, a->tokens, a->tokens, stream)))
           return rc;
       } else {
         if ((rc = ecadk_gemm_bias_headmajor(a->h, w.w_qkv1, w.b_qkv1, a->q, a->k, a->v, 3, d.heads, a->tokens,
                                             a->tokens, M, D, stream_)))
           return rc;
-        if ((rc = launch_attention(a->q, a->k, a->v, nullptr, a->attn_o, a->samples, d.heads, a->tokens, a->tokens,
-                                   stream)))
+        if ((rc = launch_attention(a->q, a->k, a->v, a->self_bias, a->attn_o, a->samples, d.heads, a->tokens,
+                                   a->tokens, stream)))
           return rc;
       }
       if ((rc = ecadk_gemm_bias_gated_residual_cache(a->attn_o, w.w_out1, w.b_out1, a->x, ex2 ? a->xb : nullptr, s1,

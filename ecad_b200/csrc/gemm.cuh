@@ -298,8 +298,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const uint32_
         } else if constexpr (EPI == EPI_BIAS_F32) {
           if (col < p.f32_cols) *reinterpret_cast<float4*>(p.f32_out + static_cast<size_t>(row) * p.ldo + col) = o;
         } else {  // EPI_UNPATCHIFY: 4 consecutive columns = 4 channels of one (p, q) sub-pixel
-          if (col < p.unp_cols) {
-            const int s_ = row / p.tokens, n_ = row - s_ * p.tokens;
+          const int s_ = row / p.tokens, n_ = row - s_ * p.tokens;  // rows [hp*wp, tokens) of a sample are padding
+          if (col < p.unp_cols && n_ < p.unp_hp * p.unp_wp) {
             const int i_h = n_ / p.unp_wp, j_w = n_ - i_h * p.unp_wp;
             const int pq = col / p.unp_c, ch = col - pq * p.unp_c;
             const int hout = 2 * p.unp_hp, wout = 2 * p.unp_wp;

@@ -267,6 +267,7 @@ struct PatchEmbedParams {
   const float* pos;
   float* x;
   int S, C, Hl, Wl, D;
+  int tokens_pad;  // rows per sample of x (>= N; the rows [N, tokens_pad) are zeroed by the launcher)
 };
 constexpr int kPatchTokensPerBlock = 8;
 __global__ void __launch_bounds__(288) patch_embed_kernel(const PatchEmbedParams p) {
@@ -313,7 +314,8 @@ __global__ void __launch_bounds__(288) patch_embed_kernel(const PatchEmbedParams
         const float4 pe = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(n) * p.D) + d4);
         float4 o = acc[t];
         o.x += pe.x; o.y += pe.y; o.z += pe.z; o.w += pe.w;
-        reinterpret_cast<float4*>(p.x + static_cast<size_t>(token) * p.D)[d4] = o;
+        const size_t xrow = static_cast<size_t>(token / N) * p.tokens_pad + n;
+        reinterpret_cast<float4*>(p.x + xrow * p.D)[d4] = o;
       }
     }
   }

@@ -355,6 +355,8 @@ class B200PixArtTransformer2D(torch.nn.Module):
         return self._pos_cache[key]
 
     def _workspace(self, S: int, N: int, T: int, hl: int, wl: int) -> dict[str, Any]:
+        """``N`` = rows per sample of every token buffer: the image token count rounded up to a multiple of 256 (the
+        attention kernels work on 256-query items); the real count is (hl / p) * (wl / p)."""
         # Buffers are sample-major, so a forward with FEWER samples (TGATE drops the CFG pair from the gate step on,
         # ecad/pipelines/tgate.py:329-341) runs in the prefix of the same workspace and keeps every cache slot.
         if self._ws_key is not None:
@@ -385,6 +387,12 @@ class B200PixArtTransformer2D(torch.nn.Module):
         ws["k2"] = torch.zeros(L, S, H, TEXT_PAD, _lib.HEAD_PAD, device=dev, dtype=bf)
         ws["v2"] = torch.zeros(L, S, H, TEXT_PAD, _lib.HEAD_PAD, device=dev, dtype=bf)
         ws["text_bias"] = torch.empty(S, TEXT_PAD, device=dev, dtype=f32)
+        n_real = (hl // cfg.patch_size) * (wl // cfg.patch_size)
+        if n_real != N:  # padded token count: the padding rows are masked as self-attention keys
+            # -10000 (the reference's own mask constant, pixart_transformer_2d_edited.py:255-291) rather than -inf: the
+            # probabilities underflow to exactly 0 either way, and a 128-key block made of padding only stays finite
+            ws["self_bias"] = torch.zeros(S, N, device=dev, dtype=f32)
+            ws["self_bias"][:, n_real:] = -10000.0
         ws["enc_bf"] = torch.empty(S * T, cfg.caption_channels, device=dev, dtype=bf)
         ws["enc_h"] = torch.empty(S * T, D, device=dev, dtype=bf)
         ws["enc_p"] = torch.empty(S * T, D, device=dev, dtype=bf)
@@ -404,6 +412,7 @@ class B200PixArtTransformer2D(torch.nn.Module):
         args.k2 = C.cast(ws["k2_ptrs"], C.POINTER(C.c_void_p))
         args.v2 = C.cast(ws["v2_ptrs"], C.POINTER(C.c_void_p))
         args.cache = C.cast(ws["cache_ptrs"], C.POINTER(C.c_void_p))
+        args.self_bias = ws["self_bias"].data_ptr() if "self_bias" in ws else None
         ws["args"] = args
         self._ws, self._ws_key = ws, key
         # a new workspace means new (empty) cache tensors
@@ -491,11 +500,13 @@ class B200PixArtTransformer2D(torch.nn.Module):
         S, Cin, hl, wl = hidden_states.shape
         p = cfg.patch_size
         hp, wp = hl // p, wl // p
-        N = hp * wp
+        n_real = hp * wp
+        # The kernels work on 256-token items.  Any other token count (384 px -> 576 tokens, the non-square 1024-MS
+        # buckets, ...) runs PADDED: N rows per sample in every buffer, the padding rows zero on entry, masked as
+        # self-attention keys, and dropped by the unpatchify epilogue - the real rows see exactly the reference's math.
+        N = -(-n_real // 256) * 256
         T = encoder_hidden_states.shape[1]
         D = cfg.inner_dim
-        if N % 256:
-            raise NotImplementedError(f"{N} image tokens: the attention kernels need a multiple of 256 queries")
         ws = self._workspace(S, N, T, hl, wl)
         TEXT_PAD = ws["text_pad"]
         st = _lib.stream_ptr()
@@ -504,8 +515,9 @@ class B200PixArtTransformer2D(torch.nn.Module):
         # 1. input: patch embed + position table (pixart_transformer_2d_edited.py:306)
         lat = hidden_states.to(device=dev, dtype=torch.float32).contiguous()
         pos = self._pos_table(hp, wp)
-        _lib.check(lib.ecadk_patch_embed(lat.data_ptr(), w["patch_wt"].data_ptr(), w["patch_b"].data_ptr(),
-                                         pos.data_ptr(), ws["x"].data_ptr(), S, Cin, hl, wl, D, st), "patch_embed")
+        _lib.check(lib.ecadk_patch_embed_padded(lat.data_ptr(), w["patch_wt"].data_ptr(), w["patch_b"].data_ptr(),
+                                                pos.data_ptr(), ws["x"].data_ptr(), S, Cin, hl, wl, D, N, st),
+                   "patch_embed")
         # adaLN-single: sinusoid -> MLP -> SiLU -> Linear(D, 6D)  (:308-313)
         # The pipeline broadcasts ONE timestep over the batch (`t[None].expand(batch)`, pass_through.py:326-329):
         # a stride-0 / single-element timestep is embedded once and every kernel reads it with row pitch 0.
@@ -630,6 +642,9 @@ class B200PixArtTransformer2D(torch.nn.Module):
                        "pixart_blocks")
             launches += n_l.value
         else:
+            if N != n_real:
+                raise NotImplementedError(f"tensor-signature custom compute functions need a token count that is a "
+                                          f"multiple of 256 (got {n_real}): the block proxy exposes unpadded views")
             # C executor for the runs of ordinary blocks, Python composition for the blocks with tensor functions
             self._tensor_ran = {}
             begin = 0
@@ -661,10 +676,10 @@ class B200PixArtTransformer2D(torch.nn.Module):
             launches += len(self._tgate_average)
 
         # 3. output (:332-376)
-        _lib.check(lib.ecadk_final_layer(ws["x"].data_ptr(), w["final_table"].data_ptr(), t_emb_buf.data_ptr(),
-                                         emb_stride, w["final_w"].data_ptr(), w["final_b"].data_ptr(),
-                                         ws["h"].data_ptr(), ws["out"].data_ptr(), S,
-                                         hp, wp, D, cfg.out_channels, cfg.norm_eps, st), "final_layer")
+        _lib.check(lib.ecadk_final_layer_padded(ws["x"].data_ptr(), w["final_table"].data_ptr(),
+                                                t_emb_buf.data_ptr(), emb_stride, w["final_w"].data_ptr(),
+                                                w["final_b"].data_ptr(), ws["h"].data_ptr(), ws["out"].data_ptr(), S,
+                                                hp, wp, N, D, cfg.out_channels, cfg.norm_eps, st), "final_layer")
         launches += 2
         self.launches += launches
         out = ws["out"][:S]

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ECADK_ABI_VERSION 1
+#define ECADK_ABI_VERSION 2
 
 #define ECADK_OK 0
 #define ECADK_EINVAL (-1)  /* bad shape / alignment / null pointer */
@@ -83,6 +83,9 @@ int ecadk_residual_ln(const EcadkResidualLnArgs* args, ecadk_stream_t stream);
  * latents fp32 [S,C,Hl,Wl]; wt fp32 [C*4, dim] (conv weight transposed); pos fp32 [(Hl/2)*(Wl/2), dim]. */
 int ecadk_patch_embed(const float* latents, const float* wt, const float* bias, const float* pos, float* x,
                       int samples, int channels, int hl, int wl, int dim, ecadk_stream_t stream);
+/* The same into a stream with `tokens_pad` >= (Hl/2)*(Wl/2) rows per sample; the padding rows are zeroed. */
+int ecadk_patch_embed_padded(const float* latents, const float* wt, const float* bias, const float* pos, float* x,
+                             int samples, int channels, int hl, int wl, int dim, int tokens_pad, ecadk_stream_t stream);
 
 /* Timestep sinusoid (diffusers Timesteps(256, flip_sin_to_cos=True)): out fp32 [S, dim] = [cos | sin].
  * Replaces the first stage of self.adaln_single (pixart_transformer_2d_edited.py:308-313). */
@@ -110,6 +113,11 @@ int ecadk_mask_bias(const float* mask, float* bias, int samples, int t, int t_pa
 int ecadk_final_layer(const float* x, const float* table, const float* emb, int emb_stride, const void* w_pad,
                       const float* bias, void* h_scratch, float* out, int samples, int hp, int wp, int dim,
                       int out_channels, float eps, ecadk_stream_t stream);
+/* The same with `tokens_pad` >= hp*wp rows per sample in x / h_scratch (padded token counts, see
+ * EcadkBlocksArgs.self_bias): the padding rows are normalised like the rest and dropped by the unpatchify epilogue. */
+int ecadk_final_layer_padded(const float* x, const float* table, const float* emb, int emb_stride, const void* w_pad,
+                             const float* bias, void* h_scratch, float* out, int samples, int hp, int wp,
+                             int tokens_pad, int dim, int out_channels, float eps, ecadk_stream_t stream);
 
 /* TGATE cache averaging: buf[0:half] = (buf[0:half] + buf[half:2*half]) / 2 over bf16 elements, in place.
  * Replaces `to_cache = (hidden_uncond + hidden_pred_text) / 2` (cached_transformer_block.py:443-449). */
@@ -368,6 +376,11 @@ typedef struct {
                           * row-major GEMM outputs into it and the attention kernels gather their (sample, head) tiles
                           * through 3-D tensor maps (ecadk_attention_ex); q / k / v above are then unused.  NULL keeps
                           * the head-major scatter path. */
+  const float* self_bias;/* fp32 [samples, tokens] or NULL (ABI v2): additive key bias of the SELF-attention.  Token
+                          * counts that are not a multiple of 256 run padded - `tokens` is the padded count, the stream
+                          * and every scratch / cache buffer hold `tokens` rows per sample, the padding rows start at zero
+                          * (ecadk_patch_embed_padded) and carry -10000 here (the reference's mask constant: the probability underflows
+                          * to exactly 0) so that no real query attends to them. */
 } EcadkBlocksArgs;
 
 /* Runs blocks 0..num_layers-1.  executed[b*3 + c] != 0 -> compute sub-block c in {attn1, attn2, ff} of block b and

@@ -411,3 +411,78 @@ def test_sigma_1024px_cached_multistep_reduced_depth(cuda_device):
         rel = float((a - b).abs().max() / b.abs().max())
         assert rel <= PER_STEP_REL_MAXABS, (s, rel)
     assert _cos(got, ref["latents"]) >= FINAL_COS
+
+
+@pytest.mark.parametrize("hl,wl", [(24, 24), (40, 40), (24, 40), (48, 48)])
+def test_token_counts_that_are_not_a_multiple_of_256(cuda_device, hl, wl):
+    """192 / 320 / 384 px and a non-square size: 144 / 400 / 240 / 576 image tokens run PADDED to 256 / 512 / 256 /
+    768 rows per sample (zero padding rows, masked as self-attention keys, dropped by the unpatchify epilogue) and
+    must give the oracle's result on the real tokens - dense step, then a step that reuses sub-blocks."""
+    from ecad_b200.schedule import PixArtCacheSchedule
+    from ecad_b200.transformer import B200PixArtTransformer2D, SequentialDiTScheduler
+    from ecad_b200.weights import PixArtConfig, random_init_state_dict, synthetic_prompt_embeddings
+    from oracle.pixart_oracle import OracleConfig, OracleSchedule, PixArtOracle
+
+    cfg = PixArtConfig(num_layers=3)
+    sd = random_init_state_dict(cfg, seed=2)
+    emb = synthetic_prompt_embeddings(2, seed=3)
+    lat = torch.randn(2, 4, hl, wl, generator=torch.Generator().manual_seed(4))
+    x_in = torch.cat([lat, lat])
+    e_in = torch.cat([emb["negative_prompt_embeds"], emb["prompt_embeds"]])
+    m_in = torch.cat([emb["negative_prompt_attention_mask"], emb["prompt_attention_mask"]])
+    flags = np.ones((2, 3, 3), bool)
+    flags[1, 0, 0] = flags[1, 1, 1] = flags[1, 2, 2] = flags[1, 2, 0] = False
+    oracle = PixArtOracle(sd, OracleConfig(num_layers=3), OracleSchedule.from_flags(flags))
+    sched = PixArtCacheSchedule.from_numpy(flags, 2, 3)
+    tr = B200PixArtTransformer2D(sd, cfg, SequentialDiTScheduler(2), sched)
+    for step, t in enumerate((949, 899)):
+        ts = torch.full((4,), t, dtype=torch.int64)
+        ref = oracle.forward(x_in, e_in, ts, None, m_in)
+        out = tr(x_in.cuda(), encoder_hidden_states=e_in.cuda(), encoder_attention_mask=m_in.cuda(),
+                 timestep=ts.cuda(), added_cond_kwargs={"resolution": None, "aspect_ratio": None},
+                 return_dict=False)[0].cpu()
+        assert out.shape == ref.shape == (4, 8, hl, wl)
+        assert np.array_equal(tr.last_executed.astype(bool), flags[step] if step else np.ones((3, 3), bool))
+        assert torch.isfinite(out).all()
+        rel = float((out - ref).abs().max() / ref.abs().max())
+        assert rel < 5e-3, (step, rel)
+        assert _cos(out, ref) > 0.99999
+        sched.per_step_callback(step)
+        oracle.cache_schedule.per_step_callback(step)
+
+
+def test_generation_at_320px_matches_oracle(cuda_device):
+    """A cached 6-step generation at 320 x 320 (400 tokens -> 512 padded rows) through the generator API
+    (``generate_images(height=, width=)``): decisions bit-exact, per-step latents within the bar."""
+    from ecad_b200.image_generator import B200PixArtAlphaImageGenerator
+    from ecad_b200.schedule import PixArtCacheSchedule
+    from ecad_b200.weights import PixArtConfig, random_init_state_dict, synthetic_prompt_embeddings
+
+    L, steps = 4, 6
+    cfg = PixArtConfig(num_layers=L)
+    sd = random_init_state_dict(cfg, seed=5)
+    rng = np.random.default_rng(3)
+    flags = rng.random((steps, L, 3)) < 0.5
+    flags[0] = True
+    emb = synthetic_prompt_embeddings(2, seed=1)
+    traces, per_step = [], []
+
+    def spy(step, timestep, latents=None, **kw):
+        traces.append(gen.diffusion_pipeline.transformer.last_executed.copy())
+        per_step.append(latents.detach().cpu().clone())
+
+    gen = B200PixArtAlphaImageGenerator(cache_schedule=PixArtCacheSchedule.from_numpy(flags, steps, L, "px320"),
+                                        start_seed=0, state_dict=sd, model_config=cfg, additional_callbacks=[spy])
+    got = gen.generate_images(emb, height=320, width=320)[0].cpu()
+    assert got.shape == (2, 4, 40, 40)
+
+    from oracle.pixart_oracle import OracleConfig, OracleSchedule, PixArtOracle, generate_latents
+    model = PixArtOracle(sd, OracleConfig(num_layers=L), OracleSchedule.from_flags(flags))
+    noise = torch.randn(2, 4, 40, 40, generator=torch.Generator().manual_seed(0))
+    ref = generate_latents(model, emb["prompt_embeds"], emb["prompt_attention_mask"], emb["negative_prompt_embeds"],
+                           emb["negative_prompt_attention_mask"], noise, steps, record_steps=True)
+    assert np.array_equal(np.stack(traces), model.trace.to_numpy(steps, L))
+    for s, (a, b) in enumerate(zip(per_step, ref["per_step"])):
+        rel = float((a - b).abs().max() / b.abs().max())
+        assert rel <= PER_STEP_REL_MAXABS, (s, rel)
+    assert _cos(got, ref["latents"]) >= FINAL_COS

@@ -35,7 +35,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_abi_version_and_error_channel(lib):
-    assert lib.ecadk_abi_version() == 1
+    assert lib.ecadk_abi_version() == 2  # 2: EcadkBlocksArgs.self_bias (padded token counts)
     assert isinstance(lib.ecadk_last_error(), bytes)
 
 
