@@ -297,6 +297,76 @@ def flux_c5_block(device, peaks):
     return out
 
 
+def pixart_c3_c4_block(device, peaks, sd):
+    """BASELINE configs 3 and 4 as secondary, driver-visible figures (N = 1 only; they are parity-test shapes, not the
+    headline): config 3 = PixArt-alpha 512 x 512 dense forward at batch 16; config 4 = PixArt-sigma 1024 x 1024 at
+    batch 8 - one dense forward and one cached 20-step generation under the shipped sigma `ours_fast` schedule.  The
+    transformer weights have the same shapes at every resolution, so the headline model's random-init state dict
+    (`sd`) is reused."""
+    from ecad_b200 import _lib
+    from ecad_b200.image_generator import B200PixArtAlphaImageGenerator, B200PixArtSigmaImageGenerator
+    from ecad_b200.macs import PixArtShape, flops_per_image
+    from ecad_b200.schedule import PixArtCacheSchedule, load_packed_schedules, schedule_from_packed, trace_decisions
+    from ecad_b200.weights import PixArtConfig, synthetic_prompt_embeddings
+
+    out = {}
+    rows = load_packed_schedules(ROOT / "tests" / "golden" / "pixart_schedules.json.gz")
+    sig_path = "schedules_in_paper/pixart_sigma_256/ours_fast.json"
+    sig_row = [r for r in rows if r["path"] == sig_path][0]
+    for name, klass, sample_size, batch, text, row in (
+            ("c3", B200PixArtAlphaImageGenerator, 64, 16, 120, None),
+            ("c4", B200PixArtSigmaImageGenerator, 128, 8, 300, sig_row)):
+        cfg = PixArtConfig(sample_size=sample_size, use_additional_conditions=False)
+        px, N = sample_size * 8, (sample_size // 2) ** 2
+        shape = PixArtShape(tokens=N, text_tokens=text)
+        dense1 = PixArtCacheSchedule.default(1, 28)
+        gen = klass(cache_schedule=dense1, start_seed=7, state_dict=sd, model_config=cfg, device=str(device))
+        emb = {k: v.to(device) for k, v in synthetic_prompt_embeddings(batch, text_tokens=text, seed=11).items()}
+
+        def timed(n):
+            return statistics.mean(gen.generate_images_timed(emb) * batch for _ in range(n))
+
+        # dense: a 1-step "generation" = one full-compute forward of 2 x batch samples + the solver step
+        gen.generate_images(emb)
+        torch.cuda.synchronize()
+        dense_ms = timed(3)
+        _lib.profile_start()
+        gen.generate_images(emb)
+        prof = _lib.profile_stop()
+        dense_flops = batch * flops_per_image(np.ones((1, 28, 3), np.uint8), shape)
+        gm, at = prof["gemm"], prof["attention"]
+        blk = {
+            "workload": f"PixArt-{'sigma' if text == 300 else 'alpha'} {px}x{px}, batch {batch} ({2 * batch} samples, "
+                        f"{N} image + {text} text tokens), random-init weights, synthetic embeddings",
+            "dense_forward_ms": dense_ms, "dense_forward_tflops": dense_flops / dense_ms / 1e9,
+            "dense_forward_frac_of_sustained": dense_flops / dense_ms / 1e9 / peaks["tf_sustained"],
+            "gemm_tflops": gm["flops"] / max(gm["total_ms"], 1e-9) / 1e9, "gemm_ms": gm["total_ms"],
+            "attention_tflops": at["flops"] / max(at["total_ms"], 1e-9) / 1e9, "attention_ms": at["total_ms"],
+            "glue_ms": prof["glue"]["total_ms"],
+            "glue_hbm_gbs": prof["glue"]["bytes"] / max(prof["glue"]["total_ms"], 1e-9) / 1e6,
+            "gpu_launches_per_forward": sum(v["launches"] for v in prof.values()),
+        }
+        if row is not None:  # the cached generation BASELINE config 4 names
+            sched = schedule_from_packed(row)
+            flags = sched.to_numpy()
+            gen.set_schedule(sched)
+            gen.generate_images(emb)
+            torch.cuda.synchronize()
+            gen_ms = timed(2)
+            gflops = batch * flops_per_image(trace_decisions(flags), shape)
+            blk.update({
+                "schedule": sig_path, "executed_fraction": float(trace_decisions(flags).mean()),
+                "ms_per_generation": gen_ms, "images_per_s": batch / (gen_ms * 1e-3),
+                "generation_tflops": gflops / gen_ms / 1e9,
+                "generation_frac_of_sustained": gflops / gen_ms / 1e9 / peaks["tf_sustained"],
+            })
+        blk["hbm_high_water_gb"] = torch.cuda.max_memory_allocated() / 1e9
+        out[name] = blk
+        del gen, emb
+        torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -310,6 +380,7 @@ def main():
     ap.add_argument("--no-population72", action="store_true", help="skip the 72-candidate LPT block")
     ap.add_argument("--no-flux", action="store_true", help="skip the FLUX.1-dev config-5 block (N = 1 only anyway)")
     ap.add_argument("--no-vae", action="store_true", help="skip the VAE-decode block (N = 1 only anyway)")
+    ap.add_argument("--no-c3c4", action="store_true", help="skip the config-3 / config-4 blocks (N = 1 only anyway)")
     ap.add_argument("--fixed-schedule", action="store_true", help="every step runs ours_fast instead of a candidate")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -556,8 +627,14 @@ def main():
         # 0.007 images/s with three parked ranks against 0.15-0.19 alone).
         dist.barrier()
         dist.destroy_process_group()
-    flux = None
+    flux = c3c4 = None
     if rank == 0:
+        if world == 1 and not args.no_c3c4 and not args.fixed_schedule:
+            try:
+                c3c4 = pixart_c3_c4_block(device, peaks, sd)
+            except Exception as exc:  # a secondary block must never cost the headline line
+                c3c4 = {"error": f"{type(exc).__name__}: {exc}"}
+        del sd
         if world == 1 and not args.no_flux and not args.fixed_schedule:
             try:
                 flux = flux_c5_block(device, peaks)
@@ -582,7 +659,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "sm_mhz": clocks_e2e["sm_mhz"] if clocks_e2e else None},
             "gpu_launches": launches, "clocks": clocks,
-            "ours_fast": ours_fast, "vae_decode": vae_blk, "population72": pop, "flux_c5": flux,
+            "ours_fast": ours_fast, "vae_decode": vae_blk, "population72": pop, "pixart_c3_c4": c3c4,
+            "flux_c5": flux,
         }
     if line is not None:
         print(json.dumps(line), file=_REAL_STDOUT, flush=True)
