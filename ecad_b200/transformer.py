@@ -100,8 +100,11 @@ class B200BlockProxy:
 
     _SLOT = {"attn1": 0, "attn2": 1, "ff": 2}
 
-    def __init__(self, owner: "B200PixArtTransformer2D", b: int, ws: dict, S: int, N: int):
+    def __init__(self, owner: "B200PixArtTransformer2D", b: int, ws: dict, S: int, N: int, NP: int | None = None):
+        # N = image tokens the functions see; NP = rows per sample of the HBM buffers (N rounded up to 256, see
+        # B200PixArtTransformer2D.forward): the proxy pads operands on the way in and slices results on the way out
         self._o, self._b, self._ws, self._S, self._N = owner, b, ws, S, N
+        self._NP = N if NP is None else NP
         self.ran = np.zeros(3, dtype=np.uint8)  # which of the block's own modules a function actually executed
         self.block_num = str(b)
         self.cache_schedule = owner.cache_schedule
@@ -111,8 +114,11 @@ class B200BlockProxy:
         c = self._SLOT[comp]
         if not self._o._has_cache[self._b, c]:
             return None
+        return self._slot(c)
+
+    def _slot(self, c: int) -> torch.Tensor:
         D = self._o.cfg.inner_dim
-        return self._ws["cache"][self._b * 3 + c][: self._S * self._N].view(self._S, self._N, D)
+        return self._ws["cache"][self._b * 3 + c][: self._S * self._NP].view(self._S, self._NP, D)[:, : self._N]
 
     def _set(self, comp: str, value) -> None:
         c = self._SLOT[comp]
@@ -122,9 +128,11 @@ class B200BlockProxy:
             o._cache_written[self._b, c] = False
             return
         D = o.cfg.inner_dim
-        slot = self._ws["cache"][self._b * 3 + c][: self._S * self._N].view(self._S, self._N, D)
-        if value.data_ptr() != slot.data_ptr():
+        slot = self._slot(c)
+        if value.data_ptr() != slot.data_ptr() or value.stride() != slot.stride():
             slot.copy_(value.reshape(self._S, self._N, D))
+        if self._NP != self._N:  # the padding rows of a slot are read by the reuse kernels: keep them finite
+            self._ws["cache"][self._b * 3 + c][: self._S * self._NP].view(self._S, self._NP, D)[:, self._N:].zero_()
         o._has_cache[self._b, c] = True
         o._cache_written[self._b, c] = True
 
@@ -137,25 +145,33 @@ class B200BlockProxy:
         D = self._o.cfg.inner_dim
         if hidden_states.shape[-1] != D or hidden_states.numel() != self._S * self._N * D:
             raise ValueError(f"expected hidden_states [{self._S}, {self._N}, {D}], got {tuple(hidden_states.shape)}")
-        return hidden_states.reshape(self._S * self._N, D).to(torch.bfloat16).contiguous()
+        a = hidden_states.reshape(self._S, self._N, D).to(torch.bfloat16)
+        if self._NP != self._N:
+            padded = torch.zeros(self._S, self._NP, D, device=a.device, dtype=torch.bfloat16)
+            padded[:, : self._N] = a
+            a = padded
+        return a.reshape(self._S * self._NP, D).contiguous()
+
+    def _result(self, out: torch.Tensor) -> torch.Tensor:
+        return out.view(self._S, self._NP, -1)[:, : self._N]
 
     def attn1(self, hidden_states, encoder_hidden_states=None, attention_mask=None, **kwargs) -> torch.Tensor:
         if encoder_hidden_states is not None or attention_mask is not None:
             raise NotImplementedError("attn1 is plain self-attention on the PixArt path")
         o, ws, w = self._o, self._ws, self._o.blocks_w[self._b]
-        S, N, H = self._S, self._N, o.cfg.num_attention_heads
+        S, N, H = self._S, self._NP, o.cfg.num_attention_heads
         a = self._as_operand(hidden_states)
         _lib.gemm_headmajor(a, w["w_qkv1"], w["b_qkv1"], (ws["q"], ws["k"], ws["v"]), H, N, N)
-        _lib.attention(ws["q"], ws["k"], ws["v"], None, ws["attn_o"], S, H, N, N)
+        _lib.attention(ws["q"], ws["k"], ws["v"], ws.get("self_bias"), ws["attn_o"], S, H, N, N)
         out = torch.empty(S * N, o.cfg.inner_dim, device=o.device, dtype=torch.bfloat16)
         _lib.gemm_bias(ws["attn_o"][: S * N], w["w_out1"], w["b_out1"], out)
         o.launches += 3
         self.ran[0] = 1
-        return out.view(S, N, -1)
+        return self._result(out)
 
     def attn2(self, hidden_states, encoder_hidden_states=None, attention_mask=None, **kwargs) -> torch.Tensor:
         o, ws, w = self._o, self._ws, self._o.blocks_w[self._b]
-        S, N, H = self._S, self._N, o.cfg.num_attention_heads
+        S, N, H = self._S, self._NP, o.cfg.num_attention_heads
         a = self._as_operand(hidden_states)
         _lib.gemm_headmajor(a, w["w_q2"], w["b_q2"], (ws["q"],), H, N, N)
         _lib.attention(ws["q"], ws["k2"][self._b], ws["v2"][self._b], ws["text_bias"], ws["attn_o"], S, H, N,
@@ -164,18 +180,18 @@ class B200BlockProxy:
         _lib.gemm_bias(ws["attn_o"][: S * N], w["w_out2"], w["b_out2"], out)
         o.launches += 3
         self.ran[1] = 1
-        return out.view(S, N, -1)
+        return self._result(out)
 
     def ff(self, hidden_states, **kwargs) -> torch.Tensor:
         o, ws, w = self._o, self._ws, self._o.blocks_w[self._b]
-        S, N = self._S, self._N
+        S, N = self._S, self._NP
         a = self._as_operand(hidden_states)
         _lib.gemm_bias(a, w["w_ff1"], w["b_ff1"], ws["ffh"][: S * N], gelu=True)
         out = torch.empty(S * N, o.cfg.inner_dim, device=o.device, dtype=torch.bfloat16)
         _lib.gemm_bias(ws["ffh"][: S * N], w["w_ff2"], w["b_ff2"], out)
         o.launches += 2
         self.ran[2] = 1
-        return out.view(S, N, -1)
+        return self._result(out)
 
 
 class B200PixArtTransformer2D(torch.nn.Module):
@@ -642,9 +658,6 @@ class B200PixArtTransformer2D(torch.nn.Module):
                        "pixart_blocks")
             launches += n_l.value
         else:
-            if N != n_real:
-                raise NotImplementedError(f"tensor-signature custom compute functions need a token count that is a "
-                                          f"multiple of 256 (got {n_real}): the block proxy exposes unpadded views")
             # C executor for the runs of ordinary blocks, Python composition for the blocks with tensor functions
             self._tensor_ran = {}
             begin = 0
@@ -656,7 +669,7 @@ class B200PixArtTransformer2D(torch.nn.Module):
                     launches += n_l.value
                 if b < cfg.num_layers:
                     l0 = self.launches
-                    self._run_tensor_block(b, ws, S, N, temb6_buf, temb_stride, encoder_hidden_states, mask)
+                    self._run_tensor_block(b, ws, S, n_real, N, temb6_buf, temb_stride, encoder_hidden_states, mask)
                     launches += self.launches - l0
                     self.launches = l0
                 begin = b + 1
@@ -688,7 +701,7 @@ class B200PixArtTransformer2D(torch.nn.Module):
             return (out,)
         return Transformer2DModelOutput(sample=out)
 
-    def _run_tensor_block(self, b: int, ws: dict, S: int, N: int, temb6: torch.Tensor, temb_stride: int,
+    def _run_tensor_block(self, b: int, ws: dict, S: int, N: int, NP: int, temb6: torch.Tensor, temb_stride: int,
                           encoder_hidden_states, mask) -> None:
         """One block executed sub-block by sub-block, restating CachedTransformerBlock.forward
         (cached_transformer_block.py:208-324) around user tensor functions: LN + adaLN modulate -> compute_attn("attn1")
@@ -696,33 +709,37 @@ class B200PixArtTransformer2D(torch.nn.Module):
         compute_ff -> gate * out + x.  Sub-blocks without a user function go through the tensor-level defaults."""
         from .registry import compute_attn_cached_tensor, compute_ff_cached_tensor
 
-        D, M = self.cfg.inner_dim, S * N
+        # N tokens are what the functions see; the stream and the scratch buffers hold NP >= N rows per sample
+        D, M = self.cfg.inner_dim, S * NP
         t_attn, attn_kw, t_ff, ff_kw = self._tensor_blocks[b]
         attn_fn = t_attn if t_attn is not None else compute_attn_cached_tensor
         ff_fn = t_ff if t_ff is not None else compute_ff_cached_tensor
         tab = self.blocks_w[b]["scale_shift_table"]  # [6, D] fp32: shift/scale/gate msa, shift/scale/gate mlp
         x, h, xb = ws["x"][:M], ws["h"][:M], ws["xb"][:M]
-        proxy = B200BlockProxy(self, b, ws, S, N)
+        proxy = B200BlockProxy(self, b, ws, S, N, NP)
 
         def as_bf16(t):
-            if t.numel() != M * D:
+            if t.numel() != S * N * D:
                 raise ValueError(f"custom compute function of block {b} returned {tuple(t.shape)}, expected [{S}, {N}, {D}]")
-            return t.reshape(M, D).to(torch.bfloat16).contiguous()
+            return proxy._as_operand(t)  # bf16 [S * NP, D], zero padding rows
+
+        def seen(buf):  # what a function receives: the real tokens of a [S * NP, D] buffer
+            return buf.view(S, NP, D)[:, :N]
 
         # attn1 on LN1 + modulate (:208-246)
-        _lib.residual_ln(x, N, h=h, shift_table=tab[0], scale_table=tab[1], shift_temb=temb6[:, 0 * D:],
+        _lib.residual_ln(x, NP, h=h, shift_table=tab[0], scale_table=tab[1], shift_temb=temb6[:, 0 * D:],
                          scale_temb=temb6[:, 1 * D:], temb_stride=temb_stride, eps=self.cfg.norm_eps)
-        o1 = as_bf16(attn_fn(proxy, "attn1", h.view(S, N, D), None, None, **attn_kw))
+        o1 = as_bf16(attn_fn(proxy, "attn1", seen(h), None, None, **attn_kw))
         # x += gate_msa * out; the bf16 shadow of the updated stream is attn2's input (:264-289: no norm for PixArt)
-        _lib.residual_ln(x, N, reuse=[(o1, tab[2], temb6[:, 2 * D:])], xb=xb, temb_stride=temb_stride,
+        _lib.residual_ln(x, NP, reuse=[(o1, tab[2], temb6[:, 2 * D:])], xb=xb, temb_stride=temb_stride,
                          eps=self.cfg.norm_eps)
-        o2 = as_bf16(attn_fn(proxy, "attn2", xb.view(S, N, D), encoder_hidden_states, mask, **attn_kw))
+        o2 = as_bf16(attn_fn(proxy, "attn2", seen(xb), encoder_hidden_states, mask, **attn_kw))
         # x += out; LN2 + modulate (:306-310)
-        _lib.residual_ln(x, N, reuse=[(o2, None, None)], h=h, shift_table=tab[3], scale_table=tab[4],
+        _lib.residual_ln(x, NP, reuse=[(o2, None, None)], h=h, shift_table=tab[3], scale_table=tab[4],
                          shift_temb=temb6[:, 3 * D:], scale_temb=temb6[:, 4 * D:], temb_stride=temb_stride,
                          eps=self.cfg.norm_eps)
-        o3 = as_bf16(ff_fn(proxy, h.view(S, N, D), **ff_kw))
-        _lib.residual_ln(x, N, reuse=[(o3, tab[5], temb6[:, 5 * D:])], temb_stride=temb_stride, eps=self.cfg.norm_eps)
+        o3 = as_bf16(ff_fn(proxy, seen(h), **ff_kw))
+        _lib.residual_ln(x, NP, reuse=[(o3, tab[5], temb6[:, 5 * D:])], temb_stride=temb_stride, eps=self.cfg.norm_eps)
         self.launches += 4
         # decisions are observed, not made, for this block: "executed" = the function ran the block's own module
         self._tensor_ran[b] = proxy.ran

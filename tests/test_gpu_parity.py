@@ -257,8 +257,10 @@ def test_second_generation_reuses_resident_model(cuda_device, weights):
     assert not torch.equal(a[0], b)
 
 
-def test_tensor_level_custom_compute_functions(cuda_device, weights):
-    """A schedule JSON that names USER-registered compute functions with the reference's tensor signatures
+@pytest.mark.parametrize("px", [256, 320])
+def test_tensor_level_custom_compute_functions(cuda_device, weights, px):
+    """(px = 320: 400 image tokens run padded to 512 rows per sample; the functions still see ``[S, 400, D]``.)
+    A schedule JSON that names USER-registered compute functions with the reference's tensor signatures
     (cached_transformer_block.py:141-149,161-165) is honoured: the same two Python functions - written against the
     reference's block attribute surface (``block.attn1/attn2/ff``, ``block.cached_*_output``, ``block.cache_schedule``,
     ``block.block_num``) - run unchanged on the B200 path (block proxy over the C ABI) and on the oracle; decisions of
@@ -319,10 +321,10 @@ def test_tensor_level_custom_compute_functions(cuda_device, weights):
 
         gen = B200PixArtAlphaImageGenerator(cache_schedule=build(PixArtCacheSchedule), start_seed=0, state_dict=weights,
                                             additional_callbacks=[spy])
-        got = gen.generate_images(emb, images_per_prompt=1)[0].cpu()
+        got = gen.generate_images(emb, images_per_prompt=1, height=px, width=px)[0].cpu()
 
         model = PixArtOracle(weights, OracleConfig(), build(OracleSchedule))
-        noise = torch.randn(2, 4, 32, 32, generator=torch.Generator().manual_seed(0))
+        noise = torch.randn(2, 4, px // 8, px // 8, generator=torch.Generator().manual_seed(0))
         ref = generate_latents(model, emb["prompt_embeds"], emb["prompt_attention_mask"], emb["negative_prompt_embeds"],
                                emb["negative_prompt_attention_mask"], noise, steps, record_steps=True)
         # executed = "the block's own module ran": identical on both sides, custom blocks included
