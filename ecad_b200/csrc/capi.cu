@@ -1799,7 +1799,7 @@ int ecadk_pixart_blocks_range(ecadk_handle_t h, const EcadkBlocksArgs* a, const 
         pend.xb = a->xb;
         if ((rc = flush())) return rc;
       }
-      if (a->qkv != nullptr && a->text_pad != 256) {  // (256 padded text keys + bias run on the first-generation kernel)
+      if (a->qkv != nullptr) {  // (256 padded text keys + bias: launch_attention_ex streams them, see `biased256`)
         __nv_bfloat16* q2 = static_cast<__nv_bfloat16*>(a->qkv);  // the query projection reuses the first dim columns
         if ((rc = ecadk_gemm_bias(a->xb, w.w_q2, w.b_q2, q2, M, D, D, 3 * D, 0, stream_))) return rc;
         if ((rc = launch_attention_ex(q2, 3 * D, a->k2[b], a->v2[b], 0, a->text_bias, a->attn_o, a->samples, d.heads,

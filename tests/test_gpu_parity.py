@@ -107,10 +107,11 @@ def test_generation_matches_oracle(cuda_device, weights, schedule_file, batch):
     assert not gen.diffusion_pipeline.transformer._has_cache.any()
 
 
-@pytest.mark.parametrize("sample_size,text_tokens", [(64, 120), (32, 300)])
+@pytest.mark.parametrize("sample_size,text_tokens", [(64, 120), (32, 300), (32, 200), (64, 200)])
 def test_single_forward_other_shapes(cuda_device, sample_size, text_tokens):
     """BASELINE configs 3 / 4 shapes on one forward: PixArt-alpha 512x512 (N = 1024 image tokens, streamed
-    self-attention) and PixArt-sigma's 300-token captions (cross-attention keys padded to 384)."""
+    self-attention) and PixArt-sigma's 300-token captions (cross-attention keys padded to 384); 200-token captions
+    (keys padded to 256 WITH a mask bias: the one key count the 256-query kernel has no room for - streamed)."""
     from ecad_b200.schedule import PixArtCacheSchedule
     from ecad_b200.transformer import B200PixArtTransformer2D, SequentialDiTScheduler
     from ecad_b200.weights import PixArtConfig, random_init_state_dict, synthetic_prompt_embeddings
