@@ -7,8 +7,13 @@ call into (AdaLayerNormZero / ZeroSingle / Continuous, Flu
 RMSNorm on q,k and EmbedND RoPE, CombinedTimestepGuidanceTextProjEmbeddings, FlowMatchEulerDiscreteScheduler).
 
 PARITY STATUS: decisions pinned (tests/test_flux_oracle.py reproduces the reference's per-step MACs of its shipped
-FLUX schedules from this oracle's execution trace); numerics **parity unpinned** (diffusers is not installable here,
-the reference ships no tensors).  The FLUX CUDA path is not built yet - this file is the checker it will be held to.
+FLUX schedules from this oracle's execution trace).  Numerics: diffusers is not installable here and the reference
+ships no tensors, but the ARCHITECTURE has a second, independent implementation in this image - Black Forest Labs'
+own model as vendored by `torchtitan.experiments.flux` - and tests/test_third_party_anchors.py pins this oracle to it:
+the same random weights, re-keyed with diffusers' published conversion rules, give the same dense forward (rel. max
+error < 2e-5) - and the shifted flow-match schedule equals BFL's `get_schedule`.  What stays recalled: the guidance
+embedder (absent from that model; same MLP form as the timestep embedder) and the caching wrapper itself, which is
+the reference's own code and is restated line by line.
 """
 from __future__ import annotations
 

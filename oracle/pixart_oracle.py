@@ -11,6 +11,11 @@ PARITY STATUS
     which is not installed here and cannot be (no network).  This file restates (a) the reference's own
     forward code, which re-states BasicTransformerBlock.forward inline, and (b) the published diffusers 0.30.3
     module semantics listed in SURVEY.md Appendix A.  Each function cites what it follows.
+    What CAN be anchored without diffusers is (tests/test_third_party_anchors.py): the 2-D sincos position table
+    against MAE's `get_2d_sincos_pos_embed` (transformers.models.vit_mae), the timestep sinusoid against BFL's
+    `timestep_embedding`, and DPM-Solver++(2M) against two analytic properties of the published algorithm (exact for
+    a constant data prediction; second-order convergence to the closed-form Gaussian probability-flow solution).
+    The block wiring (adaLN-single chunk order, mask -> bias, caption projection, final layer) stays recalled.
 
 Everything is plain fp32 PyTorch on CPU; weights come in as a ``state_dict`` keyed like
 ``diffusers.PixArtTransformer2DModel.state_dict()`` so a real checkpoint would load unchanged.
