@@ -17,53 +17,7 @@ import numpy as np
 import pytest
 import torch
 
-
-def _bfl_state_dict(sd, L, LS, D):
-    """diffusers FluxTransformer2DModel keys -> BFL keys (inverse of diffusers' convert_flux_to_diffusers.py)."""
-    out = {}
-
-    def lin(dst, src):
-        out[dst + ".weight"], out[dst + ".bias"] = sd[src + ".weight"], sd[src + ".bias"]
-
-    def cat(dst, srcs):
-        out[dst + ".weight"] = torch.cat([sd[s + ".weight"] for s in srcs], 0)
-        out[dst + ".bias"] = torch.cat([sd[s + ".bias"] for s in srcs], 0)
-
-    lin("img_in", "x_embedder")
-    lin("txt_in", "context_embedder")
-    lin("time_in.in_layer", "time_text_embed.timestep_embedder.linear_1")
-    lin("time_in.out_layer", "time_text_embed.timestep_embedder.linear_2")
-    lin("vector_in.in_layer", "time_text_embed.text_embedder.linear_1")
-    lin("vector_in.out_layer", "time_text_embed.text_embedder.linear_2")
-    for i in range(L):
-        s, d = f"transformer_blocks.{i}", f"double_blocks.{i}"
-        lin(f"{d}.img_mod.lin", f"{s}.norm1.linear")
-        lin(f"{d}.txt_mod.lin", f"{s}.norm1_context.linear")
-        cat(f"{d}.img_attn.qkv", [f"{s}.attn.to_q", f"{s}.attn.to_k", f"{s}.attn.to_v"])
-        cat(f"{d}.txt_attn.qkv", [f"{s}.attn.add_q_proj", f"{s}.attn.add_k_proj", f"{s}.attn.add_v_proj"])
-        out[f"{d}.img_attn.norm.query_norm.weight"] = sd[f"{s}.attn.norm_q.weight"]
-        out[f"{d}.img_attn.norm.key_norm.weight"] = sd[f"{s}.attn.norm_k.weight"]
-        out[f"{d}.txt_attn.norm.query_norm.weight"] = sd[f"{s}.attn.norm_added_q.weight"]
-        out[f"{d}.txt_attn.norm.key_norm.weight"] = sd[f"{s}.attn.norm_added_k.weight"]
-        lin(f"{d}.img_attn.proj", f"{s}.attn.to_out.0")
-        lin(f"{d}.txt_attn.proj", f"{s}.attn.to_add_out")
-        lin(f"{d}.img_mlp.0", f"{s}.ff.net.0.proj")
-        lin(f"{d}.img_mlp.2", f"{s}.ff.net.2")
-        lin(f"{d}.txt_mlp.0", f"{s}.ff_context.net.0.proj")
-        lin(f"{d}.txt_mlp.2", f"{s}.ff_context.net.2")
-    for i in range(LS):
-        s, d = f"single_transformer_blocks.{i}", f"single_blocks.{i}"
-        lin(f"{d}.modulation.lin", f"{s}.norm.linear")
-        cat(f"{d}.linear1", [f"{s}.attn.to_q", f"{s}.attn.to_k", f"{s}.attn.to_v", f"{s}.proj_mlp"])
-        lin(f"{d}.linear2", f"{s}.proj_out")
-        out[f"{d}.norm.query_norm.weight"] = sd[f"{s}.attn.norm_q.weight"]
-        out[f"{d}.norm.key_norm.weight"] = sd[f"{s}.attn.norm_k.weight"]
-    lin("final_layer.linear", "proj_out")
-    # AdaLayerNormContinuous chunks (scale, shift); BFL's LastLayer chunks (shift, scale): the halves swap
-    w, b = sd["norm_out.linear.weight"], sd["norm_out.linear.bias"]
-    out["final_layer.adaLN_modulation.1.weight"] = torch.cat([w[D:], w[:D]], 0)
-    out["final_layer.adaLN_modulation.1.bias"] = torch.cat([b[D:], b[:D]], 0)
-    return out
+from anchor_util import bfl_state_dict, ldm_decoder_state_dict
 
 
 def test_flux_oracle_matches_the_bfl_architecture():
@@ -86,7 +40,7 @@ def test_flux_oracle_matches_the_bfl_architecture():
 
     model = tt.FluxModel(FluxModelArgs(in_channels=64, out_channels=64, vec_in_dim=pooled, context_in_dim=ctx,
                                        hidden_size=D, num_heads=H, depth=L, depth_single_blocks=LS, axes_dim=axes))
-    model.load_state_dict(_bfl_state_dict(sd, L, LS, D), strict=True)
+    model.load_state_dict(bfl_state_dict(sd, L, LS, D), strict=True)
     for m in model.modules():  # BFL's own RMSNorm adds 1e-6 (as diffusers does); torchtitan's nn.RMSNorm defaults differ
         if isinstance(m, torch.nn.RMSNorm):
             m.eps = 1e-6
@@ -128,32 +82,7 @@ def test_vae_oracle_matches_the_ldm_decoder():
     dec = ae.Decoder(ch=32, out_ch=3, ch_mult=[1, 2, 4, 4], num_res_blocks=2, in_channels=3, resolution=64,
                      z_channels=16)
 
-    # diffusers AutoencoderKL keys -> ldm keys (inverse of diffusers' convert_ldm_vae_checkpoint)
-    out = {}
-
-    def copy(dst, src):
-        out[dst + ".weight"], out[dst + ".bias"] = sd[src + ".weight"], sd[src + ".bias"]
-
-    def resnet(dst, src):
-        for n in ("norm1", "conv1", "norm2", "conv2"):
-            copy(f"{dst}.{n}", f"{src}.{n}")
-        if src + ".conv_shortcut.weight" in sd:
-            copy(f"{dst}.nin_shortcut", f"{src}.conv_shortcut")
-
-    copy("conv_in", "decoder.conv_in")
-    resnet("mid.block_1", "decoder.mid_block.resnets.0")
-    resnet("mid.block_2", "decoder.mid_block.resnets.1")
-    copy("mid.attn_1.norm", "decoder.mid_block.attentions.0.group_norm")
-    for dst, src in (("q", "to_q"), ("k", "to_k"), ("v", "to_v"), ("proj_out", "to_out.0")):  # 1x1 convs <-> linears
-        out[f"mid.attn_1.{dst}.weight"] = sd[f"decoder.mid_block.attentions.0.{src}.weight"][:, :, None, None]
-        out[f"mid.attn_1.{dst}.bias"] = sd[f"decoder.mid_block.attentions.0.{src}.bias"]
-    for i in range(4):  # diffusers counts the up blocks from the latent side, ldm from the image side
-        for j in range(3):
-            resnet(f"up.{3 - i}.block.{j}", f"decoder.up_blocks.{i}.resnets.{j}")
-        if i < 3:
-            copy(f"up.{3 - i}.upsample.conv", f"decoder.up_blocks.{i}.upsamplers.0.conv")
-    copy("norm_out", "decoder.conv_norm_out")
-    copy("conv_out", "decoder.conv_out")
+    out = ldm_decoder_state_dict(sd)
     dec.load_state_dict(out, strict=True)
     dec.eval()
 
@@ -280,3 +209,23 @@ def test_flux_latent_packing_and_position_ids_match_the_bfl_utilities():
     b, n, c4 = packed.shape
     ours = packed.view(b, 6, 10, c4 // 4, 2, 2).permute(0, 3, 1, 4, 2, 5).reshape(b, c4 // 4, 12, 20)
     assert torch.equal(ours, x)
+
+
+def test_product_rope_tables_match_bfl_embed_nd():
+    """The host-side rotation tables the CUDA RMSNorm+RoPE kernel reads (ecad_b200.flux_transformer.rope_tables) against
+    BFL's EmbedND: pe[..., i, :, :] = [[cos, -sin], [sin, cos]] of the same angles."""
+    tt = pytest.importorskip("torchtitan.experiments.flux.model.layers")
+    from ecad_b200.flux_transformer import rope_tables
+
+    axes = (16, 56, 56)
+    ids = torch.zeros(7 * 9 + 5, 3)
+    grid = torch.zeros(7, 9, 3)
+    grid[..., 1] += torch.arange(7)[:, None]
+    grid[..., 2] += torch.arange(9)[None, :]
+    ids[5:] = grid.reshape(-1, 3)            # 5 text tokens at position 0, then the image grid
+    cos, sin = rope_tables(ids, axes)
+    pe = tt.EmbedND(dim=128, theta=10000, axes_dim=list(axes))(ids[None])   # [1, 1, S, 64, 2, 2]
+    assert pe.shape == (1, 1, ids.shape[0], 64, 2, 2) and cos.shape == sin.shape == (ids.shape[0], 64)
+    assert float((pe[0, 0, :, :, 0, 0] - cos).abs().max()) < 1e-6
+    assert float((pe[0, 0, :, :, 1, 0] - sin).abs().max()) < 1e-6
+    assert float((pe[0, 0, :, :, 0, 1] + sin).abs().max()) < 1e-6
