@@ -70,27 +70,34 @@ def test_flux_oracle_matches_the_bfl_architecture():
     assert err < 2e-5, err
 
 
-def test_vae_oracle_matches_the_ldm_decoder():
+@pytest.mark.parametrize("family", ["flux", "sd"])
+def test_vae_oracle_matches_the_ldm_decoder(family):
+    """flux: 16 latent channels, shift factor, no post_quant_conv; sd: the PixArt VAEs - 4 latent channels and the 1x1
+    post_quant_conv in front of the same decoder (applied here with F.conv2d: it is not part of the ldm Decoder)."""
     ae = pytest.importorskip("torchtitan.experiments.flux.model.autoencoder")
+    import torch.nn.functional as F
+
     from ecad_b200.vae import VaeConfig, random_init_vae_state_dict
     from oracle.vae_oracle import OracleVaeConfig, vae_decode
 
     widths = (32, 64, 128, 128)
-    cfg = VaeConfig(latent_channels=16, block_out_channels=widths, scaling_factor=0.3611, shift_factor=0.1159,
-                    use_post_quant_conv=False)
+    zc, scale, shift, pq = (16, 0.3611, 0.1159, False) if family == "flux" else (4, 0.18215, 0.0, True)
+    cfg = VaeConfig(latent_channels=zc, block_out_channels=widths, scaling_factor=scale, shift_factor=shift,
+                    use_post_quant_conv=pq)
     sd = random_init_vae_state_dict(cfg, seed=4)
     dec = ae.Decoder(ch=32, out_ch=3, ch_mult=[1, 2, 4, 4], num_res_blocks=2, in_channels=3, resolution=64,
-                     z_channels=16)
-
-    out = ldm_decoder_state_dict(sd)
-    dec.load_state_dict(out, strict=True)
+                     z_channels=zc)
+    dec.load_state_dict(ldm_decoder_state_dict(sd), strict=True)
     dec.eval()
 
-    z = torch.randn(2, 16, 8, 6, generator=torch.Generator().manual_seed(9))
+    z = torch.randn(2, zc, 8, 6, generator=torch.Generator().manual_seed(9))
     with torch.no_grad():
-        ref = dec(z / 0.3611 + 0.1159)  # AutoEncoder.decode
-    got = vae_decode(sd, z, OracleVaeConfig(latent_channels=16, block_out_channels=widths, scaling_factor=0.3611,
-                                            shift_factor=0.1159, use_post_quant_conv=False))
+        x = z / scale + shift  # AutoEncoder.decode / AutoencoderKL.decode(latents / scaling_factor)
+        if pq:
+            x = F.conv2d(x, sd["post_quant_conv.weight"], sd["post_quant_conv.bias"])
+        ref = dec(x)
+    got = vae_decode(sd, z, OracleVaeConfig(latent_channels=zc, block_out_channels=widths, scaling_factor=scale,
+                                            shift_factor=shift, use_post_quant_conv=pq))
     assert got.shape == ref.shape == (2, 3, 64, 48)
     err = float((got - ref).abs().max() / ref.abs().max())
     assert err < 2e-5, err
