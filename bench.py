@@ -390,7 +390,7 @@ def main():
 
     from ecad_b200 import _lib
     from ecad_b200.image_generator import B200PixArtAlphaImageGenerator
-    from ecad_b200.macs import PixArtShape, flops_per_image
+    from ecad_b200.macs import PixArtShape, b200_seconds_per_image, flops_per_image
     from ecad_b200.population import PopulationEvaluator
     from ecad_b200.schedule import trace_decisions
     from ecad_b200.weights import PixArtConfig, random_init_state_dict, synthetic_prompt_embeddings
@@ -547,7 +547,10 @@ def main():
     pop = None
     if not args.no_population72 and not args.fixed_schedule:
         emb_pop = {k: v.to(device) for k, v in synthetic_prompt_embeddings(B, seed=1).items()}  # same prompts everywhere
-        costs = [flops_image(r) for r in cand_rows]
+        # LPT costs: estimated B200 seconds per image (measured sub-block rates, profiles/r2_candidate_times.json) -
+        # FLOPs alone under-estimate the reuse-dominated candidates
+        tflop = [flops_image(r) for r in cand_rows]
+        costs = [b200_seconds_per_image(trace_decisions(flags_of(r)), shape) for r in cand_rows]
         barrier()
         res = evaluator.evaluate(len(cand_rows), lambda i: one_step(i, emb_pop, cand_rows[i]), costs=costs, gather=True)
         busy, total = res["busy_s"], res["total_s"]
@@ -566,8 +569,9 @@ def main():
             "per_rank_busy_s": busy_all, "per_rank_candidates": [len(p) for p in res["assignment"]],
             "efficiency": (sum(busy_all) / world) / makespan,
             "planned_efficiency": res["planned_efficiency"],
-            "candidate_tflop_per_image_min_max": [min(costs) / 1e12, max(costs) / 1e12],
-            "step_tflops_per_gpu": sum(costs) * B / makespan / 1e12 / world,
+            "cost_model": "ecad_b200.macs.b200_seconds_per_image (measured sub-block rates)",
+            "candidate_tflop_per_image_min_max": [min(tflop) / 1e12, max(tflop) / 1e12],
+            "step_tflops_per_gpu": sum(tflop) * B / makespan / 1e12 / world,
         }
 
     images = world * K * B

@@ -98,6 +98,28 @@ def flops_per_image(executed: np.ndarray, shape: PixArtShape, samples_per_image:
     return int(per_step.sum()) * samples_per_image
 
 
+# Measured B200 rates behind `b200_seconds_per_image` (profiles/r2_candidate_times.json: the 72 seed-population
+# candidates at batch 100, least-squares over executed attn1 / attn2 / ff and reused sub-blocks; rms error 0.7 % of the
+# mean candidate time against 2.5 % for a FLOPs-only model).  Algorithmic TFLOP/s of an executed sub-block including
+# its LayerNorm / glue, and the effective HBM rate of a reused sub-block (cache read + its share of the stream update).
+B200_SUBBLOCK_TFLOPS = (901.0, 967.0, 1063.0)  # attn1, attn2, ff
+B200_REUSE_BYTES_PER_S = 2.7e12
+
+
+def b200_seconds_per_image(executed: np.ndarray, shape: PixArtShape, samples_per_image: int = 2) -> float:
+    """Estimated B200 seconds per generated image under a decision trace - the COST the population partition uses
+    (ecad_b200.population.partition_lpt): cheap, reuse-dominated candidates run HBM-bound, which analytic FLOPs alone
+    under-estimate."""
+    executed = np.asarray(executed).astype(np.int64)
+    counts = executed.sum(axis=(0, 1))  # executed attn1, attn2, ff sub-blocks over the generation
+    reused = int((1 - executed).sum())
+    comp = shape.flops_components()
+    t = sum(float(counts[c]) * float(comp[c]) / (B200_SUBBLOCK_TFLOPS[c] * 1e12) for c in range(3))
+    t += reused * (shape.tokens * shape.dim * 2) / B200_REUSE_BYTES_PER_S
+    t += executed.shape[0] * shape.flops_fixed() / (B200_SUBBLOCK_TFLOPS[2] * 1e12)
+    return t * samples_per_image
+
+
 @dataclass(frozen=True)
 class FluxShape:
     """FLUX.1-dev MAC model in the reference's calflops convention."""

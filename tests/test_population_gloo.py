@@ -68,3 +68,30 @@ def test_single_rank_gather_is_identity():
     ev = PopulationEvaluator(0, 1, "cpu")
     out = ev.evaluate(3, lambda i: torch.tensor([i]))
     assert [int(t) for t in out["results"]] == [0, 1, 2]
+
+
+def test_cost_model_follows_the_measured_candidate_times():
+    """ecad_b200.macs.b200_seconds_per_image (the LPT cost) against the committed B200 measurement of all 72 seed
+    candidates at batch 100 (profiles/r2_candidate_times.json, tools/candidate_times.py): within 3 % per candidate,
+    and the partition it produces is as good on the MEASURED times as one made with hindsight, to within 1 %."""
+    import json
+    from pathlib import Path
+
+    import numpy as np
+
+    from ecad_b200.macs import PixArtShape, b200_seconds_per_image
+    from ecad_b200.population import partition_lpt
+    from ecad_b200.schedule import load_packed_schedules, schedule_from_packed, trace_decisions
+
+    root = Path(__file__).resolve().parent.parent
+    meas = json.loads((root / "profiles" / "r2_candidate_times.json").read_text())
+    rows = {r["path"]: r for r in load_packed_schedules(root / "tests" / "golden" / "pixart_schedules.json.gz")}
+    y = np.array([c["seconds"] for c in meas["candidates"]])
+    est = np.array([meas["batch"] * b200_seconds_per_image(
+        trace_decisions(schedule_from_packed(rows[c["path"]]).to_numpy()), PixArtShape()) for c in meas["candidates"]])
+    assert len(y) == 72 and np.abs(est - y).max() / y.mean() < 0.03
+    for world in (2, 4, 8):
+        def eff(costs):
+            parts = partition_lpt(list(costs), world)
+            return y.sum() / world / max(y[p].sum() for p in parts)
+        assert eff(est) > eff(y) - 0.01 and eff(est) > 0.96
