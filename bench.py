@@ -564,7 +564,7 @@ def main():
             busy_all, makespan = [busy], total
         pop = {
             "what": f"all 72 candidates of the gen_000 seed population x {B} prompts, longest-processing-time-first "
-                    "partition on analytic FLOPs, one resident model per GPU, final latents gathered over NCCL",
+                    "partition on estimated B200 seconds per image, one resident model per GPU, final latents gathered over NCCL",
             "images": len(cand_rows) * B, "makespan_s": makespan, "images_per_s": len(cand_rows) * B / makespan,
             "per_rank_busy_s": busy_all, "per_rank_candidates": [len(p) for p in res["assignment"]],
             "efficiency": (sum(busy_all) / world) / makespan,
