@@ -790,7 +790,8 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
   uint64_t* stage_free = bars + 22;  // one phase per STORE (tile 0 and tile 1 alternate): the store has read the staging
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
-  const int warp = threadIdx.x >> 5;
+  // (the shuffles tell ptxas that the values are warp-uniform - see the MMA issuer of attn_flash_kernel)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -821,7 +822,7 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   griddep_launch_dependents();  // programmatic dependent launch: see gemm_bf16_kernel
   griddep_wait();
 
@@ -859,8 +860,8 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
+    {
+      // ===================== MMA issuer (whole warp, elected-lane tcgen05 instructions: see attn_flash_kernel) =======
       // Static anti-phase order QK0(i), PV1(i-1), QK1(i), PV0(i) with blocking (hardware-suspended) barrier waits.
       // Measured and rejected (round 2): a dynamic order in which this thread polls both tiles' barriers and issues
       // whatever is ready - 128 keys 83 -> 88 us, 256 keys 99 -> 120 us: the probe loop shares its SM sub-partition's
@@ -878,23 +879,33 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
         const uint64_t dk2 = make_smem_desc(kb + NK * 128, 16, 256, kLayoutSW32);
         const uint64_t dq = make_smem_desc(qb, 16, 1024, kLayoutSW128);
         const uint64_t dq2 = make_smem_desc(qb + kAttnBM * 128, 16, 256, kLayoutSW32);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(d, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-        umma_bf16_ss(d, dq2, dk2, idesc_s, 1);
-        umma_commit(&s_full[t]);
-        umma_commit(&q_empty[t]);
+          for (int k = 0; k < 4; ++k) umma_bf16_ss(d, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+          umma_bf16_ss(d, dq2, dk2, idesc_s, 1);
+          umma_commit(&s_full[t]);
+          umma_commit(&q_empty[t]);
+        }
+        __syncwarp();
+      };
+      auto commit = [&](uint64_t* bar) {
+        if (elect_one()) umma_commit(bar);
+        __syncwarp();
       };
       auto issue_pv = [&](int t, int b) {
         const uint32_t vbase = sbase + Cfg::kV + b * Cfg::kVBuf;
         const uint32_t p_tmem = tmem + 256 * t;  // bf16 pairs: 8 columns per 16-key step
         const uint32_t o_tmem = tmem + 256 * t + Cfg::kOCol;
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < NK / 16; ++ks) {
-          const uint64_t dv = make_smem_desc(vbase + ks * 16 * 32, NK * 32, 256, kLayoutSW32);
-          const uint32_t pa = ks < NK / 32 ? p_tmem + ks * 8 : p_tmem + Cfg::kPHi + (ks - NK / 32) * 8;
-          umma_bf16_ts(o_tmem, pa, dv, idesc_o80, ks != 0);
+          for (int ks = 0; ks < NK / 16; ++ks) {
+            const uint64_t dv = make_smem_desc(vbase + ks * 16 * 32, NK * 32, 256, kLayoutSW32);
+            const uint32_t pa = ks < NK / 32 ? p_tmem + ks * 8 : p_tmem + Cfg::kPHi + (ks - NK / 32) * 8;
+            umma_bf16_ts(o_tmem, pa, dv, idesc_o80, ks != 0);
+          }
+          umma_commit(&o_full[t]);
         }
-        umma_commit(&o_full[t]);
+        __syncwarp();
       };
       int n = 0;
 #ifdef ECADK_ATTN_TIMING
@@ -918,14 +929,14 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
           mbar_wait(&p_full[1], par ^ 1);
           tc_fence_after();
           issue_pv(1, b ^ 1);
-          umma_commit(&v_empty[b ^ 1]);
+          commit(&v_empty[b ^ 1]);
         }
         ATTN_T(m4);
         mbar_wait(&q_full[1], par);
         mbar_wait(&s_empty[1], par ^ 1);
         tc_fence_after();
         issue_qk(1, b);
-        umma_commit(&k_empty[b]);
+        commit(&k_empty[b]);
         ATTN_T(m5);
         mbar_wait(&v_full[b], ph2);
         mbar_wait(&p_full[0], par);
@@ -943,15 +954,17 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
       }
 #ifdef ECADK_ATTN_TIMING
       dbg_acc[7] = n;
-      for (int i = 0; i < 8; ++i) g_attn_dbg[blockIdx.x * 32 + i] = dbg_acc[i];
-      g_attn_dbg[blockIdx.x * 32 + 24] = clock() - t_begin;
+      if (lane == 0) {
+        for (int i = 0; i < 8; ++i) g_attn_dbg[blockIdx.x * 32 + i] = dbg_acc[i];
+        g_attn_dbg[blockIdx.x * 32 + 24] = clock() - t_begin;
+      }
 #endif
       if (n > 0) {  // drain: tile 1's PV of the last item
         const int b = (n - 1) & 1;
         mbar_wait(&p_full[1], (n - 1) & 1);
         tc_fence_after();
         issue_pv(1, b);
-        umma_commit(&v_empty[b]);
+        commit(&v_empty[b]);
       }
     }
     __syncwarp();
@@ -1203,7 +1216,8 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
   uint64_t* p_half = bars + 18;   // [2] the first 32 keys of both row halves of P are in TMEM (P V can start on them)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
-  const int warp = threadIdx.x >> 5;
+  // (the shuffles tell ptxas that the values are warp-uniform - see the MMA issuer)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int nkb = n_keys / kFlashKB;            // key blocks per item
   const int pairs = p.q_tokens / 256;           // 256-query pairs per (sample, head)
@@ -1231,7 +1245,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   griddep_launch_dependents();  // programmatic dependent launch: see gemm_bf16_kernel
   griddep_wait();
 
@@ -1273,8 +1287,13 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // ===================== MMA issuer =====================
+      // The WHOLE warp runs this loop; only the tcgen05 instructions are predicated on one elected lane.  Issued from
+      // inside an `if (lane == 0)` branch ptxas cannot prove the operands warp-uniform and moves each one into a uniform
+      // register through an ELECT / R2UR.BROADCAST / BRA.U.ANY loop - ~125 clocks of the issuing thread per tcgen05.mma,
+      // which for head dim 72 (26 MMAs of 40-64 clocks per key block) was the whole period (tools/micro/
+      // mma_issue_bench.cu, profiles/r2_flash2_phase_timing.txt)
       constexpr uint32_t idesc_s = make_idesc_bf16(kAttnBM, kFlashKB);
       constexpr uint32_t idesc_o80 = make_idesc_bf16(kAttnBM, 80, 0, 1);
       constexpr uint32_t idesc_o128 = make_idesc_bf16(kAttnBM, 128, 0, 1);
@@ -1286,11 +1305,18 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
         const uint64_t dk2 = make_smem_desc(kb + kFlashKB * 128, 16, Cfg::kSBO2, Cfg::kLayout2);
         const uint64_t dq = make_smem_desc(sbase + Cfg::kQ64 + t * (kAttnBM * 128), 16, 1024, kLayoutSW128);
         const uint64_t dq2 = make_smem_desc(sbase + Cfg::kQ2 + t * (kAttnBM * Cfg::kRow2), 16, Cfg::kSBO2, Cfg::kLayout2);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(d, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+          for (int k = 0; k < 4; ++k) umma_bf16_ss(d, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
 #pragma unroll
-        for (int k = 0; k < Cfg::kC2 / 16; ++k) umma_bf16_ss(d, dq2 + 2 * k, dk2 + 2 * k, idesc_s, 1);
-        umma_commit(&s_full[t]);
+          for (int k = 0; k < Cfg::kC2 / 16; ++k) umma_bf16_ss(d, dq2 + 2 * k, dk2 + 2 * k, idesc_s, 1);
+          umma_commit(&s_full[t]);
+        }
+        __syncwarp();
+      };
+      auto commit = [&](uint64_t* bar) {
+        if (elect_one()) umma_commit(bar);
+        __syncwarp();
       };
       // P V of one key block in two parts: part 0 covers the 16-key steps whose P is written FIRST by the softmax warps
       // (keys 0..31 by the "half 0" threads, 64..95 by the "half 1" threads), part 1 the rest - so the tensor core
@@ -1299,6 +1325,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
         const uint32_t vb = sbase + Cfg::kV + st * Cfg::kKStage;
         const uint32_t p_tmem = tmem + 256 * t;
         const uint32_t o_tmem = tmem + 256 * t + 128;
+        if (elect_one()) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int ks = (i >> 1) * 4 + part * 2 + (i & 1);  // part 0: 0,1,4,5   part 1: 2,3,6,7
@@ -1313,6 +1340,8 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
             umma_bf16_ts(o_tmem, p_tmem + ks * 8, dv, idesc_o80, acc);
           }
         }
+        }
+        __syncwarp();
       };
       // tile 1's PV of block nb-1 is deferred by one block so the two tiles run in anti-phase
       bool pend = false, pend_last = false, pend_acc = false;
@@ -1326,8 +1355,8 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
         mbar_wait(&p_full[1], pend_par);
         tc_fence_after();
         issue_pv(1, pend_st, true, 1);
-        umma_commit(&v_empty[pend_st]);
-        if (pend_last) umma_commit(&o_full[1]);
+        commit(&v_empty[pend_st]);
+        if (pend_last) commit(&o_full[1]);
         pend = false;
       };
       int n = 0, nb = 0;
@@ -1353,8 +1382,8 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
           if (j == 0) mbar_wait(&s_empty[1], (n & 1) ^ 1);
           tc_fence_after();
           issue_qk(1, st);
-          umma_commit(&k_empty[st]);
-          if (j == nkb - 1) umma_commit(q_empty);
+          commit(&k_empty[st]);
+          if (j == nkb - 1) commit(q_empty);
           ATTN_T(m4);
           mbar_wait(&v_full[st], ring_ph);
           ATTN_T(m5);
@@ -1371,7 +1400,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
           ATTN_ACC(4, m4, m5);  // wait V
           ATTN_ACC(5, m5, m6);  // wait P0
           issue_pv(0, st, true, 1);
-          if (j == nkb - 1) umma_commit(&o_full[0]);
+          if (j == nkb - 1) commit(&o_full[0]);
           pend = true;
           pend_st = st;
           pend_par = blk_par;
@@ -1383,7 +1412,9 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
 #ifdef ECADK_ATTN_TIMING
       dbg_acc[6] = clock() - t_begin;
       dbg_acc[7] = nb;
-      for (int i = 0; i < 8; ++i) g_attn_dbg[blockIdx.x * 32 + i] = dbg_acc[i];
+      if (lane == 0) {
+        for (int i = 0; i < 8; ++i) g_attn_dbg[blockIdx.x * 32 + i] = dbg_acc[i];
+      }
 #endif
     }
     __syncwarp();
@@ -1569,5 +1600,415 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
     tmem_dealloc(tmem, 512);
   }
 }
+
+// =====================================================================================================
+// Second-generation streaming kernel for head dim 72 (PixArt 512 / 1024 px self-attention, sigma cross-attention).
+//
+// attn_flash_kernel's chain per query tile and key block is  softmax -> P V -> next Q K^T -> softmax: P overwrites S in
+// place, so the next S can only be produced after P V has consumed P, and the softmax warps wait for it (~1100-1500
+// clocks of a ~3300-3700 clock period, profiles/r1_attention_times.txt).  Here the chain is cut:
+//   * a thread keeps its 64 scores in registers, so the S columns are FREE as soon as the tcgen05.ld has landed
+//     (`s_free`): the MMA thread issues the NEXT block's Q K^T right then, one whole softmax ahead of its use;
+//   * P therefore cannot live over S.  With an 80-column O the two tiles leave 96 TMEM columns = 96 of a block's 128
+//     keys as packed bf16 (A operand from TMEM); the last 32 keys of every row go through shared memory as one
+//     128B-swizzled K-major slab (A operand from shared memory).  TMEM per tile: S [0,128) O [128,208) P [208,256);
+//   * the P buffers are single: a block's P is written only after the previous block's P V has retired (`pv_done`),
+//     which by then is one softmax old.
+// Each query tile has its OWN MMA-issuing thread (two warps in different sub-partitions): a single thread issuing for
+// both tiles in a static order measured ~100 clocks per tcgen05.mma next to four busy softmax warps, i.e. the issue
+// loop itself was the period.  K and V run through 3-stage rings (K is consumed one block early).
+// Shared-memory traffic per pair of tiles and key block: operands 136 KB + P 16 KB + TMA 40 KB = 1536 clk at 128 B/clk,
+// tensor pipe 1328 clk, MUFU 32768 exp = ~1700 clk at the measured 19.6/clk - the exponentials bound it.
+// =====================================================================================================
+struct AttnFlash2Cfg {
+  static constexpr int kStages = 3;
+  static constexpr int kPad = 80;
+  static constexpr int kQ64 = 0;                           // 256 rows x 128 B
+  static constexpr int kQ2 = kQ64 + 256 * 128;             // 256 rows x 32 B
+  static constexpr int kKStage = kFlashKB * (128 + 32);    // 20 KB
+  static constexpr int kK = kQ2 + 256 * 32;
+  static constexpr int kV = kK + kStages * kKStage;
+  static constexpr int kP = kV + kStages * kKStage;        // 2 tiles x [128 rows x 128 B] (64 B of every row used)
+  static constexpr int kPTile = kAttnBM * 128;
+  static constexpr int kBias = kP + 2 * kPTile;            // 16 warps x 64 floats
+  static constexpr int kXch = kBias + 8 * kFlashKB * 4;    // row-maximum exchange [2][16][32] + row sums [16][32]
+  static constexpr int kBars = kXch + 3 * 16 * 32 * 4;
+  static constexpr int kSmemBytes = kBars + 256 + 1024;
+  static constexpr uint32_t kBytesQ = 256 * kPad * 2;
+  static constexpr uint32_t kBytesKV = kFlashKB * kPad * 2;
+  static constexpr int kTmemO = 128, kTmemP = 208;         // column offsets inside a tile's 256 columns
+  static constexpr int kKeysTmem = 96;                     // keys of a block whose P goes through TMEM
+  static_assert(kP % 1024 == 0, "the P slabs are addressed with 128B-swizzle descriptors");
+  static_assert(kSmemBytes > 114 * 1024 && kSmemBytes <= 227 * 1024, "one CTA per SM (it owns all 512 TMEM columns)");
+};
+
+constexpr int kFlash2Warps = 19;  // warp 0 TMA, warp 1 MMA of tile 0, warps 2..17 softmax, warp 18 MMA of tile 1
+constexpr int kFlash2Threads = kFlash2Warps * 32;
+
+template <bool HAS_BIAS>
+__global__ void __launch_bounds__(kFlash2Threads, 1)
+attn_flash2_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_constant__ CUtensorMap tm_q16,
+                   const __grid_constant__ CUtensorMap tm_k64, const __grid_constant__ CUtensorMap tm_k16,
+                   const __grid_constant__ CUtensorMap tm_v16, const AttnParams p, const int n_keys,
+                   const int num_items) {
+  using Cfg = AttnFlash2Cfg;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBars);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* k_full = bars + 2;     // [3]
+  uint64_t* k_empty = bars + 5;    // [3]
+  uint64_t* v_full = bars + 8;     // [3]
+  uint64_t* v_empty = bars + 11;   // [3]
+  uint64_t* s_full = bars + 14;    // [2] per query tile, one phase per key block
+  uint64_t* s_free = bars + 16;    // [2] every softmax warp of the tile holds its scores in registers
+  uint64_t* p_full = bars + 18;    // [2]
+  uint64_t* pv_done = bars + 20;   // [2] the tile's P V of a block has retired (P buffers and O may be touched)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+
+  // (the shuffle tells ptxas that the value is warp-uniform - see the MMA issuers)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int nkb = n_keys / kFlashKB;
+  const int pairs = p.q_tokens / 256;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 2);  // the "empty" barriers: one commit per MMA thread
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 2);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 2);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 8);
+      mbar_init(&p_full[i], 8);
+      mbar_init(&pv_done[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  griddep_launch_dependents();
+  griddep_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int n = 0, nb = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++n) {
+        const int sh = item / pairs, pr = item - sh * pairs;
+        const int smp = sh / p.heads, hd = sh - smp * p.heads;
+        const int q_mid = p.q_rowmajor ? hd : 0, kv_mid = p.kv_rowmajor ? hd : 0;
+        const int q_row = (p.q_rowmajor ? smp : sh) * p.q_tokens + pr * 256;
+        mbar_wait(q_empty, (n & 1) ^ 1);
+        mbar_arrive_expect_tx(q_full, Cfg::kBytesQ);
+        tma_load_3d(smem + Cfg::kQ64, &tm_q64, q_full, 0, q_mid, q_row);
+        tma_load_3d(smem + Cfg::kQ2, &tm_q16, q_full, 64, q_mid, q_row);
+        for (int j = 0; j < nkb; ++j, ++nb) {
+          const int st = nb % S;
+          const uint32_t ph = ((nb / S) & 1) ^ 1;
+          const int k_row = (p.kv_rowmajor ? smp : sh) * n_keys + j * kFlashKB;
+          uint8_t* kd = smem + Cfg::kK + st * Cfg::kKStage;
+          uint8_t* vd = smem + Cfg::kV + st * Cfg::kKStage;
+          mbar_wait(&k_empty[st], ph);
+          mbar_arrive_expect_tx(&k_full[st], Cfg::kBytesKV);
+          tma_load_3d(kd, &tm_k64, &k_full[st], 0, kv_mid, k_row);
+          tma_load_3d(kd + kFlashKB * 128, &tm_k16, &k_full[st], 64, kv_mid, k_row);
+          mbar_wait(&v_empty[st], ph);
+          mbar_arrive_expect_tx(&v_full[st], Cfg::kBytesKV);
+#pragma unroll
+          for (int a = 0; a < Cfg::kPad / 16; ++a)  // five 16-column SW32 atoms: one MN-major operand
+            tma_load_3d(vd + a * (kFlashKB * 32), &tm_v16, &v_full[st], a * 16, kv_mid, k_row);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1 || warp == kFlash2Warps - 1) {
+    {
+      // ===================== MMA issuers: ONE WARP PER QUERY TILE (warp 1: tile 0, last warp: tile 1) =============
+      // The WHOLE warp runs this loop and only the tcgen05 instructions are predicated on one elected lane.  Issued from
+      // inside an `if (lane == 0)` branch, every tcgen05.mma cost ~125 clocks of the issuing thread: ptxas cannot prove
+      // the operands warp-uniform there and moves each one into a uniform register through an ELECT / R2UR.BROADCAST /
+      // BRA.U.ANY loop (7 R2UR per MMA in the SASS) - 26 MMAs x 125 clk was the whole period of a key block, for every
+      // attention kernel of this file.  Warp-uniform control flow keeps the descriptors in uniform registers.
+      // A single issuing thread shares its sub-partition's issue port with four busy softmax warps and took ~100 clocks
+      // per tcgen05.mma (26 per key block = the whole period); the tiles are independent, so each gets its own thread
+      // in a different sub-partition, and there is no issue order between the tiles left to get wrong.  K / V / Q go
+      // back to the producer when BOTH threads have committed (those barriers count 2).
+      const int t = warp == 1 ? 0 : 1;
+      constexpr uint32_t idesc_s = make_idesc_bf16(kAttnBM, kFlashKB);
+      constexpr uint32_t idesc_o = make_idesc_bf16(kAttnBM, 80, 0, 1);
+      constexpr uint32_t kStageDesc = Cfg::kKStage >> 4;  // descriptor start-address units (16 B) per ring stage
+      const uint32_t sbase = smem_u32(smem);
+      const int my_items = (num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / gridDim.x;
+      const int G = my_items * nkb;  // key blocks this CTA runs, over all of its items
+      const uint32_t s_tmem = tmem + 256 * t;
+      const uint32_t o_tmem = s_tmem + Cfg::kTmemO;
+      const uint32_t p_tmem = s_tmem + Cfg::kTmemP;
+      // loop-invariant descriptors (stage 0; a stage adds kStageDesc to the start-address field)
+      const uint64_t dq = make_smem_desc(sbase + Cfg::kQ64 + t * (kAttnBM * 128), 16, 1024, kLayoutSW128);
+      const uint64_t dq2 = make_smem_desc(sbase + Cfg::kQ2 + t * (kAttnBM * 32), 16, 256, kLayoutSW32);
+      const uint64_t dk0 = make_smem_desc(sbase + Cfg::kK, 16, 1024, kLayoutSW128);
+      const uint64_t dk20 = make_smem_desc(sbase + Cfg::kK + kFlashKB * 128, 16, 256, kLayoutSW32);
+      const uint64_t dv0 = make_smem_desc(sbase + Cfg::kV, kFlashKB * 32, 256, kLayoutSW32);
+      const uint64_t dp = make_smem_desc(sbase + Cfg::kP + t * Cfg::kPTile, 16, 1024, kLayoutSW128);
+      // operands of block g are in shared memory: K(g), and Q of its item when g opens one
+      auto operands_ready = [&](int g) {
+        if (g % nkb == 0) mbar_wait(q_full, (g / nkb) & 1);
+        mbar_wait(&k_full[g % S], (g / S) & 1);
+        tc_fence_after();
+      };
+      auto issue_qk = [&](int g) {
+        const int st = g % S;
+        const uint64_t dk = dk0 + st * kStageDesc, dk2 = dk20 + st * kStageDesc;
+        const bool last = g % nkb == nkb - 1;
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16_ss(s_tmem, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+          umma_bf16_ss(s_tmem, dq2, dk2, idesc_s, 1);
+          umma_commit(&s_full[t]);
+          umma_commit(&k_empty[st]);       // this tile is done with K(g) ...
+          if (last) umma_commit(q_empty);  // ... and with Q after an item's last block
+        }
+        __syncwarp();
+      };
+      auto issue_pv = [&](int g) {
+        const int st = g % S;
+        const uint64_t dv = dv0 + st * kStageDesc;
+        const uint32_t acc0 = (g % nkb != 0) ? 1u : 0u;
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            if (ks < Cfg::kKeysTmem / 16) {
+              umma_bf16_ts(o_tmem, p_tmem + ks * 8, dv + ks * 32, idesc_o, ks != 0 ? 1u : acc0);
+            } else {
+              umma_bf16_ss(o_tmem, dp + 2 * (ks - Cfg::kKeysTmem / 16), dv + ks * 32, idesc_o, 1);
+            }
+          }
+          umma_commit(&pv_done[t]);
+          umma_commit(&v_empty[st]);
+        }
+        __syncwarp();
+      };
+#ifdef ECADK_ATTN_TIMING
+      unsigned int dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+      operands_ready(0);
+      issue_qk(0);
+      for (int g = 0; g < G; ++g) {
+        const uint32_t par = g & 1;
+        ATTN_T(m0);
+        // the tile holds S(g) in registers -> its next Q K^T, one whole softmax ahead of its use
+        mbar_wait(&s_free[t], par);
+        ATTN_T(m1);
+        if (g + 1 < G) {
+          operands_ready(g + 1);
+          ATTN_T(m1b);
+          ATTN_ACC(1, m1, m1b);  // wait K (+ Q)
+          issue_qk(g + 1);
+        }
+        ATTN_T(m2);
+        mbar_wait(&v_full[g % S], (g / S) & 1);
+        ATTN_T(m3);
+        mbar_wait(&p_full[t], par);
+        tc_fence_after();
+        ATTN_T(m4);
+        issue_pv(g);
+        ATTN_T(m5);
+        ATTN_ACC(0, m0, m1);  // wait s_free
+        ATTN_ACC(2, m1, m2);  // wait K + issue QK
+        ATTN_ACC(3, m2, m3);  // wait V
+        ATTN_ACC(4, m3, m4);  // wait P
+        ATTN_ACC(5, m4, m5);  // issue PV
+      }
+#ifdef ECADK_ATTN_TIMING
+      if (t == 0 && lane == 0) {  // (slots 6 / 7 are written by the softmax warps: their turn waits)
+        for (int i = 0; i < 6; ++i) g_attn_dbg[blockIdx.x * 32 + i] = dbg_acc[i];
+      }
+#endif
+    }
+    __syncwarp();
+  } else {
+    // ===================== softmax + correction + epilogue =====================
+    const int sw = warp - 2;
+    const int t = sw >> 3;            // query tile
+    const int half = (sw >> 2) & 1;   // which 64 keys of a block / which output columns this thread owns
+    const int quarter = warp & 3;     // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;
+    const uint32_t t_row = tmem + 256 * t + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t bias_a = smem_u32(smem + Cfg::kBias) + sw * (kFlashKB / 2) * 4;
+    const uint32_t xch = smem_u32(smem + Cfg::kXch);
+    const uint32_t my_slot = xch + (sw * 32 + lane) * 4;
+    const uint32_t peer_slot = xch + ((sw ^ 4) * 32 + lane) * 4;
+    const int bar_id = 1 + t * 4 + quarter;  // named barrier of the two partner warps
+    // this row's 128-byte line of the tile's P slab; its 16-byte chunks are XOR-swizzled with the row (SW128)
+    const uint32_t p_line = smem_u32(smem + Cfg::kP) + t * Cfg::kPTile + (row >> 3) * 1024 + (row & 7) * 128;
+    constexpr float kLog2e = 1.4426950408889634f;
+    constexpr int kOSplit = 48;  // O columns [0, 48) -> half 0, [48, 80) -> half 1
+    float breg[2];
+    auto fetch_bias = [&](int sample, int j) {
+      const float* b = p.bias + static_cast<size_t>(sample) * n_keys + j * kFlashKB + half * 64;
+      breg[0] = __ldg(b + lane) * kLog2e;
+      breg[1] = __ldg(b + lane + 32) * kLog2e;
+    };
+    int nb = 0;
+#ifdef ECADK_ATTN_TIMING
+    unsigned int dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const unsigned int t_begin = clock();
+#endif
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int sh = item / pairs, pr = item - sh * pairs;
+      const int sample = sh / p.heads, head = sh - sample * p.heads;
+      float m_used = -INFINITY, l_sum = 0.f;  // l_sum: this thread's 64-key share of the row sum
+      if constexpr (HAS_BIAS) fetch_bias(sample, 0);
+      for (int j = 0; j < nkb; ++j, ++nb) {
+        if constexpr (HAS_BIAS) {
+          sts_f1(bias_a + lane * 4, breg[0]);
+          sts_f1(bias_a + (lane + 32) * 4, breg[1]);
+          __syncwarp();
+          if (j + 1 < nkb) fetch_bias(sample, j + 1);
+        }
+        ATTN_T(s0);
+        mbar_wait(&s_full[t], nb & 1);
+        tc_fence_after();
+        ATTN_T(s1);
+        uint32_t v[2][32];
+        tmem_ld_32x32(t_row + half * 64, v[0]);
+        tmem_ld_32x32(t_row + half * 64 + 32, v[1]);
+        tmem_ld_wait();
+        ATTN_T(s2);
+        // the scores are in registers: the tile's S columns may take the next block's Q K^T
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[t]);
+        float mx = softmax_chunk_prep<HAS_BIAS>(v[0], -INFINITY, p.scale_log2e, bias_a);
+        mx = softmax_chunk_prep<HAS_BIAS>(v[1], mx, p.scale_log2e, bias_a + 128);
+        if constexpr (!HAS_BIAS) mx *= p.scale_log2e;
+        const uint32_t buf = (nb & 1) * (16 * 32 * 4);
+        sts_f1(my_slot + buf, mx);
+        named_bar_sync(bar_id, 64);
+        mx = fmaxf(mx, lds_f1(peer_slot + buf));
+        ATTN_T(s3);
+        // lazy rescale (see attn_flash_kernel); O may only be touched once the previous block's P V has retired
+        const bool need = mx > m_used + 8.0f;
+        const bool rescale = need && j > 0 && m_used != -INFINITY;
+        const float alpha = rescale ? fast_exp2(m_used - mx) : 1.0f;
+        if (__any_sync(0xffffffffu, rescale)) {
+          mbar_wait(&pv_done[t], (nb - 1) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int c = (half ? kOSplit : 0); c < (half ? Cfg::kPad : kOSplit); c += 16) {
+            uint32_t o[16];
+            tmem_ld_32x16(t_row + Cfg::kTmemO + c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x16(t_row + Cfg::kTmemO + c, o);
+          }
+        }
+        l_sum *= alpha;
+        if (need) m_used = mx;
+        const float m_eff = m_used == -INFINITY ? 0.f : m_used;  // a fully masked prefix must not produce NaN
+        uint64_t sum2 = pack_f2(0.f, 0.f);
+        uint32_t pk[2][16];
+        // (measured and rejected: the two tiles taking strict TURNS on the exponentials - a tile's two warps per
+        // sub-partition alone reach only ~13 exp/clk/SM (dependency-bound, 1300 clk per block) against ~21 with all four
+        // warps queueing on the MUFU: 1563 -> 1902 us at the 4096-token shape)
+        softmax_chunk_exp_reg<HAS_BIAS>(v[0], pk[0], sum2, m_eff, p.scale_log2e);
+        softmax_chunk_exp_reg<HAS_BIAS>(v[1], pk[1], sum2, m_eff, p.scale_log2e);
+        {
+          float s_lo, s_hi;
+          unpack_f2(sum2, s_lo, s_hi);
+          l_sum += s_lo + s_hi;
+        }
+        // the single P buffers: the previous block's P V (issued one softmax ago) must have read them
+        ATTN_T(s4);
+        if (nb > 0) {
+          mbar_wait(&pv_done[t], (nb - 1) & 1);
+          tc_fence_after();
+        }
+        ATTN_T(s5);
+        if (half == 0) {  // keys 0..63 -> packed TMEM columns [0, 32)
+          tmem_st_32x16(t_row + Cfg::kTmemP, pk[0]);
+          tmem_st_32x16(t_row + Cfg::kTmemP + 16, pk[1]);
+        } else {          // keys 64..95 -> TMEM columns [32, 48); keys 96..127 -> the shared-memory slab
+          tmem_st_32x16(t_row + Cfg::kTmemP + 32, pk[0]);
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            sts_u4(p_line + ((c ^ (row & 7)) << 4), pk[1][4 * c], pk[1][4 * c + 1], pk[1][4 * c + 2], pk[1][4 * c + 3]);
+          fence_proxy_async_smem();
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
+        ATTN_T(s6);
+        ATTN_ACC(0, s0, s1);  // wait S
+        ATTN_ACC(1, s1, s2);  // TMEM load
+        ATTN_ACC(2, s2, s3);  // s_free arrive + max + exchange
+        ATTN_ACC(3, s3, s4);  // (rescale) + exp
+        ATTN_ACC(4, s4, s5);  // wait pv_done
+        ATTN_ACC(5, s5, s6);  // P store + fences + arrive
+      }
+      // ---- item done: O_t / l -> bf16 -> global; each partner writes its own output columns.  The next item's first
+      // P V (which overwrites O_t) is only issued behind this warp's next p_full arrival, i.e. after this read-out.
+      sts_f1(my_slot + 2 * (16 * 32 * 4), l_sum);
+      mbar_wait(&pv_done[t], (nb - 1) & 1);
+      tc_fence_after();
+      named_bar_sync(bar_id, 64);
+      const float inv = 1.0f / (l_sum + lds_f1(peer_slot + 2 * (16 * 32 * 4)));
+      const int q = pr * 256 + t * kAttnBM + row;
+      __nv_bfloat16* dst = p.out + (static_cast<size_t>(sample) * p.q_tokens + q) * p.out_ld + head * 72;
+      auto store8 = [&](const uint32_t* w, __nv_bfloat16* d) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(w[0]) * inv, __uint_as_float(w[1]) * inv);
+        o.y = pack_bf16x2(__uint_as_float(w[2]) * inv, __uint_as_float(w[3]) * inv);
+        o.z = pack_bf16x2(__uint_as_float(w[4]) * inv, __uint_as_float(w[5]) * inv);
+        o.w = pack_bf16x2(__uint_as_float(w[6]) * inv, __uint_as_float(w[7]) * inv);
+        *reinterpret_cast<uint4*>(d) = o;
+      };
+      // 72 real columns stored as 80: half 0 -> columns 0..47, half 1 -> 48..71 (72..79 are padding)
+      uint32_t w0[32];
+      tmem_ld_32x32(t_row + Cfg::kTmemO + half * 48, w0);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g8 = 0; g8 < 3; ++g8) store8(w0 + g8 * 8, dst + half * 48 + g8 * 8);
+      if (half == 0) {
+        store8(w0 + 24, dst + 24);
+        uint32_t w1[16];
+        tmem_ld_32x16(t_row + Cfg::kTmemO + 32, w1);
+        tmem_ld_wait();
+        store8(w1, dst + 32);
+        store8(w1 + 8, dst + 40);
+      }
+    }
+#ifdef ECADK_ATTN_TIMING
+    if (lane == 0 && (sw == 0 || sw == 12 || sw == 4)) {
+      dbg_acc[6] = clock() - t_begin;
+      dbg_acc[7] = nb;
+      for (int i = 0; i < 8; ++i) g_attn_dbg[blockIdx.x * 32 + (sw == 0 ? 8 : (sw == 12 ? 16 : 24)) + i] = dbg_acc[i];
+    }
+#endif
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 
 }  // namespace ecadk

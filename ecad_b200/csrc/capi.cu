@@ -711,6 +711,23 @@ int launch_attn_flash_inst(const CUtensorMap* tq, const CUtensorMap* tkv, const 
   return check_launch("attn_flash_kernel");
 }
 
+// second-generation streaming kernel (head dim 72): next Q K^T issued while the block's softmax runs
+template <bool HAS_BIAS>
+int launch_attn_flash2_inst(const CUtensorMap* tq, const CUtensorMap* tkv, const AttnParams& p, int n_keys, int items,
+                            cudaStream_t stream) {
+  using Cfg = AttnFlash2Cfg;
+  static bool configured = false;
+  auto kern = attn_flash2_kernel<HAS_BIAS>;
+  if (!configured) {
+    ECADK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int grid = items < num_sms() ? items : num_sms();
+  launch_pdl(kern, dim3(grid), dim3(kFlash2Threads), Cfg::kSmemBytes, stream, tq[0], tq[1], tkv[0], tkv[1], tkv[3], p,
+             n_keys, items);
+  return check_launch("attn_flash2_kernel");
+}
+
 // FLUX joint attention: head_dim 128 (no padding), no key bias; out row pitch given (the single-stream blocks write
 // straight into the [attn | mlp] concat buffer).
 int launch_attention_d128(const void* q, const void* k, const void* v, void* out, int out_ld, void* out_lo,
@@ -803,6 +820,18 @@ int launch_attention_ex(const void* q, int q_ld, const void* k, const void* v, i
     if ((rc = make_attn_tmap(&tkv[2], v, kv_ld, samples, heads, n_keys, kFlashKB, 64, 128))) return rc;
     if ((rc = make_attn_tmap(&tkv[3], v, kv_ld, samples, heads, n_keys, kFlashKB, 16, 32))) return rc;
     const int items = samples * heads * (q_tokens / 256);
+    // Long key sequences run the second-generation kernel (next Q K^T issued during the block's softmax): measured
+    // 1471 against 1638 us at 4096 keys, but 225 against 216 us at 1024 keys and 311 against 245 us at 384 keys, where
+    // its longer item prologue / epilogue shows (profiles/r2_attention_times_final.txt).  ECADK_ATTN_FLASH=1 / 2 force
+    // the first / second generation (A/B measurements).
+    static const int gen = [] {
+      const char* e = getenv("ECADK_ATTN_FLASH");
+      return e == nullptr ? 0 : atoi(e);
+    }();
+    if (gen == 2 || (gen != 1 && n_keys >= 2048)) {
+      return bias ? launch_attn_flash2_inst<true>(tq, tkv, p, n_keys, items, stream)
+                  : launch_attn_flash2_inst<false>(tq, tkv, p, n_keys, items, stream);
+    }
     return bias ? launch_attn_flash_inst<72, true>(tq, tkv, p, n_keys, items, stream)
                 : launch_attn_flash_inst<72, false>(tq, tkv, p, n_keys, items, stream);
   }

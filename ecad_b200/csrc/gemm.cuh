@@ -520,7 +520,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  // warp-uniform by construction; the shuffle lets ptxas know (see the MMA issuer)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int num_m = (p.M + kGemmBM - 1) / kGemmBM;
   const int num_n = p.N / BN;
@@ -547,15 +548,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   // programmatic dependent launch: the prologue above may have overlapped the previous kernel's tail; nothing below
   // touches global memory before that kernel has completed.  This grid is persistent (<= one CTA per SM), so the next
   // kernel's CTAs are released right away to set themselves up on the idle SMs.
   griddep_launch_dependents();
   griddep_wait();
 
+  // Both single-thread roles run as WHOLE warps with only the TMA / tcgen05 instructions predicated on an elected lane.
+  // Inside an `if (lane == 0)` branch ptxas cannot prove their operands warp-uniform and moves every one into a uniform
+  // register through an ELECT / R2UR.BROADCAST / BRA.U.ANY loop: 4-6 R2UR and ~100 clocks of the issuing thread per
+  // tcgen05.mma - harmless next to the 128-clock instructions of the 256-wide pair tiles, but three times the 32 clocks
+  // of the 64-wide MMAs of the batch-1 configuration (tools/micro/mma_issue_bench.cu).
   if (warp == 0) {
-    if (lane == 0) {
+    {
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
@@ -566,15 +572,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStage;
           uint8_t* sb = sa + Cfg::kStageA;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStage);
-          if (kb < p.kb_split) {
-            int a_col, a_row;
-            a_tile_coords(p, kb, m0, a_col, a_row);
-            tma_load_2d(sa, &tmap_a, &full_bar[stage], a_col, a_row);
-          } else {
-            tma_load_2d(sa, &tmap_a2, &full_bar[stage], (kb - p.kb_split) * kGemmBK, m0);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStage);
+            if (kb < p.kb_split) {
+              int a_col, a_row;
+              a_tile_coords(p, kb, m0, a_col, a_row);
+              tma_load_2d(sa, &tmap_a, &full_bar[stage], a_col, a_row);
+            } else {
+              tma_load_2d(sa, &tmap_a2, &full_bar[stage], (kb - p.kb_split) * kGemmBK, m0);
+            }
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kGemmBK, n0);
           }
-          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kGemmBK, n0);
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -583,7 +592,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // ===================== MMA issuer =====================
       constexpr uint32_t idesc = make_idesc_bf16(kGemmBM, BN);
       int stage = 0;
@@ -601,18 +610,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint32_t sb = sa + Cfg::kStageA;
           const uint64_t da = make_smem_desc(sa, 0, 1024, kLayoutSW128);
           const uint64_t db = make_smem_desc(sb, 0, 1024, kLayoutSW128);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kGemmBK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
-            umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < kGemmBK / 16; ++k) {
+              // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+              umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            }
+            umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs retire
+            if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);  // accumulator complete
           }
-          umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs retire
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -699,7 +711,8 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   uint64_t* tmem_full = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 4);
 
-  const int warp = threadIdx.x >> 5;
+  // warp-uniform by construction; the shuffle lets ptxas know (see the MMA issuer)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int S = static_cast<int>(cluster_nctarank());
   const int rank = static_cast<int>(cluster_ctarank());
@@ -727,7 +740,7 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   griddep_launch_dependents();  // programmatic dependent launch: see gemm_bf16_kernel
   griddep_wait();
 
@@ -737,8 +750,9 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   const int own0 = rank * kChunks / S, own1 = (rank + 1) * kChunks / S;  // column chunks owned by this CTA
   const int per = own1 - own0;
   float4* const ws_tile = ws + static_cast<size_t>(tile) * S * kChunks * 1024;
+  // (whole-warp roles with elected-lane TMA / tcgen05 instructions: see gemm_bf16_kernel)
   if (warp == 0) {
-    if (lane == 0) {
+    {
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
@@ -746,15 +760,18 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * Cfg::kStage;
         uint8_t* sb = sa + Cfg::kStageA;
-        mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStage);
-        if (kb < p.kb_split) {
-          int a_col, a_row;
-          a_tile_coords(p, kb, m0, a_col, a_row);
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], a_col, a_row);
-        } else {
-          tma_load_2d(sa, &tmap_a2, &full_bar[stage], (kb - p.kb_split) * kGemmBK, m0);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStage);
+          if (kb < p.kb_split) {
+            int a_col, a_row;
+            a_tile_coords(p, kb, m0, a_col, a_row);
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], a_col, a_row);
+          } else {
+            tma_load_2d(sa, &tmap_a2, &full_bar[stage], (kb - p.kb_split) * kGemmBK, m0);
+          }
+          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kGemmBK, n0);
         }
-        tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kGemmBK, n0);
+        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -762,7 +779,7 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // ===================== MMA issuer =====================
       constexpr uint32_t idesc = make_idesc_bf16(kGemmBM, BN);
       int stage = 0;
@@ -774,16 +791,19 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         const uint32_t sb = sa + Cfg::kStageA;
         const uint64_t da = make_smem_desc(sa, 0, 1024, kLayoutSW128);
         const uint64_t db = make_smem_desc(sb, 0, 1024, kLayoutSW128);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kGemmBK / 16; ++k)
-          umma_bf16_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb != kb_begin) || (k != 0));
-        umma_commit(&empty_bar[stage]);
+          for (int k = 0; k < kGemmBK / 16; ++k)
+            umma_bf16_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb != kb_begin) || (k != 0));
+          umma_commit(&empty_bar[stage]);
+          if (kb == kb_end - 1) umma_commit(&tmem_full[0]);  // this CTA's partial accumulator is complete
+        }
+        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
-      umma_commit(&tmem_full[0]);  // this CTA's partial accumulator is complete
     }
   } else {
     // ===================== partials out: the chunks owned by the other CTAs =====================
@@ -917,7 +937,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  // warp-uniform by construction; the shuffle lets ptxas know (see the MMA issuer)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t cta = cluster_ctarank();  // 0 = leader
   const int pair = blockIdx.x >> 1;
@@ -950,7 +971,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   tc_fence_before();
   cluster_sync();  // barriers of both CTAs initialised before any remote arrive / TMA credit
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   griddep_launch_dependents();  // see gemm_bf16_kernel
   griddep_wait();
 
