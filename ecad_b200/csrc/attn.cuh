@@ -1721,6 +1721,16 @@ attn_flash2_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_cons
           const int k_row = (p.kv_rowmajor ? smp : sh) * n_keys + j * kFlashKB;
           uint8_t* kd = smem + Cfg::kK + st * Cfg::kKStage;
           uint8_t* vd = smem + Cfg::kV + st * Cfg::kKStage;
+          if (j == (nkb > 2 ? nkb - 3 : 0) && item + static_cast<int>(gridDim.x) < num_items) {
+            // the next item's Q can only be LOADED once this item's last Q K^T has retired, with the MMA warps about to
+            // wait for it: bring it into L2 a few key blocks early so that the load is an L2 hit
+            const int item2 = item + gridDim.x;
+            const int sh2 = item2 / pairs, pr2 = item2 - sh2 * pairs;
+            const int smp2 = sh2 / p.heads, hd2 = sh2 - smp2 * p.heads;
+            const int q_row2 = (p.q_rowmajor ? smp2 : sh2) * p.q_tokens + pr2 * 256;
+            tma_prefetch_3d(&tm_q64, 0, p.q_rowmajor ? hd2 : 0, q_row2);
+            tma_prefetch_3d(&tm_q16, 64, p.q_rowmajor ? hd2 : 0, q_row2);
+          }
           mbar_wait(&k_empty[st], ph);
           mbar_arrive_expect_tx(&k_full[st], Cfg::kBytesKV);
           tma_load_3d(kd, &tm_k64, &k_full[st], 0, kv_mid, k_row);

@@ -890,6 +890,10 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 // Each CTA computes TWO 128-row sub-tiles there (rows m0 .. m0+255), which share the stage's W tiles: with one sub-tile
 // the narrow (C_out = 128) tile is bound by its W stream - 24 KB of W per 17 KB of A per 768 MMA clocks is the SM's L2
 // port (ncu: tensor pipe 55-66 %).  The two accumulators sit side by side in one 256-column TMEM buffer.
+#ifndef ECADK_GEMM2_UNIFORM
+#define ECADK_GEMM2_UNIFORM 1
+#endif
+constexpr bool kUniformRoles = ECADK_GEMM2_UNIFORM != 0;
 constexpr int kTap3Rows = kGemmBM + 8;
 constexpr int kTap3Sub = 2;
 template <int BN, int EPI = 0, bool TAP3 = false>
@@ -987,7 +991,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       // (measured: an L2 bulk prefetch of this tile's residual-stream block issued here does NOT help - out-projection
       // 197 -> 202 us, FF2 427 -> 488 us: the epilogue is not exposed-latency-bound and the prefetch competes with the
       // operand stream for L2)
-      if (lane == 0) {
+      // (kUniformRoles: whole-warp roles with elected-lane TMA / tcgen05 instructions, see gemm_bf16_kernel)
+      if (kUniformRoles || lane == 0) {
         const int n0 = n_idx * BN + cta * (bn_cur / 2);
         const CUtensorMap* tb = is_tail ? &tmap_b_tail : &tmap_b;
         const uint32_t stage_bytes =
@@ -996,6 +1001,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStage;
           uint8_t* sb = sa + Cfg::kStageA;
+          if (!kUniformRoles || elect_one()) {
           if (cta == 0) mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
           if constexpr (TAP3) {
             const int ky = kb / p.conv_cblocks, cb = kb - ky * p.conv_cblocks;
@@ -1015,6 +1021,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             tma_load_2d_2sm(sa, &tmap_a2, &full_bar[stage], (kb - p.kb_split) * kGemmBK, m0);
           }
           if constexpr (!TAP3) tma_load_2d_2sm(sb, tb, &full_bar[stage], kb * kGemmBK, n0);
+          }
+          if (kUniformRoles) __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -1024,7 +1032,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       __syncwarp();  // lanes 1..31 must not run ahead: the prefetch distance stays one tile
     }
   } else if (warp == 1) {
-    if (lane == 0 && cta == 0) {
+    if ((kUniformRoles || lane == 0) && cta == 0) {
       // ===================== MMA issuer (leader CTA only) =====================
       constexpr uint32_t idesc_full = make_idesc_bf16(2 * kGemmBM, BN);
       constexpr uint32_t idesc_tail = make_idesc_bf16(2 * kGemmBM, 128);
@@ -1042,6 +1050,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStage);
           const uint32_t sb = sa + Cfg::kStageA;
+          if (!kUniformRoles || elect_one()) {
           if constexpr (TAP3) {
 #pragma unroll
             for (int sub = 0; sub < Cfg::kSub; ++sub) {
@@ -1066,12 +1075,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             }
           }
           umma_commit_2sm(&empty_bar[stage], 0b11);
+          if (kb == num_kb - 1) umma_commit_2sm(&tmem_full[acc], 0b11);
+          }
+          if (kUniformRoles) __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_2sm(&tmem_full[acc], 0b11);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;

@@ -101,6 +101,13 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, ui
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// the same box brought into L2 only (no shared-memory destination, no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_3d(const void* tmap, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 // 2-D tile store shared -> global (bulk async group); c0 = innermost coordinate (elements)
 __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
