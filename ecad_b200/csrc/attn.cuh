@@ -787,7 +787,13 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
   uint64_t* o_full = bars + 16;    // [2]
   uint64_t* s_empty = bars + 18;   // [2]
   uint64_t* o_staged = bars + 20;  // [2] per query tile, one phase per item: the bf16 output tile is in shared memory
-  uint64_t* stage_free = bars + 22;  // one phase per STORE (tile 0 and tile 1 alternate): the store has read the staging
+  // [2] per query tile, one phase per item: the tile's store has read the staging tile.  ONE barrier with a phase per
+  // store (the tiles alternate) is ambiguous: a tile that tests "store k - 1 done" by parity also passes when store k - 2
+  // (its OWN previous store) is still pending - which happens when the bulk store queues behind an item's worth of
+  // strided operand gathers (row-major operands, 200 samples): tile 1 then staged too early and its rows received
+  // tile 0's output (tools/micro/determinism_stress.py: 11 % of the launches, and every launch once the MMA issue
+  // got faster).  With one barrier per tile the tested store is never more than one phase away.
+  uint64_t* stage_free = bars + 22;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   // (the shuffles tell ptxas that the values are warp-uniform - see the MMA issuer of attn_flash_kernel)
@@ -812,7 +818,8 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
       mbar_init(&s_empty[i], 8);
       mbar_init(&o_staged[i], 8);
     }
-    mbar_init(stage_free, 1);
+    mbar_init(&stage_free[0], 1);
+    mbar_init(&stage_free[1], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -982,7 +989,7 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
           tma_store_2d(&tm_o, smem + Cfg::kO, head * kHeadDim, sample * 256 + t * kAttnBM);
           tma_store_commit();
           tma_store_wait_read0();  // the staging tile has been read: the other query tile may overwrite it
-          mbar_arrive(stage_free);
+          mbar_arrive(&stage_free[t]);
         }
       }
       tma_store_wait_all0();
@@ -1103,8 +1110,9 @@ attn_pair2_kernel(const __grid_constant__ CUtensorMap tm_q64, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[t]);
       ATTN_T(s3a);
-      // the shared staging tile is free once store k - 1 has read it (k = 2 n + t; phase k - 1 has parity (t ^ 1))
-      mbar_wait(stage_free, t ^ 1);
+      // the shared staging tile is free once the OTHER tile's previous store has read it: tile 1 follows tile 0's store
+      // of this item, tile 0 follows tile 1's store of the previous item
+      mbar_wait(&stage_free[t ^ 1], t == 1 ? par : (par ^ 1));
       ATTN_T(s3b);
       const uint32_t srow = smem_u32(smem + Cfg::kO) + row * (kHeadDim * 2) + half * 96;
       auto stage8 = [&](const uint32_t* x, uint32_t addr) {
