@@ -58,8 +58,10 @@ def test_config2_batch100_matches_oracle_on_sampled_prompts_and_is_batch_invaria
             negative_prompt_embeds=part["negative_prompt_embeds"],
             negative_prompt_attention_mask=part["negative_prompt_attention_mask"], latents=noise[lo:lo + 4].clone(),
             num_inference_steps=flags.shape[0], callback=gen._call_callbacks_wrapper)[0].cpu()
+        # measured 0.0 (bit-identical) on the fixed build; up to 4.5e-4 over the staging race of attn_pair2_kernel that
+        # tests/test_gpu_determinism.py now pins, 3e-3 to 4e-3 once the faster MMA issue made it frequent
         rel = float((small - full[lo:lo + 4]).abs().max() / full.abs().max())
-        assert rel <= 2e-3 and _cos(small, full[lo:lo + 4]) >= 0.99999, (lo, rel)
+        assert rel <= 1e-4 and _cos(small, full[lo:lo + 4]) >= 0.99999, (lo, rel)
 
 
 def test_config5_flux_full_size_reuse_step_reproduces_dense_step(cuda_device):
