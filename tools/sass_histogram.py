@@ -5,7 +5,9 @@ tcgen05 / TMEM / TMA claim is checkable without rebuilding:
 
 Per kernel: instruction count and the counts of the mnemonics that prove a Blackwell-native kernel
 (UTCHMMA = tcgen05.mma kind::f16, UTMALDG/UTMASTG = TMA tensor load/store, UTMAPF = TMA prefetch, LDTM/STTM =
-tcgen05.ld/st, UTCBAR = tcgen05.commit, SYNCS = mbarrier, MUFU.EX2) and of the legacy tensor path (HMMA must be 0)."""
+tcgen05.ld/st, UTCBAR = tcgen05.commit, SYNCS = mbarrier, MUFU.EX2) and of the legacy tensor path (HMMA must be 0).
+R2UR / BRA.U.ANY: vector -> uniform register moves and the loops ptxas wraps around them when a tcgen05 / TMA instruction
+is issued from divergent code (session 4): 4-7 R2UR per UTCHMMA before, < 1 in the converted roles."""
 import collections
 import re
 import subprocess
@@ -17,7 +19,7 @@ lib = Path(sys.argv[1]) if len(sys.argv) > 1 else ROOT / "ecad_b200" / "libecad_
 sass = subprocess.run(["cuobjdump", "-sass", str(lib)], capture_output=True, text=True, check=True).stdout
 demangle = lambda n: subprocess.run(["c++filt", n], capture_output=True, text=True).stdout.strip() or n
 KEYS = ["UTCHMMA", "UTMALDG", "UTMASTG", "UTMAPF", "UBLKPF", "LDTM", "STTM", "UTCBAR", "SYNCS", "MUFU.EX2", "MUFU.TANH",
-        "HMMA", "LDG", "STG", "LDS", "STS", "FFMA2", "BAR"]
+        "HMMA", "LDG", "STG", "LDS", "STS", "FFMA2", "BAR", "R2UR", "BRA.U.ANY"]
 funcs: dict[str, collections.Counter] = {}
 cur = None
 for line in sass.splitlines():
